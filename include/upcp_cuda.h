@@ -1,0 +1,270 @@
+/*
+ * upcp_cuda.h -- C ABI of the B200-native per-tile labelling hot path.
+ *
+ * This is the boundary a maintainer of Amsterdam-AI-Team/Urban_PointCloud_Processing
+ * (`upcp`) binds to replace the third-party natives the reference calls on its hot
+ * path (numba-JIT point-in-polygon, numpy digitize, cccorelib/pycc connected
+ * components, open3d KD-tree / normals).  Each entry point cites the reference
+ * interface it replaces as `file:line` relative to the reference checkout.
+ *
+ * Conventions
+ *   - plain C, no torch / C++ types in any signature;
+ *   - every pointer named d_* is a DEVICE pointer (cudaMalloc / torch CUDA tensor
+ *     data_ptr), every pointer named h_* is a HOST pointer;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = default stream);
+ *   - scratch memory is CALLER-owned: `*_ws_bytes()` returns the size, the caller
+ *     passes a device buffer of at least that size (256-byte aligned);
+ *   - all functions return 0 (UPCP_OK) or a negative UPCP_E_* code, never throw;
+ *     `upcp_last_error()` returns a thread-local message for the last failure;
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point
+ *     returns UPCP_E_CUDA.
+ *   - point coordinates are fp64 structure-of-arrays (x[n], y[n], z[n]); labels are
+ *     int32; masks are one byte per point (0 / 1).
+ */
+#ifndef UPCP_CUDA_H
+#define UPCP_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define UPCP_OK            0
+#define UPCP_E_INVALID    -1   /* bad argument                                  */
+#define UPCP_E_CUDA       -2   /* CUDA runtime error / no device                */
+#define UPCP_E_WORKSPACE  -3   /* caller workspace too small                    */
+#define UPCP_E_CAPACITY   -4   /* an internal capacity (k, rings, ...) exceeded */
+#define UPCP_E_INTERNAL   -5   /* device-side invariant violated (flag raised)  */
+
+#define UPCP_ABI_VERSION   1
+
+/* ------------------------------------------------------------------ misc -- */
+int         upcp_abi_version(void);
+const char* upcp_last_error(void);
+/* Number of visible CUDA devices (0 when there is none); never fails. */
+int         upcp_device_count(void);
+/* Total number of kernel launches issued by this library in this process
+ * (used by bench.py for the `gpu_launches` figure). */
+int64_t     upcp_launch_count(void);
+
+/* ------------------------------------------------------- tile / layout ---- */
+/* Replaces: the implicit numpy layout of `points` (pipeline.py:124 delivers an
+ * F-ordered (N,3) float64 array; callers may also pass C-ordered).  Converts a
+ * C-ordered AoS (n, ncols) fp64 array into SoA columns.  ncols is 2 or 3; with
+ * ncols == 2, d_z is filled with 0.0 (label_connected_comp.py:61-62). */
+int upcp_points_aos_to_soa(const double* d_xyz, int64_t n, int ncols,
+                           double* d_x, double* d_y, double* d_z, void* stream);
+
+/* Bounding boxes in fp64.  d_out receives 13 doubles:
+ *   [0..5]  min x,y,z / max x,y,z over ALL n points
+ *   [6..11] min x,y,z / max x,y,z over points with d_sel[i] != 0 (all if d_sel NULL)
+ *   [12]    number of selected points (as double, exact below 2^53)
+ * Replaces: np.min/np.max in math_utils.py:21-33 (get_octree_level) and the
+ * cloud bounding box CCCoreLib computes in DgmOctree::updateMinAndMaxTables. */
+size_t upcp_bbox_ws_bytes(int64_t n);
+int upcp_bbox(const double* d_x, const double* d_y, const double* d_z, int64_t n,
+              const uint8_t* d_sel, double* d_out13,
+              void* d_ws, size_t ws_bytes, void* stream);
+
+/* Widen / narrow label arrays between the host dtype and the device int32. */
+int upcp_labels_widen_u8(const uint8_t* d_in, int64_t n, int32_t* d_out, void* stream);
+int upcp_labels_widen_u16(const uint16_t* d_in, int64_t n, int32_t* d_out, void* stream);
+int upcp_labels_narrow_u8(const int32_t* d_in, int64_t n, uint8_t* d_out, void* stream);
+int upcp_labels_narrow_u16(const int32_t* d_in, int64_t n, uint16_t* d_out, void* stream);
+
+/* out[i] = ((d_mask_in ? d_mask_in[i] != 0 : base) || labels[i] in eq[0..n_eq))
+ *          && labels[i] not in ne[0..n_ne)
+ * Replaces the numpy mask assembly of pipeline.py:90 (`labels == 0`),
+ * road_fuser.py:81, label_connected_comp.py:47-51,167-175, layer_lcc.py:118-122,
+ * region_growing.py:34-49.  n_eq, n_ne <= 8. */
+int upcp_mask_build(const int32_t* d_labels, int64_t n, const uint8_t* d_mask_in,
+                    int base, const int32_t* h_eq, int n_eq,
+                    const int32_t* h_ne, int n_ne, uint8_t* d_out, void* stream);
+
+/* op: 0 = a & b, 1 = a | b, 2 = a & ~b.  d_out may alias d_a. */
+int upcp_mask_combine(const uint8_t* d_a, const uint8_t* d_b, int64_t n, int op,
+                      uint8_t* d_out, void* stream);
+
+/* labels[i] = value where d_mask[i] != 0  (e.g. ahn_fuser.py:172). */
+int upcp_labels_assign(int32_t* d_labels, int64_t n, const uint8_t* d_mask,
+                       int32_t value, void* stream);
+
+/* *d_count (int64) = number of non-zero mask bytes. */
+int upcp_mask_count(const uint8_t* d_mask, int64_t n, int64_t* d_count, void* stream);
+
+/* Label histogram: d_hist[256] (int64) += count of each label value in [0,255];
+ * values outside go to bin 255.  Caller zeroes d_hist.
+ * Replaces np.unique(labels, return_counts=True) in analysis_tools.py:8-18. */
+int upcp_label_hist(const int32_t* d_labels, int64_t n, int64_t* d_hist256, void* stream);
+
+/* ----------------------------------------------- AHN raster (S1) ---------- */
+/* Raster = FastGridInterpolator state (interpolation.py:329-334):
+ *   d_bin_x[nx] ascending  (= grid_x - step_x/2)
+ *   d_bin_y[ny] descending (= grid_y + step_y/2)
+ *   d_values[ny*nx] fp64 row-major (NaN where AHN is empty).
+ * Cell lookup reproduces np.digitize(x, bin_x) - 1 and
+ * np.digitize(y, bin_y, right=True) - 1 including numpy's negative-index wrap
+ * (interpolation.py:346-348).
+ *
+ * upcp_raster_lookup: d_out[i] = values[y_idx, x_idx] for every i (or only where
+ * d_sel[i] != 0; other entries are left untouched). */
+int upcp_raster_lookup(const double* d_x, const double* d_y, int64_t n,
+                       const uint8_t* d_sel,
+                       const double* d_bin_x, int nx, const double* d_bin_y, int ny,
+                       const double* d_values, double* d_out, void* stream);
+
+/* Fused lookup + height-threshold classification.  v = raster value at the point.
+ *   UPCP_CLS_ABS_LT      : |z - v| < a                 (ahn_fuser.py:159, ground)
+ *   UPCP_CLS_LT          : z < v + a                   (ahn_fuser.py:170, building)
+ *   UPCP_CLS_CAP_LE      : !isfinite(v) || z <= v + a  (building_fuser.py:89-95)
+ *   UPCP_CLS_BAND_OC     : z > v + a && z <= v + b     (layer_lcc.py:72-74)
+ *   UPCP_CLS_BAND_CC     : z <= v + b && z >= v - a    (ahn_fuser.py:115-116)
+ *   UPCP_CLS_BELOW_NEG   : (z - v) < -a                (noise_filter.py:72)
+ * d_out[i] = (d_sel ? d_sel[i] != 0 : 1) && cond.  If d_labels != NULL the label
+ * `assign` is written where d_out[i] is set (fused `labels[label_mask] = label`).
+ * d_out may be NULL when d_labels is given. */
+#define UPCP_CLS_ABS_LT    0
+#define UPCP_CLS_LT        1
+#define UPCP_CLS_CAP_LE    2
+#define UPCP_CLS_BAND_OC   3
+#define UPCP_CLS_BAND_CC   4
+#define UPCP_CLS_BELOW_NEG 5
+int upcp_raster_classify(const double* d_x, const double* d_y, const double* d_z,
+                         int64_t n, const uint8_t* d_sel,
+                         const double* d_bin_x, int nx, const double* d_bin_y, int ny,
+                         const double* d_values, int mode, double a, double b,
+                         uint8_t* d_out, int32_t* d_labels, int32_t assign,
+                         void* stream);
+
+/* ------------------------------------------ BGT point-in-polygon (S2) ----- */
+/* Replaces clip_utils.poly_clip / is_inside / _point_inside_poly
+ * (clip_utils.py:119-238) OR-ed over polygons as building_fuser.py:83-87 and
+ * road_fuser.py:84-87 do.  Rings are closed (first vertex == last vertex),
+ * h_ring_xy is (total_vertices, 2) fp64 C-ordered, ring r uses vertices
+ * h_ring_off[r] .. h_ring_off[r+1]-1.  h_ring_poly[r] is the polygon id
+ * (non-decreasing), h_ring_hole[r] is 0 for the exterior ring (which must come
+ * first within its polygon) and 1 for an interior ring.
+ * Semantics per polygon: bbox-inclusive prefilter (clip_utils.py:22-40,219-236),
+ * crossing number with boundary == inside; interiors clear what the exterior set.
+ * The plan bins ring bounding boxes per uniform grid cell and ring edges per
+ * per-ring y-slab; it is built on the host (O(vertices)) and uploaded once. */
+typedef struct upcp_pip_plan upcp_pip_plan;
+int    upcp_pip_plan_create(const double* h_ring_xy, const int64_t* h_ring_off,
+                            const int32_t* h_ring_poly, const uint8_t* h_ring_hole,
+                            int32_t n_rings, int32_t grid_dim /* 0 = auto */,
+                            upcp_pip_plan** out);
+size_t upcp_pip_plan_bytes(const upcp_pip_plan* plan);
+/* Copies the plan blob into d_plan (cudaMemcpyAsync from the plan's host blob). */
+int    upcp_pip_plan_upload(const upcp_pip_plan* plan, void* d_plan, size_t bytes,
+                            void* stream);
+void   upcp_pip_plan_destroy(upcp_pip_plan* plan);
+/* d_out[i] = (d_sel ? d_sel[i] != 0 : 1) && point i inside the polygon set. */
+int    upcp_pip_query(const void* d_plan, const double* d_x, const double* d_y,
+                      int64_t n, const uint8_t* d_sel, uint8_t* d_out, void* stream);
+
+/* ------------------------------------ connected components (S3) ----------- */
+/* Octree parameters exactly as CCCoreLib derives them (float32 arithmetic):
+ * bbox of the float32 cloud -> CCMiscTools::MakeMinAndMaxCubical(enlarge 0.01)
+ * -> cell size at MAX_OCTREE_LEVEL.  Host-only helper, no device work.
+ *   h_bbox_sel6: fp64 min x,y,z / max x,y,z of the selected points
+ *   h_out4     : float32 dimMin x,y,z and the level-`max_level` cell size
+ * Replaces: the octree set-up inside
+ * cccorelib.AutoSegmentationTools.labelConnectedComponents
+ * (call site label_connected_comp.py:83-85). */
+int upcp_octree_params(const double* h_bbox_sel6, int max_level, float* h_out4);
+
+/* get_octree_level(points, grid_size) (math_utils.py:21-33), host helper working
+ * on the fp64 bbox of ALL points passed to the processor. */
+int upcp_octree_level(const double* h_bbox_all6, int ncols, double grid_size);
+
+/* Connected components of occupied octree cells at `level` under 26-connectivity
+ * for the selected points; per-point component ids.
+ *   d_comp[n] (int32): component id >= 0 for selected points whose component has
+ *       at least min_component_size points, -1 otherwise (also for unselected).
+ *       Ids are arbitrary but deterministic; compare after canonical relabelling.
+ *   d_info (int64[4]): [0] n selected, [1] n occupied cells, [2] n components
+ *       (before size filter), [3] n components kept.
+ * If d_labels != NULL the seed-fraction fill of _fill_components
+ * (label_connected_comp.py:99-135) is fused: d_fill[n] = 1 for points of kept
+ * components whose (double)seed_count / size > threshold, seeds being selected
+ * points with d_labels[i] == seed_label.
+ * Replaces: pycc.ccPointCloud + labelConnectedComponents + np.unique/np.in1d
+ * filter + _fill_components (label_connected_comp.py:53-135). */
+size_t upcp_lcc_ws_bytes(int64_t n, int64_t n_selected_upper, int level);
+int upcp_lcc(const double* d_x, const double* d_y, const double* d_z, int64_t n,
+             const uint8_t* d_sel, const float* h_octree4, int level, int max_level,
+             int32_t min_component_size,
+             const int32_t* d_labels, int32_t seed_label, double threshold,
+             int32_t* d_comp, uint8_t* d_fill, int64_t* d_info,
+             void* d_ws, size_t ws_bytes, void* stream);
+
+/* ------------------------- neighbour search + normals + growth (S4/S5) ---- */
+/* Exact k-nearest-neighbour graph + hybrid-search normals + curvature seed test
+ * over the selected points, in one pass over a uniform-grid cell list.
+ *   m            : number of selected points (ids below are "compact ids" in
+ *                  ascending original-index order, i.e. position within
+ *                  np.where(sel)[0] -- the index space region_growing.py uses);
+ *   knn          : grow_region_knn (neighbours returned per point, query first);
+ *   max_nn, radius : KDTreeSearchParamHybrid of estimate_normals;
+ *   ordering     : ascending (squared distance, compact id) -- squared distance
+ *                  is ((dx*dx + dy*dy) + dz*dz) in fp64 without FMA;
+ *   d_knn[m*knn] : int32 compact ids (-1 padding when m < knn);
+ *   d_normals[m*3] fp64, Open3D FastEigen3x3 of the cumulant covariance,
+ *                  (0,0,1) when fewer than 3 neighbours / zero normal;
+ *   d_cov[m*6]   : optional (may be NULL) covariance xx,xy,xz,yy,yz,zz of the knn
+ *                  neighbourhood (compute_mean_and_covariance, region_growing.py:69-71);
+ *   d_curv[m*3]  : optional analytic eigenvalue ratios eval_i / sum (ascending eval).
+ * Replaces: o3d.geometry.KDTreeFlann + search_knn_vector_3d + estimate_normals +
+ * compute_mean_and_covariance (region_growing.py:59-73,86-92,105-109). */
+size_t upcp_knn_ws_bytes(int64_t n, int64_t m, int kmax);
+int upcp_knn_normals(const double* d_x, const double* d_y, const double* d_z, int64_t n,
+                     const uint8_t* d_sel, int64_t m, const double* h_bbox_sel6,
+                     int knn, int max_nn, double radius, double cell_size,
+                     int32_t* d_knn, double* d_knn_d2 /* may be NULL */,
+                     double* d_normals, double* d_cov, double* d_curv,
+                     void* d_ws, size_t ws_bytes, void* stream);
+
+/* Region growing to the least fixpoint (region_growing.py:75-141, method='knn').
+ *   d_seed[m]     : 1 for initial seeds (points already carrying the label);
+ *   d_can_seed[m] : 1 if an accepted point becomes a seed (curvature <
+ *                   threshold_curve, region_growing.py:128-134);
+ *   accept p from seed s iff p in knn(s)[1:] and
+ *       degrees(acos(clip(dot(n_s/|n_s|, n_p/|n_p|), -1, 1))) < threshold_angle
+ *       (math_utils.py:9-18);
+ *   d_region[m]   : output, 1 for every point of the grown region (seeds included).
+ *   d_info (int64[2]) : [0] region size, [1] number of seeds processed. */
+size_t upcp_region_grow_ws_bytes(int64_t m);
+int upcp_region_grow(const int32_t* d_knn, int knn, const double* d_normals,
+                     const uint8_t* d_seed, const uint8_t* d_can_seed, int64_t m,
+                     double threshold_angle_deg, uint8_t* d_region, int64_t* d_info,
+                     void* d_ws, size_t ws_bytes, void* stream);
+
+/* Scatter a compact per-selected-point mask back to the full tile:
+ * d_out[i] = d_compact[rank(i)] for selected i, 0 otherwise
+ * (region_growing.py:139, `label_mask[mask_indices[region]] = True`). */
+size_t upcp_compact_ws_bytes(int64_t n);
+int upcp_mask_scatter(const uint8_t* d_sel, int64_t n, const uint8_t* d_compact,
+                      uint8_t* d_out, void* d_ws, size_t ws_bytes, void* stream);
+/* Gather: d_compact[rank(i)] = d_full[i] for selected i; *d_count = m. */
+int upcp_mask_gather(const uint8_t* d_sel, int64_t n, const uint8_t* d_full,
+                     uint8_t* d_compact, int64_t* d_count,
+                     void* d_ws, size_t ws_bytes, void* stream);
+
+/* ------------------------------------------------ primitives (exposed) ---- */
+/* LSD radix sort of (key, value) pairs, the "Morton/voxel-key radix sort" of the
+ * hot path; exposed for tests and benchmarks.  Sorts bits [0, end_bit).
+ * Result is written to d_keys_out / d_vals_out (inputs are clobbered). */
+size_t upcp_sort_ws_bytes(int64_t n);
+int upcp_sort_pairs_u32(uint32_t* d_keys_in, uint32_t* d_vals_in,
+                        uint32_t* d_keys_out, uint32_t* d_vals_out, int64_t n,
+                        int end_bit, void* d_ws, size_t ws_bytes, void* stream);
+int upcp_sort_pairs_u64(uint64_t* d_keys_in, uint32_t* d_vals_in,
+                        uint64_t* d_keys_out, uint32_t* d_vals_out, int64_t n,
+                        int end_bit, void* d_ws, size_t ws_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* UPCP_CUDA_H */

@@ -1,0 +1,612 @@
+// S4 -- exact k-nearest-neighbour graph + hybrid-search normals + curvature
+// covariance over a uniform-grid cell list (RegionGrowing set-up).
+//
+// Restates what the reference obtains from Open3D (region_growing.py:59-73,86-92,
+// 105-109): KDTreeFlann.search_knn_vector_3d(p, k) for every point, estimate_normals
+// with KDTreeSearchParamHybrid(radius, max_nn) and compute_mean_and_covariance of the
+// k-neighbourhood.  Neighbour ordering is ascending (squared distance, compact id)
+// with the squared distance computed as ((dx*dx + dy*dy) + dz*dz) in fp64, no FMA
+// [ext, unverified -- see oracle/].
+//
+// Data structure (all in HBM, built per call):
+//   * selected points get a Morton key of their uniform-grid cell (cell size c);
+//     (key, compact id) pairs are radix-sorted; coordinates are gathered into sorted
+//     SoA arrays so that every cell is a contiguous, coalesced run;
+//   * unique cells + first-point offsets (cell list) and an open-addressing hash table
+//     cell key -> cell index (4 B slots, L2-resident);
+//   * query groups: <= 32 consecutive sorted points of one 4x4x4-cell super-cell.
+// Search: one warp per query group, one lane per query.  The warp walks the cells of the
+// group's bounding box ring by ring; each lane looks up one cell (hash), cells whose
+// distance to the group exceeds every lane's current k-th distance are pruned, the
+// points of the surviving cells are staged through shared memory with coalesced loads
+// and every lane tests every staged point (conflict-free broadcast reads).  Each lane
+// keeps its k best in a shared-memory max-heap; a lane is finished when its k-th
+// distance is smaller than its distance to the unexplored region.  The epilogue sorts
+// the heap, writes the kNN row, and accumulates the Open3D cumulant covariances /
+// FastEigen3x3 normal straight from the sorted list, so the 30-neighbour lists never
+// touch HBM.
+#include <math.h>
+#include "common.cuh"
+#include "primitives.cuh"
+#include "upcp_math.cuh"
+
+namespace upcp {
+
+constexpr int kBlock = 256;
+constexpr int kSearchWarps = 4;
+constexpr int kSearchThreads = kSearchWarps * 32;
+constexpr uint32_t kEmpty = 0xffffffffu;
+
+struct GridParams {
+    double ox, oy, oz, cell, inv_cell, slack;
+    int nx, ny, nz;
+};
+
+__device__ __forceinline__ uint64_t expand_bits21(uint32_t v) {
+    uint64_t x = v & 0x1fffffu;
+    x = (x | x << 32) & 0x1f00000000ffffULL;
+    x = (x | x << 16) & 0x1f0000ff0000ffULL;
+    x = (x | x << 8) & 0x100f00f00f00f00fULL;
+    x = (x | x << 4) & 0x10c30c30c30c30c3ULL;
+    x = (x | x << 2) & 0x1249249249249249ULL;
+    return x;
+}
+__device__ __forceinline__ uint32_t compact_bits21(uint64_t x) {
+    x &= 0x1249249249249249ULL;
+    x = (x ^ (x >> 2)) & 0x10c30c30c30c30c3ULL;
+    x = (x ^ (x >> 4)) & 0x100f00f00f00f00fULL;
+    x = (x ^ (x >> 8)) & 0x1f0000ff0000ffULL;
+    x = (x ^ (x >> 16)) & 0x1f00000000ffffULL;
+    x = (x ^ (x >> 32)) & 0x1fffffULL;
+    return (uint32_t)x;
+}
+__device__ __forceinline__ uint64_t morton3(int cx, int cy, int cz) {
+    return expand_bits21((uint32_t)cx) | (expand_bits21((uint32_t)cy) << 1) | (expand_bits21((uint32_t)cz) << 2);
+}
+__device__ __forceinline__ uint64_t hash64(uint64_t k) {
+    k ^= k >> 33; k *= 0xff51afd7ed558ccdULL; k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ULL; k ^= k >> 33;
+    return k;
+}
+__device__ __forceinline__ int cell_coord(double v, double origin, double inv_cell, int n) {
+    double t = (v - origin) * inv_cell;
+    if (!(t > 0.0)) return 0;
+    if (t >= (double)n) return n - 1;
+    return (int)floor(t);
+}
+
+struct KnnCompactIdx {
+    uint32_t* sel_idx;
+    __device__ void operator()(int64_t i, bool selected, uint32_t rank) const {
+        if (selected) sel_idx[rank] = (uint32_t)i;
+    }
+};
+
+template <typename K>
+__global__ void __launch_bounds__(kBlock)
+knn_keys_kernel(const double* __restrict__ x, const double* __restrict__ y,
+                const double* __restrict__ z, const uint32_t* __restrict__ sel_idx, int64_t m,
+                GridParams g, K* __restrict__ keys, uint32_t* __restrict__ vals) {
+    int64_t stride = (int64_t)gridDim.x * kBlock;
+    for (int64_t j = (int64_t)blockIdx.x * kBlock + threadIdx.x; j < m; j += stride) {
+        int64_t i = sel_idx ? (int64_t)sel_idx[j] : j;
+        int cx = cell_coord(x[i], g.ox, g.inv_cell, g.nx);
+        int cy = cell_coord(y[i], g.oy, g.inv_cell, g.ny);
+        int cz = cell_coord(z[i], g.oz, g.inv_cell, g.nz);
+        keys[j] = (K)morton3(cx, cy, cz);
+        vals[j] = (uint32_t)j;
+    }
+}
+
+__global__ void __launch_bounds__(kBlock)
+knn_gather_kernel(const double* __restrict__ x, const double* __restrict__ y,
+                  const double* __restrict__ z, const uint32_t* __restrict__ sel_idx,
+                  const uint32_t* __restrict__ perm, int64_t m,
+                  double* __restrict__ sx, double* __restrict__ sy, double* __restrict__ sz) {
+    int64_t stride = (int64_t)gridDim.x * kBlock;
+    for (int64_t s = (int64_t)blockIdx.x * kBlock + threadIdx.x; s < m; s += stride) {
+        uint32_t j = perm[s];
+        int64_t i = sel_idx ? (int64_t)sel_idx[j] : (int64_t)j;
+        sx[s] = x[i]; sy[s] = y[i]; sz[s] = z[i];
+    }
+}
+
+// flags[s] = 1 where the key (shifted right by `shift`) differs from its predecessor
+template <typename K>
+__global__ void __launch_bounds__(kBlock)
+knn_boundary_flags_kernel(const K* __restrict__ keys, int64_t m, int shift, uint8_t* __restrict__ flags) {
+    int64_t stride = (int64_t)gridDim.x * kBlock;
+    for (int64_t s = (int64_t)blockIdx.x * kBlock + threadIdx.x; s < m; s += stride)
+        flags[s] = (s == 0 || (keys[s] >> shift) != (keys[s - 1] >> shift)) ? 1 : 0;
+}
+
+template <typename K>
+struct KnnCellFunctor {
+    const K* keys;
+    uint64_t* ucell;
+    uint32_t* cell_first;
+    __device__ void operator()(int64_t s, bool is_first, uint32_t rank) const {
+        if (is_first) { ucell[rank] = (uint64_t)keys[s]; cell_first[rank] = (uint32_t)s; }
+    }
+};
+
+struct KnnSuperFunctor {     // super-cell run starts + super-cell index per sorted position
+    uint32_t* sc_first;
+    uint32_t* sc_of;
+    __device__ void operator()(int64_t s, bool is_first, uint32_t rank) const {
+        if (is_first) sc_first[rank] = (uint32_t)s;
+        sc_of[s] = rank + (is_first ? 1u : 0u) - 1u;
+    }
+};
+
+__global__ void __launch_bounds__(kBlock)
+knn_group_flags_kernel(const uint32_t* __restrict__ sc_first, const uint32_t* __restrict__ sc_of,
+                       int64_t m, uint8_t* __restrict__ flags) {
+    int64_t stride = (int64_t)gridDim.x * kBlock;
+    for (int64_t s = (int64_t)blockIdx.x * kBlock + threadIdx.x; s < m; s += stride)
+        flags[s] = (((uint32_t)s - sc_first[sc_of[s]]) & 31u) == 0 ? 1 : 0;
+}
+
+struct KnnGroupFunctor {
+    uint32_t* group_start;
+    __device__ void operator()(int64_t s, bool is_first, uint32_t rank) const {
+        if (is_first) group_start[rank] = (uint32_t)s;
+    }
+};
+
+__global__ void knn_finish_kernel(const uint32_t* __restrict__ n_cells, uint32_t* __restrict__ cell_first,
+                                  const uint32_t* __restrict__ n_groups, uint32_t* __restrict__ group_start,
+                                  uint32_t m) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) { cell_first[*n_cells] = m; group_start[*n_groups] = m; }
+}
+
+__global__ void __launch_bounds__(kBlock)
+knn_hash_insert_kernel(const uint64_t* __restrict__ ucell, const uint32_t* __restrict__ n_cells,
+                       uint32_t* __restrict__ table, uint32_t table_mask) {
+    const uint32_t c_total = *n_cells;
+    uint32_t stride = gridDim.x * kBlock;
+    for (uint32_t c = blockIdx.x * kBlock + threadIdx.x; c < c_total; c += stride) {
+        uint32_t h = (uint32_t)hash64(ucell[c]) & table_mask;
+        while (atomicCAS(&table[h], kEmpty, c) != kEmpty) h = (h + 1) & table_mask;
+    }
+}
+
+__device__ __forceinline__ uint32_t hash_lookup(const uint64_t* __restrict__ ucell,
+                                                const uint32_t* __restrict__ table,
+                                                uint32_t table_mask, uint64_t key) {
+    uint32_t h = (uint32_t)hash64(key) & table_mask;
+    while (true) {
+        uint32_t idx = __ldg(table + h);
+        if (idx == kEmpty) return kEmpty;
+        if (__ldg(ucell + idx) == key) return idx;
+        h = (h + 1) & table_mask;
+    }
+}
+
+// ------------------------------------------------------------------ search ------
+struct SearchArgs {
+    const double* sx; const double* sy; const double* sz;   // sorted coordinates
+    const uint32_t* perm;          // sorted position -> compact id
+    const uint64_t* ucell; const uint32_t* cell_first;
+    const uint32_t* table; uint32_t table_mask;
+    const uint32_t* group_start; const uint32_t* n_groups;
+    GridParams g;
+    int64_t m;
+    int k_heap;                    // max(knn, max_nn) clipped to m
+    int knn, max_nn;
+    double radius2;
+    int32_t* out_knn; double* out_d2; double* out_normals; double* out_cov; double* out_curv;
+};
+
+template <int KMAX>
+struct LaneHeap {
+    // max-heap over (d2, compact id); storage [slot][lane] in shared memory
+    double* d2; uint32_t* pos; const uint32_t* perm; int lane; int cnt;
+    __device__ __forceinline__ double& D(int i) { return d2[i * 32 + lane]; }
+    __device__ __forceinline__ uint32_t& P(int i) { return pos[i * 32 + lane]; }
+    // (da, pa) ranks after (db, pb) in ascending (d2, compact id) order
+    __device__ __forceinline__ bool after(double da, uint32_t pa, double db, uint32_t pb) const {
+        if (da != db) return da > db;
+        return __ldg(perm + pa) > __ldg(perm + pb);
+    }
+    __device__ __forceinline__ void sift_down(int i, int n, double vd, uint32_t vp) {
+        while (true) {
+            int c = 2 * i + 1;
+            if (c >= n) break;
+            double cd = D(c); uint32_t cp = P(c);
+            if (c + 1 < n) {
+                double rd = D(c + 1); uint32_t rp = P(c + 1);
+                if (after(rd, rp, cd, cp)) { c = c + 1; cd = rd; cp = rp; }
+            }
+            if (!after(cd, cp, vd, vp)) break;
+            D(i) = cd; P(i) = cp;
+            i = c;
+        }
+        D(i) = vd; P(i) = vp;
+    }
+    __device__ __forceinline__ void push(double vd, uint32_t vp) {   // cnt < capacity
+        int i = cnt++;
+        while (i > 0) {
+            int p = (i - 1) >> 1;
+            double pd = D(p); uint32_t pp = P(p);
+            if (!after(vd, vp, pd, pp)) break;
+            D(i) = pd; P(i) = pp;
+            i = p;
+        }
+        D(i) = vd; P(i) = vp;
+    }
+    __device__ __forceinline__ void sort_ascending() {
+        for (int end = cnt - 1; end > 0; --end) {
+            double vd = D(end); uint32_t vp = P(end);
+            D(end) = D(0); P(end) = P(0);
+            sift_down(0, end, vd, vp);
+        }
+    }
+};
+
+template <int KMAX>
+__global__ void __launch_bounds__(kSearchThreads)
+knn_search_kernel(SearchArgs a) {
+    // dynamic shared memory: [warps][KMAX*32] fp64 heap keys | [warps][KMAX*32] u32 heap
+    // payloads | [warps][3][32] fp64 staged candidate coordinates
+    extern __shared__ __align__(16) unsigned char knn_smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double* const w_heap_d2 = reinterpret_cast<double*>(knn_smem) + (size_t)warp * KMAX * 32;
+    uint32_t* const w_heap_pos = reinterpret_cast<uint32_t*>(knn_smem + (size_t)kSearchWarps * KMAX * 32 * 8) + (size_t)warp * KMAX * 32;
+    double* const w_cand = reinterpret_cast<double*>(knn_smem + (size_t)kSearchWarps * KMAX * 32 * 12) + (size_t)warp * 96;
+    double* const c_x = w_cand; double* const c_y = w_cand + 32; double* const c_z = w_cand + 64;
+
+    const GridParams g = a.g;
+    const uint32_t n_groups = *a.n_groups;
+    const int K = a.k_heap;
+    const double inf = __longlong_as_double(0x7ff0000000000000LL);
+
+    for (uint32_t grp = blockIdx.x * kSearchWarps + warp; grp < n_groups; grp += gridDim.x * kSearchWarps) {
+        const uint32_t gs = a.group_start[grp];
+        const int gcount = (int)(a.group_start[grp + 1] - gs);
+        const bool valid = lane < gcount;
+        const uint32_t qpos = gs + (valid ? lane : 0);
+        const double qx = a.sx[qpos], qy = a.sy[qpos], qz = a.sz[qpos];
+        const int icx = cell_coord(qx, g.ox, g.inv_cell, g.nx);
+        const int icy = cell_coord(qy, g.oy, g.inv_cell, g.ny);
+        const int icz = cell_coord(qz, g.oz, g.inv_cell, g.nz);
+        // group bounding box in cells and in world coordinates (lane 0 is always valid and
+        // invalid lanes alias it, so plain warp reductions are exact)
+        int lox = icx, loy = icy, loz = icz, hix = icx, hiy = icy, hiz = icz;
+        double bminx = qx, bminy = qy, bminz = qz, bmaxx = qx, bmaxy = qy, bmaxz = qz;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lox = min(lox, __shfl_xor_sync(0xffffffffu, lox, o)); hix = max(hix, __shfl_xor_sync(0xffffffffu, hix, o));
+            loy = min(loy, __shfl_xor_sync(0xffffffffu, loy, o)); hiy = max(hiy, __shfl_xor_sync(0xffffffffu, hiy, o));
+            loz = min(loz, __shfl_xor_sync(0xffffffffu, loz, o)); hiz = max(hiz, __shfl_xor_sync(0xffffffffu, hiz, o));
+            bminx = fmin(bminx, __shfl_xor_sync(0xffffffffu, bminx, o)); bmaxx = fmax(bmaxx, __shfl_xor_sync(0xffffffffu, bmaxx, o));
+            bminy = fmin(bminy, __shfl_xor_sync(0xffffffffu, bminy, o)); bmaxy = fmax(bmaxy, __shfl_xor_sync(0xffffffffu, bmaxy, o));
+            bminz = fmin(bminz, __shfl_xor_sync(0xffffffffu, bminz, o)); bmaxz = fmax(bmaxz, __shfl_xor_sync(0xffffffffu, bmaxz, o));
+        }
+
+        LaneHeap<KMAX> heap;
+        heap.d2 = w_heap_d2; heap.pos = w_heap_pos; heap.perm = a.perm; heap.lane = lane; heap.cnt = 0;
+        bool done = !valid;
+        double worst = inf;         // k-th best squared distance once the heap is full
+
+        for (int r = 0;; ++r) {
+            const int bx0 = max(lox - r, 0), bx1 = min(hix + r, g.nx - 1);
+            const int by0 = max(loy - r, 0), by1 = min(hiy + r, g.ny - 1);
+            const int bz0 = max(loz - r, 0), bz1 = min(hiz + r, g.nz - 1);
+            const int wx = bx1 - bx0 + 1, wy = by1 - by0 + 1, wz = bz1 - bz0 + 1;
+            const int total = wx * wy * wz;
+            // prune bound: the largest k-th distance among unfinished lanes
+            double wmax = done ? 0.0 : worst;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) wmax = fmax(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
+
+            for (int t0 = 0; t0 < total; t0 += 32) {
+                const int t = t0 + lane;
+                uint32_t c_first = 0, c_cnt = 0;
+                if (t < total) {
+                    const int cx = bx0 + t % wx, cy = by0 + (t / wx) % wy, cz = bz0 + t / (wx * wy);
+                    const bool inner = r > 0 && cx >= lox - (r - 1) && cx <= hix + (r - 1) &&
+                                       cy >= loy - (r - 1) && cy <= hiy + (r - 1) &&
+                                       cz >= loz - (r - 1) && cz <= hiz + (r - 1);
+                    if (!inner) {
+                        // conservative squared distance between the cell and the group's queries
+                        double gx = fmax(0.0, fmax(g.ox + cx * g.cell - bmaxx, bminx - (g.ox + (cx + 1) * g.cell)) - g.slack);
+                        double gy = fmax(0.0, fmax(g.oy + cy * g.cell - bmaxy, bminy - (g.oy + (cy + 1) * g.cell)) - g.slack);
+                        double gz = fmax(0.0, fmax(g.oz + cz * g.cell - bmaxz, bminz - (g.oz + (cz + 1) * g.cell)) - g.slack);
+                        double lb = (gx * gx + gy * gy + gz * gz) * (1.0 - 1e-9);
+                        if (!(lb > wmax)) {
+                            uint32_t idx = hash_lookup(a.ucell, a.table, a.table_mask, morton3(cx, cy, cz));
+                            if (idx != kEmpty) {
+                                c_first = __ldg(a.cell_first + idx);
+                                c_cnt = __ldg(a.cell_first + idx + 1) - c_first;
+                            }
+                        }
+                    }
+                }
+                uint32_t have = __ballot_sync(0xffffffffu, c_cnt > 0);
+                while (have) {
+                    const int src = __ffs(have) - 1;
+                    have &= have - 1;
+                    const uint32_t first = __shfl_sync(0xffffffffu, c_first, src);
+                    const uint32_t cnt = __shfl_sync(0xffffffffu, c_cnt, src);
+                    for (uint32_t j0 = 0; j0 < cnt; j0 += 32) {
+                        const uint32_t p = first + j0 + lane;
+                        if (j0 + lane < cnt) {
+                            c_x[lane] = a.sx[p]; c_y[lane] = a.sy[p]; c_z[lane] = a.sz[p];
+                        }
+                        __syncwarp();
+                        const int nc = (int)min(32u, cnt - j0);
+                        if (!done) {
+                            for (int c = 0; c < nc; ++c) {
+                                const double d2 = dist2(c_x[c], c_y[c], c_z[c], qx, qy, qz);
+                                const uint32_t cp = first + j0 + c;
+                                if (heap.cnt < K) {
+                                    heap.push(d2, cp);
+                                    if (heap.cnt == K) worst = heap.D(0);
+                                } else if (d2 <= worst) {
+                                    if (heap.after(heap.D(0), heap.P(0), d2, cp)) {
+                                        heap.sift_down(0, K, d2, cp);
+                                        worst = heap.D(0);
+                                    }
+                                }
+                            }
+                        }
+                        __syncwarp();
+                    }
+                }
+            }
+            // --- termination: distance from the query to the unexplored region
+            const bool open_x0 = lox - r > 0, open_x1 = hix + r < g.nx - 1;
+            const bool open_y0 = loy - r > 0, open_y1 = hiy + r < g.ny - 1;
+            const bool open_z0 = loz - r > 0, open_z1 = hiz + r < g.nz - 1;
+            if (!done) {
+                double reach = inf;
+                if (open_x0) reach = fmin(reach, qx - (g.ox + (lox - r) * g.cell));
+                if (open_x1) reach = fmin(reach, (g.ox + (hix + r + 1) * g.cell) - qx);
+                if (open_y0) reach = fmin(reach, qy - (g.oy + (loy - r) * g.cell));
+                if (open_y1) reach = fmin(reach, (g.oy + (hiy + r + 1) * g.cell) - qy);
+                if (open_z0) reach = fmin(reach, qz - (g.oz + (loz - r) * g.cell));
+                if (open_z1) reach = fmin(reach, (g.oz + (hiz + r + 1) * g.cell) - qz);
+                reach -= g.slack;
+                if (reach == inf) done = true;                      // whole grid explored
+                else if (heap.cnt == K && reach > 0.0 && worst < reach * reach * (1.0 - 1e-9)) done = true;
+            }
+            if (__all_sync(0xffffffffu, done)) break;
+            if (!(open_x0 || open_x1 || open_y0 || open_y1 || open_z0 || open_z1)) break;
+        }
+
+        // --- epilogue: sort, write the kNN row, covariance / normal from the sorted list
+        if (valid) {
+            heap.sort_ascending();
+            const int cnt = heap.cnt;
+            const uint32_t cid = a.perm[qpos];
+            if (a.out_knn) {
+                for (int j = 0; j < a.knn; ++j)
+                    a.out_knn[(size_t)cid * a.knn + j] = j < cnt ? (int32_t)__ldg(a.perm + heap.P(j)) : -1;
+            }
+            if (a.out_d2) {
+                for (int j = 0; j < a.knn; ++j)
+                    a.out_d2[(size_t)cid * a.knn + j] = j < cnt ? heap.D(j) : inf;
+            }
+            if (a.out_normals) {
+                // KDTreeSearchParamHybrid: the max_nn nearest, of those the ones with d2 < r^2
+                Cumulants cum; cum.clear();
+                int nn = 0;
+                const int lim = cnt < a.max_nn ? cnt : a.max_nn;
+                for (int j = 0; j < lim; ++j) {
+                    if (!(heap.D(j) < a.radius2)) break;
+                    const uint32_t p = heap.P(j);
+                    cum.add(a.sx[p], a.sy[p], a.sz[p]);
+                    ++nn;
+                }
+                Vec3 nrm = {0.0, 0.0, 1.0};
+                if (nn >= 3) {
+                    double cov6[6];
+                    cum.finish(nn, cov6);
+                    nrm = normal_from_cov(cov6, nullptr);
+                }
+                a.out_normals[(size_t)cid * 3 + 0] = nrm.x;
+                a.out_normals[(size_t)cid * 3 + 1] = nrm.y;
+                a.out_normals[(size_t)cid * 3 + 2] = nrm.z;
+            }
+            if (a.out_cov || a.out_curv) {
+                // compute_mean_and_covariance of the k-neighbourhood (region_growing.py:69-71)
+                Cumulants cum; cum.clear();
+                const int kk = cnt < a.knn ? cnt : a.knn;
+                for (int j = 0; j < kk; ++j) {
+                    const uint32_t p = heap.P(j);
+                    cum.add(a.sx[p], a.sy[p], a.sz[p]);
+                }
+                double cov6[6];
+                cum.finish(kk > 0 ? kk : 1, cov6);
+                if (a.out_cov)
+                    for (int q = 0; q < 6; ++q) a.out_cov[(size_t)cid * 6 + q] = cov6[q];
+                if (a.out_curv) {
+                    double ev[3];
+                    fast_eigen3x3(cov6, ev);
+                    double sum = ev[0] + ev[1] + ev[2];
+                    for (int q = 0; q < 3; ++q) a.out_curv[(size_t)cid * 3 + q] = ev[q] / sum;
+                }
+            }
+        }
+        __syncwarp();
+    }
+}
+
+static inline int bits_for(int n) { int b = 0; while ((1 << b) < n) ++b; return b; }
+static inline size_t hash_capacity(int64_t cells) { size_t cap = 1024; while (cap < 2 * (size_t)cells) cap <<= 1; return cap; }
+template <int KMAX> constexpr size_t search_smem_bytes() { return (size_t)kSearchWarps * KMAX * 32 * 12 + (size_t)kSearchWarps * 96 * 8; }
+
+template <typename K>
+static int knn_impl(const double* d_x, const double* d_y, const double* d_z, int64_t n,
+                    const uint8_t* d_sel, int64_t m, GridParams g, int key_bits,
+                    int knn, int max_nn, double radius,
+                    int32_t* d_knn, double* d_knn_d2, double* d_normals, double* d_cov, double* d_curv,
+                    void* d_ws, size_t ws_bytes, cudaStream_t st) {
+    Workspace ws(d_ws, ws_bytes);
+    uint32_t* counters = ws.take<uint32_t>(64);          // [0] m, [1] n_cells, [2] n_super, [3] n_groups
+    uint32_t* sel_idx = d_sel ? ws.take<uint32_t>((size_t)n) : nullptr;
+    uint32_t* prim_ws = ws.take<uint32_t>(compact_ws_words(n) + sort_ws_words(m));
+    K* keys_a = ws.take<K>((size_t)m);
+    K* keys_b = ws.take<K>((size_t)m);
+    uint32_t* vals_a = ws.take<uint32_t>((size_t)m);
+    uint32_t* vals_b = ws.take<uint32_t>((size_t)m);
+    double* sx = ws.take<double>((size_t)m);
+    double* sy = ws.take<double>((size_t)m);
+    double* sz = ws.take<double>((size_t)m);
+    uint8_t* flags = ws.take<uint8_t>((size_t)m);
+    uint64_t* ucell = ws.take<uint64_t>((size_t)m);
+    uint32_t* cell_first = ws.take<uint32_t>((size_t)m + 1);
+    uint32_t* sc_first = ws.take<uint32_t>((size_t)m);
+    uint32_t* sc_of = ws.take<uint32_t>((size_t)m);
+    uint32_t* group_start = ws.take<uint32_t>((size_t)m + 1);
+    uint32_t* table = ws.take<uint32_t>(hash_capacity(m));
+    if (!ws.ok) UPCP_FAIL(UPCP_E_WORKSPACE, "knn: workspace too small");
+
+    if (d_sel) {
+        KnnCompactIdx f{sel_idx};
+        UPCP_TRY(compact_apply(d_sel, n, counters, prim_ws, st, f));
+        uint32_t hm = 0;
+        UPCP_CUDA_OK(cudaMemcpyAsync(&hm, counters, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        UPCP_CUDA_OK(cudaStreamSynchronize(st));
+        if ((int64_t)hm != m) UPCP_FAIL(UPCP_E_INVALID, "knn: m does not match the number of selected points");
+    } else if (m != n) {
+        UPCP_FAIL(UPCP_E_INVALID, "knn: m must equal n when no selection is given");
+    }
+
+    const int grid_m = grid_for(m, kBlock);
+    knn_keys_kernel<K><<<grid_m, kBlock, 0, st>>>(d_x, d_y, d_z, sel_idx, m, g, keys_a, vals_a);
+    UPCP_LAUNCH_OK();
+    bool in_b = false;
+    if (sizeof(K) == 4)
+        UPCP_TRY(radix_sort_pairs_u32((uint32_t*)keys_a, vals_a, (uint32_t*)keys_b, vals_b, m, key_bits, prim_ws, st, &in_b));
+    else
+        UPCP_TRY(radix_sort_pairs_u64((uint64_t*)keys_a, vals_a, (uint64_t*)keys_b, vals_b, m, key_bits, prim_ws, st, &in_b));
+    K* keys = in_b ? keys_b : keys_a;
+    uint32_t* perm = in_b ? vals_b : vals_a;
+    knn_gather_kernel<<<grid_m, kBlock, 0, st>>>(d_x, d_y, d_z, sel_idx, perm, m, sx, sy, sz);
+    UPCP_LAUNCH_OK();
+
+    // cell list
+    uint32_t* n_cells = counters + 1;
+    knn_boundary_flags_kernel<K><<<grid_m, kBlock, 0, st>>>(keys, m, 0, flags);
+    UPCP_LAUNCH_OK();
+    {
+        KnnCellFunctor<K> f{keys, ucell, cell_first};
+        UPCP_TRY(compact_apply(flags, m, n_cells, prim_ws, st, f));
+    }
+    // super-cells (4x4x4 cells = low 6 Morton bits) and query groups
+    uint32_t* n_super = counters + 2;
+    uint32_t* n_groups = counters + 3;
+    knn_boundary_flags_kernel<K><<<grid_m, kBlock, 0, st>>>(keys, m, 6, flags);
+    UPCP_LAUNCH_OK();
+    {
+        KnnSuperFunctor f{sc_first, sc_of};
+        UPCP_TRY(compact_apply(flags, m, n_super, prim_ws, st, f));
+    }
+    knn_group_flags_kernel<<<grid_m, kBlock, 0, st>>>(sc_first, sc_of, m, flags);
+    UPCP_LAUNCH_OK();
+    {
+        KnnGroupFunctor f{group_start};
+        UPCP_TRY(compact_apply(flags, m, n_groups, prim_ws, st, f));
+    }
+    knn_finish_kernel<<<1, 32, 0, st>>>(n_cells, cell_first, n_groups, group_start, (uint32_t)m);
+    UPCP_LAUNCH_OK();
+
+    // hash table sized from the actual number of cells (one small D2H)
+    uint32_t h_counts[4] = {0, 0, 0, 0};
+    UPCP_CUDA_OK(cudaMemcpyAsync(h_counts, counters, sizeof(h_counts), cudaMemcpyDeviceToHost, st));
+    UPCP_CUDA_OK(cudaStreamSynchronize(st));
+    const uint32_t c_total = h_counts[1];
+    uint32_t cap = 1024;
+    while (cap < 2u * c_total) cap <<= 1;
+    UPCP_CUDA_OK(cudaMemsetAsync(table, 0xff, (size_t)cap * 4, st));
+    knn_hash_insert_kernel<<<grid_for(c_total, kBlock), kBlock, 0, st>>>(ucell, n_cells, table, cap - 1);
+    UPCP_LAUNCH_OK();
+
+    SearchArgs a;
+    a.sx = sx; a.sy = sy; a.sz = sz; a.perm = perm; a.ucell = ucell; a.cell_first = cell_first;
+    a.table = table; a.table_mask = cap - 1; a.group_start = group_start; a.n_groups = n_groups;
+    a.g = g; a.m = m;
+    int kh = knn > max_nn ? knn : max_nn;
+    if ((int64_t)kh > m) kh = (int)m;
+    a.k_heap = kh; a.knn = knn; a.max_nn = max_nn; a.radius2 = radius * radius;
+    a.out_knn = d_knn; a.out_d2 = d_knn_d2; a.out_normals = d_normals; a.out_cov = d_cov; a.out_curv = d_curv;
+    const uint32_t g_total = h_counts[3];
+    int blocks = (int)((g_total + kSearchWarps - 1) / kSearchWarps);
+    int cap_blocks = num_sms() * 32;
+    if (blocks > cap_blocks) blocks = cap_blocks;
+    if (blocks < 1) blocks = 1;
+    if (kh <= 16) {
+        UPCP_CUDA_OK(cudaFuncSetAttribute(knn_search_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)search_smem_bytes<16>()));
+        knn_search_kernel<16><<<blocks, kSearchThreads, search_smem_bytes<16>(), st>>>(a);
+    } else {
+        UPCP_CUDA_OK(cudaFuncSetAttribute(knn_search_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)search_smem_bytes<32>()));
+        knn_search_kernel<32><<<blocks, kSearchThreads, search_smem_bytes<32>(), st>>>(a);
+    }
+    UPCP_LAUNCH_OK();
+    return UPCP_OK;
+}
+
+}  // namespace upcp
+
+using namespace upcp;
+
+extern "C" {
+
+size_t upcp_knn_ws_bytes(int64_t n, int64_t m, int kmax) {
+    (void)kmax;
+    if (n < 1) n = 1;
+    if (m < 1 || m > n) m = n;
+    size_t bytes = align_up(64 * 4);
+    bytes += align_up((size_t)n * 4);
+    bytes += align_up((compact_ws_words(n) + sort_ws_words(m)) * 4);
+    bytes += 2 * align_up((size_t)m * 8) + 2 * align_up((size_t)m * 4);     // keys, vals
+    bytes += 3 * align_up((size_t)m * 8);                                   // sorted coords
+    bytes += align_up((size_t)m);                                           // flags
+    bytes += align_up((size_t)m * 8);                                       // ucell
+    bytes += 2 * align_up(((size_t)m + 1) * 4);                             // cell_first, group_start
+    bytes += 2 * align_up((size_t)m * 4);                                   // sc_first, sc_of
+    { size_t cap = 1024; while (cap < 2 * (size_t)m) cap <<= 1; bytes += align_up(cap * 4); }  // hash table
+    return bytes + 4096;
+}
+
+int upcp_knn_normals(const double* d_x, const double* d_y, const double* d_z, int64_t n,
+                     const uint8_t* d_sel, int64_t m, const double* h_bbox_sel6,
+                     int knn, int max_nn, double radius, double cell_size,
+                     int32_t* d_knn, double* d_knn_d2, double* d_normals, double* d_cov, double* d_curv,
+                     void* d_ws, size_t ws_bytes, void* stream) {
+    if (n < 0 || m < 0 || m > n || !h_bbox_sel6) UPCP_FAIL(UPCP_E_INVALID, "knn: bad argument");
+    if (knn < 1 || max_nn < 0) UPCP_FAIL(UPCP_E_INVALID, "knn: knn >= 1 and max_nn >= 0 required");
+    if (knn > 32 || max_nn > 32) UPCP_FAIL(UPCP_E_CAPACITY, "knn: knn and max_nn are limited to 32");
+    if (!(cell_size > 0.0) || !(radius >= 0.0)) UPCP_FAIL(UPCP_E_INVALID, "knn: cell_size > 0 and radius >= 0 required");
+    if (n >= ((int64_t)1 << 31)) UPCP_FAIL(UPCP_E_CAPACITY, "knn: n must be < 2^31");
+    if (m == 0) return UPCP_OK;
+    GridParams g;
+    g.ox = h_bbox_sel6[0]; g.oy = h_bbox_sel6[1]; g.oz = h_bbox_sel6[2];
+    double ex = h_bbox_sel6[3] - g.ox, ey = h_bbox_sel6[4] - g.oy, ez = h_bbox_sel6[5] - g.oz;
+    if (!(ex >= 0) || !(ey >= 0) || !(ez >= 0) || !isfinite(ex + ey + ez))
+        UPCP_FAIL(UPCP_E_INVALID, "knn: bounding box is not finite");
+    // keep every axis within 2^20 cells (Morton keys of 3 x 21 bits)
+    double emax = fmax(ex, fmax(ey, ez));
+    double cell = cell_size;
+    if (emax / cell > 1000000.0) cell = emax / 1000000.0;
+    g.cell = cell; g.inv_cell = 1.0 / cell;
+    // ... and the whole grid within 2^30 cells so that box enumeration stays in int32
+    while ((floor(ex / cell) + 1) * (floor(ey / cell) + 1) * (floor(ez / cell) + 1) > 1073741824.0) cell *= 2.0;
+    g.cell = cell; g.inv_cell = 1.0 / cell;
+    g.nx = (int)floor(ex / cell) + 1; g.ny = (int)floor(ey / cell) + 1; g.nz = (int)floor(ez / cell) + 1;
+    double amax = fmax(fmax(fabs(g.ox), fabs(h_bbox_sel6[3])), fmax(fmax(fabs(g.oy), fabs(h_bbox_sel6[4])),
+                                                                     fmax(fabs(g.oz), fabs(h_bbox_sel6[5]))));
+    g.slack = cell * 1e-6 + amax * 1e-12;
+    int bits = bits_for(g.nx > g.ny ? (g.nx > g.nz ? g.nx : g.nz) : (g.ny > g.nz ? g.ny : g.nz));
+    if (bits < 2) bits = 2;
+    int key_bits = 3 * bits;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (key_bits <= 32)
+        return knn_impl<uint32_t>(d_x, d_y, d_z, n, d_sel, m, g, key_bits, knn, max_nn, radius, d_knn,
+                                  d_knn_d2, d_normals, d_cov, d_curv, d_ws, ws_bytes, st);
+    return knn_impl<uint64_t>(d_x, d_y, d_z, n, d_sel, m, g, key_bits, knn, max_nn, radius, d_knn,
+                              d_knn_d2, d_normals, d_cov, d_curv, d_ws, ws_bytes, st);
+}
+
+}  // extern "C"

@@ -1,0 +1,242 @@
+// S5 -- facade region growing as frontier expansion over the kNN graph, plus the
+// compact <-> full index-space mask helpers.
+//
+// Restates RegionGrowing._region_growing(method='knn') (region_growing.py:75-141).
+// Acceptance of a neighbour depends only on the two normals and on membership of the
+// seed's kNN row; seed-hood of an accepted point depends only on its own neighbourhood
+// (`d_can_seed`); `processed` is set only on acceptance.  The result is therefore the
+// least fixpoint of
+//     region  = S0  u  { p : exists seed s, p in knn(s)[1:], angle(n_s, n_p) < thr }
+//     seeds   = S0  u  { p in region : can_seed[p] }
+// and is independent of the expansion order, so the Python `while` loop over a growing
+// list maps onto an asynchronous device-wide work queue:
+//   one persistent kernel, grid sized to be fully co-resident; a warp pops one seed
+//   (ticket from an atomic head counter), its lanes test the k-1 neighbours, claim
+//   accepted points with an atomic exchange and push new seeds (atomic tail counter).
+//   `pending` counts pushed-but-unfinished seeds; a waiting warp leaves when it is 0.
+// No launch per BFS level, no host round trip until the fixpoint is reached.
+#include <math.h>
+#include "common.cuh"
+#include "primitives.cuh"
+#include "upcp_math.cuh"
+
+namespace upcp {
+
+constexpr int kBlock = 256;
+constexpr int kGrowThreads = 256;
+
+struct GrowCounters {      // device-resident, 64-bit aligned
+    unsigned int head;
+    unsigned int tail;
+    int pending;
+    unsigned int error;
+    unsigned long long region_size;
+};
+
+__global__ void __launch_bounds__(kBlock)
+grow_init_kernel(const uint8_t* __restrict__ seed, int64_t m, int32_t* __restrict__ state,
+                 int32_t* __restrict__ queue, GrowCounters* __restrict__ ctr) {
+    int64_t stride = (int64_t)gridDim.x * kBlock;
+    for (int64_t i0 = (int64_t)blockIdx.x * kBlock; i0 < m; i0 += stride) {
+        int64_t i = i0 + threadIdx.x;
+        bool s = i < m && seed[i] != 0;
+        if (i < m) state[i] = s ? 1 : 0;
+        // warp-aggregated queue reservation
+        uint32_t bal = __ballot_sync(0xffffffffu, s);
+        if (bal) {
+            int lane = threadIdx.x & 31;
+            int leader = __ffs(bal) - 1;
+            unsigned int base = 0;
+            if (lane == leader) {
+                base = atomicAdd(&ctr->tail, (unsigned int)__popc(bal));
+                atomicAdd(&ctr->pending, __popc(bal));
+            }
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (s) queue[base + __popc(bal & ((1u << lane) - 1u))] = (int32_t)i;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kGrowThreads)
+grow_kernel(const int32_t* __restrict__ knn, int k, const double* __restrict__ normals,
+            const uint8_t* __restrict__ can_seed, int64_t m, double threshold_deg,
+            int32_t* __restrict__ state, int32_t* __restrict__ queue, GrowCounters* __restrict__ ctr) {
+    const int lane = threadIdx.x & 31;
+    volatile int32_t* vqueue = queue;
+    volatile int* vpending = &ctr->pending;
+    while (true) {
+        unsigned int t = 0;
+        if (lane == 0) t = atomicAdd(&ctr->head, 1u);
+        t = __shfl_sync(0xffffffffu, t, 0);
+        if ((int64_t)t >= m) return;                 // at most m seeds can ever be queued
+        // wait for ticket t to be published, or for global quiescence
+        int32_t s = -1;
+        if (lane == 0) {
+            unsigned int spins = 0;
+            while (true) {
+                s = vqueue[t];
+                if (s >= 0) break;
+                if (*vpending <= 0) { s = -2; break; }
+                __nanosleep(64);
+                if (++spins > (1u << 26)) { atomicExch(&ctr->error, 1u); s = -2; break; }   // safety valve
+            }
+        }
+        s = __shfl_sync(0xffffffffu, s, 0);
+        if (s < 0) return;
+
+        const Vec3 ns = {normals[(size_t)s * 3], normals[(size_t)s * 3 + 1], normals[(size_t)s * 3 + 2]};
+        // neighbour_idx[1:k] (region_growing.py:112): the first returned index is dropped
+        for (int j0 = 1; j0 < k; j0 += 32) {
+            const int j = j0 + lane;
+            bool push = false;
+            int32_t nb = -1;
+            if (j < k) {
+                nb = knn[(size_t)s * k + j];
+                if (nb >= 0 && __ldcg(state + nb) == 0) {
+                    const Vec3 nn = {normals[(size_t)nb * 3], normals[(size_t)nb * 3 + 1], normals[(size_t)nb * 3 + 2]};
+                    if (vector_angle_deg(ns, nn) < threshold_deg) {
+                        if (atomicExch(&state[nb], 1) == 0) push = can_seed[nb] != 0;
+                    }
+                }
+            }
+            uint32_t bal = __ballot_sync(0xffffffffu, push);
+            if (bal) {
+                int leader = __ffs(bal) - 1;
+                unsigned int base = 0;
+                if (lane == leader) {
+                    atomicAdd(&ctr->pending, __popc(bal));           // before the slots become visible
+                    base = atomicAdd(&ctr->tail, (unsigned int)__popc(bal));
+                }
+                base = __shfl_sync(0xffffffffu, base, leader);
+                if (push) vqueue[base + __popc(bal & ((1u << lane) - 1u))] = nb;
+            }
+        }
+        __syncwarp();
+        if (lane == 0) { __threadfence(); atomicSub(&ctr->pending, 1); }
+    }
+}
+
+__global__ void __launch_bounds__(kBlock)
+grow_finish_kernel(const int32_t* __restrict__ state, int64_t m, uint8_t* __restrict__ region,
+                   GrowCounters* __restrict__ ctr) {
+    int64_t stride = (int64_t)gridDim.x * kBlock;
+    unsigned long long cnt = 0;
+    for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < m; i += stride) {
+        uint8_t r = state[i] != 0;
+        region[i] = r;
+        cnt += r;
+    }
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(&ctr->region_size, cnt);
+}
+
+__global__ void grow_info_kernel(const GrowCounters* __restrict__ ctr, long long* __restrict__ info) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        info[0] = (long long)ctr->region_size;
+        info[1] = (long long)ctr->tail;
+    }
+}
+
+// ------------------------------------------------------ compact <-> full masks --
+struct ScatterFunctor {
+    const uint8_t* compact; uint8_t* out;
+    __device__ void operator()(int64_t i, bool selected, uint32_t rank) const {
+        out[i] = selected ? compact[rank] : (uint8_t)0;
+    }
+};
+struct GatherFunctor {
+    const uint8_t* full; uint8_t* compact;
+    __device__ void operator()(int64_t i, bool selected, uint32_t rank) const {
+        if (selected) compact[rank] = full[i];
+    }
+};
+__global__ void widen_count_kernel(const uint32_t* __restrict__ c, long long* __restrict__ out) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) *out = (long long)*c;
+}
+
+}  // namespace upcp
+
+using namespace upcp;
+
+extern "C" {
+
+size_t upcp_region_grow_ws_bytes(int64_t m) {
+    if (m < 1) m = 1;
+    return align_up(256) + 2 * align_up((size_t)m * 4) + 4096;
+}
+
+int upcp_region_grow(const int32_t* d_knn, int knn, const double* d_normals,
+                     const uint8_t* d_seed, const uint8_t* d_can_seed, int64_t m,
+                     double threshold_angle_deg, uint8_t* d_region, int64_t* d_info,
+                     void* d_ws, size_t ws_bytes, void* stream) {
+    if (m < 0 || knn < 1) UPCP_FAIL(UPCP_E_INVALID, "region_grow: bad argument");
+    if (m >= ((int64_t)1 << 31)) UPCP_FAIL(UPCP_E_CAPACITY, "region_grow: m must be < 2^31");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (d_info) UPCP_CUDA_OK(cudaMemsetAsync(d_info, 0, 2 * sizeof(int64_t), st));
+    if (m == 0) return UPCP_OK;
+    Workspace ws(d_ws, ws_bytes);
+    GrowCounters* ctr = (GrowCounters*)ws.take<char>(256);
+    int32_t* state = ws.take<int32_t>((size_t)m);
+    int32_t* queue = ws.take<int32_t>((size_t)m);
+    if (!ws.ok) UPCP_FAIL(UPCP_E_WORKSPACE, "region_grow: workspace too small");
+    UPCP_CUDA_OK(cudaMemsetAsync(ctr, 0, 256, st));
+    UPCP_CUDA_OK(cudaMemsetAsync(queue, 0xff, (size_t)m * 4, st));
+    grow_init_kernel<<<grid_for(m, kBlock), kBlock, 0, st>>>(d_seed, m, state, queue, ctr);
+    UPCP_LAUNCH_OK();
+    // persistent kernel: every CTA must be resident (waiting warps spin on the queue)
+    int per_sm = 0;
+    UPCP_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, grow_kernel, kGrowThreads, 0));
+    if (per_sm < 1) UPCP_FAIL(UPCP_E_CUDA, "region_grow: kernel cannot be resident");
+    if (per_sm > 4) per_sm = 4;
+    int grid = num_sms() * per_sm;
+    int64_t need = (m + (kGrowThreads / 32) - 1) / (kGrowThreads / 32);
+    if (need < grid) grid = (int)(need < 1 ? 1 : need);
+    grow_kernel<<<grid, kGrowThreads, 0, st>>>(d_knn, knn, d_normals, d_can_seed, m, threshold_angle_deg,
+                                               state, queue, ctr);
+    UPCP_LAUNCH_OK();
+    grow_finish_kernel<<<grid_for(m, kBlock), kBlock, 0, st>>>(state, m, d_region, ctr);
+    UPCP_LAUNCH_OK();
+    if (d_info) {
+        grow_info_kernel<<<1, 32, 0, st>>>(ctr, (long long*)d_info);
+        UPCP_LAUNCH_OK();
+    }
+    // surface the safety valve (a spin that never resolved) as an error
+    unsigned int h_err = 0;
+    UPCP_CUDA_OK(cudaMemcpyAsync(&h_err, &ctr->error, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
+    UPCP_CUDA_OK(cudaStreamSynchronize(st));
+    if (h_err) UPCP_FAIL(UPCP_E_INTERNAL, "region_grow: work queue did not quiesce");
+    return UPCP_OK;
+}
+
+size_t upcp_compact_ws_bytes(int64_t n) { return (compact_ws_words(n < 1 ? 1 : n) + 64) * 4; }
+
+int upcp_mask_scatter(const uint8_t* d_sel, int64_t n, const uint8_t* d_compact, uint8_t* d_out,
+                      void* d_ws, size_t ws_bytes, void* stream) {
+    if (n < 0 || !d_sel) UPCP_FAIL(UPCP_E_INVALID, "mask_scatter: bad argument");
+    if (n == 0) return UPCP_OK;
+    if (!d_ws || ws_bytes < upcp_compact_ws_bytes(n)) UPCP_FAIL(UPCP_E_WORKSPACE, "mask_scatter: workspace too small");
+    uint32_t* w = (uint32_t*)d_ws;
+    ScatterFunctor f{d_compact, d_out};
+    return compact_apply(d_sel, n, w, w + 64, (cudaStream_t)stream, f);
+}
+
+int upcp_mask_gather(const uint8_t* d_sel, int64_t n, const uint8_t* d_full, uint8_t* d_compact,
+                     int64_t* d_count, void* d_ws, size_t ws_bytes, void* stream) {
+    if (n < 0 || !d_sel) UPCP_FAIL(UPCP_E_INVALID, "mask_gather: bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n == 0) {
+        if (d_count) UPCP_CUDA_OK(cudaMemsetAsync(d_count, 0, sizeof(int64_t), st));
+        return UPCP_OK;
+    }
+    if (!d_ws || ws_bytes < upcp_compact_ws_bytes(n)) UPCP_FAIL(UPCP_E_WORKSPACE, "mask_gather: workspace too small");
+    uint32_t* w = (uint32_t*)d_ws;
+    GatherFunctor f{d_full, d_compact};
+    UPCP_TRY(compact_apply(d_sel, n, w, w + 64, st, f));
+    if (d_count) {
+        widen_count_kernel<<<1, 32, 0, st>>>(w, (long long*)d_count);
+        UPCP_LAUNCH_OK();
+    }
+    return UPCP_OK;
+}
+
+}  // extern "C"

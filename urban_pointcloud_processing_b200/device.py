@@ -1,0 +1,386 @@
+"""Device-resident tile state shared by the drop-in processors.
+
+PyTorch is used here only as plumbing: device memory (``torch.empty``), the
+current CUDA stream and host<->device copies.  All arithmetic is done by the
+hand-written kernels behind the C ABI (``_lib``).
+
+HBM layout of one tile (N points):
+    x, y, z    fp64 [N] each (structure of arrays; 24 B/pt)
+    labels     int32 [N]
+    masks      uint8 [N] (0 / 1), allocated per processor call
+    rasters    fp64 [ny, nx] + bin edges (2 MB per 500x500 AHN surface, L2-resident)
+    PIP plans  one blob per polygon set (KBs .. a few MB, L2-resident)
+"""
+import ctypes
+import warnings
+import weakref
+
+import numpy as np
+import torch
+
+from . import _lib
+
+
+def stream_ptr():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def ptr(t):
+    """Device pointer of a torch tensor (or NULL)."""
+    if t is None:
+        return None
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def _from_numpy(a):
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')          # read-only numpy arrays
+        return torch.from_numpy(a)
+
+
+class Workspace:
+    """Grow-only scratch buffer handed to the C ABI (caller-owned workspace)."""
+
+    def __init__(self, device):
+        self.device = device
+        self.buf = None
+
+    def get(self, nbytes):
+        nbytes = int(nbytes)
+        if self.buf is None or self.buf.numel() < nbytes:
+            self.buf = None
+            self.buf = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=self.device)
+        return self.buf
+
+
+_workspaces = {}
+
+
+def workspace(device, slot=0):
+    key = (str(device), slot)
+    ws = _workspaces.get(key)
+    if ws is None:
+        ws = _workspaces[key] = Workspace(device)
+    return ws
+
+
+def current_device():
+    _lib.require_cuda()
+    return torch.device('cuda', torch.cuda.current_device())
+
+
+# --------------------------------------------------------------------- masks --
+def upload_mask(mask, n, device):
+    """numpy bool[n] (or None) -> uint8 cuda tensor (or None)."""
+    if mask is None:
+        return None
+    if isinstance(mask, torch.Tensor):
+        return mask
+    m = np.ascontiguousarray(np.asarray(mask, dtype=bool))
+    if m.shape != (n,):
+        raise ValueError(f'mask has shape {m.shape}, expected ({n},)')
+    return _from_numpy(m.view(np.uint8)).to(device, non_blocking=True)
+
+
+def download_mask(d_mask):
+    return d_mask.cpu().numpy().view(bool)
+
+
+def mask_build(d_labels, d_mask_in=None, base=False, eq=(), ne=()):
+    """out = ((mask_in or base) | labels in eq) & labels not in ne  (see upcp_mask_build)."""
+    lib = _lib.load()
+    n = d_labels.numel()
+    out = torch.empty(n, dtype=torch.uint8, device=d_labels.device)
+    eq = [int(v) for v in eq]
+    ne = [int(v) for v in ne]
+    if len(eq) > 8 or len(ne) > 8:
+        raise ValueError('at most 8 labels per set')
+    eq_arr = (ctypes.c_int32 * 8)(*eq)
+    ne_arr = (ctypes.c_int32 * 8)(*ne)
+    _lib.check(lib.upcp_mask_build(ptr(d_labels), n, ptr(d_mask_in), int(bool(base)), eq_arr, len(eq),
+                                   ne_arr, len(ne), ptr(out), stream_ptr()), 'upcp_mask_build')
+    return out
+
+
+def mask_combine(d_a, d_b, op, out=None):
+    """op: 'and' | 'or' | 'andnot'."""
+    lib = _lib.load()
+    code = {'and': 0, 'or': 1, 'andnot': 2}[op]
+    if out is None:
+        out = torch.empty_like(d_a)
+    _lib.check(lib.upcp_mask_combine(ptr(d_a), ptr(d_b), d_a.numel(), code, ptr(out), stream_ptr()),
+               'upcp_mask_combine')
+    return out
+
+
+def mask_count(d_mask):
+    """Number of set entries (synchronises)."""
+    lib = _lib.load()
+    cnt = torch.empty(1, dtype=torch.int64, device=d_mask.device)
+    _lib.check(lib.upcp_mask_count(ptr(d_mask), d_mask.numel(), ptr(cnt), stream_ptr()), 'upcp_mask_count')
+    return int(cnt.item())
+
+
+def labels_assign(d_labels, d_mask, value):
+    lib = _lib.load()
+    _lib.check(lib.upcp_labels_assign(ptr(d_labels), d_labels.numel(), ptr(d_mask), int(value), stream_ptr()),
+               'upcp_labels_assign')
+
+
+def label_hist(d_labels):
+    """int64[256] histogram of label values (device tensor)."""
+    lib = _lib.load()
+    hist = torch.zeros(256, dtype=torch.int64, device=d_labels.device)
+    _lib.check(lib.upcp_label_hist(ptr(d_labels), d_labels.numel(), ptr(hist), stream_ptr()), 'upcp_label_hist')
+    return hist
+
+
+# -------------------------------------------------------------------- labels --
+def upload_labels(labels, device):
+    """Host integer labels -> int32 cuda tensor (widened on the device for u8/u16)."""
+    lib = _lib.load()
+    if isinstance(labels, torch.Tensor):
+        return labels
+    a = np.asarray(labels)
+    n = a.shape[0]
+    out = torch.empty(n, dtype=torch.int32, device=device)
+    if n == 0:
+        return out
+    if a.dtype == np.uint8 and a.flags.c_contiguous:
+        raw = _from_numpy(a).to(device, non_blocking=True)
+        _lib.check(lib.upcp_labels_widen_u8(ptr(raw), n, ptr(out), stream_ptr()), 'upcp_labels_widen_u8')
+    elif a.dtype == np.uint16 and a.flags.c_contiguous:
+        raw = _from_numpy(a.view(np.int16)).to(device, non_blocking=True)
+        _lib.check(lib.upcp_labels_widen_u16(ptr(raw), n, ptr(out), stream_ptr()), 'upcp_labels_widen_u16')
+    else:
+        out.copy_(_from_numpy(np.ascontiguousarray(a.astype(np.int32))), non_blocking=True)
+    return out
+
+
+def download_labels(d_labels, labels):
+    """Write the device labels back INTO the host array `labels` (in-place contract)."""
+    lib = _lib.load()
+    n = d_labels.numel()
+    if n == 0:
+        return labels
+    if labels.dtype == np.uint8 and labels.flags.c_contiguous and labels.flags.writeable:
+        nar = torch.empty(n, dtype=torch.uint8, device=d_labels.device)
+        _lib.check(lib.upcp_labels_narrow_u8(ptr(d_labels), n, ptr(nar), stream_ptr()), 'upcp_labels_narrow_u8')
+        _from_numpy(labels).copy_(nar)
+    elif labels.dtype == np.uint16 and labels.flags.c_contiguous and labels.flags.writeable:
+        nar = torch.empty(n, dtype=torch.int16, device=d_labels.device)
+        _lib.check(lib.upcp_labels_narrow_u16(ptr(d_labels), n, ptr(nar), stream_ptr()), 'upcp_labels_narrow_u16')
+        _from_numpy(labels.view(np.int16)).copy_(nar)
+    else:
+        labels[...] = d_labels.cpu().numpy().astype(labels.dtype)
+    return labels
+
+
+# ---------------------------------------------------------------------- tile --
+class DeviceTile:
+    """One point-cloud tile resident in HBM as fp64 structure-of-arrays.
+
+    Accepts the ``points`` argument of the reference plugin contract
+    (abstract_processor.py:23-43): float64 ``(N, 3)`` (or ``(N, 2)``), C- or
+    F-ordered (pipeline.py:124 delivers F-order).  Never mutates it.
+    """
+
+    def __init__(self, points, device=None):
+        lib = _lib.require_cuda()
+        self.device = device if device is not None else current_device()
+        pts = np.asarray(points)
+        if pts.ndim != 2 or pts.shape[1] not in (2, 3):
+            raise ValueError('points must have shape (n_points, 3) or (n_points, 2)')
+        if pts.dtype != np.float64:
+            pts = pts.astype(np.float64)
+        self.n = int(pts.shape[0])
+        self.ncols = int(pts.shape[1])
+        n = self.n
+        self.x = torch.empty(n, dtype=torch.float64, device=self.device)
+        self.y = torch.empty(n, dtype=torch.float64, device=self.device)
+        self.z = torch.empty(n, dtype=torch.float64, device=self.device)
+        self.h2d_bytes = n * self.ncols * 8
+        if n:
+            if pts.strides[0] == 8:            # columns contiguous (F-order): 2-3 plain H2D copies
+                self.x.copy_(_from_numpy(pts[:, 0]), non_blocking=True)
+                self.y.copy_(_from_numpy(pts[:, 1]), non_blocking=True)
+                if self.ncols == 3:
+                    self.z.copy_(_from_numpy(pts[:, 2]), non_blocking=True)
+                else:
+                    self.z.zero_()
+            else:                              # C-order AoS: one H2D copy + transposition kernel
+                aos = _from_numpy(np.ascontiguousarray(pts)).to(self.device, non_blocking=True)
+                _lib.check(lib.upcp_points_aos_to_soa(ptr(aos), n, self.ncols, ptr(self.x), ptr(self.y),
+                                                      ptr(self.z), stream_ptr()), 'upcp_points_aos_to_soa')
+        self._bbox_all = None
+
+    @classmethod
+    def from_device(cls, x, y, z):
+        """Wrap coordinates that already live in HBM (bench / on-device generator)."""
+        self = cls.__new__(cls)
+        _lib.require_cuda()
+        self.device = x.device
+        self.n = int(x.numel())
+        self.ncols = 3
+        self.x, self.y, self.z = x, y, z
+        self.h2d_bytes = 0
+        self._bbox_all = None
+        return self
+
+    def bbox(self, d_sel=None):
+        """(bbox_all[6], bbox_sel[6], n_sel) in fp64 -- one reduction + one small D2H."""
+        lib = _lib.load()
+        out = torch.empty(13, dtype=torch.float64, device=self.device)
+        ws = workspace(self.device).get(lib.upcp_bbox_ws_bytes(self.n))
+        _lib.check(lib.upcp_bbox(ptr(self.x), ptr(self.y), ptr(self.z), self.n, ptr(d_sel), ptr(out),
+                                 ptr(ws), ws.numel(), stream_ptr()), 'upcp_bbox')
+        h = out.cpu().numpy()
+        return h[0:6].copy(), h[6:12].copy(), int(h[12])
+
+    def bbox_all(self):
+        if self._bbox_all is None:
+            self._bbox_all = self.bbox(None)[0]
+        return self._bbox_all
+
+
+# Cache of the most recent tiles keyed on the identity of the host array, so that a
+# sequence of get_labels(points, ...) calls on the same cloud uploads it once.
+_TILE_CACHE = []
+_TILE_CACHE_SIZE = 2
+
+
+def _fingerprint(pts):
+    n = pts.shape[0]
+    if n == 0:
+        return ()
+    idx = np.linspace(0, n - 1, num=min(n, 61)).astype(np.int64)
+    return tuple(pts[idx].ravel().tolist())
+
+
+def get_tile(points, device=None):
+    """DeviceTile for a host array, re-using the HBM copy of the same live array."""
+    if isinstance(points, DeviceTile):
+        return points
+    device = device if device is not None else current_device()
+    pts = np.asarray(points)
+    fp = None
+    for ref, dev, stored_fp, tile in _TILE_CACHE:
+        if ref() is pts and dev == device:
+            fp = _fingerprint(pts)
+            if fp == stored_fp:
+                return tile
+    tile = DeviceTile(pts, device)
+    try:
+        ref = weakref.ref(pts)
+    except TypeError:
+        return tile
+    _TILE_CACHE.append((ref, device, fp if fp is not None else _fingerprint(pts), tile))
+    while len(_TILE_CACHE) > _TILE_CACHE_SIZE:
+        _TILE_CACHE.pop(0)
+    return tile
+
+
+def clear_tile_cache():
+    _TILE_CACHE.clear()
+
+
+# -------------------------------------------------------------------- raster --
+class DeviceRaster:
+    """FastGridInterpolator state in HBM (interpolation.py:329-334)."""
+
+    def __init__(self, grid_x, grid_y, values, device=None):
+        _lib.require_cuda()
+        self.device = device if device is not None else current_device()
+        grid_x = np.asarray(grid_x, dtype=np.float64)
+        grid_y = np.asarray(grid_y, dtype=np.float64)
+        values = np.ascontiguousarray(np.asarray(values, dtype=np.float64))
+        # Same host arithmetic as the reference constructor.
+        step_x = grid_x[1] - grid_x[0]
+        step_y = grid_y[0] - grid_y[1]
+        bin_x = grid_x - (step_x / 2)
+        bin_y = grid_y + (step_y / 2)
+        self.nx = int(bin_x.shape[0])
+        self.ny = int(bin_y.shape[0])
+        if values.shape != (self.ny, self.nx):
+            raise ValueError(f'values has shape {values.shape}, expected ({self.ny}, {self.nx})')
+        self.bin_x = _from_numpy(np.ascontiguousarray(bin_x)).to(self.device)
+        self.bin_y = _from_numpy(np.ascontiguousarray(bin_y)).to(self.device)
+        self.values = _from_numpy(values).to(self.device)
+
+    def lookup(self, tile, d_sel=None, out=None):
+        """values[y_idx, x_idx] per point -> fp64 cuda tensor [N]."""
+        lib = _lib.load()
+        if out is None:
+            out = torch.full((tile.n,), float('nan'), dtype=torch.float64, device=self.device)
+        _lib.check(lib.upcp_raster_lookup(ptr(tile.x), ptr(tile.y), tile.n, ptr(d_sel), ptr(self.bin_x),
+                                          self.nx, ptr(self.bin_y), self.ny, ptr(self.values), ptr(out),
+                                          stream_ptr()), 'upcp_raster_lookup')
+        return out
+
+    def classify(self, tile, mode, a=0.0, b=0.0, d_sel=None, d_labels=None, assign=0, want_mask=True):
+        """Fused lookup + height-threshold test -> uint8 mask [N] (and optional label write)."""
+        lib = _lib.load()
+        out = torch.empty(tile.n, dtype=torch.uint8, device=self.device) if want_mask else None
+        _lib.check(lib.upcp_raster_classify(ptr(tile.x), ptr(tile.y), ptr(tile.z), tile.n, ptr(d_sel),
+                                            ptr(self.bin_x), self.nx, ptr(self.bin_y), self.ny,
+                                            ptr(self.values), int(mode), float(a), float(b), ptr(out),
+                                            ptr(d_labels), int(assign), stream_ptr()),
+                   'upcp_raster_classify')
+        return out
+
+
+# ----------------------------------------------------------------------- PIP --
+def rings_from_polygons(polygons):
+    """Flatten shapely-like polygons (``.exterior.coords`` / ``.interiors``) or raw
+    rings into the ring arrays of the C ABI.  Matches what clip_utils.poly_clip reads
+    (clip_utils.py:211-212)."""
+    xy, off, poly_id, hole = [], [0], [], []
+    for p, poly in enumerate(polygons):
+        if hasattr(poly, 'exterior'):
+            ext = np.asarray(poly.exterior.coords, dtype=np.float64)
+            ints = [np.asarray(i.coords, dtype=np.float64) for i in poly.interiors]
+        else:
+            ext = np.asarray(poly, dtype=np.float64)
+            ints = []
+        rings = [(ext, 0)] + [(i, 1) for i in ints]
+        for ring, is_hole in rings:
+            ring = ring.reshape(-1, ring.shape[-1] if ring.ndim == 2 else 2)[:, :2] if ring.size else ring.reshape(0, 2)
+            xy.append(ring)
+            off.append(off[-1] + ring.shape[0])
+            poly_id.append(p)
+            hole.append(is_hole)
+    ring_xy = np.ascontiguousarray(np.concatenate(xy, axis=0) if xy else np.zeros((0, 2)), dtype=np.float64)
+    return (ring_xy, np.asarray(off, dtype=np.int64), np.asarray(poly_id, dtype=np.int32),
+            np.asarray(hole, dtype=np.uint8))
+
+
+class PipPlan:
+    """Device-resident point-in-polygon plan for a set of polygons."""
+
+    def __init__(self, polygons, device=None, grid_dim=0):
+        lib = _lib.require_cuda()
+        self.device = device if device is not None else current_device()
+        ring_xy, off, poly_id, hole = rings_from_polygons(polygons)
+        self.n_rings = int(poly_id.shape[0])
+        self.n_vertices = int(ring_xy.shape[0])
+        handle = ctypes.c_void_p()
+        _lib.check(lib.upcp_pip_plan_create(
+            ring_xy.ctypes.data_as(ctypes.c_void_p), off.ctypes.data_as(ctypes.c_void_p),
+            poly_id.ctypes.data_as(ctypes.c_void_p), hole.ctypes.data_as(ctypes.c_void_p),
+            self.n_rings, int(grid_dim), ctypes.byref(handle)), 'upcp_pip_plan_create')
+        try:
+            nbytes = lib.upcp_pip_plan_bytes(handle)
+            self.blob = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+            _lib.check(lib.upcp_pip_plan_upload(handle, ptr(self.blob), nbytes, stream_ptr()),
+                       'upcp_pip_plan_upload')
+        finally:
+            lib.upcp_pip_plan_destroy(handle)
+        self.nbytes = int(nbytes)
+
+    def query(self, tile, d_sel=None):
+        """uint8 mask [N]: point inside the polygon set (restricted to d_sel)."""
+        lib = _lib.load()
+        out = torch.empty(tile.n, dtype=torch.uint8, device=self.device)
+        _lib.check(lib.upcp_pip_query(ptr(self.blob), ptr(tile.x), ptr(tile.y), tile.n, ptr(d_sel), ptr(out),
+                                      stream_ptr()), 'upcp_pip_query')
+        return out

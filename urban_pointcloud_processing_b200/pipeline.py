@@ -1,0 +1,189 @@
+"""Data-fusion pipeline (drop-in for ``upcp.pipeline.Pipeline``, reference
+src/upcp/pipeline.py:18-196).
+
+``process_cloud`` keeps the reference semantics -- processors are applied in order,
+each one sees ``mask = (labels == 0)`` (pipeline.py:90) and mutates ``labels`` -- but
+uploads the cloud ONCE, chains every drop-in processor on the device and downloads
+the labels once at the end.  Processors that are not drop-ins (no
+``_label_mask_device``) are still accepted: the labels are synchronised to the host
+around them and their own ``get_labels`` is called, exactly as the reference does.
+LAS file I/O (``process_file`` / ``process_folder``) needs ``laspy`` and is only
+available when it is installed ("next" row of the scope table)."""
+import logging
+import os
+import pathlib
+import time
+
+import numpy as np
+
+from . import device as dev
+from .analysis import analysis_tools
+from .utils import las_utils
+
+logger = logging.getLogger(__name__)
+
+
+class Pipeline:
+    """
+    Parameters
+    ----------
+    processors : iterable of type AbstractProcessor
+        The processors to apply, in order.
+    exclude_labels : list
+        List of labels to exclude from processing.
+    ahn_reader : AHNReader object
+        Pointer to the AHNReader object used in the processors. Required if caching is
+        used.
+    caching : bool (default: True)
+        Enable caching of AHN interpolation data.
+    """
+
+    FILE_TYPES = ('.LAS', '.las', '.LAZ', '.laz')
+
+    def __init__(self, processors=[], exclude_labels=[], ahn_reader=None, caching=True):
+        if ahn_reader is None and caching:
+            logger.error('An ahn_reader must be specified when caching is enabled.')
+            raise ValueError
+        self.processors = processors
+        self.exclude_labels = exclude_labels
+        self.ahn_reader = ahn_reader
+        self.caching = caching
+        if self.caching:
+            self.ahn_reader.set_caching(self.caching)
+        self.last_timings = []
+
+    def _create_mask(self, mask, labels):
+        """Create mask based on `exclude_labels` (dead in the reference too: the mask is
+        overwritten per processor, pipeline.py:90)."""
+        if mask is None:
+            mask = np.ones((len(labels),), dtype=bool)
+        for exclude_label in self.exclude_labels:
+            mask = mask & (labels != exclude_label)
+        return mask
+
+    def process_tile_device(self, tilecode, tile, d_labels, sync_timings=False):
+        """Run all processors on a device-resident tile; ``d_labels`` (int32 cuda) is
+        updated in place and returned.  This is the hot path the benchmark times."""
+        import torch
+        self.last_timings = []
+        for obj in self.processors:
+            if sync_timings:
+                torch.cuda.synchronize()
+                start = time.time()
+            d_mask = dev.mask_build(d_labels, None, base=False, eq=(0,))
+            if hasattr(obj, '_apply_device'):
+                obj._apply_device(tile, d_labels, d_mask, tilecode)
+            else:
+                raise TypeError(f'{type(obj).__name__} is not a device drop-in processor')
+            if sync_timings:
+                torch.cuda.synchronize()
+                self.last_timings.append((type(obj).__name__, time.time() - start))
+        return d_labels
+
+    def process_cloud(self, tilecode, points, labels, mask=None):
+        """
+        Process a single point cloud.
+
+        Parameters
+        ----------
+        tilecode : str
+            The CycloMedia tile-code for the given pointcloud.
+        points : array of shape (n_points, 3)
+            The point cloud <x, y, z>.
+        labels : array of shape (n_points,)
+            All labels as int values (updated in place).
+        mask : array of shape (n_points,) with dtype=bool
+            Pre-mask (ignored after the first processor, as in the reference).
+
+        Returns
+        -------
+        The ``labels`` array with the updated labels.
+        """
+        tile = dev.get_tile(points)
+        d_labels = dev.upload_labels(labels, tile.device)
+        host_stale = False
+        info = logger.isEnabledFor(logging.INFO)
+        for obj in self.processors:
+            start = time.time()
+            if hasattr(obj, '_apply_device'):
+                d_mask = dev.mask_build(d_labels, None, base=False, eq=(0,))
+                n_before = dev.mask_count(d_mask) if info else 0
+                obj._apply_device(tile, d_labels, d_mask, tilecode)
+                host_stale = True
+                if info:
+                    n_after = dev.mask_count(dev.mask_build(d_labels, None, base=False, eq=(0,)))
+                    diff = n_before - n_after
+            else:
+                if host_stale:
+                    dev.download_labels(d_labels, labels)
+                    host_stale = False
+                host_mask = (labels == 0)
+                n_before = np.count_nonzero(host_mask)
+                labels = obj.get_labels(points, labels, host_mask, tilecode)
+                diff = n_before - np.count_nonzero(labels == 0)
+                d_labels = dev.upload_labels(labels, tile.device)
+            if info:
+                duration = time.time() - start
+                logger.info(f'Processor finished in {duration:.2f}s, ' + f'{diff} points labelled.')
+        if host_stale:
+            dev.download_labels(d_labels, labels)
+        return labels
+
+    def process_file(self, in_file, out_file=None, mask=None):
+        """Process a single LAS file and save the result as .laz file (needs laspy)."""
+        logger.info(f'Processing file {in_file}.')
+        start = time.time()
+        if not os.path.isfile(in_file):
+            logger.error('The input file specified does not exist')
+            return None
+        try:
+            import laspy
+        except ImportError as e:  # LAS/LAZ I/O is outside the hot path (scope table, "next")
+            raise ImportError('Pipeline.process_file needs laspy, which is not installed') from e
+        if out_file is None:
+            out_file = in_file
+        tilecode = las_utils.get_tilecode_from_filename(in_file)
+        pointcloud = laspy.read(in_file)
+        points = np.vstack((pointcloud.x, pointcloud.y, pointcloud.z)).T
+        if 'label' not in pointcloud.point_format.extra_dimension_names:
+            labels = np.zeros((len(points),), dtype='uint16')
+        else:
+            labels = pointcloud.label
+        labels = self.process_cloud(tilecode, points, labels, mask)
+        if 'label' not in pointcloud.point_format.extra_dimension_names:
+            pointcloud.add_extra_dim(laspy.ExtraBytesParams(name='label', type='uint8',
+                                                            description='Labels'))
+        pointcloud.label = labels
+        pointcloud.write(out_file)
+        duration = time.time() - start
+        stats = analysis_tools.get_label_stats(labels)
+        logger.info('\nSTATISTICS\n' + stats)
+        logger.info(f'File processed in {duration:.2f}s, ' + f'output written to {out_file}.\n' + '=' * 20)
+
+    def process_folder(self, in_folder, out_folder=None, in_prefix='', out_prefix='', suffix='',
+                       hide_progress=False):
+        """Process a folder of LAS files and save each processed file."""
+        if not os.path.isdir(in_folder):
+            logger.error('The input path specified does not exist')
+            return None
+        in_folder = pathlib.Path(in_folder)
+        if out_folder is None:
+            out_folder = in_folder
+        else:
+            pathlib.Path(out_folder).mkdir(parents=True, exist_ok=True)
+        if suffix is None:
+            suffix = ''
+        logger.info('\n===== PIPELINE =====\n' + f'Processing folder {in_folder}, ' +
+                    f'writing results in {out_folder}.')
+        files = [f for f in in_folder.glob('*')
+                 if f.name.endswith(self.FILE_TYPES) and f.name.startswith(in_prefix)]
+        logger.debug(f'{len(files)} files found.')
+        for file in files:
+            filename, extension = os.path.splitext(file.name)
+            if in_prefix and out_prefix:
+                filename = filename.replace(in_prefix, out_prefix)
+            elif out_prefix:
+                filename = out_prefix + filename
+            outfile = os.path.join(out_folder, filename + suffix + extension)
+            self.process_file(file.as_posix(), outfile)
+        logger.info(f'Pipeline finished, {len(files)} processed.\n' + '=' * 20)

@@ -1,0 +1,162 @@
+"""Normal-based region growing (drop-in for
+``upcp.region_growing.region_growing.RegionGrowing``, reference
+src/upcp/region_growing/region_growing.py:15-170).
+
+The reference builds an Open3D KD-tree, estimates normals with a hybrid search, and grows
+the region with a Python ``while`` loop over a list of seeds.  Here: one exact
+kNN + normals + curvature-covariance pass over a uniform-grid cell list
+(``upcp_knn_normals``) and one persistent work-queue kernel that expands the frontier to
+the least fixpoint (``upcp_region_grow``) -- which is what the Python loop computes,
+independently of the order in which seeds are visited."""
+import ctypes
+import logging
+
+import numpy as np
+import torch
+
+from .. import _lib
+from .. import device as dev
+from ..abstract_processor import AbstractProcessor
+from ..labels import Labels
+
+logger = logging.getLogger(__name__)
+
+CURVATURE_TOL = 1e-9
+
+
+def knn_normals_device(tile, d_sel, m, bbox_sel, knn, max_nn, radius, cell_size=None,
+                       want_d2=False, want_cov=True, want_curv=True):
+    """kNN rows (compact ids), normals, k-neighbourhood covariance and analytic eigenvalue
+    ratios for the selected points of ``tile``."""
+    lib = _lib.load()
+    device = tile.device
+    if cell_size is None:
+        cell_size = max(float(radius) * 0.5, 1e-3)
+    d_knn = torch.empty((m, knn), dtype=torch.int32, device=device)
+    d_d2 = torch.empty((m, knn), dtype=torch.float64, device=device) if want_d2 else None
+    d_normals = torch.empty((m, 3), dtype=torch.float64, device=device)
+    d_cov = torch.empty((m, 6), dtype=torch.float64, device=device) if want_cov else None
+    d_curv = torch.empty((m, 3), dtype=torch.float64, device=device) if want_curv else None
+    ws = dev.workspace(device).get(lib.upcp_knn_ws_bytes(tile.n, m, max(knn, max_nn)))
+    bbox_arr = (ctypes.c_double * 6)(*[float(v) for v in bbox_sel])
+    _lib.check(lib.upcp_knn_normals(dev.ptr(tile.x), dev.ptr(tile.y), dev.ptr(tile.z), tile.n,
+                                    dev.ptr(d_sel), m, bbox_arr, int(knn), int(max_nn), float(radius),
+                                    float(cell_size), dev.ptr(d_knn), dev.ptr(d_d2), dev.ptr(d_normals),
+                                    dev.ptr(d_cov), dev.ptr(d_curv), dev.ptr(ws), ws.numel(),
+                                    dev.stream_ptr()), 'upcp_knn_normals')
+    return d_knn, d_d2, d_normals, d_cov, d_curv
+
+
+def can_seed_from_curvature(d_cov, d_curv, threshold_curve):
+    """uint8 cuda tensor [m]: ``eig_val[0] / eig_val.sum() < threshold_curve``
+    (region_growing.py:59-73,132).
+
+    ``eig_val[0]`` is whatever LAPACK ``dgeev`` returns first (unsorted), which no closed
+    form predicts.  The device supplies the three analytic ratios; when all three fall on
+    the same side of the threshold (the normal case for the default threshold 1.0) the
+    decision does not depend on the order.  The remaining points are resolved on the host
+    with ``np.linalg.eig`` exactly as the reference does.  Returns (d_can_seed, n_host).
+    """
+    r = d_curv
+    finite = torch.isfinite(r).all(dim=1)
+    below = (r < threshold_curve - CURVATURE_TOL).all(dim=1) & finite
+    above = (r >= threshold_curve + CURVATURE_TOL).all(dim=1) & finite
+    ambiguous = ~(below | above)
+    can_seed = below.to(torch.uint8)
+    idx = torch.nonzero(ambiguous).flatten()
+    n_host = int(idx.numel())
+    if n_host:
+        c = d_cov[idx].cpu().numpy()
+        cov = np.empty((n_host, 3, 3))
+        cov[:, 0, 0] = c[:, 0]; cov[:, 0, 1] = c[:, 1]; cov[:, 0, 2] = c[:, 2]
+        cov[:, 1, 0] = c[:, 1]; cov[:, 1, 1] = c[:, 3]; cov[:, 1, 2] = c[:, 4]
+        cov[:, 2, 0] = c[:, 2]; cov[:, 2, 1] = c[:, 4]; cov[:, 2, 2] = c[:, 5]
+        with np.errstate(all='ignore'):
+            eig_val = np.linalg.eig(cov)[0]
+            curvature = eig_val[:, 0] / eig_val.sum(axis=1)
+            res = (curvature < threshold_curve)
+        can_seed[idx] = torch.from_numpy(np.ascontiguousarray(res.astype(np.uint8))).to(can_seed.device)
+    return can_seed, n_host
+
+
+def region_grow_device(d_knn, d_normals, d_seed, d_can_seed, threshold_angle):
+    lib = _lib.load()
+    m, knn = d_knn.shape
+    device = d_knn.device
+    d_region = torch.empty(m, dtype=torch.uint8, device=device)
+    d_info = torch.zeros(2, dtype=torch.int64, device=device)
+    ws = dev.workspace(device).get(lib.upcp_region_grow_ws_bytes(m))
+    _lib.check(lib.upcp_region_grow(dev.ptr(d_knn), int(knn), dev.ptr(d_normals), dev.ptr(d_seed),
+                                    dev.ptr(d_can_seed), m, float(threshold_angle), dev.ptr(d_region),
+                                    dev.ptr(d_info), dev.ptr(ws), ws.numel(), dev.stream_ptr()),
+               'upcp_region_grow')
+    return d_region, d_info
+
+
+def mask_gather(d_sel, d_full, m):
+    lib = _lib.load()
+    n = d_sel.numel()
+    out = torch.empty(m, dtype=torch.uint8, device=d_sel.device)
+    ws = dev.workspace(d_sel.device, slot=1).get(lib.upcp_compact_ws_bytes(n))
+    _lib.check(lib.upcp_mask_gather(dev.ptr(d_sel), n, dev.ptr(d_full), dev.ptr(out), None, dev.ptr(ws),
+                                    ws.numel(), dev.stream_ptr()), 'upcp_mask_gather')
+    return out
+
+
+def mask_scatter(d_sel, d_compact):
+    lib = _lib.load()
+    n = d_sel.numel()
+    out = torch.empty(n, dtype=torch.uint8, device=d_sel.device)
+    ws = dev.workspace(d_sel.device, slot=1).get(lib.upcp_compact_ws_bytes(n))
+    _lib.check(lib.upcp_mask_scatter(dev.ptr(d_sel), n, dev.ptr(d_compact), dev.ptr(out), dev.ptr(ws),
+                                     ws.numel(), dev.stream_ptr()), 'upcp_mask_scatter')
+    return out
+
+
+class RegionGrowing(AbstractProcessor):
+    """
+    Region growing based on the smoothness constraint of
+    https://pcl.readthedocs.io/projects/tutorials/en/latest/region_growing_segmentation.html
+
+    Parameters (names and defaults as the reference, region_growing.py:20-22)
+    ----------
+    label, exclude_labels=[], threshold_angle=20, threshold_curve=1.0, max_nn=30,
+    grow_region_knn=15, grow_region_radius=0.2
+    """
+
+    def __init__(self, label, exclude_labels=[], threshold_angle=20, threshold_curve=1.0, max_nn=30,
+                 grow_region_knn=15, grow_region_radius=0.2):
+        super().__init__(label)
+        self.threshold_angle = threshold_angle
+        self.threshold_curve = threshold_curve
+        self.max_nn = max_nn
+        self.grow_region_knn = grow_region_knn
+        self.grow_region_radius = grow_region_radius
+        self.exclude_labels = exclude_labels
+        self.cell_size = None           # search-grid cell size; None = radius / 2
+        self.last_stats = {}
+
+    def _label_mask_device(self, tile, d_labels, d_mask, tilecode=None):
+        logger.info('KDTree based Region Growing ' + f'(label={self.label}, {Labels.get_str(self.label)}).')
+        if tile.ncols != 3:
+            raise ValueError('RegionGrowing needs 3D points')
+        # _set_mask (region_growing.py:34-49): the incoming mask is ignored
+        d_sel = dev.mask_build(d_labels, None, base=True, ne=tuple(self.exclude_labels))
+        _, bbox_sel, m = tile.bbox(d_sel)
+        d_label_mask = torch.zeros(tile.n, dtype=torch.uint8, device=tile.device)
+        if m == 0:
+            return d_label_mask
+        d_seed_full = dev.mask_build(d_labels, None, base=False, eq=(self.label,))
+        d_seed = mask_gather(d_sel, d_seed_full, m)
+        n_seeds = dev.mask_count(d_seed)
+        if n_seeds == 0:
+            logger.debug('Input point cloud does not contain any seed points.')
+            return d_label_mask
+        d_knn, _, d_normals, d_cov, d_curv = knn_normals_device(
+            tile, d_sel, m, bbox_sel, self.grow_region_knn, self.max_nn, self.grow_region_radius,
+            cell_size=self.cell_size)
+        d_can_seed, n_host = can_seed_from_curvature(d_cov, d_curv, self.threshold_curve)
+        d_region, d_info = region_grow_device(d_knn, d_normals, d_seed, d_can_seed, self.threshold_angle)
+        self.last_stats = {'n_selected': m, 'n_seeds': n_seeds, 'n_curvature_on_host': n_host,
+                           '_d_info': d_info}
+        return mask_scatter(d_sel, d_region)
