@@ -1,0 +1,364 @@
+"""numpy restatement of the reference's Python-level control flow on the labelling path.
+
+TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).  Every function cites the reference
+lines it follows (paths relative to /root/reference/src/upcp).  Natives the reference
+gets from third-party wheels are taken from ``oracle.natives`` (plain-C restatement).
+All functions are pure: inputs are never mutated unless stated.
+"""
+import numpy as np
+
+from . import natives
+
+GROUND, BUILDING, NOISE, UNKNOWN = 9, 10, 99, 0     # labels.py:9-24
+
+
+# ------------------------------------------------------------------ raster --------
+def fast_grid_lookup(grid_x, grid_y, values, positions):
+    """FastGridInterpolator.__init__/__call__ (utils/interpolation.py:329-348)."""
+    grid_x = np.asarray(grid_x); grid_y = np.asarray(grid_y)
+    step_x = grid_x[1] - grid_x[0]
+    step_y = grid_y[0] - grid_y[1]
+    bin_x = grid_x - (step_x / 2)
+    bin_y = grid_y + (step_y / 2)
+    x_idx = np.digitize(positions[:, 0], bin_x) - 1
+    y_idx = np.digitize(positions[:, 1], bin_y, right=True) - 1
+    return values[y_idx, x_idx]
+
+
+def interpolate(ahn_tile, points, surface='ground_surface'):
+    """AHNReader.interpolate without cache (utils/ahn_utils.py:74-102)."""
+    return fast_grid_lookup(ahn_tile['x'], ahn_tile['y'], ahn_tile[surface], points)
+
+
+# --------------------------------------------------------------------- PIP --------
+def compute_bounding_box(points):
+    """math_utils.compute_bounding_box (utils/math_utils.py:36-57)."""
+    return (np.min(points[:, 0]), np.min(points[:, 1]), np.max(points[:, 0]), np.max(points[:, 1]))
+
+
+def rectangle_clip(points, rect):
+    """clip_utils.rectangle_clip (utils/clip_utils.py:22-40)."""
+    return ((points[:, 0] >= rect[0]) & (points[:, 0] <= rect[2])
+            & (points[:, 1] >= rect[1]) & (points[:, 1] <= rect[3]))
+
+
+def poly_clip(points, poly):
+    """clip_utils.poly_clip (utils/clip_utils.py:193-238); poly has .exterior.coords/.interiors."""
+    clip_mask = np.zeros((len(points),), dtype=bool)
+    exterior = np.array(poly.exterior.coords)
+    interiors = [np.array(interior.coords) for interior in poly.interiors]
+    if len(exterior) < 3:
+        return clip_mask
+    bbox_mask = rectangle_clip(points, compute_bounding_box(exterior))
+    exterior_mask = natives.is_inside(points[bbox_mask, 0], points[bbox_mask, 1], exterior)
+    bbox_inds = np.where(bbox_mask)[0]
+    clip_mask[bbox_inds[exterior_mask]] = True
+    for interior in interiors:
+        if len(interior) < 3:
+            continue
+        bbox_mask = rectangle_clip(points, compute_bounding_box(interior))
+        interior_mask = natives.is_inside(points[bbox_mask, 0], points[bbox_mask, 1], interior)
+        bbox_inds = np.where(bbox_mask)[0]
+        clip_mask[bbox_inds[interior_mask]] = False
+    return clip_mask
+
+
+# ------------------------------------------------------------------ fusers --------
+def ahn_fuser_labels(points, labels, mask, ahn_tile, label, target='ground', epsilon=0.2):
+    """AHNFuser.get_labels with refine_ground=False (fusion/ahn_fuser.py:128-173)."""
+    surface = 'ground_surface' if target == 'ground' else 'building_surface'
+    target_z = interpolate(ahn_tile, points[mask, :], surface)
+    label_mask = np.zeros((len(points),), dtype=bool)
+    with np.errstate(invalid='ignore'):
+        if target == 'ground':
+            label_mask[mask] = (np.abs(points[mask, 2] - target_z) < epsilon)
+        else:
+            label_mask[mask] = points[mask, 2] < target_z + epsilon
+    labels[label_mask] = label
+    return labels
+
+
+def building_fuser_labels(points, labels, mask, polygons, label, ahn_tile=None, ahn_eps=0.2):
+    """BGTBuildingFuser.get_labels (fusion/building_fuser.py:46-102)."""
+    label_mask = np.zeros((len(points),), dtype=bool)
+    if len(polygons) == 0:
+        return labels
+    if mask is None:
+        mask = np.ones((len(points),), dtype=bool)
+    mask_ids = np.where(mask)[0]
+    building_mask = np.zeros((len(mask_ids),), dtype=bool)
+    for polygon in polygons:
+        building_mask = building_mask | poly_clip(points[mask, :], polygon)
+    if ahn_tile is not None:
+        bld_z = interpolate(ahn_tile, points[mask, :], 'building_surface')
+        bld_z_valid = np.isfinite(bld_z)
+        ahn_mask = (points[mask_ids[bld_z_valid], 2] <= bld_z[bld_z_valid] + ahn_eps)
+        building_mask[bld_z_valid] = building_mask[bld_z_valid] & ahn_mask
+    label_mask[mask_ids[building_mask]] = True
+    labels[label_mask] = label
+    return labels
+
+
+def road_fuser_labels(points, labels, polygons, label):
+    """BGTRoadFuser.get_labels (fusion/road_fuser.py:50-95): domain is labels == GROUND."""
+    label_mask = np.zeros(len(points), dtype=bool)
+    if len(polygons) == 0:
+        return labels
+    mask = labels == GROUND
+    mask_ids = np.where(mask)[0]
+    road_mask = np.zeros((len(mask_ids),), dtype=bool)
+    for polygon in polygons:
+        road_mask = road_mask | poly_clip(points[mask, :], polygon)
+    label_mask[mask_ids[road_mask]] = True
+    labels[label_mask] = label
+    return labels
+
+
+# --------------------------------------------------------------------- LCC --------
+def get_octree_level(points, grid_size):
+    """math_utils.get_octree_level (utils/math_utils.py:21-33)."""
+    dims = np.zeros((points.shape[1],))
+    for d in range(points.shape[1]):
+        dims[d] = np.max(points[:, d]) - np.min(points[:, d])
+    max_dim = np.max(dims)
+    if max_dim < 0.001:
+        return 0
+    octree_level = np.rint(-np.log(grid_size / max_dim) / (np.log(2)))
+    if octree_level > 0:
+        return int(np.int64(octree_level))
+    return 1
+
+
+def lcc_point_components(points, mask, grid_size, min_component_size):
+    """_convert_input_cloud + _label_connected_comp
+    (region_growing/label_connected_comp.py:53-97).  Returns float ids over masked points,
+    -1 for components below min_component_size."""
+    xs = (points[mask, 0]).astype(np.float32)
+    ys = (points[mask, 1]).astype(np.float32)
+    if points.shape[1] == 2:
+        zs = np.zeros(xs.shape).astype(np.float32)
+    else:
+        zs = (points[mask, 2]).astype(np.float32)
+    octree_level = get_octree_level(points, grid_size)
+    if len(xs) == 0:
+        return np.zeros((0,), dtype=np.float32), octree_level
+    point_components = np.around(natives.label_connected_components(xs, ys, zs, octree_level))
+    if min_component_size > 1:
+        cc_labels, counts = np.unique(point_components, return_counts=True)
+        cc_labels_filtered = cc_labels[counts < min_component_size]
+        point_components[np.isin(point_components, cc_labels_filtered)] = -1
+    return point_components, octree_level
+
+
+def lcc_fill_components(point_components, mask, point_labels, label, min_component_size, threshold,
+                        literal=False):
+    """_fill_components (label_connected_comp.py:99-135).  `literal` runs the reference's
+    per-component loop; the default computes the same thing with bincount."""
+    mask_indices = np.where(mask)[0]
+    label_mask = np.zeros(len(mask), dtype=bool)
+    if literal:
+        cc_labels = set(np.unique(point_components)).difference((-1,))
+        for cc in cc_labels:
+            cc_mask = (point_components == cc)
+            cc_size = np.count_nonzero(cc_mask)
+            if cc_size < min_component_size:
+                continue
+            seed_count = np.count_nonzero(point_labels[mask_indices[cc_mask]] == label)
+            if (float(seed_count) / cc_size) > threshold:
+                label_mask[mask_indices[cc_mask]] = True
+        return label_mask
+    valid = point_components >= 0
+    ids = point_components[valid].astype(np.int64)
+    if len(ids) == 0:
+        return label_mask
+    sizes = np.bincount(ids)
+    seeds = np.bincount(ids, weights=(point_labels[mask_indices[valid]] == label).astype(np.float64))
+    with np.errstate(invalid='ignore', divide='ignore'):
+        accept = (sizes >= min_component_size) & ((seeds.astype(np.float64) / sizes) > threshold)
+    label_mask[mask_indices[valid]] = accept[ids]
+    return label_mask
+
+
+def lcc_get_label_mask(points, labels, mask, label, exclude_labels=(), grid_size=0.1,
+                       min_component_size=100, threshold=0.1, literal=False):
+    """LabelConnectedComp.get_label_mask (label_connected_comp.py:137-181)."""
+    if exclude_labels:
+        m = np.ones((len(points),), dtype=bool)
+        for exclude_label in exclude_labels:
+            m = m & (labels != exclude_label)
+    elif mask is None:
+        m = np.ones((len(points),), dtype=bool)
+    else:
+        m = mask.copy()
+        m[labels == label] = True
+    comps, _ = lcc_point_components(points, m, grid_size, min_component_size)
+    return lcc_fill_components(comps, m, labels, label, min_component_size, threshold, literal)
+
+
+def lcc_get_components(points, grid_size, min_component_size):
+    """LabelConnectedComp.get_components with no exclusions (label_connected_comp.py:207-231)."""
+    m = np.ones((len(points),), dtype=bool)
+    return lcc_point_components(points, m, grid_size, min_component_size)[0]
+
+
+def layer_lcc_labels(points, labels, mask, ahn_tile, label, params, reset_noise=False):
+    """LayerLCC.get_labels (region_growing/layer_lcc.py:95-145)."""
+    mask_copy = mask.copy()
+    mask_copy[labels == label] = True
+    if reset_noise:
+        noise_mask = labels == NOISE
+        mask_copy[noise_mask] = True
+    points_z = interpolate(ahn_tile, points[mask_copy], 'ground_surface')
+    label_mask = np.zeros((len(points),), dtype=bool)
+    layer_mask = np.zeros((np.count_nonzero(mask_copy),), dtype=bool)
+    labels_copy = labels[mask_copy].copy()
+    pts = points[mask_copy, :]
+    for layer in params:
+        p = {'bottom': -np.inf, 'top': np.inf, 'grid_size': 0.1, 'min_comp_size': 100, 'threshold': 0.5}
+        p.update(layer)
+        # _filter_layer (layer_lcc.py:70-93)
+        with np.errstate(invalid='ignore'):
+            ids = np.where((pts[:, 2] > points_z + p['bottom']) & (pts[:, 2] <= points_z + p['top']))[0]
+        m = np.zeros((len(pts),), dtype=bool)
+        if len(ids) > 0 and np.count_nonzero(labels_copy[ids] == label) > 0:
+            lcc_mask = lcc_get_label_mask(pts[ids], labels_copy[ids].copy(), None, label,
+                                          grid_size=p['grid_size'], min_component_size=p['min_comp_size'],
+                                          threshold=p['threshold'])
+            m[ids[lcc_mask]] = True
+        layer_mask = layer_mask | m
+        labels_copy[layer_mask] = label
+    label_mask[mask_copy] = layer_mask
+    if reset_noise:
+        label_mask = label_mask & (mask | noise_mask)
+    else:
+        label_mask = label_mask & mask
+    labels[label_mask] = label
+    return labels
+
+
+def noise_filter_labels(points, labels, mask, ahn_tile, label, epsilon=0.2, grid_size=0.1,
+                        min_component_size=100):
+    """NoiseFilter.get_labels (fusion/noise_filter.py:43-84)."""
+    point_components = lcc_get_components(points[mask], grid_size, min_component_size)
+    cc_mask = point_components == -1
+    target_z = interpolate(ahn_tile, points[mask], 'ground_surface')
+    with np.errstate(invalid='ignore'):
+        ground_mask = (points[mask, 2] - target_z) < -epsilon
+    label_mask = np.zeros((len(points),), dtype=bool)
+    label_mask[mask] = cc_mask | ground_mask
+    labels[label_mask] = label
+    return labels
+
+
+# ---------------------------------------------------------------------- RG --------
+def vector_angle(u, v):
+    """math_utils.vector_angle (utils/math_utils.py:9-18)."""
+    c = np.dot(u / np.linalg.norm(u), v / np.linalg.norm(v))
+    clip = np.minimum(1, np.maximum(c, -1))
+    return np.rad2deg(np.arccos(clip))
+
+
+def rg_setup(coords, max_nn=30, grow_region_knn=15, grow_region_radius=0.2, threshold_curve=1.0):
+    """Everything _region_growing derives from the cloud alone: kNN rows (KDTreeFlann),
+    normals (estimate_normals, region_growing.py:89-92) and the curvature seed test of every
+    point (region_growing.py:59-73,128-134)."""
+    knn = natives.knn(coords, grow_region_knn)
+    normals = natives.normals_hybrid(coords, grow_region_radius, max_nn)
+    cov = natives.cov6_to_matrix(natives.cov_knn(coords, knn))
+    with np.errstate(all='ignore'):
+        eig_val = np.linalg.eig(cov)[0]
+        curvature = eig_val[:, 0] / eig_val.sum(axis=1)
+        can_seed = curvature < threshold_curve
+    return knn, normals, can_seed
+
+
+def rg_literal_loop(knn, normals, seed_ids, can_seed, threshold_angle):
+    """The Python `while` loop of _region_growing, literally (region_growing.py:94-139)."""
+    list_of_seed_ids = list(seed_ids)
+    region = list(seed_ids)
+    processed = np.full(len(knn), False)
+    processed[list_of_seed_ids] = True
+    idx = 0
+    while idx < len(list_of_seed_ids):
+        seed = list_of_seed_ids[idx]
+        seed_normal = normals[seed]
+        row = knn[seed]
+        k = int(np.count_nonzero(row >= 0))
+        neighbor_idx = row[1:k]
+        for neighbor_id in neighbor_idx:
+            if processed[neighbor_id]:
+                continue
+            current_angle = vector_angle(seed_normal, normals[neighbor_id])
+            if current_angle < threshold_angle:
+                region.append(neighbor_id)
+                processed[neighbor_id] = True
+                if can_seed[neighbor_id]:
+                    list_of_seed_ids.append(neighbor_id)
+        idx = idx + 1
+    out = np.zeros(len(knn), dtype=bool)
+    out[region] = True
+    return out
+
+
+def region_growing_labels(points, labels, label, exclude_labels=(), threshold_angle=20,
+                          threshold_curve=1.0, max_nn=30, grow_region_knn=15, grow_region_radius=0.2,
+                          literal=False, angle_tol=0.0, return_near=False):
+    """RegionGrowing.get_labels (region_growing/region_growing.py:143-170)."""
+    mask = np.ones((len(labels),), dtype=bool)
+    for exclude_label in exclude_labels:
+        mask = mask & (labels != exclude_label)
+    seed_ids = np.where(labels[mask] == label)[0]
+    mask_indices = np.where(mask)[0]
+    label_mask = np.zeros(len(mask), dtype=bool)
+    near_full = np.zeros(len(mask), dtype=bool)
+    if len(mask_indices) > 0 and len(seed_ids) > 0:
+        coords = np.ascontiguousarray(points[mask, :3])
+        knn, normals, can_seed = rg_setup(coords, max_nn, grow_region_knn, grow_region_radius,
+                                          threshold_curve)
+        if literal:
+            region = rg_literal_loop(knn, normals, seed_ids.tolist(), can_seed, threshold_angle)
+            near = np.zeros(len(coords), dtype=bool)
+        else:
+            seed = np.zeros(len(coords), dtype=np.uint8)
+            seed[seed_ids] = 1
+            region, near = natives.region_grow(knn, normals, seed, can_seed, threshold_angle, angle_tol)
+        label_mask[mask_indices[region]] = True
+        near_full[mask_indices[near]] = True
+    labels[label_mask] = label
+    if return_near:
+        return labels, near_full
+    return labels
+
+
+# ---------------------------------------------------------------- pipeline --------
+def process_cloud(processors, points, labels):
+    """Pipeline.process_cloud (pipeline.py:63-97): each processor is a callable
+    (points, labels, mask) -> labels and sees mask = (labels == 0)."""
+    for proc in processors:
+        mask = (labels == 0)
+        labels = proc(points, labels, mask)
+    return labels
+
+
+def label_histogram(labels):
+    """analysis_tools.get_label_stats counts (analysis/analysis_tools.py:8-18) as int64[256]."""
+    vals, counts = np.unique(labels, return_counts=True)
+    hist = np.zeros(256, dtype=np.int64)
+    for v, c in zip(vals, counts):
+        hist[int(v) if 0 <= int(v) <= 255 else 255] += c
+    return hist
+
+
+def canonical_components(comp):
+    """Relabel component ids by the minimum point index of each component; -1 stays -1."""
+    comp = np.asarray(comp)
+    out = np.full(comp.shape, -1, dtype=np.int64)
+    valid = comp >= 0
+    if not valid.any():
+        return out
+    ids = comp[valid].astype(np.int64)
+    idx = np.where(valid)[0]
+    first = np.full(ids.max() + 1, np.iinfo(np.int64).max, dtype=np.int64)
+    np.minimum.at(first, ids, idx)
+    out[valid] = first[ids]
+    return out

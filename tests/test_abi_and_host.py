@@ -1,0 +1,224 @@
+"""CPU: the C-ABI library loads and exports every symbol include/upcp_cuda.h declares, the
+product refuses to run without a GPU (no CPU fallback), and the host-side logic (PIP plan
+builder, octree parameters, readers, synthetic generator, device arithmetic compiled for
+the host) agrees with the oracle."""
+import ctypes
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, ROOT, has_cuda
+from oracle import natives, reference_py as R
+from urban_pointcloud_processing_b200 import _lib, synthetic
+from urban_pointcloud_processing_b200 import device as dev
+from urban_pointcloud_processing_b200.utils import ahn_utils, bgt_utils, las_utils, math_utils
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, 'include', 'upcp_cuda.h')).read()
+    declared = set(re.findall(r'\b(upcp_[a-z0-9_]+)\s*\(', header))
+    declared -= {'upcp_pip_plan'}
+    assert len(declared) >= 35
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in sorted(declared):
+        assert hasattr(lib, name), f'{name} declared in include/upcp_cuda.h but not exported'
+    # and the ctypes prototypes cover exactly the declared entry points
+    assert declared == set(_lib.EXPORTED_SYMBOLS)
+    assert _lib.load().upcp_abi_version() == 1
+
+
+def test_no_reference_or_oracle_imports_in_product():
+    pkg = os.path.join(ROOT, 'urban_pointcloud_processing_b200')
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(('.py', '.cu', '.cuh')):
+                src = open(os.path.join(dirpath, f)).read()
+                assert 'import oracle' not in src and 'from oracle' not in src, f
+                assert '/root/reference' not in src, f
+
+
+@pytest.mark.skipif(has_cuda(), reason='checks the no-GPU behaviour')
+def test_compute_fails_loudly_without_gpu():
+    pts = np.zeros((4, 3))
+    with pytest.raises(_lib.UpcpCudaError):
+        dev.DeviceTile(pts)
+    lib = _lib.load()
+    assert lib.upcp_device_count() == 0
+    # a compute entry point called directly returns UPCP_E_CUDA, it does not compute on the CPU
+    st = lib.upcp_labels_assign(None, 8, None, 1, None)
+    assert st == -2 and b'upcp' not in lib.upcp_last_error()[:0]
+
+
+def test_pip_plan_builder_host():
+    tile = synthetic.make_tile(100, seed=1)
+    ring_xy, off, poly, hole = dev.rings_from_polygons(tile['building_polygons'])
+    assert off[-1] == len(ring_xy) and hole.sum() == 3 and poly.max() == 7
+    lib = _lib.load()
+    handle = ctypes.c_void_p()
+    st = lib.upcp_pip_plan_create(ring_xy.ctypes.data_as(ctypes.c_void_p), off.ctypes.data_as(ctypes.c_void_p),
+                                  poly.ctypes.data_as(ctypes.c_void_p), hole.ctypes.data_as(ctypes.c_void_p),
+                                  len(poly), 0, ctypes.byref(handle))
+    assert st == 0 and handle.value
+    assert lib.upcp_pip_plan_bytes(handle) > 4096
+    lib.upcp_pip_plan_destroy(handle)
+    # invalid input: a polygon whose first ring is a hole
+    bad_hole = hole.copy(); bad_hole[0] = 1
+    st = lib.upcp_pip_plan_create(ring_xy.ctypes.data_as(ctypes.c_void_p), off.ctypes.data_as(ctypes.c_void_p),
+                                  poly.ctypes.data_as(ctypes.c_void_p), bad_hole.ctypes.data_as(ctypes.c_void_p),
+                                  len(poly), 0, ctypes.byref(handle))
+    assert st == -1 and b'exterior' in lib.upcp_last_error()
+
+
+def test_octree_helpers_match_oracle(golden):
+    lib = _lib.load()
+    g = golden('scalars_golden.npz')
+    for e, gs, lvl in zip(g['extent'], g['grid_size'], g['level']):
+        bbox = (ctypes.c_double * 6)(0, 0, 0, e, e * 0.3, 0)
+        assert lib.upcp_octree_level(bbox, 3, float(gs)) == lvl
+    rng = np.random.default_rng(3)
+    for scale, org in ((50, (119300, 485100, 0)), (1.0, (119300, 485100, 3)), (1e-4, (0, 0, 0)), (300, (1e6, 2e6, -5))):
+        pts = rng.random((500, 3)) * scale + np.array(org)
+        f32 = pts.astype(np.float32)
+        want = natives.octree_params(f32[:, 0], f32[:, 1], f32[:, 2])
+        bbox = (ctypes.c_double * 6)(*pts.min(0), *pts.max(0))
+        out = (ctypes.c_float * 4)()
+        assert lib.upcp_octree_params(bbox, 21, out) == 0
+        assert np.array_equal(np.array(out[:], dtype=np.float32), want)
+
+
+@pytest.fixture(scope='module')
+def emu():
+    out = os.path.join(ROOT, 'tests', 'host_emu', '_emu.so')
+    src = os.path.join(ROOT, 'tests', 'host_emu', 'emu.cpp')
+    hdr = os.path.join(ROOT, 'urban_pointcloud_processing_b200', 'csrc', 'upcp_math.cuh')
+    if not os.path.exists(out) or os.path.getmtime(out) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+        subprocess.check_call(['g++', '-O2', '-ffp-contract=off', '-fno-fast-math', '-fPIC', '-shared', '-x', 'c++',
+                               src, '-o', out, '-lm'])
+    return ctypes.CDLL(out)
+
+
+def _p(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def test_device_math_pip_matches_oracle(emu, golden):
+    g = golden('pip_golden.npz')
+    for name in ('bgt_roads', 'handmade', 'lattice'):
+        pts = np.ascontiguousarray(g[f'{name}__points'])
+        xy, off = g[f'{name}__ring_xy'], g[f'{name}__ring_off']
+        px, py = np.ascontiguousarray(pts[:, 0]), np.ascontiguousarray(pts[:, 1])
+        for r in range(len(off) - 1):
+            ring = np.ascontiguousarray(xy[off[r]:off[r + 1]])
+            if len(ring) < 2:
+                continue
+            out = np.zeros(len(pts), dtype=np.uint8)
+            emu.emu_pip_ring(_p(ring), len(ring), _p(px), _p(py), ctypes.c_long(len(pts)), _p(out))
+            assert np.array_equal(out.view(bool), natives.is_inside(px, py, ring)), (name, r)
+
+
+def test_device_math_digitize_matches_numpy(emu, golden):
+    g = golden('raster_golden.npz')
+    ahn = np.load(os.path.join(GOLDEN, 'demo', 'ahn_2386_9702.npz'))
+    gx, gy = ahn['x'], ahn['y']
+    bx = np.ascontiguousarray(gx - (gx[1] - gx[0]) / 2)
+    by = np.ascontiguousarray(gy + (gy[0] - gy[1]) / 2)
+    pts = g['points']
+    px, py = np.ascontiguousarray(pts[:, 0]), np.ascontiguousarray(pts[:, 1])
+    ix = np.zeros(len(pts), dtype=np.int32); iy = np.zeros(len(pts), dtype=np.int32)
+    emu.emu_digitize(_p(bx), len(bx), _p(by), len(by), _p(px), _p(py), ctypes.c_long(len(pts)), _p(ix), _p(iy))
+    wx = np.digitize(px, bx) - 1; wy = np.digitize(py, by, right=True) - 1
+    assert np.array_equal(ix, np.where(wx < 0, len(bx) - 1, wx))
+    assert np.array_equal(iy, np.where(wy < 0, len(by) - 1, wy))
+    for guess in (-5, 0, 250, 499, 9999):     # the fix-up must not depend on the first guess
+        emu.emu_digitize_badguess(_p(bx), len(bx), _p(by), len(by), _p(px), _p(py), ctypes.c_long(len(pts)),
+                                  guess, _p(ix), _p(iy))
+        assert np.array_equal(ix, np.where(wx < 0, len(bx) - 1, wx))
+        assert np.array_equal(iy, np.where(wy < 0, len(by) - 1, wy))
+
+
+def test_device_math_classify(emu):
+    rng = np.random.default_rng(1)
+    z = rng.normal(0, 1, 4000); v = rng.normal(0, 1, 4000)
+    v[::7] = np.nan; v[::11] = np.inf
+    z[::13] = v[::13] + 0.2          # exactly on the threshold
+    a, b = 0.2, 0.7
+    with np.errstate(invalid='ignore'):
+        want = {0: np.abs(z - v) < a, 1: z < v + a, 2: ~np.isfinite(v) | (z <= v + a),
+                3: (z > v + a) & (z <= v + b), 4: (z <= v + b) & (z >= v - a), 5: (z - v) < -a}
+    for mode, w in want.items():
+        out = np.zeros(len(z), dtype=np.uint8)
+        emu.emu_classify(mode, _p(z), _p(v), ctypes.c_long(len(z)), ctypes.c_double(a), ctypes.c_double(b), _p(out))
+        assert np.array_equal(out.view(bool), w), mode
+    out = np.zeros(len(z), dtype=np.uint8)
+    emu.emu_classify(3, _p(z), _p(v), ctypes.c_long(len(z)), ctypes.c_double(-np.inf), ctypes.c_double(np.inf), _p(out))
+    with np.errstate(invalid='ignore'):
+        assert np.array_equal(out.view(bool), (z > v - np.inf) & (z <= v + np.inf))
+
+
+def test_device_math_eigen_cov_angle_match_oracle(emu):
+    rng = np.random.default_rng(2)
+    pts = np.ascontiguousarray(rng.normal(size=(3000, 3)) * np.array([0.05, 0.05, 0.005]) + np.array([119320.0, 485120.0, 2.0]))
+    knn = natives.knn(pts, 15)
+    cov = natives.cov_knn(pts, knn)
+    mine = np.zeros(6)
+    for i in (0, 17, 2999):
+        emu.emu_cov(_p(pts), _p(np.ascontiguousarray(knn[i])), 15, _p(mine))
+        assert np.array_equal(mine, cov[i])
+    # FastEigen3x3: general, planar (rank 2), diagonal, zero matrices
+    special = np.array([[1, 0, 0, 2, 0, 3], [2, 0, 0, 2, 0, 1], [0, 0, 0, 0, 0, 0], [1, 1, 0, 1, 0, 0],
+                        [1e-3, 2e-4, 0, 5e-4, 0, 0], [4, 0, 0, 4, 0, 4]], dtype=np.float64)
+    allc = np.ascontiguousarray(np.vstack([cov, special]))
+    want = natives.fast_eigen(allc)
+    want[np.linalg.norm(want, axis=1) == 0] = (0, 0, 1)
+    got = np.zeros_like(want)
+    emu.emu_normal_from_cov(_p(allc), ctypes.c_long(len(allc)), _p(got), None)
+    assert np.array_equal(got, want)
+    u = rng.normal(size=(500, 3)); v = rng.normal(size=(500, 3))
+    out = np.zeros(500)
+    emu.emu_angle(_p(np.ascontiguousarray(u)), _p(np.ascontiguousarray(v)), ctypes.c_long(500), _p(out))
+    want = np.array([R.vector_angle(a, b) for a, b in zip(u, v)])
+    np.testing.assert_allclose(out, want, rtol=0, atol=1e-9)
+
+
+def test_device_math_octree_pos(emu):
+    rng = np.random.default_rng(4)
+    pts = (rng.random(5000) * 50 + 485100).astype(np.float32)
+    p4 = natives.octree_params(pts, pts, pts)
+    out = np.zeros(len(pts), dtype=np.int32)
+    emu.emu_octree_pos(_p(pts), ctypes.c_long(len(pts)), ctypes.c_float(p4[1]), ctypes.c_float(p4[3]), (1 << 21) - 1, _p(out))
+    t = (pts - p4[1]) / p4[3]
+    assert t.dtype == np.float32
+    assert np.array_equal(out, np.clip(t.astype(np.int64), 0, (1 << 21) - 1))
+
+
+def test_readers_on_demo_data():
+    reader = ahn_utils.NPZReader(os.path.join(GOLDEN, 'demo'))
+    t = reader.filter_tile('2386_9702')
+    assert t['ground_surface'].shape == (500, 500) and t['ground_surface'].dtype == np.float64
+    with pytest.raises(ahn_utils.AHNFileNotFoundError):
+        reader.filter_tile('0000_0000')
+    bld = bgt_utils.BGTPolyReader(bgt_file=os.path.join(GOLDEN, 'demo', 'bgt_buildings_demo.csv'))
+    polys = bld.filter_tile('2386_9702', bgt_types=['pand'], merge=True)
+    assert len(polys) == 7 and sum(len(p.exterior.coords) for p in polys) == 179
+    road = bgt_utils.BGTPolyReader(bgt_file=os.path.join(GOLDEN, 'demo', 'bgt_roads_demo.csv'))
+    assert len(road.filter_tile('2386_9702', bgt_types=['rijbaan_lokale_weg', 'parkeervlak', 'fietspad'])) == 15
+    assert len(road.filter_tile('2386_9702', bgt_types=['fietspad'])) < 15
+    if not bgt_utils.HAVE_SHAPELY:
+        with pytest.raises(NotImplementedError):
+            bld.filter_tile('2386_9702', offset=0.25)
+    assert las_utils.get_bbox_from_tile_code('2386_9702') == ((119300, 485150), (119350, 485100))
+    assert las_utils.get_tilecode_from_filename('filtered_2386_9702.laz') == '2386_9702'
+    assert math_utils.get_octree_level(np.array([[0, 0, 0], [50., 20, 3]]), 0.05) == 10
+
+
+def test_synthetic_generator_is_deterministic():
+    a = synthetic.make_tile(5000, seed=42)
+    b = synthetic.make_tile(5000, seed=42)
+    assert np.array_equal(a['points'], b['points']) and a['points'].flags.f_contiguous
+    assert np.all(np.abs(a['points'] * 1000 - np.round(a['points'] * 1000)) < 1e-6)
+    c = synthetic.make_tile(5000, seed=43)
+    assert not np.array_equal(a['points'], c['points'])
+    assert len(synthetic.make_polygon_lattice(n_side=5)) == 25

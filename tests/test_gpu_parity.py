@@ -1,0 +1,402 @@
+"""GPU: parity of the CUDA path (through the C ABI / the drop-in processors) with the oracle
+and with the golden vectors generated from the real reference code.
+
+Bar: bit-exact for masks, labels, indices, component membership (after canonical
+relabelling) and region membership; floating point outputs (raster values, squared
+distances, covariances) bit-exact, normals within 1e-9 (device acos/cos vs glibc), with
+points whose angle test lies within 1e-6 degrees of the threshold counted and excluded.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN, from_mm, unpack
+from oracle import natives, reference_py as R
+from test_oracle_golden import PIP_CASES, polygons_from_golden
+from urban_pointcloud_processing_b200 import _lib, synthetic
+from urban_pointcloud_processing_b200 import device as dev
+from urban_pointcloud_processing_b200.fusion import AHNFuser, BGTBuildingFuser, BGTRoadFuser, NoiseFilter
+from urban_pointcloud_processing_b200.labels import Labels
+from urban_pointcloud_processing_b200.pipeline import Pipeline
+from urban_pointcloud_processing_b200.region_growing import LabelConnectedComp, LayerLCC
+from urban_pointcloud_processing_b200.region_growing import region_growing as rgmod
+from urban_pointcloud_processing_b200.region_growing.region_growing import RegionGrowing
+from urban_pointcloud_processing_b200.utils import ahn_utils, bgt_utils, clip_utils
+from urban_pointcloud_processing_b200.utils.bgt_utils import RingPolygon
+from urban_pointcloud_processing_b200.utils.interpolation import FastGridInterpolator
+
+pytestmark = pytest.mark.gpu
+
+
+def readers_for(tile, drop_holes=False):
+    blds = tile['building_polygons']
+    if drop_holes:
+        blds = [RingPolygon(np.array(p.exterior.coords)) for p in blds]
+    tc = tile['tilecode']
+    ahn = ahn_utils.ArrayAHNReader({tc: tile['ahn_tile']})
+    bld = bgt_utils.ArrayBGTReader({tc: blds}, {tc: ['pand'] * len(blds)})
+    road = bgt_utils.ArrayBGTReader({tc: tile['road_polygons']}, {tc: ['rijbaan_lokale_weg', 'fietspad']})
+    return ahn, bld, road
+
+
+# ------------------------------------------------------------------ tile / masks ---
+def test_tile_upload_layouts_and_bbox():
+    rng = np.random.default_rng(0)
+    pts_c = np.ascontiguousarray(rng.random((10007, 3)) * 50 + np.array([119300, 485100, -2]))
+    for pts in (pts_c, np.asfortranarray(pts_c), pts_c[::2], pts_c[:, :2].copy()):
+        t = dev.DeviceTile(pts)
+        assert np.array_equal(t.x.cpu().numpy(), pts[:, 0]) and np.array_equal(t.y.cpu().numpy(), pts[:, 1])
+        if pts.shape[1] == 3:
+            assert np.array_equal(t.z.cpu().numpy(), pts[:, 2])
+        else:
+            assert not t.z.cpu().numpy().any()
+    t = dev.DeviceTile(pts_c)
+    sel = rng.random(len(pts_c)) < 0.3
+    ball, bsel, m = t.bbox(dev.upload_mask(sel, t.n, t.device))
+    assert np.array_equal(ball, np.concatenate([pts_c.min(0), pts_c.max(0)]))
+    assert np.array_equal(bsel, np.concatenate([pts_c[sel].min(0), pts_c[sel].max(0)])) and m == sel.sum()
+    # tile cache: same live array -> same HBM copy; different array -> new upload
+    a = dev.get_tile(pts_c)
+    assert dev.get_tile(pts_c) is a and dev.get_tile(pts_c.copy()) is not a
+
+
+def test_mask_and_label_kernels():
+    rng = np.random.default_rng(1)
+    n = 100003
+    device = dev.current_device()
+    for dtype in (np.uint16, np.uint8, np.int64):
+        labels = rng.choice(np.array([0, 1, 9, 10, 40, 99]), size=n).astype(dtype)
+        mask = rng.random(n) < 0.5
+        d_labels = dev.upload_labels(labels, device)
+        d_mask = dev.upload_mask(mask, n, device)
+        assert np.array_equal(d_labels.cpu().numpy(), labels.astype(np.int32))
+        got = dev.download_mask(dev.mask_build(d_labels, d_mask, eq=(10, 99), ne=(9,)))
+        assert np.array_equal(got, (mask | (labels == 10) | (labels == 99)) & (labels != 9))
+        got = dev.download_mask(dev.mask_build(d_labels, None, base=True, ne=(9, 1)))
+        assert np.array_equal(got, (labels != 9) & (labels != 1))
+        got = dev.download_mask(dev.mask_build(d_labels, None, base=False, eq=(0,)))
+        assert np.array_equal(got, labels == 0)
+        other = dev.upload_mask(rng.random(n) < 0.5, n, device)
+        for op, f in (('and', np.logical_and), ('or', np.logical_or), ('andnot', lambda a, b: a & ~b)):
+            assert np.array_equal(dev.download_mask(dev.mask_combine(d_mask, other, op)),
+                                  f(mask, dev.download_mask(other)))
+        assert dev.mask_count(d_mask) == mask.sum()
+        dev.labels_assign(d_labels, d_mask, 62)
+        want = labels.copy(); want[mask] = 62
+        host = labels.copy()
+        assert dev.download_labels(d_labels, host) is host and np.array_equal(host, want)
+        assert np.array_equal(dev.label_hist(d_labels).cpu().numpy(), R.label_histogram(want))
+
+
+# ------------------------------------------------------------------------ raster ---
+def test_raster_lookup_matches_reference_golden(golden):
+    g = golden('raster_golden.npz')
+    ahn = np.load(os.path.join(GOLDEN, 'demo', 'ahn_2386_9702.npz'))
+    for surface, key in (('ground_surface', 'ground'), ('building_surface', 'building')):
+        got = FastGridInterpolator(ahn['x'], ahn['y'], ahn[key].astype(float))(g['points'])
+        assert np.array_equal(got, g[surface], equal_nan=True)
+
+
+def test_raster_classify_modes_match_oracle():
+    tile = synthetic.make_tile(300000, seed=5)
+    pts, ahn = tile['points'], tile['ahn_tile']
+    t = dev.DeviceTile(pts)
+    rng = np.random.default_rng(2)
+    sel = rng.random(len(pts)) < 0.7
+    d_sel = dev.upload_mask(sel, t.n, t.device)
+    for surface in ('ground_surface', 'building_surface'):
+        raster = dev.DeviceRaster(ahn['x'], ahn['y'], ahn[surface])
+        v = R.fast_grid_lookup(ahn['x'], ahn['y'], ahn[surface], pts)
+        assert np.array_equal(raster.lookup(t).cpu().numpy(), v, equal_nan=True)
+        z = pts[:, 2]
+        with np.errstate(invalid='ignore'):
+            want = {(_lib.CLS_ABS_LT, 0.2, 0): np.abs(z - v) < 0.2, (_lib.CLS_LT, 0.2, 0): z < v + 0.2,
+                    (_lib.CLS_CAP_LE, 0.2, 0): ~np.isfinite(v) | (z <= v + 0.2),
+                    (_lib.CLS_BAND_OC, 0.5, 12.0): (z > v + 0.5) & (z <= v + 12.0),
+                    (_lib.CLS_BAND_OC, -np.inf, 1.75): (z > v - np.inf) & (z <= v + 1.75),
+                    (_lib.CLS_BAND_CC, 0.02, 0.5): (z <= v + 0.5) & (z >= v - 0.02),
+                    (_lib.CLS_BELOW_NEG, 0.2, 0): (z - v) < -0.2}
+        for (mode, a, b), w in want.items():
+            got = dev.download_mask(raster.classify(t, mode, a=a, b=b, d_sel=d_sel))
+            assert np.array_equal(got, w & sel), (surface, mode)
+    # fused label write
+    d_labels = torch.zeros(t.n, dtype=torch.int32, device=t.device)
+    raster.classify(t, _lib.CLS_LT, a=0.2, d_sel=d_sel, d_labels=d_labels, assign=7, want_mask=False)
+    with np.errstate(invalid='ignore'):
+        assert np.array_equal(d_labels.cpu().numpy() == 7, (pts[:, 2] < v + 0.2) & sel)
+
+
+# --------------------------------------------------------------------------- PIP ---
+@pytest.mark.parametrize('name', PIP_CASES)
+def test_pip_matches_reference_golden(golden, name):
+    g = golden('pip_golden.npz')
+    pts = np.ascontiguousarray(g[f'{name}__points'])
+    expected = unpack(g[f'{name}__expected'], int(g[f'{name}__n']))
+    polys = polygons_from_golden(g, name)
+    t = dev.DeviceTile(pts)
+    for grid_dim in (0, 7, 300):            # the acceleration grid must not change the result
+        got = dev.download_mask(dev.PipPlan(polys, grid_dim=grid_dim).query(t))
+        assert np.array_equal(got, expected), (name, grid_dim)
+    one = np.zeros(len(pts), dtype=bool)
+    for p in polys[:5]:
+        one |= clip_utils.poly_clip(pts, p)          # the poly_clip drop-in, polygon by polygon
+    ref = np.zeros(len(pts), dtype=bool)
+    for p in polys[:5]:
+        ref |= R.poly_clip(pts, p)
+    assert np.array_equal(one, ref)
+
+
+def test_pip_lattice_5000_polygons_matches_oracle():
+    polys = synthetic.make_polygon_lattice()
+    tile = synthetic.make_tile(400000, seed=9)
+    pts = tile['points']
+    rng = np.random.default_rng(3)
+    sel = rng.random(len(pts)) < 0.9
+    t = dev.DeviceTile(pts)
+    got = dev.download_mask(dev.PipPlan(polys).query(t, dev.upload_mask(sel, t.n, t.device)))
+    want = np.zeros(len(pts), dtype=bool)
+    sub = pts[sel]
+    acc = np.zeros(len(sub), dtype=bool)
+    for p in polys:
+        acc |= R.poly_clip(sub, p)
+    want[sel] = acc
+    assert np.array_equal(got, want) and want.sum() > 1000
+
+
+# -------------------------------------------------------------------------- sort ---
+@pytest.mark.parametrize('n', [1, 31, 4096, 4097, 300001])
+@pytest.mark.parametrize('bits,dtype', [(30, np.uint32), (32, np.uint32), (7, np.uint32), (63, np.uint64), (33, np.uint64)])
+def test_radix_sort_pairs(n, bits, dtype):
+    lib = _lib.load()
+    rng = np.random.default_rng(n + bits)
+    keys = rng.integers(0, 2 ** bits, size=n, dtype=np.uint64).astype(dtype)
+    keys[::3] = keys[0]                                # many duplicates: stability matters
+    vals = np.arange(n, dtype=np.uint32)
+    device = dev.current_device()
+    tdt = torch.int32 if dtype == np.uint32 else torch.int64
+    k_in = torch.from_numpy(keys.view(np.int32 if dtype == np.uint32 else np.int64)).to(device)
+    v_in = torch.from_numpy(vals.view(np.int32)).to(device)
+    k_out = torch.empty(n, dtype=tdt, device=device); v_out = torch.empty(n, dtype=torch.int32, device=device)
+    ws = torch.empty(lib.upcp_sort_ws_bytes(n), dtype=torch.uint8, device=device)
+    fn = lib.upcp_sort_pairs_u32 if dtype == np.uint32 else lib.upcp_sort_pairs_u64
+    _lib.check(fn(dev.ptr(k_in), dev.ptr(v_in), dev.ptr(k_out), dev.ptr(v_out), n, bits, dev.ptr(ws), ws.numel(),
+                  dev.stream_ptr()))
+    order = np.argsort(keys, kind='stable')
+    assert np.array_equal(k_out.cpu().numpy().view(dtype), keys[order])
+    assert np.array_equal(v_out.cpu().numpy().view(np.uint32), vals[order])
+
+
+# ---------------------------------------------------------------------------- CC ---
+@pytest.mark.parametrize('grid_size,min_size', [(0.4, 20), (0.1, 100), (0.05, 10), (0.02, 5)])
+def test_lcc_components_match_oracle(grid_size, min_size):
+    tile = synthetic.make_tile(200000, seed=21)
+    pts = tile['points'][tile['kind'] != 0]            # non-ground cloud (config 2 shape)
+    lcc = LabelConnectedComp(grid_size=grid_size, min_component_size=min_size)
+    got = lcc.get_components(pts)
+    want = R.lcc_get_components(pts, grid_size, min_size)
+    assert lcc.octree_level == R.get_octree_level(pts, grid_size)
+    assert got.shape == want.shape and got.dtype == np.float64
+    assert np.array_equal(R.canonical_components(got), R.canonical_components(want))
+    assert (want >= 0).any() and (want < 0).any()
+
+
+def test_lcc_label_mask_matches_oracle_and_mutates_labels():
+    tile = synthetic.make_tile(250000, seed=22)
+    pts = tile['points']
+    rng = np.random.default_rng(4)
+    labels = np.zeros(len(pts), dtype=np.uint16)
+    labels[tile['kind'] == 0] = Labels.GROUND
+    cars = np.where(tile['kind'] == 2)[0]
+    labels[cars[rng.random(len(cars)) < 0.05]] = Labels.CAR
+    for kwargs in (dict(grid_size=0.1, min_component_size=50, threshold=0.01),
+                   dict(grid_size=0.05, min_component_size=100, threshold=0.1),
+                   dict(exclude_labels=[Labels.GROUND], grid_size=0.2, min_component_size=10, threshold=0.03)):
+        mask = (labels == 0) & (rng.random(len(pts)) < 0.9)
+        l1, l2 = labels.copy(), labels.copy()
+        got = LabelConnectedComp(Labels.CAR, **kwargs).get_label_mask(pts, l1, mask)
+        want = R.lcc_get_label_mask(pts, l2, mask, Labels.CAR, **kwargs)
+        assert np.array_equal(got, want) and want.any()
+        assert np.array_equal(l1 == Labels.CAR, (labels == Labels.CAR) | want)     # :128-129 side effect
+
+
+def test_lcc_edge_cases():
+    lcc = LabelConnectedComp(7, grid_size=0.1, min_component_size=1, threshold=0.0)
+    # 2-D input (z assumed 0), a single point, an empty selection, identical points
+    pts2 = np.random.default_rng(5).random((5000, 2)) * 3 + np.array([119300.0, 485100.0])
+    got = LabelConnectedComp(grid_size=0.1, min_component_size=3).get_components(pts2)
+    assert np.array_equal(R.canonical_components(got), R.canonical_components(R.lcc_get_components(pts2, 0.1, 3)))
+    one = np.array([[119300.5, 485100.5, 1.0]])
+    assert R.canonical_components(lcc.get_components(one)).tolist() == [0]
+    same = np.repeat(one, 50, axis=0)
+    assert (R.canonical_components(LabelConnectedComp(grid_size=0.1, min_component_size=10).get_components(same)) == 0).all()
+    labels = np.zeros(5, dtype=np.uint16)
+    m = lcc.get_label_mask(np.repeat(one, 5, axis=0) + np.arange(5)[:, None], labels, np.zeros(5, dtype=bool))
+    assert not m.any()
+
+
+def test_lcc_permutation_invariance_and_level_boundaries():
+    tile = synthetic.make_tile(120000, seed=23)
+    pts = tile['points'][tile['kind'] >= 2]
+    perm = np.random.default_rng(6).permutation(len(pts))
+    lcc = LabelConnectedComp(grid_size=0.2, min_component_size=15)
+    a = lcc.get_components(pts)
+    b = lcc.get_components(pts[perm])
+    # same partition of the same points, whatever the input order (b[j] belongs to point perm[j])
+    b_orig = np.empty_like(b); b_orig[perm] = b
+    assert np.array_equal(R.canonical_components(a), R.canonical_components(b_orig))
+    assert (a >= 0).any() and (a < 0).any()
+
+
+# ------------------------------------------------------------- pipeline (golden) ---
+def test_pipeline_stages_match_reference_golden(golden):
+    g = golden('pipeline_golden.npz')
+    tile = synthetic.make_tile(int(g['n']), seed=int(g['seed']))
+    points = tile['points']
+    assert np.array_equal(points, from_mm(g['points_mm']))
+    tc = tile['tilecode']
+    ahn, bld, road = readers_for(tile, drop_holes=True)
+    stages = [
+        ('ahn_ground', AHNFuser(Labels.GROUND, ahn, target='ground', epsilon=0.2, refine_ground=False)),
+        ('bgt_road', BGTRoadFuser(Labels.ROAD, bgt_reader=road)),
+        ('bgt_building', BGTBuildingFuser(Labels.BUILDING, bgt_reader=bld, offset=0, ahn_reader=ahn)),
+        ('layer_lcc', LayerLCC(Labels.BUILDING, ahn, params=[{'bottom': 12., 'grid_size': 0.1, 'threshold': 0.5},
+                                                             {'bottom': 0., 'top': 12., 'grid_size': 0.05, 'threshold': 0.5}])),
+        ('lcc_car', LabelConnectedComp(Labels.CAR, grid_size=0.1, min_component_size=30, threshold=0.02)),
+        ('noise', NoiseFilter(Labels.NOISE, ahn, epsilon=0.2, min_component_size=10)),
+        ('region_growing', RegionGrowing(Labels.BUILDING, exclude_labels=(Labels.GROUND, Labels.ROAD))),
+    ]
+    labels = np.zeros(len(points), dtype=np.uint16)
+    for name, proc in stages:
+        if name == 'lcc_car':
+            labels[g['car_seed_ids']] = Labels.CAR
+        out = proc.get_labels(points, labels, labels == 0, tc)
+        assert out is labels                                        # in-place contract
+        assert np.array_equal(labels, g[f'labels_after_{name}']), name
+    comps = LabelConnectedComp(grid_size=0.2, min_component_size=20).get_components(points[tile['kind'] >= 2])
+    assert np.array_equal(R.canonical_components(comps), g['components_kind_ge2'])
+
+
+def test_pipeline_process_cloud_matches_stagewise(golden):
+    g = golden('pipeline_golden.npz')
+    tile = synthetic.make_tile(int(g['n']), seed=int(g['seed']))
+    ahn, bld, road = readers_for(tile, drop_holes=True)
+    procs = (AHNFuser(Labels.GROUND, ahn, target='ground', epsilon=0.2, refine_ground=False),
+             BGTRoadFuser(Labels.ROAD, bgt_reader=road),
+             BGTBuildingFuser(Labels.BUILDING, bgt_reader=bld, offset=0, ahn_reader=ahn),
+             LayerLCC(Labels.BUILDING, ahn, params=[{'bottom': 12., 'grid_size': 0.1, 'threshold': 0.5},
+                                                    {'bottom': 0., 'top': 12., 'grid_size': 0.05, 'threshold': 0.5}]))
+    labels = np.zeros(int(g['n']), dtype=np.uint16)
+    out = Pipeline(processors=procs, ahn_reader=ahn, caching=True).process_cloud(tile['tilecode'], tile['points'], labels)
+    assert out is labels and np.array_equal(labels, g['labels_after_layer_lcc'])
+    with pytest.raises(ValueError):
+        Pipeline(processors=procs, ahn_reader=None, caching=True)
+
+
+def test_demo_tile_matches_reference_golden(golden):
+    """configs[0] substitute: REAL demo AHN + BGT data of tile 2386_9702, reference pipeline."""
+    g = golden('demo_golden.npz')
+    points = np.asfortranarray(from_mm(g['points_mm']))
+    demo = os.path.join(GOLDEN, 'demo')
+    ahn = ahn_utils.NPZReader(demo)
+    bld = bgt_utils.BGTPolyReader(bgt_file=os.path.join(demo, 'bgt_buildings_demo.csv'))
+    road = bgt_utils.BGTPolyReader(bgt_file=os.path.join(demo, 'bgt_roads_demo.csv'))
+    procs = (AHNFuser(Labels.GROUND, ahn, target='ground', epsilon=0.2, refine_ground=False),
+             BGTRoadFuser(Labels.ROAD, bgt_reader=road),
+             BGTBuildingFuser(Labels.BUILDING, bgt_reader=bld, offset=0, ahn_reader=ahn))
+    labels = np.zeros(len(points), dtype=np.uint16)
+    Pipeline(processors=procs, ahn_reader=ahn, caching=True).process_cloud('2386_9702', points, labels)
+    assert np.array_equal(labels, g['labels'])
+    # the reader's own interpolate / cache path
+    gz = ahn.interpolate('2386_9702', points, None, 'ground_surface')
+    t = ahn.filter_tile('2386_9702')
+    assert np.array_equal(gz, R.fast_grid_lookup(t['x'], t['y'], t['ground_surface'], points), equal_nan=True)
+
+
+def test_layer_lcc_dense_matches_oracle():
+    """A cloud dense enough for the layers to actually grow (the 60 k golden tile is sparse)."""
+    tile = synthetic.make_tile(1500000, seed=31, facade_fraction=0.6)
+    pts = tile['points']
+    ahn, bld, road = readers_for(tile)
+    labels = np.zeros(len(pts), dtype=np.uint16)
+    labels = R.ahn_fuser_labels(pts, labels, labels == 0, tile['ahn_tile'], 9, 'ground', 0.2)
+    labels = R.building_fuser_labels(pts, labels, labels == 0, tile['building_polygons'], 10, tile['ahn_tile'], 0.2)
+    params = [{'bottom': 12., 'grid_size': 0.1, 'threshold': 0.5},
+              {'bottom': 0., 'top': 12., 'grid_size': 0.05, 'threshold': 0.5}]
+    want = R.layer_lcc_labels(pts, labels.copy(), labels == 0, tile['ahn_tile'], 10, [dict(p) for p in params])
+    got = LayerLCC(10, ahn, params=[dict(p) for p in params]).get_labels(pts, labels.copy(), labels == 0, tile['tilecode'])
+    assert np.array_equal(got, want)
+    assert np.count_nonzero(want == 10) > np.count_nonzero(labels == 10)
+
+
+# --------------------------------------------------------------- kNN / normals / RG ---
+def _rg_cloud(n, seed):
+    tile = synthetic.make_tile(n, seed=seed, facade_fraction=0.7)
+    pts = tile['points']
+    labels = np.zeros(len(pts), dtype=np.uint16)
+    labels = R.ahn_fuser_labels(pts, labels, labels == 0, tile['ahn_tile'], 9, 'ground', 0.2)
+    labels = R.building_fuser_labels(pts, labels, labels == 0, tile['building_polygons'], 10, tile['ahn_tile'], 0.2)
+    return tile, pts, labels
+
+
+@pytest.mark.parametrize('cell', [None, 0.05, 0.37])
+def test_knn_normals_cov_match_oracle(cell):
+    tile, pts, labels = _rg_cloud(150000, 41)
+    sel = labels != 9
+    coords = np.ascontiguousarray(pts[sel])
+    t = dev.DeviceTile(pts)
+    d_sel = dev.upload_mask(sel, t.n, t.device)
+    _, bbox_sel, m = t.bbox(d_sel)
+    d_knn, d_d2, d_nrm, d_cov, d_curv = rgmod.knn_normals_device(t, d_sel, m, bbox_sel, 15, 30, 0.2, cell_size=cell,
+                                                                 want_d2=True)
+    want_idx, want_d2 = natives.knn(coords, 15, want_d2=True)
+    assert np.array_equal(d_knn.cpu().numpy(), want_idx)
+    assert np.array_equal(d_d2.cpu().numpy(), want_d2)
+    assert np.array_equal(d_cov.cpu().numpy(), natives.cov_knn(coords, want_idx))
+    want_n = natives.normals_hybrid(coords, 0.2, 30)
+    got_n = d_nrm.cpu().numpy()
+    bad = np.abs(got_n - want_n).max(axis=1) > 1e-9
+    assert bad.sum() == 0, f'{bad.sum()} normals differ by more than 1e-9'
+    print(f'normals bit-identical: {np.mean((got_n == want_n).all(axis=1)):.4f}')
+
+
+def test_knn_small_and_degenerate_clouds():
+    rng = np.random.default_rng(7)
+    for pts in (rng.random((7, 3)), np.round(rng.random((3000, 3)) * 2, 1), np.repeat(rng.random((1, 3)), 40, axis=0),
+                np.column_stack((np.arange(200) * 0.01, np.zeros(200), np.zeros(200)))):
+        pts = np.ascontiguousarray(pts + np.array([119300.0, 485100.0, 0.0]))
+        t = dev.DeviceTile(pts)
+        _, bbox, m = t.bbox(None)
+        d_knn, d_d2, d_nrm, d_cov, _ = rgmod.knn_normals_device(t, None, m, bbox, 15, 30, 0.2, want_d2=True)
+        want_idx, want_d2 = natives.knn(pts, 15, want_d2=True)
+        assert np.array_equal(d_knn.cpu().numpy(), want_idx)
+        assert np.array_equal(d_d2.cpu().numpy(), want_d2)
+        np.testing.assert_allclose(d_nrm.cpu().numpy(), natives.normals_hybrid(pts, 0.2, 30), rtol=0, atol=1e-9)
+
+
+@pytest.mark.parametrize('n,seed', [(60000, 51), (400000, 52)])
+def test_region_growing_matches_oracle(n, seed):
+    tile, pts, labels = _rg_cloud(n, seed)
+    want, near = R.region_growing_labels(pts, labels.copy(), 10, exclude_labels=(9,), angle_tol=1e-6, return_near=True)
+    rg = RegionGrowing(10, exclude_labels=(9,))
+    got = rg.get_labels(pts, labels.copy(), None, tile['tilecode'])
+    assert near.sum() == 0, f'{near.sum()} angle tests within 1e-6 deg of the threshold (excluded points)'
+    assert np.array_equal(got, want)
+    assert np.count_nonzero(want == 10) > np.count_nonzero(labels == 10)
+    assert rg.last_stats['n_curvature_on_host'] < 0.01 * rg.last_stats['n_selected']
+    # idempotence: growing again from the grown region changes nothing
+    again = RegionGrowing(10, exclude_labels=(9,)).get_labels(pts, got.copy(), None, tile['tilecode'])
+    assert np.array_equal(again, got)
+
+
+def test_region_growing_parameters_and_edge_cases():
+    tile, pts, labels = _rg_cloud(50000, 53)
+    for kw in (dict(threshold_angle=5), dict(threshold_angle=60, grow_region_knn=8, max_nn=12, grow_region_radius=0.5),
+               dict(threshold_curve=0.2)):
+        want = R.region_growing_labels(pts, labels.copy(), 10, exclude_labels=(9,), **kw)
+        got = RegionGrowing(10, exclude_labels=(9,), **kw).get_labels(pts, labels.copy(), None, tile['tilecode'])
+        assert np.array_equal(got, want), kw
+    # no seeds -> unchanged; antiparallel normals are NOT merged (vector_angle has no abs)
+    l0 = np.where(labels == 10, 0, labels)
+    assert np.array_equal(RegionGrowing(10, exclude_labels=(9,)).get_labels(pts, l0.copy(), None, ''), l0)

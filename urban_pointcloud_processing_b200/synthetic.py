@@ -1,0 +1,219 @@
+"""Synthetic urban tiles: 50 x 50 m tile in RD coordinates with
+ground, facades (+ balconies), cars, street furniture / tree crowns, clutter and uniform
+noise, a matching AHN raster (ground / building surfaces, float16, NaN holes) and BGT-like
+building / road polygons.  Used by the tests, the golden-vector generator and bench.py;
+the real demo clouds of the reference are not part of its checkout.
+
+Coordinates are quantised to the LAS grid (multiples of 0.001 m, offset 0), float64.
+"""
+import numpy as np
+
+from .utils.bgt_utils import RingPolygon
+
+TILE_ORIGIN = (119300.0, 485100.0)      # tile code 2386_9702
+TILE_SIZE = 50.0
+
+
+def tilecode_for(origin=TILE_ORIGIN):
+    return f'{int(origin[0] // 50)}_{int(origin[1] // 50)}'
+
+
+def _ground_z(x, y, origin):
+    u = (x - origin[0]) / TILE_SIZE
+    v = (y - origin[1]) / TILE_SIZE
+    return 0.6 + 0.3 * np.sin(2 * np.pi * u * 1.5) * np.cos(2 * np.pi * v) + 0.15 * np.sin(2 * np.pi * (u + v) * 2.0)
+
+
+def _quantise(a):
+    return np.round(a * 1000.0) * 0.001
+
+
+def make_buildings(rng, origin, n_buildings=8):
+    """Axis-aligned building boxes on a jittered 3 x 3 layout (one slot left for the crossing)."""
+    slots = [(i, j) for i in range(3) for j in range(3) if not (i == 1 and j == 1)]
+    rng.shuffle(slots)
+    boxes = []
+    for (i, j) in slots[:n_buildings]:
+        w = rng.uniform(8.0, 13.0)
+        d = rng.uniform(8.0, 13.0)
+        cx = origin[0] + 2.0 + i * 17.0 + rng.uniform(0.5, 14.0 - w + 0.5) + w / 2 - 1.0
+        cy = origin[1] + 2.0 + j * 17.0 + rng.uniform(0.5, 14.0 - d + 0.5) + d / 2 - 1.0
+        h = rng.uniform(6.0, 18.0)
+        boxes.append((cx - w / 2, cy - d / 2, cx + w / 2, cy + d / 2, h))
+    return boxes
+
+
+def make_tile(n_points, seed=20240000, origin=TILE_ORIGIN, facade_fraction=0.33, shuffle=True,
+              order='F'):
+    """Returns a dict with
+         points   (n,3) float64 (F-ordered by default, like pipeline.py:124 delivers)
+         kind     uint8[n]  0 ground, 1 facade, 2 car, 3 furniture, 4 clutter, 5 noise
+         ahn_tile dict x, y, ground_surface, building_surface (float64 from float16)
+         building_polygons / road_polygons  lists of RingPolygon
+         tilecode
+    """
+    rng = np.random.Generator(np.random.Philox(seed))
+    ox, oy = origin
+    n = int(n_points)
+    f_fac = facade_fraction
+    rest = 1.0 - f_fac
+    # fractions of the non-facade remainder follow the 45/8/10/2/2 mix of the survey
+    base = np.array([0.45, 0.08, 0.10, 0.02, 0.02])
+    base = base / base.sum() * rest
+    counts = np.floor(np.array([base[0], f_fac, base[1], base[2], base[3], base[4]]) * n).astype(np.int64)
+    counts[0] += n - counts.sum()
+    n_ground, n_facade, n_car, n_furn, n_clutter, n_noise = counts
+
+    boxes = make_buildings(rng, origin)
+    xs, ys, zs, kinds = [], [], [], []
+
+    # ground
+    gx = ox + rng.random(n_ground) * TILE_SIZE
+    gy = oy + rng.random(n_ground) * TILE_SIZE
+    gzv = _ground_z(gx, gy, origin) + rng.normal(0.0, 0.02, n_ground)
+    xs.append(gx); ys.append(gy); zs.append(gzv); kinds.append(np.zeros(n_ground, np.uint8))
+
+    # facades: vertical walls of the boxes, sigma_perp = 0.01 m, 6 % balcony points
+    walls = []
+    for (x0, y0, x1, y1, h) in boxes:
+        walls += [(x0, y0, x1, y0, h, 0, -1), (x1, y0, x1, y1, h, 1, 0),
+                  (x1, y1, x0, y1, h, 0, 1), (x0, y1, x0, y0, h, -1, 0)]
+    warea = np.array([np.hypot(w[2] - w[0], w[3] - w[1]) * w[4] for w in walls])
+    wsel = rng.choice(len(walls), size=n_facade, p=warea / warea.sum())
+    wa = np.array(walls)
+    t = rng.random(n_facade)
+    fx = wa[wsel, 0] + t * (wa[wsel, 2] - wa[wsel, 0])
+    fy = wa[wsel, 1] + t * (wa[wsel, 3] - wa[wsel, 1])
+    base_z = _ground_z(fx, fy, origin)
+    fz = base_z + rng.random(n_facade) * wa[wsel, 4]
+    perp = rng.normal(0.0, 0.01, n_facade)
+    balcony = rng.random(n_facade) < 0.06
+    perp = np.where(balcony, rng.uniform(0.0, 0.8, n_facade), perp)
+    fx = fx + perp * wa[wsel, 5]
+    fy = fy + perp * wa[wsel, 6]
+    xs.append(fx); ys.append(fy); zs.append(fz); kinds.append(np.ones(n_facade, np.uint8))
+
+    # roads: two crossing strips; cars are 4.5 x 1.8 x 1.5 m box shells on them
+    road_h = (ox, oy + 19.5, ox + TILE_SIZE, oy + 25.0)        # x0, y0, x1, y1
+    road_v = (ox + 19.5, oy, ox + 25.0, oy + TILE_SIZE)
+    n_cars = 40
+    car_c = np.empty((n_cars, 2)); car_dim = np.empty((n_cars, 2))
+    for c in range(n_cars):
+        if c % 2 == 0:
+            car_c[c] = (ox + rng.uniform(3, 47), oy + rng.uniform(20.6, 23.9)); car_dim[c] = (4.5, 1.8)
+        else:
+            car_c[c] = (ox + rng.uniform(20.6, 23.9), oy + rng.uniform(3, 47)); car_dim[c] = (1.8, 4.5)
+    csel = rng.integers(0, n_cars, n_car)
+    face = rng.integers(0, 5, n_car)
+    u = rng.random(n_car) - 0.5; v = rng.random(n_car) - 0.5; w = rng.random(n_car)
+    lx = np.where(face == 0, -0.5, np.where(face == 1, 0.5, u))
+    ly = np.where(face == 2, -0.5, np.where(face == 3, 0.5, v))
+    lz = np.where(face == 4, 1.0, w)
+    cx = car_c[csel, 0] + lx * car_dim[csel, 0] + rng.normal(0, 0.005, n_car)
+    cy = car_c[csel, 1] + ly * car_dim[csel, 1] + rng.normal(0, 0.005, n_car)
+    cz = _ground_z(cx, cy, origin) + 0.15 + lz * 1.5
+    xs.append(cx); ys.append(cy); zs.append(cz); kinds.append(np.full(n_car, 2, np.uint8))
+
+    # street furniture: 60 poles (cylinders) + 25 ellipsoid crowns
+    n_pole, n_crown = 60, 25
+    pole_xy = np.column_stack((ox + rng.uniform(1, 49, n_pole), oy + rng.uniform(1, 49, n_pole)))
+    pole_r = rng.uniform(0.1, 0.3, n_pole); pole_h = rng.uniform(2.0, 8.0, n_pole)
+    crown_xy = np.column_stack((ox + rng.uniform(4, 46, n_crown), oy + rng.uniform(4, 46, n_crown)))
+    crown_r = rng.uniform(2.0, 3.0, n_crown); crown_z = rng.uniform(5.0, 10.0, n_crown)
+    is_crown = rng.random(n_furn) < 0.6
+    psel = rng.integers(0, n_pole, n_furn); ksel = rng.integers(0, n_crown, n_furn)
+    ang = rng.uniform(0, 2 * np.pi, n_furn)
+    hx = pole_xy[psel, 0] + pole_r[psel] * np.cos(ang)
+    hy = pole_xy[psel, 1] + pole_r[psel] * np.sin(ang)
+    hz = _ground_z(hx, hy, origin) + rng.random(n_furn) * pole_h[psel]
+    d = rng.normal(size=(n_furn, 3)); d /= np.linalg.norm(d, axis=1, keepdims=True)
+    rr = crown_r[ksel] * rng.random(n_furn) ** (1.0 / 3.0)
+    kx = crown_xy[ksel, 0] + d[:, 0] * rr
+    ky = crown_xy[ksel, 1] + d[:, 1] * rr
+    kz = crown_z[ksel] + d[:, 2] * rr * 0.8
+    xs.append(np.where(is_crown, kx, hx)); ys.append(np.where(is_crown, ky, hy))
+    zs.append(np.where(is_crown, kz, hz)); kinds.append(np.full(n_furn, 3, np.uint8))
+
+    # low-density clutter near the poles
+    qsel = rng.integers(0, n_pole, n_clutter)
+    qx = pole_xy[qsel, 0] + rng.normal(0, 0.4, n_clutter)
+    qy = pole_xy[qsel, 1] + rng.normal(0, 0.4, n_clutter)
+    qz = _ground_z(qx, qy, origin) + np.abs(rng.normal(0.3, 0.4, n_clutter))
+    xs.append(qx); ys.append(qy); zs.append(qz); kinds.append(np.full(n_clutter, 4, np.uint8))
+
+    # uniform noise
+    xs.append(ox + rng.random(n_noise) * TILE_SIZE); ys.append(oy + rng.random(n_noise) * TILE_SIZE)
+    zs.append(rng.uniform(-2.0, 25.0, n_noise)); kinds.append(np.full(n_noise, 5, np.uint8))
+
+    x = np.clip(np.concatenate(xs), ox, ox + TILE_SIZE)
+    y = np.clip(np.concatenate(ys), oy, oy + TILE_SIZE)
+    z = np.concatenate(zs)
+    kind = np.concatenate(kinds)
+    if shuffle:
+        perm = rng.permutation(n)
+        x, y, z, kind = x[perm], y[perm], z[perm], kind[perm]
+    points = np.empty((n, 3), dtype=np.float64, order=order)
+    points[:, 0] = _quantise(x); points[:, 1] = _quantise(y); points[:, 2] = _quantise(z)
+
+    # AHN raster: 500 x 500 cells of 0.1 m, x ascending, y descending, float16 like the npz
+    gx_c = ox + 0.05 + 0.1 * np.arange(500)
+    gy_c = oy + TILE_SIZE - 0.05 - 0.1 * np.arange(500)
+    XX, YY = np.meshgrid(gx_c, gy_c)
+    ground = _ground_z(XX, YY, origin)
+    building = np.full_like(ground, np.nan)
+    for (x0, y0, x1, y1, h) in boxes:
+        inside = (XX >= x0) & (XX <= x1) & (YY >= y0) & (YY <= y1)
+        building[inside] = (_ground_z(XX, YY, origin) + h)[inside]
+        ground[(XX >= x0 + 0.3) & (XX <= x1 - 0.3) & (YY >= y0 + 0.3) & (YY <= y1 - 0.3)] = np.nan
+    ahn_tile = {'x': gx_c, 'y': gy_c,
+                'ground_surface': ground.astype(np.float16).astype(float),
+                'building_surface': building.astype(np.float16).astype(float)}
+
+    # BGT-like polygons: footprints enlarged by 0.25 m (stands in for offset=0.25, which
+    # needs shapely), each with a short collinear extra vertex; road strips as rings
+    building_polygons = []
+    for b, (x0, y0, x1, y1, h) in enumerate(boxes):
+        e = 0.25
+        ring = [(x0 - e, y0 - e), ((x0 + x1) / 2, y0 - e), (x1 + e, y0 - e), (x1 + e, y1 + e),
+                (x0 - e, y1 + e), (x0 - e, y0 - e)]
+        holes = []
+        if b % 3 == 0:      # a courtyard
+            mx, my = (x0 + x1) / 2, (y0 + y1) / 2
+            holes = [[(mx - 1.5, my - 1.5), (mx - 1.5, my + 1.5), (mx + 1.5, my + 1.5),
+                      (mx + 1.5, my - 1.5), (mx - 1.5, my - 1.5)]]
+        building_polygons.append(RingPolygon(_quantise(np.array(ring)),
+                                             [_quantise(np.array(hh)) for hh in holes]))
+    def strip(r, k):
+        x0, y0, x1, y1 = r
+        top = [(x0 + (x1 - x0) * i / k, y1 + 0.2 * np.sin(i)) for i in range(k + 1)]
+        bot = [(x1 - (x1 - x0) * i / k, y0 + 0.2 * np.cos(i)) for i in range(k + 1)]
+        return RingPolygon(_quantise(np.array(bot[::-1][::-1] + top[::-1] + [bot[0]])))
+    road_polygons = [strip(road_h, 24), strip(road_v, 24)]
+
+    return {'points': points, 'kind': kind, 'ahn_tile': ahn_tile, 'boxes': boxes,
+            'building_polygons': building_polygons, 'road_polygons': road_polygons,
+            'tilecode': tilecode_for(origin), 'origin': origin}
+
+
+def make_polygon_lattice(n_side=71, seed=5000, origin=TILE_ORIGIN, hole_fraction=0.1):
+    """Config 4: jittered n_side x n_side lattice of star-shaped rings (circumradius
+    0.25-0.45 m, 5-60 vertices), a fraction with one hole."""
+    rng = np.random.Generator(np.random.Philox(seed))
+    pitch = TILE_SIZE / n_side
+    polys = []
+    for i in range(n_side):
+        for j in range(n_side):
+            cx = origin[0] + (i + 0.5) * pitch + rng.uniform(-0.05, 0.05)
+            cy = origin[1] + (j + 0.5) * pitch + rng.uniform(-0.05, 0.05)
+            nv = int(min(60, max(5, rng.geometric(0.1))))
+            ang = np.sort(rng.uniform(0, 2 * np.pi, nv))
+            rad = rng.uniform(0.25, 0.45) * rng.uniform(0.6, 1.0, nv)
+            ring = np.column_stack((cx + rad * np.cos(ang), cy + rad * np.sin(ang)))
+            ring = np.vstack([ring, ring[:1]])
+            holes = []
+            if rng.random() < hole_fraction:
+                ha = np.linspace(0, 2 * np.pi, 7)
+                holes = [np.column_stack((cx + 0.08 * np.cos(ha), cy + 0.08 * np.sin(ha)))]
+                holes[0][-1] = holes[0][0]
+            polys.append(RingPolygon(_quantise(ring), [_quantise(h) for h in holes]))
+    return polys
