@@ -49,6 +49,23 @@ int         upcp_device_count(void);
  * (used by bench.py for the `gpu_launches` figure). */
 int64_t     upcp_launch_count(void);
 
+/* Per-kernel device timing for bench.py: when enabled, the dominant kernels are bracketed
+ * with cudaEvents on their launching stream.  upcp_prof_read() synchronises the device,
+ * adds up the elapsed time of all completed brackets of `slot` since the last reset and
+ * returns the number of launches.  Slots: 0 raster, 1 pip, 2 radix sort (all passes of one
+ * sort), 3 cc link (union-find), 4 knn search, 5 region grow (persistent kernel). */
+#define UPCP_PROF_RASTER 0
+#define UPCP_PROF_PIP    1
+#define UPCP_PROF_SORT   2
+#define UPCP_PROF_LINK   3
+#define UPCP_PROF_KNN    4
+#define UPCP_PROF_GROW   5
+#define UPCP_PROF_SLOTS  6
+int         upcp_prof_enable(int on);
+int         upcp_prof_reset(void);
+int         upcp_prof_read(int slot, double* total_ms, int64_t* launches, int64_t* units);
+const char* upcp_prof_slot_name(int slot);
+
 /* ------------------------------------------------------- tile / layout ---- */
 /* Replaces: the implicit numpy layout of `points` (pipeline.py:124 delivers an
  * F-ordered (N,3) float64 array; callers may also pass C-ordered).  Converts a

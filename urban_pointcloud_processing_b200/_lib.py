@@ -33,6 +33,10 @@ _PROTOTYPES = {
     'upcp_last_error': (c_char_p, []),
     'upcp_device_count': (c_int, []),
     'upcp_launch_count': (c_int64, []),
+    'upcp_prof_enable': (c_int, [c_int]),
+    'upcp_prof_reset': (c_int, []),
+    'upcp_prof_read': (c_int, [c_int, POINTER(c_double), POINTER(c_int64), POINTER(c_int64)]),
+    'upcp_prof_slot_name': (c_char_p, [c_int]),
     'upcp_points_aos_to_soa': (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     'upcp_bbox_ws_bytes': (c_size_t, [c_int64]),
     'upcp_bbox': (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
@@ -117,6 +121,25 @@ def require_cuda():
     if lib.upcp_device_count() < 1:
         raise UpcpCudaError('no CUDA device visible: upcp_cuda has no CPU fallback')
     return lib
+
+
+PROF_SLOTS = 6
+
+
+def prof_enable(on=True):
+    load().upcp_prof_enable(int(bool(on)))
+    load().upcp_prof_reset()
+
+
+def prof_read():
+    """{slot name: (total_ms, launches, units)} since the last reset (synchronises)."""
+    lib = load()
+    out = {}
+    for slot in range(PROF_SLOTS):
+        ms, cnt, units = c_double(), c_int64(), c_int64()
+        check(lib.upcp_prof_read(slot, ctypes.byref(ms), ctypes.byref(cnt), ctypes.byref(units)), 'upcp_prof_read')
+        out[lib.upcp_prof_slot_name(slot).decode()] = (ms.value, cnt.value, units.value)
+    return out
 
 
 def launch_count():

@@ -1,5 +1,7 @@
 // Status / error plumbing and process-wide counters of the upcp_cuda C ABI.
 #include <atomic>
+#include <mutex>
+#include <vector>
 #include <cstdio>
 #include <cstring>
 #include "common.cuh"
@@ -31,9 +33,70 @@ int num_sms() {
     return cached_sms;
 }
 
+// ------------------------------------------------------------ profiling -------
+struct ProfBracket { cudaEvent_t a, b; int64_t units; };
+static std::mutex g_prof_mu;
+static std::atomic<int> g_prof_on{0};
+static std::vector<ProfBracket> g_prof[UPCP_PROF_SLOTS];
+static cudaEvent_t g_prof_open[UPCP_PROF_SLOTS];
+
+void prof_begin(int slot, cudaStream_t st) {
+    if (!g_prof_on.load(std::memory_order_relaxed)) return;
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) != cudaSuccess) return;
+    cudaEventRecord(e, st);
+    g_prof_open[slot] = e;
+}
+
+void prof_end(int slot, cudaStream_t st, int64_t units) {
+    if (!g_prof_on.load(std::memory_order_relaxed)) return;
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    if (!g_prof_open[slot]) return;
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) != cudaSuccess) return;
+    cudaEventRecord(e, st);
+    g_prof[slot].push_back({g_prof_open[slot], e, units});
+    g_prof_open[slot] = nullptr;
+}
+
 }  // namespace upcp
 
 extern "C" {
+
+int upcp_prof_enable(int on) { upcp::g_prof_on.store(on ? 1 : 0); return UPCP_OK; }
+
+int upcp_prof_reset(void) {
+    std::lock_guard<std::mutex> lk(upcp::g_prof_mu);
+    for (int s = 0; s < UPCP_PROF_SLOTS; ++s) {
+        for (auto& b : upcp::g_prof[s]) { cudaEventDestroy(b.a); cudaEventDestroy(b.b); }
+        upcp::g_prof[s].clear();
+    }
+    return UPCP_OK;
+}
+
+int upcp_prof_read(int slot, double* total_ms, int64_t* launches, int64_t* units) {
+    if (slot < 0 || slot >= UPCP_PROF_SLOTS) UPCP_FAIL(UPCP_E_INVALID, "prof_read: bad slot");
+    UPCP_CUDA_OK(cudaDeviceSynchronize());
+    std::lock_guard<std::mutex> lk(upcp::g_prof_mu);
+    double ms = 0.0; int64_t u = 0;
+    for (auto& b : upcp::g_prof[slot]) {
+        float t = 0.f;
+        if (cudaEventElapsedTime(&t, b.a, b.b) == cudaSuccess) ms += t;
+        u += b.units;
+    }
+    if (total_ms) *total_ms = ms;
+    if (launches) *launches = (int64_t)upcp::g_prof[slot].size();
+    if (units) *units = u;
+    return UPCP_OK;
+}
+
+const char* upcp_prof_slot_name(int slot) {
+    static const char* names[UPCP_PROF_SLOTS] = {"raster_kernel", "pip_query_kernel", "radix_sort (hist+scan+scatter)",
+                                                 "cc_link_kernel", "knn_search_kernel", "grow_kernel"};
+    return (slot >= 0 && slot < UPCP_PROF_SLOTS) ? names[slot] : "";
+}
+
 
 int upcp_abi_version(void) { return UPCP_ABI_VERSION; }
 

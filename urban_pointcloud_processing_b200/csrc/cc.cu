@@ -338,7 +338,9 @@ static int lcc_impl(const double* d_x, const double* d_y, const double* d_z, int
     // 4. union-find over cells
     cc_init_parent_kernel<<<grid_m, kBlock, 0, st>>>(n_cells, parent, comp_size, seed_cnt);
     UPCP_LAUNCH_OK();
+    prof_begin(UPCP_PROF_LINK, st);
     cc_link_kernel<K><<<grid_m, kBlock, 0, st>>>(ucell, n_cells, op.level, parent);
+    prof_end(UPCP_PROF_LINK, st, m);
     UPCP_LAUNCH_OK();
     cc_compress_kernel<<<grid_m, kBlock, 0, st>>>(n_cells, parent, cell_first, comp_size,
                                                   (unsigned long long*)d_info);

@@ -35,6 +35,11 @@ int num_sms();
         if (_s != UPCP_OK) return _s;                                              \
     } while (0)
 
+// Optional cudaEvent bracket around a kernel (see upcp_prof_* in the header).  `units` is
+// the number of points / cells the launch processes (for the roofline arithmetic).
+void prof_begin(int slot, cudaStream_t st);
+void prof_end(int slot, cudaStream_t st, int64_t units);
+
 static inline size_t align_up(size_t v, size_t a = 256) { return (v + a - 1) / a * a; }
 
 // Bump allocator over the caller-provided workspace.

@@ -536,6 +536,7 @@ static int knn_impl(const double* d_x, const double* d_y, const double* d_z, int
     int cap_blocks = num_sms() * 32;
     if (blocks > cap_blocks) blocks = cap_blocks;
     if (blocks < 1) blocks = 1;
+    prof_begin(UPCP_PROF_KNN, st);
     if (kh <= 16) {
         UPCP_CUDA_OK(cudaFuncSetAttribute(knn_search_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)search_smem_bytes<16>()));
         knn_search_kernel<16><<<blocks, kSearchThreads, search_smem_bytes<16>(), st>>>(a);
@@ -543,6 +544,7 @@ static int knn_impl(const double* d_x, const double* d_y, const double* d_z, int
         UPCP_CUDA_OK(cudaFuncSetAttribute(knn_search_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)search_smem_bytes<32>()));
         knn_search_kernel<32><<<blocks, kSearchThreads, search_smem_bytes<32>(), st>>>(a);
     }
+    prof_end(UPCP_PROF_KNN, st, m);
     UPCP_LAUNCH_OK();
     return UPCP_OK;
 }

@@ -338,8 +338,10 @@ int upcp_pip_query(const void* d_plan, const double* d_x, const double* d_y, int
                    const uint8_t* d_sel, uint8_t* d_out, void* stream) {
     if (n < 0 || !d_plan) UPCP_FAIL(UPCP_E_INVALID, "pip_query: bad argument");
     if (n == 0) return UPCP_OK;
+    prof_begin(UPCP_PROF_PIP, (cudaStream_t)stream);
     pip_query_kernel<<<grid_for(n, kBlock), kBlock, 0, (cudaStream_t)stream>>>(
         (const char*)d_plan, d_x, d_y, n, d_sel, d_out);
+    prof_end(UPCP_PROF_PIP, (cudaStream_t)stream, n);
     UPCP_LAUNCH_OK();
     return UPCP_OK;
 }

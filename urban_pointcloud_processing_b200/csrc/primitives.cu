@@ -293,6 +293,7 @@ static int radix_sort_impl(K* keys_a, uint32_t* vals_a, K* keys_b, uint32_t* val
     int grid = n_tiles < num_sms() * 4 ? n_tiles : num_sms() * 4;
     K* kin = keys_a; uint32_t* vin = vals_a; K* kout = keys_b; uint32_t* vout = vals_b;
     bool in_b = false;
+    prof_begin(UPCP_PROF_SORT, st);
     for (int shift = 0; shift < end_bit; shift += kRsBits) {
         int bits = end_bit - shift < kRsBits ? end_bit - shift : kRsBits;
         uint32_t mask = (1u << bits) - 1u;
@@ -305,6 +306,7 @@ static int radix_sort_impl(K* keys_a, uint32_t* vals_a, K* keys_b, uint32_t* val
         uint32_t* tv = vin; vin = vout; vout = tv;
         in_b = !in_b;
     }
+    prof_end(UPCP_PROF_SORT, st, n);
     *result_in_b = in_b;
     return UPCP_OK;
 }

@@ -79,12 +79,14 @@ static int launch_raster(bool classify, const double* d_x, const double* d_y, co
     int grid = grid_for(n, kBlock);
     bool smem_bins = nx <= kMaxBinsSmem && ny <= kMaxBinsSmem;
     size_t smem = smem_bins ? (size_t)(nx + ny) * sizeof(double) : 0;
+    prof_begin(UPCP_PROF_RASTER, st);
 #define UPCP_RASTER_LAUNCH(SB, CL)                                                   \
     raster_kernel<SB, CL><<<grid, kBlock, smem, st>>>(d_x, d_y, d_z, n, d_sel, r, mode, a, b, \
                                                      d_out_val, d_out_mask, d_labels, assign)
     if (smem_bins) { if (classify) UPCP_RASTER_LAUNCH(true, true); else UPCP_RASTER_LAUNCH(true, false); }
     else           { if (classify) UPCP_RASTER_LAUNCH(false, true); else UPCP_RASTER_LAUNCH(false, false); }
 #undef UPCP_RASTER_LAUNCH
+    prof_end(UPCP_PROF_RASTER, st, n);
     UPCP_LAUNCH_OK();
     return UPCP_OK;
 }

@@ -191,8 +191,10 @@ int upcp_region_grow(const int32_t* d_knn, int knn, const double* d_normals,
     int grid = num_sms() * per_sm;
     int64_t need = (m + (kGrowThreads / 32) - 1) / (kGrowThreads / 32);
     if (need < grid) grid = (int)(need < 1 ? 1 : need);
+    prof_begin(UPCP_PROF_GROW, st);
     grow_kernel<<<grid, kGrowThreads, 0, st>>>(d_knn, knn, d_normals, d_can_seed, m, threshold_angle_deg,
                                                state, queue, ctr);
+    prof_end(UPCP_PROF_GROW, st, m);
     UPCP_LAUNCH_OK();
     grow_finish_kernel<<<grid_for(m, kBlock), kBlock, 0, st>>>(state, m, d_region, ctr);
     UPCP_LAUNCH_OK();
