@@ -154,7 +154,10 @@ def crop_sample(tile, labels0, target):
     pts = tile['points']
     n = len(pts)
     side = 50.0 * np.sqrt(min(1.0, target / n))
-    cx, cy = tile['origin'][0] + 25.0, tile['origin'][1] + 25.0
+    # centred on a corner of the first building so that facade, ground and street all occur
+    cx, cy = tile['boxes'][0][2], tile['boxes'][0][3]
+    cx = min(max(cx, tile['origin'][0] + side / 2), tile['origin'][0] + 50.0 - side / 2)
+    cy = min(max(cy, tile['origin'][1] + side / 2), tile['origin'][1] + 50.0 - side / 2)
     keep = (np.abs(pts[:, 0] - cx) <= side / 2) & (np.abs(pts[:, 1] - cy) <= side / 2)
     return np.asfortranarray(pts[keep]), labels0[keep].copy(), side
 
