@@ -159,6 +159,20 @@ __global__ void knn_finish_kernel(const uint32_t* __restrict__ n_cells, uint32_t
     if (threadIdx.x == 0 && blockIdx.x == 0) { cell_first[*n_cells] = m; group_start[*n_groups] = m; }
 }
 
+struct KnnScCellFunctor {    // super-cell runs over the fine-cell list
+    const uint64_t* ucell;
+    uint64_t* sc_key;
+    uint32_t* sc_cell_first;
+    __device__ void operator()(int64_t e, bool is_first, uint32_t rank) const {
+        if (is_first) { sc_key[rank] = ucell[e] >> 6; sc_cell_first[rank] = (uint32_t)e; }
+    }
+};
+
+__global__ void knn_finish_sc_kernel(const uint32_t* __restrict__ n_sc, uint32_t* __restrict__ sc_cell_first,
+                                     uint32_t c_total) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) sc_cell_first[*n_sc] = c_total;
+}
+
 __global__ void __launch_bounds__(kBlock)
 knn_hash_insert_kernel(const uint64_t* __restrict__ ucell, const uint32_t* __restrict__ n_cells,
                        uint32_t* __restrict__ table, uint32_t table_mask) {
@@ -170,24 +184,15 @@ knn_hash_insert_kernel(const uint64_t* __restrict__ ucell, const uint32_t* __res
     }
 }
 
-__device__ __forceinline__ uint32_t hash_lookup(const uint64_t* __restrict__ ucell,
-                                                const uint32_t* __restrict__ table,
-                                                uint32_t table_mask, uint64_t key) {
-    uint32_t h = (uint32_t)hash64(key) & table_mask;
-    while (true) {
-        uint32_t idx = __ldg(table + h);
-        if (idx == kEmpty) return kEmpty;
-        if (__ldg(ucell + idx) == key) return idx;
-        h = (h + 1) & table_mask;
-    }
-}
-
 // ------------------------------------------------------------------ search ------
+constexpr int kCellCap = 160;      // per-warp list of candidate fine cells (flushed when nearly full)
+
 struct SearchArgs {
     const double* sx; const double* sy; const double* sz;   // sorted coordinates
     const uint32_t* perm;          // sorted position -> compact id
-    const uint64_t* ucell; const uint32_t* cell_first;
-    const uint32_t* table; uint32_t table_mask;
+    const uint64_t* ucell; const uint32_t* cell_first;       // fine cells (Morton keys, first point)
+    const uint64_t* sc_key; const uint32_t* sc_cell_first;   // super-cells (key >> 6, first fine cell)
+    const uint32_t* table; uint32_t table_mask;              // hash: super-cell key -> super-cell index
     const uint32_t* group_start; const uint32_t* n_groups;
     GridParams g;
     int64_t m;
@@ -243,22 +248,42 @@ struct LaneHeap {
     }
 };
 
+__device__ __forceinline__ double warp_max_f64(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// conservative squared distance between the axis-aligned box [lo, hi] and the box [bmin, bmax]
+__device__ __forceinline__ double box_gap2(double lox, double loy, double loz, double hix, double hiy, double hiz,
+                                           double bminx, double bminy, double bminz,
+                                           double bmaxx, double bmaxy, double bmaxz, double slack) {
+    double gx = fmax(0.0, fmax(lox - bmaxx, bminx - hix) - slack);
+    double gy = fmax(0.0, fmax(loy - bmaxy, bminy - hiy) - slack);
+    double gz = fmax(0.0, fmax(loz - bmaxz, bminz - hiz) - slack);
+    return (gx * gx + gy * gy + gz * gz) * (1.0 - 1e-9);
+}
+
 template <int KMAX>
 __global__ void __launch_bounds__(kSearchThreads)
 knn_search_kernel(SearchArgs a) {
-    // dynamic shared memory: [warps][KMAX*32] fp64 heap keys | [warps][KMAX*32] u32 heap
-    // payloads | [warps][3][32] fp64 staged candidate coordinates
+    // dynamic shared memory per warp: [KMAX*32] fp64 heap keys | [KMAX*32] u32 heap payloads |
+    // [3][32] fp64 staged candidate coordinates | [kCellCap] fp64 cell bounds + u32 cell ids
     extern __shared__ __align__(16) unsigned char knn_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double* const w_heap_d2 = reinterpret_cast<double*>(knn_smem) + (size_t)warp * KMAX * 32;
     uint32_t* const w_heap_pos = reinterpret_cast<uint32_t*>(knn_smem + (size_t)kSearchWarps * KMAX * 32 * 8) + (size_t)warp * KMAX * 32;
     double* const w_cand = reinterpret_cast<double*>(knn_smem + (size_t)kSearchWarps * KMAX * 32 * 12) + (size_t)warp * 96;
     double* const c_x = w_cand; double* const c_y = w_cand + 32; double* const c_z = w_cand + 64;
+    double* const l_lb2 = reinterpret_cast<double*>(knn_smem + (size_t)kSearchWarps * (KMAX * 32 * 12 + 96 * 8)) + (size_t)warp * kCellCap;
+    uint32_t* const l_cell = reinterpret_cast<uint32_t*>(knn_smem + (size_t)kSearchWarps * (KMAX * 32 * 12 + 96 * 8 + kCellCap * 8)) + (size_t)warp * kCellCap;
 
     const GridParams g = a.g;
     const uint32_t n_groups = *a.n_groups;
     const int K = a.k_heap;
     const double inf = __longlong_as_double(0x7ff0000000000000LL);
+    const double scell = 4.0 * g.cell;                       // super-cell edge
+    const int nsx = (g.nx + 3) >> 2, nsy = (g.ny + 3) >> 2, nsz = (g.nz + 3) >> 2;
 
     for (uint32_t grp = blockIdx.x * kSearchWarps + warp; grp < n_groups; grp += gridDim.x * kSearchWarps) {
         const uint32_t gs = a.group_start[grp];
@@ -266,18 +291,14 @@ knn_search_kernel(SearchArgs a) {
         const bool valid = lane < gcount;
         const uint32_t qpos = gs + (valid ? lane : 0);
         const double qx = a.sx[qpos], qy = a.sy[qpos], qz = a.sz[qpos];
-        const int icx = cell_coord(qx, g.ox, g.inv_cell, g.nx);
-        const int icy = cell_coord(qy, g.oy, g.inv_cell, g.ny);
-        const int icz = cell_coord(qz, g.oz, g.inv_cell, g.nz);
-        // group bounding box in cells and in world coordinates (lane 0 is always valid and
-        // invalid lanes alias it, so plain warp reductions are exact)
-        int lox = icx, loy = icy, loz = icz, hix = icx, hiy = icy, hiz = icz;
+        // every query of a group lies in the same super-cell (groups never straddle one)
+        const int sx = cell_coord(qx, g.ox, g.inv_cell, g.nx) >> 2;
+        const int sy = cell_coord(qy, g.oy, g.inv_cell, g.ny) >> 2;
+        const int sz = cell_coord(qz, g.oz, g.inv_cell, g.nz) >> 2;
+        // bounding box of the group's queries (invalid lanes alias lane 0)
         double bminx = qx, bminy = qy, bminz = qz, bmaxx = qx, bmaxy = qy, bmaxz = qz;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
-            lox = min(lox, __shfl_xor_sync(0xffffffffu, lox, o)); hix = max(hix, __shfl_xor_sync(0xffffffffu, hix, o));
-            loy = min(loy, __shfl_xor_sync(0xffffffffu, loy, o)); hiy = max(hiy, __shfl_xor_sync(0xffffffffu, hiy, o));
-            loz = min(loz, __shfl_xor_sync(0xffffffffu, loz, o)); hiz = max(hiz, __shfl_xor_sync(0xffffffffu, hiz, o));
             bminx = fmin(bminx, __shfl_xor_sync(0xffffffffu, bminx, o)); bmaxx = fmax(bmaxx, __shfl_xor_sync(0xffffffffu, bmaxx, o));
             bminy = fmin(bminy, __shfl_xor_sync(0xffffffffu, bminy, o)); bmaxy = fmax(bmaxy, __shfl_xor_sync(0xffffffffu, bmaxy, o));
             bminz = fmin(bminz, __shfl_xor_sync(0xffffffffu, bminz, o)); bmaxz = fmax(bmaxz, __shfl_xor_sync(0xffffffffu, bmaxz, o));
@@ -287,85 +308,144 @@ knn_search_kernel(SearchArgs a) {
         heap.d2 = w_heap_d2; heap.pos = w_heap_pos; heap.perm = a.perm; heap.lane = lane; heap.cnt = 0;
         bool done = !valid;
         double worst = inf;         // k-th best squared distance once the heap is full
+        int list_n = 0;             // warp-uniform
 
-        for (int r = 0;; ++r) {
-            const int bx0 = max(lox - r, 0), bx1 = min(hix + r, g.nx - 1);
-            const int by0 = max(loy - r, 0), by1 = min(hiy + r, g.ny - 1);
-            const int bz0 = max(loz - r, 0), bz1 = min(hiz + r, g.nz - 1);
-            const int wx = bx1 - bx0 + 1, wy = by1 - by0 + 1, wz = bz1 - bz0 + 1;
-            const int total = wx * wy * wz;
-            // prune bound: the largest k-th distance among unfinished lanes
-            double wmax = done ? 0.0 : worst;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) wmax = fmax(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
-
-            for (int t0 = 0; t0 < total; t0 += 32) {
-                const int t = t0 + lane;
-                uint32_t c_first = 0, c_cnt = 0;
-                if (t < total) {
-                    const int cx = bx0 + t % wx, cy = by0 + (t / wx) % wy, cz = bz0 + t / (wx * wy);
-                    const bool inner = r > 0 && cx >= lox - (r - 1) && cx <= hix + (r - 1) &&
-                                       cy >= loy - (r - 1) && cy <= hiy + (r - 1) &&
-                                       cz >= loz - (r - 1) && cz <= hiz + (r - 1);
-                    if (!inner) {
-                        // conservative squared distance between the cell and the group's queries
-                        double gx = fmax(0.0, fmax(g.ox + cx * g.cell - bmaxx, bminx - (g.ox + (cx + 1) * g.cell)) - g.slack);
-                        double gy = fmax(0.0, fmax(g.oy + cy * g.cell - bmaxy, bminy - (g.oy + (cy + 1) * g.cell)) - g.slack);
-                        double gz = fmax(0.0, fmax(g.oz + cz * g.cell - bmaxz, bminz - (g.oz + (cz + 1) * g.cell)) - g.slack);
-                        double lb = (gx * gx + gy * gy + gz * gz) * (1.0 - 1e-9);
-                        if (!(lb > wmax)) {
-                            uint32_t idx = hash_lookup(a.ucell, a.table, a.table_mask, morton3(cx, cy, cz));
-                            if (idx != kEmpty) {
-                                c_first = __ldg(a.cell_first + idx);
-                                c_cnt = __ldg(a.cell_first + idx + 1) - c_first;
-                            }
-                        }
-                    }
+        // Process the listed fine cells nearest-first; stop as soon as the nearest remaining
+        // cell is farther than every unfinished lane's k-th distance (the rest is pruned).
+        auto flush = [&]() {
+            while (list_n > 0) {
+                double mymin = inf; int myidx = -1;
+                for (int e = lane; e < list_n; e += 32) {
+                    double v = l_lb2[e];
+                    if (v < mymin) { mymin = v; myidx = e; }
                 }
-                uint32_t have = __ballot_sync(0xffffffffu, c_cnt > 0);
-                while (have) {
-                    const int src = __ffs(have) - 1;
-                    have &= have - 1;
-                    const uint32_t first = __shfl_sync(0xffffffffu, c_first, src);
-                    const uint32_t cnt = __shfl_sync(0xffffffffu, c_cnt, src);
-                    for (uint32_t j0 = 0; j0 < cnt; j0 += 32) {
-                        const uint32_t p = first + j0 + lane;
-                        if (j0 + lane < cnt) {
-                            c_x[lane] = a.sx[p]; c_y[lane] = a.sy[p]; c_z[lane] = a.sz[p];
-                        }
-                        __syncwarp();
-                        const int nc = (int)min(32u, cnt - j0);
-                        if (!done) {
-                            for (int c = 0; c < nc; ++c) {
-                                const double d2 = dist2(c_x[c], c_y[c], c_z[c], qx, qy, qz);
-                                const uint32_t cp = first + j0 + c;
-                                if (heap.cnt < K) {
-                                    heap.push(d2, cp);
-                                    if (heap.cnt == K) worst = heap.D(0);
-                                } else if (d2 <= worst) {
-                                    if (heap.after(heap.D(0), heap.P(0), d2, cp)) {
-                                        heap.sift_down(0, K, d2, cp);
-                                        worst = heap.D(0);
-                                    }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    double ov = __shfl_xor_sync(0xffffffffu, mymin, o);
+                    int oi = __shfl_xor_sync(0xffffffffu, myidx, o);
+                    if (ov < mymin || (ov == mymin && oi >= 0 && (myidx < 0 || oi < myidx))) { mymin = ov; myidx = oi; }
+                }
+                if (myidx < 0) break;                                  // list exhausted
+                const double wmax = warp_max_f64(done ? 0.0 : worst);
+                if (mymin > wmax) break;                               // everything left is pruned
+                const uint32_t cell = l_cell[myidx];
+                __syncwarp();
+                if (lane == 0) l_lb2[myidx] = inf;
+                const uint32_t first = __ldg(a.cell_first + cell);
+                const uint32_t cnt = __ldg(a.cell_first + cell + 1) - first;
+                for (uint32_t j0 = 0; j0 < cnt; j0 += 32) {
+                    const uint32_t p = first + j0 + lane;
+                    if (j0 + lane < cnt) { c_x[lane] = a.sx[p]; c_y[lane] = a.sy[p]; c_z[lane] = a.sz[p]; }
+                    __syncwarp();
+                    const int nc = (int)min(32u, cnt - j0);
+                    if (!done) {
+                        for (int c = 0; c < nc; ++c) {
+                            const double d2 = dist2(c_x[c], c_y[c], c_z[c], qx, qy, qz);
+                            const uint32_t cp = first + j0 + c;
+                            if (heap.cnt < K) {
+                                heap.push(d2, cp);
+                                if (heap.cnt == K) worst = heap.D(0);
+                            } else if (d2 <= worst) {
+                                if (heap.after(heap.D(0), heap.P(0), d2, cp)) {
+                                    heap.sift_down(0, K, d2, cp);
+                                    worst = heap.D(0);
                                 }
                             }
                         }
-                        __syncwarp();
+                    }
+                    __syncwarp();
+                }
+            }
+            list_n = 0;
+        };
+
+        for (int R = 0;; ++R) {
+            // ---- enumerate the super-cells of ring R (R = 0: the group's own super-cell)
+            const int w = 2 * R + 1, v = 2 * R - 1;
+            const int A = w * w, B = R > 0 ? w * v : 0, C = R > 0 ? v * v : 0;
+            const int total = R == 0 ? 1 : 2 * A + 2 * B + 2 * C;
+            for (int t0 = 0; t0 < total; t0 += 32) {
+                int t = t0 + lane;
+                uint32_t f0 = 0, f1 = 0;
+                // prune bound: the largest k-th distance among the unfinished lanes
+                const double wmax_chunk = warp_max_f64(done ? 0.0 : worst);
+                if (t < total) {
+                    int cx, cy, cz;
+                    if (R == 0) { cx = sx; cy = sy; cz = sz; }
+                    else if (t < 2 * A) {
+                        cz = t < A ? sz - R : sz + R; if (t >= A) t -= A;
+                        cx = sx - R + t % w; cy = sy - R + t / w;
+                    } else if (t < 2 * A + 2 * B) {
+                        t -= 2 * A;
+                        cy = t < B ? sy - R : sy + R; if (t >= B) t -= B;
+                        cx = sx - R + t % w; cz = sz - R + 1 + t / w;
+                    } else {
+                        t -= 2 * A + 2 * B;
+                        cx = t < C ? sx - R : sx + R; if (t >= C) t -= C;
+                        cy = sy - R + 1 + t % v; cz = sz - R + 1 + t / v;
+                    }
+                    if (cx >= 0 && cy >= 0 && cz >= 0 && cx < nsx && cy < nsy && cz < nsz) {
+                        const double lb = box_gap2(g.ox + cx * scell, g.oy + cy * scell, g.oz + cz * scell,
+                                                   g.ox + (cx + 1) * scell, g.oy + (cy + 1) * scell, g.oz + (cz + 1) * scell,
+                                                   bminx, bminy, bminz, bmaxx, bmaxy, bmaxz, g.slack);
+                        const uint64_t key = morton3(cx, cy, cz);
+                        uint32_t h = (uint32_t)hash64(key) & a.table_mask;
+                        while (!(lb > wmax_chunk)) {
+                            uint32_t idx = __ldg(a.table + h);
+                            if (idx == kEmpty) break;
+                            if (__ldg(a.sc_key + idx) == key) {
+                                f0 = __ldg(a.sc_cell_first + idx); f1 = __ldg(a.sc_cell_first + idx + 1);
+                                break;
+                            }
+                            h = (h + 1) & a.table_mask;
+                        }
+                    }
+                }
+                // ---- list the fine cells of the super-cells found by this chunk
+                uint32_t have = __ballot_sync(0xffffffffu, f1 > f0);
+                while (have) {
+                    const int src = __ffs(have) - 1;
+                    have &= have - 1;
+                    const uint32_t e0 = __shfl_sync(0xffffffffu, f0, src);
+                    const uint32_t e1 = __shfl_sync(0xffffffffu, f1, src);
+                    for (uint32_t eb = e0; eb < e1; eb += 32) {
+                        const uint32_t e = eb + lane;
+                        bool keep = false;
+                        double lb = inf;
+                        if (e < e1) {
+                            const uint64_t key = __ldg(a.ucell + e);
+                            const int fx = (int)compact_bits21(key), fy = (int)compact_bits21(key >> 1), fz = (int)compact_bits21(key >> 2);
+                            lb = box_gap2(g.ox + fx * g.cell, g.oy + fy * g.cell, g.oz + fz * g.cell,
+                                          g.ox + (fx + 1) * g.cell, g.oy + (fy + 1) * g.cell, g.oz + (fz + 1) * g.cell,
+                                          bminx, bminy, bminz, bmaxx, bmaxy, bmaxz, g.slack);
+                            keep = !(lb > wmax_chunk);
+                        }
+                        const uint32_t kb = __ballot_sync(0xffffffffu, keep);
+                        if (kb) {
+                            if (list_n + 32 > kCellCap) { flush(); }
+                            if (keep) {
+                                const int slot = list_n + __popc(kb & ((1u << lane) - 1u));
+                                l_lb2[slot] = lb; l_cell[slot] = e;
+                            }
+                            list_n += __popc(kb);
+                            __syncwarp();
+                        }
                     }
                 }
             }
-            // --- termination: distance from the query to the unexplored region
-            const bool open_x0 = lox - r > 0, open_x1 = hix + r < g.nx - 1;
-            const bool open_y0 = loy - r > 0, open_y1 = hiy + r < g.ny - 1;
-            const bool open_z0 = loz - r > 0, open_z1 = hiz + r < g.nz - 1;
+            flush();
+            // ---- termination: distance from the query to the unexplored region
+            const bool open_x0 = sx - R > 0, open_x1 = sx + R < nsx - 1;
+            const bool open_y0 = sy - R > 0, open_y1 = sy + R < nsy - 1;
+            const bool open_z0 = sz - R > 0, open_z1 = sz + R < nsz - 1;
             if (!done) {
                 double reach = inf;
-                if (open_x0) reach = fmin(reach, qx - (g.ox + (lox - r) * g.cell));
-                if (open_x1) reach = fmin(reach, (g.ox + (hix + r + 1) * g.cell) - qx);
-                if (open_y0) reach = fmin(reach, qy - (g.oy + (loy - r) * g.cell));
-                if (open_y1) reach = fmin(reach, (g.oy + (hiy + r + 1) * g.cell) - qy);
-                if (open_z0) reach = fmin(reach, qz - (g.oz + (loz - r) * g.cell));
-                if (open_z1) reach = fmin(reach, (g.oz + (hiz + r + 1) * g.cell) - qz);
+                if (open_x0) reach = fmin(reach, qx - (g.ox + (sx - R) * scell));
+                if (open_x1) reach = fmin(reach, (g.ox + (sx + R + 1) * scell) - qx);
+                if (open_y0) reach = fmin(reach, qy - (g.oy + (sy - R) * scell));
+                if (open_y1) reach = fmin(reach, (g.oy + (sy + R + 1) * scell) - qy);
+                if (open_z0) reach = fmin(reach, qz - (g.oz + (sz - R) * scell));
+                if (open_z1) reach = fmin(reach, (g.oz + (sz + R + 1) * scell) - qz);
                 reach -= g.slack;
                 if (reach == inf) done = true;                      // whole grid explored
                 else if (heap.cnt == K && reach > 0.0 && worst < reach * reach * (1.0 - 1e-9)) done = true;
@@ -434,7 +514,7 @@ knn_search_kernel(SearchArgs a) {
 
 static inline int bits_for(int n) { int b = 0; while ((1 << b) < n) ++b; return b; }
 static inline size_t hash_capacity(int64_t cells) { size_t cap = 1024; while (cap < 2 * (size_t)cells) cap <<= 1; return cap; }
-template <int KMAX> constexpr size_t search_smem_bytes() { return (size_t)kSearchWarps * KMAX * 32 * 12 + (size_t)kSearchWarps * 96 * 8; }
+template <int KMAX> constexpr size_t search_smem_bytes() { return (size_t)kSearchWarps * (KMAX * 32 * 12 + 96 * 8 + kCellCap * 12); }
 
 template <typename K>
 static int knn_impl(const double* d_x, const double* d_y, const double* d_z, int64_t n,
@@ -459,6 +539,8 @@ static int knn_impl(const double* d_x, const double* d_y, const double* d_z, int
     uint32_t* sc_first = ws.take<uint32_t>((size_t)m);
     uint32_t* sc_of = ws.take<uint32_t>((size_t)m);
     uint32_t* group_start = ws.take<uint32_t>((size_t)m + 1);
+    uint64_t* sc_key = ws.take<uint64_t>((size_t)m);
+    uint32_t* sc_cell_first = ws.take<uint32_t>((size_t)m + 1);
     uint32_t* table = ws.take<uint32_t>(hash_capacity(m));
     if (!ws.ok) UPCP_FAIL(UPCP_E_WORKSPACE, "knn: workspace too small");
 
@@ -512,19 +594,30 @@ static int knn_impl(const double* d_x, const double* d_y, const double* d_z, int
     knn_finish_kernel<<<1, 32, 0, st>>>(n_cells, cell_first, n_groups, group_start, (uint32_t)m);
     UPCP_LAUNCH_OK();
 
-    // hash table sized from the actual number of cells (one small D2H)
+    // counts back to the host once: number of fine cells (sizes the super-cell pass and the hash)
     uint32_t h_counts[4] = {0, 0, 0, 0};
     UPCP_CUDA_OK(cudaMemcpyAsync(h_counts, counters, sizeof(h_counts), cudaMemcpyDeviceToHost, st));
     UPCP_CUDA_OK(cudaStreamSynchronize(st));
     const uint32_t c_total = h_counts[1];
+    // super-cells over the fine-cell list: contiguous runs of ucell with equal key >> 6
+    uint32_t* n_sc = counters + 4;
+    knn_boundary_flags_kernel<uint64_t><<<grid_for(c_total, kBlock), kBlock, 0, st>>>(ucell, c_total, 6, flags);
+    UPCP_LAUNCH_OK();
+    {
+        KnnScCellFunctor f{ucell, sc_key, sc_cell_first};
+        UPCP_TRY(compact_apply(flags, c_total, n_sc, prim_ws, st, f));
+    }
+    knn_finish_sc_kernel<<<1, 32, 0, st>>>(n_sc, sc_cell_first, c_total);
+    UPCP_LAUNCH_OK();
     uint32_t cap = 1024;
-    while (cap < 2u * c_total) cap <<= 1;
+    while (cap < 2u * c_total) cap <<= 1;            // c_total >= number of super-cells
     UPCP_CUDA_OK(cudaMemsetAsync(table, 0xff, (size_t)cap * 4, st));
-    knn_hash_insert_kernel<<<grid_for(c_total, kBlock), kBlock, 0, st>>>(ucell, n_cells, table, cap - 1);
+    knn_hash_insert_kernel<<<grid_for(c_total, kBlock), kBlock, 0, st>>>(sc_key, n_sc, table, cap - 1);
     UPCP_LAUNCH_OK();
 
     SearchArgs a;
     a.sx = sx; a.sy = sy; a.sz = sz; a.perm = perm; a.ucell = ucell; a.cell_first = cell_first;
+    a.sc_key = sc_key; a.sc_cell_first = sc_cell_first;
     a.table = table; a.table_mask = cap - 1; a.group_start = group_start; a.n_groups = n_groups;
     a.g = g; a.m = m;
     int kh = knn > max_nn ? knn : max_nn;
@@ -568,6 +661,7 @@ size_t upcp_knn_ws_bytes(int64_t n, int64_t m, int kmax) {
     bytes += align_up((size_t)m * 8);                                       // ucell
     bytes += 2 * align_up(((size_t)m + 1) * 4);                             // cell_first, group_start
     bytes += 2 * align_up((size_t)m * 4);                                   // sc_first, sc_of
+    bytes += align_up((size_t)m * 8) + align_up(((size_t)m + 1) * 4);       // sc_key, sc_cell_first
     { size_t cap = 1024; while (cap < 2 * (size_t)m) cap <<= 1; bytes += align_up(cap * 4); }  // hash table
     return bytes + 4096;
 }

@@ -24,6 +24,16 @@ logger = logging.getLogger(__name__)
 CURVATURE_TOL = 1e-9
 
 
+def default_cell_size(bbox_sel, m, radius):
+    """Fine-cell edge of the search grid: aim at ~8 points per occupied cell of a surface-like
+    cloud (urban LiDAR covers roughly 3x its footprint area), bounded by the search radius."""
+    ex = max(float(bbox_sel[3] - bbox_sel[0]), 1e-3)
+    ey = max(float(bbox_sel[4] - bbox_sel[1]), 1e-3)
+    c = float(np.sqrt(24.0 * ex * ey / max(int(m), 1)))
+    r = max(float(radius), 1e-3)
+    return min(max(c, r / 8.0), r / 2.0)
+
+
 def knn_normals_device(tile, d_sel, m, bbox_sel, knn, max_nn, radius, cell_size=None,
                        want_d2=False, want_cov=True, want_curv=True):
     """kNN rows (compact ids), normals, k-neighbourhood covariance and analytic eigenvalue
@@ -31,7 +41,7 @@ def knn_normals_device(tile, d_sel, m, bbox_sel, knn, max_nn, radius, cell_size=
     lib = _lib.load()
     device = tile.device
     if cell_size is None:
-        cell_size = max(float(radius) * 0.5, 1e-3)
+        cell_size = default_cell_size(bbox_sel, m, radius)
     d_knn = torch.empty((m, knn), dtype=torch.int32, device=device)
     d_d2 = torch.empty((m, knn), dtype=torch.float64, device=device) if want_d2 else None
     d_normals = torch.empty((m, 3), dtype=torch.float64, device=device)
