@@ -264,19 +264,56 @@ __device__ __forceinline__ double box_gap2(double lox, double loy, double loz, d
     return (gx * gx + gy * gy + gz * gz) * (1.0 - 1e-9);
 }
 
+__device__ __forceinline__ uint32_t warp_incl_scan_u32(uint32_t v, int lane) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v += t;
+    }
+    return v;
+}
+
+// largest k in [0, 32) with off[k] <= i  (off is a non-decreasing exclusive scan in smem)
+__device__ __forceinline__ int seg_search(const uint32_t* off, uint32_t i) {
+    int k = 0;
+#pragma unroll
+    for (int step = 16; step > 0; step >>= 1)
+        if (off[k + step] <= i) k += step;
+    return k;
+}
+
+// per-warp shared memory carve-up (bytes)
+template <int KMAX> struct SearchSmem {
+    static constexpr size_t heap_d2 = 0;
+    static constexpr size_t heap_pos = heap_d2 + (size_t)KMAX * 32 * 8;
+    static constexpr size_t c_xy = heap_pos + (size_t)KMAX * 32 * 4;       // double2[32]
+    static constexpr size_t c_z = c_xy + 32 * 16;                           // double[32]
+    static constexpr size_t l_lb2 = c_z + 32 * 8;                           // double[kCellCap]
+    static constexpr size_t l_cell = l_lb2 + (size_t)kCellCap * 8;          // u32[kCellCap]
+    static constexpr size_t c_pos = l_cell + (size_t)kCellCap * 4;          // u32[32]
+    static constexpr size_t seg_a = c_pos + 32 * 4;                         // u32[64 + 32] candidate expansion
+    static constexpr size_t seg_b = seg_a + 96 * 4;                         // u32[64 + 32] cell listing
+    static constexpr size_t per_warp = ((seg_b + 96 * 4) + 15) / 16 * 16;
+};
+
 template <int KMAX>
 __global__ void __launch_bounds__(kSearchThreads)
 knn_search_kernel(SearchArgs a) {
-    // dynamic shared memory per warp: [KMAX*32] fp64 heap keys | [KMAX*32] u32 heap payloads |
-    // [3][32] fp64 staged candidate coordinates | [kCellCap] fp64 cell bounds + u32 cell ids
     extern __shared__ __align__(16) unsigned char knn_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    double* const w_heap_d2 = reinterpret_cast<double*>(knn_smem) + (size_t)warp * KMAX * 32;
-    uint32_t* const w_heap_pos = reinterpret_cast<uint32_t*>(knn_smem + (size_t)kSearchWarps * KMAX * 32 * 8) + (size_t)warp * KMAX * 32;
-    double* const w_cand = reinterpret_cast<double*>(knn_smem + (size_t)kSearchWarps * KMAX * 32 * 12) + (size_t)warp * 96;
-    double* const c_x = w_cand; double* const c_y = w_cand + 32; double* const c_z = w_cand + 64;
-    double* const l_lb2 = reinterpret_cast<double*>(knn_smem + (size_t)kSearchWarps * (KMAX * 32 * 12 + 96 * 8)) + (size_t)warp * kCellCap;
-    uint32_t* const l_cell = reinterpret_cast<uint32_t*>(knn_smem + (size_t)kSearchWarps * (KMAX * 32 * 12 + 96 * 8 + kCellCap * 8)) + (size_t)warp * kCellCap;
+    using L = SearchSmem<KMAX>;
+    unsigned char* const wbase = knn_smem + (size_t)warp * L::per_warp;
+    double* const w_heap_d2 = reinterpret_cast<double*>(wbase + L::heap_d2);
+    uint32_t* const w_heap_pos = reinterpret_cast<uint32_t*>(wbase + L::heap_pos);
+    double2* const c_xy = reinterpret_cast<double2*>(wbase + L::c_xy);
+    double* const c_z = reinterpret_cast<double*>(wbase + L::c_z);
+    double* const l_lb2 = reinterpret_cast<double*>(wbase + L::l_lb2);
+    uint32_t* const l_cell = reinterpret_cast<uint32_t*>(wbase + L::l_cell);
+    uint32_t* const c_pos = reinterpret_cast<uint32_t*>(wbase + L::c_pos);
+    uint32_t* const sa_off = reinterpret_cast<uint32_t*>(wbase + L::seg_a);      // [64]: 32 offsets + 32 x total
+    uint32_t* const sa_base = sa_off + 64;
+    uint32_t* const sb_off = reinterpret_cast<uint32_t*>(wbase + L::seg_b);
+    uint32_t* const sb_base = sb_off + 64;
 
     const GridParams g = a.g;
     const uint32_t n_groups = *a.n_groups;
@@ -310,50 +347,72 @@ knn_search_kernel(SearchArgs a) {
         double worst = inf;         // k-th best squared distance once the heap is full
         int list_n = 0;             // warp-uniform
 
-        // Process the listed fine cells nearest-first; stop as soon as the nearest remaining
-        // cell is farther than every unfinished lane's k-th distance (the rest is pruned).
-        auto flush = [&]() {
-            while (list_n > 0) {
-                double mymin = inf; int myidx = -1;
-                for (int e = lane; e < list_n; e += 32) {
-                    double v = l_lb2[e];
-                    if (v < mymin) { mymin = v; myidx = e; }
+        auto consider = [&](double d2, uint32_t cp) {
+            if (heap.cnt < K) {
+                heap.push(d2, cp);
+                if (heap.cnt == K) worst = heap.D(0);
+            } else if (heap.after(heap.D(0), heap.P(0), d2, cp)) {
+                heap.sift_down(0, K, d2, cp);
+                worst = heap.D(0);
+            }
+        };
+
+        // Stream the points of up to 32 cells (one per lane: `first`, `cnt`) past every query:
+        // load-balanced expansion, 32 coalesced candidate loads per batch staged in shared
+        // memory, every lane tests every staged candidate (broadcast reads).
+        auto process_cells = [&](uint32_t first, uint32_t cnt) {
+            const uint32_t incl = warp_incl_scan_u32(cnt, lane);
+            const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+            sa_off[lane] = incl - cnt; sa_off[32 + lane] = total; sa_base[lane] = first;
+            __syncwarp();
+            for (uint32_t b = 0; b < total; b += 32) {
+                const uint32_t i = b + lane;
+                if (i < total) {
+                    const int k = seg_search(sa_off, i);
+                    const uint32_t p = sa_base[k] + (i - sa_off[k]);
+                    c_xy[lane] = make_double2(a.sx[p], a.sy[p]); c_z[lane] = a.sz[p]; c_pos[lane] = p;
                 }
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) {
-                    double ov = __shfl_xor_sync(0xffffffffu, mymin, o);
-                    int oi = __shfl_xor_sync(0xffffffffu, myidx, o);
-                    if (ov < mymin || (ov == mymin && oi >= 0 && (myidx < 0 || oi < myidx))) { mymin = ov; myidx = oi; }
-                }
-                if (myidx < 0) break;                                  // list exhausted
-                const double wmax = warp_max_f64(done ? 0.0 : worst);
-                if (mymin > wmax) break;                               // everything left is pruned
-                const uint32_t cell = l_cell[myidx];
                 __syncwarp();
-                if (lane == 0) l_lb2[myidx] = inf;
-                const uint32_t first = __ldg(a.cell_first + cell);
-                const uint32_t cnt = __ldg(a.cell_first + cell + 1) - first;
-                for (uint32_t j0 = 0; j0 < cnt; j0 += 32) {
-                    const uint32_t p = first + j0 + lane;
-                    if (j0 + lane < cnt) { c_x[lane] = a.sx[p]; c_y[lane] = a.sy[p]; c_z[lane] = a.sz[p]; }
-                    __syncwarp();
-                    const int nc = (int)min(32u, cnt - j0);
-                    if (!done) {
-                        for (int c = 0; c < nc; ++c) {
-                            const double d2 = dist2(c_x[c], c_y[c], c_z[c], qx, qy, qz);
-                            const uint32_t cp = first + j0 + c;
-                            if (heap.cnt < K) {
-                                heap.push(d2, cp);
-                                if (heap.cnt == K) worst = heap.D(0);
-                            } else if (d2 <= worst) {
-                                if (heap.after(heap.D(0), heap.P(0), d2, cp)) {
-                                    heap.sift_down(0, K, d2, cp);
-                                    worst = heap.D(0);
-                                }
-                            }
+                const int nc = (int)min(32u, total - b);
+                if (!done) {
+                    for (int c = 0; c < nc; c += 4) {
+                        double d[4]; uint32_t pp[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const int cc = c + u < nc ? c + u : c;
+                            const double2 xy = c_xy[cc];
+                            d[u] = dist2(xy.x, xy.y, c_z[cc], qx, qy, qz);
+                            pp[u] = c_pos[cc];
                         }
+#pragma unroll
+                        for (int u = 0; u < 4; ++u)
+                            if (c + u < nc && d[u] <= worst) consider(d[u], pp[u]);
                     }
-                    __syncwarp();
+                }
+                __syncwarp();
+            }
+        };
+
+        // Process the listed fine cells in three rounds of decreasing urgency -- cells that
+        // overlap the group's bounding box, cells within half the current k-th distance, and
+        // whatever still passes the prune test -- with the bound refreshed for every batch of 32.
+        auto flush = [&]() {
+            for (int round = 0; round < 3 && list_n > 0; ++round) {
+                for (int j0 = 0; j0 < list_n; j0 += 32) {
+                    const int e = j0 + lane;
+                    const double wmax = warp_max_f64(done ? 0.0 : worst);
+                    const double thr = round == 0 ? 0.0 : (round == 1 ? 0.25 * wmax : wmax);
+                    const double lb = e < list_n ? l_lb2[e] : inf;
+                    const bool elig = lb <= thr;
+                    if (!__any_sync(0xffffffffu, elig)) continue;
+                    uint32_t first = 0, cnt = 0;
+                    if (elig) {
+                        l_lb2[e] = inf;
+                        const uint32_t cell = l_cell[e];
+                        first = __ldg(a.cell_first + cell);
+                        cnt = __ldg(a.cell_first + cell + 1) - first;
+                    }
+                    process_cells(first, cnt);
                 }
             }
             list_n = 0;
@@ -401,35 +460,37 @@ knn_search_kernel(SearchArgs a) {
                         }
                     }
                 }
-                // ---- list the fine cells of the super-cells found by this chunk
-                uint32_t have = __ballot_sync(0xffffffffu, f1 > f0);
-                while (have) {
-                    const int src = __ffs(have) - 1;
-                    have &= have - 1;
-                    const uint32_t e0 = __shfl_sync(0xffffffffu, f0, src);
-                    const uint32_t e1 = __shfl_sync(0xffffffffu, f1, src);
-                    for (uint32_t eb = e0; eb < e1; eb += 32) {
-                        const uint32_t e = eb + lane;
-                        bool keep = false;
-                        double lb = inf;
-                        if (e < e1) {
-                            const uint64_t key = __ldg(a.ucell + e);
-                            const int fx = (int)compact_bits21(key), fy = (int)compact_bits21(key >> 1), fz = (int)compact_bits21(key >> 2);
-                            lb = box_gap2(g.ox + fx * g.cell, g.oy + fy * g.cell, g.oz + fz * g.cell,
-                                          g.ox + (fx + 1) * g.cell, g.oy + (fy + 1) * g.cell, g.oz + (fz + 1) * g.cell,
-                                          bminx, bminy, bminz, bmaxx, bmaxy, bmaxz, g.slack);
-                            keep = !(lb > wmax_chunk);
+                // ---- list the fine cells of the super-cells found by this chunk (load-balanced)
+                const uint32_t fcnt = f1 - f0;
+                const uint32_t fincl = warp_incl_scan_u32(fcnt, lane);
+                const uint32_t ftotal = __shfl_sync(0xffffffffu, fincl, 31);
+                if (ftotal == 0) continue;
+                sb_off[lane] = fincl - fcnt; sb_off[32 + lane] = ftotal; sb_base[lane] = f0;
+                __syncwarp();
+                for (uint32_t b = 0; b < ftotal; b += 32) {
+                    const uint32_t i = b + lane;
+                    bool keep = false;
+                    double lb = inf;
+                    uint32_t e = 0;
+                    if (i < ftotal) {
+                        const int k = seg_search(sb_off, i);
+                        e = sb_base[k] + (i - sb_off[k]);
+                        const uint64_t key = __ldg(a.ucell + e);
+                        const int fx = (int)compact_bits21(key), fy = (int)compact_bits21(key >> 1), fz = (int)compact_bits21(key >> 2);
+                        lb = box_gap2(g.ox + fx * g.cell, g.oy + fy * g.cell, g.oz + fz * g.cell,
+                                      g.ox + (fx + 1) * g.cell, g.oy + (fy + 1) * g.cell, g.oz + (fz + 1) * g.cell,
+                                      bminx, bminy, bminz, bmaxx, bmaxy, bmaxz, g.slack);
+                        keep = !(lb > wmax_chunk);
+                    }
+                    const uint32_t kb = __ballot_sync(0xffffffffu, keep);
+                    if (kb) {
+                        if (list_n + 32 > kCellCap) flush();
+                        if (keep) {
+                            const int slot = list_n + __popc(kb & ((1u << lane) - 1u));
+                            l_lb2[slot] = lb; l_cell[slot] = e;
                         }
-                        const uint32_t kb = __ballot_sync(0xffffffffu, keep);
-                        if (kb) {
-                            if (list_n + 32 > kCellCap) { flush(); }
-                            if (keep) {
-                                const int slot = list_n + __popc(kb & ((1u << lane) - 1u));
-                                l_lb2[slot] = lb; l_cell[slot] = e;
-                            }
-                            list_n += __popc(kb);
-                            __syncwarp();
-                        }
+                        list_n += __popc(kb);
+                        __syncwarp();
                     }
                 }
             }
@@ -514,7 +575,7 @@ knn_search_kernel(SearchArgs a) {
 
 static inline int bits_for(int n) { int b = 0; while ((1 << b) < n) ++b; return b; }
 static inline size_t hash_capacity(int64_t cells) { size_t cap = 1024; while (cap < 2 * (size_t)cells) cap <<= 1; return cap; }
-template <int KMAX> constexpr size_t search_smem_bytes() { return (size_t)kSearchWarps * (KMAX * 32 * 12 + 96 * 8 + kCellCap * 12); }
+template <int KMAX> constexpr size_t search_smem_bytes() { return (size_t)kSearchWarps * SearchSmem<KMAX>::per_warp; }
 
 template <typename K>
 static int knn_impl(const double* d_x, const double* d_y, const double* d_z, int64_t n,
