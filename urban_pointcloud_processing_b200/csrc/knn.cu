@@ -403,7 +403,7 @@ knn_search_kernel(SearchArgs a) {
                     const double wmax = warp_max_f64(done ? 0.0 : worst);
                     const double thr = round == 0 ? 0.0 : (round == 1 ? 0.25 * wmax : wmax);
                     const double lb = e < list_n ? l_lb2[e] : inf;
-                    const bool elig = lb <= thr;
+                    const bool elig = lb < inf && lb <= thr;      // inf marks processed / absent entries
                     if (!__any_sync(0xffffffffu, elig)) continue;
                     uint32_t first = 0, cnt = 0;
                     if (elig) {
