@@ -1,5 +1,5 @@
 // S4 -- exact k-nearest-neighbour graph + hybrid-search normals + curvature
-// covariance over a uniform-grid cell list (RegionGrowing set-up).
+// covariance over a two-level uniform grid (RegionGrowing set-up).
 //
 // Restates what the reference obtains from Open3D (region_growing.py:59-73,86-92,
 // 105-109): KDTreeFlann.search_knn_vector_3d(p, k) for every point, estimate_normals
@@ -9,22 +9,26 @@
 // [ext, unverified -- see oracle/].
 //
 // Data structure (all in HBM, built per call):
-//   * selected points get a Morton key of their uniform-grid cell (cell size c);
-//     (key, compact id) pairs are radix-sorted; coordinates are gathered into sorted
-//     SoA arrays so that every cell is a contiguous, coalesced run;
-//   * unique cells + first-point offsets (cell list) and an open-addressing hash table
-//     cell key -> cell index (4 B slots, L2-resident);
-//   * query groups: <= 32 consecutive sorted points of one 4x4x4-cell super-cell.
-// Search: one warp per query group, one lane per query.  The warp walks the cells of the
-// group's bounding box ring by ring; each lane looks up one cell (hash), cells whose
-// distance to the group exceeds every lane's current k-th distance are pruned, the
-// points of the surviving cells are staged through shared memory with coalesced loads
-// and every lane tests every staged point (conflict-free broadcast reads).  Each lane
-// keeps its k best in a shared-memory max-heap; a lane is finished when its k-th
-// distance is smaller than its distance to the unexplored region.  The epilogue sorts
-// the heap, writes the kNN row, and accumulates the Open3D cumulant covariances /
-// FastEigen3x3 normal straight from the sorted list, so the 30-neighbour lists never
-// touch HBM.
+//   * selected points get the Morton key of their fine grid cell (edge c); (key, compact
+//     id) pairs are radix-sorted; coordinates are gathered into sorted SoA arrays so that
+//     every cell is a contiguous, coalesced run;
+//   * fine-cell list (unique keys + first-point offsets); super-cells (4x4x4 fine cells =
+//     key >> 6) are contiguous runs of the fine-cell list; an open-addressing hash table
+//     (4 B slots, L2-resident) maps a super-cell key to its run.
+// Search (knn_select_kernel): ONE WARP PER QUERY, one lane per candidate.
+//   * the warp walks super-cell rings around the query; each lane looks one super-cell up,
+//     the fine cells of the hits are listed (load-balanced) with their exact lower-bound
+//     distance to the query and pruned against the current k-th distance;
+//   * listed cells are processed nearest-first; 32 candidates are loaded coalesced per
+//     step, every lane computes one squared distance;
+//   * the k best are a warp-distributed sorted list in REGISTERS (lane j holds the j-th
+//     neighbour): batches with many hits are merged with a bitonic sort + bitonic merge,
+//     sparse hits are inserted with a ballot + shuffle shift.  No shared-memory heap, no
+//     divergence, occupancy bounded by registers only;
+//   * a query is finished when its k-th distance is smaller than its distance to the
+//     unexplored region (strict, with a conservative slack) -- so the result is exact.
+// Epilogue (knn_epilogue_kernel): one thread per query folds its sorted neighbour list in
+// order into the Open3D cumulant covariances / FastEigen3x3 normal and writes the kNN row.
 #include <math.h>
 #include "common.cuh"
 #include "primitives.cuh"
@@ -33,9 +37,11 @@
 namespace upcp {
 
 constexpr int kBlock = 256;
-constexpr int kSearchWarps = 4;
-constexpr int kSearchThreads = kSearchWarps * 32;
+constexpr int kSelWarps = 8;
+constexpr int kSelThreads = kSelWarps * 32;
+constexpr int kCellCap = 128;           // per-warp list of candidate fine cells
 constexpr uint32_t kEmpty = 0xffffffffu;
+constexpr uint32_t kFull = 0xffffffffu;
 
 struct GridParams {
     double ox, oy, oz, cell, inv_cell, slack;
@@ -74,6 +80,7 @@ __device__ __forceinline__ int cell_coord(double v, double origin, double inv_ce
     return (int)floor(t);
 }
 
+// ------------------------------------------------------------------ build ------
 struct KnnCompactIdx {
     uint32_t* sel_idx;
     __device__ void operator()(int64_t i, bool selected, uint32_t rank) const {
@@ -129,36 +136,6 @@ struct KnnCellFunctor {
     }
 };
 
-struct KnnSuperFunctor {     // super-cell run starts + super-cell index per sorted position
-    uint32_t* sc_first;
-    uint32_t* sc_of;
-    __device__ void operator()(int64_t s, bool is_first, uint32_t rank) const {
-        if (is_first) sc_first[rank] = (uint32_t)s;
-        sc_of[s] = rank + (is_first ? 1u : 0u) - 1u;
-    }
-};
-
-__global__ void __launch_bounds__(kBlock)
-knn_group_flags_kernel(const uint32_t* __restrict__ sc_first, const uint32_t* __restrict__ sc_of,
-                       int64_t m, uint8_t* __restrict__ flags) {
-    int64_t stride = (int64_t)gridDim.x * kBlock;
-    for (int64_t s = (int64_t)blockIdx.x * kBlock + threadIdx.x; s < m; s += stride)
-        flags[s] = (((uint32_t)s - sc_first[sc_of[s]]) & 31u) == 0 ? 1 : 0;
-}
-
-struct KnnGroupFunctor {
-    uint32_t* group_start;
-    __device__ void operator()(int64_t s, bool is_first, uint32_t rank) const {
-        if (is_first) group_start[rank] = (uint32_t)s;
-    }
-};
-
-__global__ void knn_finish_kernel(const uint32_t* __restrict__ n_cells, uint32_t* __restrict__ cell_first,
-                                  const uint32_t* __restrict__ n_groups, uint32_t* __restrict__ group_start,
-                                  uint32_t m) {
-    if (threadIdx.x == 0 && blockIdx.x == 0) { cell_first[*n_cells] = m; group_start[*n_groups] = m; }
-}
-
 struct KnnScCellFunctor {    // super-cell runs over the fine-cell list
     const uint64_t* ucell;
     uint64_t* sc_key;
@@ -168,106 +145,44 @@ struct KnnScCellFunctor {    // super-cell runs over the fine-cell list
     }
 };
 
+__global__ void knn_finish_cells_kernel(const uint32_t* __restrict__ n_cells, uint32_t* __restrict__ cell_first,
+                                        uint32_t m) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) cell_first[*n_cells] = m;
+}
+
 __global__ void knn_finish_sc_kernel(const uint32_t* __restrict__ n_sc, uint32_t* __restrict__ sc_cell_first,
                                      uint32_t c_total) {
     if (threadIdx.x == 0 && blockIdx.x == 0) sc_cell_first[*n_sc] = c_total;
 }
 
 __global__ void __launch_bounds__(kBlock)
-knn_hash_insert_kernel(const uint64_t* __restrict__ ucell, const uint32_t* __restrict__ n_cells,
+knn_hash_insert_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ n_keys,
                        uint32_t* __restrict__ table, uint32_t table_mask) {
-    const uint32_t c_total = *n_cells;
+    const uint32_t total = *n_keys;
     uint32_t stride = gridDim.x * kBlock;
-    for (uint32_t c = blockIdx.x * kBlock + threadIdx.x; c < c_total; c += stride) {
-        uint32_t h = (uint32_t)hash64(ucell[c]) & table_mask;
+    for (uint32_t c = blockIdx.x * kBlock + threadIdx.x; c < total; c += stride) {
+        uint32_t h = (uint32_t)hash64(keys[c]) & table_mask;
         while (atomicCAS(&table[h], kEmpty, c) != kEmpty) h = (h + 1) & table_mask;
     }
 }
 
 // ------------------------------------------------------------------ search ------
-constexpr int kCellCap = 160;      // per-warp list of candidate fine cells (flushed when nearly full)
-
-struct SearchArgs {
+struct SelectArgs {
     const double* sx; const double* sy; const double* sz;   // sorted coordinates
     const uint32_t* perm;          // sorted position -> compact id
     const uint64_t* ucell; const uint32_t* cell_first;       // fine cells (Morton keys, first point)
     const uint64_t* sc_key; const uint32_t* sc_cell_first;   // super-cells (key >> 6, first fine cell)
     const uint32_t* table; uint32_t table_mask;              // hash: super-cell key -> super-cell index
-    const uint32_t* group_start; const uint32_t* n_groups;
     GridParams g;
     int64_t m;
-    int k_heap;                    // max(knn, max_nn) clipped to m
-    int knn, max_nn;
-    double radius2;
-    int32_t* out_knn; double* out_d2; double* out_normals; double* out_cov; double* out_curv;
+    int k;                         // neighbours kept per query (<= 32), clipped to m
+    uint32_t* out_pos;             // [m][32] sorted positions of the k nearest (row = sorted position of the query)
 };
-
-template <int KMAX>
-struct LaneHeap {
-    // max-heap over (d2, compact id); storage [slot][lane] in shared memory
-    double* d2; uint32_t* pos; const uint32_t* perm; int lane; int cnt;
-    __device__ __forceinline__ double& D(int i) { return d2[i * 32 + lane]; }
-    __device__ __forceinline__ uint32_t& P(int i) { return pos[i * 32 + lane]; }
-    // (da, pa) ranks after (db, pb) in ascending (d2, compact id) order
-    __device__ __forceinline__ bool after(double da, uint32_t pa, double db, uint32_t pb) const {
-        if (da != db) return da > db;
-        return __ldg(perm + pa) > __ldg(perm + pb);
-    }
-    __device__ __forceinline__ void sift_down(int i, int n, double vd, uint32_t vp) {
-        while (true) {
-            int c = 2 * i + 1;
-            if (c >= n) break;
-            double cd = D(c); uint32_t cp = P(c);
-            if (c + 1 < n) {
-                double rd = D(c + 1); uint32_t rp = P(c + 1);
-                if (after(rd, rp, cd, cp)) { c = c + 1; cd = rd; cp = rp; }
-            }
-            if (!after(cd, cp, vd, vp)) break;
-            D(i) = cd; P(i) = cp;
-            i = c;
-        }
-        D(i) = vd; P(i) = vp;
-    }
-    __device__ __forceinline__ void push(double vd, uint32_t vp) {   // cnt < capacity
-        int i = cnt++;
-        while (i > 0) {
-            int p = (i - 1) >> 1;
-            double pd = D(p); uint32_t pp = P(p);
-            if (!after(vd, vp, pd, pp)) break;
-            D(i) = pd; P(i) = pp;
-            i = p;
-        }
-        D(i) = vd; P(i) = vp;
-    }
-    __device__ __forceinline__ void sort_ascending() {
-        for (int end = cnt - 1; end > 0; --end) {
-            double vd = D(end); uint32_t vp = P(end);
-            D(end) = D(0); P(end) = P(0);
-            sift_down(0, end, vd, vp);
-        }
-    }
-};
-
-__device__ __forceinline__ double warp_max_f64(double v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
-    return v;
-}
-
-// conservative squared distance between the axis-aligned box [lo, hi] and the box [bmin, bmax]
-__device__ __forceinline__ double box_gap2(double lox, double loy, double loz, double hix, double hiy, double hiz,
-                                           double bminx, double bminy, double bminz,
-                                           double bmaxx, double bmaxy, double bmaxz, double slack) {
-    double gx = fmax(0.0, fmax(lox - bmaxx, bminx - hix) - slack);
-    double gy = fmax(0.0, fmax(loy - bmaxy, bminy - hiy) - slack);
-    double gz = fmax(0.0, fmax(loz - bmaxz, bminz - hiz) - slack);
-    return (gx * gx + gy * gy + gz * gz) * (1.0 - 1e-9);
-}
 
 __device__ __forceinline__ uint32_t warp_incl_scan_u32(uint32_t v, int lane) {
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-        uint32_t t = __shfl_up_sync(0xffffffffu, v, o);
+        uint32_t t = __shfl_up_sync(kFull, v, o);
         if (lane >= o) v += t;
     }
     return v;
@@ -282,129 +197,151 @@ __device__ __forceinline__ int seg_search(const uint32_t* off, uint32_t i) {
     return k;
 }
 
-// per-warp shared memory carve-up (bytes)
-template <int KMAX> struct SearchSmem {
-    static constexpr size_t heap_d2 = 0;
-    static constexpr size_t heap_pos = heap_d2 + (size_t)KMAX * 32 * 8;
-    static constexpr size_t c_xy = heap_pos + (size_t)KMAX * 32 * 4;       // double2[32]
-    static constexpr size_t c_z = c_xy + 32 * 16;                           // double[32]
-    static constexpr size_t l_lb2 = c_z + 32 * 8;                           // double[kCellCap]
-    static constexpr size_t l_cell = l_lb2 + (size_t)kCellCap * 8;          // u32[kCellCap]
-    static constexpr size_t c_pos = l_cell + (size_t)kCellCap * 4;          // u32[32]
-    static constexpr size_t seg_a = c_pos + 32 * 4;                         // u32[64 + 32] candidate expansion
-    static constexpr size_t seg_b = seg_a + 96 * 4;                         // u32[64 + 32] cell listing
-    static constexpr size_t per_warp = ((seg_b + 96 * 4) + 15) / 16 * 16;
-};
+// conservative squared distance between the point q and the axis-aligned box [lo, hi]
+__device__ __forceinline__ double point_box_gap2(double qx, double qy, double qz,
+                                                 double lox, double loy, double loz,
+                                                 double hix, double hiy, double hiz, double slack) {
+    double gx = fmax(0.0, fmax(lox - qx, qx - hix) - slack);
+    double gy = fmax(0.0, fmax(loy - qy, qy - hiy) - slack);
+    double gz = fmax(0.0, fmax(loz - qz, qz - hiz) - slack);
+    return (gx * gx + gy * gy + gz * gz) * (1.0 - 1e-9);
+}
 
-template <int KMAX>
-__global__ void __launch_bounds__(kSearchThreads)
-knn_search_kernel(SearchArgs a) {
-    extern __shared__ __align__(16) unsigned char knn_smem[];
+// One entry of the warp-distributed neighbour list: (squared distance, compact id) is the
+// sort key, p the sorted position of the point.
+struct Nb {
+    double d; uint32_t c; uint32_t p;
+};
+__device__ __forceinline__ bool nb_less(double da, uint32_t ca, double db, uint32_t cb) {
+    return da < db || (da == db && ca < cb);
+}
+__device__ __forceinline__ Nb nb_shfl_xor(const Nb& v, int j) {
+    Nb r;
+    r.d = __shfl_xor_sync(kFull, v.d, j); r.c = __shfl_xor_sync(kFull, v.c, j); r.p = __shfl_xor_sync(kFull, v.p, j);
+    return r;
+}
+__device__ __forceinline__ Nb nb_shfl(const Nb& v, int src) {
+    Nb r;
+    r.d = __shfl_sync(kFull, v.d, src); r.c = __shfl_sync(kFull, v.c, src); r.p = __shfl_sync(kFull, v.p, src);
+    return r;
+}
+// compare-exchange with lane ^ j; keep the smaller element when `keep_min`
+__device__ __forceinline__ void nb_cx(Nb& v, int j, bool keep_min) {
+    const Nb o = nb_shfl_xor(v, j);
+    const bool o_less = nb_less(o.d, o.c, v.d, v.c);
+    if (o_less == keep_min) v = o;
+}
+// full ascending bitonic sort of 32 entries (one per lane)
+__device__ __forceinline__ void nb_sort32(Nb& v, int lane) {
+#pragma unroll
+    for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            const bool asc = (lane & k) == 0 || k == 32;
+            const bool lower = (lane & j) == 0;
+            nb_cx(v, j, lower == asc);
+        }
+    }
+}
+// ascending sort of a bitonic sequence of 32 entries
+__device__ __forceinline__ void nb_merge32(Nb& v, int lane) {
+#pragma unroll
+    for (int j = 16; j > 0; j >>= 1) nb_cx(v, j, (lane & j) == 0);
+}
+
+__global__ void __launch_bounds__(kSelThreads)
+knn_select_kernel(SelectArgs a) {
+    // per-warp shared memory: candidate-cell list + two load-balancing scratch areas
+    __shared__ double s_lb2[kSelWarps][kCellCap];
+    __shared__ uint32_t s_cell[kSelWarps][kCellCap];
+    __shared__ uint32_t s_seg[kSelWarps][2][96];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    using L = SearchSmem<KMAX>;
-    unsigned char* const wbase = knn_smem + (size_t)warp * L::per_warp;
-    double* const w_heap_d2 = reinterpret_cast<double*>(wbase + L::heap_d2);
-    uint32_t* const w_heap_pos = reinterpret_cast<uint32_t*>(wbase + L::heap_pos);
-    double2* const c_xy = reinterpret_cast<double2*>(wbase + L::c_xy);
-    double* const c_z = reinterpret_cast<double*>(wbase + L::c_z);
-    double* const l_lb2 = reinterpret_cast<double*>(wbase + L::l_lb2);
-    uint32_t* const l_cell = reinterpret_cast<uint32_t*>(wbase + L::l_cell);
-    uint32_t* const c_pos = reinterpret_cast<uint32_t*>(wbase + L::c_pos);
-    uint32_t* const sa_off = reinterpret_cast<uint32_t*>(wbase + L::seg_a);      // [64]: 32 offsets + 32 x total
-    uint32_t* const sa_base = sa_off + 64;
-    uint32_t* const sb_off = reinterpret_cast<uint32_t*>(wbase + L::seg_b);
-    uint32_t* const sb_base = sb_off + 64;
+    double* const l_lb2 = s_lb2[warp];
+    uint32_t* const l_cell = s_cell[warp];
+    uint32_t* const sa_off = s_seg[warp][0]; uint32_t* const sa_base = sa_off + 64;
+    uint32_t* const sb_off = s_seg[warp][1]; uint32_t* const sb_base = sb_off + 64;
 
     const GridParams g = a.g;
-    const uint32_t n_groups = *a.n_groups;
-    const int K = a.k_heap;
+    const int K = a.k;
     const double inf = __longlong_as_double(0x7ff0000000000000LL);
     const double scell = 4.0 * g.cell;                       // super-cell edge
     const int nsx = (g.nx + 3) >> 2, nsy = (g.ny + 3) >> 2, nsz = (g.nz + 3) >> 2;
 
-    for (uint32_t grp = blockIdx.x * kSearchWarps + warp; grp < n_groups; grp += gridDim.x * kSearchWarps) {
-        const uint32_t gs = a.group_start[grp];
-        const int gcount = (int)(a.group_start[grp + 1] - gs);
-        const bool valid = lane < gcount;
-        const uint32_t qpos = gs + (valid ? lane : 0);
-        const double qx = a.sx[qpos], qy = a.sy[qpos], qz = a.sz[qpos];
-        // every query of a group lies in the same super-cell (groups never straddle one)
+    for (int64_t q = (int64_t)blockIdx.x * kSelWarps + warp; q < a.m; q += (int64_t)gridDim.x * kSelWarps) {
+        const double qx = a.sx[q], qy = a.sy[q], qz = a.sz[q];
         const int sx = cell_coord(qx, g.ox, g.inv_cell, g.nx) >> 2;
         const int sy = cell_coord(qy, g.oy, g.inv_cell, g.ny) >> 2;
         const int sz = cell_coord(qz, g.oz, g.inv_cell, g.nz) >> 2;
-        // bounding box of the group's queries (invalid lanes alias lane 0)
-        double bminx = qx, bminy = qy, bminz = qz, bmaxx = qx, bmaxy = qy, bmaxz = qz;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            bminx = fmin(bminx, __shfl_xor_sync(0xffffffffu, bminx, o)); bmaxx = fmax(bmaxx, __shfl_xor_sync(0xffffffffu, bmaxx, o));
-            bminy = fmin(bminy, __shfl_xor_sync(0xffffffffu, bminy, o)); bmaxy = fmax(bmaxy, __shfl_xor_sync(0xffffffffu, bmaxy, o));
-            bminz = fmin(bminz, __shfl_xor_sync(0xffffffffu, bminz, o)); bmaxz = fmax(bmaxz, __shfl_xor_sync(0xffffffffu, bmaxz, o));
-        }
 
-        LaneHeap<KMAX> heap;
-        heap.d2 = w_heap_d2; heap.pos = w_heap_pos; heap.perm = a.perm; heap.lane = lane; heap.cnt = 0;
-        bool done = !valid;
-        double worst = inf;         // k-th best squared distance once the heap is full
-        int list_n = 0;             // warp-uniform
+        Nb mine; mine.d = inf; mine.c = kFull; mine.p = 0;   // lane j: j-th nearest so far
+        double kth_d = inf; uint32_t kth_c = kFull;          // the K-th entry (lane K-1), warp-uniform
+        int list_n = 0;                                      // warp-uniform
 
-        auto consider = [&](double d2, uint32_t cp) {
-            if (heap.cnt < K) {
-                heap.push(d2, cp);
-                if (heap.cnt == K) worst = heap.D(0);
-            } else if (heap.after(heap.D(0), heap.P(0), d2, cp)) {
-                heap.sift_down(0, K, d2, cp);
-                worst = heap.D(0);
-            }
+        auto refresh_kth = [&]() {
+            kth_d = __shfl_sync(kFull, mine.d, K - 1);
+            kth_c = __shfl_sync(kFull, mine.c, K - 1);
         };
 
-        // Stream the points of up to 32 cells (one per lane: `first`, `cnt`) past every query:
-        // load-balanced expansion, 32 coalesced candidate loads per batch staged in shared
-        // memory, every lane tests every staged candidate (broadcast reads).
+        // Stream the points of up to 32 cells (one per lane: first, cnt) past the query.
         auto process_cells = [&](uint32_t first, uint32_t cnt) {
             const uint32_t incl = warp_incl_scan_u32(cnt, lane);
-            const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+            const uint32_t total = __shfl_sync(kFull, incl, 31);
             sa_off[lane] = incl - cnt; sa_off[32 + lane] = total; sa_base[lane] = first;
             __syncwarp();
             for (uint32_t b = 0; b < total; b += 32) {
                 const uint32_t i = b + lane;
+                Nb cand; cand.d = inf; cand.c = kFull; cand.p = 0;
                 if (i < total) {
-                    const int k = seg_search(sa_off, i);
-                    const uint32_t p = sa_base[k] + (i - sa_off[k]);
-                    c_xy[lane] = make_double2(a.sx[p], a.sy[p]); c_z[lane] = a.sz[p]; c_pos[lane] = p;
+                    const int kk = seg_search(sa_off, i);
+                    const uint32_t p = sa_base[kk] + (i - sa_off[kk]);
+                    cand.d = dist2(a.sx[p], a.sy[p], a.sz[p], qx, qy, qz);
+                    cand.c = __ldg(a.perm + p);
+                    cand.p = p;
                 }
-                __syncwarp();
-                const int nc = (int)min(32u, total - b);
-                if (!done) {
-                    for (int c = 0; c < nc; c += 4) {
-                        double d[4]; uint32_t pp[4];
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            const int cc = c + u < nc ? c + u : c;
-                            const double2 xy = c_xy[cc];
-                            d[u] = dist2(xy.x, xy.y, c_z[cc], qx, qy, qz);
-                            pp[u] = c_pos[cc];
-                        }
-#pragma unroll
-                        for (int u = 0; u < 4; ++u)
-                            if (c + u < nc && d[u] <= worst) consider(d[u], pp[u]);
+                bool pass = nb_less(cand.d, cand.c, kth_d, kth_c);
+                uint32_t hits = __ballot_sync(kFull, pass);
+                if (hits == 0) continue;
+                if (__popc(hits) > 8) {
+                    // batch merge: sort the 32 candidates, keep the 32 smallest of list + batch
+                    if (!pass) { cand.d = inf; cand.c = kFull; }
+                    nb_sort32(cand, lane);
+                    const Nb rev = nb_shfl(cand, 31 - lane);
+                    if (nb_less(rev.d, rev.c, mine.d, mine.c)) mine = rev;
+                    nb_merge32(mine, lane);
+                    if (lane >= K) { mine.d = inf; mine.c = kFull; }
+                    refresh_kth();
+                } else {
+                    // sparse hits: insert one by one (ballot + shuffle shift)
+                    while (hits) {
+                        const int src = __ffs(hits) - 1;
+                        hits &= hits - 1;
+                        const Nb nw = nb_shfl(cand, src);
+                        if (!nb_less(nw.d, nw.c, kth_d, kth_c)) continue;        // k-th moved meanwhile
+                        const bool before = nb_less(mine.d, mine.c, nw.d, nw.c);   // my entry stays in front
+                        const int at = __popc(__ballot_sync(kFull, before));       // insertion rank
+                        Nb up;
+                        up.d = __shfl_up_sync(kFull, mine.d, 1); up.c = __shfl_up_sync(kFull, mine.c, 1);
+                        up.p = __shfl_up_sync(kFull, mine.p, 1);
+                        if (lane == at) mine = nw; else if (lane > at) mine = up;
+                        if (lane >= K) { mine.d = inf; mine.c = kFull; }
+                        refresh_kth();
                     }
                 }
-                __syncwarp();
             }
+            __syncwarp();
         };
 
-        // Process the listed fine cells in three rounds of decreasing urgency -- cells that
-        // overlap the group's bounding box, cells within half the current k-th distance, and
-        // whatever still passes the prune test -- with the bound refreshed for every batch of 32.
+        // Process the listed fine cells nearest-first in three rounds (cells containing the
+        // query, cells within a quarter of the current k-th squared distance, the rest), each
+        // batch re-checked against the current k-th distance.
         auto flush = [&]() {
             for (int round = 0; round < 3 && list_n > 0; ++round) {
                 for (int j0 = 0; j0 < list_n; j0 += 32) {
                     const int e = j0 + lane;
-                    const double wmax = warp_max_f64(done ? 0.0 : worst);
-                    const double thr = round == 0 ? 0.0 : (round == 1 ? 0.25 * wmax : wmax);
+                    const double thr = round == 0 ? 0.0 : (round == 1 ? 0.25 * kth_d : kth_d);
                     const double lb = e < list_n ? l_lb2[e] : inf;
                     const bool elig = lb < inf && lb <= thr;      // inf marks processed / absent entries
-                    if (!__any_sync(0xffffffffu, elig)) continue;
+                    if (!__any_sync(kFull, elig)) continue;
                     uint32_t first = 0, cnt = 0;
                     if (elig) {
                         l_lb2[e] = inf;
@@ -419,15 +356,13 @@ knn_search_kernel(SearchArgs a) {
         };
 
         for (int R = 0;; ++R) {
-            // ---- enumerate the super-cells of ring R (R = 0: the group's own super-cell)
+            // ---- enumerate the super-cells of ring R (R = 0: the query's own super-cell)
             const int w = 2 * R + 1, v = 2 * R - 1;
             const int A = w * w, B = R > 0 ? w * v : 0, C = R > 0 ? v * v : 0;
             const int total = R == 0 ? 1 : 2 * A + 2 * B + 2 * C;
             for (int t0 = 0; t0 < total; t0 += 32) {
                 int t = t0 + lane;
                 uint32_t f0 = 0, f1 = 0;
-                // prune bound: the largest k-th distance among the unfinished lanes
-                const double wmax_chunk = warp_max_f64(done ? 0.0 : worst);
                 if (t < total) {
                     int cx, cy, cz;
                     if (R == 0) { cx = sx; cy = sy; cz = sz; }
@@ -444,26 +379,28 @@ knn_search_kernel(SearchArgs a) {
                         cy = sy - R + 1 + t % v; cz = sz - R + 1 + t / v;
                     }
                     if (cx >= 0 && cy >= 0 && cz >= 0 && cx < nsx && cy < nsy && cz < nsz) {
-                        const double lb = box_gap2(g.ox + cx * scell, g.oy + cy * scell, g.oz + cz * scell,
-                                                   g.ox + (cx + 1) * scell, g.oy + (cy + 1) * scell, g.oz + (cz + 1) * scell,
-                                                   bminx, bminy, bminz, bmaxx, bmaxy, bmaxz, g.slack);
-                        const uint64_t key = morton3(cx, cy, cz);
-                        uint32_t h = (uint32_t)hash64(key) & a.table_mask;
-                        while (!(lb > wmax_chunk)) {
-                            uint32_t idx = __ldg(a.table + h);
-                            if (idx == kEmpty) break;
-                            if (__ldg(a.sc_key + idx) == key) {
-                                f0 = __ldg(a.sc_cell_first + idx); f1 = __ldg(a.sc_cell_first + idx + 1);
-                                break;
+                        const double lb = point_box_gap2(qx, qy, qz, g.ox + cx * scell, g.oy + cy * scell, g.oz + cz * scell,
+                                                         g.ox + (cx + 1) * scell, g.oy + (cy + 1) * scell,
+                                                         g.oz + (cz + 1) * scell, g.slack);
+                        if (!(lb > kth_d)) {
+                            const uint64_t key = morton3(cx, cy, cz);
+                            uint32_t h = (uint32_t)hash64(key) & a.table_mask;
+                            while (true) {
+                                const uint32_t idx = __ldg(a.table + h);
+                                if (idx == kEmpty) break;
+                                if (__ldg(a.sc_key + idx) == key) {
+                                    f0 = __ldg(a.sc_cell_first + idx); f1 = __ldg(a.sc_cell_first + idx + 1);
+                                    break;
+                                }
+                                h = (h + 1) & a.table_mask;
                             }
-                            h = (h + 1) & a.table_mask;
                         }
                     }
                 }
                 // ---- list the fine cells of the super-cells found by this chunk (load-balanced)
                 const uint32_t fcnt = f1 - f0;
                 const uint32_t fincl = warp_incl_scan_u32(fcnt, lane);
-                const uint32_t ftotal = __shfl_sync(0xffffffffu, fincl, 31);
+                const uint32_t ftotal = __shfl_sync(kFull, fincl, 31);
                 if (ftotal == 0) continue;
                 sb_off[lane] = fincl - fcnt; sb_off[32 + lane] = ftotal; sb_base[lane] = f0;
                 __syncwarp();
@@ -473,16 +410,16 @@ knn_search_kernel(SearchArgs a) {
                     double lb = inf;
                     uint32_t e = 0;
                     if (i < ftotal) {
-                        const int k = seg_search(sb_off, i);
-                        e = sb_base[k] + (i - sb_off[k]);
+                        const int kk = seg_search(sb_off, i);
+                        e = sb_base[kk] + (i - sb_off[kk]);
                         const uint64_t key = __ldg(a.ucell + e);
                         const int fx = (int)compact_bits21(key), fy = (int)compact_bits21(key >> 1), fz = (int)compact_bits21(key >> 2);
-                        lb = box_gap2(g.ox + fx * g.cell, g.oy + fy * g.cell, g.oz + fz * g.cell,
-                                      g.ox + (fx + 1) * g.cell, g.oy + (fy + 1) * g.cell, g.oz + (fz + 1) * g.cell,
-                                      bminx, bminy, bminz, bmaxx, bmaxy, bmaxz, g.slack);
-                        keep = !(lb > wmax_chunk);
+                        lb = point_box_gap2(qx, qy, qz, g.ox + fx * g.cell, g.oy + fy * g.cell, g.oz + fz * g.cell,
+                                            g.ox + (fx + 1) * g.cell, g.oy + (fy + 1) * g.cell, g.oz + (fz + 1) * g.cell,
+                                            g.slack);
+                        keep = !(lb > kth_d);
                     }
-                    const uint32_t kb = __ballot_sync(0xffffffffu, keep);
+                    const uint32_t kb = __ballot_sync(kFull, keep);
                     if (kb) {
                         if (list_n + 32 > kCellCap) flush();
                         if (keep) {
@@ -493,89 +430,98 @@ knn_search_kernel(SearchArgs a) {
                         __syncwarp();
                     }
                 }
+                __syncwarp();
             }
             flush();
-            // ---- termination: distance from the query to the unexplored region
+            // ---- termination: distance from the query to the unexplored region (warp-uniform)
             const bool open_x0 = sx - R > 0, open_x1 = sx + R < nsx - 1;
             const bool open_y0 = sy - R > 0, open_y1 = sy + R < nsy - 1;
             const bool open_z0 = sz - R > 0, open_z1 = sz + R < nsz - 1;
-            if (!done) {
-                double reach = inf;
-                if (open_x0) reach = fmin(reach, qx - (g.ox + (sx - R) * scell));
-                if (open_x1) reach = fmin(reach, (g.ox + (sx + R + 1) * scell) - qx);
-                if (open_y0) reach = fmin(reach, qy - (g.oy + (sy - R) * scell));
-                if (open_y1) reach = fmin(reach, (g.oy + (sy + R + 1) * scell) - qy);
-                if (open_z0) reach = fmin(reach, qz - (g.oz + (sz - R) * scell));
-                if (open_z1) reach = fmin(reach, (g.oz + (sz + R + 1) * scell) - qz);
-                reach -= g.slack;
-                if (reach == inf) done = true;                      // whole grid explored
-                else if (heap.cnt == K && reach > 0.0 && worst < reach * reach * (1.0 - 1e-9)) done = true;
-            }
-            if (__all_sync(0xffffffffu, done)) break;
-            if (!(open_x0 || open_x1 || open_y0 || open_y1 || open_z0 || open_z1)) break;
+            if (!(open_x0 || open_x1 || open_y0 || open_y1 || open_z0 || open_z1)) break;   // whole grid explored
+            double reach = inf;
+            if (open_x0) reach = fmin(reach, qx - (g.ox + (sx - R) * scell));
+            if (open_x1) reach = fmin(reach, (g.ox + (sx + R + 1) * scell) - qx);
+            if (open_y0) reach = fmin(reach, qy - (g.oy + (sy - R) * scell));
+            if (open_y1) reach = fmin(reach, (g.oy + (sy + R + 1) * scell) - qy);
+            if (open_z0) reach = fmin(reach, qz - (g.oz + (sz - R) * scell));
+            if (open_z1) reach = fmin(reach, (g.oz + (sz + R + 1) * scell) - qz);
+            reach -= g.slack;
+            if (kth_d < inf && reach > 0.0 && kth_d < reach * reach * (1.0 - 1e-9)) break;
         }
+        // sorted positions of the neighbours (kFull = absent); one coalesced 128-byte row
+        a.out_pos[(size_t)q * 32 + lane] = (lane < K && mine.d < inf) ? mine.p : kFull;
+    }
+}
 
-        // --- epilogue: sort, write the kNN row, covariance / normal from the sorted list
-        if (valid) {
-            heap.sort_ascending();
-            const int cnt = heap.cnt;
-            const uint32_t cid = a.perm[qpos];
-            if (a.out_knn) {
-                for (int j = 0; j < a.knn; ++j)
-                    a.out_knn[(size_t)cid * a.knn + j] = j < cnt ? (int32_t)__ldg(a.perm + heap.P(j)) : -1;
+// ------------------------------------------------------------------ epilogue ----
+struct EpilogueArgs {
+    const double* sx; const double* sy; const double* sz;
+    const uint32_t* perm; const uint32_t* pos;      // pos: [m][32]
+    int64_t m;
+    int knn, max_nn;
+    double radius2;
+    int32_t* out_knn; double* out_d2; double* out_normals; double* out_cov; double* out_curv;
+};
+
+__global__ void __launch_bounds__(kBlock)
+knn_epilogue_kernel(EpilogueArgs a) {
+    const double inf = __longlong_as_double(0x7ff0000000000000LL);
+    int64_t stride = (int64_t)gridDim.x * kBlock;
+    for (int64_t s = (int64_t)blockIdx.x * kBlock + threadIdx.x; s < a.m; s += stride) {
+        const uint32_t* row = a.pos + (size_t)s * 32;
+        const double qx = a.sx[s], qy = a.sy[s], qz = a.sz[s];
+        const uint32_t cid = a.perm[s];
+        Cumulants nrm_cum; nrm_cum.clear();       // hybrid search: max_nn nearest with d2 < r^2
+        Cumulants cov_cum; cov_cum.clear();       // the knn-neighbourhood (region_growing.py:69-71)
+        int nn = 0, kk = 0;
+        bool in_radius = true;
+        const int lim = a.knn > a.max_nn ? a.knn : a.max_nn;
+        for (int j = 0; j < lim; ++j) {
+            const uint32_t p = __ldg(row + j);
+            const bool present = p != kFull;
+            double px = 0, py = 0, pz = 0, d2 = inf;
+            if (present) {
+                px = a.sx[p]; py = a.sy[p]; pz = a.sz[p];
+                d2 = dist2(px, py, pz, qx, qy, qz);
             }
-            if (a.out_d2) {
-                for (int j = 0; j < a.knn; ++j)
-                    a.out_d2[(size_t)cid * a.knn + j] = j < cnt ? heap.D(j) : inf;
+            if (j < a.knn) {
+                if (a.out_knn) a.out_knn[(size_t)cid * a.knn + j] = present ? (int32_t)__ldg(a.perm + p) : -1;
+                if (a.out_d2) a.out_d2[(size_t)cid * a.knn + j] = d2;
+                if (present) { cov_cum.add(px, py, pz); ++kk; }
             }
-            if (a.out_normals) {
-                // KDTreeSearchParamHybrid: the max_nn nearest, of those the ones with d2 < r^2
-                Cumulants cum; cum.clear();
-                int nn = 0;
-                const int lim = cnt < a.max_nn ? cnt : a.max_nn;
-                for (int j = 0; j < lim; ++j) {
-                    if (!(heap.D(j) < a.radius2)) break;
-                    const uint32_t p = heap.P(j);
-                    cum.add(a.sx[p], a.sy[p], a.sz[p]);
-                    ++nn;
-                }
-                Vec3 nrm = {0.0, 0.0, 1.0};
-                if (nn >= 3) {
-                    double cov6[6];
-                    cum.finish(nn, cov6);
-                    nrm = normal_from_cov(cov6, nullptr);
-                }
-                a.out_normals[(size_t)cid * 3 + 0] = nrm.x;
-                a.out_normals[(size_t)cid * 3 + 1] = nrm.y;
-                a.out_normals[(size_t)cid * 3 + 2] = nrm.z;
-            }
-            if (a.out_cov || a.out_curv) {
-                // compute_mean_and_covariance of the k-neighbourhood (region_growing.py:69-71)
-                Cumulants cum; cum.clear();
-                const int kk = cnt < a.knn ? cnt : a.knn;
-                for (int j = 0; j < kk; ++j) {
-                    const uint32_t p = heap.P(j);
-                    cum.add(a.sx[p], a.sy[p], a.sz[p]);
-                }
-                double cov6[6];
-                cum.finish(kk > 0 ? kk : 1, cov6);
-                if (a.out_cov)
-                    for (int q = 0; q < 6; ++q) a.out_cov[(size_t)cid * 6 + q] = cov6[q];
-                if (a.out_curv) {
-                    double ev[3];
-                    fast_eigen3x3(cov6, ev);
-                    double sum = ev[0] + ev[1] + ev[2];
-                    for (int q = 0; q < 3; ++q) a.out_curv[(size_t)cid * 3 + q] = ev[q] / sum;
-                }
+            if (j < a.max_nn && present && in_radius) {
+                if (d2 < a.radius2) { nrm_cum.add(px, py, pz); ++nn; }
+                else in_radius = false;            // sorted ascending: nothing closer follows
             }
         }
-        __syncwarp();
+        if (a.out_normals) {
+            Vec3 nrm = {0.0, 0.0, 1.0};
+            if (nn >= 3) {
+                double cov6[6];
+                nrm_cum.finish(nn, cov6);
+                nrm = normal_from_cov(cov6, nullptr);
+            }
+            a.out_normals[(size_t)cid * 3 + 0] = nrm.x;
+            a.out_normals[(size_t)cid * 3 + 1] = nrm.y;
+            a.out_normals[(size_t)cid * 3 + 2] = nrm.z;
+        }
+        if (a.out_cov || a.out_curv) {
+            double cov6[6];
+            cov_cum.finish(kk > 0 ? kk : 1, cov6);
+            if (a.out_cov)
+                for (int t = 0; t < 6; ++t) a.out_cov[(size_t)cid * 6 + t] = cov6[t];
+            if (a.out_curv) {
+                double ev[3];
+                fast_eigen3x3(cov6, ev);
+                double sum = ev[0] + ev[1] + ev[2];
+                for (int t = 0; t < 3; ++t) a.out_curv[(size_t)cid * 3 + t] = ev[t] / sum;
+            }
+        }
     }
 }
 
 static inline int bits_for(int n) { int b = 0; while ((1 << b) < n) ++b; return b; }
 static inline size_t hash_capacity(int64_t cells) { size_t cap = 1024; while (cap < 2 * (size_t)cells) cap <<= 1; return cap; }
-template <int KMAX> constexpr size_t search_smem_bytes() { return (size_t)kSearchWarps * SearchSmem<KMAX>::per_warp; }
 
 template <typename K>
 static int knn_impl(const double* d_x, const double* d_y, const double* d_z, int64_t n,
@@ -584,7 +530,7 @@ static int knn_impl(const double* d_x, const double* d_y, const double* d_z, int
                     int32_t* d_knn, double* d_knn_d2, double* d_normals, double* d_cov, double* d_curv,
                     void* d_ws, size_t ws_bytes, cudaStream_t st) {
     Workspace ws(d_ws, ws_bytes);
-    uint32_t* counters = ws.take<uint32_t>(64);          // [0] m, [1] n_cells, [2] n_super, [3] n_groups
+    uint32_t* counters = ws.take<uint32_t>(64);          // [0] m, [1] n_cells, [4] n_super
     uint32_t* sel_idx = d_sel ? ws.take<uint32_t>((size_t)n) : nullptr;
     uint32_t* prim_ws = ws.take<uint32_t>(compact_ws_words(n) + sort_ws_words(m));
     K* keys_a = ws.take<K>((size_t)m);
@@ -597,12 +543,10 @@ static int knn_impl(const double* d_x, const double* d_y, const double* d_z, int
     uint8_t* flags = ws.take<uint8_t>((size_t)m);
     uint64_t* ucell = ws.take<uint64_t>((size_t)m);
     uint32_t* cell_first = ws.take<uint32_t>((size_t)m + 1);
-    uint32_t* sc_first = ws.take<uint32_t>((size_t)m);
-    uint32_t* sc_of = ws.take<uint32_t>((size_t)m);
-    uint32_t* group_start = ws.take<uint32_t>((size_t)m + 1);
     uint64_t* sc_key = ws.take<uint64_t>((size_t)m);
     uint32_t* sc_cell_first = ws.take<uint32_t>((size_t)m + 1);
     uint32_t* table = ws.take<uint32_t>(hash_capacity(m));
+    uint32_t* nb_pos = ws.take<uint32_t>((size_t)m * 32);
     if (!ws.ok) UPCP_FAIL(UPCP_E_WORKSPACE, "knn: workspace too small");
 
     if (d_sel) {
@@ -629,7 +573,7 @@ static int knn_impl(const double* d_x, const double* d_y, const double* d_z, int
     knn_gather_kernel<<<grid_m, kBlock, 0, st>>>(d_x, d_y, d_z, sel_idx, perm, m, sx, sy, sz);
     UPCP_LAUNCH_OK();
 
-    // cell list
+    // fine-cell list
     uint32_t* n_cells = counters + 1;
     knn_boundary_flags_kernel<K><<<grid_m, kBlock, 0, st>>>(keys, m, 0, flags);
     UPCP_LAUNCH_OK();
@@ -637,30 +581,13 @@ static int knn_impl(const double* d_x, const double* d_y, const double* d_z, int
         KnnCellFunctor<K> f{keys, ucell, cell_first};
         UPCP_TRY(compact_apply(flags, m, n_cells, prim_ws, st, f));
     }
-    // super-cells (4x4x4 cells = low 6 Morton bits) and query groups
-    uint32_t* n_super = counters + 2;
-    uint32_t* n_groups = counters + 3;
-    knn_boundary_flags_kernel<K><<<grid_m, kBlock, 0, st>>>(keys, m, 6, flags);
+    knn_finish_cells_kernel<<<1, 32, 0, st>>>(n_cells, cell_first, (uint32_t)m);
     UPCP_LAUNCH_OK();
-    {
-        KnnSuperFunctor f{sc_first, sc_of};
-        UPCP_TRY(compact_apply(flags, m, n_super, prim_ws, st, f));
-    }
-    knn_group_flags_kernel<<<grid_m, kBlock, 0, st>>>(sc_first, sc_of, m, flags);
-    UPCP_LAUNCH_OK();
-    {
-        KnnGroupFunctor f{group_start};
-        UPCP_TRY(compact_apply(flags, m, n_groups, prim_ws, st, f));
-    }
-    knn_finish_kernel<<<1, 32, 0, st>>>(n_cells, cell_first, n_groups, group_start, (uint32_t)m);
-    UPCP_LAUNCH_OK();
-
-    // counts back to the host once: number of fine cells (sizes the super-cell pass and the hash)
-    uint32_t h_counts[4] = {0, 0, 0, 0};
-    UPCP_CUDA_OK(cudaMemcpyAsync(h_counts, counters, sizeof(h_counts), cudaMemcpyDeviceToHost, st));
+    // number of fine cells back to the host once (sizes the super-cell pass and the hash)
+    uint32_t c_total = 0;
+    UPCP_CUDA_OK(cudaMemcpyAsync(&c_total, n_cells, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     UPCP_CUDA_OK(cudaStreamSynchronize(st));
-    const uint32_t c_total = h_counts[1];
-    // super-cells over the fine-cell list: contiguous runs of ucell with equal key >> 6
+    // super-cells: contiguous runs of the fine-cell list with equal key >> 6
     uint32_t* n_sc = counters + 4;
     knn_boundary_flags_kernel<uint64_t><<<grid_for(c_total, kBlock), kBlock, 0, st>>>(ucell, c_total, 6, flags);
     UPCP_LAUNCH_OK();
@@ -676,29 +603,25 @@ static int knn_impl(const double* d_x, const double* d_y, const double* d_z, int
     knn_hash_insert_kernel<<<grid_for(c_total, kBlock), kBlock, 0, st>>>(sc_key, n_sc, table, cap - 1);
     UPCP_LAUNCH_OK();
 
-    SearchArgs a;
-    a.sx = sx; a.sy = sy; a.sz = sz; a.perm = perm; a.ucell = ucell; a.cell_first = cell_first;
-    a.sc_key = sc_key; a.sc_cell_first = sc_cell_first;
-    a.table = table; a.table_mask = cap - 1; a.group_start = group_start; a.n_groups = n_groups;
-    a.g = g; a.m = m;
     int kh = knn > max_nn ? knn : max_nn;
     if ((int64_t)kh > m) kh = (int)m;
-    a.k_heap = kh; a.knn = knn; a.max_nn = max_nn; a.radius2 = radius * radius;
-    a.out_knn = d_knn; a.out_d2 = d_knn_d2; a.out_normals = d_normals; a.out_cov = d_cov; a.out_curv = d_curv;
-    const uint32_t g_total = h_counts[3];
-    int blocks = (int)((g_total + kSearchWarps - 1) / kSearchWarps);
-    int cap_blocks = num_sms() * 32;
-    if (blocks > cap_blocks) blocks = cap_blocks;
-    if (blocks < 1) blocks = 1;
+    SelectArgs a;
+    a.sx = sx; a.sy = sy; a.sz = sz; a.perm = perm; a.ucell = ucell; a.cell_first = cell_first;
+    a.sc_key = sc_key; a.sc_cell_first = sc_cell_first; a.table = table; a.table_mask = cap - 1;
+    a.g = g; a.m = m; a.k = kh; a.out_pos = nb_pos;
+    int64_t need = (m + kSelWarps - 1) / kSelWarps;
+    int64_t cap_blocks = (int64_t)num_sms() * 64;
+    int blocks = (int)(need < cap_blocks ? need : cap_blocks);
     prof_begin(UPCP_PROF_KNN, st);
-    if (kh <= 16) {
-        UPCP_CUDA_OK(cudaFuncSetAttribute(knn_search_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)search_smem_bytes<16>()));
-        knn_search_kernel<16><<<blocks, kSearchThreads, search_smem_bytes<16>(), st>>>(a);
-    } else {
-        UPCP_CUDA_OK(cudaFuncSetAttribute(knn_search_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)search_smem_bytes<32>()));
-        knn_search_kernel<32><<<blocks, kSearchThreads, search_smem_bytes<32>(), st>>>(a);
-    }
+    knn_select_kernel<<<blocks, kSelThreads, 0, st>>>(a);
     prof_end(UPCP_PROF_KNN, st, m);
+    UPCP_LAUNCH_OK();
+
+    EpilogueArgs e;
+    e.sx = sx; e.sy = sy; e.sz = sz; e.perm = perm; e.pos = nb_pos; e.m = m;
+    e.knn = knn; e.max_nn = max_nn; e.radius2 = radius * radius;
+    e.out_knn = d_knn; e.out_d2 = d_knn_d2; e.out_normals = d_normals; e.out_cov = d_cov; e.out_curv = d_curv;
+    knn_epilogue_kernel<<<grid_m, kBlock, 0, st>>>(e);
     UPCP_LAUNCH_OK();
     return UPCP_OK;
 }
@@ -720,10 +643,10 @@ size_t upcp_knn_ws_bytes(int64_t n, int64_t m, int kmax) {
     bytes += 3 * align_up((size_t)m * 8);                                   // sorted coords
     bytes += align_up((size_t)m);                                           // flags
     bytes += align_up((size_t)m * 8);                                       // ucell
-    bytes += 2 * align_up(((size_t)m + 1) * 4);                             // cell_first, group_start
-    bytes += 2 * align_up((size_t)m * 4);                                   // sc_first, sc_of
+    bytes += align_up(((size_t)m + 1) * 4);                                 // cell_first
     bytes += align_up((size_t)m * 8) + align_up(((size_t)m + 1) * 4);       // sc_key, sc_cell_first
     { size_t cap = 1024; while (cap < 2 * (size_t)m) cap <<= 1; bytes += align_up(cap * 4); }  // hash table
+    bytes += align_up((size_t)m * 32 * 4);                                  // neighbour positions
     return bytes + 4096;
 }
 
@@ -747,8 +670,7 @@ int upcp_knn_normals(const double* d_x, const double* d_y, const double* d_z, in
     double emax = fmax(ex, fmax(ey, ez));
     double cell = cell_size;
     if (emax / cell > 1000000.0) cell = emax / 1000000.0;
-    g.cell = cell; g.inv_cell = 1.0 / cell;
-    // ... and the whole grid within 2^30 cells so that box enumeration stays in int32
+    // ... and the whole grid within 2^30 cells
     while ((floor(ex / cell) + 1) * (floor(ey / cell) + 1) * (floor(ez / cell) + 1) > 1073741824.0) cell *= 2.0;
     g.cell = cell; g.inv_cell = 1.0 / cell;
     g.nx = (int)floor(ex / cell) + 1; g.ny = (int)floor(ey / cell) + 1; g.nz = (int)floor(ez / cell) + 1;
