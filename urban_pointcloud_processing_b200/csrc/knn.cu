@@ -40,6 +40,11 @@ constexpr int kBlock = 256;
 constexpr int kSelWarps = 8;
 constexpr int kSelThreads = kSelWarps * 32;
 constexpr int kCellCap = 128;           // per-warp list of candidate fine cells
+constexpr int kRow = 48;                // neighbour-candidate row stride (u32 sorted positions)
+constexpr int kGrpWarps = 4;
+constexpr int kGrpThreads = kGrpWarps * 32;
+constexpr int kBuckets = 64;            // radial histogram resolution of the group kernel
+constexpr int kEpiThreads = 128;
 constexpr uint32_t kEmpty = 0xffffffffu;
 constexpr uint32_t kFull = 0xffffffffu;
 
@@ -176,7 +181,10 @@ struct SelectArgs {
     GridParams g;
     int64_t m;
     int k;                         // neighbours kept per query (<= 32), clipped to m
-    uint32_t* out_pos;             // [m][32] sorted positions of the k nearest (row = sorted position of the query)
+    const uint32_t* todo_idx;      // queries (sorted positions) to process, or NULL = all m
+    const uint32_t* todo_cnt;      // device count of todo_idx
+    uint32_t* out_pos;             // [m][kRow] sorted positions of the k nearest, ascending
+    uint8_t* out_cnt;              // [m] number of valid entries of the row
 };
 
 __device__ __forceinline__ uint32_t warp_incl_scan_u32(uint32_t v, int lane) {
@@ -204,6 +212,16 @@ __device__ __forceinline__ double point_box_gap2(double qx, double qy, double qz
     double gx = fmax(0.0, fmax(lox - qx, qx - hix) - slack);
     double gy = fmax(0.0, fmax(loy - qy, qy - hiy) - slack);
     double gz = fmax(0.0, fmax(loz - qz, qz - hiz) - slack);
+    return (gx * gx + gy * gy + gz * gz) * (1.0 - 1e-9);
+}
+
+// conservative squared distance between two axis-aligned boxes
+__device__ __forceinline__ double box_box_gap2(double lox, double loy, double loz, double hix, double hiy, double hiz,
+                                               double bminx, double bminy, double bminz,
+                                               double bmaxx, double bmaxy, double bmaxz, double slack) {
+    double gx = fmax(0.0, fmax(lox - bmaxx, bminx - hix) - slack);
+    double gy = fmax(0.0, fmax(loy - bmaxy, bminy - hiy) - slack);
+    double gz = fmax(0.0, fmax(loz - bmaxz, bminz - hiz) - slack);
     return (gx * gx + gy * gy + gz * gz) * (1.0 - 1e-9);
 }
 
@@ -267,7 +285,9 @@ knn_select_kernel(SelectArgs a) {
     const double scell = 4.0 * g.cell;                       // super-cell edge
     const int nsx = (g.nx + 3) >> 2, nsy = (g.ny + 3) >> 2, nsz = (g.nz + 3) >> 2;
 
-    for (int64_t q = (int64_t)blockIdx.x * kSelWarps + warp; q < a.m; q += (int64_t)gridDim.x * kSelWarps) {
+    const int64_t n_todo = a.todo_idx ? (int64_t)*a.todo_cnt : a.m;
+    for (int64_t qi = (int64_t)blockIdx.x * kSelWarps + warp; qi < n_todo; qi += (int64_t)gridDim.x * kSelWarps) {
+        const int64_t q = a.todo_idx ? (int64_t)a.todo_idx[qi] : qi;
         const double qx = a.sx[q], qy = a.sy[q], qz = a.sz[q];
         const int sx = cell_coord(qx, g.ox, g.inv_cell, g.nx) >> 2;
         const int sy = cell_coord(qy, g.oy, g.inv_cell, g.ny) >> 2;
@@ -448,44 +468,349 @@ knn_select_kernel(SelectArgs a) {
             reach -= g.slack;
             if (kth_d < inf && reach > 0.0 && kth_d < reach * reach * (1.0 - 1e-9)) break;
         }
-        // sorted positions of the neighbours (kFull = absent); one coalesced 128-byte row
-        a.out_pos[(size_t)q * 32 + lane] = (lane < K && mine.d < inf) ? mine.p : kFull;
+        // sorted positions of the neighbours, ascending; one coalesced 128-byte row
+        const bool have = lane < K && mine.d < inf;
+        a.out_pos[(size_t)q * kRow + lane] = have ? mine.p : kFull;
+        const uint32_t hv = __ballot_sync(kFull, have);
+        if (lane == 0) a.out_cnt[q] = (uint8_t)__popc(hv);
     }
+}
+
+// ------------------------------------------------------------------ group kernel --
+// Dense bulk: ONE WARP PER GROUP of <= 32 Morton-consecutive queries of one super-cell, one
+// lane per query; every staged candidate is tested by all lanes (broadcast reads), so
+// candidate loads and the cell walk are amortised over the group.  Selection is a two-pass
+// radial histogram ("radix select") instead of a per-candidate priority queue:
+//   bound    all members of the group lie in their bounding box, so (with >= k members) the
+//            k-th neighbour of lane i is no farther than tau_i = the farthest corner of the box;
+//   pass A   stream every point of the cells within tau_max of the box; each lane counts the
+//            candidates with d2 <= tau_i into 64 equal-width d2 buckets (shared-memory u16);
+//   select   b*_i = first bucket whose cumulative count reaches k; the bucket index is a monotone
+//            function of d2, so every candidate outside buckets <= b*_i is strictly farther than
+//            every candidate inside: the k nearest are among the (few more than k) inside;
+//   pass B   stream the same cells again and append the inside candidates to the query's row.
+// The row is sorted exactly by (d2, compact id) in the epilogue kernel.  Queries the scheme
+// cannot serve (groups with < k members, rows that would overflow, elongated groups) are flagged
+// and handled by the warp-per-query kernel above.  Both paths are exact.
+struct GroupArgs {
+    const double* sx; const double* sy; const double* sz;
+    const uint64_t* ucell; const uint32_t* cell_first;
+    const uint64_t* sc_key; const uint32_t* sc_cell_first;
+    const uint32_t* table; uint32_t table_mask;
+    const uint4* groups; const uint32_t* n_groups;     // member_start, n_members, chunk_start, chunk_cnt
+    GridParams g;
+    int k;
+    uint32_t* out_pos; uint8_t* out_cnt; uint8_t* todo;
+};
+
+__global__ void __launch_bounds__(kGrpThreads)
+knn_group_kernel(GroupArgs a) {
+    __shared__ uint16_t s_hist[kGrpWarps][kBuckets * 32];
+    __shared__ double2 s_cxy[kGrpWarps][32];
+    __shared__ double s_cz[kGrpWarps][32];
+    __shared__ uint32_t s_cpos[kGrpWarps][32];
+    __shared__ uint32_t s_cells[kGrpWarps][kCellCap];
+    __shared__ uint32_t s_gseg[kGrpWarps][2][96];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint16_t* const hist = s_hist[warp];
+    double2* const c_xy = s_cxy[warp]; double* const c_z = s_cz[warp]; uint32_t* const c_pos = s_cpos[warp];
+    uint32_t* const l_cell = s_cells[warp];
+    uint32_t* const sa_off = s_gseg[warp][0]; uint32_t* const sa_base = sa_off + 64;
+    uint32_t* const sb_off = s_gseg[warp][1]; uint32_t* const sb_base = sb_off + 64;
+
+    const GridParams g = a.g;
+    const int K = a.k;
+    const uint32_t n_groups = *a.n_groups;
+    const double scell = 4.0 * g.cell;
+    const int nsx = (g.nx + 3) >> 2, nsy = (g.ny + 3) >> 2, nsz = (g.nz + 3) >> 2;
+
+    for (uint32_t grp = blockIdx.x * kGrpWarps + warp; grp < n_groups; grp += gridDim.x * kGrpWarps) {
+        const uint4 gd = a.groups[grp];
+        const uint32_t member_start = gd.x, n_members = gd.y, chunk_start = gd.z, chunk_cnt = gd.w;
+        const bool member = (uint32_t)lane < n_members;
+        const uint32_t pos = member_start + (member ? lane : 0);
+        const bool is_query = member && pos >= chunk_start && pos < chunk_start + chunk_cnt;
+        const double qx = a.sx[pos], qy = a.sy[pos], qz = a.sz[pos];
+        // bounding box of the members (non-member lanes alias member 0)
+        double bminx = qx, bminy = qy, bminz = qz, bmaxx = qx, bmaxy = qy, bmaxz = qz;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            bminx = fmin(bminx, __shfl_xor_sync(kFull, bminx, o)); bmaxx = fmax(bmaxx, __shfl_xor_sync(kFull, bmaxx, o));
+            bminy = fmin(bminy, __shfl_xor_sync(kFull, bminy, o)); bmaxy = fmax(bmaxy, __shfl_xor_sync(kFull, bmaxy, o));
+            bminz = fmin(bminz, __shfl_xor_sync(kFull, bminz, o)); bmaxz = fmax(bmaxz, __shfl_xor_sync(kFull, bmaxz, o));
+        }
+        // tau_i: squared distance to the farthest corner of the box (>= d2 to every member, with slack)
+        double tau;
+        {
+            const double ex = fmax(qx - bminx, bmaxx - qx), ey = fmax(qy - bminy, bmaxy - qy), ez = fmax(qz - bminz, bmaxz - qz);
+            tau = (ex * ex + ey * ey + ez * ez) * (1.0 + 1e-9) + 1e-300;
+        }
+        double tau_max = tau;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) tau_max = fmax(tau_max, __shfl_xor_sync(kFull, tau_max, o));
+        const double scale = (double)kBuckets / tau;
+        const int sx = cell_coord(qx, g.ox, g.inv_cell, g.nx) >> 2;       // same for all members
+        const int sy = cell_coord(qy, g.oy, g.inv_cell, g.ny) >> 2;
+        const int sz = cell_coord(qz, g.oz, g.inv_cell, g.nz) >> 2;
+        const int gsx = __shfl_sync(kFull, sx, 0), gsy = __shfl_sync(kFull, sy, 0), gsz = __shfl_sync(kFull, sz, 0);
+        const int rmax = (int)ceil((sqrt(tau_max) + g.slack) / scell);
+        bool active = is_query;
+        if (rmax > 2 || (int)n_members < K) {            // not served here: hand over to the per-query kernel
+            if (is_query) a.todo[pos] = 1;
+            continue;
+        }
+
+        int bstar = -1;            // selected bucket (pass B keeps buckets <= bstar)
+        uint32_t row_n = 0;        // entries appended to the row so far
+        for (int pass = 0; pass < 2; ++pass) {
+            if (pass == 0) {
+                for (int i = lane; i < kBuckets * 32; i += 32) hist[i] = 0;      // [bucket][lane]
+                __syncwarp();
+            }
+            int list_n = 0;
+            auto flush = [&]() {
+                for (int j0 = 0; j0 < list_n; j0 += 32) {
+                    const int e = j0 + lane;
+                    uint32_t first = 0, cnt = 0;
+                    if (e < list_n) {
+                        const uint32_t cell = l_cell[e];
+                        first = __ldg(a.cell_first + cell);
+                        cnt = __ldg(a.cell_first + cell + 1) - first;
+                    }
+                    const uint32_t incl = warp_incl_scan_u32(cnt, lane);
+                    const uint32_t total = __shfl_sync(kFull, incl, 31);
+                    sa_off[lane] = incl - cnt; sa_off[32 + lane] = total; sa_base[lane] = first;
+                    __syncwarp();
+                    for (uint32_t b = 0; b < total; b += 32) {
+                        const uint32_t i = b + lane;
+                        if (i < total) {
+                            const int kk = seg_search(sa_off, i);
+                            const uint32_t p = sa_base[kk] + (i - sa_off[kk]);
+                            c_xy[lane] = make_double2(a.sx[p], a.sy[p]); c_z[lane] = a.sz[p]; c_pos[lane] = p;
+                        }
+                        __syncwarp();
+                        const int nc = (int)min(32u, total - b);
+                        if (active) {
+#pragma unroll 4
+                            for (int c = 0; c < nc; ++c) {
+                                const double2 xy = c_xy[c];
+                                const double d2 = dist2(xy.x, xy.y, c_z[c], qx, qy, qz);
+                                if (d2 <= tau) {
+                                    int bk = (int)(d2 * scale);
+                                    bk = bk > kBuckets - 1 ? kBuckets - 1 : bk;
+                                    if (pass == 0) {
+                                        hist[bk * 32 + lane] += 1;
+                                    } else if (bk <= bstar) {
+                                        a.out_pos[(size_t)pos * kRow + row_n] = c_pos[c];
+                                        ++row_n;
+                                    }
+                                }
+                            }
+                        }
+                        __syncwarp();
+                    }
+                }
+                list_n = 0;
+            };
+            for (int R = 0; R <= rmax; ++R) {
+                const int w = 2 * R + 1, v = 2 * R - 1;
+                const int A = w * w, B = R > 0 ? w * v : 0, C = R > 0 ? v * v : 0;
+                const int total = R == 0 ? 1 : 2 * A + 2 * B + 2 * C;
+                for (int t0 = 0; t0 < total; t0 += 32) {
+                    int t = t0 + lane;
+                    uint32_t f0 = 0, f1 = 0;
+                    if (t < total) {
+                        int cx, cy, cz;
+                        if (R == 0) { cx = gsx; cy = gsy; cz = gsz; }
+                        else if (t < 2 * A) {
+                            cz = t < A ? gsz - R : gsz + R; if (t >= A) t -= A;
+                            cx = gsx - R + t % w; cy = gsy - R + t / w;
+                        } else if (t < 2 * A + 2 * B) {
+                            t -= 2 * A;
+                            cy = t < B ? gsy - R : gsy + R; if (t >= B) t -= B;
+                            cx = gsx - R + t % w; cz = gsz - R + 1 + t / w;
+                        } else {
+                            t -= 2 * A + 2 * B;
+                            cx = t < C ? gsx - R : gsx + R; if (t >= C) t -= C;
+                            cy = gsy - R + 1 + t % v; cz = gsz - R + 1 + t / v;
+                        }
+                        if (cx >= 0 && cy >= 0 && cz >= 0 && cx < nsx && cy < nsy && cz < nsz) {
+                            const double lb = box_box_gap2(g.ox + cx * scell, g.oy + cy * scell, g.oz + cz * scell,
+                                                           g.ox + (cx + 1) * scell, g.oy + (cy + 1) * scell, g.oz + (cz + 1) * scell,
+                                                           bminx, bminy, bminz, bmaxx, bmaxy, bmaxz, g.slack);
+                            if (!(lb > tau_max)) {
+                                const uint64_t key = morton3(cx, cy, cz);
+                                uint32_t h = (uint32_t)hash64(key) & a.table_mask;
+                                while (true) {
+                                    const uint32_t idx = __ldg(a.table + h);
+                                    if (idx == kEmpty) break;
+                                    if (__ldg(a.sc_key + idx) == key) {
+                                        f0 = __ldg(a.sc_cell_first + idx); f1 = __ldg(a.sc_cell_first + idx + 1);
+                                        break;
+                                    }
+                                    h = (h + 1) & a.table_mask;
+                                }
+                            }
+                        }
+                    }
+                    const uint32_t fcnt = f1 - f0;
+                    const uint32_t fincl = warp_incl_scan_u32(fcnt, lane);
+                    const uint32_t ftotal = __shfl_sync(kFull, fincl, 31);
+                    if (ftotal == 0) continue;
+                    sb_off[lane] = fincl - fcnt; sb_off[32 + lane] = ftotal; sb_base[lane] = f0;
+                    __syncwarp();
+                    for (uint32_t b = 0; b < ftotal; b += 32) {
+                        const uint32_t i = b + lane;
+                        bool keep = false;
+                        uint32_t e = 0;
+                        if (i < ftotal) {
+                            const int kk = seg_search(sb_off, i);
+                            e = sb_base[kk] + (i - sb_off[kk]);
+                            const uint64_t key = __ldg(a.ucell + e);
+                            const int fx = (int)compact_bits21(key), fy = (int)compact_bits21(key >> 1), fz = (int)compact_bits21(key >> 2);
+                            const double lb = box_box_gap2(g.ox + fx * g.cell, g.oy + fy * g.cell, g.oz + fz * g.cell,
+                                                           g.ox + (fx + 1) * g.cell, g.oy + (fy + 1) * g.cell, g.oz + (fz + 1) * g.cell,
+                                                           bminx, bminy, bminz, bmaxx, bmaxy, bmaxz, g.slack);
+                            keep = !(lb > tau_max);
+                        }
+                        const uint32_t kb = __ballot_sync(kFull, keep);
+                        if (kb) {
+                            if (list_n + 32 > kCellCap) flush();
+                            if (keep) l_cell[list_n + __popc(kb & ((1u << lane) - 1u))] = e;
+                            list_n += __popc(kb);
+                            __syncwarp();
+                        }
+                    }
+                    __syncwarp();
+                }
+            }
+            flush();
+            if (pass == 0) {
+                // select: first bucket whose cumulative count reaches K
+                __syncwarp();
+                uint32_t cum = 0;
+                int bs = kBuckets - 1;
+                bool found = false;
+                for (int b = 0; b < kBuckets; ++b) {
+                    cum += hist[b * 32 + lane];
+                    if (!found && cum >= (uint32_t)K) { found = true; bs = b; break; }
+                }
+                if (active && (!found || cum > (uint32_t)kRow)) {     // row would overflow (or bound broken)
+                    a.todo[pos] = 1;
+                    active = false;
+                }
+                bstar = bs;
+                if (!__any_sync(kFull, active)) break;
+            }
+        }
+        if (active) a.out_cnt[pos] = (uint8_t)row_n;
+    }
+}
+
+// ---- query groups: <= 32 consecutive sorted points of one super-cell run
+__global__ void __launch_bounds__(kBlock)
+knn_group_count_kernel(const uint32_t* __restrict__ run_first, const uint32_t* __restrict__ n_runs,
+                       uint32_t* __restrict__ ng) {
+    const uint32_t total = *n_runs;
+    uint32_t stride = gridDim.x * kBlock;
+    for (uint32_t r = blockIdx.x * kBlock + threadIdx.x; r < total; r += stride)
+        ng[r] = (run_first[r + 1] - run_first[r] + 31) / 32;
+}
+
+__global__ void __launch_bounds__(kBlock)
+knn_group_fill_kernel(const uint32_t* __restrict__ run_first, const uint32_t* __restrict__ n_runs,
+                      const uint32_t* __restrict__ goff, uint4* __restrict__ groups) {
+    const uint32_t total = *n_runs;
+    uint32_t stride = gridDim.x * kBlock;
+    for (uint32_t r = blockIdx.x * kBlock + threadIdx.x; r < total; r += stride) {
+        const uint32_t s0 = run_first[r], s1 = run_first[r + 1], len = s1 - s0;
+        uint32_t o = goff[r];
+        for (uint32_t c = s0; c < s1; c += 32, ++o) {
+            const uint32_t ccnt = s1 - c < 32 ? s1 - c : 32;
+            // a short tail borrows members from the preceding chunk of the same run so that the
+            // bounding-box bound still covers 32 points
+            const uint32_t mstart = (ccnt == 32 || len < 32) ? c : s1 - 32;
+            const uint32_t mcnt = len < 32 ? len : 32;
+            groups[o] = make_uint4(mstart, mcnt, c, ccnt);
+        }
+    }
+}
+
+struct RunFunctor {
+    uint32_t* run_first;
+    __device__ void operator()(int64_t s, bool is_first, uint32_t rank) const {
+        if (is_first) run_first[rank] = (uint32_t)s;
+    }
+};
+struct TodoFunctor {
+    uint32_t* todo_idx;
+    __device__ void operator()(int64_t s, bool is_todo, uint32_t rank) const {
+        if (is_todo) todo_idx[rank] = (uint32_t)s;
+    }
+};
+__global__ void knn_finish_runs_kernel(const uint32_t* __restrict__ n_runs, uint32_t* __restrict__ run_first, uint32_t m) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) run_first[*n_runs] = m;
 }
 
 // ------------------------------------------------------------------ epilogue ----
 struct EpilogueArgs {
     const double* sx; const double* sy; const double* sz;
-    const uint32_t* perm; const uint32_t* pos;      // pos: [m][32]
+    const uint32_t* perm; const uint32_t* pos; const uint8_t* cnt;      // pos: [m][kRow]
     int64_t m;
     int knn, max_nn;
     double radius2;
     int32_t* out_knn; double* out_d2; double* out_normals; double* out_cov; double* out_curv;
 };
 
-__global__ void __launch_bounds__(kBlock)
+// One thread per query.  The candidate row (k exact neighbours from the per-query kernel, or
+// the slightly larger unsorted superset from the group kernel) is sorted by (d2, compact id)
+// with an insertion sort in shared memory ([slot][thread] layout: conflict-free), then folded
+// IN ORDER into the cumulant covariances (fp summation order is part of the contract).
+__global__ void __launch_bounds__(kEpiThreads)
 knn_epilogue_kernel(EpilogueArgs a) {
+    extern __shared__ __align__(16) unsigned char epi_smem[];
+    double* const s_d = reinterpret_cast<double*>(epi_smem);                              // [kRow][threads]
+    uint32_t* const s_c = reinterpret_cast<uint32_t*>(epi_smem + (size_t)kRow * kEpiThreads * 8);
+    uint32_t* const s_p = s_c + (size_t)kRow * kEpiThreads;
+    const int tx = threadIdx.x;
     const double inf = __longlong_as_double(0x7ff0000000000000LL);
-    int64_t stride = (int64_t)gridDim.x * kBlock;
-    for (int64_t s = (int64_t)blockIdx.x * kBlock + threadIdx.x; s < a.m; s += stride) {
-        const uint32_t* row = a.pos + (size_t)s * 32;
+    int64_t stride = (int64_t)gridDim.x * kEpiThreads;
+    for (int64_t s = (int64_t)blockIdx.x * kEpiThreads + tx; s < a.m; s += stride) {
+        const uint32_t* row = a.pos + (size_t)s * kRow;
         const double qx = a.sx[s], qy = a.sy[s], qz = a.sz[s];
         const uint32_t cid = a.perm[s];
+        const int n = (int)a.cnt[s];
+        for (int j = 0; j < n; ++j) {
+            const uint32_t p = __ldg(row + j);
+            const double d2 = dist2(a.sx[p], a.sy[p], a.sz[p], qx, qy, qz);
+            const uint32_t c = __ldg(a.perm + p);
+            int i = j;
+            while (i > 0) {
+                const double dp = s_d[(i - 1) * kEpiThreads + tx];
+                const uint32_t cp = s_c[(i - 1) * kEpiThreads + tx];
+                if (!(d2 < dp || (d2 == dp && c < cp))) break;
+                s_d[i * kEpiThreads + tx] = dp; s_c[i * kEpiThreads + tx] = cp;
+                s_p[i * kEpiThreads + tx] = s_p[(i - 1) * kEpiThreads + tx];
+                --i;
+            }
+            s_d[i * kEpiThreads + tx] = d2; s_c[i * kEpiThreads + tx] = c; s_p[i * kEpiThreads + tx] = p;
+        }
         Cumulants nrm_cum; nrm_cum.clear();       // hybrid search: max_nn nearest with d2 < r^2
         Cumulants cov_cum; cov_cum.clear();       // the knn-neighbourhood (region_growing.py:69-71)
         int nn = 0, kk = 0;
         bool in_radius = true;
         const int lim = a.knn > a.max_nn ? a.knn : a.max_nn;
         for (int j = 0; j < lim; ++j) {
-            const uint32_t p = __ldg(row + j);
-            const bool present = p != kFull;
+            const bool present = j < n;
             double px = 0, py = 0, pz = 0, d2 = inf;
+            uint32_t c = 0;
             if (present) {
+                const uint32_t p = s_p[j * kEpiThreads + tx];
                 px = a.sx[p]; py = a.sy[p]; pz = a.sz[p];
-                d2 = dist2(px, py, pz, qx, qy, qz);
+                d2 = s_d[j * kEpiThreads + tx]; c = s_c[j * kEpiThreads + tx];
             }
             if (j < a.knn) {
-                if (a.out_knn) a.out_knn[(size_t)cid * a.knn + j] = present ? (int32_t)__ldg(a.perm + p) : -1;
+                if (a.out_knn) a.out_knn[(size_t)cid * a.knn + j] = present ? (int32_t)c : -1;
                 if (a.out_d2) a.out_d2[(size_t)cid * a.knn + j] = d2;
                 if (present) { cov_cum.add(px, py, pz); ++kk; }
             }
@@ -546,7 +871,13 @@ static int knn_impl(const double* d_x, const double* d_y, const double* d_z, int
     uint64_t* sc_key = ws.take<uint64_t>((size_t)m);
     uint32_t* sc_cell_first = ws.take<uint32_t>((size_t)m + 1);
     uint32_t* table = ws.take<uint32_t>(hash_capacity(m));
-    uint32_t* nb_pos = ws.take<uint32_t>((size_t)m * 32);
+    uint32_t* nb_pos = ws.take<uint32_t>((size_t)m * kRow);
+    uint8_t* nb_cnt = ws.take<uint8_t>((size_t)m);
+    uint8_t* todo = ws.take<uint8_t>((size_t)m);
+    uint32_t* todo_idx = ws.take<uint32_t>((size_t)m);
+    uint32_t* run_first = ws.take<uint32_t>((size_t)m + 1);
+    uint32_t* run_ng = ws.take<uint32_t>((size_t)m + 1);
+    uint4* groups = ws.take<uint4>((size_t)m / 32 + (size_t)m + 2);
     if (!ws.ok) UPCP_FAIL(UPCP_E_WORKSPACE, "knn: workspace too small");
 
     if (d_sel) {
@@ -583,10 +914,29 @@ static int knn_impl(const double* d_x, const double* d_y, const double* d_z, int
     }
     knn_finish_cells_kernel<<<1, 32, 0, st>>>(n_cells, cell_first, (uint32_t)m);
     UPCP_LAUNCH_OK();
-    // number of fine cells back to the host once (sizes the super-cell pass and the hash)
-    uint32_t c_total = 0;
-    UPCP_CUDA_OK(cudaMemcpyAsync(&c_total, n_cells, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    // super-cell runs over the sorted POINTS (query groups are cut from them)
+    uint32_t* n_runs = counters + 2;
+    knn_boundary_flags_kernel<K><<<grid_m, kBlock, 0, st>>>(keys, m, 6, flags);
+    UPCP_LAUNCH_OK();
+    {
+        RunFunctor f{run_first};
+        UPCP_TRY(compact_apply(flags, m, n_runs, prim_ws, st, f));
+    }
+    knn_finish_runs_kernel<<<1, 32, 0, st>>>(n_runs, run_first, (uint32_t)m);
+    UPCP_LAUNCH_OK();
+    // number of fine cells / runs back to the host once (sizes the following passes)
+    uint32_t h_counts[4] = {0, 0, 0, 0};
+    UPCP_CUDA_OK(cudaMemcpyAsync(h_counts, counters, sizeof(h_counts), cudaMemcpyDeviceToHost, st));
     UPCP_CUDA_OK(cudaStreamSynchronize(st));
+    const uint32_t c_total = h_counts[1];
+    const uint32_t r_total = h_counts[2];
+    // query groups: ceil(len / 32) per run
+    uint32_t* n_groups = counters + 3;
+    knn_group_count_kernel<<<grid_for(r_total, kBlock), kBlock, 0, st>>>(run_first, n_runs, run_ng);
+    UPCP_LAUNCH_OK();
+    UPCP_TRY(exclusive_scan_u32(run_ng, run_ng, r_total, n_groups, prim_ws, st));
+    knn_group_fill_kernel<<<grid_for(r_total, kBlock), kBlock, 0, st>>>(run_first, n_runs, run_ng, groups);
+    UPCP_LAUNCH_OK();
     // super-cells: contiguous runs of the fine-cell list with equal key >> 6
     uint32_t* n_sc = counters + 4;
     knn_boundary_flags_kernel<uint64_t><<<grid_for(c_total, kBlock), kBlock, 0, st>>>(ucell, c_total, 6, flags);
@@ -605,23 +955,42 @@ static int knn_impl(const double* d_x, const double* d_y, const double* d_z, int
 
     int kh = knn > max_nn ? knn : max_nn;
     if ((int64_t)kh > m) kh = (int)m;
+    UPCP_CUDA_OK(cudaMemsetAsync(todo, 0, (size_t)m, st));
+    prof_begin(UPCP_PROF_KNN, st);
+    // dense bulk: warp per group, lane per query, two-pass radial histogram selection
+    GroupArgs ga;
+    ga.sx = sx; ga.sy = sy; ga.sz = sz; ga.ucell = ucell; ga.cell_first = cell_first;
+    ga.sc_key = sc_key; ga.sc_cell_first = sc_cell_first; ga.table = table; ga.table_mask = cap - 1;
+    ga.groups = groups; ga.n_groups = n_groups; ga.g = g; ga.k = kh;
+    ga.out_pos = nb_pos; ga.out_cnt = nb_cnt; ga.todo = todo;
+    {
+        int64_t upper = (int64_t)m / 32 + r_total + 1;            // >= number of groups
+        int64_t need = (upper + kGrpWarps - 1) / kGrpWarps;
+        int64_t cap_blocks = (int64_t)num_sms() * 32;
+        knn_group_kernel<<<(int)(need < cap_blocks ? need : cap_blocks), kGrpThreads, 0, st>>>(ga);
+        UPCP_LAUNCH_OK();
+    }
+    // the rest (sparse / short / overflowing queries): warp per query
+    uint32_t* n_todo = counters + 5;
+    {
+        TodoFunctor f{todo_idx};
+        UPCP_TRY(compact_apply(todo, m, n_todo, prim_ws, st, f));
+    }
     SelectArgs a;
     a.sx = sx; a.sy = sy; a.sz = sz; a.perm = perm; a.ucell = ucell; a.cell_first = cell_first;
     a.sc_key = sc_key; a.sc_cell_first = sc_cell_first; a.table = table; a.table_mask = cap - 1;
-    a.g = g; a.m = m; a.k = kh; a.out_pos = nb_pos;
-    int64_t need = (m + kSelWarps - 1) / kSelWarps;
-    int64_t cap_blocks = (int64_t)num_sms() * 64;
-    int blocks = (int)(need < cap_blocks ? need : cap_blocks);
-    prof_begin(UPCP_PROF_KNN, st);
-    knn_select_kernel<<<blocks, kSelThreads, 0, st>>>(a);
+    a.g = g; a.m = m; a.k = kh; a.todo_idx = todo_idx; a.todo_cnt = n_todo; a.out_pos = nb_pos; a.out_cnt = nb_cnt;
+    knn_select_kernel<<<num_sms() * 16, kSelThreads, 0, st>>>(a);
     prof_end(UPCP_PROF_KNN, st, m);
     UPCP_LAUNCH_OK();
 
     EpilogueArgs e;
-    e.sx = sx; e.sy = sy; e.sz = sz; e.perm = perm; e.pos = nb_pos; e.m = m;
+    e.sx = sx; e.sy = sy; e.sz = sz; e.perm = perm; e.pos = nb_pos; e.cnt = nb_cnt; e.m = m;
     e.knn = knn; e.max_nn = max_nn; e.radius2 = radius * radius;
     e.out_knn = d_knn; e.out_d2 = d_knn_d2; e.out_normals = d_normals; e.out_cov = d_cov; e.out_curv = d_curv;
-    knn_epilogue_kernel<<<grid_m, kBlock, 0, st>>>(e);
+    const size_t epi_smem = (size_t)kRow * kEpiThreads * 16;
+    UPCP_CUDA_OK(cudaFuncSetAttribute(knn_epilogue_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)epi_smem));
+    knn_epilogue_kernel<<<grid_for(m, kEpiThreads, 2), kEpiThreads, epi_smem, st>>>(e);
     UPCP_LAUNCH_OK();
     return UPCP_OK;
 }
@@ -646,7 +1015,9 @@ size_t upcp_knn_ws_bytes(int64_t n, int64_t m, int kmax) {
     bytes += align_up(((size_t)m + 1) * 4);                                 // cell_first
     bytes += align_up((size_t)m * 8) + align_up(((size_t)m + 1) * 4);       // sc_key, sc_cell_first
     { size_t cap = 1024; while (cap < 2 * (size_t)m) cap <<= 1; bytes += align_up(cap * 4); }  // hash table
-    bytes += align_up((size_t)m * 32 * 4);                                  // neighbour positions
+    bytes += align_up((size_t)m * kRow * 4) + 2 * align_up((size_t)m);      // neighbour rows, counts, todo flags
+    bytes += 3 * align_up(((size_t)m + 1) * 4);                             // todo_idx, run_first, run_ng
+    bytes += align_up(((size_t)m / 32 + (size_t)m + 2) * 16);               // groups
     return bytes + 4096;
 }
 
