@@ -509,11 +509,13 @@ knn_group_kernel(GroupArgs a) {
     __shared__ double2 s_cxy[kGrpWarps][32];
     __shared__ double s_cz[kGrpWarps][32];
     __shared__ uint32_t s_cpos[kGrpWarps][32];
+    __shared__ double s_lb2[kGrpWarps][kCellCap];
     __shared__ uint32_t s_cells[kGrpWarps][kCellCap];
     __shared__ uint32_t s_gseg[kGrpWarps][2][96];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint16_t* const hist = s_hist[warp];
     double2* const c_xy = s_cxy[warp]; double* const c_z = s_cz[warp]; uint32_t* const c_pos = s_cpos[warp];
+    double* const l_lb2 = s_lb2[warp];
     uint32_t* const l_cell = s_cells[warp];
     uint32_t* const sa_off = s_gseg[warp][0]; uint32_t* const sa_base = sa_off + 64;
     uint32_t* const sb_off = s_gseg[warp][1]; uint32_t* const sb_base = sb_off + 64;
@@ -521,6 +523,7 @@ knn_group_kernel(GroupArgs a) {
     const GridParams g = a.g;
     const int K = a.k;
     const uint32_t n_groups = *a.n_groups;
+    const double inf = __longlong_as_double(0x7ff0000000000000LL);
     const double scell = 4.0 * g.cell;
     const int nsx = (g.nx + 3) >> 2, nsy = (g.ny + 3) >> 2, nsz = (g.nz + 3) >> 2;
 
@@ -553,65 +556,102 @@ knn_group_kernel(GroupArgs a) {
         const int sy = cell_coord(qy, g.oy, g.inv_cell, g.ny) >> 2;
         const int sz = cell_coord(qz, g.oz, g.inv_cell, g.nz) >> 2;
         const int gsx = __shfl_sync(kFull, sx, 0), gsy = __shfl_sync(kFull, sy, 0), gsz = __shfl_sync(kFull, sz, 0);
-        const int rmax = (int)ceil((sqrt(tau_max) + g.slack) / scell);
         bool active = is_query;
-        if (rmax > 2 || (int)n_members < K) {            // not served here: hand over to the per-query kernel
-            if (is_query) a.todo[pos] = 1;
+        if ((int)ceil((sqrt(tau_max) + g.slack) / scell) > 2 || (int)n_members < K) {
+            if (is_query) a.todo[pos] = 1;               // not served here: per-query kernel
             continue;
         }
 
         int bstar = -1;            // selected bucket (pass B keeps buckets <= bstar)
-        uint32_t row_n = 0;        // entries appended to the row so far
+        double bound = tau;        // current upper bound of this lane's k-th squared distance
+        double bound_max = tau_max;
+        int list_n = 0;
+
+        // first bucket whose cumulative count reaches K -> tightened bound (upper bucket edge)
+        auto tighten = [&]() {
+            uint32_t cum = 0;
+            int b1 = -1;
+            for (int b = 0; b < kBuckets; ++b) {
+                cum += hist[b * 32 + lane];
+                if (cum >= (uint32_t)K) { b1 = b; break; }
+            }
+            if (b1 >= 0) bound = fmin(bound, (double)(b1 + 1) / scale * (1.0 + 1e-9));
+            bound_max = active ? bound : 0.0;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) bound_max = fmax(bound_max, __shfl_xor_sync(kFull, bound_max, o));
+        };
+
+        // stream the points of the eligible listed cells past every lane (pass 0: count into the
+        // histogram, pass 1: counting-sort placement into the row)
+        auto stream = [&](int pass, double lo_excl, double hi_incl) {
+            for (int j0 = 0; j0 < list_n; j0 += 32) {
+                const int e = j0 + lane;
+                uint32_t first = 0, cnt = 0;
+                if (e < list_n) {
+                    const double lb = l_lb2[e];
+                    if (lb > lo_excl && lb <= hi_incl) {
+                        const uint32_t cell = l_cell[e];
+                        first = __ldg(a.cell_first + cell);
+                        cnt = __ldg(a.cell_first + cell + 1) - first;
+                    }
+                }
+                const uint32_t incl = warp_incl_scan_u32(cnt, lane);
+                const uint32_t total = __shfl_sync(kFull, incl, 31);
+                if (total == 0) continue;
+                sa_off[lane] = incl - cnt; sa_off[32 + lane] = total; sa_base[lane] = first;
+                __syncwarp();
+                for (uint32_t b = 0; b < total; b += 32) {
+                    const uint32_t i = b + lane;
+                    if (i < total) {
+                        const int kk = seg_search(sa_off, i);
+                        const uint32_t p = sa_base[kk] + (i - sa_off[kk]);
+                        c_xy[lane] = make_double2(a.sx[p], a.sy[p]); c_z[lane] = a.sz[p]; c_pos[lane] = p;
+                    }
+                    __syncwarp();
+                    const int nc = (int)min(32u, total - b);
+                    if (active) {
+#pragma unroll 4
+                        for (int c = 0; c < nc; ++c) {
+                            const double2 xy = c_xy[c];
+                            const double d2 = dist2(xy.x, xy.y, c_z[c], qx, qy, qz);
+                            if (d2 <= tau) {
+                                int bk = (int)(d2 * scale);
+                                bk = bk > kBuckets - 1 ? kBuckets - 1 : bk;
+                                if (pass == 0) {
+                                    hist[bk * 32 + lane] += 1;
+                                } else if (bk <= bstar) {
+                                    const uint32_t slot = hist[bk * 32 + lane];
+                                    hist[bk * 32 + lane] = (uint16_t)(slot + 1);
+                                    a.out_pos[(size_t)pos * kRow + slot] = c_pos[c];
+                                }
+                            }
+                        }
+                    }
+                    __syncwarp();
+                }
+            }
+        };
+
+        auto flush = [&](int pass) {
+            if (pass == 0) {
+                // cells overlapping the members' box first: they hold >= k points, which tightens
+                // the bound before anything farther away is touched
+                stream(0, -1.0, 0.0);
+                tighten();
+                stream(0, 0.0, bound_max);
+                tighten();
+            } else {
+                stream(1, -1.0, bound_max);
+            }
+            list_n = 0;
+        };
+
         for (int pass = 0; pass < 2; ++pass) {
             if (pass == 0) {
                 for (int i = lane; i < kBuckets * 32; i += 32) hist[i] = 0;      // [bucket][lane]
                 __syncwarp();
             }
-            int list_n = 0;
-            auto flush = [&]() {
-                for (int j0 = 0; j0 < list_n; j0 += 32) {
-                    const int e = j0 + lane;
-                    uint32_t first = 0, cnt = 0;
-                    if (e < list_n) {
-                        const uint32_t cell = l_cell[e];
-                        first = __ldg(a.cell_first + cell);
-                        cnt = __ldg(a.cell_first + cell + 1) - first;
-                    }
-                    const uint32_t incl = warp_incl_scan_u32(cnt, lane);
-                    const uint32_t total = __shfl_sync(kFull, incl, 31);
-                    sa_off[lane] = incl - cnt; sa_off[32 + lane] = total; sa_base[lane] = first;
-                    __syncwarp();
-                    for (uint32_t b = 0; b < total; b += 32) {
-                        const uint32_t i = b + lane;
-                        if (i < total) {
-                            const int kk = seg_search(sa_off, i);
-                            const uint32_t p = sa_base[kk] + (i - sa_off[kk]);
-                            c_xy[lane] = make_double2(a.sx[p], a.sy[p]); c_z[lane] = a.sz[p]; c_pos[lane] = p;
-                        }
-                        __syncwarp();
-                        const int nc = (int)min(32u, total - b);
-                        if (active) {
-#pragma unroll 4
-                            for (int c = 0; c < nc; ++c) {
-                                const double2 xy = c_xy[c];
-                                const double d2 = dist2(xy.x, xy.y, c_z[c], qx, qy, qz);
-                                if (d2 <= tau) {
-                                    int bk = (int)(d2 * scale);
-                                    bk = bk > kBuckets - 1 ? kBuckets - 1 : bk;
-                                    if (pass == 0) {
-                                        hist[bk * 32 + lane] += 1;
-                                    } else if (bk <= bstar) {
-                                        a.out_pos[(size_t)pos * kRow + row_n] = c_pos[c];
-                                        ++row_n;
-                                    }
-                                }
-                            }
-                        }
-                        __syncwarp();
-                    }
-                }
-                list_n = 0;
-            };
+            const int rmax = (int)ceil((sqrt(bound_max) + g.slack) / scell);
             for (int R = 0; R <= rmax; ++R) {
                 const int w = 2 * R + 1, v = 2 * R - 1;
                 const int A = w * w, B = R > 0 ? w * v : 0, C = R > 0 ? v * v : 0;
@@ -638,7 +678,7 @@ knn_group_kernel(GroupArgs a) {
                             const double lb = box_box_gap2(g.ox + cx * scell, g.oy + cy * scell, g.oz + cz * scell,
                                                            g.ox + (cx + 1) * scell, g.oy + (cy + 1) * scell, g.oz + (cz + 1) * scell,
                                                            bminx, bminy, bminz, bmaxx, bmaxy, bmaxz, g.slack);
-                            if (!(lb > tau_max)) {
+                            if (!(lb > bound_max)) {
                                 const uint64_t key = morton3(cx, cy, cz);
                                 uint32_t h = (uint32_t)hash64(key) & a.table_mask;
                                 while (true) {
@@ -662,21 +702,25 @@ knn_group_kernel(GroupArgs a) {
                     for (uint32_t b = 0; b < ftotal; b += 32) {
                         const uint32_t i = b + lane;
                         bool keep = false;
+                        double lb = inf;
                         uint32_t e = 0;
                         if (i < ftotal) {
                             const int kk = seg_search(sb_off, i);
                             e = sb_base[kk] + (i - sb_off[kk]);
                             const uint64_t key = __ldg(a.ucell + e);
                             const int fx = (int)compact_bits21(key), fy = (int)compact_bits21(key >> 1), fz = (int)compact_bits21(key >> 2);
-                            const double lb = box_box_gap2(g.ox + fx * g.cell, g.oy + fy * g.cell, g.oz + fz * g.cell,
-                                                           g.ox + (fx + 1) * g.cell, g.oy + (fy + 1) * g.cell, g.oz + (fz + 1) * g.cell,
-                                                           bminx, bminy, bminz, bmaxx, bmaxy, bmaxz, g.slack);
-                            keep = !(lb > tau_max);
+                            lb = box_box_gap2(g.ox + fx * g.cell, g.oy + fy * g.cell, g.oz + fz * g.cell,
+                                              g.ox + (fx + 1) * g.cell, g.oy + (fy + 1) * g.cell, g.oz + (fz + 1) * g.cell,
+                                              bminx, bminy, bminz, bmaxx, bmaxy, bmaxz, g.slack);
+                            keep = !(lb > bound_max);
                         }
                         const uint32_t kb = __ballot_sync(kFull, keep);
                         if (kb) {
-                            if (list_n + 32 > kCellCap) flush();
-                            if (keep) l_cell[list_n + __popc(kb & ((1u << lane) - 1u))] = e;
+                            if (list_n + 32 > kCellCap) flush(pass);
+                            if (keep) {
+                                const int slot = list_n + __popc(kb & ((1u << lane) - 1u));
+                                l_lb2[slot] = lb; l_cell[slot] = e;
+                            }
                             list_n += __popc(kb);
                             __syncwarp();
                         }
@@ -684,26 +728,35 @@ knn_group_kernel(GroupArgs a) {
                     __syncwarp();
                 }
             }
-            flush();
+            flush(pass);
             if (pass == 0) {
-                // select: first bucket whose cumulative count reaches K
+                // select: first bucket whose cumulative count reaches K; turn the histogram into
+                // exclusive offsets so that pass B places candidates bucket-sorted (counting sort)
                 __syncwarp();
                 uint32_t cum = 0;
-                int bs = kBuckets - 1;
-                bool found = false;
+                int bs = -1;
                 for (int b = 0; b < kBuckets; ++b) {
-                    cum += hist[b * 32 + lane];
-                    if (!found && cum >= (uint32_t)K) { found = true; bs = b; break; }
+                    const uint32_t hb = hist[b * 32 + lane];
+                    hist[b * 32 + lane] = (uint16_t)cum;
+                    cum += hb;
+                    if (cum >= (uint32_t)K) { bs = b; break; }
                 }
-                if (active && (!found || cum > (uint32_t)kRow)) {     // row would overflow (or bound broken)
+                if (active && (bs < 0 || cum > (uint32_t)kRow)) {     // row would overflow (or bound broken)
                     a.todo[pos] = 1;
                     active = false;
                 }
                 bstar = bs;
+                if (active) {
+                    a.out_cnt[pos] = (uint8_t)cum;
+                    bound = fmin(bound, (double)(bs + 1) / scale * (1.0 + 1e-9));
+                }
+                bound_max = active ? bound : 0.0;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) bound_max = fmax(bound_max, __shfl_xor_sync(kFull, bound_max, o));
                 if (!__any_sync(kFull, active)) break;
+                __syncwarp();
             }
         }
-        if (active) a.out_cnt[pos] = (uint8_t)row_n;
     }
 }
 
