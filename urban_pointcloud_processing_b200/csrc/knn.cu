@@ -571,6 +571,7 @@ knn_group_kernel(GroupArgs a) {
         auto tighten = [&]() {
             uint32_t cum = 0;
             int b1 = -1;
+#pragma unroll 1
             for (int b = 0; b < kBuckets; ++b) {
                 cum += hist[b * 32 + lane];
                 if (cum >= (uint32_t)K) { b1 = b; break; }
@@ -610,7 +611,7 @@ knn_group_kernel(GroupArgs a) {
                     __syncwarp();
                     const int nc = (int)min(32u, total - b);
                     if (active) {
-#pragma unroll 4
+#pragma unroll 2
                         for (int c = 0; c < nc; ++c) {
                             const double2 xy = c_xy[c];
                             const double d2 = dist2(xy.x, xy.y, c_z[c], qx, qy, qz);
@@ -632,75 +633,76 @@ knn_group_kernel(GroupArgs a) {
             }
         };
 
-        auto flush = [&](int pass) {
-            if (pass == 0) {
-                // cells overlapping the members' box first: they hold >= k points, which tightens
-                // the bound before anything farther away is touched
-                stream(0, -1.0, 0.0);
-                tighten();
-                stream(0, 0.0, bound_max);
-                tighten();
-            } else {
-                stream(1, -1.0, bound_max);
-            }
-            list_n = 0;
-        };
-
         for (int pass = 0; pass < 2; ++pass) {
             if (pass == 0) {
                 for (int i = lane; i < kBuckets * 32; i += 32) hist[i] = 0;      // [bucket][lane]
                 __syncwarp();
             }
             const int rmax = (int)ceil((sqrt(bound_max) + g.slack) / scell);
-            for (int R = 0; R <= rmax; ++R) {
-                const int w = 2 * R + 1, v = 2 * R - 1;
-                const int A = w * w, B = R > 0 ? w * v : 0, C = R > 0 ? v * v : 0;
-                const int total = R == 0 ? 1 : 2 * A + 2 * B + 2 * C;
-                for (int t0 = 0; t0 < total; t0 += 32) {
-                    int t = t0 + lane;
-                    uint32_t f0 = 0, f1 = 0;
-                    if (t < total) {
-                        int cx, cy, cz;
-                        if (R == 0) { cx = gsx; cy = gsy; cz = gsz; }
-                        else if (t < 2 * A) {
-                            cz = t < A ? gsz - R : gsz + R; if (t >= A) t -= A;
-                            cx = gsx - R + t % w; cy = gsy - R + t / w;
-                        } else if (t < 2 * A + 2 * B) {
-                            t -= 2 * A;
-                            cy = t < B ? gsy - R : gsy + R; if (t >= B) t -= B;
-                            cx = gsx - R + t % w; cz = gsz - R + 1 + t / w;
-                        } else {
-                            t -= 2 * A + 2 * B;
-                            cx = t < C ? gsx - R : gsx + R; if (t >= C) t -= C;
-                            cy = gsy - R + 1 + t % v; cz = gsz - R + 1 + t / v;
-                        }
-                        if (cx >= 0 && cy >= 0 && cz >= 0 && cx < nsx && cy < nsy && cz < nsz) {
-                            const double lb = box_box_gap2(g.ox + cx * scell, g.oy + cy * scell, g.oz + cz * scell,
-                                                           g.ox + (cx + 1) * scell, g.oy + (cy + 1) * scell, g.oz + (cz + 1) * scell,
-                                                           bminx, bminy, bminz, bmaxx, bmaxy, bmaxz, g.slack);
-                            if (!(lb > bound_max)) {
-                                const uint64_t key = morton3(cx, cy, cz);
-                                uint32_t h = (uint32_t)hash64(key) & a.table_mask;
-                                while (true) {
-                                    const uint32_t idx = __ldg(a.table + h);
-                                    if (idx == kEmpty) break;
-                                    if (__ldg(a.sc_key + idx) == key) {
-                                        f0 = __ldg(a.sc_cell_first + idx); f1 = __ldg(a.sc_cell_first + idx + 1);
-                                        break;
+            // Enumeration state machine: fill the cell list until it is full or the rings are
+            // exhausted, then flush it -- ONE flush / stream site keeps the kernel small enough
+            // for the instruction cache.
+            int R = 0, t0 = 0;
+            uint32_t fb = 0, ftotal = 0;
+            bool have_chunk = false, enum_done = false;
+            while (!enum_done) {
+                while (true) {
+                    if (!have_chunk) {
+                        if (R > rmax) { enum_done = true; break; }
+                        const int w = 2 * R + 1, v = 2 * R - 1;
+                        const int A = w * w, B = R > 0 ? w * v : 0, C = R > 0 ? v * v : 0;
+                        const int total = R == 0 ? 1 : 2 * A + 2 * B + 2 * C;
+                        int t = t0 + lane;
+                        uint32_t f0 = 0, f1 = 0;
+                        if (t < total) {
+                            int cx, cy, cz;
+                            if (R == 0) { cx = gsx; cy = gsy; cz = gsz; }
+                            else if (t < 2 * A) {
+                                cz = t < A ? gsz - R : gsz + R; if (t >= A) t -= A;
+                                cx = gsx - R + t % w; cy = gsy - R + t / w;
+                            } else if (t < 2 * A + 2 * B) {
+                                t -= 2 * A;
+                                cy = t < B ? gsy - R : gsy + R; if (t >= B) t -= B;
+                                cx = gsx - R + t % w; cz = gsz - R + 1 + t / w;
+                            } else {
+                                t -= 2 * A + 2 * B;
+                                cx = t < C ? gsx - R : gsx + R; if (t >= C) t -= C;
+                                cy = gsy - R + 1 + t % v; cz = gsz - R + 1 + t / v;
+                            }
+                            if (cx >= 0 && cy >= 0 && cz >= 0 && cx < nsx && cy < nsy && cz < nsz) {
+                                const double lb = box_box_gap2(g.ox + cx * scell, g.oy + cy * scell, g.oz + cz * scell,
+                                                               g.ox + (cx + 1) * scell, g.oy + (cy + 1) * scell, g.oz + (cz + 1) * scell,
+                                                               bminx, bminy, bminz, bmaxx, bmaxy, bmaxz, g.slack);
+                                if (!(lb > bound_max)) {
+                                    const uint64_t key = morton3(cx, cy, cz);
+                                    uint32_t h = (uint32_t)hash64(key) & a.table_mask;
+                                    while (true) {
+                                        const uint32_t idx = __ldg(a.table + h);
+                                        if (idx == kEmpty) break;
+                                        if (__ldg(a.sc_key + idx) == key) {
+                                            f0 = __ldg(a.sc_cell_first + idx); f1 = __ldg(a.sc_cell_first + idx + 1);
+                                            break;
+                                        }
+                                        h = (h + 1) & a.table_mask;
                                     }
-                                    h = (h + 1) & a.table_mask;
                                 }
                             }
                         }
+                        t0 += 32;
+                        if (t0 >= total) { ++R; t0 = 0; }
+                        const uint32_t fcnt = f1 - f0;
+                        const uint32_t fincl = warp_incl_scan_u32(fcnt, lane);
+                        ftotal = __shfl_sync(kFull, fincl, 31);
+                        if (ftotal == 0) continue;
+                        __syncwarp();
+                        sb_off[lane] = fincl - fcnt; sb_off[32 + lane] = ftotal; sb_base[lane] = f0;
+                        __syncwarp();
+                        fb = 0;
+                        have_chunk = true;
                     }
-                    const uint32_t fcnt = f1 - f0;
-                    const uint32_t fincl = warp_incl_scan_u32(fcnt, lane);
-                    const uint32_t ftotal = __shfl_sync(kFull, fincl, 31);
-                    if (ftotal == 0) continue;
-                    sb_off[lane] = fincl - fcnt; sb_off[32 + lane] = ftotal; sb_base[lane] = f0;
-                    __syncwarp();
-                    for (uint32_t b = 0; b < ftotal; b += 32) {
-                        const uint32_t i = b + lane;
+                    // expand the fine cells of the current chunk into the list
+                    while (fb < ftotal && list_n + 32 <= kCellCap) {
+                        const uint32_t i = fb + lane;
                         bool keep = false;
                         double lb = inf;
                         uint32_t e = 0;
@@ -715,26 +717,35 @@ knn_group_kernel(GroupArgs a) {
                             keep = !(lb > bound_max);
                         }
                         const uint32_t kb = __ballot_sync(kFull, keep);
-                        if (kb) {
-                            if (list_n + 32 > kCellCap) flush(pass);
-                            if (keep) {
-                                const int slot = list_n + __popc(kb & ((1u << lane) - 1u));
-                                l_lb2[slot] = lb; l_cell[slot] = e;
-                            }
-                            list_n += __popc(kb);
-                            __syncwarp();
+                        if (keep) {
+                            const int slot = list_n + __popc(kb & ((1u << lane) - 1u));
+                            l_lb2[slot] = lb; l_cell[slot] = e;
                         }
+                        list_n += __popc(kb);
+                        fb += 32;
                     }
                     __syncwarp();
+                    if (fb >= ftotal) have_chunk = false;
+                    else break;                      // list full: flush, then resume this chunk
                 }
+                // ---- flush: pass 0 counts (cells overlapping the members' box first, which hold
+                // >= k points and tighten the bound before anything farther is touched), pass 1 places
+                const int n_rounds = pass == 0 ? 2 : 1;
+                for (int round = 0; round < n_rounds && list_n > 0; ++round) {
+                    const double lo_excl = (pass == 0 && round == 1) ? 0.0 : -1.0;
+                    const double hi_incl = (pass == 0 && round == 0) ? 0.0 : bound_max;
+                    stream(pass, lo_excl, hi_incl);
+                    if (pass == 0) tighten();
+                }
+                list_n = 0;
             }
-            flush(pass);
             if (pass == 0) {
                 // select: first bucket whose cumulative count reaches K; turn the histogram into
                 // exclusive offsets so that pass B places candidates bucket-sorted (counting sort)
                 __syncwarp();
                 uint32_t cum = 0;
                 int bs = -1;
+#pragma unroll 1
                 for (int b = 0; b < kBuckets; ++b) {
                     const uint32_t hb = hist[b * 32 + lane];
                     hist[b * 32 + lane] = (uint16_t)cum;
