@@ -30,6 +30,7 @@
 // Epilogue (knn_epilogue_kernel): one thread per query folds its sorted neighbour list in
 // order into the Open3D cumulant covariances / FastEigen3x3 normal and writes the kNN row.
 #include <math.h>
+#include <stdlib.h>
 #include "common.cuh"
 #include "primitives.cuh"
 #include "upcp_math.cuh"
@@ -51,6 +52,7 @@ constexpr uint32_t kFull = 0xffffffffu;
 struct GridParams {
     double ox, oy, oz, cell, inv_cell, slack;
     int nx, ny, nz;
+    int sc_log;        // super-cell = (1 << sc_log)^3 fine cells (2 or 3)
 };
 
 __device__ __forceinline__ uint64_t expand_bits21(uint32_t v) {
@@ -145,8 +147,9 @@ struct KnnScCellFunctor {    // super-cell runs over the fine-cell list
     const uint64_t* ucell;
     uint64_t* sc_key;
     uint32_t* sc_cell_first;
+    int sc_shift;
     __device__ void operator()(int64_t e, bool is_first, uint32_t rank) const {
-        if (is_first) { sc_key[rank] = ucell[e] >> 6; sc_cell_first[rank] = (uint32_t)e; }
+        if (is_first) { sc_key[rank] = ucell[e] >> sc_shift; sc_cell_first[rank] = (uint32_t)e; }
     }
 };
 
@@ -282,16 +285,17 @@ knn_select_kernel(SelectArgs a) {
     const GridParams g = a.g;
     const int K = a.k;
     const double inf = __longlong_as_double(0x7ff0000000000000LL);
-    const double scell = 4.0 * g.cell;                       // super-cell edge
-    const int nsx = (g.nx + 3) >> 2, nsy = (g.ny + 3) >> 2, nsz = (g.nz + 3) >> 2;
+    const int scl = g.sc_log, scm = (1 << g.sc_log) - 1;
+    const double scell = (double)(1 << g.sc_log) * g.cell;   // super-cell edge
+    const int nsx = (g.nx + scm) >> scl, nsy = (g.ny + scm) >> scl, nsz = (g.nz + scm) >> scl;
 
     const int64_t n_todo = a.todo_idx ? (int64_t)*a.todo_cnt : a.m;
     for (int64_t qi = (int64_t)blockIdx.x * kSelWarps + warp; qi < n_todo; qi += (int64_t)gridDim.x * kSelWarps) {
         const int64_t q = a.todo_idx ? (int64_t)a.todo_idx[qi] : qi;
         const double qx = a.sx[q], qy = a.sy[q], qz = a.sz[q];
-        const int sx = cell_coord(qx, g.ox, g.inv_cell, g.nx) >> 2;
-        const int sy = cell_coord(qy, g.oy, g.inv_cell, g.ny) >> 2;
-        const int sz = cell_coord(qz, g.oz, g.inv_cell, g.nz) >> 2;
+        const int sx = cell_coord(qx, g.ox, g.inv_cell, g.nx) >> scl;
+        const int sy = cell_coord(qy, g.oy, g.inv_cell, g.ny) >> scl;
+        const int sz = cell_coord(qz, g.oz, g.inv_cell, g.nz) >> scl;
 
         Nb mine; mine.d = inf; mine.c = kFull; mine.p = 0;   // lane j: j-th nearest so far
         double kth_d = inf; uint32_t kth_c = kFull;          // the K-th entry (lane K-1), warp-uniform
@@ -524,8 +528,9 @@ knn_group_kernel(GroupArgs a) {
     const int K = a.k;
     const uint32_t n_groups = *a.n_groups;
     const double inf = __longlong_as_double(0x7ff0000000000000LL);
-    const double scell = 4.0 * g.cell;
-    const int nsx = (g.nx + 3) >> 2, nsy = (g.ny + 3) >> 2, nsz = (g.nz + 3) >> 2;
+    const int scl = g.sc_log, scm = (1 << g.sc_log) - 1;
+    const double scell = (double)(1 << g.sc_log) * g.cell;
+    const int nsx = (g.nx + scm) >> scl, nsy = (g.ny + scm) >> scl, nsz = (g.nz + scm) >> scl;
 
     for (uint32_t grp = blockIdx.x * kGrpWarps + warp; grp < n_groups; grp += gridDim.x * kGrpWarps) {
         const uint4 gd = a.groups[grp];
@@ -552,9 +557,9 @@ knn_group_kernel(GroupArgs a) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) tau_max = fmax(tau_max, __shfl_xor_sync(kFull, tau_max, o));
         const double scale = (double)kBuckets / tau;
-        const int sx = cell_coord(qx, g.ox, g.inv_cell, g.nx) >> 2;       // same for all members
-        const int sy = cell_coord(qy, g.oy, g.inv_cell, g.ny) >> 2;
-        const int sz = cell_coord(qz, g.oz, g.inv_cell, g.nz) >> 2;
+        const int sx = cell_coord(qx, g.ox, g.inv_cell, g.nx) >> scl;       // same for all members
+        const int sy = cell_coord(qy, g.oy, g.inv_cell, g.ny) >> scl;
+        const int sz = cell_coord(qz, g.oz, g.inv_cell, g.nz) >> scl;
         const int gsx = __shfl_sync(kFull, sx, 0), gsy = __shfl_sync(kFull, sy, 0), gsz = __shfl_sync(kFull, sz, 0);
         bool active = is_query;
         if ((int)ceil((sqrt(tau_max) + g.slack) / scell) > 2 || (int)n_members < K) {
@@ -980,7 +985,7 @@ static int knn_impl(const double* d_x, const double* d_y, const double* d_z, int
     UPCP_LAUNCH_OK();
     // super-cell runs over the sorted POINTS (query groups are cut from them)
     uint32_t* n_runs = counters + 2;
-    knn_boundary_flags_kernel<K><<<grid_m, kBlock, 0, st>>>(keys, m, 6, flags);
+    knn_boundary_flags_kernel<K><<<grid_m, kBlock, 0, st>>>(keys, m, 3 * g.sc_log, flags);
     UPCP_LAUNCH_OK();
     {
         RunFunctor f{run_first};
@@ -1003,10 +1008,10 @@ static int knn_impl(const double* d_x, const double* d_y, const double* d_z, int
     UPCP_LAUNCH_OK();
     // super-cells: contiguous runs of the fine-cell list with equal key >> 6
     uint32_t* n_sc = counters + 4;
-    knn_boundary_flags_kernel<uint64_t><<<grid_for(c_total, kBlock), kBlock, 0, st>>>(ucell, c_total, 6, flags);
+    knn_boundary_flags_kernel<uint64_t><<<grid_for(c_total, kBlock), kBlock, 0, st>>>(ucell, c_total, 3 * g.sc_log, flags);
     UPCP_LAUNCH_OK();
     {
-        KnnScCellFunctor f{ucell, sc_key, sc_cell_first};
+        KnnScCellFunctor f{ucell, sc_key, sc_cell_first, 3 * g.sc_log};
         UPCP_TRY(compact_apply(flags, c_total, n_sc, prim_ws, st, f));
     }
     knn_finish_sc_kernel<<<1, 32, 0, st>>>(n_sc, sc_cell_first, c_total);
@@ -1112,6 +1117,8 @@ int upcp_knn_normals(const double* d_x, const double* d_y, const double* d_z, in
     double amax = fmax(fmax(fabs(g.ox), fabs(h_bbox_sel6[3])), fmax(fmax(fabs(g.oy), fabs(h_bbox_sel6[4])),
                                                                      fmax(fabs(g.oz), fabs(h_bbox_sel6[5]))));
     g.slack = cell * 1e-6 + amax * 1e-12;
+    g.sc_log = 2;
+    if (const char* env = getenv("UPCP_KNN_SCLOG")) { int v = atoi(env); if (v == 2 || v == 3) g.sc_log = v; }   // tuning knob
     int bits = bits_for(g.nx > g.ny ? (g.nx > g.nz ? g.nx : g.nz) : (g.ny > g.nz ? g.ny : g.nz));
     if (bits < 2) bits = 2;
     int key_bits = 3 * bits;

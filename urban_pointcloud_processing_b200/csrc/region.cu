@@ -64,55 +64,75 @@ grow_kernel(const int32_t* __restrict__ knn, int k, const double* __restrict__ n
     const int lane = threadIdx.x & 31;
     volatile int32_t* vqueue = queue;
     volatile int* vpending = &ctr->pending;
+    // two seeds per step when a kNN row fits a half-warp, else one
+    const int per_step = k <= 16 ? 2 : 1;
+    const int sub = per_step == 2 ? (lane >> 4) : 0;          // which seed of the step this lane serves
+    const int j = per_step == 2 ? (lane & 15) : lane;        // neighbour slot within the row
     while (true) {
-        unsigned int t = 0;
-        if (lane == 0) t = atomicAdd(&ctr->head, 1u);
-        t = __shfl_sync(0xffffffffu, t, 0);
-        if ((int64_t)t >= m) return;                 // at most m seeds can ever be queued
-        // wait for ticket t to be published, or for global quiescence
-        int32_t s = -1;
-        if (lane == 0) {
-            unsigned int spins = 0;
-            while (true) {
-                s = vqueue[t];
-                if (s >= 0) break;
-                if (*vpending <= 0) { s = -2; break; }
+        // a warp takes 32 tickets at once (one atomic on the shared head counter per 32 seeds) ...
+        unsigned int t0 = 0;
+        if (lane == 0) t0 = atomicAdd(&ctr->head, 32u);
+        t0 = __shfl_sync(0xffffffffu, t0, 0);
+        if ((int64_t)t0 >= m) return;                 // at most m seeds can ever be queued
+        // ... and serves them as they are published: waiting for all 32 first could deadlock,
+        // because the seeds that fill the later tickets may come from the earlier ones
+        int32_t mine = -1;
+        uint32_t remaining = __ballot_sync(0xffffffffu, (int64_t)t0 + lane < m);
+        unsigned int spins = 0;
+        while (remaining) {
+            if (((remaining >> lane) & 1u) && mine < 0) mine = vqueue[t0 + lane];
+            const uint32_t ready = __ballot_sync(0xffffffffu, ((remaining >> lane) & 1u) && mine >= 0);
+            if (ready == 0) {
+                int pend = 1;
+                if (lane == 0) pend = *vpending;
+                pend = __shfl_sync(0xffffffffu, pend, 0);
+                if (pend <= 0) return;                 // global quiescence: nothing left anywhere
                 __nanosleep(64);
-                if (++spins > (1u << 26)) { atomicExch(&ctr->error, 1u); s = -2; break; }   // safety valve
+                if (++spins > (1u << 26)) { if (lane == 0) atomicExch(&ctr->error, 1u); return; }   // safety valve
+                continue;
             }
-        }
-        s = __shfl_sync(0xffffffffu, s, 0);
-        if (s < 0) return;
-
-        const Vec3 ns = {normals[(size_t)s * 3], normals[(size_t)s * 3 + 1], normals[(size_t)s * 3 + 2]};
-        // neighbour_idx[1:k] (region_growing.py:112): the first returned index is dropped
-        for (int j0 = 1; j0 < k; j0 += 32) {
-            const int j = j0 + lane;
-            bool push = false;
-            int32_t nb = -1;
-            if (j < k) {
-                nb = knn[(size_t)s * k + j];
-                if (nb >= 0 && __ldcg(state + nb) == 0) {
-                    const Vec3 nn = {normals[(size_t)nb * 3], normals[(size_t)nb * 3 + 1], normals[(size_t)nb * 3 + 2]};
-                    if (vector_angle_deg(ns, nn) < threshold_deg) {
-                        if (atomicExch(&state[nb], 1) == 0) push = can_seed[nb] != 0;
+            uint32_t todo = ready;
+            while (todo) {
+                // pick the seed(s) of this step
+                const int srcA = __ffs(todo) - 1;
+                todo &= todo - 1;
+                int srcB = -1;
+                if (per_step == 2 && todo) { srcB = __ffs(todo) - 1; todo &= todo - 1; }
+                const int src = sub == 0 ? srcA : srcB;
+                const int32_t s = __shfl_sync(0xffffffffu, mine, src < 0 ? 0 : src);
+                bool push = false;
+                int32_t nb = -1;
+                // neighbour_idx[1:k] (region_growing.py:112): the first returned index is dropped
+                for (int jj = j; jj < k; jj += (per_step == 2 ? 16 : 32)) {
+                    // (k <= 32: at most one trip)
+                    if (src >= 0 && jj >= 1) {
+                        nb = knn[(size_t)s * k + jj];
+                        if (nb >= 0 && __ldcg(state + nb) == 0) {
+                            const Vec3 ns = {normals[(size_t)s * 3], normals[(size_t)s * 3 + 1], normals[(size_t)s * 3 + 2]};
+                            const Vec3 nn = {normals[(size_t)nb * 3], normals[(size_t)nb * 3 + 1], normals[(size_t)nb * 3 + 2]};
+                            if (vector_angle_deg(ns, nn) < threshold_deg) {
+                                if (atomicExch(&state[nb], 1) == 0) push = can_seed[nb] != 0;
+                            }
+                        }
                     }
                 }
-            }
-            uint32_t bal = __ballot_sync(0xffffffffu, push);
-            if (bal) {
-                int leader = __ffs(bal) - 1;
-                unsigned int base = 0;
-                if (lane == leader) {
-                    atomicAdd(&ctr->pending, __popc(bal));           // before the slots become visible
-                    base = atomicAdd(&ctr->tail, (unsigned int)__popc(bal));
+                const uint32_t bal = __ballot_sync(0xffffffffu, push);
+                if (bal) {
+                    const int leader = __ffs(bal) - 1;
+                    unsigned int base = 0;
+                    if (lane == leader) {
+                        atomicAdd(&ctr->pending, __popc(bal));           // before the slots become visible
+                        base = atomicAdd(&ctr->tail, (unsigned int)__popc(bal));
+                    }
+                    base = __shfl_sync(0xffffffffu, base, leader);
+                    if (push) vqueue[base + __popc(bal & ((1u << lane) - 1u))] = nb;
                 }
-                base = __shfl_sync(0xffffffffu, base, leader);
-                if (push) vqueue[base + __popc(bal & ((1u << lane) - 1u))] = nb;
             }
+            __syncwarp();
+            if (lane == 0) { __threadfence(); atomicSub(&ctr->pending, __popc(ready)); }
+            remaining &= ~ready;
+            spins = 0;
         }
-        __syncwarp();
-        if (lane == 0) { __threadfence(); atomicSub(&ctr->pending, 1); }
     }
 }
 

@@ -25,11 +25,11 @@ CURVATURE_TOL = 1e-9
 
 
 def default_cell_size(bbox_sel, m, radius):
-    """Fine-cell edge of the search grid: aim at ~8 points per occupied cell of a surface-like
+    """Fine-cell edge of the search grid: aim at ~16 points per occupied cell of a surface-like
     cloud (urban LiDAR covers roughly 3x its footprint area), bounded by the search radius."""
     ex = max(float(bbox_sel[3] - bbox_sel[0]), 1e-3)
     ey = max(float(bbox_sel[4] - bbox_sel[1]), 1e-3)
-    c = float(np.sqrt(24.0 * ex * ey / max(int(m), 1)))
+    c = float(np.sqrt(48.0 * ex * ey / max(int(m), 1)))
     r = max(float(radius), 1e-3)
     return min(max(c, r / 8.0), r / 2.0)
 
