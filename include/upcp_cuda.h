@@ -232,7 +232,13 @@ int upcp_lcc(const double* d_x, const double* d_y, const double* d_z, int64_t n,
  *                  (0,0,1) when fewer than 3 neighbours / zero normal;
  *   d_cov[m*6]   : optional (may be NULL) covariance xx,xy,xz,yy,yz,zz of the knn
  *                  neighbourhood (compute_mean_and_covariance, region_growing.py:69-71);
- *   d_curv[m*3]  : optional analytic eigenvalue ratios eval_i / sum (ascending eval).
+ *   d_curv[m*3]  : optional analytic eigenvalue ratios eval_i / sum (ascending eval);
+ *   d_seed_flag[m] : optional; the curvature seed test `eig_val[0] / sum < threshold_curve`
+ *                  (region_growing.py:59-73,132) decided on the device where it does not
+ *                  depend on LAPACK's eigenvalue order: 1 = all three analytic ratios are below
+ *                  the threshold (minus 1e-9), 0 = all are at or above it (plus 1e-9),
+ *                  2 = undecided (mixed sides / non-finite): the caller resolves these few on
+ *                  the host with dgeev exactly as the reference does.
  * Replaces: o3d.geometry.KDTreeFlann + search_knn_vector_3d + estimate_normals +
  * compute_mean_and_covariance (region_growing.py:59-73,86-92,105-109). */
 size_t upcp_knn_ws_bytes(int64_t n, int64_t m, int kmax);
@@ -241,6 +247,7 @@ int upcp_knn_normals(const double* d_x, const double* d_y, const double* d_z, in
                      int knn, int max_nn, double radius, double cell_size,
                      int32_t* d_knn, double* d_knn_d2 /* may be NULL */,
                      double* d_normals, double* d_cov, double* d_curv,
+                     double threshold_curve, uint8_t* d_seed_flag /* may be NULL */,
                      void* d_ws, size_t ws_bytes, void* stream);
 
 /* Region growing to the least fixpoint (region_growing.py:75-141, method='knn').

@@ -1,0 +1,41 @@
+"""Phase timing of RegionGrowing on the bench tile (development tool)."""
+import os, sys, time
+import numpy as np, torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from urban_pointcloud_processing_b200 import _lib, synthetic
+from urban_pointcloud_processing_b200 import device as dev
+from urban_pointcloud_processing_b200.region_growing import region_growing as rg
+from oracle import reference_py as R
+
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 20_000_000
+tile = synthetic.make_tile(n, seed=20240000)
+pts = tile['points']
+labels = np.zeros(n, dtype=np.uint16)
+labels = R.ahn_fuser_labels(pts, labels, labels == 0, tile['ahn_tile'], 9, 'ground', 0.2)
+labels = R.building_fuser_labels(pts, labels, labels == 0, tile['building_polygons'], 10, tile['ahn_tile'], 0.2)
+t = dev.DeviceTile(pts)
+d_labels = dev.upload_labels(labels, t.device)
+
+def phase(name, fn, acc):
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    out = fn()
+    torch.cuda.synchronize(); acc.append((name, (time.perf_counter() - t0) * 1e3))
+    return out
+
+for rep in range(3):
+    acc = []
+    d_sel = phase('mask_build sel', lambda: dev.mask_build(d_labels, None, base=True, ne=(9, 1)), acc)
+    bb = phase('bbox', lambda: t.bbox(d_sel), acc)
+    _, bbox_sel, m = bb
+    d_seed_full = phase('mask_build seed', lambda: dev.mask_build(d_labels, None, base=False, eq=(10,)), acc)
+    d_seed = phase('mask_gather', lambda: rg.mask_gather(d_sel, d_seed_full, m), acc)
+    ns = phase('mask_count', lambda: dev.mask_count(d_seed), acc)
+    out = phase('knn_normals', lambda: rg.knn_normals_device(t, d_sel, m, bbox_sel, 15, 30, 0.2, want_curv=False, threshold_curve=1.0), acc)
+    d_knn, _, d_normals, d_cov, _, d_flag = out
+    cs = phase('can_seed', lambda: rg.resolve_seed_flags(d_flag, d_cov, 1.0), acc)
+    gr = phase('region_grow', lambda: rg.region_grow_device(d_knn, d_normals, d_seed, cs[0], 20), acc)
+    sc = phase('mask_scatter', lambda: rg.mask_scatter(d_sel, gr[0]), acc)
+print(f'm={m} seeds={ns} host-resolved curvature={cs[1]} region={int(gr[1][0])}')
+for name, ms in acc:
+    print(f'{name:18s} {ms:8.2f} ms')
+print('total', sum(ms for _, ms in acc))

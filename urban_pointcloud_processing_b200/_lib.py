@@ -70,7 +70,8 @@ _PROTOTYPES = {
     'upcp_knn_ws_bytes': (c_size_t, [c_int64, c_int64, c_int]),
     'upcp_knn_normals': (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int64,
                                  POINTER(c_double), c_int, c_int, c_double, c_double, c_void_p,
-                                 c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+                                 c_void_p, c_void_p, c_void_p, c_void_p, c_double, c_void_p, c_void_p,
+                                 c_size_t, c_void_p]),
     'upcp_region_grow_ws_bytes': (c_size_t, [c_int64]),
     'upcp_region_grow': (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int64, c_double,
                                  c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),

@@ -55,6 +55,16 @@ struct GridParams {
     int sc_log;        // super-cell = (1 << sc_log)^3 fine cells (2 or 3)
 };
 
+// Sorted points as 32-byte records (x, y, z, compact id): one sector per gathered neighbour.
+struct __align__(32) P4 { double x, y, z, w; };
+__device__ __forceinline__ P4 load_p4(const P4* __restrict__ p) {
+    const double2 a = __ldg(reinterpret_cast<const double2*>(p));
+    const double2 b = __ldg(reinterpret_cast<const double2*>(p) + 1);
+    P4 r; r.x = a.x; r.y = a.y; r.z = b.x; r.w = b.y;
+    return r;
+}
+__device__ __forceinline__ uint32_t p4_cid(const P4& v) { return (uint32_t)__double_as_longlong(v.w); }
+
 __device__ __forceinline__ uint64_t expand_bits21(uint32_t v) {
     uint64_t x = v & 0x1fffffu;
     x = (x | x << 32) & 0x1f00000000ffffULL;
@@ -114,13 +124,14 @@ knn_keys_kernel(const double* __restrict__ x, const double* __restrict__ y,
 __global__ void __launch_bounds__(kBlock)
 knn_gather_kernel(const double* __restrict__ x, const double* __restrict__ y,
                   const double* __restrict__ z, const uint32_t* __restrict__ sel_idx,
-                  const uint32_t* __restrict__ perm, int64_t m,
-                  double* __restrict__ sx, double* __restrict__ sy, double* __restrict__ sz) {
+                  const uint32_t* __restrict__ perm, int64_t m, P4* __restrict__ spts) {
     int64_t stride = (int64_t)gridDim.x * kBlock;
     for (int64_t s = (int64_t)blockIdx.x * kBlock + threadIdx.x; s < m; s += stride) {
         uint32_t j = perm[s];
         int64_t i = sel_idx ? (int64_t)sel_idx[j] : (int64_t)j;
-        sx[s] = x[i]; sy[s] = y[i]; sz[s] = z[i];
+        double2* o = reinterpret_cast<double2*>(spts + s);
+        o[0] = make_double2(x[i], y[i]);
+        o[1] = make_double2(z[i], __longlong_as_double((long long)j));
     }
 }
 
@@ -176,8 +187,7 @@ knn_hash_insert_kernel(const uint64_t* __restrict__ keys, const uint32_t* __rest
 
 // ------------------------------------------------------------------ search ------
 struct SelectArgs {
-    const double* sx; const double* sy; const double* sz;   // sorted coordinates
-    const uint32_t* perm;          // sorted position -> compact id
+    const P4* spts;                // sorted points (x, y, z, compact id)
     const uint64_t* ucell; const uint32_t* cell_first;       // fine cells (Morton keys, first point)
     const uint64_t* sc_key; const uint32_t* sc_cell_first;   // super-cells (key >> 6, first fine cell)
     const uint32_t* table; uint32_t table_mask;              // hash: super-cell key -> super-cell index
@@ -292,7 +302,8 @@ knn_select_kernel(SelectArgs a) {
     const int64_t n_todo = a.todo_idx ? (int64_t)*a.todo_cnt : a.m;
     for (int64_t qi = (int64_t)blockIdx.x * kSelWarps + warp; qi < n_todo; qi += (int64_t)gridDim.x * kSelWarps) {
         const int64_t q = a.todo_idx ? (int64_t)a.todo_idx[qi] : qi;
-        const double qx = a.sx[q], qy = a.sy[q], qz = a.sz[q];
+        const P4 qp = load_p4(a.spts + q);
+        const double qx = qp.x, qy = qp.y, qz = qp.z;
         const int sx = cell_coord(qx, g.ox, g.inv_cell, g.nx) >> scl;
         const int sy = cell_coord(qy, g.oy, g.inv_cell, g.ny) >> scl;
         const int sz = cell_coord(qz, g.oz, g.inv_cell, g.nz) >> scl;
@@ -318,8 +329,9 @@ knn_select_kernel(SelectArgs a) {
                 if (i < total) {
                     const int kk = seg_search(sa_off, i);
                     const uint32_t p = sa_base[kk] + (i - sa_off[kk]);
-                    cand.d = dist2(a.sx[p], a.sy[p], a.sz[p], qx, qy, qz);
-                    cand.c = __ldg(a.perm + p);
+                    const P4 cp = load_p4(a.spts + p);
+                    cand.d = dist2(cp.x, cp.y, cp.z, qx, qy, qz);
+                    cand.c = p4_cid(cp);
                     cand.p = p;
                 }
                 bool pass = nb_less(cand.d, cand.c, kth_d, kth_c);
@@ -497,7 +509,7 @@ knn_select_kernel(SelectArgs a) {
 // cannot serve (groups with < k members, rows that would overflow, elongated groups) are flagged
 // and handled by the warp-per-query kernel above.  Both paths are exact.
 struct GroupArgs {
-    const double* sx; const double* sy; const double* sz;
+    const P4* spts;
     const uint64_t* ucell; const uint32_t* cell_first;
     const uint64_t* sc_key; const uint32_t* sc_cell_first;
     const uint32_t* table; uint32_t table_mask;
@@ -538,7 +550,8 @@ knn_group_kernel(GroupArgs a) {
         const bool member = (uint32_t)lane < n_members;
         const uint32_t pos = member_start + (member ? lane : 0);
         const bool is_query = member && pos >= chunk_start && pos < chunk_start + chunk_cnt;
-        const double qx = a.sx[pos], qy = a.sy[pos], qz = a.sz[pos];
+        const P4 qp = load_p4(a.spts + pos);
+        const double qx = qp.x, qy = qp.y, qz = qp.z;
         // bounding box of the members (non-member lanes alias member 0)
         double bminx = qx, bminy = qy, bminz = qz, bmaxx = qx, bmaxy = qy, bmaxz = qz;
 #pragma unroll
@@ -611,7 +624,8 @@ knn_group_kernel(GroupArgs a) {
                     if (i < total) {
                         const int kk = seg_search(sa_off, i);
                         const uint32_t p = sa_base[kk] + (i - sa_off[kk]);
-                        c_xy[lane] = make_double2(a.sx[p], a.sy[p]); c_z[lane] = a.sz[p]; c_pos[lane] = p;
+                        const P4 cp = load_p4(a.spts + p);
+                        c_xy[lane] = make_double2(cp.x, cp.y); c_z[lane] = cp.z; c_pos[lane] = p;
                     }
                     __syncwarp();
                     const int nc = (int)min(32u, total - b);
@@ -823,12 +837,13 @@ __global__ void knn_finish_runs_kernel(const uint32_t* __restrict__ n_runs, uint
 
 // ------------------------------------------------------------------ epilogue ----
 struct EpilogueArgs {
-    const double* sx; const double* sy; const double* sz;
-    const uint32_t* perm; const uint32_t* pos; const uint8_t* cnt;      // pos: [m][kRow]
+    const P4* spts;
+    const uint32_t* pos; const uint8_t* cnt;      // pos: [m][kRow]
     int64_t m;
     int knn, max_nn;
     double radius2;
     int32_t* out_knn; double* out_d2; double* out_normals; double* out_cov; double* out_curv;
+    double thr_curve; uint8_t* out_flag;
 };
 
 // One thread per query.  The candidate row (k exact neighbours from the per-query kernel, or
@@ -846,13 +861,15 @@ knn_epilogue_kernel(EpilogueArgs a) {
     int64_t stride = (int64_t)gridDim.x * kEpiThreads;
     for (int64_t s = (int64_t)blockIdx.x * kEpiThreads + tx; s < a.m; s += stride) {
         const uint32_t* row = a.pos + (size_t)s * kRow;
-        const double qx = a.sx[s], qy = a.sy[s], qz = a.sz[s];
-        const uint32_t cid = a.perm[s];
+        const P4 qp = load_p4(a.spts + s);
+        const double qx = qp.x, qy = qp.y, qz = qp.z;
+        const uint32_t cid = p4_cid(qp);
         const int n = (int)a.cnt[s];
         for (int j = 0; j < n; ++j) {
             const uint32_t p = __ldg(row + j);
-            const double d2 = dist2(a.sx[p], a.sy[p], a.sz[p], qx, qy, qz);
-            const uint32_t c = __ldg(a.perm + p);
+            const P4 cp = load_p4(a.spts + p);
+            const double d2 = dist2(cp.x, cp.y, cp.z, qx, qy, qz);
+            const uint32_t c = p4_cid(cp);
             int i = j;
             while (i > 0) {
                 const double dp = s_d[(i - 1) * kEpiThreads + tx];
@@ -875,7 +892,8 @@ knn_epilogue_kernel(EpilogueArgs a) {
             uint32_t c = 0;
             if (present) {
                 const uint32_t p = s_p[j * kEpiThreads + tx];
-                px = a.sx[p]; py = a.sy[p]; pz = a.sz[p];
+                const P4 cp = load_p4(a.spts + p);
+                px = cp.x; py = cp.y; pz = cp.z;
                 d2 = s_d[j * kEpiThreads + tx]; c = s_c[j * kEpiThreads + tx];
             }
             if (j < a.knn) {
@@ -899,16 +917,27 @@ knn_epilogue_kernel(EpilogueArgs a) {
             a.out_normals[(size_t)cid * 3 + 1] = nrm.y;
             a.out_normals[(size_t)cid * 3 + 2] = nrm.z;
         }
-        if (a.out_cov || a.out_curv) {
+        if (a.out_cov || a.out_curv || a.out_flag) {
             double cov6[6];
             cov_cum.finish(kk > 0 ? kk : 1, cov6);
             if (a.out_cov)
                 for (int t = 0; t < 6; ++t) a.out_cov[(size_t)cid * 6 + t] = cov6[t];
-            if (a.out_curv) {
+            if (a.out_curv || a.out_flag) {
                 double ev[3];
                 fast_eigen3x3(cov6, ev);
-                double sum = ev[0] + ev[1] + ev[2];
-                for (int t = 0; t < 3; ++t) a.out_curv[(size_t)cid * 3 + t] = ev[t] / sum;
+                const double sum = ev[0] + ev[1] + ev[2];
+                const double r0 = ev[0] / sum, r1 = ev[1] / sum, r2 = ev[2] / sum;
+                if (a.out_curv) {
+                    a.out_curv[(size_t)cid * 3 + 0] = r0; a.out_curv[(size_t)cid * 3 + 1] = r1;
+                    a.out_curv[(size_t)cid * 3 + 2] = r2;
+                }
+                if (a.out_flag) {
+                    const double tol = 1e-9;
+                    const bool fin = isfinite(r0) && isfinite(r1) && isfinite(r2);
+                    const bool below = fin && r0 < a.thr_curve - tol && r1 < a.thr_curve - tol && r2 < a.thr_curve - tol;
+                    const bool above = fin && r0 >= a.thr_curve + tol && r1 >= a.thr_curve + tol && r2 >= a.thr_curve + tol;
+                    a.out_flag[cid] = below ? 1 : (above ? 0 : 2);
+                }
             }
         }
     }
@@ -922,7 +951,7 @@ static int knn_impl(const double* d_x, const double* d_y, const double* d_z, int
                     const uint8_t* d_sel, int64_t m, GridParams g, int key_bits,
                     int knn, int max_nn, double radius,
                     int32_t* d_knn, double* d_knn_d2, double* d_normals, double* d_cov, double* d_curv,
-                    void* d_ws, size_t ws_bytes, cudaStream_t st) {
+                    double thr_curve, uint8_t* d_flag, void* d_ws, size_t ws_bytes, cudaStream_t st) {
     Workspace ws(d_ws, ws_bytes);
     uint32_t* counters = ws.take<uint32_t>(64);          // [0] m, [1] n_cells, [4] n_super
     uint32_t* sel_idx = d_sel ? ws.take<uint32_t>((size_t)n) : nullptr;
@@ -931,9 +960,7 @@ static int knn_impl(const double* d_x, const double* d_y, const double* d_z, int
     K* keys_b = ws.take<K>((size_t)m);
     uint32_t* vals_a = ws.take<uint32_t>((size_t)m);
     uint32_t* vals_b = ws.take<uint32_t>((size_t)m);
-    double* sx = ws.take<double>((size_t)m);
-    double* sy = ws.take<double>((size_t)m);
-    double* sz = ws.take<double>((size_t)m);
+    P4* spts = ws.take<P4>((size_t)m);
     uint8_t* flags = ws.take<uint8_t>((size_t)m);
     uint64_t* ucell = ws.take<uint64_t>((size_t)m);
     uint32_t* cell_first = ws.take<uint32_t>((size_t)m + 1);
@@ -970,7 +997,7 @@ static int knn_impl(const double* d_x, const double* d_y, const double* d_z, int
         UPCP_TRY(radix_sort_pairs_u64((uint64_t*)keys_a, vals_a, (uint64_t*)keys_b, vals_b, m, key_bits, prim_ws, st, &in_b));
     K* keys = in_b ? keys_b : keys_a;
     uint32_t* perm = in_b ? vals_b : vals_a;
-    knn_gather_kernel<<<grid_m, kBlock, 0, st>>>(d_x, d_y, d_z, sel_idx, perm, m, sx, sy, sz);
+    knn_gather_kernel<<<grid_m, kBlock, 0, st>>>(d_x, d_y, d_z, sel_idx, perm, m, spts);
     UPCP_LAUNCH_OK();
 
     // fine-cell list
@@ -1028,7 +1055,7 @@ static int knn_impl(const double* d_x, const double* d_y, const double* d_z, int
     prof_begin(UPCP_PROF_KNN, st);
     // dense bulk: warp per group, lane per query, two-pass radial histogram selection
     GroupArgs ga;
-    ga.sx = sx; ga.sy = sy; ga.sz = sz; ga.ucell = ucell; ga.cell_first = cell_first;
+    ga.spts = spts; ga.ucell = ucell; ga.cell_first = cell_first;
     ga.sc_key = sc_key; ga.sc_cell_first = sc_cell_first; ga.table = table; ga.table_mask = cap - 1;
     ga.groups = groups; ga.n_groups = n_groups; ga.g = g; ga.k = kh;
     ga.out_pos = nb_pos; ga.out_cnt = nb_cnt; ga.todo = todo;
@@ -1046,7 +1073,7 @@ static int knn_impl(const double* d_x, const double* d_y, const double* d_z, int
         UPCP_TRY(compact_apply(todo, m, n_todo, prim_ws, st, f));
     }
     SelectArgs a;
-    a.sx = sx; a.sy = sy; a.sz = sz; a.perm = perm; a.ucell = ucell; a.cell_first = cell_first;
+    a.spts = spts; a.ucell = ucell; a.cell_first = cell_first;
     a.sc_key = sc_key; a.sc_cell_first = sc_cell_first; a.table = table; a.table_mask = cap - 1;
     a.g = g; a.m = m; a.k = kh; a.todo_idx = todo_idx; a.todo_cnt = n_todo; a.out_pos = nb_pos; a.out_cnt = nb_cnt;
     knn_select_kernel<<<num_sms() * 16, kSelThreads, 0, st>>>(a);
@@ -1054,9 +1081,10 @@ static int knn_impl(const double* d_x, const double* d_y, const double* d_z, int
     UPCP_LAUNCH_OK();
 
     EpilogueArgs e;
-    e.sx = sx; e.sy = sy; e.sz = sz; e.perm = perm; e.pos = nb_pos; e.cnt = nb_cnt; e.m = m;
+    e.spts = spts; e.pos = nb_pos; e.cnt = nb_cnt; e.m = m;
     e.knn = knn; e.max_nn = max_nn; e.radius2 = radius * radius;
     e.out_knn = d_knn; e.out_d2 = d_knn_d2; e.out_normals = d_normals; e.out_cov = d_cov; e.out_curv = d_curv;
+    e.thr_curve = thr_curve; e.out_flag = d_flag;
     const size_t epi_smem = (size_t)kRow * kEpiThreads * 16;
     UPCP_CUDA_OK(cudaFuncSetAttribute(knn_epilogue_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)epi_smem));
     knn_epilogue_kernel<<<grid_for(m, kEpiThreads, 2), kEpiThreads, epi_smem, st>>>(e);
@@ -1078,7 +1106,7 @@ size_t upcp_knn_ws_bytes(int64_t n, int64_t m, int kmax) {
     bytes += align_up((size_t)n * 4);
     bytes += align_up((compact_ws_words(n) + sort_ws_words(m)) * 4);
     bytes += 2 * align_up((size_t)m * 8) + 2 * align_up((size_t)m * 4);     // keys, vals
-    bytes += 3 * align_up((size_t)m * 8);                                   // sorted coords
+    bytes += align_up((size_t)m * 32);                                      // sorted points (x, y, z, id)
     bytes += align_up((size_t)m);                                           // flags
     bytes += align_up((size_t)m * 8);                                       // ucell
     bytes += align_up(((size_t)m + 1) * 4);                                 // cell_first
@@ -1094,7 +1122,7 @@ int upcp_knn_normals(const double* d_x, const double* d_y, const double* d_z, in
                      const uint8_t* d_sel, int64_t m, const double* h_bbox_sel6,
                      int knn, int max_nn, double radius, double cell_size,
                      int32_t* d_knn, double* d_knn_d2, double* d_normals, double* d_cov, double* d_curv,
-                     void* d_ws, size_t ws_bytes, void* stream) {
+                     double threshold_curve, uint8_t* d_seed_flag, void* d_ws, size_t ws_bytes, void* stream) {
     if (n < 0 || m < 0 || m > n || !h_bbox_sel6) UPCP_FAIL(UPCP_E_INVALID, "knn: bad argument");
     if (knn < 1 || max_nn < 0) UPCP_FAIL(UPCP_E_INVALID, "knn: knn >= 1 and max_nn >= 0 required");
     if (knn > 32 || max_nn > 32) UPCP_FAIL(UPCP_E_CAPACITY, "knn: knn and max_nn are limited to 32");
@@ -1125,9 +1153,9 @@ int upcp_knn_normals(const double* d_x, const double* d_y, const double* d_z, in
     cudaStream_t st = (cudaStream_t)stream;
     if (key_bits <= 32)
         return knn_impl<uint32_t>(d_x, d_y, d_z, n, d_sel, m, g, key_bits, knn, max_nn, radius, d_knn,
-                                  d_knn_d2, d_normals, d_cov, d_curv, d_ws, ws_bytes, st);
+                                  d_knn_d2, d_normals, d_cov, d_curv, threshold_curve, d_seed_flag, d_ws, ws_bytes, st);
     return knn_impl<uint64_t>(d_x, d_y, d_z, n, d_sel, m, g, key_bits, knn, max_nn, radius, d_knn,
-                              d_knn_d2, d_normals, d_cov, d_curv, d_ws, ws_bytes, st);
+                              d_knn_d2, d_normals, d_cov, d_curv, threshold_curve, d_seed_flag, d_ws, ws_bytes, st);
 }
 
 }  // extern "C"

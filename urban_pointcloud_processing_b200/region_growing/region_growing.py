@@ -10,6 +10,7 @@ the least fixpoint (``upcp_region_grow``) -- which is what the Python loop compu
 independently of the order in which seeds are visited."""
 import ctypes
 import logging
+import os
 
 import numpy as np
 import torch
@@ -35,7 +36,7 @@ def default_cell_size(bbox_sel, m, radius):
 
 
 def knn_normals_device(tile, d_sel, m, bbox_sel, knn, max_nn, radius, cell_size=None,
-                       want_d2=False, want_cov=True, want_curv=True):
+                       want_d2=False, want_cov=True, want_curv=True, threshold_curve=None):
     """kNN rows (compact ids), normals, k-neighbourhood covariance and analytic eigenvalue
     ratios for the selected points of ``tile``."""
     lib = _lib.load()
@@ -47,13 +48,18 @@ def knn_normals_device(tile, d_sel, m, bbox_sel, knn, max_nn, radius, cell_size=
     d_normals = torch.empty((m, 3), dtype=torch.float64, device=device)
     d_cov = torch.empty((m, 6), dtype=torch.float64, device=device) if want_cov else None
     d_curv = torch.empty((m, 3), dtype=torch.float64, device=device) if want_curv else None
+    d_flag = torch.empty(m, dtype=torch.uint8, device=device) if threshold_curve is not None else None
     ws = dev.workspace(device).get(lib.upcp_knn_ws_bytes(tile.n, m, max(knn, max_nn)))
     bbox_arr = (ctypes.c_double * 6)(*[float(v) for v in bbox_sel])
     _lib.check(lib.upcp_knn_normals(dev.ptr(tile.x), dev.ptr(tile.y), dev.ptr(tile.z), tile.n,
                                     dev.ptr(d_sel), m, bbox_arr, int(knn), int(max_nn), float(radius),
                                     float(cell_size), dev.ptr(d_knn), dev.ptr(d_d2), dev.ptr(d_normals),
-                                    dev.ptr(d_cov), dev.ptr(d_curv), dev.ptr(ws), ws.numel(),
-                                    dev.stream_ptr()), 'upcp_knn_normals')
+                                    dev.ptr(d_cov), dev.ptr(d_curv),
+                                    float(threshold_curve) if threshold_curve is not None else 0.0,
+                                    dev.ptr(d_flag), dev.ptr(ws), ws.numel(), dev.stream_ptr()),
+               'upcp_knn_normals')
+    if threshold_curve is not None:
+        return d_knn, d_d2, d_normals, d_cov, d_curv, d_flag
     return d_knn, d_d2, d_normals, d_cov, d_curv
 
 
@@ -87,6 +93,38 @@ def can_seed_from_curvature(d_cov, d_curv, threshold_curve):
             res = (curvature < threshold_curve)
         can_seed[idx] = torch.from_numpy(np.ascontiguousarray(res.astype(np.uint8))).to(can_seed.device)
     return can_seed, n_host
+
+
+def _host_curvature(cov6, threshold_curve):
+    cov = np.empty((len(cov6), 3, 3))
+    cov[:, 0, 0] = cov6[:, 0]; cov[:, 0, 1] = cov6[:, 1]; cov[:, 0, 2] = cov6[:, 2]
+    cov[:, 1, 0] = cov6[:, 1]; cov[:, 1, 1] = cov6[:, 3]; cov[:, 1, 2] = cov6[:, 4]
+    cov[:, 2, 0] = cov6[:, 2]; cov[:, 2, 1] = cov6[:, 4]; cov[:, 2, 2] = cov6[:, 5]
+    with np.errstate(all='ignore'):
+        eig_val = np.linalg.eig(cov)[0]
+        return (eig_val[:, 0] / eig_val.sum(axis=1)) < threshold_curve
+
+
+def resolve_seed_flags(d_flag, d_cov, threshold_curve):
+    """Turn the device seed flags (1 / 0 / 2 = undecided) into a 0 / 1 mask: the undecided
+    points are resolved with ``np.linalg.eig`` (LAPACK dgeev, unsorted eigenvalues) exactly as
+    the reference does (region_growing.py:69-73), in parallel over the host cores.  Returns
+    (d_can_seed, number of host-resolved points)."""
+    idx = torch.nonzero(d_flag == 2).flatten()
+    n_host = int(idx.numel())
+    if n_host == 0:
+        return d_flag, 0
+    c = d_cov[idx].cpu().numpy()
+    n_thr = max(1, min(os.cpu_count() or 1, 16, n_host // 256))
+    if n_thr > 1:
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(n_thr) as ex:
+            parts = list(ex.map(lambda a: _host_curvature(a, threshold_curve), np.array_split(c, n_thr)))
+        res = np.concatenate(parts)
+    else:
+        res = _host_curvature(c, threshold_curve)
+    d_flag[idx] = torch.from_numpy(np.ascontiguousarray(res.astype(np.uint8))).to(d_flag.device)
+    return d_flag, n_host
 
 
 def region_grow_device(d_knn, d_normals, d_seed, d_can_seed, threshold_angle):
@@ -162,10 +200,10 @@ class RegionGrowing(AbstractProcessor):
         if n_seeds == 0:
             logger.debug('Input point cloud does not contain any seed points.')
             return d_label_mask
-        d_knn, _, d_normals, d_cov, d_curv = knn_normals_device(
+        d_knn, _, d_normals, d_cov, _, d_flag = knn_normals_device(
             tile, d_sel, m, bbox_sel, self.grow_region_knn, self.max_nn, self.grow_region_radius,
-            cell_size=self.cell_size)
-        d_can_seed, n_host = can_seed_from_curvature(d_cov, d_curv, self.threshold_curve)
+            cell_size=self.cell_size, want_curv=False, threshold_curve=self.threshold_curve)
+        d_can_seed, n_host = resolve_seed_flags(d_flag, d_cov, self.threshold_curve)
         d_region, d_info = region_grow_device(d_knn, d_normals, d_seed, d_can_seed, self.threshold_angle)
         self.last_stats = {'n_selected': m, 'n_seeds': n_seeds, 'n_curvature_on_host': n_host,
                            '_d_info': d_info}
