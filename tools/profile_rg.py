@@ -30,7 +30,7 @@ for rep in range(3):
     d_seed_full = phase('mask_build seed', lambda: dev.mask_build(d_labels, None, base=False, eq=(10,)), acc)
     d_seed = phase('mask_gather', lambda: rg.mask_gather(d_sel, d_seed_full, m), acc)
     ns = phase('mask_count', lambda: dev.mask_count(d_seed), acc)
-    out = phase('knn_normals', lambda: rg.knn_normals_device(t, d_sel, m, bbox_sel, 15, 30, 0.2, want_curv=False, threshold_curve=1.0), acc)
+    out = phase('knn_normals', lambda: rg.knn_normals_device(t, d_sel, m, bbox_sel, 15, 30, 0.2, cell_size=(float(os.environ['CELL']) if 'CELL' in os.environ else None), want_curv=False, threshold_curve=1.0), acc)
     d_knn, _, d_normals, d_cov, _, d_flag = out
     cs = phase('can_seed', lambda: rg.resolve_seed_flags(d_flag, d_cov, 1.0), acc)
     gr = phase('region_grow', lambda: rg.region_grow_device(d_knn, d_normals, d_seed, cs[0], 20), acc)

@@ -865,11 +865,28 @@ knn_epilogue_kernel(EpilogueArgs a) {
         const double qx = qp.x, qy = qp.y, qz = qp.z;
         const uint32_t cid = p4_cid(qp);
         const int n = (int)a.cnt[s];
-        for (int j = 0; j < n; ++j) {
-            const uint32_t p = __ldg(row + j);
-            const P4 cp = load_p4(a.spts + p);
-            const double d2 = dist2(cp.x, cp.y, cp.z, qx, qy, qz);
-            const uint32_t c = p4_cid(cp);
+        // phase 1: fetch the candidate records (independent loads, software-pipelined by 4)
+        for (int j0 = 0; j0 < n; j0 += 4) {
+            uint32_t pp[4]; P4 cp[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) pp[u] = j0 + u < n ? __ldg(row + j0 + u) : 0u;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) cp[u] = load_p4(a.spts + pp[u]);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (j0 + u < n) {
+                    s_d[(j0 + u) * kEpiThreads + tx] = dist2(cp[u].x, cp[u].y, cp[u].z, qx, qy, qz);
+                    s_c[(j0 + u) * kEpiThreads + tx] = p4_cid(cp[u]);
+                    s_p[(j0 + u) * kEpiThreads + tx] = pp[u];
+                }
+            }
+        }
+        // phase 2: insertion sort by (d2, compact id) in shared memory (rows arrive bucket-sorted
+        // from the group kernel / fully sorted from the per-query kernel, so moves are few)
+        for (int j = 1; j < n; ++j) {
+            const double d2 = s_d[j * kEpiThreads + tx];
+            const uint32_t c = s_c[j * kEpiThreads + tx];
+            const uint32_t p = s_p[j * kEpiThreads + tx];
             int i = j;
             while (i > 0) {
                 const double dp = s_d[(i - 1) * kEpiThreads + tx];
@@ -879,31 +896,39 @@ knn_epilogue_kernel(EpilogueArgs a) {
                 s_p[i * kEpiThreads + tx] = s_p[(i - 1) * kEpiThreads + tx];
                 --i;
             }
-            s_d[i * kEpiThreads + tx] = d2; s_c[i * kEpiThreads + tx] = c; s_p[i * kEpiThreads + tx] = p;
+            if (i != j) { s_d[i * kEpiThreads + tx] = d2; s_c[i * kEpiThreads + tx] = c; s_p[i * kEpiThreads + tx] = p; }
         }
         Cumulants nrm_cum; nrm_cum.clear();       // hybrid search: max_nn nearest with d2 < r^2
         Cumulants cov_cum; cov_cum.clear();       // the knn-neighbourhood (region_growing.py:69-71)
         int nn = 0, kk = 0;
         bool in_radius = true;
         const int lim = a.knn > a.max_nn ? a.knn : a.max_nn;
-        for (int j = 0; j < lim; ++j) {
-            const bool present = j < n;
-            double px = 0, py = 0, pz = 0, d2 = inf;
-            uint32_t c = 0;
-            if (present) {
-                const uint32_t p = s_p[j * kEpiThreads + tx];
-                const P4 cp = load_p4(a.spts + p);
-                px = cp.x; py = cp.y; pz = cp.z;
-                d2 = s_d[j * kEpiThreads + tx]; c = s_c[j * kEpiThreads + tx];
+        for (int j0 = 0; j0 < lim; j0 += 4) {
+            P4 cp[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int j = j0 + u;
+                const uint32_t p = j < n ? s_p[j * kEpiThreads + tx] : 0u;
+                cp[u] = load_p4(a.spts + p);
             }
-            if (j < a.knn) {
-                if (a.out_knn) a.out_knn[(size_t)cid * a.knn + j] = present ? (int32_t)c : -1;
-                if (a.out_d2) a.out_d2[(size_t)cid * a.knn + j] = d2;
-                if (present) { cov_cum.add(px, py, pz); ++kk; }
-            }
-            if (j < a.max_nn && present && in_radius) {
-                if (d2 < a.radius2) { nrm_cum.add(px, py, pz); ++nn; }
-                else in_radius = false;            // sorted ascending: nothing closer follows
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int j = j0 + u;
+                if (j >= lim) break;
+                const bool present = j < n;
+                const double px = cp[u].x, py = cp[u].y, pz = cp[u].z;
+                double d2 = inf;
+                uint32_t c = 0;
+                if (present) { d2 = s_d[j * kEpiThreads + tx]; c = s_c[j * kEpiThreads + tx]; }
+                if (j < a.knn) {
+                    if (a.out_knn) a.out_knn[(size_t)cid * a.knn + j] = present ? (int32_t)c : -1;
+                    if (a.out_d2) a.out_d2[(size_t)cid * a.knn + j] = d2;
+                    if (present) { cov_cum.add(px, py, pz); ++kk; }
+                }
+                if (j < a.max_nn && present && in_radius) {
+                    if (d2 < a.radius2) { nrm_cum.add(px, py, pz); ++nn; }
+                    else in_radius = false;            // sorted ascending: nothing closer follows
+                }
             }
         }
         if (a.out_normals) {
