@@ -505,7 +505,11 @@ knn_select_kernel(SelectArgs a) {
 //            function of d2, so every candidate outside buckets <= b*_i is strictly farther than
 //            every candidate inside: the k nearest are among the (few more than k) inside;
 //   pass B   stream the same cells again and append the inside candidates to the query's row.
-// The row is sorted exactly by (d2, compact id) in the epilogue kernel.  Queries the scheme
+// Both passes only FILTER, so they run in fp32 on coordinates relative to the box corner (full-rate
+// pipe, 16-byte staged records); pass B keeps one bucket more than b*_i, a margin thousands of
+// times larger than the fp32 rounding of a squared distance, so the kept set provably contains
+// the k nearest under the exact fp64 ordering.
+// The row is sorted exactly by (fp64 d2, compact id) in the epilogue kernel.  Queries the scheme
 // cannot serve (groups with < k members, rows that would overflow, elongated groups) are flagged
 // and handled by the warp-per-query kernel above.  Both paths are exact.
 struct GroupArgs {
@@ -522,15 +526,13 @@ struct GroupArgs {
 __global__ void __launch_bounds__(kGrpThreads)
 knn_group_kernel(GroupArgs a) {
     __shared__ uint16_t s_hist[kGrpWarps][kBuckets * 32];
-    __shared__ double2 s_cxy[kGrpWarps][32];
-    __shared__ double s_cz[kGrpWarps][32];
-    __shared__ uint32_t s_cpos[kGrpWarps][32];
+    __shared__ float4 s_cf[kGrpWarps][32];          // staged candidate: box-relative x, y, z, sorted position
     __shared__ double s_lb2[kGrpWarps][kCellCap];
     __shared__ uint32_t s_cells[kGrpWarps][kCellCap];
     __shared__ uint32_t s_gseg[kGrpWarps][2][96];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint16_t* const hist = s_hist[warp];
-    double2* const c_xy = s_cxy[warp]; double* const c_z = s_cz[warp]; uint32_t* const c_pos = s_cpos[warp];
+    float4* const c_f = s_cf[warp];
     double* const l_lb2 = s_lb2[warp];
     uint32_t* const l_cell = s_cells[warp];
     uint32_t* const sa_off = s_gseg[warp][0]; uint32_t* const sa_base = sa_off + 64;
@@ -569,13 +571,16 @@ knn_group_kernel(GroupArgs a) {
         double tau_max = tau;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) tau_max = fmax(tau_max, __shfl_xor_sync(kFull, tau_max, o));
-        const double scale = (double)kBuckets / tau;
+        const float scale = (float)((double)kBuckets / tau);
+        const float qfx = (float)(qx - bminx), qfy = (float)(qy - bminy), qfz = (float)(qz - bminz);
         const int sx = cell_coord(qx, g.ox, g.inv_cell, g.nx) >> scl;       // same for all members
         const int sy = cell_coord(qy, g.oy, g.inv_cell, g.ny) >> scl;
         const int sz = cell_coord(qz, g.oz, g.inv_cell, g.nz) >> scl;
         const int gsx = __shfl_sync(kFull, sx, 0), gsy = __shfl_sync(kFull, sy, 0), gsz = __shfl_sync(kFull, sz, 0);
         bool active = is_query;
-        if ((int)ceil((sqrt(tau_max) + g.slack) / scell) > 2 || (int)n_members < K) {
+        // (a degenerate box -- members within a fraction of a millimetre -- leaves no room for the
+        // fp32 margin: hand it over as well)
+        if ((int)ceil((sqrt(tau_max) + g.slack) / scell) > 2 || (int)n_members < K || !(tau_max > 1e-7)) {
             if (is_query) a.todo[pos] = 1;               // not served here: per-query kernel
             continue;
         }
@@ -594,7 +599,8 @@ knn_group_kernel(GroupArgs a) {
                 cum += hist[b * 32 + lane];
                 if (cum >= (uint32_t)K) { b1 = b; break; }
             }
-            if (b1 >= 0) bound = fmin(bound, (double)(b1 + 1) / scale * (1.0 + 1e-9));
+            // pruning bound: upper edge of bucket b1 + 1 (pass B keeps one extra bucket)
+            if (b1 >= 0) bound = fmin(bound, (double)(b1 + 2) / (double)scale * (1.0 + 1e-6));
             bound_max = active ? bound : 0.0;
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) bound_max = fmax(bound_max, __shfl_xor_sync(kFull, bound_max, o));
@@ -625,25 +631,25 @@ knn_group_kernel(GroupArgs a) {
                         const int kk = seg_search(sa_off, i);
                         const uint32_t p = sa_base[kk] + (i - sa_off[kk]);
                         const P4 cp = load_p4(a.spts + p);
-                        c_xy[lane] = make_double2(cp.x, cp.y); c_z[lane] = cp.z; c_pos[lane] = p;
+                        c_f[lane] = make_float4((float)(cp.x - bminx), (float)(cp.y - bminy), (float)(cp.z - bminz),
+                                                __uint_as_float(p));
                     }
                     __syncwarp();
                     const int nc = (int)min(32u, total - b);
                     if (active) {
-#pragma unroll 2
+#pragma unroll 4
                         for (int c = 0; c < nc; ++c) {
-                            const double2 xy = c_xy[c];
-                            const double d2 = dist2(xy.x, xy.y, c_z[c], qx, qy, qz);
-                            if (d2 <= tau) {
-                                int bk = (int)(d2 * scale);
-                                bk = bk > kBuckets - 1 ? kBuckets - 1 : bk;
-                                if (pass == 0) {
-                                    hist[bk * 32 + lane] += 1;
-                                } else if (bk <= bstar) {
-                                    const uint32_t slot = hist[bk * 32 + lane];
-                                    hist[bk * 32 + lane] = (uint16_t)(slot + 1);
-                                    a.out_pos[(size_t)pos * kRow + slot] = c_pos[c];
-                                }
+                            const float4 cf = c_f[c];
+                            const float dx = cf.x - qfx, dy = cf.y - qfy, dz = cf.z - qfz;
+                            const float d2f = dx * dx + dy * dy + dz * dz;
+                            int bk = __float2int_rz(d2f * scale);          // saturating; monotone in d2f
+                            bk = bk > kBuckets - 1 ? kBuckets - 1 : bk;
+                            if (pass == 0) {
+                                hist[bk * 32 + lane] += 1;
+                            } else if (bk <= bstar) {
+                                const uint32_t slot = hist[bk * 32 + lane];
+                                hist[bk * 32 + lane] = (uint16_t)(slot + 1);
+                                a.out_pos[(size_t)pos * kRow + slot] = __float_as_uint(cf.w);
                             }
                         }
                     }
@@ -763,22 +769,25 @@ knn_group_kernel(GroupArgs a) {
                 // exclusive offsets so that pass B places candidates bucket-sorted (counting sort)
                 __syncwarp();
                 uint32_t cum = 0;
-                int bs = -1;
+                int bs = -1;       // last bucket kept = (first bucket whose cumulative count reaches K) + 1
 #pragma unroll 1
                 for (int b = 0; b < kBuckets; ++b) {
                     const uint32_t hb = hist[b * 32 + lane];
                     hist[b * 32 + lane] = (uint16_t)cum;
+                    const bool reached = cum >= (uint32_t)K;      // K reached by the buckets before b
                     cum += hb;
-                    if (cum >= (uint32_t)K) { bs = b; break; }
+                    if (reached) { bs = b; break; }
                 }
-                if (active && (bs < 0 || cum > (uint32_t)kRow)) {     // row would overflow (or bound broken)
+                // bs < 0: K is only reached inside the last (clamp) bucket, or never -- not served here;
+                // bs == kBuckets - 1 would keep the clamp bucket, which also holds far candidates
+                if (active && (bs < 0 || bs >= kBuckets - 1 || cum > (uint32_t)kRow)) {
                     a.todo[pos] = 1;
                     active = false;
                 }
                 bstar = bs;
                 if (active) {
                     a.out_cnt[pos] = (uint8_t)cum;
-                    bound = fmin(bound, (double)(bs + 1) / scale * (1.0 + 1e-9));
+                    bound = fmin(bound, (double)(bs + 1) / (double)scale * (1.0 + 1e-6));
                 }
                 bound_max = active ? bound : 0.0;
 #pragma unroll
