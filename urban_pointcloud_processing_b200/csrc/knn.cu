@@ -508,7 +508,8 @@ knn_select_kernel(SelectArgs a) {
 // Both passes only FILTER, so they run in fp32 on coordinates relative to the box corner (full-rate
 // pipe, 16-byte staged records); pass B keeps one bucket more than b*_i, a margin thousands of
 // times larger than the fp32 rounding of a squared distance, so the kept set provably contains
-// the k nearest under the exact fp64 ordering.
+// the k nearest under the exact fp64 ordering.  (Precisely: pass B keeps a quarter of the next
+// bucket beyond b*_i; the fp32 error of a squared distance is < 1e-3 of a bucket width.)
 // The row is sorted exactly by (fp64 d2, compact id) in the epilogue kernel.  Queries the scheme
 // cannot serve (groups with < k members, rows that would overflow, elongated groups) are flagged
 // and handled by the warp-per-query kernel above.  Both paths are exact.
@@ -585,7 +586,9 @@ knn_group_kernel(GroupArgs a) {
             continue;
         }
 
-        int bstar = -1;            // selected bucket (pass B keeps buckets <= bstar)
+        int bstar = -1;            // last (partially) kept bucket
+        float tkeep = 0.0f;        // pass B keeps candidates with d2f * scale < tkeep
+        bool overflow = false;
         double bound = tau;        // current upper bound of this lane's k-th squared distance
         double bound_max = tau_max;
         int list_n = 0;
@@ -599,8 +602,8 @@ knn_group_kernel(GroupArgs a) {
                 cum += hist[b * 32 + lane];
                 if (cum >= (uint32_t)K) { b1 = b; break; }
             }
-            // pruning bound: upper edge of bucket b1 + 1 (pass B keeps one extra bucket)
-            if (b1 >= 0) bound = fmin(bound, (double)(b1 + 2) / (double)scale * (1.0 + 1e-6));
+            // pruning bound: upper edge of bucket b1 plus the quarter-bucket margin pass B keeps
+            if (b1 >= 0) bound = fmin(bound, ((double)(b1 + 1) + 0.25) / (double)scale * (1.0 + 1e-6));
             bound_max = active ? bound : 0.0;
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) bound_max = fmax(bound_max, __shfl_xor_sync(kFull, bound_max, o));
@@ -642,14 +645,16 @@ knn_group_kernel(GroupArgs a) {
                             const float4 cf = c_f[c];
                             const float dx = cf.x - qfx, dy = cf.y - qfy, dz = cf.z - qfz;
                             const float d2f = dx * dx + dy * dy + dz * dz;
-                            int bk = __float2int_rz(d2f * scale);          // saturating; monotone in d2f
+                            const float tb = d2f * scale;                  // monotone in d2f
+                            int bk = __float2int_rz(tb);                   // saturating
                             bk = bk > kBuckets - 1 ? kBuckets - 1 : bk;
                             if (pass == 0) {
                                 hist[bk * 32 + lane] += 1;
-                            } else if (bk <= bstar) {
+                            } else if (tb < tkeep) {                       // bk <= bstar
                                 const uint32_t slot = hist[bk * 32 + lane];
                                 hist[bk * 32 + lane] = (uint16_t)(slot + 1);
-                                a.out_pos[(size_t)pos * kRow + slot] = __float_as_uint(cf.w);
+                                if (slot < (uint32_t)kRow) a.out_pos[(size_t)pos * kRow + slot] = __float_as_uint(cf.w);
+                                else overflow = true;
                             }
                         }
                     }
@@ -778,23 +783,29 @@ knn_group_kernel(GroupArgs a) {
                     cum += hb;
                     if (reached) { bs = b; break; }
                 }
-                // bs < 0: K is only reached inside the last (clamp) bucket, or never -- not served here;
-                // bs == kBuckets - 1 would keep the clamp bucket, which also holds far candidates
-                if (active && (bs < 0 || bs >= kBuckets - 1 || cum > (uint32_t)kRow)) {
+                // bs = (first bucket whose cumulative count reaches K) + 1; pass B keeps that bucket's
+                // first quarter.  bs < 0: K only reached inside the clamp bucket (or never); bs == last:
+                // the margin would reach into the clamp bucket, which also holds far candidates.
+                if (active && (bs < 0 || bs >= kBuckets - 1)) {
                     a.todo[pos] = 1;
                     active = false;
                 }
                 bstar = bs;
-                if (active) {
-                    a.out_cnt[pos] = (uint8_t)cum;
-                    bound = fmin(bound, (double)(bs + 1) / (double)scale * (1.0 + 1e-6));
-                }
+                tkeep = (float)bs + 0.25f;
+                if (active) bound = fmin(bound, ((double)bs + 0.25) / (double)scale * (1.0 + 1e-6));
                 bound_max = active ? bound : 0.0;
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) bound_max = fmax(bound_max, __shfl_xor_sync(kFull, bound_max, o));
                 if (!__any_sync(kFull, active)) break;
                 __syncwarp();
             }
+        }
+        if (active) {
+            // kept candidates = running counter of the last bucket (its offset started at the count
+            // of all buckets before it)
+            const uint32_t kept = hist[bstar * 32 + lane];
+            if (overflow || kept > (uint32_t)kRow) a.todo[pos] = 1;
+            else a.out_cnt[pos] = (uint8_t)kept;
         }
     }
 }
