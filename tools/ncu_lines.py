@@ -26,7 +26,14 @@ for l in open(sass):
     m = re.match(r'\s+/\*([0-9a-f]{4,})\*/\s+(\S.*?);', l)
     if m:
         line_of[int(m.group(1), 16)] = cur
-rows = list(csv.reader(open(src_csv)))
+allrows = list(csv.reader(open(src_csv)))
+# the page holds one section per profiled kernel ("Kernel Name", <demangled>): keep the one asked for
+short = re.sub(r'^_ZN\d+[a-z]+(\d+)', '', kname)
+starts = [i for i, r in enumerate(allrows) if r and r[0] == 'Kernel Name']
+sel = [i for i in starts if any(part in allrows[i][1] for part in re.findall(r'[a-z_]{6,}', kname))] or starts[:1]
+beg = sel[-1]
+end = min([i for i in starts if i > beg] + [len(allrows)])
+rows = allrows[beg:end]
 hdr = rows[1]
 ia, iinst, ithr, isamp = (hdr.index(h) for h in ('Address', 'Instructions Executed', 'Thread Instructions Executed', '# Samples'))
 base = int(rows[2][ia], 16)

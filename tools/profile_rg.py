@@ -22,7 +22,7 @@ def phase(name, fn, acc):
     torch.cuda.synchronize(); acc.append((name, (time.perf_counter() - t0) * 1e3))
     return out
 
-for rep in range(3):
+for rep in range(int(os.environ.get('REPS', '3'))):
     acc = []
     d_sel = phase('mask_build sel', lambda: dev.mask_build(d_labels, None, base=True, ne=(9, 1)), acc)
     bb = phase('bbox', lambda: t.bbox(d_sel), acc)

@@ -30,6 +30,7 @@
 // Epilogue (knn_epilogue_kernel): one thread per query folds its sorted neighbour list in
 // order into the Open3D cumulant covariances / FastEigen3x3 normal and writes the kNN row.
 #include <math.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include "common.cuh"
 #include "primitives.cuh"
@@ -196,7 +197,7 @@ struct SelectArgs {
     int k;                         // neighbours kept per query (<= 32), clipped to m
     const uint32_t* todo_idx;      // queries (sorted positions) to process, or NULL = all m
     const uint32_t* todo_cnt;      // device count of todo_idx
-    uint32_t* out_pos;             // [m][kRow] sorted positions of the k nearest, ascending
+    uint32_t* out_pos;             // [kRow][m] sorted positions of the k nearest, ascending
     uint8_t* out_cnt;              // [m] number of valid entries of the row
 };
 
@@ -486,7 +487,7 @@ knn_select_kernel(SelectArgs a) {
         }
         // sorted positions of the neighbours, ascending; one coalesced 128-byte row
         const bool have = lane < K && mine.d < inf;
-        a.out_pos[(size_t)q * kRow + lane] = have ? mine.p : kFull;
+        a.out_pos[(size_t)lane * a.m + q] = have ? mine.p : kFull;
         const uint32_t hv = __ballot_sync(kFull, have);
         if (lane == 0) a.out_cnt[q] = (uint8_t)__popc(hv);
     }
@@ -520,6 +521,7 @@ struct GroupArgs {
     const uint32_t* table; uint32_t table_mask;
     const uint4* groups; const uint32_t* n_groups;     // member_start, n_members, chunk_start, chunk_cnt
     GridParams g;
+    int64_t m;
     int k;
     uint32_t* out_pos; uint8_t* out_cnt; uint8_t* todo;
 };
@@ -653,7 +655,7 @@ knn_group_kernel(GroupArgs a) {
                             } else if (tb < tkeep) {                       // bk <= bstar
                                 const uint32_t slot = hist[bk * 32 + lane];
                                 hist[bk * 32 + lane] = (uint16_t)(slot + 1);
-                                if (slot < (uint32_t)kRow) a.out_pos[(size_t)pos * kRow + slot] = __float_as_uint(cf.w);
+                                if (slot < (uint32_t)kRow) a.out_pos[(size_t)slot * a.m + pos] = __float_as_uint(cf.w);
                                 else overflow = true;
                             }
                         }
@@ -858,7 +860,7 @@ __global__ void knn_finish_runs_kernel(const uint32_t* __restrict__ n_runs, uint
 // ------------------------------------------------------------------ epilogue ----
 struct EpilogueArgs {
     const P4* spts;
-    const uint32_t* pos; const uint8_t* cnt;      // pos: [m][kRow]
+    const uint32_t* pos; const uint8_t* cnt;      // pos: [kRow][m] (slot-major: coalesced per query thread)
     int64_t m;
     int knn, max_nn;
     double radius2;
@@ -867,56 +869,87 @@ struct EpilogueArgs {
 };
 
 // One thread per query.  The candidate row (k exact neighbours from the per-query kernel, or
-// the slightly larger unsorted superset from the group kernel) is sorted by (d2, compact id)
-// with an insertion sort in shared memory ([slot][thread] layout: conflict-free), then folded
-// IN ORDER into the cumulant covariances (fp summation order is part of the contract).
-__global__ void __launch_bounds__(kEpiThreads)
+// the slightly larger bucket-ordered superset from the group kernel) is ordered by
+// (fp64 d2, compact id) and folded IN ORDER into the cumulant covariances (fp summation order
+// is part of the contract).
+// Shared memory holds ONE 8-byte key per candidate ([slot][thread] layout, conflict-free):
+// the bit pattern of the non-negative fp64 squared distance -- monotone as an unsigned integer
+// -- with its 6 low mantissa bits replaced by the candidate's slot in the row.  An insertion
+// sort on these integers (rows arrive nearly sorted) orders every pair of candidates whose
+// distances differ above the 58th bit; runs of keys that agree in the upper 58 bits (exact
+// ties, duplicates) are re-ordered by the exact (d2, compact id) comparison afterwards.
+// Everything else (positions, coordinates) is re-read through L1/L2 instead of being parked
+// in shared memory: 384 B instead of 768 B per query, twice the resident warps.
+__device__ __forceinline__ void epi_exact(const EpilogueArgs& a, int64_t s, uint64_t key, double qx, double qy, double qz,
+                                          double& d2, uint32_t& c) {
+    const uint32_t p = __ldg(a.pos + (size_t)(key & 63u) * a.m + s);
+    const P4 cp = load_p4(a.spts + p);
+    d2 = dist2(cp.x, cp.y, cp.z, qx, qy, qz);
+    c = p4_cid(cp);
+}
+
+__global__ void __launch_bounds__(kEpiThreads, 4)
 knn_epilogue_kernel(EpilogueArgs a) {
     extern __shared__ __align__(16) unsigned char epi_smem[];
-    double* const s_d = reinterpret_cast<double*>(epi_smem);                              // [kRow][threads]
-    uint32_t* const s_c = reinterpret_cast<uint32_t*>(epi_smem + (size_t)kRow * kEpiThreads * 8);
-    uint32_t* const s_p = s_c + (size_t)kRow * kEpiThreads;
+    uint64_t* const s_key = reinterpret_cast<uint64_t*>(epi_smem);                       // [kRow][threads]
     const int tx = threadIdx.x;
     const double inf = __longlong_as_double(0x7ff0000000000000LL);
     int64_t stride = (int64_t)gridDim.x * kEpiThreads;
     for (int64_t s = (int64_t)blockIdx.x * kEpiThreads + tx; s < a.m; s += stride) {
-        const uint32_t* row = a.pos + (size_t)s * kRow;
+        const uint32_t* col = a.pos + s;               // slot j of this query: col[j * m]
         const P4 qp = load_p4(a.spts + s);
         const double qx = qp.x, qy = qp.y, qz = qp.z;
         const uint32_t cid = p4_cid(qp);
         const int n = (int)a.cnt[s];
-        // phase 1: fetch the candidate records (independent loads, software-pipelined by 4)
+        // phase 1: candidate records (independent loads, software-pipelined by 4) -> keys
         for (int j0 = 0; j0 < n; j0 += 4) {
             uint32_t pp[4]; P4 cp[4];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) pp[u] = j0 + u < n ? __ldg(row + j0 + u) : 0u;
+            for (int u = 0; u < 4; ++u) pp[u] = j0 + u < n ? __ldg(col + (size_t)(j0 + u) * a.m) : 0u;
 #pragma unroll
             for (int u = 0; u < 4; ++u) cp[u] = load_p4(a.spts + pp[u]);
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 if (j0 + u < n) {
-                    s_d[(j0 + u) * kEpiThreads + tx] = dist2(cp[u].x, cp[u].y, cp[u].z, qx, qy, qz);
-                    s_c[(j0 + u) * kEpiThreads + tx] = p4_cid(cp[u]);
-                    s_p[(j0 + u) * kEpiThreads + tx] = pp[u];
+                    const double d2 = dist2(cp[u].x, cp[u].y, cp[u].z, qx, qy, qz);
+                    s_key[(j0 + u) * kEpiThreads + tx] =
+                        ((uint64_t)__double_as_longlong(d2) & ~(uint64_t)63) | (uint64_t)(j0 + u);
                 }
             }
         }
-        // phase 2: insertion sort by (d2, compact id) in shared memory (rows arrive bucket-sorted
-        // from the group kernel / fully sorted from the per-query kernel, so moves are few)
+        // phase 2: insertion sort of the packed keys
+        bool tie = false;
         for (int j = 1; j < n; ++j) {
-            const double d2 = s_d[j * kEpiThreads + tx];
-            const uint32_t c = s_c[j * kEpiThreads + tx];
-            const uint32_t p = s_p[j * kEpiThreads + tx];
+            const uint64_t kj = s_key[j * kEpiThreads + tx];
             int i = j;
             while (i > 0) {
-                const double dp = s_d[(i - 1) * kEpiThreads + tx];
-                const uint32_t cp = s_c[(i - 1) * kEpiThreads + tx];
-                if (!(d2 < dp || (d2 == dp && c < cp))) break;
-                s_d[i * kEpiThreads + tx] = dp; s_c[i * kEpiThreads + tx] = cp;
-                s_p[i * kEpiThreads + tx] = s_p[(i - 1) * kEpiThreads + tx];
+                const uint64_t kp = s_key[(i - 1) * kEpiThreads + tx];
+                tie |= ((kp ^ kj) >> 6) == 0;
+                if (kp <= kj) break;
+                s_key[i * kEpiThreads + tx] = kp;
                 --i;
             }
-            if (i != j) { s_d[i * kEpiThreads + tx] = d2; s_c[i * kEpiThreads + tx] = c; s_p[i * kEpiThreads + tx] = p; }
+            if (i != j) s_key[i * kEpiThreads + tx] = kj;
+        }
+        if (tie) {
+            // exact order inside runs of keys that agree in their upper 58 bits (rare)
+            for (int j = 1; j < n; ++j) {
+                const uint64_t kj = s_key[j * kEpiThreads + tx];
+                if (((s_key[(j - 1) * kEpiThreads + tx] ^ kj) >> 6) != 0) continue;
+                double dj; uint32_t cj;
+                epi_exact(a, s, kj, qx, qy, qz, dj, cj);
+                int i = j;
+                while (i > 0) {
+                    const uint64_t kp = s_key[(i - 1) * kEpiThreads + tx];
+                    if (((kp ^ kj) >> 6) != 0) break;
+                    double dp; uint32_t cp;
+                    epi_exact(a, s, kp, qx, qy, qz, dp, cp);
+                    if (!(dj < dp || (dj == dp && cj < cp))) break;
+                    s_key[i * kEpiThreads + tx] = kp;
+                    --i;
+                }
+                if (i != j) s_key[i * kEpiThreads + tx] = kj;
+            }
         }
         Cumulants nrm_cum; nrm_cum.clear();       // hybrid search: max_nn nearest with d2 < r^2
         Cumulants cov_cum; cov_cum.clear();       // the knn-neighbourhood (region_growing.py:69-71)
@@ -924,13 +957,14 @@ knn_epilogue_kernel(EpilogueArgs a) {
         bool in_radius = true;
         const int lim = a.knn > a.max_nn ? a.knn : a.max_nn;
         for (int j0 = 0; j0 < lim; j0 += 4) {
-            P4 cp[4];
+            P4 cp[4]; uint32_t pp[4];
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 const int j = j0 + u;
-                const uint32_t p = j < n ? s_p[j * kEpiThreads + tx] : 0u;
-                cp[u] = load_p4(a.spts + p);
+                pp[u] = j < n ? __ldg(col + (size_t)(s_key[j * kEpiThreads + tx] & 63u) * a.m) : 0u;
             }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) cp[u] = load_p4(a.spts + pp[u]);
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 const int j = j0 + u;
@@ -939,7 +973,7 @@ knn_epilogue_kernel(EpilogueArgs a) {
                 const double px = cp[u].x, py = cp[u].y, pz = cp[u].z;
                 double d2 = inf;
                 uint32_t c = 0;
-                if (present) { d2 = s_d[j * kEpiThreads + tx]; c = s_c[j * kEpiThreads + tx]; }
+                if (present) { d2 = dist2(px, py, pz, qx, qy, qz); c = p4_cid(cp[u]); }
                 if (j < a.knn) {
                     if (a.out_knn) a.out_knn[(size_t)cid * a.knn + j] = present ? (int32_t)c : -1;
                     if (a.out_d2) a.out_d2[(size_t)cid * a.knn + j] = d2;
@@ -1102,7 +1136,7 @@ static int knn_impl(const double* d_x, const double* d_y, const double* d_z, int
     GroupArgs ga;
     ga.spts = spts; ga.ucell = ucell; ga.cell_first = cell_first;
     ga.sc_key = sc_key; ga.sc_cell_first = sc_cell_first; ga.table = table; ga.table_mask = cap - 1;
-    ga.groups = groups; ga.n_groups = n_groups; ga.g = g; ga.k = kh;
+    ga.groups = groups; ga.n_groups = n_groups; ga.g = g; ga.m = m; ga.k = kh;
     ga.out_pos = nb_pos; ga.out_cnt = nb_cnt; ga.todo = todo;
     {
         int64_t upper = (int64_t)m / 32 + r_total + 1;            // >= number of groups
@@ -1124,13 +1158,20 @@ static int knn_impl(const double* d_x, const double* d_y, const double* d_z, int
     knn_select_kernel<<<num_sms() * 16, kSelThreads, 0, st>>>(a);
     prof_end(UPCP_PROF_KNN, st, m);
     UPCP_LAUNCH_OK();
+    if (getenv("UPCP_KNN_DEBUG")) {       // development aid: sizes of the search structures
+        uint32_t h[8];
+        cudaMemcpyAsync(h, counters, sizeof(h), cudaMemcpyDeviceToHost, st);
+        cudaStreamSynchronize(st);
+        fprintf(stderr, "[upcp knn] m=%lld cells=%u runs=%u groups=%u super=%u todo=%u cell=%.4f\n", (long long)m, h[1], h[2],
+                h[3], h[4], h[5], g.cell);
+    }
 
     EpilogueArgs e;
     e.spts = spts; e.pos = nb_pos; e.cnt = nb_cnt; e.m = m;
     e.knn = knn; e.max_nn = max_nn; e.radius2 = radius * radius;
     e.out_knn = d_knn; e.out_d2 = d_knn_d2; e.out_normals = d_normals; e.out_cov = d_cov; e.out_curv = d_curv;
     e.thr_curve = thr_curve; e.out_flag = d_flag;
-    const size_t epi_smem = (size_t)kRow * kEpiThreads * 16;
+    const size_t epi_smem = (size_t)kRow * kEpiThreads * 8;
     UPCP_CUDA_OK(cudaFuncSetAttribute(knn_epilogue_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)epi_smem));
     knn_epilogue_kernel<<<grid_for(m, kEpiThreads, 2), kEpiThreads, epi_smem, st>>>(e);
     UPCP_LAUNCH_OK();
