@@ -31,7 +31,8 @@ allrows = list(csv.reader(open(src_csv)))
 short = re.sub(r'^_ZN\d+[a-z]+(\d+)', '', kname)
 starts = [i for i, r in enumerate(allrows) if r and r[0] == 'Kernel Name']
 sel = [i for i in starts if any(part in allrows[i][1] for part in re.findall(r'[a-z_]{6,}', kname))] or starts[:1]
-beg = sel[-1]
+import os
+beg = sel[int(os.environ.get('SECTION', '-1'))]
 end = min([i for i in starts if i > beg] + [len(allrows)])
 rows = allrows[beg:end]
 hdr = rows[1]
