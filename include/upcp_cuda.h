@@ -250,6 +250,27 @@ int upcp_knn_normals(const double* d_x, const double* d_y, const double* d_z, in
                      double threshold_curve, uint8_t* d_seed_flag /* may be NULL */,
                      void* d_ws, size_t ws_bytes, void* stream);
 
+/* The same search with every output in SORTED space: row s belongs to the s-th point of the
+ * library's spatial (grid-cell) order, neighbours in d_knn are sorted positions, and
+ * d_order[s] is the ORIGINAL point index (0..n-1) of sorted position s.  Spatially close points
+ * get close row numbers, so the frontier expansion of upcp_region_grow gathers from cache
+ * instead of HBM, and the epilogue writes its rows contiguously.  Membership results do not
+ * depend on the numbering (the region is a least fixpoint); use upcp_mask_take / upcp_mask_put
+ * to move masks between the two index spaces.
+ * Replaces the same reference calls as upcp_knn_normals (region_growing.py:59-73,86-92,105-109). */
+int upcp_knn_normals_sorted(const double* d_x, const double* d_y, const double* d_z, int64_t n,
+                            const uint8_t* d_sel, int64_t m, const double* h_bbox_sel6,
+                            int knn, int max_nn, double radius, double cell_size,
+                            int32_t* d_knn, double* d_normals, double* d_cov /* may be NULL */,
+                            double threshold_curve, uint8_t* d_seed_flag /* may be NULL */,
+                            uint32_t* d_order, void* d_ws, size_t ws_bytes, void* stream);
+/* d_out[s] = d_full[d_order[s]], s < m          (region_growing.py:80-84: seeds of the masked cloud) */
+int upcp_mask_take(const uint8_t* d_full, const uint32_t* d_order, int64_t m, uint8_t* d_out, void* stream);
+/* d_full[0..n) = 0; d_full[d_order[s]] = 1 where d_sorted[s] != 0
+ * (region_growing.py:139, `label_mask[mask_indices[region]] = True`) */
+int upcp_mask_put(const uint8_t* d_sorted, const uint32_t* d_order, int64_t m, int64_t n, uint8_t* d_full,
+                  void* stream);
+
 /* Region growing to the least fixpoint (region_growing.py:75-141, method='knn').
  *   d_seed[m]     : 1 for initial seeds (points already carrying the label);
  *   d_can_seed[m] : 1 if an accepted point becomes a seed (curvature <
@@ -258,12 +279,33 @@ int upcp_knn_normals(const double* d_x, const double* d_y, const double* d_z, in
  *       degrees(acos(clip(dot(n_s/|n_s|, n_p/|n_p|), -1, 1))) < threshold_angle
  *       (math_utils.py:9-18);
  *   d_region[m]   : output, 1 for every point of the grown region (seeds included).
- *   d_info (int64[2]) : [0] region size, [1] number of seeds processed. */
+ *   d_info (int64[2]) : [0] region size, [1] number of points that went through the work queue
+ *                   (the initial seeds are expanded data-parallel and are not counted).
+ * d_can_seed may hold the value 2 = "undecided": such a point is treated as not (yet) a seed. */
 size_t upcp_region_grow_ws_bytes(int64_t m);
 int upcp_region_grow(const int32_t* d_knn, int knn, const double* d_normals,
                      const uint8_t* d_seed, const uint8_t* d_can_seed, int64_t m,
                      double threshold_angle_deg, uint8_t* d_region, int64_t* d_info,
                      void* d_ws, size_t ws_bytes, void* stream);
+
+/* The same growth in three asynchronous steps, so that the host can decide the seed flags the
+ * device left undecided (upcp_knn_normals: d_seed_flag == 2, the curvature test that depends on
+ * LAPACK's eigenvalue order, region_growing.py:69-73) WHILE the device grows:
+ *   begin   grows from d_seed with the flags as they are (2 = not a seed); returns without
+ *           synchronising; the state lives in the caller's workspace (same buffer for all three);
+ *   resume  after the caller rewrote d_can_seed for the n_extra points listed in d_extra (int64
+ *           indices): continues from those that are in the region, were no seeds and are seeds now.
+ *           Growth is monotone, so the result is the least fixpoint for the final flags;
+ *   end     writes d_region / d_info and synchronises (work-queue error check). */
+int upcp_region_grow_begin(const int32_t* d_knn, int knn, const double* d_normals,
+                           const uint8_t* d_seed, const uint8_t* d_can_seed, int64_t m,
+                           double threshold_angle_deg, void* d_ws, size_t ws_bytes, void* stream);
+int upcp_region_grow_resume(const int32_t* d_knn, int knn, const double* d_normals,
+                            const uint8_t* d_seed, const uint8_t* d_can_seed, int64_t m,
+                            const int64_t* d_extra, int64_t n_extra,
+                            double threshold_angle_deg, void* d_ws, size_t ws_bytes, void* stream);
+int upcp_region_grow_end(int64_t m, uint8_t* d_region, int64_t* d_info, void* d_ws, size_t ws_bytes,
+                         void* stream);
 
 /* Scatter a compact per-selected-point mask back to the full tile:
  * d_out[i] = d_compact[rank(i)] for selected i, 0 otherwise

@@ -363,6 +363,31 @@ def test_knn_normals_cov_match_oracle(cell):
     print(f'normals bit-identical: {np.mean((got_n == want_n).all(axis=1)):.4f}')
 
 
+def test_knn_sorted_space_equals_compact_space():
+    """upcp_knn_normals_sorted: the same rows, numbered by the library's spatial order."""
+    tile, pts, labels = _rg_cloud(120000, 43)
+    sel = labels != 9
+    t = dev.DeviceTile(pts)
+    d_sel = dev.upload_mask(sel, t.n, t.device)
+    _, bbox_sel, m = t.bbox(d_sel)
+    d_knn, _, d_nrm, d_cov, _, d_flag = rgmod.knn_normals_device(t, d_sel, m, bbox_sel, 15, 30, 0.2, threshold_curve=1.0)
+    s_knn, s_nrm, s_cov, s_flag, s_order = rgmod.knn_normals_sorted_device(t, d_sel, m, bbox_sel, 15, 30, 0.2, 1.0)
+    order = s_order.cpu().numpy().astype(np.int64)               # original index of sorted position s
+    ids = np.where(sel)[0]
+    assert np.array_equal(np.sort(order), ids)                   # a permutation of the selected points
+    compact_of_sorted = np.searchsorted(ids, order)              # compact id of sorted position s
+    assert np.array_equal(compact_of_sorted[s_knn.cpu().numpy()], d_knn.cpu().numpy()[compact_of_sorted])
+    assert np.array_equal(s_nrm.cpu().numpy(), d_nrm.cpu().numpy()[compact_of_sorted])
+    assert np.array_equal(s_cov.cpu().numpy(), d_cov.cpu().numpy()[compact_of_sorted])
+    assert np.array_equal(s_flag.cpu().numpy(), d_flag.cpu().numpy()[compact_of_sorted])
+    # mask_take / mask_put round trip
+    full = np.zeros(t.n, dtype=bool); full[ids[::3]] = True
+    d_full = dev.upload_mask(full, t.n, t.device)
+    taken = rgmod.mask_take(d_full, s_order)
+    assert np.array_equal(taken.cpu().numpy().astype(bool), full[order])
+    assert np.array_equal(dev.download_mask(rgmod.mask_put(taken, s_order, t.n)), full)
+
+
 def test_knn_small_and_degenerate_clouds():
     rng = np.random.default_rng(7)
     for pts in (rng.random((7, 3)), np.round(rng.random((3000, 3)) * 2, 1), np.repeat(rng.random((1, 3)), 40, axis=0),

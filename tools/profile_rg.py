@@ -27,14 +27,14 @@ for rep in range(int(os.environ.get('REPS', '3'))):
     d_sel = phase('mask_build sel', lambda: dev.mask_build(d_labels, None, base=True, ne=(9, 1)), acc)
     bb = phase('bbox', lambda: t.bbox(d_sel), acc)
     _, bbox_sel, m = bb
-    d_seed_full = phase('mask_build seed', lambda: dev.mask_build(d_labels, None, base=False, eq=(10,)), acc)
-    d_seed = phase('mask_gather', lambda: rg.mask_gather(d_sel, d_seed_full, m), acc)
-    ns = phase('mask_count', lambda: dev.mask_count(d_seed), acc)
-    out = phase('knn_normals', lambda: rg.knn_normals_device(t, d_sel, m, bbox_sel, 15, 30, 0.2, cell_size=(float(os.environ['CELL']) if 'CELL' in os.environ else None), want_curv=False, threshold_curve=1.0), acc)
-    d_knn, _, d_normals, d_cov, _, d_flag = out
-    cs = phase('can_seed', lambda: rg.resolve_seed_flags(d_flag, d_cov, 1.0), acc)
-    gr = phase('region_grow', lambda: rg.region_grow_device(d_knn, d_normals, d_seed, cs[0], 20), acc)
-    sc = phase('mask_scatter', lambda: rg.mask_scatter(d_sel, gr[0]), acc)
+    d_seed_full = phase('mask_build seed', lambda: dev.mask_build(d_labels, None, base=False, eq=(10,), ne=(9, 1)), acc)
+    ns = phase('mask_count', lambda: dev.mask_count(d_seed_full), acc)
+    out = phase('knn_normals', lambda: rg.knn_normals_sorted_device(t, d_sel, m, bbox_sel, 15, 30, 0.2, 1.0, cell_size=(float(os.environ['CELL']) if 'CELL' in os.environ else None)), acc)
+    d_knn, d_normals, d_cov, d_flag, d_order = out
+    d_seed = phase('mask_take', lambda: rg.mask_take(d_seed_full, d_order), acc)
+    gr = phase('region_grow+can_seed', lambda: rg.region_grow_overlapped(d_knn, d_normals, d_seed, d_flag, d_cov, 1.0, 20), acc)
+    cs = (None, gr[2])
+    sc = phase('mask_put', lambda: rg.mask_put(gr[0], d_order, t.n), acc)
 print(f'm={m} seeds={ns} host-resolved curvature={cs[1]} region={int(gr[1][0])}')
 for name, ms in acc:
     print(f'{name:18s} {ms:8.2f} ms')

@@ -72,9 +72,20 @@ _PROTOTYPES = {
                                  POINTER(c_double), c_int, c_int, c_double, c_double, c_void_p,
                                  c_void_p, c_void_p, c_void_p, c_void_p, c_double, c_void_p, c_void_p,
                                  c_size_t, c_void_p]),
+    'upcp_knn_normals_sorted': (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int64,
+                                        POINTER(c_double), c_int, c_int, c_double, c_double, c_void_p,
+                                        c_void_p, c_void_p, c_double, c_void_p, c_void_p, c_void_p,
+                                        c_size_t, c_void_p]),
+    'upcp_mask_take': (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
+    'upcp_mask_put': (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p]),
     'upcp_region_grow_ws_bytes': (c_size_t, [c_int64]),
     'upcp_region_grow': (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int64, c_double,
                                  c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    'upcp_region_grow_begin': (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int64, c_double,
+                                       c_void_p, c_size_t, c_void_p]),
+    'upcp_region_grow_resume': (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int64, c_void_p,
+                                        c_int64, c_double, c_void_p, c_size_t, c_void_p]),
+    'upcp_region_grow_end': (c_int, [c_int64, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     'upcp_compact_ws_bytes': (c_size_t, [c_int64]),
     'upcp_mask_scatter': (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     'upcp_mask_gather': (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,

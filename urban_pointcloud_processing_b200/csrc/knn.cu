@@ -109,7 +109,7 @@ __global__ void __launch_bounds__(kBlock)
 knn_gather_kernel(const double* __restrict__ x, const double* __restrict__ y,
                   const double* __restrict__ z, const uint32_t* __restrict__ sel_idx,
                   const uint32_t* __restrict__ perm, int64_t m, GridParams g,
-                  P4* __restrict__ spts, float4* __restrict__ spf) {
+                  P4* __restrict__ spts, float4* __restrict__ spf, uint32_t* __restrict__ order) {
     int64_t stride = (int64_t)gridDim.x * kBlock;
     for (int64_t s = (int64_t)blockIdx.x * kBlock + threadIdx.x; s < m; s += stride) {
         uint32_t j = perm[s];
@@ -120,6 +120,7 @@ knn_gather_kernel(const double* __restrict__ x, const double* __restrict__ y,
         o[1] = make_double2(pz, __longlong_as_double((long long)j));
         // origin-relative fp32 copy for the filter passes (error bound: see knn_block_kernel)
         spf[s] = make_float4((float)(px - g.ox), (float)(py - g.oy), (float)(pz - g.oz), 0.0f);
+        if (order) order[s] = (uint32_t)i;          // original point index of sorted position s
     }
 }
 
@@ -588,6 +589,7 @@ struct EpilogueArgs {
     double radius2;
     int32_t* out_knn; double* out_d2; double* out_normals; double* out_cov; double* out_curv;
     double thr_curve; uint8_t* out_flag;
+    int sorted_out;     // 0: outputs indexed by compact id, neighbours as compact ids; 1: both as sorted positions
 };
 
 // One thread per query.  The candidate row (k exact neighbours from the per-query kernel, or
@@ -621,7 +623,7 @@ knn_epilogue_kernel(EpilogueArgs a) {
         const uint32_t* col = a.pos + s;               // slot j of this query: col[j * m]
         const P4 qp = load_p4(a.spts + s);
         const double qx = qp.x, qy = qp.y, qz = qp.z;
-        const uint32_t cid = p4_cid(qp);
+        const uint32_t cid = a.sorted_out ? (uint32_t)s : p4_cid(qp);     // output row of this query
         const int n = (int)a.cnt[s];
         // phase 1: candidate records (independent loads, software-pipelined by 4) -> keys
         for (int j0 = 0; j0 < n; j0 += 4) {
@@ -695,7 +697,7 @@ knn_epilogue_kernel(EpilogueArgs a) {
                 const double px = cp[u].x, py = cp[u].y, pz = cp[u].z;
                 double d2 = inf;
                 uint32_t c = 0;
-                if (present) { d2 = dist2(px, py, pz, qx, qy, qz); c = p4_cid(cp[u]); }
+                if (present) { d2 = dist2(px, py, pz, qx, qy, qz); c = a.sorted_out ? pp[u] : p4_cid(cp[u]); }
                 if (j < a.knn) {
                     if (a.out_knn) a.out_knn[(size_t)cid * a.knn + j] = present ? (int32_t)c : -1;
                     if (a.out_d2) a.out_d2[(size_t)cid * a.knn + j] = d2;
@@ -755,7 +757,7 @@ static int knn_impl(const double* d_x, const double* d_y, const double* d_z, int
                     const uint8_t* d_sel, int64_t m, GridParams g,
                     int knn, int max_nn, double radius,
                     int32_t* d_knn, double* d_knn_d2, double* d_normals, double* d_cov, double* d_curv,
-                    double thr_curve, uint8_t* d_flag, void* d_ws, size_t ws_bytes, cudaStream_t st) {
+                    double thr_curve, uint8_t* d_flag, uint32_t* d_order, void* d_ws, size_t ws_bytes, cudaStream_t st) {
     const uint64_t G = (uint64_t)g.nx * (uint64_t)g.ny * (uint64_t)g.nz;
     Workspace ws(d_ws, ws_bytes);
     uint32_t* counters = ws.take<uint32_t>(64);          // [0] m, [1] tier-2 queries, [2] tier-3 queries
@@ -795,7 +797,7 @@ static int knn_impl(const double* d_x, const double* d_y, const double* d_z, int
     bool in_b = false;
     UPCP_TRY(radix_sort_pairs_u32(keys_a, vals_a, keys_b, vals_b, m, bits_for_u64(G), prim_ws, st, &in_b));
     uint32_t* perm = in_b ? vals_b : vals_a;
-    knn_gather_kernel<<<grid_m, kBlock, 0, st>>>(d_x, d_y, d_z, sel_idx, perm, m, g, spts, spf);
+    knn_gather_kernel<<<grid_m, kBlock, 0, st>>>(d_x, d_y, d_z, sel_idx, perm, m, g, spts, spf, d_order);
     UPCP_LAUNCH_OK();
 
     int kh = knn > max_nn ? knn : max_nn;
@@ -856,7 +858,7 @@ static int knn_impl(const double* d_x, const double* d_y, const double* d_z, int
     e.spts = spts; e.pos = nb_pos; e.cnt = nb_cnt; e.m = m;
     e.knn = knn; e.max_nn = max_nn; e.radius2 = radius * radius;
     e.out_knn = d_knn; e.out_d2 = d_knn_d2; e.out_normals = d_normals; e.out_cov = d_cov; e.out_curv = d_curv;
-    e.thr_curve = thr_curve; e.out_flag = d_flag;
+    e.thr_curve = thr_curve; e.out_flag = d_flag; e.sorted_out = d_order ? 1 : 0;
     const size_t epi_smem = (size_t)kRow * kEpiThreads * 8;
     UPCP_CUDA_OK(cudaFuncSetAttribute(knn_epilogue_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)epi_smem));
     knn_epilogue_kernel<<<grid_for(m, kEpiThreads, 4), kEpiThreads, epi_smem, st>>>(e);
@@ -887,11 +889,12 @@ size_t upcp_knn_ws_bytes(int64_t n, int64_t m, int kmax) {
     return bytes + 4096;
 }
 
-int upcp_knn_normals(const double* d_x, const double* d_y, const double* d_z, int64_t n,
+static int knn_entry(const double* d_x, const double* d_y, const double* d_z, int64_t n,
                      const uint8_t* d_sel, int64_t m, const double* h_bbox_sel6,
                      int knn, int max_nn, double radius, double cell_size,
                      int32_t* d_knn, double* d_knn_d2, double* d_normals, double* d_cov, double* d_curv,
-                     double threshold_curve, uint8_t* d_seed_flag, void* d_ws, size_t ws_bytes, void* stream) {
+                     double threshold_curve, uint8_t* d_seed_flag, uint32_t* d_order,
+                     void* d_ws, size_t ws_bytes, void* stream) {
     if (n < 0 || m < 0 || m > n || !h_bbox_sel6) UPCP_FAIL(UPCP_E_INVALID, "knn: bad argument");
     if (knn < 1 || max_nn < 0) UPCP_FAIL(UPCP_E_INVALID, "knn: knn >= 1 and max_nn >= 0 required");
     if (knn > 32 || max_nn > 32) UPCP_FAIL(UPCP_E_CAPACITY, "knn: knn and max_nn are limited to 32");
@@ -916,7 +919,27 @@ int upcp_knn_normals(const double* d_x, const double* d_y, const double* d_z, in
     g.slack = cell * 1e-6 + amax * 1e-12;
     g.extent = emax > cell ? emax : cell;
     return knn_impl(d_x, d_y, d_z, n, d_sel, m, g, knn, max_nn, radius, d_knn, d_knn_d2, d_normals, d_cov,
-                    d_curv, threshold_curve, d_seed_flag, d_ws, ws_bytes, (cudaStream_t)stream);
+                    d_curv, threshold_curve, d_seed_flag, d_order, d_ws, ws_bytes, (cudaStream_t)stream);
+}
+
+int upcp_knn_normals(const double* d_x, const double* d_y, const double* d_z, int64_t n,
+                     const uint8_t* d_sel, int64_t m, const double* h_bbox_sel6,
+                     int knn, int max_nn, double radius, double cell_size,
+                     int32_t* d_knn, double* d_knn_d2, double* d_normals, double* d_cov, double* d_curv,
+                     double threshold_curve, uint8_t* d_seed_flag, void* d_ws, size_t ws_bytes, void* stream) {
+    return knn_entry(d_x, d_y, d_z, n, d_sel, m, h_bbox_sel6, knn, max_nn, radius, cell_size, d_knn, d_knn_d2,
+                     d_normals, d_cov, d_curv, threshold_curve, d_seed_flag, nullptr, d_ws, ws_bytes, stream);
+}
+
+int upcp_knn_normals_sorted(const double* d_x, const double* d_y, const double* d_z, int64_t n,
+                            const uint8_t* d_sel, int64_t m, const double* h_bbox_sel6,
+                            int knn, int max_nn, double radius, double cell_size,
+                            int32_t* d_knn, double* d_normals, double* d_cov,
+                            double threshold_curve, uint8_t* d_seed_flag, uint32_t* d_order,
+                            void* d_ws, size_t ws_bytes, void* stream) {
+    if (!d_order) UPCP_FAIL(UPCP_E_INVALID, "knn: d_order is required");
+    return knn_entry(d_x, d_y, d_z, n, d_sel, m, h_bbox_sel6, knn, max_nn, radius, cell_size, d_knn, nullptr,
+                     d_normals, d_cov, nullptr, threshold_curve, d_seed_flag, d_order, d_ws, ws_bytes, stream);
 }
 
 }  // extern "C"

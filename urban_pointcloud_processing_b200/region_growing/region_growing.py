@@ -63,6 +63,49 @@ def knn_normals_device(tile, d_sel, m, bbox_sel, knn, max_nn, radius, cell_size=
     return d_knn, d_d2, d_normals, d_cov, d_curv
 
 
+def knn_normals_sorted_device(tile, d_sel, m, bbox_sel, knn, max_nn, radius, threshold_curve, cell_size=None):
+    """The same search with all outputs in the library's spatial order (``upcp_knn_normals_sorted``):
+    returns (d_knn, d_normals, d_cov, d_flag, d_order) where row s / neighbour ids are sorted
+    positions and ``d_order[s]`` is the original point index of sorted position s."""
+    lib = _lib.load()
+    device = tile.device
+    if cell_size is None:
+        cell_size = default_cell_size(bbox_sel, m, radius)
+    d_knn = torch.empty((m, knn), dtype=torch.int32, device=device)
+    d_normals = torch.empty((m, 3), dtype=torch.float64, device=device)
+    d_cov = torch.empty((m, 6), dtype=torch.float64, device=device)
+    d_flag = torch.empty(m, dtype=torch.uint8, device=device)
+    d_order = torch.empty(m, dtype=torch.int32, device=device)
+    ws = dev.workspace(device).get(lib.upcp_knn_ws_bytes(tile.n, m, max(knn, max_nn)))
+    bbox_arr = (ctypes.c_double * 6)(*[float(v) for v in bbox_sel])
+    _lib.check(lib.upcp_knn_normals_sorted(dev.ptr(tile.x), dev.ptr(tile.y), dev.ptr(tile.z), tile.n,
+                                           dev.ptr(d_sel), m, bbox_arr, int(knn), int(max_nn), float(radius),
+                                           float(cell_size), dev.ptr(d_knn), dev.ptr(d_normals), dev.ptr(d_cov),
+                                           float(threshold_curve), dev.ptr(d_flag), dev.ptr(d_order),
+                                           dev.ptr(ws), ws.numel(), dev.stream_ptr()),
+               'upcp_knn_normals_sorted')
+    return d_knn, d_normals, d_cov, d_flag, d_order
+
+
+def mask_take(d_full, d_order):
+    """out[s] = full[order[s]] (full-tile mask -> sorted space)."""
+    lib = _lib.load()
+    m = d_order.numel()
+    out = torch.empty(m, dtype=torch.uint8, device=d_full.device)
+    _lib.check(lib.upcp_mask_take(dev.ptr(d_full), dev.ptr(d_order), m, dev.ptr(out), dev.stream_ptr()),
+               'upcp_mask_take')
+    return out
+
+
+def mask_put(d_sorted, d_order, n):
+    """full[order[s]] = 1 where sorted[s] (sorted space -> full-tile mask, zero elsewhere)."""
+    lib = _lib.load()
+    out = torch.empty(n, dtype=torch.uint8, device=d_order.device)
+    _lib.check(lib.upcp_mask_put(dev.ptr(d_sorted), dev.ptr(d_order), d_order.numel(), n, dev.ptr(out),
+                                 dev.stream_ptr()), 'upcp_mask_put')
+    return out
+
+
 def can_seed_from_curvature(d_cov, d_curv, threshold_curve):
     """uint8 cuda tensor [m]: ``eig_val[0] / eig_val.sum() < threshold_curve``
     (region_growing.py:59-73,132).
@@ -141,6 +184,71 @@ def region_grow_device(d_knn, d_normals, d_seed, d_can_seed, threshold_angle):
     return d_region, d_info
 
 
+_SIDE_STREAMS = {}
+_POOL = None
+
+
+def _side_stream(device):
+    key = str(device)
+    if key not in _SIDE_STREAMS:
+        _SIDE_STREAMS[key] = torch.cuda.Stream(device=device)
+    return _SIDE_STREAMS[key]
+
+
+def _pool():
+    global _POOL
+    if _POOL is None:
+        from concurrent.futures import ThreadPoolExecutor
+        _POOL = ThreadPoolExecutor(max(1, min(os.cpu_count() or 1, 16)))
+    return _POOL
+
+
+def region_grow_overlapped(d_knn, d_normals, d_seed, d_flag, d_cov, threshold_curve, threshold_angle):
+    """Growth to the least fixpoint with the undecided curvature flags (value 2) resolved on the
+    host WHILE the device grows (``upcp_region_grow_begin / _resume / _end``).
+
+    The device starts from the flags it could decide itself.  On a side stream the undecided
+    covariances are fetched and put through ``np.linalg.eig`` exactly as the reference does
+    (region_growing.py:69-73); the flags are then rewritten and the growth resumed from the points
+    that turned out to be seeds.  Growth is monotone, so the result equals the one-shot fixpoint.
+    Returns (d_region, d_info, n_host)."""
+    lib = _lib.load()
+    m, knn = d_knn.shape
+    device = d_knn.device
+    main = torch.cuda.current_stream(device)
+    flags_ready = torch.cuda.Event()
+    flags_ready.record(main)
+    d_region = torch.empty(m, dtype=torch.uint8, device=device)
+    d_info = torch.zeros(2, dtype=torch.int64, device=device)
+    ws = dev.workspace(device, slot=2).get(lib.upcp_region_grow_ws_bytes(m))
+    _lib.check(lib.upcp_region_grow_begin(dev.ptr(d_knn), int(knn), dev.ptr(d_normals), dev.ptr(d_seed),
+                                          dev.ptr(d_flag), m, float(threshold_angle), dev.ptr(ws), ws.numel(),
+                                          dev.stream_ptr()), 'upcp_region_grow_begin')
+    # ---- host resolution of the undecided flags, overlapped with the kernels queued above
+    side = _side_stream(device)
+    with torch.cuda.stream(side):
+        side.wait_event(flags_ready)
+        idx = torch.nonzero(d_flag == 2).flatten()
+        n_host = int(idx.numel())                       # waits for the side stream only
+        c = d_cov[idx].cpu().numpy() if n_host else None
+    if n_host:
+        n_thr = max(1, min(os.cpu_count() or 1, 16, n_host // 256))
+        if n_thr > 1:
+            parts = list(_pool().map(lambda a: _host_curvature(a, threshold_curve), np.array_split(c, n_thr)))
+            res = np.concatenate(parts)
+        else:
+            res = _host_curvature(c, threshold_curve)
+        main.wait_stream(side)
+        d_flag[idx] = torch.from_numpy(np.ascontiguousarray(res.astype(np.uint8))).to(device)
+        _lib.check(lib.upcp_region_grow_resume(dev.ptr(d_knn), int(knn), dev.ptr(d_normals), dev.ptr(d_seed),
+                                               dev.ptr(d_flag), m, dev.ptr(idx), n_host, float(threshold_angle),
+                                               dev.ptr(ws), ws.numel(), dev.stream_ptr()),
+                   'upcp_region_grow_resume')
+    _lib.check(lib.upcp_region_grow_end(m, dev.ptr(d_region), dev.ptr(d_info), dev.ptr(ws), ws.numel(),
+                                        dev.stream_ptr()), 'upcp_region_grow_end')
+    return d_region, d_info, n_host
+
+
 def mask_gather(d_sel, d_full, m):
     lib = _lib.load()
     n = d_sel.numel()
@@ -194,17 +302,19 @@ class RegionGrowing(AbstractProcessor):
         d_label_mask = torch.zeros(tile.n, dtype=torch.uint8, device=tile.device)
         if m == 0:
             return d_label_mask
-        d_seed_full = dev.mask_build(d_labels, None, base=False, eq=(self.label,))
-        d_seed = mask_gather(d_sel, d_seed_full, m)
-        n_seeds = dev.mask_count(d_seed)
+        # seeds: selected points already carrying the label (region_growing.py:80-84)
+        d_seed_full = dev.mask_build(d_labels, None, base=False, eq=(self.label,), ne=tuple(self.exclude_labels))
+        n_seeds = dev.mask_count(d_seed_full)
         if n_seeds == 0:
             logger.debug('Input point cloud does not contain any seed points.')
             return d_label_mask
-        d_knn, _, d_normals, d_cov, _, d_flag = knn_normals_device(
+        # everything below lives in the search grid's spatial order (close points, close rows)
+        d_knn, d_normals, d_cov, d_flag, d_order = knn_normals_sorted_device(
             tile, d_sel, m, bbox_sel, self.grow_region_knn, self.max_nn, self.grow_region_radius,
-            cell_size=self.cell_size, want_curv=False, threshold_curve=self.threshold_curve)
-        d_can_seed, n_host = resolve_seed_flags(d_flag, d_cov, self.threshold_curve)
-        d_region, d_info = region_grow_device(d_knn, d_normals, d_seed, d_can_seed, self.threshold_angle)
+            self.threshold_curve, cell_size=self.cell_size)
+        d_seed = mask_take(d_seed_full, d_order)
+        d_region, d_info, n_host = region_grow_overlapped(d_knn, d_normals, d_seed, d_flag, d_cov,
+                                                          self.threshold_curve, self.threshold_angle)
         self.last_stats = {'n_selected': m, 'n_seeds': n_seeds, 'n_curvature_on_host': n_host,
                            '_d_info': d_info}
-        return mask_scatter(d_sel, d_region)
+        return mask_put(d_region, d_order, tile.n)
