@@ -22,6 +22,12 @@
 namespace upcp {
 
 constexpr int kBlock = 256;
+constexpr int kRowTableMaxLevel = 12;    // dense (y, z) row table of the link step: 4^level entries
+static inline size_t row_table_rows(int level, int64_t m) {
+    if (level > kRowTableMaxLevel) return 0;
+    const size_t rows = (size_t)1 << (2 * level);
+    return rows <= 8 * (size_t)m + 65536 ? rows : 0;        // not worth zeroing for a handful of cells
+}
 
 struct OctreeParams {
     float min_x, min_y, min_z, cs;
@@ -93,6 +99,17 @@ cc_init_parent_kernel(const uint32_t* __restrict__ n_cells, uint32_t* __restrict
     }
 }
 
+// number of occupied cells per grid row (y, z); its exclusive prefix is the row table
+template <typename K>
+__global__ void __launch_bounds__(kBlock)
+cc_row_count_kernel(const K* __restrict__ ucell, const uint32_t* __restrict__ n_cells, int level,
+                    uint32_t* __restrict__ row_count) {
+    const uint32_t c_total = *n_cells;
+    uint32_t stride = gridDim.x * kBlock;
+    for (uint32_t c = blockIdx.x * kBlock + threadIdx.x; c < c_total; c += stride)
+        atomicAdd(row_count + (uint32_t)(ucell[c] >> level), 1u);
+}
+
 __device__ __forceinline__ uint32_t uf_find(uint32_t* parent, uint32_t a) {
     // path halving; racing writers only ever shorten paths towards smaller indices
     // L2 (.cg) loads: other SMs hook roots concurrently, never trust a stale L1 line
@@ -133,7 +150,7 @@ __device__ __forceinline__ uint32_t lower_bound_key(const K* __restrict__ ucell,
 template <typename K>
 __global__ void __launch_bounds__(kBlock)
 cc_link_kernel(const K* __restrict__ ucell, const uint32_t* __restrict__ n_cells, int level,
-               uint32_t* __restrict__ parent) {
+               const uint32_t* __restrict__ row_first, uint32_t* __restrict__ parent) {
     const uint32_t c_total = *n_cells;
     const int dim = 1 << level;
     const K axis_mask = ((K)1 << level) - 1;
@@ -156,8 +173,15 @@ cc_link_kernel(const K* __restrict__ ucell, const uint32_t* __restrict__ n_cells
             const int x1 = cx + 1 < dim ? cx + 1 : dim - 1;
             const K k0 = pack_key<K>(x0, ny, nz, level);
             const K k1 = pack_key<K>(x1, ny, nz, level);
-            uint32_t idx = lower_bound_key<K>(ucell, c + 1, c_total, k0);
-            for (int t = 0; t < 3 && idx < c_total; ++t, ++idx) {
+            // the cells of grid row (ny, nz) are one contiguous run of the sorted list: with the row
+            // table (levels <= 12) the search is confined to that run, else to everything after c
+            uint32_t lo = c + 1, hi = c_total;
+            if (row_first) {
+                const uint32_t rowid = (uint32_t)nz * (uint32_t)dim + (uint32_t)ny;
+                lo = __ldg(row_first + rowid); hi = __ldg(row_first + rowid + 1);
+            }
+            uint32_t idx = lower_bound_key<K>(ucell, lo, hi, k0);
+            for (int t = 0; t < 3 && idx < hi; ++t, ++idx) {
                 if (ucell[idx] > k1) break;
                 uf_union(parent, c, idx);
             }
@@ -275,7 +299,7 @@ static int lcc_impl(const double* d_x, const double* d_y, const double* d_z, int
     Workspace ws(d_ws, ws_bytes);
     uint32_t* counters = ws.take<uint32_t>(64);           // [0] m, [1] n_cells
     uint32_t* sel_idx = d_sel ? ws.take<uint32_t>((size_t)n) : nullptr;
-    uint32_t* prim_ws = ws.take<uint32_t>(compact_ws_words(n) + sort_ws_words(n));
+    uint32_t* prim_ws = ws.take<uint32_t>(compact_ws_words(n) + sort_ws_words(n) + scan_ws_words(((int64_t)1 << (2 * kRowTableMaxLevel)) + 1));
     if (!ws.ok) UPCP_FAIL(UPCP_E_WORKSPACE, "lcc: workspace too small");
 
     UPCP_CUDA_OK(cudaMemsetAsync(d_info, 0, 4 * sizeof(int64_t), st));
@@ -309,6 +333,8 @@ static int lcc_impl(const double* d_x, const double* d_y, const double* d_z, int
     uint32_t* parent = ws.take<uint32_t>((size_t)m);
     int32_t* comp_size = ws.take<int32_t>((size_t)m);
     int32_t* seed_cnt = ws.take<int32_t>((size_t)m);
+    const size_t n_rows = row_table_rows(op.level, m);
+    uint32_t* row_first = n_rows ? ws.take<uint32_t>(n_rows + 1) : nullptr;
     if (!ws.ok) UPCP_FAIL(UPCP_E_WORKSPACE, "lcc: workspace too small");
 
     // 2. voxel keys + radix sort
@@ -339,7 +365,13 @@ static int lcc_impl(const double* d_x, const double* d_y, const double* d_z, int
     cc_init_parent_kernel<<<grid_m, kBlock, 0, st>>>(n_cells, parent, comp_size, seed_cnt);
     UPCP_LAUNCH_OK();
     prof_begin(UPCP_PROF_LINK, st);
-    cc_link_kernel<K><<<grid_m, kBlock, 0, st>>>(ucell, n_cells, op.level, parent);
+    if (row_first) {
+        UPCP_CUDA_OK(cudaMemsetAsync(row_first, 0, (n_rows + 1) * 4, st));
+        cc_row_count_kernel<K><<<grid_m, kBlock, 0, st>>>(ucell, n_cells, op.level, row_first);
+        UPCP_LAUNCH_OK();
+        UPCP_TRY(exclusive_scan_u32(row_first, row_first, (int64_t)n_rows + 1, nullptr, prim_ws, st));
+    }
+    cc_link_kernel<K><<<grid_m, kBlock, 0, st>>>(ucell, n_cells, op.level, row_first, parent);
     prof_end(UPCP_PROF_LINK, st, m);
     UPCP_LAUNCH_OK();
     cc_compress_kernel<<<grid_m, kBlock, 0, st>>>(n_cells, parent, cell_first, comp_size,
@@ -412,13 +444,14 @@ size_t upcp_lcc_ws_bytes(int64_t n, int64_t n_selected_upper, int level) {
     size_t bytes = 0;
     bytes += align_up(64 * 4);
     bytes += align_up((size_t)n * 4);                                        // sel_idx
-    bytes += align_up((compact_ws_words(n) + sort_ws_words(n)) * 4);          // primitives
+    bytes += align_up((compact_ws_words(n) + sort_ws_words(n) + scan_ws_words(((int64_t)1 << (2 * kRowTableMaxLevel)) + 1)) * 4);   // primitives
     bytes += 2 * align_up((size_t)m * key_bytes);                             // keys a/b
     bytes += 2 * align_up((size_t)m * 4);                                     // vals a/b
     bytes += align_up((size_t)m);                                             // flags
     bytes += align_up((size_t)m * 4);                                         // cell_of
     bytes += align_up(((size_t)m + 1) * 4);                                   // cell_first
     bytes += 3 * align_up((size_t)m * 4);                                     // parent, sizes, seeds
+    bytes += align_up((row_table_rows(level, m) + 1) * 4);                      // row table of the link step
     return bytes + 4096;
 }
 

@@ -162,12 +162,17 @@ grow_kernel(const int32_t* __restrict__ knn, int k, const double* __restrict__ n
                 for (int jj = j; jj < k; jj += (per_step == 2 ? 16 : 32)) {
                     // (k <= 32: at most one trip)
                     if (src >= 0 && jj >= 1) {
+                        // the expansion is a chain of dependent round trips to L2 and the frontier is
+                        // narrow: issue every load that only needs the indices at once (the seed's
+                        // normal with the row, the neighbour's state / normal / flag together)
+                        const Vec3 ns = {normals[(size_t)s * 3], normals[(size_t)s * 3 + 1], normals[(size_t)s * 3 + 2]};
                         nb = knn[(size_t)s * k + jj];
-                        if (nb >= 0 && __ldcg(state + nb) == 0) {
-                            const Vec3 ns = {normals[(size_t)s * 3], normals[(size_t)s * 3 + 1], normals[(size_t)s * 3 + 2]};
+                        if (nb >= 0) {
+                            const int32_t st = __ldcg(state + nb);
                             const Vec3 nn = {normals[(size_t)nb * 3], normals[(size_t)nb * 3 + 1], normals[(size_t)nb * 3 + 2]};
-                            if (vector_angle_deg(ns, nn) < threshold_deg) {
-                                if (atomicExch(&state[nb], 1) == 0) push = can_seed[nb] == 1;
+                            const uint8_t cs = can_seed[nb];
+                            if (st == 0 && vector_angle_deg(ns, nn) < threshold_deg) {
+                                if (atomicExch(&state[nb], 1) == 0) push = cs == 1;
                             }
                         }
                     }
