@@ -69,7 +69,9 @@ __device__ __forceinline__ P4 load_p4(const P4* __restrict__ p) {
     P4 r; r.x = a.x; r.y = a.y; r.z = b.x; r.w = b.y;
     return r;
 }
+// w packs the compact id (low 32 bits) and the point's position in the fine-grid order (high 32 bits)
 __device__ __forceinline__ uint32_t p4_cid(const P4& v) { return (uint32_t)__double_as_longlong(v.w); }
+__device__ __forceinline__ uint32_t p4_pos(const P4& v) { return (uint32_t)((unsigned long long)__double_as_longlong(v.w) >> 32); }
 
 __device__ __forceinline__ int cell_coord(double v, double origin, double inv_cell, int n) {
     double t = (v - origin) * inv_cell;
@@ -117,10 +119,37 @@ knn_gather_kernel(const double* __restrict__ x, const double* __restrict__ y,
         const double px = x[i], py = y[i], pz = z[i];
         double2* o = reinterpret_cast<double2*>(spts + s);
         o[0] = make_double2(px, py);
-        o[1] = make_double2(pz, __longlong_as_double((long long)j));
+        o[1] = make_double2(pz, __longlong_as_double((long long)(((unsigned long long)s << 32) | (unsigned long long)j)));
         // origin-relative fp32 copy for the filter passes (error bound: see knn_block_kernel)
         spf[s] = make_float4((float)(px - g.ox), (float)(py - g.oy), (float)(pz - g.oz), 0.0f);
         if (order) order[s] = (uint32_t)i;          // original point index of sorted position s
+    }
+}
+
+// Second, coarser grid for the per-query tier: keys from the fine-sorted records, ...
+__global__ void __launch_bounds__(kBlock)
+knn_keys2_kernel(const P4* __restrict__ spts, int64_t m, GridParams g, uint32_t* __restrict__ keys,
+                 uint32_t* __restrict__ vals, uint32_t* __restrict__ cell_count) {
+    int64_t stride = (int64_t)gridDim.x * kBlock;
+    for (int64_t s = (int64_t)blockIdx.x * kBlock + threadIdx.x; s < m; s += stride) {
+        const P4 p = load_p4(spts + s);
+        int cx = cell_coord(p.x, g.ox, g.inv_cell, g.nx);
+        int cy = cell_coord(p.y, g.oy, g.inv_cell, g.ny);
+        int cz = cell_coord(p.z, g.oz, g.inv_cell, g.nz);
+        const uint32_t key = ((uint32_t)cz * (uint32_t)g.ny + (uint32_t)cy) * (uint32_t)g.nx + (uint32_t)cx;
+        keys[s] = key;
+        vals[s] = (uint32_t)s;
+        atomicAdd(cell_count + key, 1u);
+    }
+}
+// ... and the records re-ordered by coarse cell (they keep their fine-grid position in w)
+__global__ void __launch_bounds__(kBlock)
+knn_gather2_kernel(const P4* __restrict__ spts, const uint32_t* __restrict__ perm, int64_t m, P4* __restrict__ spts2) {
+    int64_t stride = (int64_t)gridDim.x * kBlock;
+    for (int64_t t = (int64_t)blockIdx.x * kBlock + threadIdx.x; t < m; t += stride) {
+        const double2* src = reinterpret_cast<const double2*>(spts + perm[t]);
+        double2* dst = reinterpret_cast<double2*>(spts2 + t);
+        dst[0] = __ldg(src); dst[1] = __ldg(src + 1);
     }
 }
 
@@ -324,7 +353,8 @@ knn_block_kernel(BlockArgs a) {
 
 // ------------------------------------------------------------------ tier 3 ------
 struct SelectArgs {
-    const P4* spts;                // sorted points (x, y, z, compact id)
+    const P4* qpts;                // query records, fine-grid order
+    const P4* spts;                // candidate records in the order of THIS grid (fine or coarse)
     const uint32_t* cell_first;
     GridParams g;
     int64_t m;
@@ -408,7 +438,7 @@ knn_select_kernel(SelectArgs a) {
     const int64_t n_todo = a.todo_idx ? (int64_t)*a.todo_cnt : a.m;
     for (int64_t qi = (int64_t)blockIdx.x * kSelWarps + warp; qi < n_todo; qi += (int64_t)gridDim.x * kSelWarps) {
         const int64_t q = a.todo_idx ? (int64_t)a.todo_idx[qi] : qi;
-        const P4 qp = load_p4(a.spts + q);
+        const P4 qp = load_p4(a.qpts + q);
         const double qx = qp.x, qy = qp.y, qz = qp.z;
         const int cx = cell_coord(qx, g.ox, g.inv_cell, g.nx);
         const int cy = cell_coord(qy, g.oy, g.inv_cell, g.ny);
@@ -438,7 +468,7 @@ knn_select_kernel(SelectArgs a) {
                     const P4 cp = load_p4(a.spts + p);
                     cand.d = dist2(cp.x, cp.y, cp.z, qx, qy, qz);
                     cand.c = p4_cid(cp);
-                    cand.p = p;
+                    cand.p = p4_pos(cp);           // position in the fine-grid order (what the rows hold)
                 }
                 bool pass = nb_less(cand.d, cand.c, kth_d, kth_c);
                 uint32_t hits = __ballot_sync(kFull, pass);
@@ -473,6 +503,11 @@ knn_select_kernel(SelectArgs a) {
             __syncwarp();
         };
 
+        // points of the cells lo..hi (flat cell numbers of one grid row)
+        auto range = [&](uint32_t lo, uint32_t hi, uint32_t& first, uint32_t& cnt) {
+            first = __ldg(a.cell_first + lo);
+            cnt = __ldg(a.cell_first + hi + 1) - first;
+        };
         // squared gap between the query and the slab of cell index c along one axis (conservative)
         auto axis_gap = [&](double qv, double origin, int c, int cq) -> double {
             if (c == cq) return 0.0;
@@ -514,18 +549,11 @@ knn_select_kernel(SelectArgs a) {
                             const int xa = max(cx - hw, 0), xb = min(cx + hw, g.nx - 1);
                             const bool inner = dy >= -Rdone && dy <= Rdone && dz >= -Rdone && dz <= Rdone;
                             if (!inner) {
-                                f1 = __ldg(a.cell_first + row + xa);
-                                n1 = __ldg(a.cell_first + row + xb + 1) - f1;
+                                range(row + xa, row + xb, f1, n1);
                             } else {
                                 const int xl = cx - Rdone - 1, xr = cx + Rdone + 1;
-                                if (xa <= xl) {
-                                    f1 = __ldg(a.cell_first + row + xa);
-                                    n1 = __ldg(a.cell_first + row + xl + 1) - f1;
-                                }
-                                if (xr <= xb) {
-                                    f2 = __ldg(a.cell_first + row + xr);
-                                    n2 = __ldg(a.cell_first + row + xb + 1) - f2;
-                                }
+                                if (xa <= xl) range(row + xa, row + xl, f1, n1);
+                                if (xr <= xb) range(row + xr, row + xb, f2, n2);
                             }
                         }
                     }
@@ -770,6 +798,8 @@ static int knn_impl(const double* d_x, const double* d_y, const double* d_z, int
     P4* spts = ws.take<P4>((size_t)m);
     float4* spf = ws.take<float4>((size_t)m);
     uint32_t* cell_first = ws.take<uint32_t>((size_t)grid_cell_cap(m) + 1);
+    P4* spts2 = ws.take<P4>((size_t)m);                                   // coarse grid of the per-query tier
+    uint32_t* cell_first2 = ws.take<uint32_t>((size_t)grid_cell_cap(m) / 4 + 2);
     uint32_t* nb_pos = ws.take<uint32_t>((size_t)m * kRow);
     uint8_t* nb_cnt = ws.take<uint8_t>((size_t)m);
     uint8_t* todo[2] = {ws.take<uint8_t>((size_t)m), ws.take<uint8_t>((size_t)m)};
@@ -840,18 +870,47 @@ static int knn_impl(const double* d_x, const double* d_y, const double* d_z, int
         TodoFunctor f{todo_last_idx};
         UPCP_TRY(compact_apply(todo[(kTiers - 1) & 1], m, n_todo_last, prim_ws, st, f));
     }
+    // The per-query tier walks grid rows; where it has much to do (sparse clutter, noise) it gets a
+    // second grid with `coarse` times larger cells -- coarse^2 times fewer rows per shell -- built
+    // from the fine-sorted records (3 more radix passes, one gather).
+    uint32_t h_last = 0;
+    UPCP_CUDA_OK(cudaMemcpyAsync(&h_last, n_todo_last, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    UPCP_CUDA_OK(cudaStreamSynchronize(st));
     SelectArgs a;
-    a.spts = spts; a.cell_first = cell_first; a.g = g; a.m = m; a.k = kh;
+    a.qpts = spts; a.spts = spts; a.cell_first = cell_first; a.g = g; a.m = m; a.k = kh;
     a.todo_idx = todo_last_idx; a.todo_cnt = n_todo_last; a.out_pos = nb_pos; a.out_cnt = nb_cnt;
-    knn_select_kernel<<<num_sms() * 8, kSelThreads, 0, st>>>(a);
+    int coarse = 2;
+    if (const char* env = getenv("UPCP_KNN_COARSE")) { int v = atoi(env); if (v >= 1 && v <= 16) coarse = v; }   // tuning knobs
+    if (h_last > 0 && coarse > 1 && (int64_t)h_last * 200 >= m) {
+        GridParams g2 = g;
+        g2.cell = g.cell * (double)coarse; g2.inv_cell = 1.0 / g2.cell;
+        g2.nx = (g.nx + coarse - 1) / coarse; g2.ny = (g.ny + coarse - 1) / coarse; g2.nz = (g.nz + coarse - 1) / coarse;
+        g2.slack = g2.cell * 1e-6 + (g.slack - g.cell * 1e-6);
+        const uint64_t G2 = (uint64_t)g2.nx * (uint64_t)g2.ny * (uint64_t)g2.nz;
+        if (G2 + 1 <= grid_cell_cap(m) / 4 + 2) {
+            // keys_a / vals_a / keys_b / vals_b are free again (the sorted keys of grid 1 are not needed any more)
+            UPCP_CUDA_OK(cudaMemsetAsync(cell_first2, 0, ((size_t)G2 + 1) * 4, st));
+            knn_keys2_kernel<<<grid_m, kBlock, 0, st>>>(spts, m, g2, keys_a, vals_a, cell_first2);
+            UPCP_LAUNCH_OK();
+            UPCP_TRY(exclusive_scan_u32(cell_first2, cell_first2, (int64_t)G2 + 1, nullptr, prim_ws, st));
+            bool in_b2 = false;
+            UPCP_TRY(radix_sort_pairs_u32(keys_a, vals_a, keys_b, vals_b, m, bits_for_u64(G2), prim_ws, st, &in_b2));
+            knn_gather2_kernel<<<grid_m, kBlock, 0, st>>>(spts, in_b2 ? vals_b : vals_a, m, spts2);
+            UPCP_LAUNCH_OK();
+            a.spts = spts2; a.cell_first = cell_first2; a.g = g2;
+        }
+    }
+    if (h_last > 0) {
+        knn_select_kernel<<<num_sms() * 8, kSelThreads, 0, st>>>(a);
+        UPCP_LAUNCH_OK();
+    }
     prof_end(UPCP_PROF_KNN, st, m);
-    UPCP_LAUNCH_OK();
     if (getenv("UPCP_KNN_DEBUG")) {       // development aid: sizes of the search structures
         uint32_t h[8];
         cudaMemcpyAsync(h, counters, sizeof(h), cudaMemcpyDeviceToHost, st);
         cudaStreamSynchronize(st);
-        fprintf(stderr, "[upcp knn] m=%lld grid=%dx%dx%d (%llu cells) cell=%.4f tier2=%u tier3=%u tier4=%u select=%u\n",
-                (long long)m, g.nx, g.ny, g.nz, (unsigned long long)G, g.cell, h[1], h[2], h[3], h[4]);
+        fprintf(stderr, "[upcp knn] m=%lld grid=%dx%dx%d (%llu cells) cell=%.4f block<2>=%u per-query=%u\n",
+                (long long)m, g.nx, g.ny, g.nz, (unsigned long long)G, g.cell, h[1], h[2]);
     }
 
     EpilogueArgs e;
@@ -884,6 +943,7 @@ size_t upcp_knn_ws_bytes(int64_t n, int64_t m, int kmax) {
     bytes += align_up((size_t)m * 32);                                      // sorted points (x, y, z, id)
     bytes += align_up((size_t)m * 16);                                      // fp32 origin-relative copy
     bytes += align_up((gcap + 1) * 4);                                      // dense cell prefix
+    bytes += align_up((size_t)m * 32) + align_up((gcap / 4 + 2) * 4);       // coarse grid of the per-query tier
     bytes += align_up((size_t)m * kRow * 4) + 3 * align_up((size_t)m);      // neighbour rows, counts, todo flags
     bytes += 2 * align_up((size_t)m * 4);                                   // todo lists
     return bytes + 4096;
