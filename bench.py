@@ -17,7 +17,9 @@ one NCCL all_gather after the timed steps.
          PINNED host memory): H2D of the points + labels and D2H of the labels inside the
          timed region.
   roofline   for the kernel with the largest share of the step (cudaEvent brackets inside
-         the library); algorithmic bytes per point from SURVEY.md 8(d) / DESIGN.md.
+         the library); algorithmic bytes per point from SURVEY.md 8(d) / DESIGN.md.  The
+         `knn_search_kernel` bracket is the neighbour search proper: the two lane-per-query
+         block tiers plus the warp-per-query tier (and the coarse grid built for it).
   cpu_baseline   the oracle port of the reference pipeline on the host cores, on a
          full-density crop of the same tile (rank 0, N = 1 only).
 
@@ -49,6 +51,16 @@ WORKLOAD = ('synthetic 50 m urban tile, {n} points: AHNFuser(ground) + BGTRoadFu
 # algorithmic HBM bytes per point, SURVEY.md section 8(d)
 B_ALG = {'raster_kernel': 27.0, 'pip_query_kernel': 19.0, 'radix_sort (hist+scan+scatter)': 96.0,
          'cc_link_kernel': 8.0, 'knn_search_kernel': 140.0, 'grow_kernel': 421.0}
+
+
+def measured_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the bracketed kernel(s), from the
+    committed ncu --set full capture of this command (profiles/r1_traffic.json), or None."""
+    path = os.path.join(ROOT, 'profiles', 'r1_traffic.json')
+    try:
+        return float(json.load(open(path))['bracket_traffic_bytes_per_launch'][kernel])
+    except Exception:
+        return None
 
 
 def peaks():
@@ -343,7 +355,8 @@ def main():
     alg_bytes = B_ALG[name] * units_per_launch
     achieved = alg_bytes / (per_launch_ms * 1e-3) / 1e9 if per_launch_ms > 0 else 0.0
     roofline = {'bound': 'hbm', 'kernel': name, 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
-                'frac': achieved / peak, 'traffic': None, 'peak_source': peak_src,
+                'frac': achieved / peak, 'traffic': measured_traffic(name), 'traffic_unit': 'bytes per launch (ncu dram read + write, profiles/r1_traffic.json)',
+                'algorithmic_bytes_per_launch': alg_bytes, 'peak_source': peak_src,
                 'algorithmic_bytes_per_point': B_ALG[name], 'points_per_launch': units_per_launch,
                 'launch_ms': per_launch_ms, 'share_of_step': tot_ms / max(ms_dev, 1e-9),
                 'kernels_ms_per_step': {k: round(v[0] / args.steps, 3) for k, v in prof.items()}}
