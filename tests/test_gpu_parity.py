@@ -402,6 +402,31 @@ def test_knn_small_and_degenerate_clouds():
         np.testing.assert_allclose(d_nrm.cpu().numpy(), natives.normals_hybrid(pts, 0.2, 30), rtol=0, atol=1e-9)
 
 
+def test_knn_extreme_extents_stay_exact():
+    """Clouds that force the dense grid to coarsen (few points over kilometres), degenerate axes
+    (a line along y: one cell per row) and extents where the fp32 filter must hand over to the
+    fp64 tier: every tier is exact, so the rows still equal the oracle's."""
+    rng = np.random.default_rng(8)
+    clusters = rng.random((40, 3)) * np.array([5000.0, 5000.0, 300.0])
+    wide = (clusters[rng.integers(0, 40, 20000)] + rng.normal(0, 0.05, (20000, 3)))
+    line_y = np.column_stack((np.zeros(5000), np.sort(rng.random(5000)) * 80.0, np.zeros(5000)))
+    plane = np.column_stack((rng.random(30000) * 3.0, rng.random(30000) * 3.0, np.zeros(30000)))
+    far = rng.random((20000, 3)) * np.array([2.0, 2.0, 0.5]) + np.array([9.0e6, 4.0e6, 0.0])      # 1e-9-m ulp region
+    mixed = np.vstack((rng.random((20000, 3)) * 0.5, rng.random((300, 3)) * 400.0))               # dense blob + far sparse
+    for name, pts in (('wide', wide), ('line_y', line_y), ('plane', plane), ('far', far), ('mixed', mixed)):
+        pts = np.ascontiguousarray(np.round(pts + np.array([119300.0, 485100.0, 0.0]) * (name != 'far'), 3))
+        t = dev.DeviceTile(pts)
+        _, bbox, m = t.bbox(None)
+        for cell in (None, 0.02):
+            d_knn, d_d2, d_nrm, d_cov, _ = rgmod.knn_normals_device(t, None, m, bbox, 15, 30, 0.2, cell_size=cell,
+                                                                    want_d2=True)
+            want_idx, want_d2 = natives.knn(pts, 15, want_d2=True)
+            assert np.array_equal(d_knn.cpu().numpy(), want_idx), (name, cell)
+            assert np.array_equal(d_d2.cpu().numpy(), want_d2), (name, cell)
+            assert np.array_equal(d_cov.cpu().numpy(), natives.cov_knn(pts, want_idx)), (name, cell)
+            np.testing.assert_allclose(d_nrm.cpu().numpy(), natives.normals_hybrid(pts, 0.2, 30), rtol=0, atol=1e-9)
+
+
 @pytest.mark.parametrize('n,seed', [(60000, 51), (400000, 52)])
 def test_region_growing_matches_oracle(n, seed):
     tile, pts, labels = _rg_cloud(n, seed)
