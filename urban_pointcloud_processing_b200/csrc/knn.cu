@@ -10,9 +10,9 @@
 //
 // Data structure (all in HBM, built per call):
 //   * a DENSE uniform grid over the bounding box of the selected points, cells numbered
-//     row-major (x fastest).  Selected points are radix-sorted by cell number and gathered
-//     into sorted records, so every cell -- and every run of x-adjacent cells -- is one
-//     contiguous, coalesced range of points;
+//     row-major (x fastest).  Selected points are counting-sorted by cell number into sorted
+//     records, so every cell -- and every run of x-adjacent cells -- is one contiguous,
+//     coalesced range of points;
 //   * cell_first[G + 1]: exclusive prefix of the per-cell point counts (empty cells
 //     included), so the points of cells [x0, x1] of a grid row are
 //     cell_first[row + x0] .. cell_first[row + x1 + 1]: TWO loads per row, no hashing, no
@@ -88,33 +88,52 @@ struct KnnCompactIdx {
     }
 };
 
-// key = row-major cell number; per-cell counts by atomics (mostly distinct addresses)
+// Counting sort by cell number in two kernels around one scan: the first computes every point's
+// cell and its arrival rank within the cell (one atomic per distinct cell per warp), the scan turns
+// the per-cell counts into the dense prefix table, the second places the records.  The order of
+// the points INSIDE a cell is the arrival order -- not reproducible from run to run, and
+// irrelevant: every consumer orders candidates by (exact squared distance, compact id).
+__device__ __forceinline__ uint32_t cell_rank(uint32_t* __restrict__ cell_count, uint32_t key, bool valid) {
+    const uint32_t peers = __match_any_sync(__activemask(), valid ? key : 0xffffffffu);
+    const int lane = threadIdx.x & 31;
+    const int leader = __ffs(peers) - 1;
+    uint32_t base = 0;
+    if (valid && lane == leader) base = atomicAdd(cell_count + key, (uint32_t)__popc(peers));
+    base = __shfl_sync(peers, base, leader);
+    return base + __popc(peers & ((1u << lane) - 1u));
+}
+
 __global__ void __launch_bounds__(kBlock)
 knn_keys_kernel(const double* __restrict__ x, const double* __restrict__ y,
                 const double* __restrict__ z, const uint32_t* __restrict__ sel_idx, int64_t m,
-                GridParams g, uint32_t* __restrict__ keys, uint32_t* __restrict__ vals,
+                GridParams g, uint32_t* __restrict__ keys, uint32_t* __restrict__ rank,
                 uint32_t* __restrict__ cell_count) {
-    int64_t stride = (int64_t)gridDim.x * kBlock;
-    for (int64_t j = (int64_t)blockIdx.x * kBlock + threadIdx.x; j < m; j += stride) {
-        int64_t i = sel_idx ? (int64_t)sel_idx[j] : j;
-        int cx = cell_coord(x[i], g.ox, g.inv_cell, g.nx);
-        int cy = cell_coord(y[i], g.oy, g.inv_cell, g.ny);
-        int cz = cell_coord(z[i], g.oz, g.inv_cell, g.nz);
-        const uint32_t key = ((uint32_t)cz * (uint32_t)g.ny + (uint32_t)cy) * (uint32_t)g.nx + (uint32_t)cx;
-        keys[j] = key;
-        vals[j] = (uint32_t)j;
-        atomicAdd(cell_count + key, 1u);
+    const int64_t stride = (int64_t)gridDim.x * kBlock;
+    const int64_t m_warp = (m + 31) & ~(int64_t)31;
+    for (int64_t j = (int64_t)blockIdx.x * kBlock + threadIdx.x; j < m_warp; j += stride) {
+        const bool valid = j < m;
+        uint32_t key = 0;
+        if (valid) {
+            int64_t i = sel_idx ? (int64_t)sel_idx[j] : j;
+            int cx = cell_coord(x[i], g.ox, g.inv_cell, g.nx);
+            int cy = cell_coord(y[i], g.oy, g.inv_cell, g.ny);
+            int cz = cell_coord(z[i], g.oz, g.inv_cell, g.nz);
+            key = ((uint32_t)cz * (uint32_t)g.ny + (uint32_t)cy) * (uint32_t)g.nx + (uint32_t)cx;
+        }
+        const uint32_t r = cell_rank(cell_count, key, valid);
+        if (valid) { keys[j] = key; rank[j] = r; }
     }
 }
 
 __global__ void __launch_bounds__(kBlock)
-knn_gather_kernel(const double* __restrict__ x, const double* __restrict__ y,
-                  const double* __restrict__ z, const uint32_t* __restrict__ sel_idx,
-                  const uint32_t* __restrict__ perm, int64_t m, GridParams g,
-                  P4* __restrict__ spts, float4* __restrict__ spf, uint32_t* __restrict__ order) {
+knn_place_kernel(const double* __restrict__ x, const double* __restrict__ y,
+                 const double* __restrict__ z, const uint32_t* __restrict__ sel_idx,
+                 const uint32_t* __restrict__ keys, const uint32_t* __restrict__ rank,
+                 const uint32_t* __restrict__ cell_first, int64_t m, GridParams g,
+                 P4* __restrict__ spts, float4* __restrict__ spf, uint32_t* __restrict__ order) {
     int64_t stride = (int64_t)gridDim.x * kBlock;
-    for (int64_t s = (int64_t)blockIdx.x * kBlock + threadIdx.x; s < m; s += stride) {
-        uint32_t j = perm[s];
+    for (int64_t j = (int64_t)blockIdx.x * kBlock + threadIdx.x; j < m; j += stride) {
+        const uint32_t s = __ldg(cell_first + keys[j]) + rank[j];
         int64_t i = sel_idx ? (int64_t)sel_idx[j] : (int64_t)j;
         const double px = x[i], py = y[i], pz = z[i];
         double2* o = reinterpret_cast<double2*>(spts + s);
@@ -126,28 +145,34 @@ knn_gather_kernel(const double* __restrict__ x, const double* __restrict__ y,
     }
 }
 
-// Second, coarser grid for the per-query tier: keys from the fine-sorted records, ...
+// Second, coarser grid for the per-query tier, built the same way from the fine-sorted records
+// (they keep their fine-grid position in w).
 __global__ void __launch_bounds__(kBlock)
 knn_keys2_kernel(const P4* __restrict__ spts, int64_t m, GridParams g, uint32_t* __restrict__ keys,
-                 uint32_t* __restrict__ vals, uint32_t* __restrict__ cell_count) {
-    int64_t stride = (int64_t)gridDim.x * kBlock;
-    for (int64_t s = (int64_t)blockIdx.x * kBlock + threadIdx.x; s < m; s += stride) {
-        const P4 p = load_p4(spts + s);
-        int cx = cell_coord(p.x, g.ox, g.inv_cell, g.nx);
-        int cy = cell_coord(p.y, g.oy, g.inv_cell, g.ny);
-        int cz = cell_coord(p.z, g.oz, g.inv_cell, g.nz);
-        const uint32_t key = ((uint32_t)cz * (uint32_t)g.ny + (uint32_t)cy) * (uint32_t)g.nx + (uint32_t)cx;
-        keys[s] = key;
-        vals[s] = (uint32_t)s;
-        atomicAdd(cell_count + key, 1u);
+                 uint32_t* __restrict__ rank, uint32_t* __restrict__ cell_count) {
+    const int64_t stride = (int64_t)gridDim.x * kBlock;
+    const int64_t m_warp = (m + 31) & ~(int64_t)31;
+    for (int64_t s = (int64_t)blockIdx.x * kBlock + threadIdx.x; s < m_warp; s += stride) {
+        const bool valid = s < m;
+        uint32_t key = 0;
+        if (valid) {
+            const P4 p = load_p4(spts + s);
+            int cx = cell_coord(p.x, g.ox, g.inv_cell, g.nx);
+            int cy = cell_coord(p.y, g.oy, g.inv_cell, g.ny);
+            int cz = cell_coord(p.z, g.oz, g.inv_cell, g.nz);
+            key = ((uint32_t)cz * (uint32_t)g.ny + (uint32_t)cy) * (uint32_t)g.nx + (uint32_t)cx;
+        }
+        const uint32_t r = cell_rank(cell_count, key, valid);
+        if (valid) { keys[s] = key; rank[s] = r; }
     }
 }
-// ... and the records re-ordered by coarse cell (they keep their fine-grid position in w)
 __global__ void __launch_bounds__(kBlock)
-knn_gather2_kernel(const P4* __restrict__ spts, const uint32_t* __restrict__ perm, int64_t m, P4* __restrict__ spts2) {
+knn_place2_kernel(const P4* __restrict__ spts, const uint32_t* __restrict__ keys, const uint32_t* __restrict__ rank,
+                  const uint32_t* __restrict__ cell_first, int64_t m, P4* __restrict__ spts2) {
     int64_t stride = (int64_t)gridDim.x * kBlock;
-    for (int64_t t = (int64_t)blockIdx.x * kBlock + threadIdx.x; t < m; t += stride) {
-        const double2* src = reinterpret_cast<const double2*>(spts + perm[t]);
+    for (int64_t s = (int64_t)blockIdx.x * kBlock + threadIdx.x; s < m; s += stride) {
+        const uint32_t t = __ldg(cell_first + keys[s]) + rank[s];
+        const double2* src = reinterpret_cast<const double2*>(spts + s);
         double2* dst = reinterpret_cast<double2*>(spts2 + t);
         dst[0] = __ldg(src); dst[1] = __ldg(src + 1);
     }
@@ -774,7 +799,6 @@ knn_epilogue_kernel(EpilogueArgs a) {
     }
 }
 
-static inline int bits_for_u64(uint64_t n) { int b = 0; while (((uint64_t)1 << b) < n) ++b; return b; }
 // the dense grid may hold up to this many cells for m selected points
 static inline uint64_t grid_cell_cap(int64_t m) {
     uint64_t cap = 16ull * (uint64_t)(m < 1 ? 1 : m) + (1ull << 20);
@@ -791,10 +815,8 @@ static int knn_impl(const double* d_x, const double* d_y, const double* d_z, int
     uint32_t* counters = ws.take<uint32_t>(64);          // [0] m, [1] tier-2 queries, [2] tier-3 queries
     uint32_t* sel_idx = d_sel ? ws.take<uint32_t>((size_t)n) : nullptr;
     uint32_t* prim_ws = ws.take<uint32_t>(compact_ws_words(n) + sort_ws_words(m) + scan_ws_words((int64_t)grid_cell_cap(m) + 1));
-    uint32_t* keys_a = ws.take<uint32_t>((size_t)m);
-    uint32_t* keys_b = ws.take<uint32_t>((size_t)m);
-    uint32_t* vals_a = ws.take<uint32_t>((size_t)m);
-    uint32_t* vals_b = ws.take<uint32_t>((size_t)m);
+    uint32_t* keys = ws.take<uint32_t>((size_t)m);
+    uint32_t* rank = ws.take<uint32_t>((size_t)m);
     P4* spts = ws.take<P4>((size_t)m);
     float4* spf = ws.take<float4>((size_t)m);
     uint32_t* cell_first = ws.take<uint32_t>((size_t)grid_cell_cap(m) + 1);
@@ -818,16 +840,13 @@ static int knn_impl(const double* d_x, const double* d_y, const double* d_z, int
         UPCP_FAIL(UPCP_E_INVALID, "knn: m must equal n when no selection is given");
     }
 
-    // cell numbers + per-cell counts, exclusive prefix over ALL cells, sort, gather
+    // cell numbers + arrival ranks + per-cell counts, exclusive prefix over ALL cells, placement
     const int grid_m = grid_for(m, kBlock);
     UPCP_CUDA_OK(cudaMemsetAsync(cell_first, 0, ((size_t)G + 1) * 4, st));
-    knn_keys_kernel<<<grid_m, kBlock, 0, st>>>(d_x, d_y, d_z, sel_idx, m, g, keys_a, vals_a, cell_first);
+    knn_keys_kernel<<<grid_m, kBlock, 0, st>>>(d_x, d_y, d_z, sel_idx, m, g, keys, rank, cell_first);
     UPCP_LAUNCH_OK();
     UPCP_TRY(exclusive_scan_u32(cell_first, cell_first, (int64_t)G + 1, nullptr, prim_ws, st));
-    bool in_b = false;
-    UPCP_TRY(radix_sort_pairs_u32(keys_a, vals_a, keys_b, vals_b, m, bits_for_u64(G), prim_ws, st, &in_b));
-    uint32_t* perm = in_b ? vals_b : vals_a;
-    knn_gather_kernel<<<grid_m, kBlock, 0, st>>>(d_x, d_y, d_z, sel_idx, perm, m, g, spts, spf, d_order);
+    knn_place_kernel<<<grid_m, kBlock, 0, st>>>(d_x, d_y, d_z, sel_idx, keys, rank, cell_first, m, g, spts, spf, d_order);
     UPCP_LAUNCH_OK();
 
     int kh = knn > max_nn ? knn : max_nn;
@@ -872,7 +891,7 @@ static int knn_impl(const double* d_x, const double* d_y, const double* d_z, int
     }
     // The per-query tier walks grid rows; where it has much to do (sparse clutter, noise) it gets a
     // second grid with `coarse` times larger cells -- coarse^2 times fewer rows per shell -- built
-    // from the fine-sorted records (3 more radix passes, one gather).
+    // from the fine-sorted records (one more counting sort).
     uint32_t h_last = 0;
     UPCP_CUDA_OK(cudaMemcpyAsync(&h_last, n_todo_last, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     UPCP_CUDA_OK(cudaStreamSynchronize(st));
@@ -888,14 +907,12 @@ static int knn_impl(const double* d_x, const double* d_y, const double* d_z, int
         g2.slack = g2.cell * 1e-6 + (g.slack - g.cell * 1e-6);
         const uint64_t G2 = (uint64_t)g2.nx * (uint64_t)g2.ny * (uint64_t)g2.nz;
         if (G2 + 1 <= grid_cell_cap(m) / 4 + 2) {
-            // keys_a / vals_a / keys_b / vals_b are free again (the sorted keys of grid 1 are not needed any more)
+            // (keys / rank are free again)
             UPCP_CUDA_OK(cudaMemsetAsync(cell_first2, 0, ((size_t)G2 + 1) * 4, st));
-            knn_keys2_kernel<<<grid_m, kBlock, 0, st>>>(spts, m, g2, keys_a, vals_a, cell_first2);
+            knn_keys2_kernel<<<grid_m, kBlock, 0, st>>>(spts, m, g2, keys, rank, cell_first2);
             UPCP_LAUNCH_OK();
             UPCP_TRY(exclusive_scan_u32(cell_first2, cell_first2, (int64_t)G2 + 1, nullptr, prim_ws, st));
-            bool in_b2 = false;
-            UPCP_TRY(radix_sort_pairs_u32(keys_a, vals_a, keys_b, vals_b, m, bits_for_u64(G2), prim_ws, st, &in_b2));
-            knn_gather2_kernel<<<grid_m, kBlock, 0, st>>>(spts, in_b2 ? vals_b : vals_a, m, spts2);
+            knn_place2_kernel<<<grid_m, kBlock, 0, st>>>(spts, keys, rank, cell_first2, m, spts2);
             UPCP_LAUNCH_OK();
             a.spts = spts2; a.cell_first = cell_first2; a.g = g2;
         }
@@ -939,7 +956,7 @@ size_t upcp_knn_ws_bytes(int64_t n, int64_t m, int kmax) {
     size_t bytes = align_up(64 * 4);
     bytes += align_up((size_t)n * 4);
     bytes += align_up((compact_ws_words(n) + sort_ws_words(m) + scan_ws_words((int64_t)gcap + 1)) * 4);
-    bytes += 4 * align_up((size_t)m * 4);                                   // keys, vals (ping-pong)
+    bytes += 2 * align_up((size_t)m * 4);                                   // cell numbers, arrival ranks
     bytes += align_up((size_t)m * 32);                                      // sorted points (x, y, z, id)
     bytes += align_up((size_t)m * 16);                                      // fp32 origin-relative copy
     bytes += align_up((gcap + 1) * 4);                                      // dense cell prefix
