@@ -359,7 +359,11 @@ def main():
                 'algorithmic_bytes_per_launch': alg_bytes, 'peak_source': peak_src,
                 'algorithmic_bytes_per_point': B_ALG[name], 'points_per_launch': units_per_launch,
                 'launch_ms': per_launch_ms, 'share_of_step': tot_ms / max(ms_dev, 1e-9),
-                'kernels_ms_per_step': {k: round(v[0] / args.steps, 3) for k, v in prof.items()}}
+                'kernels_ms_per_step': {k: round(v[0] / args.steps, 3) for k, v in prof.items()},
+                # algorithmic GB/s of every bracketed kernel (B_ALG x units / bracketed time), fraction of the peak
+                'kernels_algorithmic_gbs': {k: [round(B_ALG[k] * v[2] / (v[0] * 1e-3) / 1e9, 1),
+                                                round(B_ALG[k] * v[2] / (v[0] * 1e-3) / 1e9 / peak, 4)]
+                                            for k, v in prof.items() if v[0] > 0}}
 
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:

@@ -23,6 +23,7 @@
 //     them on the host while the device grows, and resume from the points that turned out to
 //     be seeds -- growth is monotone, so the fixpoint is the same.
 #include <math.h>
+#include <stdlib.h>
 #include "common.cuh"
 #include "primitives.cuh"
 #include "upcp_math.cuh"
@@ -113,17 +114,96 @@ grow_requeue_kernel(const int64_t* __restrict__ extra, int64_t n_extra, const ui
     }
 }
 
+// Seeds a warp discovers stay with that warp (a small ring in shared memory) up to kLocalCap; only
+// the overflow goes through the global queue.  The frontier is narrow and every hop through the
+// global queue costs three dependent L2 round trips (tail / pending atomics, slot write, the
+// consumer's poll) on top of the expansion itself; the local path removes them from the chain.
+constexpr int kLocalCap = 2;              // measured optimum (1 .. 32 swept): latency of the chain vs load balance
+constexpr int kRing = 64;                // ring size (power of two, >= the largest local cap + 32)
+
 __global__ void __launch_bounds__(kGrowThreads)
 grow_kernel(const int32_t* __restrict__ knn, int k, const double* __restrict__ normals,
             const uint8_t* __restrict__ can_seed, int64_t m, double threshold_deg,
-            int32_t* __restrict__ state, int32_t* __restrict__ queue, GrowCounters* __restrict__ ctr) {
+            int32_t* __restrict__ state, int32_t* __restrict__ queue, GrowCounters* __restrict__ ctr,
+            int local_cap, int sleep_ns) {
+    __shared__ int32_t s_ring[kGrowThreads / 32][kRing];
     const int lane = threadIdx.x & 31;
+    int32_t* const ring = s_ring[threadIdx.x >> 5];
+    unsigned int r_head = 0, r_tail = 0;                       // warp-uniform
     volatile int32_t* vqueue = queue;
     volatile int* vpending = &ctr->pending;
     // two seeds per step when a kNN row fits a half-warp, else one
     const int per_step = k <= 16 ? 2 : 1;
     const int sub = per_step == 2 ? (lane >> 4) : 0;          // which seed of the step this lane serves
     const int j = per_step == 2 ? (lane & 15) : lane;        // neighbour slot within the row
+
+    // expand the seeds held by the lanes of `batch` (lane l holds seed `mine`)
+    auto process = [&](int32_t mine, uint32_t batch) {
+        uint32_t todo = batch;
+        while (todo) {
+            // pick the seed(s) of this step
+            const int srcA = __ffs(todo) - 1;
+            todo &= todo - 1;
+            int srcB = -1;
+            if (per_step == 2 && todo) { srcB = __ffs(todo) - 1; todo &= todo - 1; }
+            const int src = sub == 0 ? srcA : srcB;
+            const int32_t s = __shfl_sync(0xffffffffu, mine, src < 0 ? 0 : src);
+            bool push = false;
+            int32_t nb = -1;
+            // neighbour_idx[1:k] (region_growing.py:112): the first returned index is dropped
+            for (int jj = j; jj < k; jj += (per_step == 2 ? 16 : 32)) {
+                // (k <= 32: at most one trip)
+                if (src >= 0 && jj >= 1) {
+                    // issue every load that only needs the indices at once (the seed's normal with
+                    // the row, the neighbour's state / normal / flag together)
+                    const Vec3 ns = {normals[(size_t)s * 3], normals[(size_t)s * 3 + 1], normals[(size_t)s * 3 + 2]};
+                    nb = knn[(size_t)s * k + jj];
+                    if (nb >= 0) {
+                        const int32_t st = __ldcg(state + nb);
+                        const Vec3 nn = {normals[(size_t)nb * 3], normals[(size_t)nb * 3 + 1], normals[(size_t)nb * 3 + 2]};
+                        const uint8_t cs = can_seed[nb];
+                        if (st == 0 && vector_angle_deg(ns, nn) < threshold_deg) {
+                            if (atomicExch(&state[nb], 1) == 0) push = cs == 1;
+                        }
+                    }
+                }
+            }
+            // new seeds: the first ones stay in this warp's ring, the rest go to the global queue
+            const uint32_t bal = __ballot_sync(0xffffffffu, push);
+            if (bal) {
+                const int cnt = __popc(bal);
+                const int room = local_cap - (int)(r_tail - r_head);
+                const int n_loc = room > 0 ? (cnt < room ? cnt : room) : 0;
+                const int my = __popc(bal & ((1u << lane) - 1u));
+                const int leader = __ffs(bal) - 1;
+                unsigned int base = 0;
+                if (lane == leader) {
+                    atomicAdd(&ctr->pending, cnt);               // before any of them becomes visible
+                    if (cnt > n_loc) base = atomicAdd(&ctr->tail, (unsigned int)(cnt - n_loc));
+                }
+                base = __shfl_sync(0xffffffffu, base, leader);
+                if (push) {
+                    if (my < n_loc) ring[(r_tail + my) & (kRing - 1)] = nb;
+                    else vqueue[base + (my - n_loc)] = nb;
+                }
+                r_tail += n_loc;
+                __syncwarp();
+            }
+        }
+    };
+    // drain the local ring
+    auto drain_local = [&]() {
+        while (r_tail != r_head) {
+            const int cnt = min((int)(r_tail - r_head), 32);
+            const int32_t mine = lane < cnt ? ring[(r_head + lane) & (kRing - 1)] : -1;
+            __syncwarp();
+            r_head += cnt;
+            process(mine, cnt == 32 ? 0xffffffffu : ((1u << cnt) - 1u));
+            __syncwarp();
+            if (lane == 0) { __threadfence(); atomicSub(&ctr->pending, cnt); }
+        }
+    };
+
     while (true) {
         // a warp takes 32 tickets at once (one atomic on the shared head counter per 32 seeds) ...
         unsigned int t0 = 0;
@@ -143,46 +223,16 @@ grow_kernel(const int32_t* __restrict__ knn, int k, const double* __restrict__ n
                 if (lane == 0) pend = *vpending;
                 pend = __shfl_sync(0xffffffffu, pend, 0);
                 if (pend <= 0) return;                 // global quiescence: nothing left anywhere
-                __nanosleep(64);
+                __nanosleep(sleep_ns);
                 if (++spins > (1u << 26)) { if (lane == 0) atomicExch(&ctr->error, 1u); return; }   // safety valve
                 continue;
             }
-            uint32_t todo = ready;
-            while (todo) {
-                // pick the seed(s) of this step
-                const int srcA = __ffs(todo) - 1;
-                todo &= todo - 1;
-                int srcB = -1;
-                if (per_step == 2 && todo) { srcB = __ffs(todo) - 1; todo &= todo - 1; }
-                const int src = sub == 0 ? srcA : srcB;
-                const int32_t s = __shfl_sync(0xffffffffu, mine, src < 0 ? 0 : src);
-                bool push = false;
-                int32_t nb = -1;
-                // neighbour_idx[1:k] (region_growing.py:112): the first returned index is dropped
-                for (int jj = j; jj < k; jj += (per_step == 2 ? 16 : 32)) {
-                    // (k <= 32: at most one trip)
-                    if (src >= 0 && jj >= 1) {
-                        // the expansion is a chain of dependent round trips to L2 and the frontier is
-                        // narrow: issue every load that only needs the indices at once (the seed's
-                        // normal with the row, the neighbour's state / normal / flag together)
-                        const Vec3 ns = {normals[(size_t)s * 3], normals[(size_t)s * 3 + 1], normals[(size_t)s * 3 + 2]};
-                        nb = knn[(size_t)s * k + jj];
-                        if (nb >= 0) {
-                            const int32_t st = __ldcg(state + nb);
-                            const Vec3 nn = {normals[(size_t)nb * 3], normals[(size_t)nb * 3 + 1], normals[(size_t)nb * 3 + 2]};
-                            const uint8_t cs = can_seed[nb];
-                            if (st == 0 && vector_angle_deg(ns, nn) < threshold_deg) {
-                                if (atomicExch(&state[nb], 1) == 0) push = cs == 1;
-                            }
-                        }
-                    }
-                }
-                grow_push(push, nb, vqueue, ctr);
-            }
+            process(mine, ready);
             __syncwarp();
             if (lane == 0) { __threadfence(); atomicSub(&ctr->pending, __popc(ready)); }
             remaining &= ~ready;
             spins = 0;
+            drain_local();
         }
     }
 }
@@ -268,14 +318,19 @@ int grow_drain(const int32_t* d_knn, int knn, const double* d_normals, const uin
     if (per_sm == 0) {
         UPCP_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, grow_kernel, kGrowThreads, 0));
         if (per_sm < 1) UPCP_FAIL(UPCP_E_CUDA, "region_grow: kernel cannot be resident");
-        if (per_sm > 4) per_sm = 4;
+        // one CTA per SM: more pollers only add contention on the queue counters (1 / 2 / 4 swept)
+        if (per_sm > 1) per_sm = 1;
         per_sm_cached = per_sm;
     }
     int grid = num_sms() * per_sm;
     int64_t need = (m + (kGrowThreads / 32) - 1) / (kGrowThreads / 32);
     if (need < grid) grid = (int)(need < 1 ? 1 : need);
+    int local_cap = kLocalCap;
+    const int sleep_ns = 64;
+    if (const char* env = getenv("UPCP_GROW_LOCAL")) { int v = atoi(env); if (v >= 0 && v <= 32) local_cap = v; }   // tuning knobs
+    if (const char* env = getenv("UPCP_GROW_GRID")) { int v = atoi(env); if (v >= 1 && v < grid) grid = v; }
     grow_kernel<<<grid, kGrowThreads, 0, st>>>(d_knn, knn, d_normals, d_can_seed, m, threshold_angle_deg,
-                                               w.state, w.queue, w.ctr);
+                                               w.state, w.queue, w.ctr, local_cap, sleep_ns);
     UPCP_LAUNCH_OK();
     return UPCP_OK;
 }

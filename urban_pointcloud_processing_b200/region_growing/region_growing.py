@@ -184,15 +184,7 @@ def region_grow_device(d_knn, d_normals, d_seed, d_can_seed, threshold_angle):
     return d_region, d_info
 
 
-_SIDE_STREAMS = {}
 _POOL = None
-
-
-def _side_stream(device):
-    key = str(device)
-    if key not in _SIDE_STREAMS:
-        _SIDE_STREAMS[key] = torch.cuda.Stream(device=device)
-    return _SIDE_STREAMS[key]
 
 
 def _pool():
@@ -207,17 +199,19 @@ def region_grow_overlapped(d_knn, d_normals, d_seed, d_flag, d_cov, threshold_cu
     """Growth to the least fixpoint with the undecided curvature flags (value 2) resolved on the
     host WHILE the device grows (``upcp_region_grow_begin / _resume / _end``).
 
-    The device starts from the flags it could decide itself.  On a side stream the undecided
-    covariances are fetched and put through ``np.linalg.eig`` exactly as the reference does
-    (region_growing.py:69-73); the flags are then rewritten and the growth resumed from the points
-    that turned out to be seeds.  Growth is monotone, so the result equals the one-shot fixpoint.
+    The undecided covariances are fetched first; the device then starts growing from the flags it
+    could decide itself while the host puts the fetched ones through ``np.linalg.eig`` exactly as
+    the reference does (region_growing.py:69-73); the flags are then rewritten and the growth
+    resumed from the points that turned out to be seeds.  Growth is monotone, so the result equals the one-shot fixpoint.
     Returns (d_region, d_info, n_host)."""
     lib = _lib.load()
     m, knn = d_knn.shape
     device = d_knn.device
-    main = torch.cuda.current_stream(device)
-    flags_ready = torch.cuda.Event()
-    flags_ready.record(main)
+    # the undecided covariances leave the device BEFORE the growth is queued: the persistent
+    # kernel occupies every SM, nothing else would get through while it runs
+    idx = torch.nonzero(d_flag == 2).flatten()
+    n_host = int(idx.numel())
+    c = d_cov[idx].cpu().numpy() if n_host else None
     d_region = torch.empty(m, dtype=torch.uint8, device=device)
     d_info = torch.zeros(2, dtype=torch.int64, device=device)
     ws = dev.workspace(device, slot=2).get(lib.upcp_region_grow_ws_bytes(m))
@@ -225,12 +219,6 @@ def region_grow_overlapped(d_knn, d_normals, d_seed, d_flag, d_cov, threshold_cu
                                           dev.ptr(d_flag), m, float(threshold_angle), dev.ptr(ws), ws.numel(),
                                           dev.stream_ptr()), 'upcp_region_grow_begin')
     # ---- host resolution of the undecided flags, overlapped with the kernels queued above
-    side = _side_stream(device)
-    with torch.cuda.stream(side):
-        side.wait_event(flags_ready)
-        idx = torch.nonzero(d_flag == 2).flatten()
-        n_host = int(idx.numel())                       # waits for the side stream only
-        c = d_cov[idx].cpu().numpy() if n_host else None
     if n_host:
         n_thr = max(1, min(os.cpu_count() or 1, 16, n_host // 256))
         if n_thr > 1:
@@ -238,7 +226,6 @@ def region_grow_overlapped(d_knn, d_normals, d_seed, d_flag, d_cov, threshold_cu
             res = np.concatenate(parts)
         else:
             res = _host_curvature(c, threshold_curve)
-        main.wait_stream(side)
         d_flag[idx] = torch.from_numpy(np.ascontiguousarray(res.astype(np.uint8))).to(device)
         _lib.check(lib.upcp_region_grow_resume(dev.ptr(d_knn), int(knn), dev.ptr(d_normals), dev.ptr(d_seed),
                                                dev.ptr(d_flag), m, dev.ptr(idx), n_host, float(threshold_angle),
