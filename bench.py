@@ -339,6 +339,36 @@ def main():
         same = bool(np.array_equal(labels_host.astype(np.int32), d_labels.cpu().numpy()))
         e2e['labels_equal_device_arm'] = same
 
+    # ---- supplementary: the LAS-file route (Pipeline.process_file without the disk): raw int32 X, Y, Z
+    # in pinned host memory -> device (12 B/pt), coordinates scaled on the device, labels back
+    e2e_las = None
+    if not args.no_e2e:
+        from urban_pointcloud_processing_b200.utils import las_io
+        scales, offsets = np.array([0.001, 0.001, 0.001]), np.array([100000.0, 400000.0, 0.0])
+        ints = np.rint((tile['points'] - offsets) / scales).astype(np.int32)
+        pinned_ints = [torch.from_numpy(np.ascontiguousarray(ints[:, k])).pin_memory() for k in range(3)]
+
+        class _Las:                                   # the attributes DeviceTile.from_las reads
+            X, Y, Z = (p_.numpy() for p_ in pinned_ints)
+            header = las_io.LasHeader()
+        _Las.header.scales, _Las.header.offsets = scales, offsets
+        lab_u8 = torch.zeros(n, dtype=torch.uint8).pin_memory()
+
+        def las_step():
+            lab_u8.zero_()
+            t_las = dev.DeviceTile.from_las(_Las, device)
+            dl = dev.upload_labels(lab_u8.numpy(), device)
+            pipeline.process_tile_device(tc, t_las, dl)
+            dev.download_labels(dl, lab_u8.numpy())
+        for _ in range(2):
+            las_step()
+        ms_las, wall_las, _ = timed(las_step, args.steps)
+        las_ms = max(ms_las, wall_las)
+        e2e_las = {'value': world * n * args.steps / (las_ms * 1e-3) / 1e6, 'unit': 'Mpts/s',
+                   'ms_per_step': las_ms / args.steps, 'h2d_bytes_per_step': int(n * 12 + n), 'd2h_bytes_per_step': int(n),
+                   'api': 'DeviceTile.from_las (int32 X, Y, Z + scale / offset, as Pipeline.process_file uploads them) + '
+                          'process_tile_device + label download; no initial car seeds (labels start at 0)'}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -382,7 +412,7 @@ def main():
             'config': {'workload': WORKLOAD.format(n=n), 'tiles_per_step': world, 'points_per_tile': n,
                        'l2_policy': 'inputs (480 MB of coordinates per tile) are larger than the 126 MB L2',
                        'tiles_per_s': world * args.steps / (ms_dev * 1e-3)},
-            'clocks': clocks, 'e2e': e2e, 'gpu_launches': int(launches), 'roofline': roofline,
+            'clocks': clocks, 'e2e': e2e, 'e2e_las': e2e_las, 'gpu_launches': int(launches), 'roofline': roofline,
             'cpu_baseline': cpu_baseline, 'stage_ms': stage_s, 'points_labelled_last_step': labelled,
             'wall_ms_per_step': wall_dev / args.steps}
     print(json.dumps(line))

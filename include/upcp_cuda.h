@@ -74,6 +74,15 @@ const char* upcp_prof_slot_name(int slot);
 int upcp_points_aos_to_soa(const double* d_xyz, int64_t n, int ncols,
                            double* d_x, double* d_y, double* d_z, void* stream);
 
+/* LAS ingest: coordinates from the raw integer fields of the point records,
+ *   x = X * scale + offset  (fp64, product and sum rounded separately)
+ * which is what laspy's scaled `las.x / las.y / las.z` deliver to pipeline.py:123-124
+ * (las_utils.read_las, las_utils.py:118-120) -- computed on the device from 12 B per point
+ * instead of uploading 24 B per point of host-side doubles. */
+int upcp_points_from_scaled_int32(const int32_t* d_X, const int32_t* d_Y, const int32_t* d_Z, int64_t n,
+                                  const double* h_scale3, const double* h_offset3,
+                                  double* d_x, double* d_y, double* d_z, void* stream);
+
 /* Bounding boxes in fp64.  d_out receives 13 doubles:
  *   [0..5]  min x,y,z / max x,y,z over ALL n points
  *   [6..11] min x,y,z / max x,y,z over points with d_sel[i] != 0 (all if d_sel NULL)

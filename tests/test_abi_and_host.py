@@ -222,3 +222,36 @@ def test_synthetic_generator_is_deterministic():
     c = synthetic.make_tile(5000, seed=43)
     assert not np.array_equal(a['points'], c['points'])
     assert len(synthetic.make_polygon_lattice(n_side=5)) == 25
+
+
+def test_native_las_io_round_trip(tmp_path):
+    """utils.las_io: what las_utils.read_las / label_and_save_las fall back to without laspy."""
+    from urban_pointcloud_processing_b200.utils import las_io, las_utils
+    rng = np.random.default_rng(3)
+    P = (rng.integers(0, 50000, (5000, 3)) + np.array([119300000, 485100000, -2000])).astype(np.int32)
+    scales, offsets = [0.001, 0.001, 0.001], [0.0, 0.0, 0.0]
+    las = las_io.create(P, scales, offsets, point_format_id=1)
+    assert las.point_format.extra_dimension_names == [] and las.header.point_count == 5000
+    assert np.array_equal(las.x, P[:, 0] * 0.001 + 0.0) and las.x.dtype == np.float64
+    f1 = str(tmp_path / 'filtered_2386_9702.las')
+    las.write(f1)
+    back = las_utils.read_las(f1)
+    assert np.array_equal(back.X, P[:, 0]) and np.array_equal(back.Y, P[:, 1]) and np.array_equal(back.Z, P[:, 2])
+    assert np.array_equal(back.header.scales, scales) and back.point_format.extra_dimension_names == []
+    labels = rng.integers(0, 99, 5000).astype(np.uint16)
+    f2 = str(tmp_path / 'labelled_2386_9702.las')
+    las_utils.label_and_save_las(back, labels, f2)
+    again = las_utils.read_las(f2)
+    assert again.point_format.extra_dimension_names == ['label']
+    assert np.array_equal(again.label, labels.astype(np.uint8)) and np.array_equal(again.X, P[:, 0])
+    assert again.header.point_size == back.header.point_size       # 28 + 1 extra byte, header rewritten
+    # a second labelling overwrites the existing dimension instead of adding one
+    las_utils.label_and_save_las(again, labels[::-1].copy(), f2)
+    third = las_utils.read_las(f2)
+    assert third.point_format.extra_dimension_names == ['label'] and np.array_equal(third.label, labels[::-1].astype(np.uint8))
+    assert las_utils.get_tilecode_from_filename(f2) == '2386_9702'
+    try:
+        import laspy  # noqa: F401
+    except ImportError:
+        with pytest.raises(ImportError):
+            las_utils.read_las(str(tmp_path / 'x_2386_9702.laz'))

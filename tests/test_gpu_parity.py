@@ -90,6 +90,40 @@ def test_mask_and_label_kernels():
         assert np.array_equal(dev.label_hist(d_labels).cpu().numpy(), R.label_histogram(want))
 
 
+def test_las_ingest_scaled_on_device_and_process_file(tmp_path):
+    """LAS path: int32 X, Y, Z up, x = X * scale + offset on the device == the host-side scaled view;
+    Pipeline.process_file == Pipeline.process_cloud on the same cloud."""
+    from urban_pointcloud_processing_b200.utils import las_io, las_utils
+    tile = synthetic.make_tile(200000, seed=77)
+    pts = tile['points']
+    scales, offsets = np.array([0.001, 0.001, 0.001]), np.array([100000.0, 400000.0, 0.0])
+    P = np.rint((pts - offsets) / scales).astype(np.int32)
+    las = las_io.create(P, scales, offsets)
+    t = dev.DeviceTile.from_las(las)
+    assert np.array_equal(t.x.cpu().numpy(), las.x) and np.array_equal(t.y.cpu().numpy(), las.y)
+    assert np.array_equal(t.z.cpu().numpy(), las.z) and t.h2d_bytes == 12 * len(P)
+    # awkward scales / offsets: the two roundings must match numpy's
+    las2 = las_io.create(P, [0.00025, 0.01, 1.0 / 3.0], [0.1, -7.3, 1e6])
+    t2 = dev.DeviceTile.from_las(las2)
+    assert np.array_equal(t2.x.cpu().numpy(), las2.x) and np.array_equal(t2.z.cpu().numpy(), las2.z)
+    f_in, f_out = str(tmp_path / f"filtered_{tile['tilecode']}.las"), str(tmp_path / f"labelled_{tile['tilecode']}.las")
+    las.write(f_in)
+    ahn, bld, road = readers_for(tile)
+
+    def procs():
+        return (AHNFuser(Labels.GROUND, ahn, target='ground', epsilon=0.2, refine_ground=False),
+                BGTRoadFuser(Labels.ROAD, bgt_reader=road),
+                BGTBuildingFuser(Labels.BUILDING, bgt_reader=bld, offset=0, ahn_reader=ahn),
+                RegionGrowing(Labels.BUILDING, exclude_labels=(Labels.GROUND, Labels.ROAD)))
+    Pipeline(processors=procs(), ahn_reader=ahn, caching=True).process_file(f_in, f_out)
+    out = las_utils.read_las(f_out)
+    points = np.vstack((las.x, las.y, las.z)).T
+    want = Pipeline(processors=procs(), ahn_reader=ahn, caching=True).process_cloud(
+        tile['tilecode'], points, np.zeros(len(points), dtype=np.uint16))
+    assert np.array_equal(out.label, want.astype(np.uint8)) and (want != 0).sum() > 100000
+    assert np.array_equal(out.X, P[:, 0])
+
+
 # ------------------------------------------------------------------------ raster ---
 def test_raster_lookup_matches_reference_golden(golden):
     g = golden('raster_golden.npz')

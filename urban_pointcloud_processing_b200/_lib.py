@@ -37,6 +37,8 @@ _PROTOTYPES = {
     'upcp_prof_reset': (c_int, []),
     'upcp_prof_read': (c_int, [c_int, POINTER(c_double), POINTER(c_int64), POINTER(c_int64)]),
     'upcp_prof_slot_name': (c_char_p, [c_int]),
+    'upcp_points_from_scaled_int32': (c_int, [c_void_p, c_void_p, c_void_p, c_int64, POINTER(c_double),
+                                              POINTER(c_double), c_void_p, c_void_p, c_void_p, c_void_p]),
     'upcp_points_aos_to_soa': (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     'upcp_bbox_ws_bytes': (c_size_t, [c_int64]),
     'upcp_bbox': (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),

@@ -234,7 +234,34 @@ label_hist_kernel(const int32_t* __restrict__ labels, int64_t n, unsigned long l
 
 using namespace upcp;
 
+namespace upcp {
+// x = X * scale + offset in fp64, two roundings (this translation unit is compiled without FMA
+// contraction): what laspy's scaled view computes on the host, from 12 B instead of 24 B per point
+__global__ void __launch_bounds__(kBlock)
+scaled_int_kernel(const int32_t* __restrict__ X, const int32_t* __restrict__ Y, const int32_t* __restrict__ Z,
+                  int64_t n, double sx, double sy, double sz, double ox, double oy, double oz,
+                  double* __restrict__ x, double* __restrict__ y, double* __restrict__ z) {
+    int64_t stride = (int64_t)gridDim.x * kBlock;
+    for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < n; i += stride) {
+        x[i] = __dadd_rn(__dmul_rn((double)X[i], sx), ox);
+        y[i] = __dadd_rn(__dmul_rn((double)Y[i], sy), oy);
+        z[i] = __dadd_rn(__dmul_rn((double)Z[i], sz), oz);
+    }
+}
+}  // namespace upcp
+
 extern "C" {
+
+int upcp_points_from_scaled_int32(const int32_t* d_X, const int32_t* d_Y, const int32_t* d_Z, int64_t n,
+                                  const double* h_scale3, const double* h_offset3,
+                                  double* d_x, double* d_y, double* d_z, void* stream) {
+    if (n < 0 || !h_scale3 || !h_offset3) UPCP_FAIL(UPCP_E_INVALID, "points_from_scaled_int32: bad argument");
+    if (n == 0) return UPCP_OK;
+    upcp::scaled_int_kernel<<<grid_for(n, kBlock), kBlock, 0, (cudaStream_t)stream>>>(
+        d_X, d_Y, d_Z, n, h_scale3[0], h_scale3[1], h_scale3[2], h_offset3[0], h_offset3[1], h_offset3[2], d_x, d_y, d_z);
+    UPCP_LAUNCH_OK();
+    return UPCP_OK;
+}
 
 int upcp_points_aos_to_soa(const double* d_xyz, int64_t n, int ncols,
                            double* d_x, double* d_y, double* d_z, void* stream) {

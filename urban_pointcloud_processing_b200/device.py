@@ -227,6 +227,32 @@ class DeviceTile:
         self._bbox_all = None
         return self
 
+    @classmethod
+    def from_las(cls, las, device=None):
+        """Tile from a LAS object (``laspy.LasData`` or ``utils.las_io.LasData``): the raw int32
+        ``X, Y, Z`` are uploaded (12 B per point) and ``x = X * scale + offset`` is evaluated in
+        fp64 on the device -- bit for bit the host-side scaled view the reference stacks into
+        ``points`` (pipeline.py:123-124)."""
+        lib = _lib.require_cuda()
+        self = cls.__new__(cls)
+        self.device = device if device is not None else current_device()
+        ints = [np.ascontiguousarray(np.asarray(getattr(las, k)), dtype=np.int32) for k in ('X', 'Y', 'Z')]
+        n = int(ints[0].shape[0])
+        self.n, self.ncols = n, 3
+        self.x = torch.empty(n, dtype=torch.float64, device=self.device)
+        self.y = torch.empty(n, dtype=torch.float64, device=self.device)
+        self.z = torch.empty(n, dtype=torch.float64, device=self.device)
+        self.h2d_bytes = n * 12
+        self._bbox_all = None
+        if n:
+            d_ints = [_from_numpy(a).to(self.device, non_blocking=True) for a in ints]
+            scale = (ctypes.c_double * 3)(*[float(v) for v in las.header.scales])
+            offset = (ctypes.c_double * 3)(*[float(v) for v in las.header.offsets])
+            _lib.check(lib.upcp_points_from_scaled_int32(ptr(d_ints[0]), ptr(d_ints[1]), ptr(d_ints[2]), n, scale,
+                                                         offset, ptr(self.x), ptr(self.y), ptr(self.z), stream_ptr()),
+                       'upcp_points_from_scaled_int32')
+        return self
+
     def bbox(self, d_sel=None):
         """(bbox_all[6], bbox_sel[6], n_sel) in fp64 -- one reduction + one small D2H."""
         lib = _lib.load()

@@ -7,8 +7,9 @@ uploads the cloud ONCE, chains every drop-in processor on the device and downloa
 the labels once at the end.  Processors that are not drop-ins (no
 ``_label_mask_device``) are still accepted: the labels are synchronised to the host
 around them and their own ``get_labels`` is called, exactly as the reference does.
-LAS file I/O (``process_file`` / ``process_folder``) needs ``laspy`` and is only
-available when it is installed ("next" row of the scope table)."""
+LAS file I/O (``process_file`` / ``process_folder``): ``laspy`` when installed, the native
+``utils.las_io`` for plain ``.las`` otherwise; with drop-in processors only the raw integer
+coordinates are uploaded and scaled on the device."""
 import logging
 import os
 import pathlib
@@ -130,31 +131,31 @@ class Pipeline:
         return labels
 
     def process_file(self, in_file, out_file=None, mask=None):
-        """Process a single LAS file and save the result as .laz file (needs laspy)."""
+        """Process a single LAS file and save the result (pipeline.py:99-137); ``.laz`` needs laspy."""
         logger.info(f'Processing file {in_file}.')
         start = time.time()
         if not os.path.isfile(in_file):
             logger.error('The input file specified does not exist')
             return None
-        try:
-            import laspy
-        except ImportError as e:  # LAS/LAZ I/O is outside the hot path (scope table, "next")
-            raise ImportError('Pipeline.process_file needs laspy, which is not installed') from e
         if out_file is None:
             out_file = in_file
         tilecode = las_utils.get_tilecode_from_filename(in_file)
-        pointcloud = laspy.read(in_file)
-        points = np.vstack((pointcloud.x, pointcloud.y, pointcloud.z)).T
+        pointcloud = las_utils.read_las(in_file)
         if 'label' not in pointcloud.point_format.extra_dimension_names:
-            labels = np.zeros((len(points),), dtype='uint16')
+            labels = np.zeros((pointcloud.header.point_count,), dtype='uint16')
         else:
-            labels = pointcloud.label
-        labels = self.process_cloud(tilecode, points, labels, mask)
-        if 'label' not in pointcloud.point_format.extra_dimension_names:
-            pointcloud.add_extra_dim(laspy.ExtraBytesParams(name='label', type='uint8',
-                                                            description='Labels'))
-        pointcloud.label = labels
-        pointcloud.write(out_file)
+            labels = np.asarray(pointcloud.label)
+        if all(hasattr(obj, '_apply_device') for obj in self.processors):
+            # device path: raw int32 X, Y, Z up (12 B/pt), coordinates rebuilt in fp64 on the device
+            tile = dev.DeviceTile.from_las(pointcloud)
+            d_labels = dev.upload_labels(labels, tile.device)
+            self.process_tile_device(tilecode, tile, d_labels)
+            labels = np.array(labels, copy=True)
+            dev.download_labels(d_labels, labels)
+        else:
+            points = np.vstack((pointcloud.x, pointcloud.y, pointcloud.z)).T
+            labels = self.process_cloud(tilecode, points, labels, mask)
+        las_utils.label_and_save_las(pointcloud, labels, out_file)
         duration = time.time() - start
         stats = analysis_tools.get_label_stats(labels)
         logger.info('\nSTATISTICS\n' + stats)

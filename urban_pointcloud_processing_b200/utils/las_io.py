@@ -1,0 +1,210 @@
+"""Minimal native LAS reader / writer (uncompressed ``.las``, point formats 0-3 and 6-8).
+
+The reference reads and writes its clouds with ``laspy`` (``las_utils.read_las`` /
+``label_and_save_las``, reference src/upcp/utils/las_utils.py:118-130; ``Pipeline.process_file``,
+pipeline.py:99-137).  ``laspy`` is used when it is installed (it is required for ``.laz``); this
+module covers plain ``.las`` without it and -- the point of the exercise -- exposes the RAW
+integer coordinates, so that the pipeline uploads 12 B per point and rebuilds
+``x = X * scale + offset`` in fp64 on the device (``upcp_points_from_scaled_int32``), bit for bit
+what ``laspy``'s scaled view computes on the host.
+
+Only what the labelling pipeline touches is modelled: header, VLRs (kept verbatim), point
+records (kept verbatim), the scaled coordinates and the ``label`` extra byte.
+"""
+import struct
+
+import numpy as np
+
+_STD_SIZE = {0: 20, 1: 28, 2: 26, 3: 34, 4: 57, 5: 63, 6: 30, 7: 36, 8: 38, 9: 59, 10: 67}
+_EXTRA_BYTES_USER = b'LASF_Spec'
+_EXTRA_BYTES_RECORD = 4
+_EB_SIZES = {1: 1, 2: 1, 3: 2, 4: 2, 5: 4, 6: 4, 7: 8, 8: 8, 9: 4, 10: 8}
+
+
+class LasHeader:
+    def __init__(self):
+        self.version = (1, 2)
+        self.point_format_id = 0
+        self.point_size = 20
+        self.point_count = 0
+        self.scales = np.array([0.001, 0.001, 0.001])
+        self.offsets = np.zeros(3)
+        self.raw = b''                 # header bytes as read (re-used on write)
+        self.header_size = 227
+        self.offset_to_points = 227
+
+
+class _PointFormat:
+    def __init__(self, names):
+        self.extra_dimension_names = list(names)
+
+
+class LasData:
+    """The subset of ``laspy.LasData`` the pipeline uses: ``x y z`` (scaled fp64), ``X Y Z`` (raw
+    int32), ``header``, ``point_format.extra_dimension_names``, ``label``, ``write``."""
+
+    def __init__(self, header, vlrs, records, extra_dims):
+        self.header = header
+        self.vlrs = vlrs                      # list of (user_id, record_id, description, payload)
+        self.records = records                # uint8 [n, point_size]
+        self._extra = extra_dims              # list of (name, numpy dtype, byte offset in record)
+        self.point_format = _PointFormat([e[0] for e in extra_dims])
+
+    def _ints(self, k):
+        return np.ascontiguousarray(self.records[:, 4 * k:4 * k + 4]).view('<i4').ravel()
+
+    X = property(lambda self: self._ints(0))
+    Y = property(lambda self: self._ints(1))
+    Z = property(lambda self: self._ints(2))
+    # laspy's ScaledArrayView: array * scale + offset in float64
+    x = property(lambda self: self.X * self.header.scales[0] + self.header.offsets[0])
+    y = property(lambda self: self.Y * self.header.scales[1] + self.header.offsets[1])
+    z = property(lambda self: self.Z * self.header.scales[2] + self.header.offsets[2])
+
+    def _extra_view(self, name):
+        for nm, dt, off in self._extra:
+            if nm == name:
+                return np.ascontiguousarray(self.records[:, off:off + dt.itemsize]).view(dt).ravel()
+        raise AttributeError(name)
+
+    @property
+    def label(self):
+        return self._extra_view('label')
+
+    @label.setter
+    def label(self, values):
+        values = np.asarray(values)
+        if len(values) != self.header.point_count:
+            raise ValueError('label: wrong length')
+        if 'label' not in self.point_format.extra_dimension_names:
+            self.add_extra_dim('label', np.uint8, 'Labels')
+        for nm, dt, off in self._extra:
+            if nm == 'label':
+                self.records[:, off:off + dt.itemsize] = values.astype(dt).reshape(-1, 1).view(np.uint8)
+
+    def add_extra_dim(self, name, dtype=np.uint8, description=''):
+        dt = np.dtype(dtype).newbyteorder('<')
+        n = self.records.shape[0]
+        off = self.records.shape[1]
+        self.records = np.concatenate([self.records, np.zeros((n, dt.itemsize), dtype=np.uint8)], axis=1)
+        self._extra.append((name, dt, off))
+        self.point_format.extra_dimension_names.append(name)
+        self.header.point_size = self.records.shape[1]
+        code = {np.dtype('u1'): 1, np.dtype('i1'): 2, np.dtype('<u2'): 3, np.dtype('<i2'): 4, np.dtype('<u4'): 5,
+                np.dtype('<i4'): 6, np.dtype('<u8'): 7, np.dtype('<i8'): 8, np.dtype('<f4'): 9, np.dtype('<f8'): 10}[dt]
+        desc = bytearray(192)
+        desc[2] = code
+        desc[4:4 + min(len(name), 32)] = name.encode()[:32]
+        desc[160:160 + min(len(description), 32)] = description.encode()[:32]
+        for i, v in enumerate(self.vlrs):
+            if v[0] == _EXTRA_BYTES_USER and v[1] == _EXTRA_BYTES_RECORD:
+                self.vlrs[i] = (v[0], v[1], v[2], v[3] + bytes(desc))
+                return
+        self.vlrs.append((_EXTRA_BYTES_USER, _EXTRA_BYTES_RECORD, b'Extra bytes', bytes(desc)))
+
+    def write(self, path):
+        h = self.header
+        raw = bytearray(h.raw[:h.header_size])
+        vlr_blob = b''
+        for user, rec, desc, payload in self.vlrs:
+            vlr_blob += struct.pack('<H16sHH32s', 0, user.ljust(16, b'\0'), rec, len(payload), desc.ljust(32, b'\0')) + payload
+        offset_to_points = h.header_size + len(vlr_blob)
+        struct.pack_into('<I', raw, 96, offset_to_points)
+        struct.pack_into('<I', raw, 100, len(self.vlrs))
+        struct.pack_into('<H', raw, 105, self.records.shape[1])
+        with open(path, 'wb') as f:
+            f.write(bytes(raw))
+            f.write(vlr_blob)
+            f.write(np.ascontiguousarray(self.records).tobytes())
+
+
+def read(path):
+    """Read an uncompressed LAS file."""
+    with open(path, 'rb') as f:
+        data = f.read()
+    if data[:4] != b'LASF':
+        raise ValueError(f'{path}: not a LAS file')
+    h = LasHeader()
+    h.version = (data[24], data[25])
+    h.header_size = struct.unpack_from('<H', data, 94)[0]
+    h.offset_to_points = struct.unpack_from('<I', data, 96)[0]
+    n_vlrs = struct.unpack_from('<I', data, 100)[0]
+    fmt = data[104]
+    if fmt & 0x80 or fmt & 0x40:
+        raise ValueError(f'{path}: compressed (LAZ) point data needs laspy[lazrs]')
+    h.point_format_id = fmt & 0x3f
+    h.point_size = struct.unpack_from('<H', data, 105)[0]
+    legacy_count = struct.unpack_from('<I', data, 107)[0]
+    h.scales = np.array(struct.unpack_from('<3d', data, 131))
+    h.offsets = np.array(struct.unpack_from('<3d', data, 155))
+    h.point_count = legacy_count
+    if h.version >= (1, 4) and h.header_size >= 375:
+        count64 = struct.unpack_from('<Q', data, 247)[0]
+        if count64:
+            h.point_count = count64
+    h.raw = data[:h.header_size]
+    vlrs = []
+    pos = h.header_size
+    for _ in range(n_vlrs):
+        _, user, rec, length, desc = struct.unpack_from('<H16sHH32s', data, pos)
+        payload = data[pos + 54:pos + 54 + length]
+        vlrs.append((user.rstrip(b'\0'), rec, desc.rstrip(b'\0'), payload))
+        pos += 54 + length
+    if h.point_format_id not in _STD_SIZE:
+        raise ValueError(f'{path}: unsupported point format {h.point_format_id}')
+    std = _STD_SIZE[h.point_format_id]
+    extra = []
+    off = std
+    for user, rec, _, payload in vlrs:
+        if user == _EXTRA_BYTES_USER and rec == _EXTRA_BYTES_RECORD:
+            for k in range(len(payload) // 192):
+                d = payload[192 * k:192 * (k + 1)]
+                code = d[2]
+                name = d[4:36].split(b'\0')[0].decode(errors='replace')
+                if code == 0:
+                    size = d[3]
+                    dt = np.dtype(('V', size))
+                else:
+                    dt = {1: 'u1', 2: 'i1', 3: '<u2', 4: '<i2', 5: '<u4', 6: '<i4', 7: '<u8', 8: '<i8', 9: '<f4',
+                          10: '<f8'}.get(code)
+                    if dt is None:
+                        break
+                    dt = np.dtype(dt)
+                extra.append((name, dt, off))
+                off += dt.itemsize
+    n = int(h.point_count)
+    body = np.frombuffer(data, dtype=np.uint8, count=n * h.point_size, offset=h.offset_to_points)
+    records = body.reshape(n, h.point_size).copy()
+    extra = [e for e in extra if e[2] + e[1].itemsize <= h.point_size and e[1].kind != 'V']
+    return LasData(h, vlrs, records, extra)
+
+
+def create(points_int, scales, offsets, point_format_id=1):
+    """A new LAS 1.2 cloud from raw integer coordinates (tests / synthetic data)."""
+    points_int = np.asarray(points_int, dtype='<i4')
+    n = len(points_int)
+    h = LasHeader()
+    h.point_format_id = point_format_id
+    h.point_size = _STD_SIZE[point_format_id]
+    h.point_count = n
+    h.scales = np.asarray(scales, dtype=np.float64)
+    h.offsets = np.asarray(offsets, dtype=np.float64)
+    raw = bytearray(227)
+    raw[0:4] = b'LASF'
+    raw[24], raw[25] = 1, 2
+    raw[26:26 + 9] = b'upcp-b200'
+    struct.pack_into('<H', raw, 94, 227)
+    struct.pack_into('<I', raw, 96, 227)
+    raw[104] = point_format_id
+    struct.pack_into('<H', raw, 105, h.point_size)
+    struct.pack_into('<I', raw, 107, n)
+    struct.pack_into('<3d', raw, 131, *h.scales)
+    struct.pack_into('<3d', raw, 155, *h.offsets)
+    if n:
+        xyz = points_int * h.scales + h.offsets
+        mx, mn = xyz.max(axis=0), xyz.min(axis=0)
+        struct.pack_into('<6d', raw, 179, mx[0], mn[0], mx[1], mn[1], mx[2], mn[2])
+    h.raw = bytes(raw)
+    records = np.zeros((n, h.point_size), dtype=np.uint8)
+    records[:, 0:12] = np.ascontiguousarray(points_int).view(np.uint8).reshape(n, 12)
+    return LasData(h, [], records, [])

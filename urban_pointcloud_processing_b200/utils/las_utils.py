@@ -1,8 +1,10 @@
-"""Tile-code helpers (host side; mirrors the tile-code part of
-``upcp.utils.las_utils``, reference src/upcp/utils/las_utils.py:12-53).
-LAS/LAZ I/O is the "next" row of the scope table and is not provided here."""
+"""Tile-code helpers and LAS I/O (host side; mirrors ``upcp.utils.las_utils``, reference
+src/upcp/utils/las_utils.py:12-53,118-130).  ``laspy`` is used when it is installed (required for
+``.laz``); plain ``.las`` files are handled natively by ``las_io``."""
 import pathlib
 import re
+
+from . import las_io
 
 
 def get_tilecode_from_filename(filename):
@@ -27,3 +29,30 @@ def get_bbox_from_tile_code(tile_code, padding=0, width=50, height=50):
     y_min = int(tile_split[1]) * 50
     return ((x_min - padding, y_min + height + padding),
             (x_min + height + padding, y_min - padding))
+
+
+def read_las(las_file):
+    """Read a las file and return the las object (las_utils.py:118-120)."""
+    try:
+        import laspy
+    except ImportError:
+        if str(las_file).lower().endswith('.laz'):
+            raise ImportError('reading .laz needs laspy[lazrs], which is not installed') from None
+        return las_io.read(las_file)
+    return laspy.read(las_file)
+
+
+def label_and_save_las(las, labels, outfile):
+    """Label a las file using the provided class labels and save to outfile (las_utils.py:123-130)."""
+    assert len(labels) == las.header.point_count
+    if isinstance(las, las_io.LasData):
+        if str(outfile).lower().endswith('.laz'):
+            raise ImportError('writing .laz needs laspy[lazrs], which is not installed')
+        las.label = labels          # adds the uint8 "label" extra dimension when missing
+        las.write(outfile)
+        return
+    import laspy
+    if 'label' not in las.point_format.extra_dimension_names:
+        las.add_extra_dim(laspy.ExtraBytesParams(name='label', type='uint8', description='Labels'))
+    las.label = labels
+    las.write(outfile)
