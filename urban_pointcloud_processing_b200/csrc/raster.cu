@@ -22,13 +22,12 @@ struct RasterParams {
 
 template <bool SMEM_BINS>
 __device__ __forceinline__ double raster_value(const RasterParams& r, const double* sbx,
-                                               const double* sby, double px, double py) {
+                                               const double* sby, double inv_step_x, double inv_step_y,
+                                               double px, double py) {
     const double* bx = SMEM_BINS ? sbx : r.bin_x;
     const double* by = SMEM_BINS ? sby : r.bin_y;
-    // arithmetic guess (uniform-step estimate), then exact fix-up against the same
-    // fp64 bin edges numpy compares with
-    double inv_step_x = r.nx >= 2 ? 1.0 / (bx[1] - bx[0]) : 0.0;
-    double inv_step_y = r.ny >= 2 ? 1.0 / (by[0] - by[1]) : 0.0;
+    // arithmetic guess (uniform-step estimate, steps inverted once per thread), then exact fix-up
+    // against the same fp64 bin edges numpy compares with
     int gx = guess_index(px, bx[0], inv_step_x, r.nx);
     int gy = (py == py) ? guess_index(-py, -by[0], inv_step_y, r.ny) : -1;
     int ix = digitize_asc_wrap(bx, r.nx, px, gx);
@@ -51,19 +50,23 @@ raster_kernel(const double* __restrict__ x, const double* __restrict__ y,
         for (int i = threadIdx.x; i < r.ny; i += kBlock) sby[i] = r.bin_y[i];
         __syncthreads();
     }
+    const double* bx = SMEM_BINS ? sbx : r.bin_x;
+    const double* by = SMEM_BINS ? sby : r.bin_y;
+    const double inv_step_x = r.nx >= 2 ? 1.0 / (bx[1] - bx[0]) : 0.0;
+    const double inv_step_y = r.ny >= 2 ? 1.0 / (by[0] - by[1]) : 0.0;
     int64_t stride = (int64_t)gridDim.x * kBlock;
     for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < n; i += stride) {
         bool s = sel ? (sel[i] != 0) : true;
         if (CLASSIFY) {
             bool res = false;
             if (s) {
-                double v = raster_value<SMEM_BINS>(r, sbx, sby, x[i], y[i]);
+                double v = raster_value<SMEM_BINS>(r, sbx, sby, inv_step_x, inv_step_y, x[i], y[i]);
                 res = classify_height(mode, z[i], v, a, b);
             }
             if (out_mask) out_mask[i] = res ? 1 : 0;
             if (labels && res) labels[i] = assign;
         } else {
-            if (s) out_val[i] = raster_value<SMEM_BINS>(r, sbx, sby, x[i], y[i]);
+            if (s) out_val[i] = raster_value<SMEM_BINS>(r, sbx, sby, inv_step_x, inv_step_y, x[i], y[i]);
         }
     }
 }
