@@ -388,6 +388,10 @@ struct SelectArgs {
     const uint32_t* todo_cnt;      // device count of todo_idx
     uint32_t* out_pos;             // [kRow][m] sorted positions of the k nearest, ascending
     uint8_t* out_cnt;              // [m] number of valid entries of the row
+    // What the consumers use: the k_row nearest (kNN row, covariance) and, of the k nearest, those
+    // within radius2 (hybrid-search normals).  Beyond BOTH the k_row-th distance and the radius
+    // nothing matters, so the walk may stop there instead of at the k-th distance.
+    int k_row; double radius2;
 };
 
 __device__ __forceinline__ uint32_t warp_incl_scan_u32(uint32_t v, int lane) {
@@ -472,9 +476,11 @@ knn_select_kernel(SelectArgs a) {
         Nb mine; mine.d = inf; mine.c = kFull; mine.p = 0;   // lane j: j-th nearest so far
         double kth_d = inf; uint32_t kth_c = kFull;          // the K-th entry (lane K-1), warp-uniform
 
+        double need_d = inf;                                  // min(k-th, max(k_row-th, radius^2)): see SelectArgs
         auto refresh_kth = [&]() {
             kth_d = __shfl_sync(kFull, mine.d, K - 1);
             kth_c = __shfl_sync(kFull, mine.c, K - 1);
+            need_d = fmin(kth_d, fmax(__shfl_sync(kFull, mine.d, a.k_row - 1), a.radius2));
         };
 
         // Stream the points of up to 32 ranges (one per lane: first, cnt) past the query.
@@ -563,12 +569,12 @@ knn_select_kernel(SelectArgs a) {
                     {
                         const double gy = axis_gap(qy, g.oy, yy, cy), gz = axis_gap(qz, g.oz, zz, cz);
                         const double lb_yz = (gy * gy + gz * gz) * (1.0 - 1e-9);
-                        if (!(lb_yz > kth_d)) {
+                        if (!(lb_yz > need_d)) {
                             const uint32_t row = ((uint32_t)zz * (uint32_t)g.ny + (uint32_t)yy) * (uint32_t)g.nx;
                             // cells farther than this along x cannot matter any more
                             int hw = Rn;
-                            if (kth_d < inf) {
-                                const double h = (sqrt(kth_d - lb_yz) + g.slack) * g.inv_cell + 2.0;
+                            if (need_d < inf) {
+                                const double h = (sqrt(need_d - lb_yz) + g.slack) * g.inv_cell + 2.0;
                                 if (h < (double)hw) hw = (int)h;
                             }
                             const int xa = max(cx - hw, 0), xb = min(cx + hw, g.nx - 1);
@@ -600,11 +606,11 @@ knn_select_kernel(SelectArgs a) {
             if (open_z0) reach = fmin(reach, qz - (g.oz + (double)(cz - Rdone) * g.cell));
             if (open_z1) reach = fmin(reach, (g.oz + (double)(cz + Rdone + 1) * g.cell) - qz);
             reach -= g.slack;
-            if (kth_d < inf && reach > 0.0 && kth_d < reach * reach * (1.0 - 1e-9)) break;
+            if (need_d < inf && reach > 0.0 && need_d < reach * reach * (1.0 - 1e-9)) break;
             // ---- next radius
-            if (kth_d < inf) {
-                // reach(R) >= R * cell - slack: this radius certifies the current k-th distance
-                const double need = (sqrt(kth_d) + 2.0 * g.slack) * g.inv_cell;
+            if (need_d < inf) {
+                // reach(R) >= R * cell - slack: this radius certifies what is still needed
+                const double need = (sqrt(need_d) + 2.0 * g.slack) * g.inv_cell;
                 Rn = need < (double)Rmax ? (int)need + 1 : Rmax;
             } else {
                 const int found = __popc(__ballot_sync(kFull, mine.d < inf));
@@ -898,6 +904,7 @@ static int knn_impl(const double* d_x, const double* d_y, const double* d_z, int
     SelectArgs a;
     a.qpts = spts; a.spts = spts; a.cell_first = cell_first; a.g = g; a.m = m; a.k = kh;
     a.todo_idx = todo_last_idx; a.todo_cnt = n_todo_last; a.out_pos = nb_pos; a.out_cnt = nb_cnt;
+    a.k_row = knn < kh ? knn : kh; a.radius2 = radius * radius;
     int coarse = 2;
     if (const char* env = getenv("UPCP_KNN_COARSE")) { int v = atoi(env); if (v >= 1 && v <= 16) coarse = v; }   // tuning knobs
     if (h_last > 0 && coarse > 1 && (int64_t)h_last * 200 >= m) {
