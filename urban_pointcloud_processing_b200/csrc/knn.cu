@@ -187,6 +187,7 @@ struct BlockArgs {
     const uint32_t* q_idx; const uint32_t* q_cnt;      // queries (sorted positions) or NULL = all m
     uint32_t* out_pos; uint8_t* out_cnt;               // rows [kRow][m], counts [m]
     uint8_t* todo;                                     // [m] 1 = not served by this tier
+    int k_row; double radius2;                         // kNN row length, squared normal-estimation radius
 };
 
 // One lane per query; see the header comment.  The per-lane histogram is kBuckets counters in
@@ -240,7 +241,7 @@ knn_block_kernel(BlockArgs a) {
         const int x0 = max(cx - R, 0), x1 = min(cx + R, g.nx - 1);
         bool active = valid && reach > 0.0;
 
-        // cheap certificate first: a block with fewer than K points cannot serve the query
+        // cheap certificate first: a block with fewer than k_row points cannot serve the query
         // (2 prefix lookups per row instead of a wasted counting pass)
         uint32_t total = 0;
 #pragma unroll 1
@@ -255,7 +256,7 @@ knn_block_kernel(BlockArgs a) {
             }
         }
         // (u16 counters: a block with more candidates than they can count goes to the next tier)
-        if (total < (uint32_t)K || total > 60000u) active = false;
+        if (total < (uint32_t)a.k_row || total > 60000u) active = false;
         if (!__any_sync(kFull, active)) {
             if (valid) a.todo[q] = 1;
             continue;
@@ -275,7 +276,7 @@ knn_block_kernel(BlockArgs a) {
         if (!fp32_ok(tau)) active = false;
         float scale = (float)((double)kBuckets / tau);
 
-        int bstar = -1;            // last (partially) kept bucket = b* + 1
+        float tkeep = 0.0f;        // pass B keeps the candidates with d2f * scale below this
         bool counting = active;    // this lane takes part in the current counting pass
         for (int attempt = 0; attempt < 2; ++attempt) {
             if (!__any_sync(kFull, counting)) break;
@@ -312,22 +313,33 @@ knn_block_kernel(BlockArgs a) {
                     }
                 }
             }
-            // ---- select: b* = first bucket whose cumulative count reaches K; the counters become
-            // exclusive offsets so that pass B places the kept candidates bucket-ordered
+            // ---- select.  What the consumers use is the k_row nearest (kNN row, covariance) and, of the
+            // K nearest, those within the normal radius.  The block certifies that when
+            //   (a) the K-th candidate falls below the last bucket (everything needed is nearer), or
+            //   (b) the k_row-th does AND the radius lies inside the histogram range (then every point
+            //       within the radius is in the block, and there are fewer than K of them);
+            // pass B keeps the candidates below the smaller of the two limits, plus the fp32 margin.
+            // The counters become exclusive offsets so that pass B places the kept candidates bucket-ordered.
             if (counting) {
                 uint32_t cum = 0;
-                int bs = -1;
+                int bK = -1, bk = -1;           // first bucket whose cumulative count reaches K / k_row
 #pragma unroll 1
                 for (int b = 0; b < kBuckets; ++b) {
                     const uint32_t hb = HIST(b);
                     HIST(b) = (uint16_t)cum;
-                    const bool reached = cum >= (uint32_t)K;        // K reached by the buckets before b
                     cum += hb;
-                    if (reached) { bs = b; break; }
+                    if (bk < 0 && cum >= (uint32_t)a.k_row) bk = b;
+                    if (bK < 0 && cum >= (uint32_t)K) bK = b;
                 }
-                // bs = b* + 1 <= kBuckets - 1 certifies the k nearest (see header); otherwise K was only
-                // reached in the last bucket or not at all: retry with the full range, then give up
-                if (bs >= 0) { bstar = bs; counting = false; }
+                const float rb = (float)(a.radius2 * (double)scale);           // the radius in bucket units
+                float lim = -1.0f;
+                if (bK >= 0 && bK <= kBuckets - 2) lim = (float)bK + 1.25f;
+                if (bk >= 0 && bk <= kBuckets - 2 && rb + 0.25f <= (float)kBuckets) {
+                    const float alt = fmaxf((float)bk + 1.25f, rb + 0.25f);
+                    if (lim < 0.0f || alt < lim) lim = alt;
+                }
+                // otherwise: retry with the full range, then give up
+                if (lim >= 0.0f) { tkeep = lim; counting = false; }
                 else if (attempt == 0 && tau < tau_full && fp32_ok(tau_full)) {
                     tau = tau_full;
                     scale = (float)((double)kBuckets / tau);
@@ -336,8 +348,8 @@ knn_block_kernel(BlockArgs a) {
         }
         // ---- pass B: append the candidates of buckets <= b* (+ a quarter bucket) to the row
         bool overflow = false;
+        uint32_t kept = 0;
         if (__any_sync(kFull, active)) {
-            const float tkeep = (float)bstar + 0.25f;
 #pragma unroll 1
             for (int dz = -R; dz <= R; ++dz) {
 #pragma unroll 1
@@ -353,10 +365,11 @@ knn_block_kernel(BlockArgs a) {
                         const float4 c0 = __ldg(a.spf + p);
                         const float ax = c0.x - qf.x, ay = c0.y - qf.y, az = c0.z - qf.z;
                         const float t0 = fmaf(az, az, fmaf(ay, ay, ax * ax)) * scale;
-                        if (t0 < tkeep) {                                   // bucket <= b* + 1
+                        if (t0 < tkeep) {
                             const int b0 = __float2int_rz(t0);
                             const uint32_t slot = HIST(b0);
                             HIST(b0) = (uint16_t)(slot + 1);
+                            ++kept;
                             if (slot < (uint32_t)kRow) a.out_pos[(size_t)slot * a.m + q] = p;
                             else overflow = true;
                         }
@@ -366,10 +379,7 @@ knn_block_kernel(BlockArgs a) {
         }
         if (valid) {
             bool served = false;
-            if (active) {
-                const uint32_t kept = HIST(bstar);      // running counter of the last kept bucket
-                if (!overflow && kept <= (uint32_t)kRow) { a.out_cnt[q] = (uint8_t)kept; served = true; }
-            }
+            if (active && !overflow && kept <= (uint32_t)kRow) { a.out_cnt[q] = (uint8_t)kept; served = true; }
             a.todo[q] = served ? 0 : 1;
         }
     }
@@ -863,6 +873,7 @@ static int knn_impl(const double* d_x, const double* d_y, const double* d_z, int
     BlockArgs ba;
     ba.spts = spts; ba.spf = spf; ba.cell_first = cell_first; ba.g = g; ba.m = m; ba.k = kh;
     ba.q_idx = nullptr; ba.q_cnt = nullptr; ba.out_pos = nb_pos; ba.out_cnt = nb_cnt; ba.todo = todo[0];
+    ba.k_row = knn < kh ? knn : kh; ba.radius2 = radius * radius;
     // the filter passes live on L1 hits (each candidate is read by ~150 queries, twice): keep the
     // shared-memory carve-out at what the resident CTAs need, the rest of the 256 KB stays L1
     UPCP_CUDA_OK(cudaFuncSetAttribute(knn_block_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, 40));

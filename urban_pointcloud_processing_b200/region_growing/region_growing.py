@@ -27,12 +27,15 @@ CURVATURE_TOL = 1e-9
 
 def default_cell_size(bbox_sel, m, radius):
     """Fine-cell edge of the search grid: aim at ~16 points per occupied cell of a surface-like
-    cloud (urban LiDAR covers roughly 3x its footprint area), bounded by the search radius."""
+    cloud (urban LiDAR covers roughly 3x its footprint area), bounded by the search radius.  Near
+    the upper bound the cell snaps to 0.525 x radius: a 5^3-cell block then always contains the
+    whole normal-estimation ball, which lets the second block tier certify sparse queries."""
     ex = max(float(bbox_sel[3] - bbox_sel[0]), 1e-3)
     ey = max(float(bbox_sel[4] - bbox_sel[1]), 1e-3)
     c = float(np.sqrt(48.0 * ex * ey / max(int(m), 1)))
     r = max(float(radius), 1e-3)
-    return min(max(c, r / 8.0), r / 2.0)
+    c = min(max(c, r / 8.0), 0.525 * r)
+    return 0.525 * r if c > 0.45 * r else c
 
 
 def knn_normals_device(tile, d_sel, m, bbox_sel, knn, max_nn, radius, cell_size=None,
