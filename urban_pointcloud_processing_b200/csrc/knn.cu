@@ -17,21 +17,25 @@
 //     included), so the points of cells [x0, x1] of a grid row are
 //     cell_first[row + x0] .. cell_first[row + x1 + 1]: TWO loads per row, no hashing, no
 //     tree.  With 180 GB of HBM the table (4 B per cell, a few cells per point) is cheap.
+// What has to be found per query is what the consumers read: the `knn` nearest (kNN row, curvature
+// covariance) and those of the `max_nn` nearest that lie within `radius` (hybrid-search normal).
+// Beyond BOTH the knn-th distance and the radius nothing matters, so every tier certifies
+// "the max_nn nearest are known" OR "the knn nearest and everything within the radius are known".
 // Search, three exact tiers:
 //   1. knn_block_kernel<1>: one LANE per query, candidates = the query's own 3x3x3 cell block
 //      (9 contiguous row ranges).  Selection is a two-pass radial histogram: pass A counts the
-//      candidates into 64 equal-width buckets of squared distance over [0, reach^2), reach = the
-//      distance from the query to the nearest face of its block (everything outside the block
-//      is farther); b* = first bucket whose cumulative count reaches k; pass B appends the
-//      candidates of buckets <= b* (plus a quarter bucket of margin) to the query's row.  Both
-//      passes only FILTER, so they run in fp32 on origin-relative coordinates; the margin is
-//      at least ten times the fp32 error bound (checked per query), so the kept set provably
-//      contains the k nearest under the exact fp64 ordering.  If k is not reached before the
-//      last bucket the block cannot certify the answer and the query moves on to
+//      candidates into 32 equal-width buckets of squared distance over [0, tau), tau <= reach^2,
+//      reach = the distance from the query to the nearest face of its block (everything outside
+//      the block is farther); the cumulative counts give the bucket below which everything needed
+//      lies; pass B appends the candidates below it (plus a quarter bucket of margin) to the
+//      query's row.  Both passes only FILTER, so they run in fp32 on origin-relative coordinates;
+//      the margin is at least two rigorous fp32 error bounds (checked per query), so the kept set
+//      provably contains what is needed under the exact fp64 ordering.  If the needed candidates
+//      do not end below the last bucket the block cannot certify the answer and the query moves on to
 //   2. knn_block_kernel<2>: the same over the 5x5x5 block (25 row ranges), then
-//   3. knn_select_kernel: one WARP per query, shell-by-shell walk of the dense grid with a
-//      register-resident sorted top-k list (bitonic merge / shuffle insert) in fp64, until the
-//      k-th distance is smaller than the distance to the unexplored region.
+//   3. knn_select_kernel: one WARP per query, thick shells of grid rows (on a 2x coarser second
+//      grid when this tier has much to do) with a register-resident sorted top-k list (bitonic
+//      merge / shuffle insert) in fp64, until what is still needed is nearer than the unexplored region.
 // Epilogue (knn_epilogue_kernel): one thread per query orders its row exactly by
 // (fp64 d2, compact id), folds it in order into the Open3D cumulant covariances /
 // FastEigen3x3 normal and writes the kNN row.
@@ -868,7 +872,7 @@ static int knn_impl(const double* d_x, const double* d_y, const double* d_z, int
     int kh = knn > max_nn ? knn : max_nn;
     if ((int64_t)kh > m) kh = (int)m;
     prof_begin(UPCP_PROF_KNN, st);
-    // tiers 1..4: lane per query over its (2R+1)^3 cell block; each tier takes the queries the
+    // block tiers: lane per query over its (2R+1)^3 cell block; each tier takes the queries the
     // previous one could not certify
     BlockArgs ba;
     ba.spts = spts; ba.spf = spf; ba.cell_first = cell_first; ba.g = g; ba.m = m; ba.k = kh;
