@@ -290,6 +290,10 @@ cc_output_kernel(const uint32_t* __restrict__ sel_idx, const uint32_t* __restric
     }
 }
 
+__global__ void cc_set_info_kernel(long long* __restrict__ info, long long m) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) info[0] = m;
+}
+
 template <typename K>
 static int lcc_impl(const double* d_x, const double* d_y, const double* d_z, int64_t n,
                     const uint8_t* d_sel, OctreeParams op, int32_t min_size,
@@ -316,11 +320,8 @@ static int lcc_impl(const double* d_x, const double* d_y, const double* d_z, int
         UPCP_CUDA_OK(cudaStreamSynchronize(st));
         m = hm;
     }
-    {
-        long long hm = m;
-        UPCP_CUDA_OK(cudaMemcpyAsync(d_info, &hm, sizeof(long long), cudaMemcpyHostToDevice, st));
-        UPCP_CUDA_OK(cudaStreamSynchronize(st));   // hm is a stack variable
-    }
+    cc_set_info_kernel<<<1, 32, 0, st>>>((long long*)d_info, (long long)m);      // d_info[0] = m, no host round trip
+    UPCP_LAUNCH_OK();
     if (m == 0) return UPCP_OK;
 
     K* keys_a = ws.take<K>((size_t)m);

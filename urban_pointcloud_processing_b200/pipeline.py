@@ -71,11 +71,11 @@ class Pipeline:
             if sync_timings:
                 torch.cuda.synchronize()
                 start = time.time()
-            d_mask = dev.mask_build(d_labels, None, base=False, eq=(0,))
-            if hasattr(obj, '_apply_device'):
-                obj._apply_device(tile, d_labels, d_mask, tilecode)
-            else:
+            if not hasattr(obj, '_apply_device'):
                 raise TypeError(f'{type(obj).__name__} is not a device drop-in processor')
+            # mask = labels == 0 (pipeline.py:90); processors that overwrite it anyway do not get one built
+            d_mask = None if getattr(obj, 'ignores_mask', False) else dev.mask_build(d_labels, None, base=False, eq=(0,))
+            obj._apply_device(tile, d_labels, d_mask, tilecode)
             if sync_timings:
                 torch.cuda.synchronize()
                 self.last_timings.append((type(obj).__name__, time.time() - start))

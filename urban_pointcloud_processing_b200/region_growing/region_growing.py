@@ -270,6 +270,8 @@ class RegionGrowing(AbstractProcessor):
     grow_region_knn=15, grow_region_radius=0.2
     """
 
+    ignores_mask = True        # _set_mask (region_growing.py:34-49) replaces the incoming mask
+
     def __init__(self, label, exclude_labels=[], threshold_angle=20, threshold_curve=1.0, max_nn=30,
                  grow_region_knn=15, grow_region_radius=0.2):
         super().__init__(label)
