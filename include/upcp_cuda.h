@@ -270,7 +270,8 @@ int upcp_knn_normals(const double* d_x, const double* d_y, const double* d_z, in
 int upcp_knn_normals_sorted(const double* d_x, const double* d_y, const double* d_z, int64_t n,
                             const uint8_t* d_sel, int64_t m, const double* h_bbox_sel6,
                             int knn, int max_nn, double radius, double cell_size,
-                            int32_t* d_knn, double* d_normals, double* d_cov /* may be NULL */,
+                            int32_t* d_knn, double* d_normals,
+                            double* d_cov /* may be NULL; with d_seed_flag given only the rows with flag 2 are written */,
                             double threshold_curve, uint8_t* d_seed_flag /* may be NULL */,
                             uint32_t* d_order, void* d_ws, size_t ws_bytes, void* stream);
 /* d_out[s] = d_full[d_order[s]], s < m          (region_growing.py:80-84: seeds of the masked cloud) */

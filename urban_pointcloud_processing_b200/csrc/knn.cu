@@ -796,8 +796,7 @@ knn_epilogue_kernel(EpilogueArgs a) {
         if (a.out_cov || a.out_curv || a.out_flag) {
             double cov6[6];
             cov_cum.finish(kk > 0 ? kk : 1, cov6);
-            if (a.out_cov)
-                for (int t = 0; t < 6; ++t) a.out_cov[(size_t)cid * 6 + t] = cov6[t];
+            bool want_cov = a.out_cov != nullptr && !a.sorted_out;      // sorted space: only where the flag is undecided
             if (a.out_curv || a.out_flag) {
                 double ev[3];
                 fast_eigen3x3(cov6, ev);
@@ -813,8 +812,13 @@ knn_epilogue_kernel(EpilogueArgs a) {
                     const bool below = fin && r0 < a.thr_curve - tol && r1 < a.thr_curve - tol && r2 < a.thr_curve - tol;
                     const bool above = fin && r0 >= a.thr_curve + tol && r1 >= a.thr_curve + tol && r2 >= a.thr_curve + tol;
                     a.out_flag[cid] = below ? 1 : (above ? 0 : 2);
+                    if (!below && !above) want_cov = a.out_cov != nullptr;
                 }
+            } else {
+                want_cov = a.out_cov != nullptr;
             }
+            if (want_cov)
+                for (int t = 0; t < 6; ++t) a.out_cov[(size_t)cid * 6 + t] = cov6[t];
         }
     }
 }
