@@ -87,7 +87,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(['nvidia-smi', f'--id={self.index}', f'--query-gpu={self.FIELDS}',
-                                          '--format=csv,noheader,nounits', '-lms', '200'],
+                                          '--format=csv,noheader,nounits', '-lms', '25'],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -95,7 +95,12 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.perf_counter(), line.strip()))
+
+    def window(self, t0, t1):
+        """Only the samples taken between t0 and t1 (perf_counter) count: the sampler is started
+        before the warm-up so that nvidia-smi is already streaming when the timed region begins."""
+        self.t0, self.t1 = t0, t1
 
     def stop(self):
         if self.proc is not None:
@@ -105,7 +110,10 @@ class ClockSampler:
             except Exception:
                 self.proc.kill()
         sm, smax, reasons = [], [], set()
-        for line in self.lines:
+        t0, t1 = getattr(self, 't0', None), getattr(self, 't1', None)
+        for stamp, line in self.lines:
+            if t0 is not None and not (t0 <= stamp <= t1):
+                continue
             parts = [p.strip() for p in line.split(',')]
             if len(parts) < 6:
                 continue
@@ -208,7 +216,7 @@ def run_reference(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--points', type=int, default=20_000_000)
     ap.add_argument('--impl', default='b200')
@@ -301,18 +309,22 @@ def main():
         barrier()
         return float(t[0]), float(t[1]), out
 
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
     for _ in range(warmup):
         hist = device_step()
     torch.cuda.synchronize()
 
     # ---- timed region: device-resident pipeline
     _lib.prof_enable(True)
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     launches0 = _lib.launch_count()
+    t_begin = time.perf_counter()
     ms_dev, wall_dev, hist = timed(device_step, args.steps)
+    t_end = time.perf_counter()
     launches = _lib.launch_count() - launches0
+    if rank == 0:
+        sampler.window(t_begin, t_end)
     clocks = sampler.stop() if rank == 0 else None
     prof = _lib.prof_read()
     _lib.prof_enable(False)
