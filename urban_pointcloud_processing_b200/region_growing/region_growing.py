@@ -161,11 +161,9 @@ def resolve_seed_flags(d_flag, d_cov, threshold_curve):
     if n_host == 0:
         return d_flag, 0
     c = d_cov[idx].cpu().numpy()
-    n_thr = max(1, min(os.cpu_count() or 1, 16, n_host // 256))
+    n_thr = max(1, min(_host_threads(), n_host // 256))
     if n_thr > 1:
-        from concurrent.futures import ThreadPoolExecutor
-        with ThreadPoolExecutor(n_thr) as ex:
-            parts = list(ex.map(lambda a: _host_curvature(a, threshold_curve), np.array_split(c, n_thr)))
+        parts = list(_pool().map(lambda a: _host_curvature(a, threshold_curve), np.array_split(c, n_thr)))
         res = np.concatenate(parts)
     else:
         res = _host_curvature(c, threshold_curve)
@@ -190,11 +188,17 @@ def region_grow_device(d_knn, d_normals, d_seed, d_can_seed, threshold_angle):
 _POOL = None
 
 
+def _host_threads():
+    """Host threads for the LAPACK resolution: the cores of this box divided by the ranks sharing it."""
+    ranks = max(1, int(os.environ.get('LOCAL_WORLD_SIZE', '1') or 1))
+    return max(1, min((os.cpu_count() or 1) // ranks, 16))
+
+
 def _pool():
     global _POOL
     if _POOL is None:
         from concurrent.futures import ThreadPoolExecutor
-        _POOL = ThreadPoolExecutor(max(1, min(os.cpu_count() or 1, 16)))
+        _POOL = ThreadPoolExecutor(_host_threads())
     return _POOL
 
 
@@ -223,7 +227,7 @@ def region_grow_overlapped(d_knn, d_normals, d_seed, d_flag, d_cov, threshold_cu
                                           dev.stream_ptr()), 'upcp_region_grow_begin')
     # ---- host resolution of the undecided flags, overlapped with the kernels queued above
     if n_host:
-        n_thr = max(1, min(os.cpu_count() or 1, 16, n_host // 256))
+        n_thr = max(1, min(_host_threads(), n_host // 256))
         if n_thr > 1:
             parts = list(_pool().map(lambda a: _host_curvature(a, threshold_curve), np.array_split(c, n_thr)))
             res = np.concatenate(parts)
