@@ -15,7 +15,10 @@ one NCCL all_gather after the timed steps.
   e2e    the same pipeline through the reference-facing plugin API
          (Pipeline.process_cloud(tilecode, points, labels) with numpy arrays living in
          PINNED host memory): H2D of the points + labels and D2H of the labels inside the
-         timed region.
+         timed region.  Two public entry points are timed: `Pipeline.process_clouds` over the K
+         tiles of the run (the upload of tile i+1 rides a second stream while tile i computes;
+         reported as `e2e` when it is the faster one) and one `Pipeline.process_cloud` call per
+         tile, strictly serial (`e2e_process_cloud`).
   roofline   for the kernel with the largest share of the step (cudaEvent brackets inside
          the library); algorithmic bytes per point from SURVEY.md 8(d) / DESIGN.md.  The
          `knn_search_kernel` bracket is the neighbour search proper: the two lane-per-query
@@ -351,6 +354,35 @@ def main():
         same = bool(np.array_equal(labels_host.astype(np.int32), d_labels.cpu().numpy()))
         e2e['labels_equal_device_arm'] = same
 
+    # ---- e2e, batch form: Pipeline.process_clouds over `steps` tiles in pinned host memory -- the upload of
+    # tile i+1 rides a second stream while the kernels of tile i run; every tile's H2D and D2H is inside
+    # the timed region
+    e2e_batch = None
+    if not args.no_e2e:
+        lab_bufs = [torch.empty(n, dtype=torch.int16).pin_memory() for _ in range(args.steps)]
+
+        def reset_labels():
+            for b_ in lab_bufs:
+                b_.copy_(lab_init_pinned)
+
+        def batch_call():
+            k_ = len(lab_bufs)
+            pipeline.process_clouds([tc] * k_, [points_host] * k_, [b_.numpy().view(np.uint16) for b_ in lab_bufs])
+        reset_labels()
+        pipeline.process_clouds([tc] * 2, [points_host] * 2, [b_.numpy().view(np.uint16) for b_ in lab_bufs[:2]])
+        reset_labels()
+        ms_b, wall_b, _ = timed(batch_call, 1)
+        b_ms = max(ms_b, wall_b)
+        e2e_batch = {'value': world * n * args.steps / (b_ms * 1e-3) / 1e6, 'unit': 'Mpts/s',
+                     'ms_per_step': b_ms / args.steps,
+                     'h2d_bytes_per_step': int(n * 24 + n * 2), 'd2h_bytes_per_step': int(n * 2),
+                     'api': f'Pipeline.process_clouds(tilecodes, clouds, labels_list) over {args.steps} tiles, numpy arrays in '
+                            'pinned host memory; the H2D of tile i+1 overlaps the kernels of tile i (second stream)',
+                     'labels_equal_device_arm': bool(all(
+                         np.array_equal(b_.numpy().view(np.uint16).astype(np.int32), d_labels.cpu().numpy())
+                         for b_ in (lab_bufs[0], lab_bufs[-1])))}
+        del lab_bufs
+
     # ---- supplementary: the LAS-file route (Pipeline.process_file without the disk): raw int32 X, Y, Z
     # in pinned host memory -> device (12 B/pt), coordinates scaled on the device, labels back
     e2e_las = None
@@ -418,13 +450,15 @@ def main():
                         'sample': f'{side:.1f} x {side:.1f} m full-density crop ({len(pts_c)} points) of the same tile, '
                                   f'one pass of the oracle port ({dt:.1f} s)'}
 
+    # headline e2e: the batch call when it is the faster of the two public entry points
+    e2e_head = e2e_batch if (e2e_batch and e2e and e2e_batch['value'] >= e2e['value']) else e2e
     line = {'metric': METRIC, 'value': value, 'unit': 'Mpts/s', 'n_gpus': world, 'steps': args.steps,
             'warmup': warmup, 'ms_per_step': step_ms, 'higher_is_better': True, 'scaling': 'weak',
             'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
             'config': {'workload': WORKLOAD.format(n=n), 'tiles_per_step': world, 'points_per_tile': n,
                        'l2_policy': 'inputs (480 MB of coordinates per tile) are larger than the 126 MB L2',
                        'tiles_per_s': world * args.steps / (ms_dev * 1e-3)},
-            'clocks': clocks, 'e2e': e2e, 'e2e_las': e2e_las, 'gpu_launches': int(launches), 'roofline': roofline,
+            'clocks': clocks, 'e2e': e2e_head, 'e2e_process_cloud': e2e, 'e2e_las': e2e_las, 'gpu_launches': int(launches), 'roofline': roofline,
             'cpu_baseline': cpu_baseline, 'stage_ms': stage_s, 'points_labelled_last_step': labelled,
             'wall_ms_per_step': wall_dev / args.steps}
     print(json.dumps(line))

@@ -330,6 +330,44 @@ def test_pipeline_process_cloud_matches_stagewise(golden):
         Pipeline(processors=procs, ahn_reader=None, caching=True)
 
 
+def test_process_clouds_batch_equals_per_tile_calls():
+    """Pipeline.process_clouds (upload of tile i+1 overlapped with the kernels of tile i) labels every
+    tile exactly as one process_cloud call per tile does: different tiles and sizes, pinned / pageable,
+    C- / F-ordered host arrays, in-place contract per tile."""
+    tiles = [synthetic.make_tile(n, seed=20240000 + k) for k, n in enumerate((90000, 150000, 40000, 150001))]
+    tcs = [f'{1000 + k}_{2000 + k}' for k in range(len(tiles))]             # distinct tilecodes per tile
+    ahn = ahn_utils.ArrayAHNReader({tc: t['ahn_tile'] for tc, t in zip(tcs, tiles)})
+    bld = bgt_utils.ArrayBGTReader({tc: t['building_polygons'] for tc, t in zip(tcs, tiles)})
+    road = bgt_utils.ArrayBGTReader({tc: t['road_polygons'] for tc, t in zip(tcs, tiles)})
+    procs = (AHNFuser(Labels.GROUND, ahn, target='ground', epsilon=0.2, refine_ground=False),
+             BGTRoadFuser(Labels.ROAD, bgt_reader=road),
+             BGTBuildingFuser(Labels.BUILDING, bgt_reader=bld, offset=0, ahn_reader=ahn),
+             LayerLCC(Labels.BUILDING, ahn, params=[{'bottom': 12., 'grid_size': 0.1, 'threshold': 0.5},
+                                                    {'bottom': 0., 'top': 12., 'grid_size': 0.05, 'threshold': 0.5}]),
+             RegionGrowing(Labels.BUILDING, exclude_labels=(Labels.GROUND, Labels.ROAD)))
+    pipe = Pipeline(processors=procs, ahn_reader=ahn, caching=False)
+    clouds = []
+    for k, t in enumerate(tiles):
+        p = t['points']
+        if k % 2 == 0:                                                        # pinned, F-ordered (pipeline.py:124)
+            buf = torch.empty((3, len(p)), dtype=torch.float64).pin_memory()
+            buf.numpy()[...] = p.T
+            clouds.append(buf.numpy().T)
+        else:                                                                 # pageable, C-ordered
+            clouds.append(np.ascontiguousarray(p))
+    want = [pipe.process_cloud(tc, c, np.zeros(len(c), dtype=np.uint16)) for tc, c in zip(tcs, clouds)]
+    dev.clear_tile_cache()
+    labels = [np.zeros(len(c), dtype=np.uint16 if k != 1 else np.uint8) for k, c in enumerate(clouds)]
+    out = pipe.process_clouds(tcs, clouds, labels)
+    assert all(o is l for o, l in zip(out, labels))
+    for k in range(len(tiles)):
+        assert np.array_equal(labels[k], want[k]), k
+        assert (labels[k] != 0).sum() > 1000
+    assert pipe.process_clouds([], [], []) == []
+    with pytest.raises(ValueError):
+        pipe.process_clouds(tcs[:2], clouds[:1], labels[:2])
+
+
 def test_demo_tile_matches_reference_golden(golden):
     """configs[0] substitute: REAL demo AHN + BGT data of tile 2386_9702, reference pipeline."""
     g = golden('demo_golden.npz')

@@ -130,6 +130,48 @@ class Pipeline:
             dev.download_labels(d_labels, labels)
         return labels
 
+    def process_clouds(self, tilecodes, clouds, labels_list):
+        """Process a batch of point clouds (what ``process_folder`` does file by file,
+        pipeline.py:186-194, for clouds that are already in host memory).
+
+        Tiles are independent, so while the kernels of tile ``i`` run, the coordinates and
+        labels of tile ``i + 1`` are already on their way to the device on a second CUDA stream
+        (truly asynchronous when the host arrays are pinned; from pageable memory the copies
+        simply serialise).  Per tile the result is exactly that of ``process_cloud``: every
+        ``labels_list[i]`` is updated in place.  Returns ``labels_list``.
+        """
+        import torch
+        n_tiles = len(tilecodes)
+        if not (len(clouds) == n_tiles and len(labels_list) == n_tiles):
+            logger.error('tilecodes, clouds and labels_list must have the same length')
+            raise ValueError
+        if not all(hasattr(obj, '_apply_device') for obj in self.processors):
+            for tc, pts, lab in zip(tilecodes, clouds, labels_list):
+                self.process_cloud(tc, pts, lab)
+            return labels_list
+        device = dev.current_device()
+        main = torch.cuda.current_stream(device)
+        side = torch.cuda.Stream(device)
+
+        def prefetch(i):
+            # the side stream may recycle memory the main stream has finished with
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                tile = dev.DeviceTile(clouds[i], device)
+                d_labels = dev.upload_labels(labels_list[i], device)
+                done = side.record_event()
+            return tile, d_labels, done
+
+        nxt = prefetch(0) if n_tiles else None
+        for i in range(n_tiles):
+            tile, d_labels, done = nxt
+            nxt = prefetch(i + 1) if i + 1 < n_tiles else None      # queued BEFORE the kernels of tile i
+            main.wait_event(done)
+            self.process_tile_device(tilecodes[i], tile, d_labels)
+            dev.download_labels(d_labels, labels_list[i])
+            del tile, d_labels
+        return labels_list
+
     def process_file(self, in_file, out_file=None, mask=None):
         """Process a single LAS file and save the result (pipeline.py:99-137); ``.laz`` needs laspy."""
         logger.info(f'Processing file {in_file}.')
