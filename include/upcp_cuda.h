@@ -328,6 +328,49 @@ int upcp_mask_gather(const uint8_t* d_sel, int64_t n, const uint8_t* d_full,
                      uint8_t* d_compact, int64_t* d_count,
                      void* d_ws, size_t ws_bytes, void* stream);
 
+/* ------------------------------------------- per-object reductions ("next" row 2) ---- */
+/* Replaces the per-cluster Python loops of the clients of LabelConnectedComp.get_components:
+ * CarFuser._label_car_like_components (reference fusion/car_fuser.py:45-89) and
+ * BGTStreetFurnitureFuser._label_street_furniture_like_components
+ * (fusion/street_furniture_fuser.py:46-89), which rescan the masked cloud once per cluster
+ * (`cc_mask = point_components == cc`, `ground_z[cc_mask]`, `np.amax(points[cc_mask][:, 2])`).
+ *
+ * d_comp [n]: cluster id per point as upcp_lcc writes it (any value in [0, n), -1 = none).
+ * One pass groups the points by cluster and reduces every cluster:
+ *   d_dense [n]          dense cluster id 0..K-1 (ascending d_comp value) or -1
+ *   d_order [n]          original point indices grouped by dense id, ascending inside a group
+ *                        (the order of points[mask][cc_mask], i.e. the qhull input order)
+ *   d_seg_first [cap+1]  group k is d_order[d_seg_first[k] .. d_seg_first[k+1])
+ *   d_count_finite [cap] number of points with a finite d_gz (np.isfinite, car_fuser.py:62)
+ *   d_sum_fixed [cap]    sum of those d_gz in units of 2^-24 m (integer: order-independent;
+ *                        exact for float16-derived AHN values)   mean = sum / 2^24 / count
+ *   d_max_z [cap]        np.amax of z over the cluster (car_fuser.py:68)
+ *   d_bbox_xy [cap][4]   x_min, y_min, x_max, y_max of the cluster
+ *   d_info [4]           K, points in clusters, 0, points whose |d_gz| >= 2^20 (ignored)
+ * d_gz may be NULL (no elevation statistics).  Synchronises the stream twice.
+ * UPCP_E_CAPACITY when K > cap (d_info[0] still holds K). */
+size_t upcp_component_stats_ws_bytes(int64_t n);
+int upcp_component_stats(const int32_t* d_comp, int64_t n, const double* d_x, const double* d_y,
+                         const double* d_z, const double* d_gz, int32_t cap, int32_t* d_dense,
+                         uint32_t* d_order, int64_t* d_seg_first, int64_t* d_count_finite,
+                         int64_t* d_sum_fixed, double* d_max_z, double* d_bbox_xy, int64_t* d_info,
+                         void* d_ws, size_t ws_bytes, void* stream);
+/* d_out_xy[s] = (d_x[d_idx[s]], d_y[d_idx[s]]): the xy of one cluster for the host-side
+ * convex hull / minimum bounding rectangle (math_utils.py:62-125). */
+int upcp_gather_xy(const double* d_x, const double* d_y, const uint32_t* d_idx, int64_t cnt,
+                   double* d_out_xy, void* stream);
+/* d_out[i] = d_dense[i] >= 0 && d_accepted[d_dense[i]]
+ * (`street_furniture_mask[cc_mask] = True`, street_furniture_fuser.py:80). */
+int upcp_component_mark(const int32_t* d_dense, int64_t n, const uint8_t* d_accepted,
+                        int32_t n_comp, uint8_t* d_out, void* stream);
+/* clip_utils.poly_box_clip (clip_utils.py:240-262) for a list of hole-free rings at once:
+ * d_out[i] = OR over prisms p of (inclusive bbox prefilter && crossing-number test of ring p,
+ * boundary == inside && d_zrange[p][0] <= z <= d_zrange[p][1]), restricted to d_sel.
+ * Rings are closed (first == last vertex): ring p = d_ring_xy[d_ring_off[p] .. d_ring_off[p+1]). */
+int upcp_prism_clip(const double* d_x, const double* d_y, const double* d_z, int64_t n,
+                    const uint8_t* d_sel, const double* d_ring_xy, const int32_t* d_ring_off,
+                    const double* d_zrange, int32_t n_prisms, uint8_t* d_out, void* stream);
+
 /* ------------------------------------------------ primitives (exposed) ---- */
 /* LSD radix sort of (key, value) pairs, the "Morton/voxel-key radix sort" of the
  * hot path; exposed for tests and benchmarks.  Sorts bits [0, end_bit).

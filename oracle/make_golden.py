@@ -307,6 +307,73 @@ def golden_demo(upcp):
     print(f'  demo: hist {dict(zip(*np.unique(labels, return_counts=True)))}')
 
 
+OBJ_N, OBJ_SEED, OBJ_CARS = 600000, 20240007, 12
+CAR_PARAMS = {'min_height': 1.2, 'max_height': 2.4, 'min_width': 1.4, 'max_width': 2.4, 'min_length': 3.0,
+              'max_length': 6.0}
+POLE_PARAMS = {'min_height': 1.5, 'max_height': 9.0, 'min_width': 0.1, 'max_width': 1.2, 'min_length': 0.1,
+               'max_length': 1.2}
+
+
+def golden_objects(upcp):
+    """The REAL CarFuser / BGTStreetFurnitureFuser classes (clients of get_components) on a synthetic tile;
+    stand-ins: clustering (oracle natives) and the rectangle / road overlap (half-plane clipping)."""
+    from upcp.fusion import AHNFuser, CarFuser, BGTStreetFurnitureFuser
+    from upcp.utils.ahn_utils import NPZReader
+    from upcp.utils.bgt_utils import BGTPolyReader, BGTPointReader
+    from upcp.labels import Labels
+    from urban_pointcloud_processing_b200 import synthetic
+    tile = synthetic.make_tile(OBJ_N, seed=OBJ_SEED, n_cars=OBJ_CARS)
+    points, tc = tile['points'], tile['tilecode']
+    tmp = tempfile.mkdtemp()
+    write_readers(tmp, tile)
+    pd.DataFrame([('lichtmast', x, y) for x, y in tile['pole_xy']][::2] + [('boom', x, y) for x, y in tile['pole_xy']][1::2],
+                 columns=['bgt_type', 'x', 'y']).to_csv(os.path.join(tmp, 'points.csv'), index=False)
+    ahn_reader = NPZReader(tmp)
+    road = BGTPolyReader(bgt_file=os.path.join(tmp, 'roads.csv'))
+    poles = BGTPointReader(bgt_file=os.path.join(tmp, 'points.csv'))
+    ahn_tile = tile['ahn_tile']
+    out = {'n': np.array(OBJ_N), 'seed': np.array(OBJ_SEED), 'points_mm': mm(points).astype(np.int32)}
+    labels = np.zeros(OBJ_N, dtype=np.uint16)
+    labels = AHNFuser(Labels.GROUND, ahn_reader, target='ground', epsilon=0.2, refine_ground=False).get_labels(
+        points, labels, labels == 0, tc)
+    want = labels.copy()
+    out['labels_after_ground'] = labels.astype(np.uint8).copy()
+    car = CarFuser(Labels.CAR, ahn_reader, road, grid_size=0.1, min_component_size=300, params=dict(CAR_PARAMS),
+                   exclude_types=['fietspad'])
+    labels = car.get_labels(points, labels, labels == 0, tc)
+    roads_kept = road.filter_tile(tc, exclude_types=['fietspad'], merge=False)
+    want = R.car_fuser_labels(points, want, want == 0, ahn_tile, roads_kept, Labels.CAR, 0.1, 300, 20, CAR_PARAMS)
+    assert np.array_equal(labels, want), 'oracle mismatch: car fuser'
+    out['labels_after_car'] = labels.astype(np.uint8).copy()
+    n_car = int((labels == Labels.CAR).sum())
+    sf = BGTStreetFurnitureFuser(Labels.STREET_LIGHT, 'lichtmast', poles, ahn_reader, grid_size=0.1,
+                                 min_component_size=100, params=dict(POLE_PARAMS))
+    labels = sf.get_labels(points, labels, labels == 0, tc)
+    pts_kept = poles.filter_tile(tc, bgt_types=['lichtmast'])
+    want = R.street_furniture_labels(points, want, want == 0, ahn_tile, pts_kept, Labels.STREET_LIGHT, 0.1, 100, 1.,
+                                     POLE_PARAMS)
+    assert np.array_equal(labels, want), 'oracle mismatch: street furniture fuser'
+    out['labels_after_street_light'] = labels.astype(np.uint8).copy()
+    n_sf = int((labels == Labels.STREET_LIGHT).sum())
+    # minimum bounding rectangles of a few clusters, straight from the reference function
+    from upcp.utils.math_utils import minimum_bounding_rectangle
+    rng = np.random.default_rng(5)
+    rects = []
+    for k in range(6):
+        c = rng.random((200 + 50 * k, 2)) * np.array([4.5, 1.8])
+        a = rng.uniform(0, np.pi)
+        c = c @ np.array([[np.cos(a), -np.sin(a)], [np.sin(a), np.cos(a)]]) + np.array([119320.0, 485120.0])
+        rect, _, w, l, ctr = minimum_bounding_rectangle(c)
+        r2, w2, l2, c2 = R.minimum_bounding_rectangle(c)
+        assert np.array_equal(rect, r2) and w == w2 and l == l2 and np.array_equal(ctr, c2)
+        out[f'mbr_in_{k}'] = c
+        out[f'mbr_out_{k}'] = np.concatenate([rect.ravel(), [w, l], ctr])
+    np.savez_compressed(os.path.join(GOLDEN, 'objects_golden.npz'), **out)
+    shutil.rmtree(tmp, ignore_errors=True)
+    print(f'  objects: {n_car} car points, {n_sf} street-light points')
+    assert n_car > 1000 and n_sf > 300
+
+
 def main():
     os.makedirs(GOLDEN, exist_ok=True)
     upcp = ref_harness.load_reference()
@@ -317,6 +384,7 @@ def main():
     golden_scalars(upcp)
     golden_demo(upcp)
     golden_pipeline(upcp)
+    golden_objects(upcp)
     print('golden vectors written to', GOLDEN)
 
 

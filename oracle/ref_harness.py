@@ -5,7 +5,9 @@ GPU box).  The reference's own Python is imported UNCHANGED; stand-in modules ar
 ``sys.modules`` only for third-party natives that are not installed here:
 
     shapely            duck-typed Polygon (buffer(0) is the identity, unary_union keeps
-                       the list) -- enough for offset=0 / merge=True call sites
+                       the list) -- enough for offset=0 / merge=True call sites; area /
+                       intersects / intersection(...).area for a CONVEX self (CarFuser's
+                       bounding rectangle) by half-plane clipping
     pycc, cccorelib    ccPointCloud + labelConnectedComponents backed by oracle.natives
     open3d             PointCloud / KDTreeFlann / estimate_normals backed by oracle.natives
     laspy, tifffile, zarr, pyntcloud      empty stubs (never called on this path)
@@ -48,6 +50,20 @@ class _Polygon:
         if offset != 0:
             raise NotImplementedError('shapely stand-in: buffer(offset != 0)')
         return self
+
+    # car_fuser.py:73-79 only: self is the (convex) minimum bounding rectangle of a cluster
+    @property
+    def area(self):
+        from . import reference_py
+        return abs(reference_py._shoelace([tuple(c) for c in self.exterior.coords[:-1]]))
+
+    def intersects(self, other):
+        return self.intersection(other).area > 0
+
+    def intersection(self, other):
+        from . import reference_py
+        perc = reference_py.rect_overlap_percentage(np.asarray(self.exterior.coords), other)
+        return types.SimpleNamespace(area=perc / 100.0 * self.area)
 
 
 class _Multi:

@@ -250,6 +250,138 @@ def noise_filter_labels(points, labels, mask, ahn_tile, label, epsilon=0.2, grid
     return labels
 
 
+# ------------------------------------------------ object fusers (clients of LCC) ----
+def minimum_bounding_rectangle(points):
+    """math_utils.minimum_bounding_rectangle (utils/math_utils.py:62-125): qhull convex hull,
+    candidate orientations = directions of the OPEN chain of hull edges folded into [0, pi/2),
+    smallest-area box.  Returns (corners, width, length, centre)."""
+    from scipy.spatial import ConvexHull
+    pi2 = np.pi / 2.
+    hull_points = points[ConvexHull(points).vertices]
+    edges = hull_points[1:] - hull_points[:-1]
+    angles = np.unique(np.abs(np.mod(np.arctan2(edges[:, 1], edges[:, 0]), pi2)))
+    rotations = np.vstack([np.cos(angles), np.cos(angles - pi2), np.cos(angles + pi2), np.cos(angles)]).T
+    rotations = rotations.reshape((-1, 2, 2))
+    rot_points = np.dot(rotations, hull_points.T)
+    min_x = np.nanmin(rot_points[:, 0], axis=1); max_x = np.nanmax(rot_points[:, 0], axis=1)
+    min_y = np.nanmin(rot_points[:, 1], axis=1); max_y = np.nanmax(rot_points[:, 1], axis=1)
+    best_idx = np.argmin((max_x - min_x) * (max_y - min_y))
+    x1, x2, y1, y2 = max_x[best_idx], min_x[best_idx], max_y[best_idx], min_y[best_idx]
+    r = rotations[best_idx]
+    center_point = np.dot([(x1 + x2) / 2, (y1 + y2) / 2], r)
+    rect = np.zeros((4, 2))
+    rect[0] = np.dot([x1, y2], r); rect[1] = np.dot([x2, y2], r)
+    rect[2] = np.dot([x2, y1], r); rect[3] = np.dot([x1, y1], r)
+    dims = [(x1 - x2), (y1 - y2)]
+    return rect, min(dims), max(dims), center_point
+
+
+def _half_plane_cut(poly, a, b):
+    """Vertices of the closed polygon ``poly`` (list of (x, y), not repeated) on the left of a->b."""
+    def side(p):
+        return (b[0] - a[0]) * (p[1] - a[1]) - (b[1] - a[1]) * (p[0] - a[0])
+    out = []
+    for i in range(len(poly)):
+        p, q = poly[i], poly[(i + 1) % len(poly)]
+        sp, sq = side(p), side(q)
+        if sp >= 0:
+            out.append(p)
+        if (sp >= 0) != (sq >= 0):
+            t = sp / (sp - sq)
+            out.append((p[0] + t * (q[0] - p[0]), p[1] + t * (q[1] - p[1])))
+    return out
+
+
+def _shoelace(poly):
+    return 0.5 * sum(poly[i][0] * poly[(i + 1) % len(poly)][1] - poly[(i + 1) % len(poly)][0] * poly[i][1]
+                     for i in range(len(poly))) if len(poly) >= 3 else 0.0
+
+
+def rect_overlap_percentage(rect_ring, poly):
+    """(p1.intersection(p2).area / p1.area) * 100 for a convex p1 (car_fuser.py:74-79); stands in for
+    GEOS: successive half-plane cuts of p2's rings by the rectangle's edges, shoelace areas."""
+    rect = [tuple(p) for p in np.asarray(rect_ring)[:-1]]
+    if _shoelace(rect) < 0:
+        rect = rect[::-1]
+    area = _shoelace(rect)
+    if area == 0:
+        return 0.0
+
+    def clipped_area(coords):
+        ring = [tuple(c[:2]) for c in list(coords)[:-1]]
+        for i in range(len(rect)):
+            if len(ring) < 3:
+                return 0.0
+            ring = _half_plane_cut(ring, rect[i], rect[(i + 1) % len(rect)])
+        return abs(_shoelace(ring))
+    inter = clipped_area(poly.exterior.coords) - sum(clipped_area(h.coords) for h in poly.interiors)
+    return inter / area * 100
+
+
+def _object_candidates(points_m, ground_z, point_components, min_height, max_height):
+    """Shared head of the two per-cluster loops (car_fuser.py:53-69)."""
+    for cc in sorted(set(np.unique(point_components)).difference((-1,))):
+        cc_mask = (point_components == cc)
+        target_z = ground_z[cc_mask]
+        valid_values = target_z[np.isfinite(target_z)]
+        if valid_values.size != 0:
+            cc_z = np.mean(valid_values)
+            min_z = cc_z + min_height
+            max_z = cc_z + max_height
+            cluster_height = np.amax(points_m[cc_mask][:, 2])
+            if min_z <= cluster_height <= max_z:
+                yield cc_mask, cc_z, max_z
+
+
+def car_fuser_labels(points, labels, mask, ahn_tile, road_polygons, label, grid_size=0.05,
+                     min_component_size=5000, overlap_perc=20, params=None):
+    """CarFuser.get_labels + _label_car_like_components (fusion/car_fuser.py:45-137)."""
+    if len(road_polygons) == 0:
+        return labels
+    p = params
+    pm = points[mask]
+    ground_z = interpolate(ahn_tile, pm, 'ground_surface')
+    point_components = lcc_get_components(pm, grid_size, min_component_size)
+    car_mask = np.zeros(len(pm), dtype=bool)
+    for cc_mask, cc_z, max_z in _object_candidates(pm, ground_z, point_components, p['min_height'], p['max_height']):
+        mbrect, mbr_width, mbr_length, _ = minimum_bounding_rectangle(pm[cc_mask][:, :2])
+        poly = np.vstack((mbrect, mbrect[0]))
+        if p['min_width'] < mbr_width < p['max_width'] and p['min_length'] < mbr_length < p['max_length']:
+            for p2 in road_polygons:
+                if rect_overlap_percentage(poly, p2) > overlap_perc:
+                    box = type('P', (), {'exterior': type('R', (), {'coords': poly})(), 'interiors': []})()
+                    car_mask = car_mask | (poly_clip(pm, box) & ((pm[:, 2] <= max_z) & (pm[:, 2] >= cc_z)))
+                    break
+    label_mask = np.zeros((len(points),), dtype=bool)
+    label_mask[mask] = car_mask
+    labels[label_mask] = label
+    return labels
+
+
+def street_furniture_labels(points, labels, mask, ahn_tile, bgt_points, label, grid_size=0.05,
+                            min_component_size=1500, max_dist=1., params=None):
+    """BGTStreetFurnitureFuser.get_labels + _label_street_furniture_like_components
+    (fusion/street_furniture_fuser.py:46-137)."""
+    if len(bgt_points) == 0:
+        return labels
+    p = params
+    pm = points[mask]
+    ground_z = interpolate(ahn_tile, pm, 'ground_surface')
+    point_components = lcc_get_components(pm, grid_size, min_component_size)
+    sf_mask = np.zeros(len(pm), dtype=bool)
+    for cc_mask, cc_z, max_z in _object_candidates(pm, ground_z, point_components, p['min_height'], p['max_height']):
+        _, mbr_width, mbr_length, center_point = minimum_bounding_rectangle(pm[cc_mask][:, :2])
+        if p['min_width'] < mbr_width < p['max_width'] and p['min_length'] < mbr_length < p['max_length']:
+            for bgt_point in bgt_points:
+                if np.linalg.norm(np.asarray(bgt_point) - center_point) <= max_dist:
+                    sf_mask[cc_mask] = True
+                    break
+    label_mask = np.zeros((len(points),), dtype=bool)
+    label_mask[mask] = sf_mask
+    labels[label_mask] = label
+    return labels
+
+
 # ---------------------------------------------------------------------- RG --------
 def vector_angle(u, v):
     """math_utils.vector_angle (utils/math_utils.py:9-18)."""

@@ -368,6 +368,109 @@ def test_process_clouds_batch_equals_per_tile_calls():
         pipe.process_clouds(tcs[:2], clouds[:1], labels[:2])
 
 
+# ------------------------------------------------ object fusers ("next" row 2) ---
+def test_component_stats_match_numpy():
+    """upcp_component_stats: grouping, per-cluster reductions and the mean of the finite ground values
+    against plain numpy on the oracle-independent device clustering."""
+    from urban_pointcloud_processing_b200.region_growing.label_connected_comp import lcc_device
+    from urban_pointcloud_processing_b200.utils import object_utils
+    tile = synthetic.make_tile(400000, seed=91)
+    pts = tile['points']
+    t = dev.DeviceTile(pts)
+    sel = tile['kind'] >= 1
+    d_sel = dev.upload_mask(sel, t.n, t.device)
+    gz = R.interpolate(tile['ahn_tile'], pts, 'ground_surface')
+    gz[~sel] = np.nan
+    d_gz = ahn_utils.device_raster_for(ahn_utils.ArrayAHNReader({'t': tile['ahn_tile']}), 't', 'ground_surface').lookup(t, d_sel=d_sel)
+    assert np.array_equal(d_gz.cpu().numpy(), gz, equal_nan=True)
+    d_comp, _, _ = lcc_device(t, d_sel, 0.2, 50, level_from='sel')
+    comp = d_comp.cpu().numpy()
+    for cap in (1 << 16, 3):                                                  # 3: forces the capacity retry
+        st = object_utils.ComponentStats(t, d_comp, d_gz, cap=cap)
+        ids = np.unique(comp[comp >= 0])
+        assert st.n_components == len(ids) > 20 and st.n_points == (comp >= 0).sum() and st.n_gz_out_of_range == 0
+        dense = st.d_dense.cpu().numpy()
+        assert np.array_equal(dense >= 0, comp >= 0) and np.array_equal(ids[dense[comp >= 0]], comp[comp >= 0])
+        order = st.d_order.cpu().numpy().view(np.uint32)
+        for k in list(range(0, len(ids), 7)) + [len(ids) - 1]:
+            m = comp == ids[k]
+            assert np.array_equal(order[st.seg_first[k]:st.seg_first[k + 1]], np.where(m)[0])
+            assert st.size[k] == m.sum() and st.max_z[k] == pts[m, 2].max()
+            assert np.array_equal(st.bbox[k], [pts[m, 0].min(), pts[m, 1].min(), pts[m, 0].max(), pts[m, 1].max()])
+            fin = gz[m][np.isfinite(gz[m])]
+            assert st.count_finite[k] == len(fin)
+            if len(fin):
+                assert st.mean_gz[k] == np.mean(fin)                          # bit-identical (float16-derived values)
+            else:
+                assert np.isnan(st.mean_gz[k])
+            assert np.array_equal(st.xy_of(k), pts[m][:, :2])
+        acc = np.zeros(len(ids), dtype=bool); acc[::3] = True
+        assert np.array_equal(dev.download_mask(st.mark(acc)), np.isin(comp, ids[acc]))
+    # no clusters at all / empty tile
+    none = torch.full((t.n,), -1, dtype=torch.int32, device=t.device)
+    st = object_utils.ComponentStats(t, none, d_gz)
+    assert st.n_components == 0 and not st.mark(np.zeros(0, bool)).any()
+
+
+def test_prism_clip_matches_oracle():
+    from urban_pointcloud_processing_b200.utils import object_utils
+    tile = synthetic.make_tile(300000, seed=92)
+    pts = tile['points']
+    t = dev.DeviceTile(pts)
+    rng = np.random.default_rng(9)
+    sel = rng.random(len(pts)) < 0.8
+    rings, zr = [], []
+    for k in range(700):                                                      # > one shared-memory chunk of prisms
+        c, a = rng.uniform(2, 48, 2) + np.array(tile['origin']), rng.uniform(0, np.pi)
+        rot = np.array([[np.cos(a), -np.sin(a)], [np.sin(a), np.cos(a)]])
+        box = (np.array([[-1.1, -0.5], [1.1, -0.5], [1.1, 0.5], [-1.1, 0.5], [-1.1, -0.5]]) @ rot.T) + c
+        if k % 50 == 0:                                                       # vertices / edges through cloud points
+            box[0] = box[4] = pts[rng.integers(len(pts)), :2]
+        rings.append(box); zr.append((rng.uniform(-1, 2), rng.uniform(2, 9)))
+    zr[3] = (pts[5, 2], pts[5, 2])                                            # closed z interval
+    got = dev.download_mask(object_utils.prism_clip_device(t, dev.upload_mask(sel, t.n, t.device), rings, zr))
+    want = np.zeros(len(pts), dtype=bool)
+    for ring, (b, tp) in zip(rings, zr):
+        want |= R.poly_clip(pts, RingPolygon(ring)) & ((pts[:, 2] <= tp) & (pts[:, 2] >= b))
+    want &= sel
+    assert np.array_equal(got, want) and want.sum() > 1000
+    assert not object_utils.prism_clip_device(t, None, [], []).any()
+
+
+def test_object_fusers_match_reference_golden(golden):
+    """CarFuser / BGTStreetFurnitureFuser drop-ins vs the REAL reference classes (objects_golden.npz)."""
+    from test_oracle_golden import OBJ_CAR_PARAMS, OBJ_POLE_PARAMS, objects_tile
+    from urban_pointcloud_processing_b200.fusion import BGTStreetFurnitureFuser, CarFuser
+    g = golden('objects_golden.npz')
+    tile, poles = objects_tile(g)
+    points, tc = tile['points'], tile['tilecode']
+    ahn, _, road = readers_for(tile)
+    pole_reader = bgt_utils.ArrayBGTPointReader({tc: poles})
+    labels = np.zeros(len(points), dtype=np.uint16)
+    labels = AHNFuser(Labels.GROUND, ahn, target='ground', epsilon=0.2, refine_ground=False).get_labels(
+        points, labels, labels == 0, tc)
+    assert np.array_equal(labels, g['labels_after_ground'])
+    car = CarFuser(Labels.CAR, ahn, road, grid_size=0.1, min_component_size=300, params=dict(OBJ_CAR_PARAMS),
+                   exclude_types=['fietspad'])
+    out = car.get_labels(points, labels, labels == 0, tc)
+    assert out is labels and np.array_equal(labels, g['labels_after_car']) and len(car.last_objects) >= 3
+    sf = BGTStreetFurnitureFuser(Labels.STREET_LIGHT, 'lichtmast', pole_reader, ahn, grid_size=0.1,
+                                 min_component_size=100, params=dict(OBJ_POLE_PARAMS))
+    labels = sf.get_labels(points, labels, labels == 0, tc)
+    assert np.array_equal(labels, g['labels_after_street_light']) and sf.last_accepted >= 3
+    # nothing to do: no road parts / no point objects -> labels unchanged
+    before = labels.copy()
+    CarFuser(Labels.CAR, ahn, bgt_utils.ArrayBGTReader({}), params=dict(OBJ_CAR_PARAMS)).get_labels(
+        points, labels, labels == 0, tc)
+    BGTStreetFurnitureFuser(Labels.TREE, 'geen', pole_reader, ahn, params=dict(OBJ_POLE_PARAMS)).get_labels(
+        points, labels, labels == 0, tc)
+    assert np.array_equal(labels, before)
+    # chained on the device by the Pipeline like every other drop-in
+    procs = (AHNFuser(Labels.GROUND, ahn, target='ground', epsilon=0.2, refine_ground=False), car, sf)
+    piped = Pipeline(processors=procs, ahn_reader=ahn, caching=True).process_cloud(tc, points, np.zeros(len(points), np.uint16))
+    assert np.array_equal(piped, g['labels_after_street_light'])
+
+
 def test_demo_tile_matches_reference_golden(golden):
     """configs[0] substitute: REAL demo AHN + BGT data of tile 2386_9702, reference pipeline."""
     g = golden('demo_golden.npz')

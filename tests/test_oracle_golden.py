@@ -147,3 +147,63 @@ def test_knn_native_against_bruteforce():
     order = np.lexsort((np.broadcast_to(np.arange(len(pts)), dd.shape), dd), axis=1)[:, :9]
     assert np.array_equal(idx, order)
     assert np.array_equal(d2, np.take_along_axis(dd, order, axis=1))
+
+
+# ------------------------------------------------- object fusers ("next" row 2) ---
+OBJ_CAR_PARAMS = {'min_height': 1.2, 'max_height': 2.4, 'min_width': 1.4, 'max_width': 2.4, 'min_length': 3.0,
+                  'max_length': 6.0}
+OBJ_POLE_PARAMS = {'min_height': 1.5, 'max_height': 9.0, 'min_width': 0.1, 'max_width': 1.2, 'min_length': 0.1,
+                   'max_length': 1.2}
+
+
+def objects_tile(g):
+    tile = synthetic.make_tile(int(g['n']), seed=int(g['seed']), n_cars=12)
+    assert np.array_equal(tile['points'], from_mm(g['points_mm']))
+    poles = [('lichtmast', x, y) for x, y in tile['pole_xy']][::2] + [('boom', x, y) for x, y in tile['pole_xy']][1::2]
+    return tile, poles
+
+
+def test_object_fusers_oracle_matches_reference_golden(golden):
+    """CarFuser / BGTStreetFurnitureFuser of the REAL reference (objects_golden.npz) vs the restatement."""
+    g = golden('objects_golden.npz')
+    tile, poles = objects_tile(g)
+    points, ahn = tile['points'], tile['ahn_tile']
+    labels = np.zeros(len(points), dtype=np.uint16)
+    labels = R.ahn_fuser_labels(points, labels, labels == 0, ahn, 9, 'ground', 0.2)
+    assert np.array_equal(labels, g['labels_after_ground'])
+    labels = R.car_fuser_labels(points, labels, labels == 0, ahn, tile['road_polygons'][:1], 40, 0.1, 300, 20,
+                                OBJ_CAR_PARAMS)
+    assert np.array_equal(labels, g['labels_after_car']) and (labels == 40).sum() > 1000
+    lights = [(x, y) for t, x, y in poles if t == 'lichtmast']
+    labels = R.street_furniture_labels(points, labels, labels == 0, ahn, lights, 60, 0.1, 100, 1., OBJ_POLE_PARAMS)
+    assert np.array_equal(labels, g['labels_after_street_light']) and (labels == 60).sum() > 300
+
+
+def test_minimum_bounding_rectangle_and_overlap_host_logic(golden):
+    """The product's host-side object geometry: bit-identical to the reference's
+    minimum_bounding_rectangle (golden vectors), overlap percentage equal to the oracle's
+    independent clipping and to closed-form cases."""
+    from urban_pointcloud_processing_b200.utils import math_utils, object_utils
+    from urban_pointcloud_processing_b200.utils.bgt_utils import RingPolygon
+    g = golden('objects_golden.npz')
+    for k in range(6):
+        rect, hull, w, l, ctr = math_utils.minimum_bounding_rectangle(g[f'mbr_in_{k}'])
+        assert np.array_equal(np.concatenate([rect.ravel(), [w, l], ctr]), g[f'mbr_out_{k}'])
+        r2, w2, l2, c2 = R.minimum_bounding_rectangle(g[f'mbr_in_{k}'])
+        assert np.array_equal(rect, r2) and (w, l) == (w2, l2)
+    unit = np.array([[0., 0.], [2., 0.], [2., 1.], [0., 1.], [0., 0.]])
+    half = RingPolygon([(1., -5.), (9., -5.), (9., 5.), (1., 5.)])
+    assert object_utils.overlap_percentage(unit, half) == 50.0 == R.rect_overlap_percentage(unit, half)
+    assert object_utils.overlap_percentage(unit[::-1], half) == 50.0
+    holed = RingPolygon([(-1., -1.), (3., -1.), (3., 2.), (-1., 2.)], [[(0.5, 0.25), (1.5, 0.25), (1.5, 0.75), (0.5, 0.75)]])
+    assert abs(object_utils.overlap_percentage(unit, holed) - 75.0) < 1e-12
+    away = RingPolygon([(5., 5.), (6., 5.), (6., 6.)])
+    assert object_utils.overlap_percentage(unit, away) == 0.0 == R.rect_overlap_percentage(unit, away)
+    rng = np.random.default_rng(3)
+    tile = synthetic.make_tile(1000, seed=1)
+    for _ in range(50):                                      # rotated rectangles against the concave road strips
+        c, a = rng.uniform(10, 40, 2) + np.array(tile['origin']), rng.uniform(0, np.pi)
+        rot = np.array([[np.cos(a), -np.sin(a)], [np.sin(a), np.cos(a)]])
+        box = (np.array([[-2.2, -0.9], [2.2, -0.9], [2.2, 0.9], [-2.2, 0.9], [-2.2, -0.9]]) @ rot.T) + c
+        for road in tile['road_polygons']:
+            assert abs(object_utils.overlap_percentage(box, road) - R.rect_overlap_percentage(box, road)) < 1e-9

@@ -92,6 +92,14 @@ _PROTOTYPES = {
     'upcp_mask_scatter': (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     'upcp_mask_gather': (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
                                  c_void_p]),
+    'upcp_component_stats_ws_bytes': (c_size_t, [c_int64]),
+    'upcp_component_stats': (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_void_p,
+                                     c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                     c_void_p, c_size_t, c_void_p]),
+    'upcp_gather_xy': (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
+    'upcp_component_mark': (c_int, [c_void_p, c_int64, c_void_p, c_int32, c_void_p, c_void_p]),
+    'upcp_prism_clip': (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p,
+                                c_int32, c_void_p, c_void_p]),
     'upcp_sort_ws_bytes': (c_size_t, [c_int64]),
     'upcp_sort_pairs_u32': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p,
                                     c_size_t, c_void_p]),

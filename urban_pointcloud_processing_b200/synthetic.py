@@ -44,13 +44,14 @@ def make_buildings(rng, origin, n_buildings=8):
 
 
 def make_tile(n_points, seed=20240000, origin=TILE_ORIGIN, facade_fraction=0.33, shuffle=True,
-              order='F'):
+              order='F', n_cars=40):
     """Returns a dict with
          points   (n,3) float64 (F-ordered by default, like pipeline.py:124 delivers)
          kind     uint8[n]  0 ground, 1 facade, 2 car, 3 furniture, 4 clutter, 5 noise
          ahn_tile dict x, y, ground_surface, building_surface (float64 from float16)
          building_polygons / road_polygons  lists of RingPolygon
          tilecode
+         car_centres / car_dims, pole_xy / pole_r / pole_h   layout of the cars and poles
     """
     rng = np.random.Generator(np.random.Philox(seed))
     ox, oy = origin
@@ -96,7 +97,6 @@ def make_tile(n_points, seed=20240000, origin=TILE_ORIGIN, facade_fraction=0.33,
     # roads: two crossing strips; cars are 4.5 x 1.8 x 1.5 m box shells on them
     road_h = (ox, oy + 19.5, ox + TILE_SIZE, oy + 25.0)        # x0, y0, x1, y1
     road_v = (ox + 19.5, oy, ox + 25.0, oy + TILE_SIZE)
-    n_cars = 40
     car_c = np.empty((n_cars, 2)); car_dim = np.empty((n_cars, 2))
     for c in range(n_cars):
         if c % 2 == 0:
@@ -192,7 +192,8 @@ def make_tile(n_points, seed=20240000, origin=TILE_ORIGIN, facade_fraction=0.33,
 
     return {'points': points, 'kind': kind, 'ahn_tile': ahn_tile, 'boxes': boxes,
             'building_polygons': building_polygons, 'road_polygons': road_polygons,
-            'tilecode': tilecode_for(origin), 'origin': origin}
+            'tilecode': tilecode_for(origin), 'origin': origin,
+            'car_centres': car_c, 'car_dims': car_dim, 'pole_xy': pole_xy, 'pole_r': pole_r, 'pole_h': pole_h}
 
 
 def make_polygon_lattice(n_side=71, seed=5000, origin=TILE_ORIGIN, hole_fraction=0.1):

@@ -121,6 +121,45 @@ class BGTPolyReader(BGTReader):
         return [poly for poly in poly_offset if len(poly.exterior.coords) > 1]
 
 
+class BGTPointReader(BGTReader):
+    """CSV columns: [bgt_type, x, y] (drop-in for bgt_utils.py:97-126; read by
+    BGTStreetFurnitureFuser)."""
+
+    COLUMNS = ['bgt_type', 'x', 'y']
+
+    def filter_tile(self, tilecode, bgt_types=[], exclude_types=[], padding=0, return_types=False):
+        """Points of the objects inside the (padded, inclusive) area of the given tile code."""
+        ((bx_min, by_max), (bx_max, by_min)) = get_bbox_from_tile_code(tilecode, padding=padding)
+        df = self.bgt_df
+        sel = (df.x <= bx_max) & (df.x >= bx_min) & (df.y <= by_max) & (df.y >= by_min)
+        if len(bgt_types) >= 1:
+            sel &= df.bgt_type.isin(list(bgt_types))
+        if len(exclude_types) >= 1:
+            sel &= ~df.bgt_type.isin(list(exclude_types))
+        records = list(df[sel.values].to_records(index=False))
+        if return_types:
+            return records
+        return [(x, y) for (_, x, y) in records]
+
+
+class ArrayBGTPointReader:
+    """In-memory point reader (synthetic tiles, tests): ``tiles`` maps a tile code to a list of
+    (bgt_type, x, y)."""
+
+    def __init__(self, tiles):
+        self.tiles = tiles
+
+    def filter_tile(self, tilecode, bgt_types=[], exclude_types=[], padding=0, return_types=False):
+        out = []
+        for t, x, y in self.tiles.get(tilecode, []):
+            if len(bgt_types) >= 1 and t not in bgt_types:
+                continue
+            if len(exclude_types) >= 1 and t in exclude_types:
+                continue
+            out.append((t, x, y) if return_types else (x, y))
+        return out
+
+
 class ArrayBGTReader:
     """In-memory polygon reader (synthetic tiles, tests): ``tiles`` maps a tile code to a
     list of polygons (RingPolygon / shapely-like / raw rings); ``types`` optionally gives
@@ -149,3 +188,8 @@ class ArrayBGTReader:
 def get_polygons(bgt_file, tilecode, padding=0, offset=0, merge=False):
     """Polygons from a bgt_file for a specific tilecode."""
     return BGTPolyReader(bgt_file=bgt_file).filter_tile(tilecode, padding=padding, offset=offset, merge=merge)
+
+
+def get_points(bgt_file, tilecode, padding=0, return_types=True):
+    """Point objects from a bgt_file for a specific tilecode."""
+    return BGTPointReader(bgt_file=bgt_file).filter_tile(tilecode, padding=padding, return_types=return_types)

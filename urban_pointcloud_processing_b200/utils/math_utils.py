@@ -37,3 +37,35 @@ def compute_bounding_box(points):
     """(x_min, y_min, x_max, y_max) of a point list; further columns are ignored."""
     points = np.asarray(points)
     return (np.min(points[:, 0]), np.min(points[:, 1]), np.max(points[:, 0]), np.max(points[:, 1]))
+
+
+def minimum_bounding_rectangle(points):
+    """Smallest-area enclosing rectangle of an (n, 2) point set (drop-in for
+    math_utils.py:62-125; per-object host work of CarFuser / BGTStreetFurnitureFuser).
+
+    Returns (corners (4, 2), hull_points, width, length, center_point) with width <= length.
+    The candidate orientations are the hull edge directions folded into [0, pi/2); as in the
+    reference the hull is walked as an OPEN chain (the edge closing the qhull vertex cycle is not
+    a candidate), and every product goes through the same numpy calls on the same operands so
+    that the corners come out bit for bit."""
+    from scipy.spatial import ConvexHull
+    points = np.asarray(points)
+    quarter = np.pi / 2.
+    hull_points = points[ConvexHull(points).vertices]
+    steps = hull_points[1:] - hull_points[:-1]
+    theta = np.unique(np.abs(np.mod(np.arctan2(steps[:, 1], steps[:, 0]), quarter)))
+    # one 2 x 2 rotation per candidate angle: [[c, cos(t - pi/2)], [cos(t + pi/2), c]]
+    frames = np.vstack([np.cos(theta), np.cos(theta - quarter), np.cos(theta + quarter), np.cos(theta)]).T
+    frames = frames.reshape((-1, 2, 2))
+    turned = np.dot(frames, hull_points.T)
+    lo_x, hi_x = np.nanmin(turned[:, 0], axis=1), np.nanmax(turned[:, 0], axis=1)
+    lo_y, hi_y = np.nanmin(turned[:, 1], axis=1), np.nanmax(turned[:, 1], axis=1)
+    best = np.argmin((hi_x - lo_x) * (hi_y - lo_y))
+    x1, x2, y1, y2 = hi_x[best], lo_x[best], hi_y[best], lo_y[best]
+    frame = frames[best]
+    center_point = np.dot([(x1 + x2) / 2, (y1 + y2) / 2], frame)
+    corners = np.zeros((4, 2))
+    for row, corner in enumerate(([x1, y2], [x2, y2], [x2, y1], [x1, y1])):
+        corners[row] = np.dot(corner, frame)
+    extent = [(x1 - x2), (y1 - y2)]
+    return corners, hull_points, min(extent), max(extent), center_point
