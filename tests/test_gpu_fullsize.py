@@ -242,3 +242,65 @@ def test_config5_pipeline_20m_host_api_equals_device_arm(tile20):
     assert hist.sum() == N20 and hist[Labels.GROUND] > 5_000_000 and hist[Labels.BUILDING] > 5_000_000
     d_hist = dev.label_hist(dev.upload_labels(labels, dev.current_device())).cpu().numpy()
     assert np.array_equal(d_hist, hist)
+
+
+# ------------------------------- "next" row 2 at full size: object fusers on the 20 M tile ---
+def test_object_fusers_20m_reductions_and_clip():
+    """CarFuser / BGTStreetFurnitureFuser on the 20 M-point tile.  The oracle's per-cluster Python loops do not
+    finish in seconds at this size, so: the per-cluster reductions are re-derived with numpy bincounts from
+    the device's own cluster ids (clusters themselves are checked against the oracle in config 2), every
+    accepted car is re-judged on the host, and the final mask must equal the OR of the oracle's
+    poly_box_clip over the accepted rectangles."""
+    from urban_pointcloud_processing_b200.fusion import BGTStreetFurnitureFuser, CarFuser
+    from urban_pointcloud_processing_b200.region_growing.label_connected_comp import lcc_device
+    from urban_pointcloud_processing_b200.utils import ahn_utils, bgt_utils, math_utils, object_utils
+    tile20 = synthetic.make_tile(N20, seed=20240001, n_cars=12)          # few cars: most stand alone
+    pts, tc = tile20['points'], tile20['tilecode']
+    ahn, _, road = readers_for(tile20)
+    labels = np.zeros(N20, dtype=np.uint16)
+    labels[tile20['kind'] == 0] = Labels.GROUND
+    mask = labels == 0
+    t = dev.get_tile(pts)
+    d_mask = dev.upload_mask(mask, t.n, t.device)
+    d_gz = ahn_utils.device_raster_for(ahn, tc, 'ground_surface').lookup(t, d_sel=d_mask)
+    d_comp, _, _ = lcc_device(t, d_mask, 0.1, 1500, level_from='sel')
+    st = object_utils.ComponentStats(t, d_comp, d_gz)
+    comp, gz = d_comp.cpu().numpy(), d_gz.cpu().numpy()
+    inc = comp >= 0
+    ids, dense = np.unique(comp[inc], return_inverse=True)
+    assert st.n_components == len(ids) > 10 and st.n_points == inc.sum() > 5_000_000
+    assert np.array_equal(st.d_dense.cpu().numpy()[inc], dense)
+    assert np.array_equal(st.size, np.bincount(dense))
+    fin = np.isfinite(gz[inc])
+    assert np.array_equal(st.count_finite, np.bincount(dense[fin], minlength=len(ids)))
+    mean = np.bincount(dense[fin], weights=gz[inc][fin], minlength=len(ids)) / np.maximum(st.count_finite, 1)
+    has = st.count_finite > 0
+    assert np.abs(st.mean_gz[has] - mean[has]).max() < 1e-9 and np.isnan(st.mean_gz[~has]).all()
+    order = np.argsort(dense, kind='stable')
+    assert np.array_equal(st.d_order.cpu().numpy().view(np.uint32)[:inc.sum()], np.where(inc)[0][order])
+    zmax = np.full(len(ids), -np.inf); np.maximum.at(zmax, dense, pts[inc, 2])
+    assert np.array_equal(st.max_z, zmax)
+
+    params = {'min_height': 1.2, 'max_height': 2.4, 'min_width': 1.4, 'max_width': 2.4, 'min_length': 3.0, 'max_length': 6.0}
+    car = CarFuser(Labels.CAR, ahn, road, grid_size=0.1, min_component_size=1500, params=params, exclude_types=[])
+    got = car.get_label_mask(pts, labels, mask, tc)
+    assert len(car.last_objects) >= 1
+    sub = pts[mask]
+    want = np.zeros(len(sub), dtype=bool)
+    for ring, bottom, top in car.last_objects:
+        _, _, w, l, _ = math_utils.minimum_bounding_rectangle(ring[:4])
+        assert 1.4 < w < 2.4 and 3.0 < l < 6.0
+        assert max(R.rect_overlap_percentage(ring, p) for p in tile20['road_polygons']) > 20
+        want |= R.poly_clip(sub, bgt_utils.RingPolygon(ring)) & ((sub[:, 2] <= top) & (sub[:, 2] >= bottom))
+    full = np.zeros(N20, dtype=bool); full[mask] = want
+    assert np.array_equal(got, full) and got.sum() > 10_000
+
+    poles = bgt_utils.ArrayBGTPointReader({tc: [('lichtmast', x, y) for x, y in tile20['pole_xy']]})
+    pole_params = {'min_height': 1.0, 'max_height': 12.0, 'min_width': 0.1, 'max_width': 6.0, 'min_length': 0.1, 'max_length': 6.0}
+    sf = BGTStreetFurnitureFuser(Labels.STREET_LIGHT, 'lichtmast', poles, ahn, grid_size=0.1, min_component_size=1500,
+                                 params=pole_params)
+    lm = sf.get_label_mask(pts, labels, mask, tc)
+    assert sf.last_accepted >= 1 and lm.sum() > 5_000 and not (lm & ~mask).any()
+    # whole clusters are labelled: the mask is a union of clusters of the same clustering
+    hit = np.bincount(dense, weights=lm[inc].astype(np.float64))
+    assert np.array_equal((hit > 0) & (hit < st.size), np.zeros(len(ids), dtype=bool)) and lm[~inc].sum() == 0

@@ -124,6 +124,35 @@ def test_las_ingest_scaled_on_device_and_process_file(tmp_path):
     assert np.array_equal(out.X, P[:, 0])
 
 
+def test_process_folder_pipelined_equals_per_file(tmp_path):
+    """Pipeline.process_folder (file i+1 read and file i-1 written on host threads while the device labels
+    file i) writes exactly what one process_file call per file writes; prefixes / suffix as the reference."""
+    from urban_pointcloud_processing_b200.utils import las_io, las_utils
+    scales, offsets = np.array([0.001, 0.001, 0.001]), np.array([100000.0, 400000.0, 0.0])
+    tiles, tcs = [], ['2386_9702', '2386_9703', '2387_9702']
+    in_dir, out_a, out_b = tmp_path / 'in', tmp_path / 'a', tmp_path / 'b'
+    in_dir.mkdir(); out_b.mkdir()
+    for k, tc in enumerate(tcs):
+        tile = synthetic.make_tile(60000 + 7000 * k, seed=300 + k)
+        P = np.rint((tile['points'] - offsets) / scales).astype(np.int32)
+        las_io.create(P, scales, offsets).write(str(in_dir / f'filtered_{tc}.las'))
+        tiles.append(tile)
+    (in_dir / 'notes.txt').write_text('ignored')
+    ahn = ahn_utils.ArrayAHNReader({tc: t['ahn_tile'] for tc, t in zip(tcs, tiles)})
+    bld = bgt_utils.ArrayBGTReader({tc: t['building_polygons'] for tc, t in zip(tcs, tiles)})
+    procs = (AHNFuser(Labels.GROUND, ahn, target='ground', epsilon=0.2, refine_ground=False),
+             BGTBuildingFuser(Labels.BUILDING, bgt_reader=bld, offset=0, ahn_reader=ahn),
+             RegionGrowing(Labels.BUILDING, exclude_labels=(Labels.GROUND,)))
+    pipe = Pipeline(processors=procs, ahn_reader=ahn, caching=True)
+    pipe.process_folder(str(in_dir), str(out_a), in_prefix='filtered_', out_prefix='labelled_')
+    for tc in tcs:
+        pipe.process_file(str(in_dir / f'filtered_{tc}.las'), str(out_b / f'labelled_{tc}.las'))
+        a, b = las_utils.read_las(str(out_a / f'labelled_{tc}.las')), las_utils.read_las(str(out_b / f'labelled_{tc}.las'))
+        assert np.array_equal(a.label, b.label) and np.array_equal(a.X, b.X) and (np.asarray(a.label) != 0).sum() > 10000
+    assert sorted(f.name for f in out_a.iterdir()) == sorted(f'labelled_{tc}.las' for tc in tcs)
+    assert pipe.process_folder(str(tmp_path / 'missing')) is None
+
+
 # ------------------------------------------------------------------------ raster ---
 def test_raster_lookup_matches_reference_golden(golden):
     g = golden('raster_golden.npz')

@@ -172,6 +172,36 @@ class Pipeline:
             del tile, d_labels
         return labels_list
 
+    def _load_file(self, in_file):
+        """Host side of process_file before the processors: read + parse (pipeline.py:114-121)."""
+        tilecode = las_utils.get_tilecode_from_filename(in_file)
+        pointcloud = las_utils.read_las(in_file)
+        if 'label' not in pointcloud.point_format.extra_dimension_names:
+            labels = np.zeros((pointcloud.header.point_count,), dtype='uint16')
+        else:
+            labels = np.asarray(pointcloud.label)
+        return tilecode, pointcloud, labels
+
+    def _label_file(self, tilecode, pointcloud, labels, mask=None):
+        """The processors on one loaded file; returns the final labels."""
+        if all(hasattr(obj, '_apply_device') for obj in self.processors):
+            # device path: raw int32 X, Y, Z up (12 B/pt), coordinates rebuilt in fp64 on the device
+            tile = dev.DeviceTile.from_las(pointcloud)
+            d_labels = dev.upload_labels(labels, tile.device)
+            self.process_tile_device(tilecode, tile, d_labels)
+            labels = np.array(labels, copy=True)
+            dev.download_labels(d_labels, labels)
+            return labels
+        points = np.vstack((pointcloud.x, pointcloud.y, pointcloud.z)).T
+        return self.process_cloud(tilecode, points, labels, mask)
+
+    def _save_file(self, pointcloud, labels, out_file, start):
+        las_utils.label_and_save_las(pointcloud, labels, out_file)
+        duration = time.time() - start
+        stats = analysis_tools.get_label_stats(labels)
+        logger.info('\nSTATISTICS\n' + stats)
+        logger.info(f'File processed in {duration:.2f}s, ' + f'output written to {out_file}.\n' + '=' * 20)
+
     def process_file(self, in_file, out_file=None, mask=None):
         """Process a single LAS file and save the result (pipeline.py:99-137); ``.laz`` needs laspy."""
         logger.info(f'Processing file {in_file}.')
@@ -181,27 +211,9 @@ class Pipeline:
             return None
         if out_file is None:
             out_file = in_file
-        tilecode = las_utils.get_tilecode_from_filename(in_file)
-        pointcloud = las_utils.read_las(in_file)
-        if 'label' not in pointcloud.point_format.extra_dimension_names:
-            labels = np.zeros((pointcloud.header.point_count,), dtype='uint16')
-        else:
-            labels = np.asarray(pointcloud.label)
-        if all(hasattr(obj, '_apply_device') for obj in self.processors):
-            # device path: raw int32 X, Y, Z up (12 B/pt), coordinates rebuilt in fp64 on the device
-            tile = dev.DeviceTile.from_las(pointcloud)
-            d_labels = dev.upload_labels(labels, tile.device)
-            self.process_tile_device(tilecode, tile, d_labels)
-            labels = np.array(labels, copy=True)
-            dev.download_labels(d_labels, labels)
-        else:
-            points = np.vstack((pointcloud.x, pointcloud.y, pointcloud.z)).T
-            labels = self.process_cloud(tilecode, points, labels, mask)
-        las_utils.label_and_save_las(pointcloud, labels, out_file)
-        duration = time.time() - start
-        stats = analysis_tools.get_label_stats(labels)
-        logger.info('\nSTATISTICS\n' + stats)
-        logger.info(f'File processed in {duration:.2f}s, ' + f'output written to {out_file}.\n' + '=' * 20)
+        tilecode, pointcloud, labels = self._load_file(in_file)
+        labels = self._label_file(tilecode, pointcloud, labels, mask)
+        self._save_file(pointcloud, labels, out_file, start)
 
     def process_folder(self, in_folder, out_folder=None, in_prefix='', out_prefix='', suffix='',
                        hide_progress=False):
@@ -221,12 +233,29 @@ class Pipeline:
         files = [f for f in in_folder.glob('*')
                  if f.name.endswith(self.FILE_TYPES) and f.name.startswith(in_prefix)]
         logger.debug(f'{len(files)} files found.')
+        jobs = []
         for file in files:
             filename, extension = os.path.splitext(file.name)
             if in_prefix and out_prefix:
                 filename = filename.replace(in_prefix, out_prefix)
             elif out_prefix:
                 filename = out_prefix + filename
-            outfile = os.path.join(out_folder, filename + suffix + extension)
-            self.process_file(file.as_posix(), outfile)
+            jobs.append((file.as_posix(), os.path.join(out_folder, filename + suffix + extension)))
+        # Files are independent (pipeline.py:186-194 handles them one after the other): while the device
+        # labels file i, one host thread already reads and parses file i+1 and another writes file i-1.
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(max_workers=1) as reader, ThreadPoolExecutor(max_workers=1) as writer:
+            loading = reader.submit(self._load_file, jobs[0][0]) if jobs else None
+            saving = None
+            for i, (in_file, outfile) in enumerate(jobs):
+                logger.info(f'Processing file {in_file}.')
+                start = time.time()
+                tilecode, pointcloud, labels = loading.result()
+                loading = reader.submit(self._load_file, jobs[i + 1][0]) if i + 1 < len(jobs) else None
+                labels = self._label_file(tilecode, pointcloud, labels)
+                if saving is not None:
+                    saving.result()                         # one write in flight at a time; surfaces I/O errors
+                saving = writer.submit(self._save_file, pointcloud, labels, outfile, start)
+            if saving is not None:
+                saving.result()
         logger.info(f'Pipeline finished, {len(files)} processed.\n' + '=' * 20)
