@@ -714,19 +714,27 @@ knn_epilogue_kernel(EpilogueArgs a) {
                 }
             }
         }
-        // phase 2: insertion sort of the packed keys
+        // phase 2: insertion sort of the packed keys.  ONE flat loop whose step is either "shift one
+        // entry" or "place and fetch the next": a lane's trip count is its own n + inversions, so the
+        // warp pays the maximum over its lanes once instead of the maximum per inserted element.
         bool tie = false;
-        for (int j = 1; j < n; ++j) {
-            const uint64_t kj = s_key[j * kEpiThreads + tx];
-            int i = j;
-            while (i > 0) {
-                const uint64_t kp = s_key[(i - 1) * kEpiThreads + tx];
-                tie |= ((kp ^ kj) >> 6) == 0;
-                if (kp <= kj) break;
-                s_key[i * kEpiThreads + tx] = kp;
-                --i;
+        {
+            int j = 1, i = 1;
+            uint64_t kj = n > 1 ? s_key[kEpiThreads + tx] : 0;
+            while (j < n) {
+                const uint64_t kp = i > 0 ? s_key[(i - 1) * kEpiThreads + tx] : 0;
+                const bool shift = i > 0 && kp > kj;
+                tie |= i > 0 && ((kp ^ kj) >> 6) == 0;
+                if (shift) {
+                    s_key[i * kEpiThreads + tx] = kp;
+                    --i;
+                } else {
+                    if (i != j) s_key[i * kEpiThreads + tx] = kj;
+                    ++j;
+                    i = j;
+                    if (j < n) kj = s_key[j * kEpiThreads + tx];
+                }
             }
-            if (i != j) s_key[i * kEpiThreads + tx] = kj;
         }
         if (tie) {
             // exact order inside runs of keys that agree in their upper 58 bits (rare)
