@@ -192,6 +192,7 @@ struct BlockArgs {
     uint32_t* out_pos; uint8_t* out_cnt;               // rows [kRow][m], counts [m]
     uint8_t* todo;                                     // [m] 1 = not served by this tier
     int k_row; double radius2;                         // kNN row length, squared normal-estimation radius
+    uint32_t max_total;                                // blocks with more candidates go to the next tier (<= 60000: u16 counters)
 };
 
 // One lane per query; see the header comment.  The per-lane histogram is kBuckets counters in
@@ -260,7 +261,7 @@ knn_block_kernel(BlockArgs a) {
             }
         }
         // (u16 counters: a block with more candidates than they can count goes to the next tier)
-        if (total < (uint32_t)a.k_row || total > 60000u) active = false;
+        if (total < (uint32_t)a.k_row || total > a.max_total) active = false;
         if (!__any_sync(kFull, active)) {
             if (valid) a.todo[q] = 1;
             continue;
@@ -890,6 +891,13 @@ static int knn_impl(const double* d_x, const double* d_y, const double* d_z, int
     ba.spts = spts; ba.spf = spf; ba.cell_first = cell_first; ba.g = g; ba.m = m; ba.k = kh;
     ba.q_idx = nullptr; ba.q_cnt = nullptr; ba.out_pos = nb_pos; ba.out_cnt = nb_cnt; ba.todo = todo[0];
     ba.k_row = knn < kh ? knn : kh; ba.radius2 = radius * radius;
+    // A lane that has to scan a crowded 5^3 block alone holds its whole warp up; such queries are better
+    // served by the warp-per-query tier, which prunes (swept on the bench tile: 60000 / 4000 / 1500 / 600 /
+    // 300 candidates -> 17.6 / 17.4 / 17.2 / 16.5 / 17.0 ms for the search).
+    uint32_t max_total1 = 60000u, max_total2 = 600u;
+    if (const char* env = getenv("UPCP_BLK1_MAXTOTAL")) { int v = atoi(env); if (v >= 1 && v <= 60000) max_total1 = (uint32_t)v; }
+    if (const char* env = getenv("UPCP_BLK2_MAXTOTAL")) { int v = atoi(env); if (v >= 1 && v <= 60000) max_total2 = (uint32_t)v; }
+    ba.max_total = max_total1;
     // the filter passes live on L1 hits (each candidate is read by ~150 queries, twice): keep the
     // shared-memory carve-out at what the resident CTAs need, the rest of the 256 KB stays L1
     UPCP_CUDA_OK(cudaFuncSetAttribute(knn_block_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, 40));
@@ -908,7 +916,7 @@ static int knn_impl(const double* d_x, const double* d_y, const double* d_z, int
         TodoFunctor f{idx};
         UPCP_TRY(compact_apply(prev, m, cnt, prim_ws, st, f));
         UPCP_CUDA_OK(cudaMemsetAsync(next, 0, (size_t)m, st));
-        ba.q_idx = idx; ba.q_cnt = cnt; ba.todo = next;
+        ba.q_idx = idx; ba.q_cnt = cnt; ba.todo = next; ba.max_total = max_total2;
         const int grid = num_sms() * 8;
         if (tier == 2) knn_block_kernel<2><<<grid, kBlkThreads, 0, st>>>(ba);
         else if (tier == 3) knn_block_kernel<3><<<grid, kBlkThreads, 0, st>>>(ba);
