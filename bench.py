@@ -227,6 +227,8 @@ def main():
     ap.add_argument('--cpu-sample', type=int, default=2_000_000, dest='cpu_sample')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--workers', type=int, default=3,
+                    help='tiles in flight per GPU (one CUDA stream + host thread each) in the batch arms')
     ap.add_argument('--min-warmup', type=int, default=3, dest='min_warmup',
                     help='timing rule W >= 3; lower only for profiler runs whose numbers are never reported')
     args = ap.parse_args()
@@ -324,13 +326,35 @@ def main():
     launches0 = _lib.launch_count()
     t_begin = time.perf_counter()
     ms_dev, wall_dev, hist = timed(device_step, args.steps)
-    t_end = time.perf_counter()
     launches = _lib.launch_count() - launches0
+    prof = _lib.prof_read()
+    _lib.prof_enable(False)
+
+    # ---- timed region 2: the same K device-resident tile passes, `workers` tiles in flight (one stream and
+    # host thread each, Pipeline.process_tiles_device).  No per-kernel brackets here: kernels of different
+    # tiles overlap, the roofline numbers come from the single-stream region above.
+    conc = None
+    if args.workers > 1:
+        bufs = [torch.empty_like(d_labels0) for _ in range(args.steps)]
+
+        def concurrent_steps():
+            for b_ in bufs:
+                b_.copy_(d_labels0)
+            pipeline.process_tiles_device([tc] * len(bufs), [d_tile] * len(bufs), bufs, workers=args.workers)
+            return [dev.label_hist(b_) for b_ in bufs][-1]
+        saved, bufs = bufs, bufs[:min(len(bufs), 2 * args.workers)]
+        concurrent_steps()                                   # warm-up: worker streams, their scratch buffers
+        bufs = saved
+        launches1 = _lib.launch_count()
+        ms_c, wall_c, hist_c = timed(concurrent_steps, 1)
+        conc = {'ms_per_step': ms_c / args.steps, 'value': world * n * args.steps / (ms_c * 1e-3) / 1e6,
+                'launches': _lib.launch_count() - launches1, 'wall_ms_per_step': wall_c / args.steps,
+                'labels_equal_single_stream': bool(torch.equal(bufs[-1], d_labels) and torch.equal(bufs[0], d_labels))}
+        del bufs, saved
+    t_end = time.perf_counter()
     if rank == 0:
         sampler.window(t_begin, t_end)
     clocks = sampler.stop() if rank == 0 else None
-    prof = _lib.prof_read()
-    _lib.prof_enable(False)
     stage_s = []
     pipeline.process_tile_device(tc, d_tile, d_labels.copy_(d_labels0), sync_timings=True)
     stage_s = [(name, round(sec * 1e3, 3)) for name, sec in pipeline.last_timings]
@@ -367,17 +391,22 @@ def main():
 
         def batch_call():
             k_ = len(lab_bufs)
-            pipeline.process_clouds([tc] * k_, [points_host] * k_, [b_.numpy().view(np.uint16) for b_ in lab_bufs])
+            pipeline.process_clouds([tc] * k_, [points_host] * k_, [b_.numpy().view(np.uint16) for b_ in lab_bufs],
+                                    workers=args.workers)
         reset_labels()
-        pipeline.process_clouds([tc] * 2, [points_host] * 2, [b_.numpy().view(np.uint16) for b_ in lab_bufs[:2]])
+        k_w = min(len(lab_bufs), 2 * max(args.workers, 1))
+        pipeline.process_clouds([tc] * k_w, [points_host] * k_w, [b_.numpy().view(np.uint16) for b_ in lab_bufs[:k_w]],
+                                workers=args.workers)
         reset_labels()
         ms_b, wall_b, _ = timed(batch_call, 1)
         b_ms = max(ms_b, wall_b)
         e2e_batch = {'value': world * n * args.steps / (b_ms * 1e-3) / 1e6, 'unit': 'Mpts/s',
                      'ms_per_step': b_ms / args.steps,
                      'h2d_bytes_per_step': int(n * 24 + n * 2), 'd2h_bytes_per_step': int(n * 2),
-                     'api': f'Pipeline.process_clouds(tilecodes, clouds, labels_list) over {args.steps} tiles, numpy arrays in '
-                            'pinned host memory; the H2D of tile i+1 overlaps the kernels of tile i (second stream)',
+                     'api': f'Pipeline.process_clouds(tilecodes, clouds, labels_list, workers={args.workers}) over {args.steps} '
+                            'tiles, numpy arrays in pinned host memory; each worker (host thread + CUDA stream) uploads, '
+                            'labels and downloads one tile at a time, so copies and latency-bound phases of one tile '
+                            'overlap the kernels of the others',
                      'labels_equal_device_arm': bool(all(
                          np.array_equal(b_.numpy().view(np.uint16).astype(np.int32), d_labels.cpu().numpy())
                          for b_ in (lab_bufs[0], lab_bufs[-1])))}
@@ -420,6 +449,12 @@ def main():
 
     step_ms = max(ms_dev, 0.0) / args.steps
     value = world * n * args.steps / (ms_dev * 1e-3) / 1e6
+    single = {'value': value, 'ms_per_step': step_ms, 'gpu_launches': int(launches),
+              'what': 'one tile at a time on one stream (the region the roofline brackets were taken in)'}
+    tiles_in_flight = 1
+    if conc and conc['value'] > value and conc['labels_equal_single_stream']:
+        value, step_ms, launches, tiles_in_flight = conc['value'], conc['ms_per_step'], conc['launches'], args.workers
+        wall_dev = conc['wall_ms_per_step'] * args.steps
     peak, peak_src = peaks()
     # dominant kernel = largest bracketed share of the step
     top = max(prof.items(), key=lambda kv: kv[1][0])
@@ -433,6 +468,7 @@ def main():
                 'algorithmic_bytes_per_launch': alg_bytes, 'peak_source': peak_src,
                 'algorithmic_bytes_per_point': B_ALG[name], 'points_per_launch': units_per_launch,
                 'launch_ms': per_launch_ms, 'share_of_step': tot_ms / max(ms_dev, 1e-9),
+                'region': 'single-stream timed region (K steps, one tile at a time); `value` may come from the region with several tiles in flight',
                 'kernels_ms_per_step': {k: round(v[0] / args.steps, 3) for k, v in prof.items()},
                 # algorithmic GB/s of every bracketed kernel (B_ALG x units / bracketed time), fraction of the peak
                 'kernels_algorithmic_gbs': {k: [round(B_ALG[k] * v[2] / (v[0] * 1e-3) / 1e9, 1),
@@ -457,7 +493,8 @@ def main():
             'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
             'config': {'workload': WORKLOAD.format(n=n), 'tiles_per_step': world, 'points_per_tile': n,
                        'l2_policy': 'inputs (480 MB of coordinates per tile) are larger than the 126 MB L2',
-                       'tiles_per_s': world * args.steps / (ms_dev * 1e-3)},
+                       'tiles_per_s': value * 1e6 / n, 'tiles_in_flight_per_gpu': tiles_in_flight},
+            'single_stream': single, 'concurrent': conc,
             'clocks': clocks, 'e2e': e2e_head, 'e2e_process_cloud': e2e, 'e2e_las': e2e_las, 'gpu_launches': int(launches), 'roofline': roofline,
             'cpu_baseline': cpu_baseline, 'stage_ms': stage_s, 'points_labelled_last_step': labelled,
             'wall_ms_per_step': wall_dev / args.steps}

@@ -387,11 +387,23 @@ def test_process_clouds_batch_equals_per_tile_calls():
     want = [pipe.process_cloud(tc, c, np.zeros(len(c), dtype=np.uint16)) for tc, c in zip(tcs, clouds)]
     dev.clear_tile_cache()
     labels = [np.zeros(len(c), dtype=np.uint16 if k != 1 else np.uint8) for k, c in enumerate(clouds)]
-    out = pipe.process_clouds(tcs, clouds, labels)
-    assert all(o is l for o, l in zip(out, labels))
-    for k in range(len(tiles)):
-        assert np.array_equal(labels[k], want[k]), k
-        assert (labels[k] != 0).sum() > 1000
+    for workers in (2, 1, 3):                   # tiles in flight: worker threads + streams / one stream + copy stream
+        labels = [np.zeros(len(c), dtype=np.uint16 if k != 1 else np.uint8) for k, c in enumerate(clouds)]
+        out = pipe.process_clouds(tcs, clouds, labels, workers=workers)
+        assert all(o is l for o, l in zip(out, labels))
+        for k in range(len(tiles)):
+            assert np.array_equal(labels[k], want[k]), (workers, k)
+            assert (labels[k] != 0).sum() > 1000
+    # device-resident batch, the same tile several times over (shared read-only inputs)
+    d_tiles = [dev.DeviceTile(c) for c in clouds]
+    reps = [0, 1, 2, 3, 0, 0, 2]
+    d_labels = [torch.zeros(d_tiles[k].n, dtype=torch.int32, device=d_tiles[k].device) for k in reps]
+    pipe.process_tiles_device([tcs[k] for k in reps], [d_tiles[k] for k in reps], d_labels, workers=3)
+    for k, d in zip(reps, d_labels):
+        assert np.array_equal(d.cpu().numpy(), want[k].astype(np.int32))
+    # a failing tile surfaces in the caller
+    with pytest.raises(Exception):
+        pipe.process_clouds(tcs[:2] + ['0000_0000'], clouds[:3], [np.zeros(len(c), np.uint16) for c in clouds[:3]], workers=2)
     assert pipe.process_clouds([], [], []) == []
     with pytest.raises(ValueError):
         pipe.process_clouds(tcs[:2], clouds[:1], labels[:2])

@@ -56,12 +56,39 @@ class Workspace:
 _workspaces = {}
 
 
+def stream_key(device=None):
+    """Handle of the current CUDA stream: scratch memory and cached device objects are kept per
+    stream, so that tiles in flight on different streams (Pipeline.process_clouds workers) never
+    share a buffer and freed memory is only ever recycled in stream order."""
+    return int(torch.cuda.current_stream(device).cuda_stream)
+
+
 def workspace(device, slot=0):
-    key = (str(device), slot)
+    key = (str(device), slot, stream_key(device))
     ws = _workspaces.get(key)
     if ws is None:
         ws = _workspaces[key] = Workspace(device)
     return ws
+
+
+_worker_streams = {}
+
+
+def worker_stream(device, name):
+    """Persistent side stream ``name`` of ``device``.  The streams are created once and re-used by
+    every batch call: the caching allocator keeps freed blocks per stream, so fresh streams per call
+    would strand the previous call's memory in pools nobody allocates from any more."""
+    key = (str(device), name)
+    st = _worker_streams.get(key)
+    if st is None:
+        st = _worker_streams[key] = torch.cuda.Stream(device)
+    return st
+
+
+def release_workspaces(device, stream_handle):
+    """Drop the scratch buffers of one stream (a finished worker)."""
+    for key in [k for k in list(_workspaces) if k[0] == str(device) and k[2] == int(stream_handle)]:
+        _workspaces.pop(key, None)
 
 
 def current_device():

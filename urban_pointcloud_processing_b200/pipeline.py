@@ -130,15 +130,81 @@ class Pipeline:
             dev.download_labels(d_labels, labels)
         return labels
 
-    def process_clouds(self, tilecodes, clouds, labels_list):
+    def _run_tile_workers(self, n_tiles, workers, body):
+        """Run ``body(i)`` for i in 0..n_tiles-1 on ``workers`` host threads, each with its own CUDA
+        stream (and therefore its own scratch buffers, see device.workspace).  Tiles are independent;
+        having 2-3 of them in flight lets the device fill the latency-bound phases of one tile
+        (frontier growth, union-find linking, host round trips, uploads) with the kernels of another.
+        Tiles are handed out from a shared counter.  The first exception of a worker is re-raised."""
+        import threading
+
+        import torch
+        device = dev.current_device()
+        lock = threading.Lock()
+        state = {'next': 0}
+        errors = []
+
+        def take():
+            with lock:
+                i = state['next']
+                state['next'] = i + 1
+            return i
+
+        def run(k):
+            try:
+                torch.cuda.set_device(device)               # the current device is per host thread
+                stream = dev.worker_stream(device, k)       # persistent: its scratch buffers are re-used
+                with torch.cuda.stream(stream):
+                    while not errors:
+                        i = take()
+                        if i >= n_tiles:
+                            break
+                        body(i)
+                    stream.synchronize()
+            except BaseException as exc:                    # noqa: BLE001 -- handed to the caller
+                errors.append(exc)
+
+        threads = [threading.Thread(target=run, args=(k,), name=f'upcp-tile-worker-{k}') for k in range(workers)]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        if errors:
+            raise errors[0]
+
+    def process_tiles_device(self, tilecodes, tiles, d_labels_list, workers=2):
+        """``process_tile_device`` for a batch of device-resident tiles, ``workers`` tiles in flight
+        (one CUDA stream and host thread each).  Every ``d_labels_list[i]`` is updated in place."""
+        n_tiles = len(tilecodes)
+        if not (len(tiles) == n_tiles and len(d_labels_list) == n_tiles):
+            logger.error('tilecodes, tiles and d_labels_list must have the same length')
+            raise ValueError
+        workers = max(1, min(int(workers), n_tiles))
+        if workers == 1:
+            for tc, tile, d_labels in zip(tilecodes, tiles, d_labels_list):
+                self.process_tile_device(tc, tile, d_labels)
+            return d_labels_list
+        import torch
+        main = torch.cuda.current_stream()
+        ready = main.record_event()                         # whatever produced the inputs on the caller's stream
+
+        def body(i):
+            torch.cuda.current_stream().wait_event(ready)
+            self.process_tile_device(tilecodes[i], tiles[i], d_labels_list[i])
+        self._run_tile_workers(n_tiles, workers, body)       # workers synchronise their streams before returning
+        return d_labels_list
+
+    def process_clouds(self, tilecodes, clouds, labels_list, workers=2):
         """Process a batch of point clouds (what ``process_folder`` does file by file,
         pipeline.py:186-194, for clouds that are already in host memory).
 
-        Tiles are independent, so while the kernels of tile ``i`` run, the coordinates and
-        labels of tile ``i + 1`` are already on their way to the device on a second CUDA stream
-        (truly asynchronous when the host arrays are pinned; from pageable memory the copies
-        simply serialise).  Per tile the result is exactly that of ``process_cloud``: every
-        ``labels_list[i]`` is updated in place.  Returns ``labels_list``.
+        Tiles are independent, so ``workers`` of them are in flight at once, each on its own CUDA
+        stream driven by its own host thread: while one tile is being uploaded (truly asynchronous
+        when the host arrays are pinned) or sits in a latency-bound phase, the kernels of another
+        run.  With ``workers=1`` a single stream is used and only the upload of tile ``i + 1`` is
+        overlapped with the kernels of tile ``i`` (second copy stream).  Per tile the result is
+        exactly that of ``process_cloud``: every ``labels_list[i]`` is updated in place.  Returns
+        ``labels_list``.
         """
         import torch
         n_tiles = len(tilecodes)
@@ -150,8 +216,17 @@ class Pipeline:
                 self.process_cloud(tc, pts, lab)
             return labels_list
         device = dev.current_device()
+        workers = max(1, min(int(workers), n_tiles))
+        if workers > 1:
+            def body(i):
+                tile = dev.DeviceTile(clouds[i], device)
+                d_labels = dev.upload_labels(labels_list[i], device)
+                self.process_tile_device(tilecodes[i], tile, d_labels)
+                dev.download_labels(d_labels, labels_list[i])
+            self._run_tile_workers(n_tiles, workers, body)
+            return labels_list
         main = torch.cuda.current_stream(device)
-        side = torch.cuda.Stream(device)
+        side = dev.worker_stream(device, 'copy')
 
         def prefetch(i):
             # the side stream may recycle memory the main stream has finished with

@@ -64,7 +64,7 @@ class AHNReader(ABC):
     # -- device side -----------------------------------------------------------
     def device_raster(self, tilecode, surface='ground_surface'):
         """HBM-resident raster (bin edges + values) of one surface of one tile."""
-        key = (tilecode, surface, str(dev.current_device()))
+        key = (tilecode, surface, str(dev.current_device()), dev.stream_key())
         raster = self._rasters.get(key)
         if raster is None:
             ahn_tile = self.filter_tile(tilecode)
@@ -178,7 +178,7 @@ def device_raster_for(ahn_reader, tilecode, surface):
             ahn_reader._upcp_b200_rasters = cache
         except AttributeError:
             pass
-    key = (tilecode, surface, str(dev.current_device()))
+    key = (tilecode, surface, str(dev.current_device()), dev.stream_key())
     raster = cache.get(key)
     if raster is None:
         ahn_tile = ahn_reader.filter_tile(tilecode)
