@@ -227,7 +227,7 @@ def main():
     ap.add_argument('--cpu-sample', type=int, default=2_000_000, dest='cpu_sample')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
-    ap.add_argument('--workers', type=int, default=3,
+    ap.add_argument('--workers', type=int, default=4,
                     help='tiles in flight per GPU (one CUDA stream + host thread each) in the batch arms')
     ap.add_argument('--min-warmup', type=int, default=3, dest='min_warmup',
                     help='timing rule W >= 3; lower only for profiler runs whose numbers are never reported')
