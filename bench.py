@@ -11,7 +11,12 @@ scaling, no collective on the hot path); the per-tile label histograms are gathe
 one NCCL all_gather after the timed steps.
 
   value  device-resident throughput: tile coordinates already in HBM, labels reset on the
-         device, pipeline chained on the device, label histogram left on the device.
+         device, pipeline chained on the device, label histogram left on the device.  Two
+         regions of K steps each are timed: one tile at a time on one stream (`single_stream`;
+         the per-kernel cudaEvent brackets, hence `roofline`, are taken here) and `--workers`
+         tiles in flight, one CUDA stream + host thread each (`concurrent`,
+         Pipeline.process_tiles_device).  `value` / `ms_per_step` are those of the faster region
+         whose labels equal the single-stream ones; `config.tiles_in_flight_per_gpu` says which.
   e2e    the same pipeline through the reference-facing plugin API
          (Pipeline.process_cloud(tilecode, points, labels) with numpy arrays living in
          PINNED host memory): H2D of the points + labels and D2H of the labels inside the
