@@ -255,3 +255,31 @@ def test_native_las_io_round_trip(tmp_path):
     except ImportError:
         with pytest.raises(ImportError):
             las_utils.read_las(str(tmp_path / 'x_2386_9702.laz'))
+
+
+def test_bgt_point_reader_matches_reference_semantics(tmp_path):
+    """utils.bgt_utils.BGTPointReader (bgt_utils.py:97-126): inclusive tile bbox with padding, type include /
+    exclude lists, tuples with or without the type; and, where /root/reference is present, the reference's own
+    reader on the same file."""
+    import pandas as pd
+    rows = [('lichtmast', 119300.0, 485100.0), ('lichtmast', 119350.0, 485150.0), ('boom', 119325.5, 485120.25),
+            ('verkeersbord', 119350.5, 485120.0), ('lichtmast', 119299.5, 485149.0), ('boom', 119400.0, 485100.0)]
+    path = str(tmp_path / 'bgt_points.csv')
+    pd.DataFrame(rows, columns=['bgt_type', 'x', 'y']).to_csv(path, index=False)
+    reader = bgt_utils.BGTPointReader(bgt_file=path)
+    assert reader.filter_tile('2386_9702') == [(119300.0, 485100.0), (119350.0, 485150.0), (119325.5, 485120.25)]
+    assert reader.filter_tile('2386_9702', bgt_types=['lichtmast']) == [(119300.0, 485100.0), (119350.0, 485150.0)]
+    assert reader.filter_tile('2386_9702', exclude_types=['lichtmast']) == [(119325.5, 485120.25)]
+    padded = reader.filter_tile('2386_9702', padding=1, return_types=True)
+    assert [tuple(r) for r in padded] == [tuple(r) for r in rows[:5]]
+    assert bgt_utils.get_points(path, '2386_9702', return_types=False) == reader.filter_tile('2386_9702')
+    arr = bgt_utils.ArrayBGTPointReader({'2386_9702': rows})
+    assert arr.filter_tile('2386_9702', bgt_types=['boom']) == [(119325.5, 485120.25), (119400.0, 485100.0)]
+    assert arr.filter_tile('0000_0000') == []
+    from oracle import ref_harness
+    if ref_harness.available():
+        ref_harness.load_reference()
+        from upcp.utils.bgt_utils import BGTPointReader as RefReader
+        ref = RefReader(bgt_file=path)
+        for kw in ({}, {'bgt_types': ['lichtmast']}, {'exclude_types': ['boom']}, {'padding': 1}):
+            assert reader.filter_tile('2386_9702', **kw) == [tuple(p) for p in ref.filter_tile('2386_9702', **kw)]
