@@ -38,7 +38,7 @@ struct ProfBracket { cudaEvent_t a, b; int64_t units; };
 static std::mutex g_prof_mu;
 static std::atomic<int> g_prof_on{0};
 static std::vector<ProfBracket> g_prof[UPCP_PROF_SLOTS];
-static cudaEvent_t g_prof_open[UPCP_PROF_SLOTS];
+static thread_local cudaEvent_t g_prof_open[UPCP_PROF_SLOTS];   // per host thread: begin / end pair up on the thread's own stream
 
 void prof_begin(int slot, cudaStream_t st) {
     if (!g_prof_on.load(std::memory_order_relaxed)) return;

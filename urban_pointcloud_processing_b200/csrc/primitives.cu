@@ -285,11 +285,8 @@ static int radix_sort_impl(K* keys_a, uint32_t* vals_a, K* keys_b, uint32_t* val
     uint32_t* hist = d_ws;
     uint32_t* scan_ws = d_ws + align_up((size_t)kRsBins * n_tiles * 4) / 4;
     const size_t smem = (size_t)kRsTile * (sizeof(K) + 4) + ((kRsThreads / 32) * kRsBins + 2 * kRsBins + 16) * 4;
-    static bool attr_set = false;
-    if (!attr_set || true) {
-        UPCP_CUDA_OK(cudaFuncSetAttribute(rs_scatter_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
-    }
+    // (set on every call: the attribute is per device, and callers may drive several devices / threads)
+    UPCP_CUDA_OK(cudaFuncSetAttribute(rs_scatter_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int grid = n_tiles < num_sms() * 4 ? n_tiles : num_sms() * 4;
     K* kin = keys_a; uint32_t* vin = vals_a; K* kout = keys_b; uint32_t* vout = vals_b;
     bool in_b = false;
