@@ -207,3 +207,86 @@ def test_minimum_bounding_rectangle_and_overlap_host_logic(golden):
         box = (np.array([[-2.2, -0.9], [2.2, -0.9], [2.2, 0.9], [-2.2, 0.9], [-2.2, -0.9]]) @ rot.T) + c
         for road in tile['road_polygons']:
             assert abs(object_utils.overlap_percentage(box, road) - R.rect_overlap_percentage(box, road)) < 1e-9
+
+
+# ---------- natives with no reference golden ("parity unpinned"): independent cross-checks ----------
+def test_cc_native_connectivity_against_scipy_ndimage():
+    """The graph half of the cccorelib restatement: components of occupied cells under 26-connectivity must
+    be what scipy.ndimage.label finds on the same voxel grid (the cell arithmetic itself is DgmOctree's and
+    stays unpinned; here it is only re-used to rasterise)."""
+    from scipy import ndimage
+    rng = np.random.default_rng(12)
+    blobs = [rng.normal(c, s, (n, 3)) for c, s, n in (((2, 2, 2), 0.3, 1500), ((6, 2, 2), 0.5, 2500),
+                                                      ((4, 7, 3), 0.2, 800), ((8, 8, 8), 0.05, 300))]
+    pts = np.vstack(blobs + [rng.random((400, 3)) * 10]).astype(np.float32)
+    for level in (4, 6, 8):
+        got = natives.label_connected_components(pts[:, 0], pts[:, 1], pts[:, 2], level).astype(np.int64)
+        mn = natives.octree_params(pts[:, 0], pts[:, 1], pts[:, 2])
+        cs = mn[3]
+        pos = np.empty((len(pts), 3), dtype=np.int64)
+        for d in range(3):                                          # float32 arithmetic, clamp, then >> (21 - level)
+            q = ((pts[:, d] - mn[d]) / cs).astype(np.float32)
+            pos[:, d] = np.clip(q.astype(np.int64), 0, (1 << 21) - 1) >> (21 - level)
+        grid = np.zeros((1 << level,) * 3, dtype=bool) if level <= 6 else None
+        if grid is not None:
+            grid[pos[:, 0], pos[:, 1], pos[:, 2]] = True
+            lab, k = ndimage.label(grid, structure=np.ones((3, 3, 3)))
+            want = lab[pos[:, 0], pos[:, 1], pos[:, 2]]
+        else:                                                       # level 8: sparse graph instead of a dense volume
+            from scipy.sparse import coo_matrix
+            from scipy.sparse.csgraph import connected_components
+            cells, inv = np.unique(pos, axis=0, return_inverse=True)
+            index = {tuple(c): i for i, c in enumerate(cells)}
+            rows, cols = [], []
+            for i, c in enumerate(cells):
+                for off in np.ndindex(3, 3, 3):
+                    j = index.get((c[0] + off[0] - 1, c[1] + off[1] - 1, c[2] + off[2] - 1))
+                    if j is not None and j != i:
+                        rows.append(i); cols.append(j)
+            k, comp = connected_components(coo_matrix((np.ones(len(rows)), (rows, cols)), shape=(len(cells),) * 2))
+            want = comp[inv.ravel()] + 1
+        assert got.min() == 1 and got.max() == k
+        assert np.array_equal(R.canonical_components(got.astype(np.float64)), R.canonical_components(want.astype(np.float64)))
+
+
+def test_normals_and_covariance_natives_against_lapack():
+    """The Open3D restatement (hybrid search, cumulant covariance, FastEigen3x3 normal) against an independent
+    formulation: cKDTree neighbourhoods, two-pass covariance, LAPACK eigh.  Normals agree up to sign within the
+    perturbation bound of the single-pass covariance wherever the two smallest eigenvalues are separated; points with fewer than 3 neighbours inside the
+    radius get (0, 0, 1)."""
+    from scipy.spatial import cKDTree
+    tile = synthetic.make_tile(30000, seed=17, facade_fraction=0.6)
+    pts = tile['points'][tile['kind'] != 0]
+    radius, max_nn, knn = 0.2, 30, 15
+    nrm = natives.normals_hybrid(pts, radius, max_nn)
+    tree = cKDTree(pts)
+    dist, idx = tree.query(pts, k=max_nn)
+    inside = dist < radius                                           # strict, as nanoflann's radius test on d2 < r2
+    checked = defaults = 0
+    for i in range(0, len(pts), 2):
+        nb = pts[idx[i][inside[i]]]
+        if len(nb) < 3:
+            assert np.array_equal(nrm[i], [0.0, 0.0, 1.0])
+            defaults += 1
+            continue
+        c = np.cov((nb - nb.mean(axis=0)).T, bias=True)
+        w, v = np.linalg.eigh(c)
+        gap = w[1] - w[0]
+        if gap < 1e-3 * max(w[2], 1e-30):                            # smallest eigenvector ill-defined: skip
+            continue
+        # Open3D accumulates the cumulants on the unshifted RD coordinates (y ~ 4.9e5): its covariance carries an
+        # absolute error ~ eps * y^2 ~ 1e-4, which turns the eigenvector by at most ~ error / gap
+        sin_bound = 2e-4 / gap
+        assert 1.0 - abs(np.dot(v[:, 0], nrm[i])) < max(1e-9, sin_bound * sin_bound), (i, gap)
+        checked += 1
+    assert checked > 800 and defaults > 5
+    rows = natives.knn(pts, knn)
+    cov6 = natives.cov_knn(pts, rows)
+    for i in range(0, len(pts), 11):
+        nb = pts[rows[i][rows[i] >= 0]]
+        want = np.cov((nb - nb.mean(axis=0)).T, bias=True)
+        got = natives.cov6_to_matrix(cov6[i])
+        # single-pass cumulants on unshifted RD coordinates (x ~ 1.2e5, y ~ 4.9e5): absolute error ~ eps * y^2
+        assert np.abs(got - want).max() < 5e-4, i
+    ev = natives.fast_eigen(cov6[::11])
+    assert ev.shape == (len(cov6[::11]), 3)
