@@ -283,3 +283,68 @@ def test_bgt_point_reader_matches_reference_semantics(tmp_path):
         ref = RefReader(bgt_file=path)
         for kw in ({}, {'bgt_types': ['lichtmast']}, {'exclude_types': ['boom']}, {'padding': 1}):
             assert reader.filter_tile('2386_9702', **kw) == [tuple(p) for p in ref.filter_tile('2386_9702', **kw)]
+
+
+def test_tile_worker_scheduling_host_logic(monkeypatch):
+    """Pipeline._run_tile_workers (the host side of 'several tiles in flight'): every tile is handed out exactly
+    once, each worker thread runs inside its own persistent stream, the first exception is re-raised and stops
+    the hand-out.  CUDA is stood in for by recording stubs -- the test covers the scheduling, not the kernels."""
+    import contextlib
+    import threading
+
+    import torch
+
+    from urban_pointcloud_processing_b200 import device as dev
+    from urban_pointcloud_processing_b200.pipeline import Pipeline
+
+    class FakeStream:
+        def __init__(self, name):
+            self.name, self.synced = name, 0
+
+        def synchronize(self):
+            self.synced += 1
+
+    streams, entered = {}, []
+    tls = threading.local()
+
+    def worker_stream(device, name):
+        return streams.setdefault(name, FakeStream(name))
+
+    @contextlib.contextmanager
+    def stream_ctx(stream):
+        tls.stream = stream
+        entered.append(stream.name)
+        yield
+        tls.stream = None
+
+    monkeypatch.setattr(dev, 'current_device', lambda: 'cuda:0')
+    monkeypatch.setattr(dev, 'worker_stream', worker_stream)
+    monkeypatch.setattr(torch.cuda, 'set_device', lambda d: None)
+    monkeypatch.setattr(torch.cuda, 'stream', stream_ctx)
+    pipe = Pipeline(processors=(), caching=False)
+    for n_tiles, workers in ((11, 3), (2, 4), (0, 2), (5, 1)):
+        seen, lock = [], threading.Lock()
+        streams.clear(); entered.clear()
+
+        def body(i):
+            with lock:
+                seen.append((i, tls.stream.name))
+        pipe._run_tile_workers(n_tiles, workers, body)
+        assert sorted(i for i, _ in seen) == list(range(n_tiles))
+        assert sorted(entered) == list(range(workers)) and all(s.synced == 1 for s in streams.values())
+        assert {name for _, name in seen} <= set(range(workers))
+
+    done = []
+
+    def failing(i):
+        if i == 3:
+            raise RuntimeError('tile 3 is broken')
+        done.append(i)
+    with pytest.raises(RuntimeError, match='tile 3'):
+        pipe._run_tile_workers(200, 2, failing)
+    assert len(done) < 199                                    # the hand-out stopped early
+    # argument checks happen before any device work
+    with pytest.raises(ValueError):
+        pipe.process_clouds(['a', 'b'], [None], [None, None])
+    with pytest.raises(ValueError):
+        pipe.process_tiles_device(['a'], [], [None])
