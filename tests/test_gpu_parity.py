@@ -150,6 +150,11 @@ def test_process_folder_pipelined_equals_per_file(tmp_path):
         a, b = las_utils.read_las(str(out_a / f'labelled_{tc}.las')), las_utils.read_las(str(out_b / f'labelled_{tc}.las'))
         assert np.array_equal(a.label, b.label) and np.array_equal(a.X, b.X) and (np.asarray(a.label) != 0).sum() > 10000
     assert sorted(f.name for f in out_a.iterdir()) == sorted(f'labelled_{tc}.las' for tc in tcs)
+    out_c = tmp_path / 'c'
+    pipe.process_folder(str(in_dir), str(out_c), in_prefix='filtered_', out_prefix='labelled_', workers=2)   # files in flight
+    for tc in tcs:
+        c, b = las_utils.read_las(str(out_c / f'labelled_{tc}.las')), las_utils.read_las(str(out_b / f'labelled_{tc}.las'))
+        assert np.array_equal(c.label, b.label) and np.array_equal(c.X, b.X)
     assert pipe.process_folder(str(tmp_path / 'missing')) is None
 
 

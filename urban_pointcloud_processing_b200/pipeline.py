@@ -291,8 +291,12 @@ class Pipeline:
         self._save_file(pointcloud, labels, out_file, start)
 
     def process_folder(self, in_folder, out_folder=None, in_prefix='', out_prefix='', suffix='',
-                       hide_progress=False):
-        """Process a folder of LAS files and save each processed file."""
+                       hide_progress=False, workers=1):
+        """Process a folder of LAS files and save each processed file.
+
+        ``workers`` (not in the reference): with 1, file ``i + 1`` is read and file ``i - 1`` written on
+        host threads while the device labels file ``i``; with more, that many files are in flight, each
+        read, labelled (own CUDA stream) and written by its own host thread, as in ``process_clouds``."""
         if not os.path.isdir(in_folder):
             logger.error('The input path specified does not exist')
             return None
@@ -316,6 +320,18 @@ class Pipeline:
             elif out_prefix:
                 filename = out_prefix + filename
             jobs.append((file.as_posix(), os.path.join(out_folder, filename + suffix + extension)))
+        workers = max(1, min(int(workers), len(jobs)))
+        if workers > 1 and all(hasattr(obj, '_apply_device') for obj in self.processors):
+            def body(i):
+                in_file, outfile = jobs[i]
+                logger.info(f'Processing file {in_file}.')
+                start = time.time()
+                tilecode, pointcloud, labels = self._load_file(in_file)
+                labels = self._label_file(tilecode, pointcloud, labels)
+                self._save_file(pointcloud, labels, outfile, start)
+            self._run_tile_workers(len(jobs), workers, body)
+            logger.info(f'Pipeline finished, {len(files)} processed.\n' + '=' * 20)
+            return
         # Files are independent (pipeline.py:186-194 handles them one after the other): while the device
         # labels file i, one host thread already reads and parses file i+1 and another writes file i-1.
         from concurrent.futures import ThreadPoolExecutor
