@@ -1,6 +1,8 @@
 """Experiment: two tiles in flight on two CUDA streams driven by two host threads (development tool).
 Does the device fill the latency-bound phases of one tile (frontier growth, union-find link, host round
-trips) with the kernels of the other?  Prints tiles/s for 1 and 2 workers."""
+trips) with the kernels of the other?  Prints tiles/s for 1, 2 and 3 workers.
+(The experiment that preceded Pipeline.process_tiles_device / process_clouds(workers=W), which is the product
+form: per-stream workspaces live in device.workspace now, the thread-local patch below predates that.)"""
 import os
 import sys
 import threading
