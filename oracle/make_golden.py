@@ -374,6 +374,91 @@ def golden_objects(upcp):
     assert n_car > 1000 and n_sf > 300
 
 
+VAR_N, VAR_SEED = 40000, 20240011
+VAR_RG = (dict(threshold_angle=5), dict(threshold_angle=60, grow_region_knn=8, max_nn=12, grow_region_radius=0.5),
+          dict(threshold_curve=0.2))
+VAR_LCC = dict(exclude_labels=[9], grid_size=0.2, min_component_size=10, threshold=0.03)
+VAR_LAYER = [{'bottom': -1.0, 'top': 3.0, 'grid_size': 0.2, 'min_comp_size': 20, 'threshold': 0.2}]
+
+
+def golden_variants(upcp):
+    """Non-default constructor arguments through the REAL reference classes: AHNFuser(target='building'),
+    BGTBuildingFuser without the AHN cap, BGTRoadFuser(bgt_types=...), LabelConnectedComp(exclude_labels=...),
+    LayerLCC(reset_noise=True), RegionGrowing with other angles / neighbourhoods / a curvature threshold
+    inside the range of the ratios (the LAPACK eigenvalue-order path)."""
+    from upcp.fusion import AHNFuser, BGTBuildingFuser, BGTRoadFuser
+    from upcp.region_growing import LabelConnectedComp, LayerLCC
+    from upcp.region_growing.region_growing import RegionGrowing
+    from upcp.utils.ahn_utils import NPZReader
+    from upcp.utils.bgt_utils import BGTPolyReader
+    from upcp.labels import Labels
+    tile = synthetic.make_tile(VAR_N, seed=VAR_SEED, facade_fraction=0.5)
+    points, tc = tile['points'], tile['tilecode']
+    tmp = tempfile.mkdtemp(prefix='upcp_golden_')
+    write_readers(tmp, tile)
+    ahn_reader = NPZReader(tmp)
+    bld_reader = BGTPolyReader(bgt_file=os.path.join(tmp, 'buildings.csv'))
+    road_reader = BGTPolyReader(bgt_file=os.path.join(tmp, 'roads.csv'))
+    ahn_tile = ahn_reader.filter_tile(tc)
+    out = {'points_mm': mm(points).astype(np.int32), 'seed': np.array(VAR_SEED), 'n': np.array(VAR_N)}
+
+    def both(name, ref_call, oracle_call, labels):
+        got = ref_call(labels.copy())
+        want = oracle_call(labels.copy())
+        assert np.array_equal(got, want), f'oracle mismatch: {name}'
+        out[name] = got.astype(np.uint8)
+        print(f'  variants/{name}: {np.count_nonzero(got != labels)} labels changed')
+        return got
+
+    zero = np.zeros(VAR_N, dtype=np.uint16)
+    bsurf = both('ahn_building', lambda l: AHNFuser(Labels.BUILDING, ahn_reader, target='building', epsilon=0.1,
+                                                    refine_ground=False).get_labels(points, l, l == 0, tc),
+                 lambda l: R.ahn_fuser_labels(points, l, l == 0, ahn_tile, Labels.BUILDING, 'building', 0.1), zero)
+    ground = both('ahn_ground', lambda l: AHNFuser(Labels.GROUND, ahn_reader, target='ground', epsilon=0.3,
+                                                   refine_ground=False).get_labels(points, l, l == 0, tc),
+                  lambda l: R.ahn_fuser_labels(points, l, l == 0, ahn_tile, Labels.GROUND, 'ground', 0.3), zero)
+    bld_polys = bld_reader.filter_tile(tc, bgt_types=['pand'], merge=True)
+    nocap = both('building_no_ahn', lambda l: BGTBuildingFuser(Labels.BUILDING, bgt_reader=bld_reader, offset=0)
+                 .get_labels(points, l, l == 0, tc),
+                 lambda l: R.building_fuser_labels(points, l, l == 0, bld_polys, Labels.BUILDING, None), ground)
+    bike = road_reader.filter_tile(tc, bgt_types=['fietspad'], merge=True)
+    both('road_fietspad', lambda l: BGTRoadFuser(Labels.ROAD, bgt_reader=road_reader, bgt_types=['fietspad'])
+         .get_labels(points, l, l == 0, tc),
+         lambda l: R.road_fuser_labels(points, l, bike, Labels.ROAD), ground)
+    # LabelConnectedComp with an exclusion list: 2 % of the car points as seeds
+    seeded = ground.copy()
+    cars = np.where(tile['kind'] == 2)[0]
+    seeded[cars[::50]] = Labels.CAR
+    out['car_seed_ids'] = cars[::50].astype(np.int32)
+
+    def ref_lcc(l):
+        return LabelConnectedComp(Labels.CAR, **VAR_LCC).get_labels(points, l, l == 0, tc)
+
+    def oracle_lcc(l):
+        lm = R.lcc_get_label_mask(points, l, l == 0, Labels.CAR, **VAR_LCC)
+        l[lm] = Labels.CAR
+        return l
+    both('lcc_exclude', ref_lcc, oracle_lcc, seeded)
+    # LayerLCC with reset_noise: some building points and some unlabelled ones arrive as NOISE
+    noisy = nocap.copy()
+    rng = np.random.default_rng(4)
+    flip = rng.random(VAR_N) < 0.1
+    noisy[flip & (noisy != Labels.GROUND)] = Labels.NOISE
+    out['noise_ids'] = np.where(noisy == Labels.NOISE)[0].astype(np.int32)
+    both('layer_lcc_reset_noise',
+         lambda l: LayerLCC(Labels.BUILDING, ahn_reader, reset_noise=True, params=[dict(p) for p in VAR_LAYER])
+         .get_labels(points, l, l == 0, tc),
+         lambda l: R.layer_lcc_labels(points, l, l == 0, ahn_tile, Labels.BUILDING, [dict(p) for p in VAR_LAYER],
+                                      reset_noise=True), noisy)
+    for k, kw in enumerate(VAR_RG):
+        both(f'region_growing_{k}',
+             lambda l: RegionGrowing(Labels.BUILDING, exclude_labels=(Labels.GROUND,), **kw).get_labels(points, l, None, tc),
+             lambda l: R.region_growing_labels(points, l, Labels.BUILDING, exclude_labels=(Labels.GROUND,), **kw), nocap)
+    np.savez_compressed(os.path.join(GOLDEN, 'variants_golden.npz'), **out)
+    shutil.rmtree(tmp, ignore_errors=True)
+    assert np.count_nonzero(bsurf) > 1000
+
+
 def main():
     os.makedirs(GOLDEN, exist_ok=True)
     upcp = ref_harness.load_reference()
@@ -385,6 +470,7 @@ def main():
     golden_demo(upcp)
     golden_pipeline(upcp)
     golden_objects(upcp)
+    golden_variants(upcp)
     print('golden vectors written to', GOLDEN)
 
 

@@ -517,6 +517,45 @@ def test_object_fusers_match_reference_golden(golden):
     assert np.array_equal(piped, g['labels_after_street_light'])
 
 
+def test_parameter_variants_match_reference_golden(golden):
+    """variants_golden.npz: non-default constructor arguments through the REAL reference classes -- AHNFuser on the
+    building surface, BGTBuildingFuser without the AHN cap, BGTRoadFuser with a type list, LabelConnectedComp with
+    an exclusion list, LayerLCC(reset_noise=True), RegionGrowing with other angles / neighbourhoods / a curvature
+    threshold inside the range of the ratios (host LAPACK path)."""
+    from test_oracle_golden import VAR_LAYER, VAR_LCC, VAR_RG
+    g = golden('variants_golden.npz')
+    tile = synthetic.make_tile(int(g['n']), seed=int(g['seed']), facade_fraction=0.5)
+    points, tc = tile['points'], tile['tilecode']
+    assert np.array_equal(points, from_mm(g['points_mm']))
+    ahn, bld, road = readers_for(tile, drop_holes=True)
+
+    def run(proc, labels, mask='unlabelled'):
+        labels = labels.copy()
+        out = proc.get_labels(points, labels, (labels == 0) if mask == 'unlabelled' else mask, tc)
+        assert out is labels
+        return labels
+    zero = np.zeros(len(points), dtype=np.uint16)
+    got = run(AHNFuser(Labels.BUILDING, ahn, target='building', epsilon=0.1, refine_ground=False), zero)
+    assert np.array_equal(got, g['ahn_building'])
+    ground = run(AHNFuser(Labels.GROUND, ahn, target='ground', epsilon=0.3, refine_ground=False), zero)
+    assert np.array_equal(ground, g['ahn_ground'])
+    nocap = run(BGTBuildingFuser(Labels.BUILDING, bgt_reader=bld, offset=0), ground)
+    assert np.array_equal(nocap, g['building_no_ahn'])
+    got = run(BGTRoadFuser(Labels.ROAD, bgt_reader=road, bgt_types=['fietspad']), ground)
+    assert np.array_equal(got, g['road_fietspad'])
+    seeded = ground.copy()
+    seeded[g['car_seed_ids']] = Labels.CAR
+    got = run(LabelConnectedComp(Labels.CAR, **VAR_LCC), seeded)
+    assert np.array_equal(got, g['lcc_exclude'])
+    noisy = nocap.copy()
+    noisy[g['noise_ids']] = Labels.NOISE
+    got = run(LayerLCC(Labels.BUILDING, ahn, reset_noise=True, params=[dict(p) for p in VAR_LAYER]), noisy)
+    assert np.array_equal(got, g['layer_lcc_reset_noise'])
+    for k, kw in enumerate(VAR_RG):
+        got = run(RegionGrowing(Labels.BUILDING, exclude_labels=(Labels.GROUND,), **kw), nocap, mask=None)
+        assert np.array_equal(got, g[f'region_growing_{k}']), kw
+
+
 def test_demo_tile_matches_reference_golden(golden):
     """configs[0] substitute: REAL demo AHN + BGT data of tile 2386_9702, reference pipeline."""
     g = golden('demo_golden.npz')

@@ -290,3 +290,41 @@ def test_normals_and_covariance_natives_against_lapack():
         assert np.abs(got - want).max() < 5e-4, i
     ev = natives.fast_eigen(cov6[::11])
     assert ev.shape == (len(cov6[::11]), 3)
+
+
+# ------------------------------------------- non-default constructor arguments ---
+VAR_RG = (dict(threshold_angle=5), dict(threshold_angle=60, grow_region_knn=8, max_nn=12, grow_region_radius=0.5),
+          dict(threshold_curve=0.2))
+VAR_LCC = dict(exclude_labels=[9], grid_size=0.2, min_component_size=10, threshold=0.03)
+VAR_LAYER = [{'bottom': -1.0, 'top': 3.0, 'grid_size': 0.2, 'min_comp_size': 20, 'threshold': 0.2}]
+
+
+def test_parameter_variants_oracle_matches_reference_golden(golden):
+    """variants_golden.npz: the REAL reference classes with non-default arguments (building surface, no AHN cap,
+    road type list, LCC exclusion list, LayerLCC(reset_noise=True), RegionGrowing angles / neighbourhoods /
+    curvature threshold) vs the restatement."""
+    g = golden('variants_golden.npz')
+    tile = synthetic.make_tile(int(g['n']), seed=int(g['seed']), facade_fraction=0.5)
+    points, ahn = tile['points'], tile['ahn_tile']
+    assert np.array_equal(points, from_mm(g['points_mm']))
+    blds = [type(p)(np.array(p.exterior.coords)) for p in tile['building_polygons']]      # the CSV format has no holes
+    zero = np.zeros(len(points), dtype=np.uint16)
+    assert np.array_equal(R.ahn_fuser_labels(points, zero.copy(), zero == 0, ahn, 10, 'building', 0.1), g['ahn_building'])
+    ground = R.ahn_fuser_labels(points, zero.copy(), zero == 0, ahn, 9, 'ground', 0.3)
+    assert np.array_equal(ground, g['ahn_ground'])
+    nocap = R.building_fuser_labels(points, ground.copy(), ground == 0, blds, 10, None)
+    assert np.array_equal(nocap, g['building_no_ahn'])
+    assert np.array_equal(R.road_fuser_labels(points, ground.copy(), tile['road_polygons'][1:], 1), g['road_fietspad'])
+    seeded = ground.copy()
+    seeded[g['car_seed_ids']] = 40
+    lm = R.lcc_get_label_mask(points, seeded, seeded == 0, 40, **VAR_LCC)
+    seeded[lm] = 40
+    assert np.array_equal(seeded, g['lcc_exclude'])
+    noisy = nocap.copy()
+    noisy[g['noise_ids']] = 99
+    got = R.layer_lcc_labels(points, noisy, noisy == 0, ahn, 10, [dict(p) for p in VAR_LAYER], reset_noise=True)
+    assert np.array_equal(got, g['layer_lcc_reset_noise'])
+    for k, kw in enumerate(VAR_RG):
+        got = R.region_growing_labels(points, nocap.copy(), 10, exclude_labels=(9,), **kw)
+        assert np.array_equal(got, g[f'region_growing_{k}']), kw
+        assert (got != nocap).sum() > 500
