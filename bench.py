@@ -57,6 +57,7 @@ WORKLOAD = ('synthetic 50 m urban tile, {n} points: AHNFuser(ground) + BGTRoadFu
             '+ LayerLCC(building, 2 layers) + LabelConnectedComp(car, grid 0.1) + RegionGrowing(building, knn 15, '
             'hybrid r 0.2 / max_nn 30)')
 # algorithmic HBM bytes per point, SURVEY.md section 8(d)
+MAX_BATCH_BUFFERS = 64        # label buffers kept alive at once by the batch arms (80 MB on the device / 40 MB pinned each)
 B_ALG = {'raster_kernel': 27.0, 'pip_query_kernel': 19.0, 'radix_sort (hist+scan+scatter)': 96.0,
          'cc_link_kernel': 8.0, 'knn_search_kernel': 140.0, 'grow_kernel': 421.0}
 
@@ -238,6 +239,7 @@ def main():
                     help='timing rule W >= 3; lower only for profiler runs whose numbers are never reported')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
+    args.steps = max(args.steps, 1)
 
     rank = int(os.environ.get('RANK', '0'))
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
@@ -340,22 +342,27 @@ def main():
     # tiles overlap, the roofline numbers come from the single-stream region above.
     conc = None
     if args.workers > 1:
-        bufs = [torch.empty_like(d_labels0) for _ in range(args.steps)]
+        bufs = [torch.empty_like(d_labels0) for _ in range(min(args.steps, MAX_BATCH_BUFFERS))]
 
         def concurrent_steps():
-            for b_ in bufs:
-                b_.copy_(d_labels0)
-            pipeline.process_tiles_device([tc] * len(bufs), [d_tile] * len(bufs), bufs, workers=args.workers)
-            return [dev.label_hist(b_) for b_ in bufs][-1]
-        saved, bufs = bufs, bufs[:min(len(bufs), 2 * args.workers)]
+            # K tile passes; label buffers are recycled every MAX_BATCH_BUFFERS tiles (bounded memory for large K)
+            h_ = None
+            for first in range(0, args.steps, len(bufs)):
+                part = bufs[:min(len(bufs), args.steps - first)]
+                for b_ in part:
+                    b_.copy_(d_labels0)
+                pipeline.process_tiles_device([tc] * len(part), [d_tile] * len(part), part, workers=args.workers)
+                h_ = [dev.label_hist(b_) for b_ in part][-1]
+            return h_
+        saved_steps, args.steps = args.steps, min(args.steps, 2 * args.workers)
         concurrent_steps()                                   # warm-up: worker streams, their scratch buffers
-        bufs = saved
+        args.steps = saved_steps
         launches1 = _lib.launch_count()
         ms_c, wall_c, hist_c = timed(concurrent_steps, 1)
         conc = {'ms_per_step': ms_c / args.steps, 'value': world * n * args.steps / (ms_c * 1e-3) / 1e6,
                 'launches': _lib.launch_count() - launches1, 'wall_ms_per_step': wall_c / args.steps,
                 'labels_equal_single_stream': bool(torch.equal(bufs[-1], d_labels) and torch.equal(bufs[0], d_labels))}
-        del bufs, saved
+        del bufs
     t_end = time.perf_counter()
     if rank == 0:
         sampler.window(t_begin, t_end)
@@ -388,16 +395,20 @@ def main():
     # the timed region
     e2e_batch = None
     if not args.no_e2e:
-        lab_bufs = [torch.empty(n, dtype=torch.int16).pin_memory() for _ in range(args.steps)]
+        lab_bufs = [torch.empty(n, dtype=torch.int16).pin_memory() for _ in range(min(args.steps, MAX_BATCH_BUFFERS))]
 
         def reset_labels():
             for b_ in lab_bufs:
                 b_.copy_(lab_init_pinned)
 
         def batch_call():
-            k_ = len(lab_bufs)
-            pipeline.process_clouds([tc] * k_, [points_host] * k_, [b_.numpy().view(np.uint16) for b_ in lab_bufs],
-                                    workers=args.workers)
+            # K tiles; beyond MAX_BATCH_BUFFERS the pinned label buffers are reset and recycled inside the timed region
+            for first in range(0, args.steps, len(lab_bufs)):
+                k_ = min(len(lab_bufs), args.steps - first)
+                if first:
+                    reset_labels()
+                pipeline.process_clouds([tc] * k_, [points_host] * k_, [b_.numpy().view(np.uint16) for b_ in lab_bufs[:k_]],
+                                        workers=args.workers)
         reset_labels()
         k_w = min(len(lab_bufs), 2 * max(args.workers, 1))
         pipeline.process_clouds([tc] * k_w, [points_host] * k_w, [b_.numpy().view(np.uint16) for b_ in lab_bufs[:k_w]],
