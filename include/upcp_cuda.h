@@ -53,18 +53,41 @@ int64_t     upcp_launch_count(void);
  * with cudaEvents on their launching stream.  upcp_prof_read() synchronises the device,
  * adds up the elapsed time of all completed brackets of `slot` since the last reset and
  * returns the number of launches.  Slots: 0 raster, 1 pip, 2 radix sort (all passes of one
- * sort), 3 cc link (union-find), 4 knn search, 5 region grow (persistent kernel). */
+ * sort), 3 cc link (union-find), 4 neighbour search + normals (the WHOLE stage S4),
+ * 5 region grow (persistent kernel). */
 #define UPCP_PROF_RASTER 0
 #define UPCP_PROF_PIP    1
 #define UPCP_PROF_SORT   2
 #define UPCP_PROF_LINK   3
 #define UPCP_PROF_KNN    4
 #define UPCP_PROF_GROW   5
-#define UPCP_PROF_SLOTS  6
+/* sub-brackets of slot 4 (which spans the whole neighbour-search stage S4: grid build, all search
+ * tiers, epilogues): 6 grid build (cell keys, prefix, placement), 7 segment tiers (search + fused
+ * epilogue out of shared memory), 8 per-query tier (compaction, second grid, search, its epilogue) */
+#define UPCP_PROF_KNN_BUILD  6
+#define UPCP_PROF_KNN_SEG    7
+#define UPCP_PROF_KNN_SELECT 8
+#define UPCP_PROF_SLOTS  9
 int         upcp_prof_enable(int on);
 int         upcp_prof_reset(void);
 int         upcp_prof_read(int slot, double* total_ms, int64_t* launches, int64_t* units);
 const char* upcp_prof_slot_name(int slot);
+
+/* Tuning knobs of the kernels, process-wide, explicit (no environment variables are read).
+ * upcp_tuning_default() fills in what bench.py was measured with; upcp_tuning_set() validates
+ * and installs a copy that every later call reads once at entry. */
+typedef struct upcp_tuning {
+    int32_t knn_tiers;            /* segment tiers before the per-query tier: 1 or 2                     */
+    int32_t knn_tier1_max_block;  /* 3^3 blocks with more candidates leave tier 1 to the next tier       */
+    int32_t knn_tier2_max_block;  /* the same for the 5^3 blocks of tier 2                               */
+    int32_t knn_coarse;           /* cell factor of the per-query tier's second grid (1 = none)          */
+    int32_t grow_local_chain;     /* region growth: warp-local continuation cap (0..32)                  */
+    int32_t grow_ctas_per_sm;     /* region growth: resident CTAs per SM of the persistent kernel (>= 1) */
+    int32_t reserved[10];
+} upcp_tuning;
+void upcp_tuning_default(upcp_tuning* out);
+int  upcp_tuning_get(upcp_tuning* out);
+int  upcp_tuning_set(const upcp_tuning* in);
 
 /* ------------------------------------------------------- tile / layout ---- */
 /* Replaces: the implicit numpy layout of `points` (pipeline.py:124 delivers an

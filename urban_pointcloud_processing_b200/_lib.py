@@ -6,7 +6,7 @@ entry point raises, and if no CUDA device is present every compute call raises.
 """
 import ctypes
 import os
-from ctypes import (POINTER, c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_size_t,
+from ctypes import (POINTER, Structure, c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_size_t,
                     c_uint8, c_void_p)
 
 HERE = os.path.dirname(os.path.abspath(__file__))
@@ -27,6 +27,13 @@ class UpcpCudaMissing(ImportError):
     """Raised when libupcp_cuda.so has not been built."""
 
 
+class Tuning(Structure):
+    """``upcp_tuning`` of include/upcp_cuda.h (explicit, process-wide kernel tuning knobs)."""
+    _fields_ = [('knn_tiers', c_int32), ('knn_tier1_max_block', c_int32), ('knn_tier2_max_block', c_int32),
+                ('knn_coarse', c_int32), ('grow_local_chain', c_int32), ('grow_ctas_per_sm', c_int32),
+                ('reserved', c_int32 * 10)]
+
+
 _PROTOTYPES = {
     # name: (restype, [argtypes])
     'upcp_abi_version': (c_int, []),
@@ -37,6 +44,9 @@ _PROTOTYPES = {
     'upcp_prof_reset': (c_int, []),
     'upcp_prof_read': (c_int, [c_int, POINTER(c_double), POINTER(c_int64), POINTER(c_int64)]),
     'upcp_prof_slot_name': (c_char_p, [c_int]),
+    'upcp_tuning_default': (None, [POINTER(Tuning)]),
+    'upcp_tuning_get': (c_int, [POINTER(Tuning)]),
+    'upcp_tuning_set': (c_int, [POINTER(Tuning)]),
     'upcp_points_from_scaled_int32': (c_int, [c_void_p, c_void_p, c_void_p, c_int64, POINTER(c_double),
                                               POINTER(c_double), c_void_p, c_void_p, c_void_p, c_void_p]),
     'upcp_points_aos_to_soa': (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
@@ -145,7 +155,29 @@ def require_cuda():
     return lib
 
 
-PROF_SLOTS = 6
+PROF_SLOTS = 9
+
+
+def tuning(**changes):
+    """Read the process-wide tuning knobs; with keyword arguments, change those and install the result
+    (``upcp_tuning_set``).  Returns the knobs in force as a dict."""
+    lib = load()
+    t = Tuning()
+    check(lib.upcp_tuning_get(ctypes.byref(t)), 'upcp_tuning_get')
+    if changes:
+        for k, v in changes.items():
+            if k not in dict(Tuning._fields_) or k == 'reserved':
+                raise KeyError(k)
+            setattr(t, k, int(v))
+        check(lib.upcp_tuning_set(ctypes.byref(t)), 'upcp_tuning_set')
+    return {k: getattr(t, k) for k, _ in Tuning._fields_ if k != 'reserved'}
+
+
+def tuning_reset():
+    lib = load()
+    t = Tuning()
+    lib.upcp_tuning_default(ctypes.byref(t))
+    check(lib.upcp_tuning_set(ctypes.byref(t)), 'upcp_tuning_set')
 
 
 def prof_enable(on=True):

@@ -33,6 +33,27 @@ int num_sms() {
     return cached_sms;
 }
 
+// --------------------------------------------------------------- tuning -------
+static std::mutex g_tune_mu;
+static upcp_tuning g_tune;
+static bool g_tune_init = false;
+
+static void tuning_defaults(upcp_tuning* t) {
+    memset(t, 0, sizeof(*t));
+    t->knn_tiers = 2;
+    t->knn_tier1_max_block = 60000;
+    t->knn_tier2_max_block = 600;
+    t->knn_coarse = 2;
+    t->grow_local_chain = 2;
+    t->grow_ctas_per_sm = 1;
+}
+
+upcp_tuning tuning() {
+    std::lock_guard<std::mutex> lk(g_tune_mu);
+    if (!g_tune_init) { tuning_defaults(&g_tune); g_tune_init = true; }
+    return g_tune;
+}
+
 // ------------------------------------------------------------ profiling -------
 struct ProfBracket { cudaEvent_t a, b; int64_t units; };
 static std::mutex g_prof_mu;
@@ -93,10 +114,32 @@ int upcp_prof_read(int slot, double* total_ms, int64_t* launches, int64_t* units
 
 const char* upcp_prof_slot_name(int slot) {
     static const char* names[UPCP_PROF_SLOTS] = {"raster_kernel", "pip_query_kernel", "radix_sort (hist+scan+scatter)",
-                                                 "cc_link_kernel", "knn_search_kernel", "grow_kernel"};
+                                                 "cc_link_kernel", "knn_stage (build+search+epilogue)", "grow_kernel",
+                                                 "knn_build", "knn_seg_kernel (tiers 1+2, fused epilogue)",
+                                                 "knn_select (per-query tier + epilogue)"};
     return (slot >= 0 && slot < UPCP_PROF_SLOTS) ? names[slot] : "";
 }
 
+
+void upcp_tuning_default(upcp_tuning* out) { if (out) upcp::tuning_defaults(out); }
+
+int upcp_tuning_get(upcp_tuning* out) {
+    if (!out) UPCP_FAIL(UPCP_E_INVALID, "tuning_get: NULL");
+    *out = upcp::tuning();
+    return UPCP_OK;
+}
+
+int upcp_tuning_set(const upcp_tuning* in) {
+    if (!in) UPCP_FAIL(UPCP_E_INVALID, "tuning_set: NULL");
+    if (in->knn_tiers < 1 || in->knn_tiers > 2 || in->knn_tier1_max_block < 1 || in->knn_tier1_max_block > 60000 ||
+        in->knn_tier2_max_block < 1 || in->knn_tier2_max_block > 60000 || in->knn_coarse < 1 || in->knn_coarse > 16 ||
+        in->grow_local_chain < 0 || in->grow_local_chain > 32 || in->grow_ctas_per_sm < 1 || in->grow_ctas_per_sm > 8)
+        UPCP_FAIL(UPCP_E_INVALID, "tuning_set: value out of range");
+    std::lock_guard<std::mutex> lk(upcp::g_tune_mu);
+    upcp::g_tune = *in;
+    upcp::g_tune_init = true;
+    return UPCP_OK;
+}
 
 int upcp_abi_version(void) { return UPCP_ABI_VERSION; }
 

@@ -11,6 +11,7 @@ namespace upcp {
 int set_error(int code, const char* msg, const char* file, int line);
 void count_launch(int n = 1);
 int num_sms();
+upcp_tuning tuning();        // copy of the process-wide tuning knobs (upcp_tuning_set)
 
 #define UPCP_FAIL(code, msg) return ::upcp::set_error((code), (msg), __FILE__, __LINE__)
 

@@ -10,35 +10,42 @@
 //
 // Data structure (all in HBM, built per call):
 //   * a DENSE uniform grid over the bounding box of the selected points, cells numbered
-//     row-major (x fastest).  Selected points are counting-sorted by cell number into sorted
-//     records, so every cell -- and every run of x-adjacent cells -- is one contiguous,
-//     coalesced range of points;
+//     row-major (x fastest).  Selected points are counting-sorted by cell number, so every
+//     cell -- and every run of x-adjacent cells -- is one contiguous range of points;
 //   * cell_first[G + 1]: exclusive prefix of the per-cell point counts (empty cells
 //     included), so the points of cells [x0, x1] of a grid row are
 //     cell_first[row + x0] .. cell_first[row + x1 + 1]: TWO loads per row, no hashing, no
-//     tree.  With 180 GB of HBM the table (4 B per cell, a few cells per point) is cheap.
+//     tree.  With 180 GB of HBM the table (4 B per cell, a few cells per point) is cheap;
+//   * the sorted coordinates twice: fp64 SoA (sx, sy, sz: what the segment kernel stages,
+//     row range by row range, into shared memory) and 32-byte records (x, y, z, ids) for the
+//     scattered gathers of the per-query tier.
 // What has to be found per query is what the consumers read: the `knn` nearest (kNN row, curvature
 // covariance) and those of the `max_nn` nearest that lie within `radius` (hybrid-search normal).
 // Beyond BOTH the knn-th distance and the radius nothing matters, so every tier certifies
 // "the max_nn nearest are known" OR "the knn nearest and everything within the radius are known".
 // Search, three exact tiers:
-//   1. knn_block_kernel<1>: one LANE per query, candidates = the query's own 3x3x3 cell block
-//      (9 contiguous row ranges).  Selection is a two-pass radial histogram: pass A counts the
-//      candidates into 32 equal-width buckets of squared distance over [0, tau), tau <= reach^2,
-//      reach = the distance from the query to the nearest face of its block (everything outside
-//      the block is farther); the cumulative counts give the bucket below which everything needed
-//      lies; pass B appends the candidates below it (plus a quarter bucket of margin) to the
-//      query's row.  Both passes only FILTER, so they run in fp32 on origin-relative coordinates;
-//      the margin is at least two rigorous fp32 error bounds (checked per query), so the kept set
-//      provably contains what is needed under the exact fp64 ordering.  If the needed candidates
-//      do not end below the last bucket the block cannot certify the answer and the query moves on to
-//   2. knn_block_kernel<2>: the same over the 5x5x5 block (25 row ranges), then
+//   1. knn_seg_kernel<1>: a WARP takes 32 consecutive queries of the sorted order and works
+//      through them in steps; a step serves the queries that share a small window of cells
+//      (same z, <= 3 y-rows, <= 7 x-cells).  The window plus a one-cell halo is a handful of grid
+//      rows, each ONE contiguous range of the sorted arrays: the warp copies them (coalesced,
+//      every candidate once per step) into its slice of shared memory, and from then on nothing
+//      of the step touches global memory until the results are written.  Every lane then runs
+//      its own query over its own 3x3x3 cell block out of shared memory -- lanes of one cell
+//      read the same addresses (broadcast) --: pass A counts the candidates into 32 equal-width
+//      buckets of EXACT fp64 squared distance over [0, tau), tau <= reach^2 (reach = distance to the
+//      nearest face of the block: everything outside is farther); the cumulative counts give the
+//      bucket below which everything needed lies; pass B appends the candidates up to that bucket,
+//      bucket-ordered, to the lane's row (indices into the staged arrays).  The kept set is an
+//      exact initial segment of the (distance, id) order, so there are no error margins.
+//      The epilogue is FUSED: the lane orders its row exactly (insertion sort, distances
+//      recomputed from the staged coordinates), folds it in order into the Open3D cumulant
+//      covariances / FastEigen3x3 normal and writes kNN row, normal and seed flag.  Candidate
+//      rows never reach HBM.
+//   2. knn_seg_kernel<2>: the same over the 5x5x5 block for the queries tier 1 could not certify.
 //   3. knn_select_kernel: one WARP per query, thick shells of grid rows (on a 2x coarser second
 //      grid when this tier has much to do) with a register-resident sorted top-k list (bitonic
-//      merge / shuffle insert) in fp64, until what is still needed is nearer than the unexplored region.
-// Epilogue (knn_epilogue_kernel): one thread per query orders its row exactly by
-// (fp64 d2, compact id), folds it in order into the Open3D cumulant covariances /
-// FastEigen3x3 normal and writes the kNN row.
+//      merge / shuffle insert) in fp64, until what is still needed is nearer than the unexplored
+//      region; knn_epilogue_kernel (thread per query) finishes these few queries.
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -51,12 +58,15 @@ namespace upcp {
 constexpr int kBlock = 256;
 constexpr int kSelWarps = 8;
 constexpr int kSelThreads = kSelWarps * 32;
-constexpr int kRow = 48;                // candidate-row capacity (sorted positions, slot-major)
-constexpr int kBlkWarps = 4;
-constexpr int kBlkThreads = kBlkWarps * 32;
+constexpr int kRow = 48;                // candidate-row capacity of the segment kernel (slot-major)
+constexpr int kSelRow = 32;             // row capacity of the per-query tier (its k <= 32 exact neighbours)
 constexpr int kBuckets = 32;            // radial histogram resolution
-constexpr int kTiers = 2;               // block tiers (R = 1..4) before the per-query kernel
 constexpr int kEpiThreads = 128;
+// segment kernel (tiers 1 and 2)
+constexpr int kSegWarps = 4;
+constexpr int kSegThreads = kSegWarps * 32;
+constexpr int kCap = 480;               // staged candidates per step (fp64 x, y, z: 11.25 KB per warp)
+constexpr int kStepHalfX = 3;           // a step takes queries with |cx - cx_leader| <= kStepHalfX
 constexpr uint32_t kFull = 0xffffffffu;
 
 struct GridParams {
@@ -109,7 +119,7 @@ __device__ __forceinline__ uint32_t cell_rank(uint32_t* __restrict__ cell_count,
 
 __global__ void __launch_bounds__(kBlock)
 knn_keys_kernel(const double* __restrict__ x, const double* __restrict__ y,
-                const double* __restrict__ z, const uint32_t* __restrict__ sel_idx, int64_t m,
+                const double* __restrict__ z, const uint32_t* __restrict__ sel_idx, int64_t n, int64_t m,
                 GridParams g, uint32_t* __restrict__ keys, uint32_t* __restrict__ rank,
                 uint32_t* __restrict__ cell_count) {
     const int64_t stride = (int64_t)gridDim.x * kBlock;
@@ -119,6 +129,7 @@ knn_keys_kernel(const double* __restrict__ x, const double* __restrict__ y,
         uint32_t key = 0;
         if (valid) {
             int64_t i = sel_idx ? (int64_t)sel_idx[j] : j;
+            if (i >= n) i = n - 1;                  // (only with a wrong m: stay inside the arrays)
             int cx = cell_coord(x[i], g.ox, g.inv_cell, g.nx);
             int cy = cell_coord(y[i], g.oy, g.inv_cell, g.ny);
             int cz = cell_coord(z[i], g.oz, g.inv_cell, g.nz);
@@ -133,18 +144,21 @@ __global__ void __launch_bounds__(kBlock)
 knn_place_kernel(const double* __restrict__ x, const double* __restrict__ y,
                  const double* __restrict__ z, const uint32_t* __restrict__ sel_idx,
                  const uint32_t* __restrict__ keys, const uint32_t* __restrict__ rank,
-                 const uint32_t* __restrict__ cell_first, int64_t m, GridParams g,
-                 P4* __restrict__ spts, float4* __restrict__ spf, uint32_t* __restrict__ order) {
+                 const uint32_t* __restrict__ cell_first, int64_t n, int64_t m,
+                 P4* __restrict__ spts, double* __restrict__ sx, double* __restrict__ sy, double* __restrict__ sz,
+                 uint32_t* __restrict__ scid, uint32_t* __restrict__ order) {
     int64_t stride = (int64_t)gridDim.x * kBlock;
     for (int64_t j = (int64_t)blockIdx.x * kBlock + threadIdx.x; j < m; j += stride) {
         const uint32_t s = __ldg(cell_first + keys[j]) + rank[j];
         int64_t i = sel_idx ? (int64_t)sel_idx[j] : (int64_t)j;
+        if (i >= n) i = n - 1;
         const double px = x[i], py = y[i], pz = z[i];
         double2* o = reinterpret_cast<double2*>(spts + s);
         o[0] = make_double2(px, py);
         o[1] = make_double2(pz, __longlong_as_double((long long)(((unsigned long long)s << 32) | (unsigned long long)j)));
-        // origin-relative fp32 copy for the filter passes (error bound: see knn_block_kernel)
-        spf[s] = make_float4((float)(px - g.ox), (float)(py - g.oy), (float)(pz - g.oz), 0.0f);
+        // the same coordinates as three plain arrays: what the segment kernel stages, range by range
+        sx[s] = px; sy[s] = py; sz[s] = pz;
+        scid[s] = (uint32_t)j;                      // compact id of sorted position s (tie order, compact-space outputs)
         if (order) order[s] = (uint32_t)i;          // original point index of sorted position s
     }
 }
@@ -153,7 +167,9 @@ knn_place_kernel(const double* __restrict__ x, const double* __restrict__ y,
 // (they keep their fine-grid position in w).
 __global__ void __launch_bounds__(kBlock)
 knn_keys2_kernel(const P4* __restrict__ spts, int64_t m, GridParams g, uint32_t* __restrict__ keys,
-                 uint32_t* __restrict__ rank, uint32_t* __restrict__ cell_count) {
+                 uint32_t* __restrict__ rank, uint32_t* __restrict__ cell_count,
+                 const uint32_t* __restrict__ todo_cnt, int min_share) {
+    if ((int64_t)*todo_cnt * min_share < m || *todo_cnt == 0) return;     // the per-query tier stays on the fine grid
     const int64_t stride = (int64_t)gridDim.x * kBlock;
     const int64_t m_warp = (m + 31) & ~(int64_t)31;
     for (int64_t s = (int64_t)blockIdx.x * kBlock + threadIdx.x; s < m_warp; s += stride) {
@@ -172,7 +188,9 @@ knn_keys2_kernel(const P4* __restrict__ spts, int64_t m, GridParams g, uint32_t*
 }
 __global__ void __launch_bounds__(kBlock)
 knn_place2_kernel(const P4* __restrict__ spts, const uint32_t* __restrict__ keys, const uint32_t* __restrict__ rank,
-                  const uint32_t* __restrict__ cell_first, int64_t m, P4* __restrict__ spts2) {
+                  const uint32_t* __restrict__ cell_first, int64_t m, P4* __restrict__ spts2,
+                  const uint32_t* __restrict__ todo_cnt, int min_share) {
+    if ((int64_t)*todo_cnt * min_share < m || *todo_cnt == 0) return;
     int64_t stride = (int64_t)gridDim.x * kBlock;
     for (int64_t s = (int64_t)blockIdx.x * kBlock + threadIdx.x; s < m; s += stride) {
         const uint32_t t = __ldg(cell_first + keys[s]) + rank[s];
@@ -182,232 +200,58 @@ knn_place2_kernel(const P4* __restrict__ spts, const uint32_t* __restrict__ keys
     }
 }
 
-// ------------------------------------------------------------------ tier 1 / 2 ----
-struct BlockArgs {
-    const P4* spts; const float4* spf; const uint32_t* cell_first;
-    GridParams g;
-    int64_t m;
-    int k;
-    const uint32_t* q_idx; const uint32_t* q_cnt;      // queries (sorted positions) or NULL = all m
-    uint32_t* out_pos; uint8_t* out_cnt;               // rows [kRow][m], counts [m]
-    uint8_t* todo;                                     // [m] 1 = not served by this tier
-    int k_row; double radius2;                         // kNN row length, squared normal-estimation radius
-    uint32_t max_total;                                // blocks with more candidates go to the next tier (<= 60000: u16 counters)
+// ------------------------------------------------------------------ epilogue tail ----
+struct EpiOut {
+    int knn, max_nn;
+    double radius2;
+    int32_t* out_knn; double* out_d2; double* out_normals; double* out_cov; double* out_curv;
+    double thr_curve; uint8_t* out_flag;
+    int sorted_out;     // 0: outputs indexed by compact id, neighbours as compact ids; 1: both as sorted positions
 };
 
-// One lane per query; see the header comment.  The per-lane histogram is kBuckets counters in
-// shared memory (u16, laid out so that a lane only ever touches its own bank).
-//   tau      upper edge of the histogram (squared distance).  The block can certify anything up to
-//            reach^2, but its candidates mostly lie much farther than the k-th neighbour, so the
-//            first attempt uses a data-driven guess -- three times the k-th squared distance a planar
-//            cloud of the block's point count would have -- and only falls back to reach^2 when k is
-//            not reached below it: fine buckets where the cloud is dense, few candidates kept.
-//   fp32     |d2f - d2| <= 3.47 sqrt(d2) delta + 3 delta^2 + 2^-22 d2 with delta = 2^-23 extent (origin-
-//            relative coordinates rounded to fp32, differences and products in fp32); a query is only
-//            served when this bound is below an eighth of a bucket (pass B keeps a quarter bucket
-//            beyond b*, i.e. two error bounds).
-template <int R>
-__global__ void __launch_bounds__(kBlkThreads)
-knn_block_kernel(BlockArgs a) {
-    __shared__ uint16_t s_hist[kBlkWarps][kBuckets * 32];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint16_t* const hist = s_hist[warp] + lane * 2;          // counter of bucket b: HIST(b), bank = lane
-#define HIST(b) hist[(((b) >> 1) << 6) + ((b) & 1)]
-    const GridParams g = a.g;
-    const int K = a.k;
-    const int64_t n_q = a.q_idx ? (int64_t)*a.q_cnt : a.m;
-    const int64_t n_q_warp = (n_q + 31) & ~(int64_t)31;
-    const double inf = __longlong_as_double(0x7ff0000000000000LL);
-    const double delta = g.extent * (1.01 / 8388608.0);
-    const float nbf = (float)kBuckets;
-
-    for (int64_t qb = ((int64_t)blockIdx.x * kBlkWarps + warp) * 32; qb < n_q_warp;
-         qb += (int64_t)gridDim.x * kBlkThreads) {
-        const int64_t qi = qb + lane;
-        const bool valid = qi < n_q;
-        const int64_t q = valid ? (a.q_idx ? (int64_t)a.q_idx[qi] : qi) : 0;
-        const P4 qp = load_p4(a.spts + q);
-        const float4 qf = __ldg(a.spf + q);
-        const int cx = cell_coord(qp.x, g.ox, g.inv_cell, g.nx);
-        const int cy = cell_coord(qp.y, g.oy, g.inv_cell, g.ny);
-        const int cz = cell_coord(qp.z, g.oz, g.inv_cell, g.nz);
-        // reach: distance to the nearest face of the (2R+1)^3 block that has grid beyond it
-        double reach = inf;
-        if (cx - R > 0) reach = fmin(reach, qp.x - (g.ox + (double)(cx - R) * g.cell));
-        if (cx + R < g.nx - 1) reach = fmin(reach, (g.ox + (double)(cx + R + 1) * g.cell) - qp.x);
-        if (cy - R > 0) reach = fmin(reach, qp.y - (g.oy + (double)(cy - R) * g.cell));
-        if (cy + R < g.ny - 1) reach = fmin(reach, (g.oy + (double)(cy + R + 1) * g.cell) - qp.y);
-        if (cz - R > 0) reach = fmin(reach, qp.z - (g.oz + (double)(cz - R) * g.cell));
-        if (cz + R < g.nz - 1) reach = fmin(reach, (g.oz + (double)(cz + R + 1) * g.cell) - qp.z);
-        // block covers the grid on every side: every pair of points is within the block diagonal
-        if (!(reach < inf)) reach = 1.7320508075688774 * (double)(2 * R + 1) * g.cell * 1.001 + g.slack;
-        reach -= g.slack;
-        const double tau_full = reach * reach * (1.0 - 1e-9);
-        const int x0 = max(cx - R, 0), x1 = min(cx + R, g.nx - 1);
-        bool active = valid && reach > 0.0;
-
-        // cheap certificate first: a block with fewer than k_row points cannot serve the query
-        // (2 prefix lookups per row instead of a wasted counting pass)
-        uint32_t total = 0;
-#pragma unroll 1
-        for (int dz = -R; dz <= R; ++dz) {
-#pragma unroll 1
-            for (int dy = -R; dy <= R; ++dy) {
-                const int yy = cy + dy, zz = cz + dz;
-                if (active && yy >= 0 && yy < g.ny && zz >= 0 && zz < g.nz) {
-                    const uint32_t row = ((uint32_t)zz * (uint32_t)g.ny + (uint32_t)yy) * (uint32_t)g.nx;
-                    total += __ldg(a.cell_first + row + x1 + 1) - __ldg(a.cell_first + row + x0);
-                }
+// Normal, k-neighbourhood covariance, analytic eigenvalue ratios and seed flag of one query from its
+// two cumulant sets (hybrid-search neighbours / the knn nearest), written to output row `cid`.
+__device__ __forceinline__ void epi_finish(const EpiOut& a, uint32_t cid, int nn, int kk,
+                                           Cumulants& nrm_cum, Cumulants& cov_cum) {
+    if (a.out_normals) {
+        Vec3 nrm = {0.0, 0.0, 1.0};
+        if (nn >= 3) {
+            double cov6[6];
+            nrm_cum.finish(nn, cov6);
+            nrm = normal_from_cov(cov6, nullptr);
+        }
+        a.out_normals[(size_t)cid * 3 + 0] = nrm.x;
+        a.out_normals[(size_t)cid * 3 + 1] = nrm.y;
+        a.out_normals[(size_t)cid * 3 + 2] = nrm.z;
+    }
+    if (a.out_cov || a.out_curv || a.out_flag) {
+        double cov6[6];
+        cov_cum.finish(kk > 0 ? kk : 1, cov6);
+        bool want_cov = a.out_cov != nullptr && !a.sorted_out;      // sorted space: only where the flag is undecided
+        if (a.out_curv || a.out_flag) {
+            double ev[3];
+            fast_eigen3x3(cov6, ev);
+            const double sum = ev[0] + ev[1] + ev[2];
+            const double r0 = ev[0] / sum, r1 = ev[1] / sum, r2 = ev[2] / sum;
+            if (a.out_curv) {
+                a.out_curv[(size_t)cid * 3 + 0] = r0; a.out_curv[(size_t)cid * 3 + 1] = r1;
+                a.out_curv[(size_t)cid * 3 + 2] = r2;
             }
-        }
-        // (u16 counters: a block with more candidates than they can count goes to the next tier)
-        if (total < (uint32_t)a.k_row || total > a.max_total) active = false;
-        if (!__any_sync(kFull, active)) {
-            if (valid) a.todo[q] = 1;
-            continue;
-        }
-        // histogram edge: data-driven guess first, reach^2 as the fall-back
-        double tau = tau_full;
-        {
-            const double side = (double)(2 * R + 1) * g.cell;
-            const double guess = 3.0 * (double)K * side * side / (3.141592653589793 * (double)(total > 0 ? total : 1));
-            if (guess < 0.25 * tau) tau = guess;        // only where the full range would be too coarse
-        }
-        auto fp32_ok = [&](double t) {
-            const double err = 3.47 * sqrt(t) * delta + 3.0 * delta * delta + t * (1.0 / 4194304.0);
-            return 8.0 * err <= t * (1.0 / kBuckets);
-        };
-        if (!fp32_ok(tau)) tau = tau_full;
-        if (!fp32_ok(tau)) active = false;
-        float scale = (float)((double)kBuckets / tau);
-
-        float tkeep = 0.0f;        // pass B keeps the candidates with d2f * scale below this
-        bool counting = active;    // this lane takes part in the current counting pass
-        for (int attempt = 0; attempt < 2; ++attempt) {
-            if (!__any_sync(kFull, counting)) break;
-            if (counting) {
-#pragma unroll
-                for (int b = 0; b < kBuckets; ++b) HIST(b) = 0;
+            if (a.out_flag) {
+                const double tol = 1e-9;
+                const bool fin = isfinite(r0) && isfinite(r1) && isfinite(r2);
+                const bool below = fin && r0 < a.thr_curve - tol && r1 < a.thr_curve - tol && r2 < a.thr_curve - tol;
+                const bool above = fin && r0 >= a.thr_curve + tol && r1 >= a.thr_curve + tol && r2 >= a.thr_curve + tol;
+                a.out_flag[cid] = below ? 1 : (above ? 0 : 2);
+                if (!below && !above) want_cov = a.out_cov != nullptr;
             }
-            // ---- pass A: radial histogram of the block's candidates
-#pragma unroll 1
-            for (int dz = -R; dz <= R; ++dz) {
-#pragma unroll 1
-                for (int dy = -R; dy <= R; ++dy) {
-                    const int yy = cy + dy, zz = cz + dz;
-                    uint32_t p = 0, pb = 0;
-                    if (counting && yy >= 0 && yy < g.ny && zz >= 0 && zz < g.nz) {
-                        const uint32_t row = ((uint32_t)zz * (uint32_t)g.ny + (uint32_t)yy) * (uint32_t)g.nx;
-                        p = __ldg(a.cell_first + row + x0);
-                        pb = __ldg(a.cell_first + row + x1 + 1);
-                    }
-                    for (; p + 1 < pb; p += 2) {
-                        const float4 c0 = __ldg(a.spf + p), c1 = __ldg(a.spf + p + 1);
-                        const float ax = c0.x - qf.x, ay = c0.y - qf.y, az = c0.z - qf.z;
-                        const float bx = c1.x - qf.x, by = c1.y - qf.y, bz = c1.z - qf.z;
-                        const float t0 = fmaf(az, az, fmaf(ay, ay, ax * ax)) * scale;
-                        const float t1 = fmaf(bz, bz, fmaf(by, by, bx * bx)) * scale;
-                        if (t0 < nbf) HIST(__float2int_rz(t0)) += 1;
-                        if (t1 < nbf) HIST(__float2int_rz(t1)) += 1;
-                    }
-                    if (p < pb) {
-                        const float4 c0 = __ldg(a.spf + p);
-                        const float ax = c0.x - qf.x, ay = c0.y - qf.y, az = c0.z - qf.z;
-                        const float t0 = fmaf(az, az, fmaf(ay, ay, ax * ax)) * scale;
-                        if (t0 < nbf) HIST(__float2int_rz(t0)) += 1;
-                    }
-                }
-            }
-            // ---- select.  What the consumers use is the k_row nearest (kNN row, covariance) and, of the
-            // K nearest, those within the normal radius.  The block certifies that when
-            //   (a) the K-th candidate falls below the last bucket (everything needed is nearer), or
-            //   (b) the k_row-th does AND the radius lies inside the histogram range (then every point
-            //       within the radius is in the block, and there are fewer than K of them);
-            // pass B keeps the candidates below the smaller of the two limits, plus the fp32 margin.
-            // The counters become exclusive offsets so that pass B places the kept candidates bucket-ordered.
-            if (counting) {
-                uint32_t cum = 0;
-                int bK = -1, bk = -1;           // first bucket whose cumulative count reaches K / k_row
-#pragma unroll 1
-                for (int b = 0; b < kBuckets; ++b) {
-                    const uint32_t hb = HIST(b);
-                    HIST(b) = (uint16_t)cum;
-                    cum += hb;
-                    if (bk < 0 && cum >= (uint32_t)a.k_row) bk = b;
-                    if (bK < 0 && cum >= (uint32_t)K) bK = b;
-                }
-                const float rb = (float)(a.radius2 * (double)scale);           // the radius in bucket units
-                float lim = -1.0f;
-                if (bK >= 0 && bK <= kBuckets - 2) lim = (float)bK + 1.25f;
-                if (bk >= 0 && bk <= kBuckets - 2 && rb + 0.25f <= (float)kBuckets) {
-                    const float alt = fmaxf((float)bk + 1.25f, rb + 0.25f);
-                    if (lim < 0.0f || alt < lim) lim = alt;
-                }
-                // otherwise: retry with the full range, then give up
-                if (lim >= 0.0f) { tkeep = lim; counting = false; }
-                else if (attempt == 0 && tau < tau_full && fp32_ok(tau_full)) {
-                    tau = tau_full;
-                    scale = (float)((double)kBuckets / tau);
-                } else { active = false; counting = false; }
-            }
+        } else {
+            want_cov = a.out_cov != nullptr;
         }
-        // ---- pass B: append the candidates of buckets <= b* (+ a quarter bucket) to the row
-        bool overflow = false;
-        uint32_t kept = 0;
-        if (__any_sync(kFull, active)) {
-#pragma unroll 1
-            for (int dz = -R; dz <= R; ++dz) {
-#pragma unroll 1
-                for (int dy = -R; dy <= R; ++dy) {
-                    const int yy = cy + dy, zz = cz + dz;
-                    uint32_t p = 0, pb = 0;
-                    if (active && yy >= 0 && yy < g.ny && zz >= 0 && zz < g.nz) {
-                        const uint32_t row = ((uint32_t)zz * (uint32_t)g.ny + (uint32_t)yy) * (uint32_t)g.nx;
-                        p = __ldg(a.cell_first + row + x0);
-                        pb = __ldg(a.cell_first + row + x1 + 1);
-                    }
-                    for (; p < pb; ++p) {
-                        const float4 c0 = __ldg(a.spf + p);
-                        const float ax = c0.x - qf.x, ay = c0.y - qf.y, az = c0.z - qf.z;
-                        const float t0 = fmaf(az, az, fmaf(ay, ay, ax * ax)) * scale;
-                        if (t0 < tkeep) {
-                            const int b0 = __float2int_rz(t0);
-                            const uint32_t slot = HIST(b0);
-                            HIST(b0) = (uint16_t)(slot + 1);
-                            ++kept;
-                            if (slot < (uint32_t)kRow) a.out_pos[(size_t)slot * a.m + q] = p;
-                            else overflow = true;
-                        }
-                    }
-                }
-            }
-        }
-        if (valid) {
-            bool served = false;
-            if (active && !overflow && kept <= (uint32_t)kRow) { a.out_cnt[q] = (uint8_t)kept; served = true; }
-            a.todo[q] = served ? 0 : 1;
-        }
+        if (want_cov)
+            for (int t = 0; t < 6; ++t) a.out_cov[(size_t)cid * 6 + t] = cov6[t];
     }
 }
-#undef HIST
-
-// ------------------------------------------------------------------ tier 3 ------
-struct SelectArgs {
-    const P4* qpts;                // query records, fine-grid order
-    const P4* spts;                // candidate records in the order of THIS grid (fine or coarse)
-    const uint32_t* cell_first;
-    GridParams g;
-    int64_t m;
-    int k;                         // neighbours kept per query (<= 32), clipped to m
-    const uint32_t* todo_idx;      // queries (sorted positions) to process, or NULL = all m
-    const uint32_t* todo_cnt;      // device count of todo_idx
-    uint32_t* out_pos;             // [kRow][m] sorted positions of the k nearest, ascending
-    uint8_t* out_cnt;              // [m] number of valid entries of the row
-    // What the consumers use: the k_row nearest (kNN row, covariance) and, of the k nearest, those
-    // within radius2 (hybrid-search normals).  Beyond BOTH the k_row-th distance and the radius
-    // nothing matters, so the walk may stop there instead of at the k-th distance.
-    int k_row; double radius2;
-};
 
 __device__ __forceinline__ uint32_t warp_incl_scan_u32(uint32_t v, int lane) {
 #pragma unroll
@@ -417,6 +261,409 @@ __device__ __forceinline__ uint32_t warp_incl_scan_u32(uint32_t v, int lane) {
     }
     return v;
 }
+
+// ------------------------------------------------------------------ tier 1 / 2 ----
+// Geometry of one step of the segment kernel: the queries of a step lie in one z-layer, kYWin
+// consecutive y-rows and 2 * kStepHalfX + 1 x-cells; with the R-cell halo that is at most kRows grid
+// rows (one lane each) of at most kCells cells.
+template <int R> struct SegDims {
+    static constexpr int kYWin = R == 1 ? 3 : 2;
+    static constexpr int kRows = (kYWin + 2 * R) * (2 * R + 1);          // 15 / 30
+    static constexpr int kCells = 2 * kStepHalfX + 1 + 2 * R;            // 9 / 11
+    static constexpr int kTab = ((kRows * (kCells + 1) + 7) / 8) * 8;
+};
+static_assert(SegDims<1>::kRows <= 32 && SegDims<2>::kRows <= 32, "one lane per staged grid row");
+static_assert(kCap <= 1024, "row entries pack the staged index into 10 bits");
+
+// Shared memory of ONE warp (warps never share anything: no block-level barrier in the kernel).
+template <int R> struct __align__(16) SegSmem {
+    double x[kCap], y[kCap], z[kCap];       // staged candidates: the rows of the step, concatenated
+    uint16_t hist[kBuckets * 32];           // per-lane radial histogram / placement cursors (bank = lane)
+    uint16_t keep[kRow * 32];               // per-lane candidate row [slot][lane]: (staged row << 10) | staged index
+    uint16_t tab[SegDims<R>::kTab];         // [row][cell]: staged index of the first point of the cell (+ row end)
+    uint16_t rowoff[32];                    // staged index of the first point of every staged row
+    int32_t delta[32];                      // sorted position = staged index + delta[row]
+};
+
+struct SegArgs {
+    const double* sx; const double* sy; const double* sz;   // sorted coordinates
+    const uint32_t* scid;                                   // compact id of sorted position
+    const uint32_t* cell_first;
+    GridParams g;
+    int64_t m;
+    int K, k_row;                                           // max(knn, max_nn) and knn, clipped to m
+    const uint32_t* q_idx; const uint32_t* q_cnt;           // queries (sorted positions, ascending) or NULL = all m
+    uint8_t* todo;                                          // [m] 1 = not served by this tier
+    uint32_t max_total;                                     // blocks with more candidates go to the next tier
+    EpiOut o;
+};
+
+// Bucket of a squared distance: round-to-nearest of d2 * scale - 0.5 (one fma, then the 1.5 * 2^52
+// trick instead of a conversion).  Monotone in d2, equal distances share a bucket, bucket b holds
+// d2 * scale in [b, b + 1] (up to one rounding): "all candidates with bucket <= b" is an exact
+// initial segment of the distance order.  Everything at or beyond kBuckets maps to kBuckets.
+__device__ __forceinline__ uint32_t bucket_of(double d2, double scale) {
+    const double r = fma(d2, scale, -0.5) + 6755399441055744.0;
+    const uint32_t lo = (uint32_t)__double2loint(r);
+    const uint32_t hi = (uint32_t)__double2hiint(r);
+    return (hi == 0x43380000u && lo < (uint32_t)kBuckets) ? lo : (uint32_t)kBuckets;
+}
+
+template <int R>
+__global__ void __launch_bounds__(kSegThreads, 3)
+knn_seg_kernel(SegArgs a) {
+    extern __shared__ __align__(16) unsigned char seg_smem_raw[];
+    using D = SegDims<R>;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    SegSmem<R>& sm = reinterpret_cast<SegSmem<R>*>(seg_smem_raw)[warp];
+    uint16_t* const hist = sm.hist + lane * 2;               // counter of bucket b: HIST(b), bank = lane
+#define HIST(b) hist[(((b) >> 1) << 6) + ((b) & 1)]
+    uint16_t* const keep = sm.keep + lane;                   // slot j of this lane: keep[j * 32]
+    const GridParams g = a.g;
+    const int K = a.K, k_row = a.k_row;
+    const double inf = __longlong_as_double(0x7ff0000000000000LL);
+    const int64_t n_q = a.q_idx ? (int64_t)*a.q_cnt : a.m;
+    const int64_t n_chunks = (n_q + 31) >> 5;
+
+    for (int64_t chunk = (int64_t)blockIdx.x * kSegWarps + warp; chunk < n_chunks;
+         chunk += (int64_t)gridDim.x * kSegWarps) {
+        const int64_t qi = chunk * 32 + lane;
+        const bool valid = qi < n_q;
+        const int64_t q = valid ? (a.q_idx ? (int64_t)a.q_idx[qi] : qi) : 0;
+        const double qx = __ldg(a.sx + q), qy = __ldg(a.sy + q), qz = __ldg(a.sz + q);
+        const int cx = cell_coord(qx, g.ox, g.inv_cell, g.nx);
+        const int cy = cell_coord(qy, g.oy, g.inv_cell, g.ny);
+        const int cz = cell_coord(qz, g.oz, g.inv_cell, g.nz);
+        uint32_t pending = __ballot_sync(kFull, valid);
+
+        while (pending) {
+            // ---- the queries of this step: those that share the leader's window of cells
+            const int leader = __ffs(pending) - 1;
+            const int cx0 = __shfl_sync(kFull, cx, leader), cy0 = __shfl_sync(kFull, cy, leader);
+            const int cz0 = __shfl_sync(kFull, cz, leader);
+            bool in_step = ((pending >> lane) & 1u) && cz == cz0 && cy >= cy0 && cy < cy0 + D::kYWin &&
+                           cx >= cx0 - kStepHalfX && cx <= cx0 + kStepHalfX;
+            int xl = 0, ncell = 0, nyr = 0, nrows = 0;
+            uint32_t g0 = 0, len = 0, rowoff = 0, C = 0, act = 0;
+            for (int attempt = 0; attempt < 2; ++attempt) {
+                if (attempt == 1) in_step = in_step && cx == cx0 && cy == cy0;       // the leader's cell alone
+                act = __ballot_sync(kFull, in_step);
+                const int xmin = __reduce_min_sync(kFull, in_step ? cx : 0x7fffffff);
+                const int xmax = __reduce_max_sync(kFull, in_step ? cx : -1);
+                const int ymax = __reduce_max_sync(kFull, in_step ? cy : -1);
+                xl = max(xmin - R, 0);
+                const int xh = min(xmax + R, g.nx - 1);
+                ncell = xh - xl + 1;
+                nyr = ymax - cy0 + 1 + 2 * R;
+                nrows = nyr * (2 * R + 1);
+                // lane r: grid row r of the window (y fastest), ONE contiguous range of the sorted arrays
+                g0 = 0; len = 0;
+                if (lane < nrows) {
+                    const int zi = lane / nyr, yi = lane - zi * nyr;
+                    const int yy = cy0 - R + yi, zz = cz0 - R + zi;
+                    if (yy >= 0 && yy < g.ny && zz >= 0 && zz < g.nz) {
+                        const uint32_t row = ((uint32_t)zz * (uint32_t)g.ny + (uint32_t)yy) * (uint32_t)g.nx;
+                        g0 = __ldg(a.cell_first + row + xl);
+                        len = __ldg(a.cell_first + row + xh + 1) - g0;
+                    }
+                }
+                const uint32_t incl = warp_incl_scan_u32(len, lane);
+                C = __shfl_sync(kFull, incl, 31);
+                rowoff = incl - len;
+                if (C <= (uint32_t)kCap) break;
+            }
+            if (C > (uint32_t)kCap) {
+                // even the leader's cell with its halo does not fit: a crowded spot, left to the next tier
+                if (in_step) a.todo[q] = 1;
+                pending &= ~act;
+                continue;
+            }
+            sm.rowoff[lane] = (uint16_t)rowoff;
+            sm.delta[lane] = (int32_t)g0 - (int32_t)rowoff;
+            __syncwarp();
+            // ---- cell table of the window, in staged indices
+            const int tabw = ncell + 1;
+            for (int e = lane; e < nrows * tabw; e += 32) {
+                const int r = e / tabw, c = e - r * tabw;
+                const int zi = r / nyr, yi = r - zi * nyr;
+                const int yy = cy0 - R + yi, zz = cz0 - R + zi;
+                uint32_t gv = 0;
+                if (yy >= 0 && yy < g.ny && zz >= 0 && zz < g.nz) {
+                    const uint32_t row = ((uint32_t)zz * (uint32_t)g.ny + (uint32_t)yy) * (uint32_t)g.nx;
+                    gv = __ldg(a.cell_first + row + xl + c);
+                }
+                sm.tab[e] = (uint16_t)((int32_t)gv - sm.delta[r]);
+            }
+            // ---- stage the candidates: every point of the window once, coalesced
+#pragma unroll 2
+            for (uint32_t s0 = 0; s0 < C; s0 += 32) {
+                const uint32_t s = s0 + lane;
+                if (s < C) {
+                    int r = 0;
+#pragma unroll
+                    for (int step = 16; step > 0; step >>= 1)
+                        if ((uint32_t)sm.rowoff[r + step] <= s) r += step;
+                    const int64_t gs = (int64_t)s + (int64_t)sm.delta[r];
+                    sm.x[s] = __ldg(a.sx + gs); sm.y[s] = __ldg(a.sy + gs); sm.z[s] = __ldg(a.sz + gs);
+                }
+            }
+            __syncwarp();
+
+            // ---- per-lane set-up: reach = distance to the nearest face of the lane's own (2R+1)^3 block
+            // that has grid beyond it (everything outside the block is at least that far away)
+            double reach = inf;
+            if (cx - R > 0) reach = fmin(reach, qx - (g.ox + (double)(cx - R) * g.cell));
+            if (cx + R < g.nx - 1) reach = fmin(reach, (g.ox + (double)(cx + R + 1) * g.cell) - qx);
+            if (cy - R > 0) reach = fmin(reach, qy - (g.oy + (double)(cy - R) * g.cell));
+            if (cy + R < g.ny - 1) reach = fmin(reach, (g.oy + (double)(cy + R + 1) * g.cell) - qy);
+            if (cz - R > 0) reach = fmin(reach, qz - (g.oz + (double)(cz - R) * g.cell));
+            if (cz + R < g.nz - 1) reach = fmin(reach, (g.oz + (double)(cz + R + 1) * g.cell) - qz);
+            // block covers the grid on every side: every pair of points is within the block diagonal
+            if (!(reach < inf)) reach = 1.7320508075688774 * (double)(2 * R + 1) * g.cell * 1.001 + g.slack;
+            reach -= g.slack;
+            const double tau_full = reach * reach * (1.0 - 1e-9);
+            bool active = in_step && reach > 0.0;
+            // this lane's cells inside a staged row, and its first staged row
+            const int c_lo = max(cx - R, 0) - xl, c_hi1 = min(cx + R, g.nx - 1) - xl + 1;
+            const uint16_t* const tab0 = sm.tab + (cy - cy0) * tabw;       // row (dy = -R, dz = -R) of this lane
+            uint32_t total = 0;
+            if (active) {
+#pragma unroll 1
+                for (int dz = 0; dz <= 2 * R; ++dz)
+#pragma unroll 1
+                    for (int dy = 0; dy <= 2 * R; ++dy) {
+                        const uint16_t* trow = tab0 + (dz * nyr + dy) * tabw;
+                        total += (uint32_t)trow[c_hi1] - (uint32_t)trow[c_lo];
+                    }
+            }
+            // a block with fewer than k_row points cannot serve the query; a crowded one (a lane scanning
+            // it alone holds its warp up) is better served by the pruning warp-per-query tier
+            if (total < (uint32_t)k_row || total > a.max_total) active = false;
+            // histogram edge: data-driven guess first (three times the K-th squared distance a planar cloud
+            // of the block's point count would have), reach^2 as the fall-back
+            double tau = tau_full;
+            {
+                const double side = (double)(2 * R + 1) * g.cell;
+                const double guess = 3.0 * (double)K * side * side / (3.141592653589793 * (double)(total > 0 ? total : 1));
+                if (guess < 0.25 * tau) tau = guess;
+            }
+            double scale = (double)kBuckets / tau;
+            uint32_t b_keep = 0, n_keep = 0;
+            bool counting = active;
+#pragma unroll 1
+            for (int attempt = 0; attempt < 3; ++attempt) {
+                if (!__any_sync(kFull, counting)) break;
+                if (counting) {
+#pragma unroll
+                    for (int b = 0; b < kBuckets; ++b) HIST(b) = 0;
+                }
+                // ---- pass A: radial histogram of the block's candidates (exact fp64 distances)
+#pragma unroll 1
+                for (int dz = 0; dz <= 2 * R; ++dz) {
+#pragma unroll 1
+                    for (int dy = 0; dy <= 2 * R; ++dy) {
+                        int p = 0, pe = 0;
+                        if (counting) {
+                            const uint16_t* trow = tab0 + (dz * nyr + dy) * tabw;
+                            p = trow[c_lo]; pe = trow[c_hi1];
+                        }
+                        for (; p + 1 < pe; p += 2) {
+                            const double d0 = dist2(sm.x[p], sm.y[p], sm.z[p], qx, qy, qz);
+                            const double d1 = dist2(sm.x[p + 1], sm.y[p + 1], sm.z[p + 1], qx, qy, qz);
+                            const uint32_t b0 = bucket_of(d0, scale), b1 = bucket_of(d1, scale);
+                            if (b0 < (uint32_t)kBuckets) HIST(b0) += 1;
+                            if (b1 < (uint32_t)kBuckets) HIST(b1) += 1;
+                        }
+                        if (p < pe) {
+                            const uint32_t b0 = bucket_of(dist2(sm.x[p], sm.y[p], sm.z[p], qx, qy, qz), scale);
+                            if (b0 < (uint32_t)kBuckets) HIST(b0) += 1;
+                        }
+                    }
+                }
+                // ---- select.  What the consumers use is the k_row nearest (kNN row, covariance) and, of the
+                // K nearest, those within the normal radius.  The block certifies that when
+                //   (a) the K-th candidate falls below the last bucket (everything needed is nearer), or
+                //   (b) the k_row-th does AND so does the radius (then every point within the radius is in
+                //       the block, and there are fewer than K of them);
+                // pass B keeps the candidates up to the smaller of the two buckets.  The counters become
+                // exclusive offsets so that pass B places the kept candidates bucket-ordered.
+                if (counting) {
+                    uint32_t cum = 0;
+                    int bK = -1, bk = -1;           // first bucket whose cumulative count reaches K / k_row
+#pragma unroll 1
+                    for (int b = 0; b < kBuckets; ++b) {
+                        const uint32_t hb = HIST(b);
+                        HIST(b) = (uint16_t)cum;
+                        cum += hb;
+                        if (bk < 0 && cum >= (uint32_t)k_row) bk = b;
+                        if (bK < 0 && cum >= (uint32_t)K) bK = b;
+                    }
+                    const int br = (int)bucket_of(a.o.radius2, scale);
+                    int bsel = -1;
+                    if (bK >= 0 && bK <= kBuckets - 2) bsel = bK;
+                    if (bk >= 0) {
+                        const int alt = max(bk, br);
+                        if (alt <= kBuckets - 2 && (bsel < 0 || alt < bsel)) bsel = alt;
+                    }
+                    if (bsel >= 0) {
+                        n_keep = HIST(bsel + 1);                    // candidates in buckets <= bsel
+                        if (n_keep <= (uint32_t)kRow) { b_keep = (uint32_t)bsel; counting = false; }
+                        else { tau = (double)(bsel + 1) / scale; scale = (double)kBuckets / tau; }   // zoom in
+                    } else if (tau < tau_full) {
+                        tau = tau_full; scale = (double)kBuckets / tau;                              // full range
+                    } else { active = false; counting = false; }
+                }
+            }
+            if (counting) { active = false; counting = false; }    // attempts used up
+            // ---- pass B: append the candidates of buckets <= b_keep to the row, bucket-ordered
+            if (__any_sync(kFull, active)) {
+#pragma unroll 1
+                for (int dz = 0; dz <= 2 * R; ++dz) {
+#pragma unroll 1
+                    for (int dy = 0; dy <= 2 * R; ++dy) {
+                        int p = 0, pe = 0;
+                        uint32_t tag = 0;
+                        if (active) {
+                            const int ri = (cy - cy0) + dz * nyr + dy;
+                            const uint16_t* trow = sm.tab + ri * tabw;
+                            p = trow[c_lo]; pe = trow[c_hi1];
+                            tag = (uint32_t)ri << 10;
+                        }
+                        for (; p + 1 < pe; p += 2) {
+                            const double d0 = dist2(sm.x[p], sm.y[p], sm.z[p], qx, qy, qz);
+                            const double d1 = dist2(sm.x[p + 1], sm.y[p + 1], sm.z[p + 1], qx, qy, qz);
+                            const uint32_t b0 = bucket_of(d0, scale), b1 = bucket_of(d1, scale);
+                            if (b0 <= b_keep) {
+                                const uint32_t slot = HIST(b0);
+                                HIST(b0) = (uint16_t)(slot + 1);
+                                keep[slot * 32] = (uint16_t)(tag | (uint32_t)p);
+                            }
+                            if (b1 <= b_keep) {
+                                const uint32_t slot = HIST(b1);
+                                HIST(b1) = (uint16_t)(slot + 1);
+                                keep[slot * 32] = (uint16_t)(tag | (uint32_t)(p + 1));
+                            }
+                        }
+                        if (p < pe) {
+                            const uint32_t b0 = bucket_of(dist2(sm.x[p], sm.y[p], sm.z[p], qx, qy, qz), scale);
+                            if (b0 <= b_keep) {
+                                const uint32_t slot = HIST(b0);
+                                HIST(b0) = (uint16_t)(slot + 1);
+                                keep[slot * 32] = (uint16_t)(tag | (uint32_t)p);
+                            }
+                        }
+                    }
+                }
+            }
+            // ---- fused epilogue.  The row is an exact initial segment of the (distance, id) order, bucket-
+            // ordered; order it exactly.  Distances are recomputed from the staged coordinates (nothing but
+            // the 2-byte entries is parked); ONE flat loop whose step is either "shift one entry" or "place
+            // and fetch the next", so the warp pays the largest n + inversions of its lanes once.
+            const int n = active ? (int)n_keep : 0;
+            auto d2_of = [&](uint32_t e) {
+                const int idx = (int)(e & 1023u);
+                return dist2(sm.x[idx], sm.y[idx], sm.z[idx], qx, qy, qz);
+            };
+            auto cid_of = [&](uint32_t e) {
+                return __ldg(a.scid + ((int64_t)(e & 1023u) + (int64_t)sm.delta[e >> 10]));
+            };
+            if (n > 1) {
+                int j = 1, i = 1;
+                uint32_t ej = keep[32];
+                double dj = d2_of(ej);
+                double d_top = d2_of(keep[0]);      // distance of the entry at position j - 1
+                bool at_top = true;                 // the next comparison is against position j - 1
+                while (j < n) {
+                    bool shift = false;
+                    uint32_t ep = 0;
+                    if (i > 0) {
+                        ep = keep[(i - 1) * 32];
+                        const double dp = at_top ? d_top : d2_of(ep);
+                        shift = dp > dj || (dp == dj && cid_of(ep) > cid_of(ej));
+                    }
+                    if (shift) {
+                        keep[i * 32] = (uint16_t)ep;
+                        --i;
+                        at_top = false;
+                    } else {
+                        if (i != j) keep[i * 32] = (uint16_t)ej;
+                        else d_top = dj;                                   // ej stays on top
+                        ++j;
+                        i = j;
+                        at_top = true;
+                        if (j < n) { ej = keep[j * 32]; dj = d2_of(ej); }
+                    }
+                }
+            }
+            // ---- in order: kNN row, cumulant covariances of the knn nearest and of the hybrid-search set
+            if (active) {
+                const EpiOut& o = a.o;
+                const uint32_t cid = o.sorted_out ? (uint32_t)q : __ldg(a.scid + q);      // output row of this query
+                Cumulants nrm_cum; nrm_cum.clear();       // hybrid search: max_nn nearest with d2 < r^2
+                Cumulants cov_cum; cov_cum.clear();       // the knn-neighbourhood (region_growing.py:69-71)
+                int nn = 0, kk = 0;
+                bool in_radius = true;
+                const int lim = o.knn > o.max_nn ? o.knn : o.max_nn;
+#pragma unroll 1
+                for (int j = 0; j < lim; ++j) {
+                    const bool present = j < n;
+                    double px = 0.0, py = 0.0, pz = 0.0, d2 = inf;
+                    uint32_t e = 0;
+                    if (present) {
+                        e = keep[j * 32];
+                        const int idx = (int)(e & 1023u);
+                        px = sm.x[idx]; py = sm.y[idx]; pz = sm.z[idx];
+                        d2 = dist2(px, py, pz, qx, qy, qz);
+                    }
+                    if (j < o.knn) {
+                        if (o.out_knn) {
+                            int32_t c = -1;
+                            if (present) {
+                                const int64_t pos = (int64_t)(e & 1023u) + (int64_t)sm.delta[e >> 10];
+                                c = o.sorted_out ? (int32_t)pos : (int32_t)__ldg(a.scid + pos);
+                            }
+                            o.out_knn[(size_t)cid * o.knn + j] = c;
+                        }
+                        if (o.out_d2) o.out_d2[(size_t)cid * o.knn + j] = d2;
+                        if (present) { cov_cum.add(px, py, pz); ++kk; }
+                    }
+                    if (j < o.max_nn && present && in_radius) {
+                        if (d2 < o.radius2) { nrm_cum.add(px, py, pz); ++nn; }
+                        else in_radius = false;            // sorted ascending: nothing closer follows
+                    }
+                }
+                epi_finish(o, cid, nn, kk, nrm_cum, cov_cum);
+            }
+            if (in_step) a.todo[q] = active ? 0 : 1;
+            pending &= ~act;
+            __syncwarp();
+        }
+    }
+}
+#undef HIST
+
+
+// ------------------------------------------------------------------ tier 3 ------
+struct SelectArgs {
+    const P4* qpts;                // query records, fine-grid order
+    // candidate records, cell prefix and geometry of [0] the fine grid and [1] the coarse second grid;
+    // the kernel uses [1] when at least m / coarse_min_share queries are left (the builders of the
+    // second grid test the same device counter), 0 = no second grid
+    const P4* spts[2];
+    const uint32_t* cell_first[2];
+    GridParams g[2];
+    int coarse_min_share;
+    int64_t m;
+    int k;                         // neighbours kept per query (<= 32), clipped to m
+    const uint32_t* todo_idx;      // queries (sorted positions) to process, or NULL = all m
+    const uint32_t* todo_cnt;      // device count of todo_idx
+    uint32_t* out_pos;             // [kSelRow][m] sorted positions of the k nearest, ascending
+    uint8_t* out_cnt;              // [m] number of valid entries of the row
+    // What the consumers use: the k_row nearest (kNN row, covariance) and, of the k nearest, those
+    // within radius2 (hybrid-search normals).  Beyond BOTH the k_row-th distance and the radius
+    // nothing matters, so the walk may stop there instead of at the k-th distance.
+    int k_row; double radius2;
+};
 
 // largest k in [0, 32) with off[k] <= i  (off is a non-decreasing exclusive scan in smem)
 __device__ __forceinline__ int seg_search(const uint32_t* off, uint32_t i) {
@@ -475,11 +722,14 @@ knn_select_kernel(SelectArgs a) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint32_t* const sa_off = s_seg[warp]; uint32_t* const sa_base = sa_off + 64;
 
-    const GridParams g = a.g;
     const int K = a.k;
     const double inf = __longlong_as_double(0x7ff0000000000000LL);
 
     const int64_t n_todo = a.todo_idx ? (int64_t)*a.todo_cnt : a.m;
+    const int which = (a.coarse_min_share > 0 && n_todo > 0 && n_todo * a.coarse_min_share >= a.m) ? 1 : 0;
+    const GridParams g = a.g[which];
+    const P4* const cand_pts = a.spts[which];
+    const uint32_t* const cfirst = a.cell_first[which];
     for (int64_t qi = (int64_t)blockIdx.x * kSelWarps + warp; qi < n_todo; qi += (int64_t)gridDim.x * kSelWarps) {
         const int64_t q = a.todo_idx ? (int64_t)a.todo_idx[qi] : qi;
         const P4 qp = load_p4(a.qpts + q);
@@ -511,7 +761,7 @@ knn_select_kernel(SelectArgs a) {
                 if (i < total) {
                     const int kk = seg_search(sa_off, i);
                     const uint32_t p = sa_base[kk] + (i - sa_off[kk]);
-                    const P4 cp = load_p4(a.spts + p);
+                    const P4 cp = load_p4(cand_pts + p);
                     cand.d = dist2(cp.x, cp.y, cp.z, qx, qy, qz);
                     cand.c = p4_cid(cp);
                     cand.p = p4_pos(cp);           // position in the fine-grid order (what the rows hold)
@@ -551,8 +801,8 @@ knn_select_kernel(SelectArgs a) {
 
         // points of the cells lo..hi (flat cell numbers of one grid row)
         auto range = [&](uint32_t lo, uint32_t hi, uint32_t& first, uint32_t& cnt) {
-            first = __ldg(a.cell_first + lo);
-            cnt = __ldg(a.cell_first + hi + 1) - first;
+            first = __ldg(cfirst + lo);
+            cnt = __ldg(cfirst + hi + 1) - first;
         };
         // squared gap between the query and the slab of cell index c along one axis (conservative)
         auto axis_gap = [&](double qv, double origin, int c, int cq) -> double {
@@ -654,30 +904,24 @@ struct TodoFunctor {
     }
 };
 
-// ------------------------------------------------------------------ epilogue ----
+// ------------------------------------------------------------------ epilogue (tier 3) ----
 struct EpilogueArgs {
     const P4* spts;
     const uint32_t* pos; const uint8_t* cnt;      // pos: [kRow][m] (slot-major: coalesced per query thread)
     int64_t m;
-    int knn, max_nn;
-    double radius2;
-    int32_t* out_knn; double* out_d2; double* out_normals; double* out_cov; double* out_curv;
-    double thr_curve; uint8_t* out_flag;
-    int sorted_out;     // 0: outputs indexed by compact id, neighbours as compact ids; 1: both as sorted positions
+    const uint32_t* q_idx; const uint32_t* q_cnt; // the queries the per-query tier served (sorted positions)
+    EpiOut o;
 };
 
-// One thread per query.  The candidate row (k exact neighbours from the per-query kernel, or
-// the slightly larger bucket-ordered superset from the group kernel) is ordered by
-// (fp64 d2, compact id) and folded IN ORDER into the cumulant covariances (fp summation order
-// is part of the contract).
+// One thread per query of the per-query tier.  The candidate row (its k exact neighbours) is
+// ordered by (fp64 d2, compact id) and folded IN ORDER into the cumulant covariances (fp summation
+// order is part of the contract).
 // Shared memory holds ONE 8-byte key per candidate ([slot][thread] layout, conflict-free):
 // the bit pattern of the non-negative fp64 squared distance -- monotone as an unsigned integer
 // -- with its 6 low mantissa bits replaced by the candidate's slot in the row.  An insertion
 // sort on these integers (rows arrive nearly sorted) orders every pair of candidates whose
 // distances differ above the 58th bit; runs of keys that agree in the upper 58 bits (exact
 // ties, duplicates) are re-ordered by the exact (d2, compact id) comparison afterwards.
-// Everything else (positions, coordinates) is re-read through L1/L2 instead of being parked
-// in shared memory: 384 B instead of 768 B per query, twice the resident warps.
 __device__ __forceinline__ void epi_exact(const EpilogueArgs& a, int64_t s, uint64_t key, double qx, double qy, double qz,
                                           double& d2, uint32_t& c) {
     const uint32_t p = __ldg(a.pos + (size_t)(key & 63u) * a.m + s);
@@ -691,13 +935,16 @@ knn_epilogue_kernel(EpilogueArgs a) {
     extern __shared__ __align__(16) unsigned char epi_smem[];
     uint64_t* const s_key = reinterpret_cast<uint64_t*>(epi_smem);                       // [kRow][threads]
     const int tx = threadIdx.x;
+    const EpiOut& o = a.o;
     const double inf = __longlong_as_double(0x7ff0000000000000LL);
+    const int64_t n_q = a.q_idx ? (int64_t)*a.q_cnt : a.m;
     int64_t stride = (int64_t)gridDim.x * kEpiThreads;
-    for (int64_t s = (int64_t)blockIdx.x * kEpiThreads + tx; s < a.m; s += stride) {
+    for (int64_t qi = (int64_t)blockIdx.x * kEpiThreads + tx; qi < n_q; qi += stride) {
+        const int64_t s = a.q_idx ? (int64_t)a.q_idx[qi] : qi;
         const uint32_t* col = a.pos + s;               // slot j of this query: col[j * m]
         const P4 qp = load_p4(a.spts + s);
         const double qx = qp.x, qy = qp.y, qz = qp.z;
-        const uint32_t cid = a.sorted_out ? (uint32_t)s : p4_cid(qp);     // output row of this query
+        const uint32_t cid = o.sorted_out ? (uint32_t)s : p4_cid(qp);     // output row of this query
         const int n = (int)a.cnt[s];
         // phase 1: candidate records (independent loads, software-pipelined by 4) -> keys
         for (int j0 = 0; j0 < n; j0 += 4) {
@@ -761,7 +1008,7 @@ knn_epilogue_kernel(EpilogueArgs a) {
         Cumulants cov_cum; cov_cum.clear();       // the knn-neighbourhood (region_growing.py:69-71)
         int nn = 0, kk = 0;
         bool in_radius = true;
-        const int lim = a.knn > a.max_nn ? a.knn : a.max_nn;
+        const int lim = o.knn > o.max_nn ? o.knn : o.max_nn;
         for (int j0 = 0; j0 < lim; j0 += 4) {
             P4 cp[4]; uint32_t pp[4];
 #pragma unroll
@@ -779,56 +1026,19 @@ knn_epilogue_kernel(EpilogueArgs a) {
                 const double px = cp[u].x, py = cp[u].y, pz = cp[u].z;
                 double d2 = inf;
                 uint32_t c = 0;
-                if (present) { d2 = dist2(px, py, pz, qx, qy, qz); c = a.sorted_out ? pp[u] : p4_cid(cp[u]); }
-                if (j < a.knn) {
-                    if (a.out_knn) a.out_knn[(size_t)cid * a.knn + j] = present ? (int32_t)c : -1;
-                    if (a.out_d2) a.out_d2[(size_t)cid * a.knn + j] = d2;
+                if (present) { d2 = dist2(px, py, pz, qx, qy, qz); c = o.sorted_out ? pp[u] : p4_cid(cp[u]); }
+                if (j < o.knn) {
+                    if (o.out_knn) o.out_knn[(size_t)cid * o.knn + j] = present ? (int32_t)c : -1;
+                    if (o.out_d2) o.out_d2[(size_t)cid * o.knn + j] = d2;
                     if (present) { cov_cum.add(px, py, pz); ++kk; }
                 }
-                if (j < a.max_nn && present && in_radius) {
-                    if (d2 < a.radius2) { nrm_cum.add(px, py, pz); ++nn; }
+                if (j < o.max_nn && present && in_radius) {
+                    if (d2 < o.radius2) { nrm_cum.add(px, py, pz); ++nn; }
                     else in_radius = false;            // sorted ascending: nothing closer follows
                 }
             }
         }
-        if (a.out_normals) {
-            Vec3 nrm = {0.0, 0.0, 1.0};
-            if (nn >= 3) {
-                double cov6[6];
-                nrm_cum.finish(nn, cov6);
-                nrm = normal_from_cov(cov6, nullptr);
-            }
-            a.out_normals[(size_t)cid * 3 + 0] = nrm.x;
-            a.out_normals[(size_t)cid * 3 + 1] = nrm.y;
-            a.out_normals[(size_t)cid * 3 + 2] = nrm.z;
-        }
-        if (a.out_cov || a.out_curv || a.out_flag) {
-            double cov6[6];
-            cov_cum.finish(kk > 0 ? kk : 1, cov6);
-            bool want_cov = a.out_cov != nullptr && !a.sorted_out;      // sorted space: only where the flag is undecided
-            if (a.out_curv || a.out_flag) {
-                double ev[3];
-                fast_eigen3x3(cov6, ev);
-                const double sum = ev[0] + ev[1] + ev[2];
-                const double r0 = ev[0] / sum, r1 = ev[1] / sum, r2 = ev[2] / sum;
-                if (a.out_curv) {
-                    a.out_curv[(size_t)cid * 3 + 0] = r0; a.out_curv[(size_t)cid * 3 + 1] = r1;
-                    a.out_curv[(size_t)cid * 3 + 2] = r2;
-                }
-                if (a.out_flag) {
-                    const double tol = 1e-9;
-                    const bool fin = isfinite(r0) && isfinite(r1) && isfinite(r2);
-                    const bool below = fin && r0 < a.thr_curve - tol && r1 < a.thr_curve - tol && r2 < a.thr_curve - tol;
-                    const bool above = fin && r0 >= a.thr_curve + tol && r1 >= a.thr_curve + tol && r2 >= a.thr_curve + tol;
-                    a.out_flag[cid] = below ? 1 : (above ? 0 : 2);
-                    if (!below && !above) want_cov = a.out_cov != nullptr;
-                }
-            } else {
-                want_cov = a.out_cov != nullptr;
-            }
-            if (want_cov)
-                for (int t = 0; t < 6; ++t) a.out_cov[(size_t)cid * 6 + t] = cov6[t];
-        }
+        epi_finish(o, cid, nn, kk, nrm_cum, cov_cum);
     }
 }
 
@@ -844,6 +1054,7 @@ static int knn_impl(const double* d_x, const double* d_y, const double* d_z, int
                     int32_t* d_knn, double* d_knn_d2, double* d_normals, double* d_cov, double* d_curv,
                     double thr_curve, uint8_t* d_flag, uint32_t* d_order, void* d_ws, size_t ws_bytes, cudaStream_t st) {
     const uint64_t G = (uint64_t)g.nx * (uint64_t)g.ny * (uint64_t)g.nz;
+    const upcp_tuning tune = tuning();
     Workspace ws(d_ws, ws_bytes);
     uint32_t* counters = ws.take<uint32_t>(64);          // [0] m, [1] tier-2 queries, [2] tier-3 queries
     uint32_t* sel_idx = d_sel ? ws.take<uint32_t>((size_t)n) : nullptr;
@@ -851,24 +1062,28 @@ static int knn_impl(const double* d_x, const double* d_y, const double* d_z, int
     uint32_t* keys = ws.take<uint32_t>((size_t)m);
     uint32_t* rank = ws.take<uint32_t>((size_t)m);
     P4* spts = ws.take<P4>((size_t)m);
-    float4* spf = ws.take<float4>((size_t)m);
+    double* sx = ws.take<double>((size_t)m);
+    double* sy = ws.take<double>((size_t)m);
+    double* sz = ws.take<double>((size_t)m);
+    uint32_t* scid = ws.take<uint32_t>((size_t)m);
     uint32_t* cell_first = ws.take<uint32_t>((size_t)grid_cell_cap(m) + 1);
     P4* spts2 = ws.take<P4>((size_t)m);                                   // coarse grid of the per-query tier
     uint32_t* cell_first2 = ws.take<uint32_t>((size_t)grid_cell_cap(m) / 4 + 2);
-    uint32_t* nb_pos = ws.take<uint32_t>((size_t)m * kRow);
+    uint32_t* nb_pos = ws.take<uint32_t>((size_t)m * kSelRow);             // rows of the per-query tier
     uint8_t* nb_cnt = ws.take<uint8_t>((size_t)m);
     uint8_t* todo[2] = {ws.take<uint8_t>((size_t)m), ws.take<uint8_t>((size_t)m)};
     uint32_t* todo_idx[2] = {ws.take<uint32_t>((size_t)m), ws.take<uint32_t>((size_t)m)};
     if (!ws.ok) UPCP_FAIL(UPCP_E_WORKSPACE, "knn: workspace too small");
     if (G > grid_cell_cap(m)) UPCP_FAIL(UPCP_E_INTERNAL, "knn: grid larger than its cap");
 
+    prof_begin(UPCP_PROF_KNN, st);
+    prof_begin(UPCP_PROF_KNN_BUILD, st);
     if (d_sel) {
+        // (m is the caller's count of the same mask -- DeviceTile.bbox delivers it with the bounding box --;
+        // it is not re-read from the device here: no host round trip inside the search.  The builders
+        // clamp their gathers, so a wrong m gives unspecified rows but never an out-of-bounds access.)
         KnnCompactIdx f{sel_idx};
         UPCP_TRY(compact_apply(d_sel, n, counters, prim_ws, st, f));
-        uint32_t hm = 0;
-        UPCP_CUDA_OK(cudaMemcpyAsync(&hm, counters, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-        UPCP_CUDA_OK(cudaStreamSynchronize(st));
-        if ((int64_t)hm != m) UPCP_FAIL(UPCP_E_INVALID, "knn: m does not match the number of selected points");
     } else if (m != n) {
         UPCP_FAIL(UPCP_E_INVALID, "knn: m must equal n when no selection is given");
     }
@@ -876,73 +1091,76 @@ static int knn_impl(const double* d_x, const double* d_y, const double* d_z, int
     // cell numbers + arrival ranks + per-cell counts, exclusive prefix over ALL cells, placement
     const int grid_m = grid_for(m, kBlock);
     UPCP_CUDA_OK(cudaMemsetAsync(cell_first, 0, ((size_t)G + 1) * 4, st));
-    knn_keys_kernel<<<grid_m, kBlock, 0, st>>>(d_x, d_y, d_z, sel_idx, m, g, keys, rank, cell_first);
+    knn_keys_kernel<<<grid_m, kBlock, 0, st>>>(d_x, d_y, d_z, sel_idx, n, m, g, keys, rank, cell_first);
     UPCP_LAUNCH_OK();
     UPCP_TRY(exclusive_scan_u32(cell_first, cell_first, (int64_t)G + 1, nullptr, prim_ws, st));
-    knn_place_kernel<<<grid_m, kBlock, 0, st>>>(d_x, d_y, d_z, sel_idx, keys, rank, cell_first, m, g, spts, spf, d_order);
+    knn_place_kernel<<<grid_m, kBlock, 0, st>>>(d_x, d_y, d_z, sel_idx, keys, rank, cell_first, n, m, spts, sx, sy, sz,
+                                                scid, d_order);
     UPCP_LAUNCH_OK();
+    prof_end(UPCP_PROF_KNN_BUILD, st, m);
 
     int kh = knn > max_nn ? knn : max_nn;
     if ((int64_t)kh > m) kh = (int)m;
-    prof_begin(UPCP_PROF_KNN, st);
-    // block tiers: lane per query over its (2R+1)^3 cell block; each tier takes the queries the
+    EpiOut eo;
+    eo.knn = knn; eo.max_nn = max_nn; eo.radius2 = radius * radius;
+    eo.out_knn = d_knn; eo.out_d2 = d_knn_d2; eo.out_normals = d_normals; eo.out_cov = d_cov; eo.out_curv = d_curv;
+    eo.thr_curve = thr_curve; eo.out_flag = d_flag; eo.sorted_out = d_order ? 1 : 0;
+
+    // ---- segment tiers: search + fused epilogue out of shared memory; each tier takes the queries the
     // previous one could not certify
-    BlockArgs ba;
-    ba.spts = spts; ba.spf = spf; ba.cell_first = cell_first; ba.g = g; ba.m = m; ba.k = kh;
-    ba.q_idx = nullptr; ba.q_cnt = nullptr; ba.out_pos = nb_pos; ba.out_cnt = nb_cnt; ba.todo = todo[0];
-    ba.k_row = knn < kh ? knn : kh; ba.radius2 = radius * radius;
-    // A lane that has to scan a crowded 5^3 block alone holds its whole warp up; such queries are better
-    // served by the warp-per-query tier, which prunes (swept on the bench tile: 60000 / 4000 / 1500 / 600 /
-    // 300 candidates -> 17.6 / 17.4 / 17.2 / 16.5 / 17.0 ms for the search).
-    uint32_t max_total1 = 60000u, max_total2 = 600u;
-    if (const char* env = getenv("UPCP_BLK1_MAXTOTAL")) { int v = atoi(env); if (v >= 1 && v <= 60000) max_total1 = (uint32_t)v; }
-    if (const char* env = getenv("UPCP_BLK2_MAXTOTAL")) { int v = atoi(env); if (v >= 1 && v <= 60000) max_total2 = (uint32_t)v; }
-    ba.max_total = max_total1;
-    // the filter passes live on L1 hits (each candidate is read by ~150 queries, twice): keep the
-    // shared-memory carve-out at what the resident CTAs need, the rest of the 256 KB stays L1
-    UPCP_CUDA_OK(cudaFuncSetAttribute(knn_block_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, 40));
-    UPCP_CUDA_OK(cudaFuncSetAttribute(knn_block_kernel<2>, cudaFuncAttributePreferredSharedMemoryCarveout, 40));
+    prof_begin(UPCP_PROF_KNN_SEG, st);
+    SegArgs sa;
+    sa.sx = sx; sa.sy = sy; sa.sz = sz; sa.scid = scid; sa.cell_first = cell_first; sa.g = g; sa.m = m;
+    sa.K = kh; sa.k_row = knn < kh ? knn : kh;
+    sa.q_idx = nullptr; sa.q_cnt = nullptr; sa.todo = todo[0];
+    sa.max_total = (uint32_t)tune.knn_tier1_max_block;
+    sa.o = eo;
+    const size_t smem1 = sizeof(SegSmem<1>) * kSegWarps, smem2 = sizeof(SegSmem<2>) * kSegWarps;
+    UPCP_CUDA_OK(cudaFuncSetAttribute(knn_seg_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
+    UPCP_CUDA_OK(cudaFuncSetAttribute(knn_seg_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
     {
-        const int64_t cap_blocks = (int64_t)num_sms() * 32;
-        const int64_t need = (m + kBlkThreads - 1) / kBlkThreads;
-        knn_block_kernel<1><<<(int)(need < cap_blocks ? need : cap_blocks), kBlkThreads, 0, st>>>(ba);
+        // one 32-query chunk per warp while the grid stays below a few thousand waves, grid-stride beyond
+        const int64_t cap_blocks = (int64_t)num_sms() * 3 * 256;
+        const int64_t need = ((m + 31) / 32 + kSegWarps - 1) / kSegWarps;
+        knn_seg_kernel<1><<<(int)(need < cap_blocks ? need : cap_blocks), kSegThreads, smem1, st>>>(sa);
         UPCP_LAUNCH_OK();
     }
-    for (int tier = 2; tier <= kTiers; ++tier) {
-        uint8_t* prev = todo[(tier - 2) & 1];
-        uint8_t* next = todo[(tier - 1) & 1];
-        uint32_t* idx = todo_idx[(tier - 2) & 1];
-        uint32_t* cnt = counters + tier - 1;            // counters[1..]: queries entering tier 2, 3, ...
-        TodoFunctor f{idx};
-        UPCP_TRY(compact_apply(prev, m, cnt, prim_ws, st, f));
-        UPCP_CUDA_OK(cudaMemsetAsync(next, 0, (size_t)m, st));
-        ba.q_idx = idx; ba.q_cnt = cnt; ba.todo = next; ba.max_total = max_total2;
-        const int grid = num_sms() * 8;
-        if (tier == 2) knn_block_kernel<2><<<grid, kBlkThreads, 0, st>>>(ba);
-        else if (tier == 3) knn_block_kernel<3><<<grid, kBlkThreads, 0, st>>>(ba);
-        else knn_block_kernel<4><<<grid, kBlkThreads, 0, st>>>(ba);
+    int last = 0;                                           // todo[last]: what the tiers so far left over
+    if (tune.knn_tiers >= 2) {
+        TodoFunctor f{todo_idx[0]};
+        UPCP_TRY(compact_apply(todo[0], m, counters + 1, prim_ws, st, f));
+        UPCP_CUDA_OK(cudaMemsetAsync(todo[1], 0, (size_t)m, st));
+        sa.q_idx = todo_idx[0]; sa.q_cnt = counters + 1; sa.todo = todo[1];
+        sa.max_total = (uint32_t)tune.knn_tier2_max_block;
+        const int64_t cap_blocks = (int64_t)num_sms() * 3 * 4;
+        const int64_t need = ((m + 31) / 32 + kSegWarps - 1) / kSegWarps;
+        knn_seg_kernel<2><<<(int)(need < cap_blocks ? need : cap_blocks), kSegThreads, smem2, st>>>(sa);
         UPCP_LAUNCH_OK();
+        last = 1;
     }
-    // last tier: the rest (sparse surroundings, overflowing rows): warp per query
-    uint32_t* n_todo_last = counters + kTiers;
-    uint32_t* todo_last_idx = todo_idx[(kTiers - 1) & 1];
+    prof_end(UPCP_PROF_KNN_SEG, st, m);
+
+    // ---- last tier: the rest (sparse surroundings, crowded blocks, overflowing rows): warp per query
+    prof_begin(UPCP_PROF_KNN_SELECT, st);
+    uint32_t* n_todo_last = counters + 2;
+    uint32_t* todo_last_idx = todo_idx[last];
     {
         TodoFunctor f{todo_last_idx};
-        UPCP_TRY(compact_apply(todo[(kTiers - 1) & 1], m, n_todo_last, prim_ws, st, f));
+        UPCP_TRY(compact_apply(todo[last], m, n_todo_last, prim_ws, st, f));
     }
     // The per-query tier walks grid rows; where it has much to do (sparse clutter, noise) it gets a
     // second grid with `coarse` times larger cells -- coarse^2 times fewer rows per shell -- built
-    // from the fine-sorted records (one more counting sort).
-    uint32_t h_last = 0;
-    UPCP_CUDA_OK(cudaMemcpyAsync(&h_last, n_todo_last, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-    UPCP_CUDA_OK(cudaStreamSynchronize(st));
+    // from the fine-sorted records (one more counting sort).  Whether it pays is decided ON THE DEVICE
+    // from the number of queries left (the builders and the search read the same counter): no host
+    // round trip.
     SelectArgs a;
-    a.qpts = spts; a.spts = spts; a.cell_first = cell_first; a.g = g; a.m = m; a.k = kh;
+    a.qpts = spts; a.m = m; a.k = kh;
+    a.spts[0] = spts; a.cell_first[0] = cell_first; a.g[0] = g;
+    a.spts[1] = spts; a.cell_first[1] = cell_first; a.g[1] = g; a.coarse_min_share = 0;
     a.todo_idx = todo_last_idx; a.todo_cnt = n_todo_last; a.out_pos = nb_pos; a.out_cnt = nb_cnt;
     a.k_row = knn < kh ? knn : kh; a.radius2 = radius * radius;
-    int coarse = 2;
-    if (const char* env = getenv("UPCP_KNN_COARSE")) { int v = atoi(env); if (v >= 1 && v <= 16) coarse = v; }   // tuning knobs
-    if (h_last > 0 && coarse > 1 && (int64_t)h_last * 200 >= m) {
+    const int coarse = tune.knn_coarse;
+    if (coarse > 1) {
         GridParams g2 = g;
         g2.cell = g.cell * (double)coarse; g2.inv_cell = 1.0 / g2.cell;
         g2.nx = (g.nx + coarse - 1) / coarse; g2.ny = (g.ny + coarse - 1) / coarse; g2.nz = (g.nz + coarse - 1) / coarse;
@@ -950,37 +1168,28 @@ static int knn_impl(const double* d_x, const double* d_y, const double* d_z, int
         const uint64_t G2 = (uint64_t)g2.nx * (uint64_t)g2.ny * (uint64_t)g2.nz;
         if (G2 + 1 <= grid_cell_cap(m) / 4 + 2) {
             // (keys / rank are free again)
+            const int share = 200;                      // coarse grid when at least m / 200 queries are left
             UPCP_CUDA_OK(cudaMemsetAsync(cell_first2, 0, ((size_t)G2 + 1) * 4, st));
-            knn_keys2_kernel<<<grid_m, kBlock, 0, st>>>(spts, m, g2, keys, rank, cell_first2);
+            knn_keys2_kernel<<<grid_m, kBlock, 0, st>>>(spts, m, g2, keys, rank, cell_first2, n_todo_last, share);
             UPCP_LAUNCH_OK();
             UPCP_TRY(exclusive_scan_u32(cell_first2, cell_first2, (int64_t)G2 + 1, nullptr, prim_ws, st));
-            knn_place2_kernel<<<grid_m, kBlock, 0, st>>>(spts, keys, rank, cell_first2, m, spts2);
+            knn_place2_kernel<<<grid_m, kBlock, 0, st>>>(spts, keys, rank, cell_first2, m, spts2, n_todo_last, share);
             UPCP_LAUNCH_OK();
-            a.spts = spts2; a.cell_first = cell_first2; a.g = g2;
+            a.spts[1] = spts2; a.cell_first[1] = cell_first2; a.g[1] = g2; a.coarse_min_share = share;
         }
     }
-    if (h_last > 0) {
-        knn_select_kernel<<<num_sms() * 8, kSelThreads, 0, st>>>(a);
-        UPCP_LAUNCH_OK();
-    }
-    prof_end(UPCP_PROF_KNN, st, m);
-    if (getenv("UPCP_KNN_DEBUG")) {       // development aid: sizes of the search structures
-        uint32_t h[8];
-        cudaMemcpyAsync(h, counters, sizeof(h), cudaMemcpyDeviceToHost, st);
-        cudaStreamSynchronize(st);
-        fprintf(stderr, "[upcp knn] m=%lld grid=%dx%dx%d (%llu cells) cell=%.4f block<2>=%u per-query=%u\n",
-                (long long)m, g.nx, g.ny, g.nz, (unsigned long long)G, g.cell, h[1], h[2]);
-    }
+    knn_select_kernel<<<num_sms() * 8, kSelThreads, 0, st>>>(a);
+    UPCP_LAUNCH_OK();
 
     EpilogueArgs e;
     e.spts = spts; e.pos = nb_pos; e.cnt = nb_cnt; e.m = m;
-    e.knn = knn; e.max_nn = max_nn; e.radius2 = radius * radius;
-    e.out_knn = d_knn; e.out_d2 = d_knn_d2; e.out_normals = d_normals; e.out_cov = d_cov; e.out_curv = d_curv;
-    e.thr_curve = thr_curve; e.out_flag = d_flag; e.sorted_out = d_order ? 1 : 0;
-    const size_t epi_smem = (size_t)kRow * kEpiThreads * 8;
+    e.q_idx = todo_last_idx; e.q_cnt = n_todo_last; e.o = eo;
+    const size_t epi_smem = (size_t)kSelRow * kEpiThreads * 8;
     UPCP_CUDA_OK(cudaFuncSetAttribute(knn_epilogue_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)epi_smem));
     knn_epilogue_kernel<<<grid_for(m, kEpiThreads, 4), kEpiThreads, epi_smem, st>>>(e);
     UPCP_LAUNCH_OK();
+    prof_end(UPCP_PROF_KNN_SELECT, st, m);
+    prof_end(UPCP_PROF_KNN, st, m);
     return UPCP_OK;
 }
 
@@ -999,11 +1208,11 @@ size_t upcp_knn_ws_bytes(int64_t n, int64_t m, int kmax) {
     bytes += align_up((size_t)n * 4);
     bytes += align_up((compact_ws_words(n) + sort_ws_words(m) + scan_ws_words((int64_t)gcap + 1)) * 4);
     bytes += 2 * align_up((size_t)m * 4);                                   // cell numbers, arrival ranks
-    bytes += align_up((size_t)m * 32);                                      // sorted points (x, y, z, id)
-    bytes += align_up((size_t)m * 16);                                      // fp32 origin-relative copy
+    bytes += align_up((size_t)m * 32);                                      // sorted points (x, y, z, ids)
+    bytes += 3 * align_up((size_t)m * 8) + align_up((size_t)m * 4);         // sorted coordinates (SoA), compact ids
     bytes += align_up((gcap + 1) * 4);                                      // dense cell prefix
     bytes += align_up((size_t)m * 32) + align_up((gcap / 4 + 2) * 4);       // coarse grid of the per-query tier
-    bytes += align_up((size_t)m * kRow * 4) + 3 * align_up((size_t)m);      // neighbour rows, counts, todo flags
+    bytes += align_up((size_t)m * kSelRow * 4) + 3 * align_up((size_t)m);   // per-query-tier rows, counts, todo flags
     bytes += 2 * align_up((size_t)m * 4);                                   // todo lists
     return bytes + 4096;
 }

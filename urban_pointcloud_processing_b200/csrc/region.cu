@@ -114,11 +114,11 @@ grow_requeue_kernel(const int64_t* __restrict__ extra, int64_t n_extra, const ui
     }
 }
 
-// Seeds a warp discovers stay with that warp (a small ring in shared memory) up to kLocalCap; only
+// Seeds a warp discovers stay with that warp (a small ring in shared memory) up to the tuning knob grow_local_chain (measured optimum 2; 1 .. 32 swept); only
 // the overflow goes through the global queue.  The frontier is narrow and every hop through the
 // global queue costs three dependent L2 round trips (tail / pending atomics, slot write, the
 // consumer's poll) on top of the expansion itself; the local path removes them from the chain.
-constexpr int kLocalCap = 2;              // measured optimum (1 .. 32 swept): latency of the chain vs load balance
+
 constexpr int kRing = 64;                // ring size (power of two, >= the largest local cap + 32)
 
 __global__ void __launch_bounds__(kGrowThreads)
@@ -312,23 +312,18 @@ int grow_ws(void* d_ws, size_t ws_bytes, int64_t m, GrowWs* out) {
 }
 int grow_drain(const int32_t* d_knn, int knn, const double* d_normals, const uint8_t* d_can_seed, int64_t m,
                double threshold_angle_deg, const GrowWs& w, cudaStream_t st) {
-    // persistent kernel: every CTA must be resident (waiting warps spin on the queue)
-    static int per_sm_cached = 0;
-    int per_sm = per_sm_cached;
-    if (per_sm == 0) {
-        UPCP_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, grow_kernel, kGrowThreads, 0));
-        if (per_sm < 1) UPCP_FAIL(UPCP_E_CUDA, "region_grow: kernel cannot be resident");
-        // one CTA per SM: more pollers only add contention on the queue counters (1 / 2 / 4 swept)
-        if (per_sm > 1) per_sm = 1;
-        per_sm_cached = per_sm;
-    }
+    // persistent kernel: every CTA must be resident (waiting warps spin on the queue).  One CTA per
+    // SM by default: more pollers only add contention on the queue counters (1 / 2 / 4 swept).
+    const upcp_tuning tune = tuning();
+    int per_sm = 0;
+    UPCP_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, grow_kernel, kGrowThreads, 0));
+    if (per_sm < 1) UPCP_FAIL(UPCP_E_CUDA, "region_grow: kernel cannot be resident");
+    if (per_sm > tune.grow_ctas_per_sm) per_sm = tune.grow_ctas_per_sm;
     int grid = num_sms() * per_sm;
     int64_t need = (m + (kGrowThreads / 32) - 1) / (kGrowThreads / 32);
     if (need < grid) grid = (int)(need < 1 ? 1 : need);
-    int local_cap = kLocalCap;
+    const int local_cap = tune.grow_local_chain;
     const int sleep_ns = 64;
-    if (const char* env = getenv("UPCP_GROW_LOCAL")) { int v = atoi(env); if (v >= 0 && v <= 32) local_cap = v; }   // tuning knobs
-    if (const char* env = getenv("UPCP_GROW_GRID")) { int v = atoi(env); if (v >= 1 && v < grid) grid = v; }
     grow_kernel<<<grid, kGrowThreads, 0, st>>>(d_knn, knn, d_normals, d_can_seed, m, threshold_angle_deg,
                                                w.state, w.queue, w.ctr, local_cap, sleep_ns);
     UPCP_LAUNCH_OK();
