@@ -61,12 +61,12 @@ int64_t     upcp_launch_count(void);
 #define UPCP_PROF_LINK   3
 #define UPCP_PROF_KNN    4
 #define UPCP_PROF_GROW   5
-/* sub-brackets of slot 4 (which spans the whole neighbour-search stage S4: grid build, all search
- * tiers, epilogues): 6 grid build (cell keys, prefix, placement), 7 segment tiers (search + fused
- * epilogue out of shared memory), 8 per-query tier (compaction, second grid, search, its epilogue) */
-#define UPCP_PROF_KNN_BUILD  6
-#define UPCP_PROF_KNN_SEG    7
-#define UPCP_PROF_KNN_SELECT 8
+/* sub-brackets of slot 4 (which spans the whole neighbour-search stage S4): 6 grid build (cell keys,
+ * prefix, placement of the sorted records), 7 search (both block tiers, compactions, second grid,
+ * per-query tier), 8 epilogue (exact order, covariances, normals, kNN rows) */
+#define UPCP_PROF_KNN_BUILD    6
+#define UPCP_PROF_KNN_SEARCH   7
+#define UPCP_PROF_KNN_EPILOGUE 8
 #define UPCP_PROF_SLOTS  9
 int         upcp_prof_enable(int on);
 int         upcp_prof_reset(void);
@@ -77,7 +77,7 @@ const char* upcp_prof_slot_name(int slot);
  * upcp_tuning_default() fills in what bench.py was measured with; upcp_tuning_set() validates
  * and installs a copy that every later call reads once at entry. */
 typedef struct upcp_tuning {
-    int32_t knn_tiers;            /* segment tiers before the per-query tier: 1 or 2                     */
+    int32_t knn_tiers;            /* block tiers before the per-query tier: 1 or 2                       */
     int32_t knn_tier1_max_block;  /* 3^3 blocks with more candidates leave tier 1 to the next tier       */
     int32_t knn_tier2_max_block;  /* the same for the 5^3 blocks of tier 2                               */
     int32_t knn_coarse;           /* cell factor of the per-query tier's second grid (1 = none)          */

@@ -459,18 +459,76 @@ def golden_variants(upcp):
     assert np.count_nonzero(bsurf) > 1000
 
 
+CONFIG1_N, CONFIG1_SEED = 4_000_000, 23869702
+CONFIG1_LAYERS = [{'bottom': 12., 'grid_size': 0.1, 'threshold': 0.5},
+                  {'bottom': 0., 'top': 12., 'grid_size': 0.05, 'threshold': 0.5}]
+
+
+def config1_cloud(data_dir):
+    """The config-1 cloud (regenerated from its seed wherever it is needed: the fixture stores labels only)."""
+    from urban_pointcloud_processing_b200.utils.ahn_utils import load_ahn_tile
+    ahn = load_ahn_tile(os.path.join(data_dir, 'ahn_2386_9702.npz'))
+    df = pd.read_csv(os.path.join(data_dir, 'bgt_buildings_demo.csv'))
+    rings = [np.array(ast.literal_eval(p), dtype=np.float64) for p in df.polygon.values]
+    return synthetic.make_demo_cloud(CONFIG1_N, ahn, rings, seed=CONFIG1_SEED)
+
+
+def golden_config1(upcp):
+    """BASELINE.json config 1 as SURVEY 8(d) specifies it: 4 M synthetic points over the REAL demo AHN
+    raster (NaN holes) and BGT footprints, the notebook-0 processor list restricted to the hot path
+    (AHN ground -> BGT road -> BGT building -> LayerLCC) through the reference's own Pipeline, then the
+    reference's RegionGrowing on the result (Region growing.ipynb).  shapely is not installed here, so
+    offset = 0 and refine_ground = False (flagged in DESIGN.md)."""
+    import time
+    from upcp.fusion import AHNFuser, BGTBuildingFuser, BGTRoadFuser
+    from upcp.region_growing import LayerLCC
+    from upcp.region_growing.region_growing import RegionGrowing
+    from upcp.utils.ahn_utils import NPZReader
+    from upcp.utils.bgt_utils import BGTPolyReader
+    from upcp.labels import Labels
+    from upcp.pipeline import Pipeline
+    points, kind = config1_cloud(os.path.join(GOLDEN, 'demo'))
+    ahn_reader = NPZReader(os.path.join(REF_DATA, 'ahn'))
+    bld = BGTPolyReader(bgt_file=os.path.join(REF_DATA, 'bgt', 'bgt_buildings_demo.csv'))
+    road = BGTPolyReader(bgt_file=os.path.join(REF_DATA, 'bgt', 'bgt_roads_demo.csv'))
+    procs = (AHNFuser(Labels.GROUND, ahn_reader, target='ground', epsilon=0.2, refine_ground=False),
+             BGTRoadFuser(Labels.ROAD, bgt_reader=road),
+             BGTBuildingFuser(Labels.BUILDING, bgt_reader=bld, offset=0, ahn_reader=ahn_reader),
+             LayerLCC(Labels.BUILDING, ahn_reader, params=[dict(p) for p in CONFIG1_LAYERS]))
+    labels = np.zeros(len(points), dtype=np.uint16)
+    t0 = time.time()
+    labels = Pipeline(processors=procs, ahn_reader=ahn_reader, caching=True).process_cloud(TILECODE, points, labels)
+    t1 = time.time()
+    print(f'  config1 pipeline: {t1 - t0:.1f} s, hist {dict(zip(*np.unique(labels, return_counts=True)))}')
+    rg = RegionGrowing(Labels.BUILDING, exclude_labels=(Labels.GROUND,))
+    grown = rg.get_labels(points, labels.copy(), labels == 0, TILECODE)          # REAL reference class
+    t2 = time.time()
+    print(f'  config1 region growing: {t2 - t1:.1f} s, hist {dict(zip(*np.unique(grown, return_counts=True)))}')
+    # the restatement gives the same labels (this is what pins the oracle's control flow at this size)
+    ahn_tile = ahn_reader.filter_tile(TILECODE)
+    o = np.zeros(len(points), dtype=np.uint16)
+    o = R.ahn_fuser_labels(points, o, o == 0, ahn_tile, Labels.GROUND, 'ground', 0.2)
+    o = R.road_fuser_labels(points, o, road.filter_tile(TILECODE, bgt_types=BGTRoadFuser.ALL_TYPES, merge=True), Labels.ROAD)
+    o = R.building_fuser_labels(points, o, o == 0, bld.filter_tile(TILECODE, bgt_types=['pand'], merge=True),
+                                Labels.BUILDING, ahn_tile, 0.2)
+    o = R.layer_lcc_labels(points, o, o == 0, ahn_tile, Labels.BUILDING, [dict(p) for p in CONFIG1_LAYERS])
+    assert np.array_equal(o, labels), 'oracle mismatch on config 1 (pipeline)'
+    np.savez_compressed(os.path.join(GOLDEN, 'config1_golden.npz'), n=np.array(CONFIG1_N), seed=np.array(CONFIG1_SEED),
+                        labels_pipeline=labels.astype(np.uint8), labels_region_growing=grown.astype(np.uint8),
+                        checksum_points=np.array(int(mm(points).astype(np.int64).sum())))
+
+
 def main():
     os.makedirs(GOLDEN, exist_ok=True)
     upcp = ref_harness.load_reference()
     print('reference loaded from', upcp.__file__)
-    copy_demo_data()
-    golden_pip(upcp)
-    golden_raster(upcp)
-    golden_scalars(upcp)
-    golden_demo(upcp)
-    golden_pipeline(upcp)
-    golden_objects(upcp)
-    golden_variants(upcp)
+    steps = {'demo_data': lambda u: copy_demo_data(), 'pip': golden_pip, 'raster': golden_raster,
+             'scalars': golden_scalars, 'demo': golden_demo, 'pipeline': golden_pipeline, 'objects': golden_objects,
+             'variants': golden_variants, 'config1': golden_config1}
+    wanted = sys.argv[1:] or list(steps)
+    for name in wanted:
+        print(name)
+        steps[name](upcp)
     print('golden vectors written to', GOLDEN)
 
 

@@ -348,3 +348,41 @@ def test_tile_worker_scheduling_host_logic(monkeypatch):
         pipe.process_clouds(['a', 'b'], [None], [None, None])
     with pytest.raises(ValueError):
         pipe.process_tiles_device(['a'], [], [None])
+
+
+def test_ahn_reader_cache_is_safe_under_concurrent_tiles(tmp_path, monkeypatch):
+    """One NPZReader shared by worker threads that label DIFFERENT tiles (process_clouds /
+    process_folder(workers=W)): every filter_tile / interpolation-cache access must deliver the tile
+    that was asked for, however the (slow) file loads interleave."""
+    import threading
+    import time
+    codes = ['1000_2000', '1001_2000', '1002_2000']
+    for k, code in enumerate(codes):
+        np.savez(tmp_path / f'ahn_{code}.npz', x=np.arange(4.0), y=np.arange(4.0)[::-1].copy(),
+                 ground=np.full((4, 4), float(k), dtype=np.float16), building=np.full((4, 4), 10.0 + k, dtype=np.float16))
+    real_load = ahn_utils.load_ahn_tile
+
+    def slow_load(fname):
+        tile = real_load(fname)
+        time.sleep(0.002 * (1 + (hash(fname) & 3)))         # uneven load times: the interleavings that used to mix tiles
+        return tile
+    monkeypatch.setattr(ahn_utils, 'load_ahn_tile', slow_load)
+    reader = ahn_utils.NPZReader(tmp_path, caching=True)
+    bad = []
+
+    def worker(k):
+        for it in range(60):
+            code = codes[(k + it) % len(codes)] if it % 7 == 0 else codes[k]
+            want = float(codes.index(code))
+            tile = reader.filter_tile(code)
+            if tile['ground_surface'][0, 0] != want or tile['building_surface'][0, 0] != want + 10.0:
+                bad.append((k, it, code))
+            if it % 5 == 0:
+                reader._clear_cache()                        # what cache_interpolator of another tile does
+    threads = [threading.Thread(target=worker, args=(k,)) for k in range(3)]
+    [t.start() for t in threads]
+    [t.join() for t in threads]
+    assert not bad, bad[:5]
+    # caching off: still the right tile, nothing kept
+    reader.set_caching(False)
+    assert reader.filter_tile(codes[1])['ground_surface'][0, 0] == 1.0 and len(reader._tiles) == 0

@@ -76,6 +76,38 @@ def lcc_components(points, grid_size, min_size):
     return LabelConnectedComp(grid_size=grid_size, min_component_size=min_size).get_components(points)
 
 
+def test_config2_lcc_20m_level10_matches_oracle(tile20):
+    """grid 0.05 (level 10) and min_component_size in {100, 1500, 5000} (BASELINE config 2) against the
+    oracle DIRECTLY at full size, plus grid 0.1 with 5000."""
+    sub = tile20['points'][tile20['kind'] != 0]
+    assert R.get_octree_level(sub, 0.05) == 10
+    want_all = R.lcc_get_components(sub, 0.05, 1)               # the full partition, once (20 s of CPU)
+    sizes = np.bincount(want_all.astype(np.int64))
+    for min_size in (100, 1500, 5000):
+        got = lcc_components(sub, 0.05, min_size)
+        want = np.where(sizes[want_all.astype(np.int64)] >= min_size, want_all, -1)      # label_connected_comp.py:89-97
+        assert np.array_equal(R.canonical_components(got), R.canonical_components(want)), min_size
+        print(f'level 10, min {min_size}: {len(np.unique(got[got >= 0]))} components, {(got < 0).sum()} points dropped')
+    # the oracle's own filter for the largest size, and the coarser grid with it
+    assert np.array_equal(R.canonical_components(lcc_components(sub, 0.05, 5000)),
+                          R.canonical_components(R.lcc_get_components(sub, 0.05, 5000)))
+    assert np.array_equal(R.canonical_components(lcc_components(sub, 0.1, 5000)),
+                          R.canonical_components(R.lcc_get_components(sub, 0.1, 5000)))
+    # how exposed the float32 cell arithmetic is on this cloud: points whose level-10 cell coordinate
+    # lies within one float32 ulp of a cell boundary (a differently rounded division would move them)
+    from oracle import natives
+    xs, ys, zs = (np.ascontiguousarray(sub[:, i].astype(np.float32)) for i in range(3))
+    p = natives.octree_params(xs, ys, zs)
+    dim_min, cs = np.asarray(p[:3], dtype=np.float32), np.float32(p[3])
+    width = np.float32(cs * np.float32(1 << (21 - 10)))
+    near = np.zeros(len(sub), dtype=bool)
+    for i, c in enumerate((xs, ys, zs)):
+        t = (c - dim_min[i]) / width                             # float32, like the cell position itself
+        near |= (np.nextafter(t, np.float32(np.inf)).astype(np.int64) != t.astype(np.int64)) | \
+                (np.nextafter(t, np.float32(-np.inf)).astype(np.int64) != t.astype(np.int64))
+    print(f'level 10: {near.sum()} of {len(sub)} points within 1 float32 ulp of a cell boundary')
+
+
 def test_config2_lcc_20m_level10_invariants(tile20):
     """grid 0.05 (level 10): cell-graph invariants re-derived in numpy from the oracle's own cell
     assignment + permutation invariance."""

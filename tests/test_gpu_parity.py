@@ -576,6 +576,67 @@ def test_demo_tile_matches_reference_golden(golden):
     assert np.array_equal(gz, R.fast_grid_lookup(t['x'], t['y'], t['ground_surface'], points), equal_nan=True)
 
 
+def test_config1_demo_tile_4m_matches_reference_golden(golden):
+    """BASELINE config 1 as SURVEY 8(d) specifies it: 4 M synthetic points over the REAL demo AHN raster (NaN
+    holes) and BGT footprints; AHN ground -> BGT road -> BGT building -> LayerLCC through Pipeline, then
+    RegionGrowing -- bit for bit the labels of the reference's own classes (tests/golden/config1_golden.npz,
+    oracle/make_golden.py config1).  offset = 0 / refine_ground = False: shapely is in neither container."""
+    from conftest import CONFIG1_LAYERS, config1_cloud
+    g = golden('config1_golden.npz')
+    points, _ = config1_cloud(g)
+    demo = os.path.join(GOLDEN, 'demo')
+    ahn = ahn_utils.NPZReader(demo)
+    bld = bgt_utils.BGTPolyReader(bgt_file=os.path.join(demo, 'bgt_buildings_demo.csv'))
+    road = bgt_utils.BGTPolyReader(bgt_file=os.path.join(demo, 'bgt_roads_demo.csv'))
+    procs = (AHNFuser(Labels.GROUND, ahn, target='ground', epsilon=0.2, refine_ground=False),
+             BGTRoadFuser(Labels.ROAD, bgt_reader=road),
+             BGTBuildingFuser(Labels.BUILDING, bgt_reader=bld, offset=0, ahn_reader=ahn),
+             LayerLCC(Labels.BUILDING, ahn, params=[dict(p) for p in CONFIG1_LAYERS]))
+    labels = np.zeros(len(points), dtype=np.uint16)
+    out = Pipeline(processors=procs, ahn_reader=ahn, caching=True).process_cloud('2386_9702', points, labels)
+    assert out is labels and np.array_equal(labels, g['labels_pipeline'])
+    rg = RegionGrowing(Labels.BUILDING, exclude_labels=(Labels.GROUND,))
+    grown = rg.get_labels(points, labels.copy(), labels == 0, '2386_9702')
+    n_diff = int(np.count_nonzero(grown != g['labels_region_growing']))
+    print(f'config 1: {len(points)} points, region growing added {np.count_nonzero(grown == 10) - np.count_nonzero(labels == 10)} '
+          f'points, {n_diff} labels differ from the reference, {rg.last_stats["n_curvature_on_host"]} curvature flags on the host')
+    assert n_diff == 0
+
+
+def test_shared_npz_reader_with_tiles_in_flight(tmp_path):
+    """One real NPZReader shared by the worker threads of process_clouds, every worker on ITS OWN tilecode
+    (the single-slot tile cache used to hand tile A's raster to tile B)."""
+    codes = ['2386_9702', '2387_9702', '2388_9702', '2389_9702']
+    tiles = []
+    for k, code in enumerate(codes):
+        ox = 119300.0 + 50.0 * k
+        t = synthetic.make_tile(150_000, seed=777 + k, origin=(ox, 485100.0))
+        assert t['tilecode'] == code
+        a = t['ahn_tile']
+        np.savez(tmp_path / f'ahn_{code}.npz', x=a['x'], y=a['y'], ground=(a['ground_surface'] + 0.7 * k).astype(np.float16),
+                 building=a['building_surface'].astype(np.float16))
+        t['points'][:, 2] += 0.7 * k                   # every tile has its own ground level: a foreign raster labels nothing
+        t['points'][:, 2] = np.round(t['points'][:, 2] * 1000.0) * 0.001
+        tiles.append(t)
+    reader = ahn_utils.NPZReader(tmp_path, caching=True)
+    bld = bgt_utils.ArrayBGTReader({t['tilecode']: t['building_polygons'] for t in tiles})
+    procs = lambda: (AHNFuser(Labels.GROUND, reader, target='ground', epsilon=0.2, refine_ground=False),    # noqa: E731
+                     BGTBuildingFuser(Labels.BUILDING, bgt_reader=bld, offset=0, ahn_reader=reader),
+                     LayerLCC(Labels.BUILDING, reader, params=[{'bottom': 0., 'top': 12., 'grid_size': 0.1, 'threshold': 0.5}]))
+    want = []
+    for t in tiles:                                    # one tile at a time
+        lab = np.zeros(len(t['points']), dtype=np.uint16)
+        want.append(Pipeline(processors=procs(), ahn_reader=reader, caching=True).process_cloud(t['tilecode'], t['points'], lab))
+        assert np.count_nonzero(lab == Labels.GROUND) > 30_000
+    for rep in range(3):
+        batch = tiles * 2
+        got = Pipeline(processors=procs(), ahn_reader=reader, caching=True).process_clouds(
+            [t['tilecode'] for t in batch], [t['points'] for t in batch],
+            [np.zeros(len(t['points']), dtype=np.uint16) for t in batch], workers=4)
+        for k, lab in enumerate(got):
+            assert np.array_equal(lab, want[k % len(tiles)]), (rep, k)
+
+
 def test_layer_lcc_dense_matches_oracle():
     """A cloud dense enough for the layers to actually grow (the 60 k golden tile is sparse)."""
     tile = synthetic.make_tile(1500000, seed=31, facade_fraction=0.6)
@@ -621,6 +682,53 @@ def test_knn_normals_cov_match_oracle(cell):
     bad = np.abs(got_n - want_n).max(axis=1) > 1e-9
     assert bad.sum() == 0, f'{bad.sum()} normals differ by more than 1e-9'
     print(f'normals bit-identical: {np.mean((got_n == want_n).all(axis=1)):.4f}')
+    report_tie_exposure(coords)
+    check_normals_independently(coords, got_n, 0.2, 30)
+
+
+def report_tie_exposure(coords, k_row=15, k_nn=30):
+    """How exposed the fixture is to the one place where the restated neighbour order could differ from
+    nanoflann's: exact squared-distance ties.  A tie INSIDE a list only permutes two entries; a tie
+    ACROSS the cut (rank k | k + 1) changes which point is in the list."""
+    _, d2 = natives.knn(coords, k_nn + 1, want_d2=True)
+    cut_row = int((d2[:, k_row - 1] == d2[:, k_row]).sum())
+    cut_nn = int((d2[:, k_nn - 1] == d2[:, k_nn]).sum())
+    in_row = int((d2[:, 1:k_row] == d2[:, :k_row - 1]).any(axis=1).sum())
+    in_nn = int((d2[:, 1:k_nn] == d2[:, :k_nn - 1]).any(axis=1).sum())
+    print(f'exact d2 ties over {len(coords)} queries: across the cut at rank {k_row}: {cut_row}, at rank {k_nn}: {cut_nn}; '
+          f'inside the {k_row}-row: {in_row}, inside the {k_nn} nearest: {in_nn}')
+    return cut_row, cut_nn, in_row, in_nn
+
+
+def check_normals_independently(coords, normals, radius, max_nn, sample=60000, seed=5):
+    """The device normals against a formulation that shares NOTHING with upcp_math.cuh / upcp_oracle.c (both
+    transcribe Open3D's FastEigen3x3): scipy cKDTree neighbourhoods, two-pass (centred) covariance, LAPACK
+    eigh.  The eigenvector of the smallest eigenvalue is defined up to sign and as well as the eigenvalue gap
+    allows; the single-pass covariance of Open3D loses ~ |x|^2 eps of absolute accuracy (coordinates ~ 5e5)."""
+    from scipy.spatial import cKDTree
+    rng = np.random.default_rng(seed)
+    ids = rng.choice(len(coords), size=min(sample, len(coords)), replace=False)
+    tree = cKDTree(coords)
+    dist, nb = tree.query(coords[ids], k=max_nn, distance_upper_bound=np.nextafter(radius, 0.0))
+    checked = worst = 0
+    for row, (d, j) in enumerate(zip(dist, nb)):
+        j = j[np.isfinite(d)]
+        if len(j) < 3:
+            assert np.array_equal(normals[ids[row]], [0.0, 0.0, 1.0])
+            continue
+        q = coords[j] - coords[j].mean(axis=0)
+        w, v = np.linalg.eigh(q.T @ q / len(j))
+        gap = w[1] - w[0]
+        noise = 64 * np.finfo(float).eps * float((coords[j] ** 2).sum(axis=1).max())      # cancellation of E[xx] - E[x]E[x]
+        if gap < 1e4 * noise:
+            continue                                      # the direction is not determined to 1e-4 by the data
+        c = abs(float(v[:, 0] @ normals[ids[row]]))
+        worst = max(worst, 1.0 - c)
+        checked += 1
+        assert c > 1.0 - 1e-6, (row, c, gap, noise)
+    print(f'normals vs cKDTree + two-pass covariance + eigh: {checked} of {len(ids)} sampled points checked, '
+          f'worst 1 - |cos| = {worst:.2e}')
+    assert checked > 0.5 * len(ids)
 
 
 def test_knn_sorted_space_equals_compact_space():

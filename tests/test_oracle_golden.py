@@ -328,3 +328,27 @@ def test_parameter_variants_oracle_matches_reference_golden(golden):
         got = R.region_growing_labels(points, nocap.copy(), 10, exclude_labels=(9,), **kw)
         assert np.array_equal(got, g[f'region_growing_{k}']), kw
         assert (got != nocap).sum() > 500
+
+
+def test_config1_oracle_matches_reference_golden(golden):
+    """BASELINE config 1 at its full size (4 M points over the real demo AHN / BGT data): the oracle's
+    restatement against the labels the reference's own Pipeline + RegionGrowing classes produced."""
+    from conftest import CONFIG1_LAYERS, config1_cloud
+    from urban_pointcloud_processing_b200.utils import ahn_utils, bgt_utils
+    g = golden('config1_golden.npz')
+    points, _ = config1_cloud(g)
+    demo = os.path.join(GOLDEN, 'demo')
+    ahn_tile = ahn_utils.load_ahn_tile(os.path.join(demo, 'ahn_2386_9702.npz'))
+    bld = bgt_utils.BGTPolyReader(bgt_file=os.path.join(demo, 'bgt_buildings_demo.csv')).filter_tile(
+        '2386_9702', bgt_types=['pand'], merge=True)
+    road = bgt_utils.BGTPolyReader(bgt_file=os.path.join(demo, 'bgt_roads_demo.csv')).filter_tile(
+        '2386_9702', bgt_types=['rijbaan_lokale_weg', 'parkeervlak', 'fietspad'], merge=True)
+    o = np.zeros(len(points), dtype=np.uint16)
+    o = R.ahn_fuser_labels(points, o, o == 0, ahn_tile, 9, 'ground', 0.2)
+    o = R.road_fuser_labels(points, o, road, 1)
+    o = R.building_fuser_labels(points, o, o == 0, bld, 10, ahn_tile, 0.2)
+    o = R.layer_lcc_labels(points, o, o == 0, ahn_tile, 10, [dict(p) for p in CONFIG1_LAYERS])
+    assert np.array_equal(o, g['labels_pipeline'])
+    grown = R.region_growing_labels(points, o.copy(), 10, exclude_labels=(9,))
+    assert np.array_equal(grown, g['labels_region_growing'])
+    assert np.count_nonzero(grown == 10) > np.count_nonzero(o == 10) + 100_000

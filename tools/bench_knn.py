@@ -45,6 +45,8 @@ for var in variants:
             prof = _lib.prof_read()
             _lib.prof_enable(False)
         ms = {k.split(' ')[0]: v[0] for k, v in prof.items()}
-        print(f'cell {cell:.3f}: wall {dt * 1e3:7.2f} ms | S4 {ms["knn_stage"]:6.2f} = build {ms["knn_build"]:5.2f} + seg tiers '
-              f'{ms["knn_seg_kernel"]:6.2f} + per-query tier {ms["knn_select"]:5.2f} ms -> {m / ms["knn_stage"] / 1e3:7.1f} Mq/s')
+        cnt = dev.workspace(t.device).buf[:256].view(torch.int32)[:4].cpu().numpy()
+        print(f'   queries left for tier 2: {cnt[1]}, for the per-query tier: {cnt[2]}')
+        print(f'cell {cell:.3f}: wall {dt * 1e3:7.2f} ms | S4 {ms["knn_stage"]:6.2f} = build {ms["knn_build"]:5.2f} + search '
+              f'{ms["knn_search"]:6.2f} + epilogue {ms["knn_epilogue_kernel"]:5.2f} ms -> {m / ms["knn_stage"] / 1e3:7.1f} Mq/s')
 _lib.tuning_reset()

@@ -115,8 +115,8 @@ int upcp_prof_read(int slot, double* total_ms, int64_t* launches, int64_t* units
 const char* upcp_prof_slot_name(int slot) {
     static const char* names[UPCP_PROF_SLOTS] = {"raster_kernel", "pip_query_kernel", "radix_sort (hist+scan+scatter)",
                                                  "cc_link_kernel", "knn_stage (build+search+epilogue)", "grow_kernel",
-                                                 "knn_build", "knn_seg_kernel (tiers 1+2, fused epilogue)",
-                                                 "knn_select (per-query tier + epilogue)"};
+                                                 "knn_build", "knn_search (block tiers + per-query tier)",
+                                                 "knn_epilogue_kernel"};
     return (slot >= 0 && slot < UPCP_PROF_SLOTS) ? names[slot] : "";
 }
 

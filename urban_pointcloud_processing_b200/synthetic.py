@@ -196,6 +196,92 @@ def make_tile(n_points, seed=20240000, origin=TILE_ORIGIN, facade_fraction=0.33,
             'car_centres': car_c, 'car_dims': car_dim, 'pole_xy': pole_xy, 'pole_r': pole_r, 'pole_h': pole_h}
 
 
+def make_demo_cloud(n_points, ahn_tile, building_rings, seed=23869702, origin=TILE_ORIGIN):
+    """Config 1: a synthetic cloud over the REAL demo tile 2386_9702 -- the reference's demo
+    clouds are not part of its checkout, its AHN raster (NaN holes included) and BGT footprints are.
+    Ground follows the real AHN ground surface, facades stand on the real building rings and rise to
+    the real building surface, roofs lie on it; plus clutter, crowns and uniform noise.
+    ``ahn_tile``: dict x, y (descending), ground_surface, building_surface; ``building_rings``: list of
+    closed (V, 2) rings.  Returns (points (n, 3) float64 F-ordered on the LAS millimetre grid, kind uint8
+    0 ground, 1 facade, 2 roof, 3 clutter, 4 crown, 5 noise)."""
+    rng = np.random.Generator(np.random.Philox(seed))
+    ox, oy = origin
+    n = int(n_points)
+    frac = np.array([0.42, 0.30, 0.16, 0.05, 0.05, 0.02])
+    counts = np.floor(frac * n).astype(np.int64)
+    counts[0] += n - counts.sum()
+    gx0, gy0 = float(ahn_tile['x'][0]), float(ahn_tile['y'][0])
+    step = float(ahn_tile['x'][1] - ahn_tile['x'][0])
+    ground, building = ahn_tile['ground_surface'], ahn_tile['building_surface']
+    ny, nx = ground.shape
+
+    def cell(x, y):
+        ix = np.clip(np.floor((x - gx0) / step + 0.5).astype(np.int64), 0, nx - 1)
+        iy = np.clip(np.floor((gy0 - y) / step + 0.5).astype(np.int64), 0, ny - 1)
+        return iy, ix
+
+    def ground_at(x, y):
+        iy, ix = cell(x, y)
+        return np.nan_to_num(ground[iy, ix], nan=0.5)
+
+    xs, ys, zs, kinds = [], [], [], []
+    # ground
+    x = ox + rng.random(counts[0]) * TILE_SIZE; y = oy + rng.random(counts[0]) * TILE_SIZE
+    xs.append(x); ys.append(y); zs.append(ground_at(x, y) + rng.normal(0.0, 0.03, counts[0])); kinds.append(0)
+    # facades on the ring edges that lie inside the tile
+    seg = np.vstack([np.column_stack((r[:-1], r[1:])) for r in building_rings])
+    mid = 0.5 * (seg[:, :2] + seg[:, 2:])
+    keep = (mid[:, 0] > ox) & (mid[:, 0] < ox + TILE_SIZE) & (mid[:, 1] > oy) & (mid[:, 1] < oy + TILE_SIZE)
+    seg = seg[keep]
+    length = np.hypot(seg[:, 2] - seg[:, 0], seg[:, 3] - seg[:, 1])
+    sel = rng.choice(len(seg), size=counts[1], p=length / length.sum())
+    t = rng.random(counts[1])
+    fx = seg[sel, 0] + t * (seg[sel, 2] - seg[sel, 0]); fy = seg[sel, 1] + t * (seg[sel, 3] - seg[sel, 1])
+    nrm = np.column_stack((seg[sel, 3] - seg[sel, 1], -(seg[sel, 2] - seg[sel, 0]))) / length[sel, None]
+    # eaves height: the building surface a little to either side of the wall, 9 m where AHN has none
+    iy, ix = cell(fx + 0.3 * nrm[:, 0], fy + 0.3 * nrm[:, 1]); h1 = building[iy, ix]
+    iy, ix = cell(fx - 0.3 * nrm[:, 0], fy - 0.3 * nrm[:, 1]); h2 = building[iy, ix]
+    top = np.nan_to_num(np.fmax(h1, h2), nan=9.0)
+    base = ground_at(fx, fy)
+    perp = rng.normal(0.0, 0.012, counts[1])
+    xs.append(fx + perp * nrm[:, 0]); ys.append(fy + perp * nrm[:, 1])
+    zs.append(base + rng.random(counts[1]) * np.maximum(top - base, 2.5)); kinds.append(1)
+    # roofs: raster cells with a building surface
+    by, bx = np.nonzero(np.isfinite(building))
+    pick = rng.integers(0, len(by), counts[2])
+    rx = gx0 + (bx[pick] + rng.random(counts[2]) - 0.5) * step
+    ry = gy0 - (by[pick] + rng.random(counts[2]) - 0.5) * step
+    xs.append(rx); ys.append(ry); zs.append(building[by[pick], bx[pick]] + rng.normal(0.0, 0.03, counts[2])); kinds.append(2)
+    # clutter: blobs on the ground (cars, bins, ...)
+    n_blob = 60
+    bxy = np.column_stack((ox + rng.uniform(2, 48, n_blob), oy + rng.uniform(2, 48, n_blob)))
+    bsz = rng.uniform(0.3, 1.6, n_blob)
+    b = rng.integers(0, n_blob, counts[3])
+    cx_ = bxy[b, 0] + rng.uniform(-1, 1, counts[3]) * bsz[b]; cy_ = bxy[b, 1] + rng.uniform(-1, 1, counts[3]) * bsz[b]
+    xs.append(cx_); ys.append(cy_); zs.append(ground_at(cx_, cy_) + 0.1 + rng.random(counts[3]) * 1.4); kinds.append(3)
+    # crowns
+    n_crown = 20
+    cxy = np.column_stack((ox + rng.uniform(4, 46, n_crown), oy + rng.uniform(4, 46, n_crown)))
+    cr = rng.uniform(1.5, 3.0, n_crown); cz = rng.uniform(5.0, 9.0, n_crown)
+    k = rng.integers(0, n_crown, counts[4])
+    d = rng.normal(size=(counts[4], 3)); d /= np.linalg.norm(d, axis=1, keepdims=True)
+    rr = cr[k] * rng.random(counts[4]) ** (1.0 / 3.0)
+    xs.append(cxy[k, 0] + d[:, 0] * rr); ys.append(cxy[k, 1] + d[:, 1] * rr); zs.append(cz[k] + 0.8 * d[:, 2] * rr)
+    kinds.append(4)
+    # noise
+    xs.append(ox + rng.random(counts[5]) * TILE_SIZE); ys.append(oy + rng.random(counts[5]) * TILE_SIZE)
+    zs.append(rng.uniform(-2.0, 25.0, counts[5])); kinds.append(5)
+
+    x = np.clip(np.concatenate(xs), ox, ox + TILE_SIZE - 0.001)
+    y = np.clip(np.concatenate(ys), oy + 0.001, oy + TILE_SIZE)
+    z = np.concatenate(zs)
+    kind = np.concatenate([np.full(c, k_, np.uint8) for c, k_ in zip(counts, kinds)])
+    perm = rng.permutation(n)
+    points = np.empty((n, 3), dtype=np.float64, order='F')
+    points[:, 0] = _quantise(x[perm]); points[:, 1] = _quantise(y[perm]); points[:, 2] = _quantise(z[perm])
+    return points, kind[perm]
+
+
 def make_polygon_lattice(n_side=71, seed=5000, origin=TILE_ORIGIN, hole_fraction=0.1):
     """Config 4: jittered n_side x n_side lattice of star-shaped rings (circumradius
     0.25-0.45 m, 5-60 vertices), a fraction with one hole."""
