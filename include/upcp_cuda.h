@@ -394,6 +394,21 @@ int upcp_prism_clip(const double* d_x, const double* d_y, const double* d_z, int
                     const uint8_t* d_sel, const double* d_ring_xy, const int32_t* d_ring_off,
                     const double* d_zrange, int32_t n_prisms, uint8_t* d_out, void* stream);
 
+/* ------------------------------------------ synthetic tiles (measurement) ---- */
+/* synthetic urban tile i generated ON THE DEVICE from seed 20240000 + i (the
+ * reference ships no clouds and 512 x 20 M points cannot be fed from the host).  Scene model and value
+ * distributions of synthetic.make_tile: ground, facades (+ balconies), car shells, poles / crowns,
+ * clutter, uniform noise, millimetre grid; one counter-based Philox4x32-10 stream per point.  Used by
+ * bench.py and the full-size tests, not by the labelling path.
+ *   h_origin_size3 : tile origin x, y and edge length;  h_cum_kind6 : cumulative point fractions of the
+ *   six kinds (0 ground .. 5 noise);  d_walls8 [n][8] x0, y0, x1, y1, height, outward normal x, y,
+ *   cumulative area share;  d_cars4 centre x, y, size x, y;  d_poles4 x, y, radius, height;
+ *   d_crowns4 x, y, radius, centre z.  d_kind receives the kind of every point. */
+int upcp_synth_tile(int64_t n, uint64_t seed, const double* h_origin_size3, const double* h_cum_kind6,
+                    const double* d_walls8, int32_t n_walls, const double* d_cars4, int32_t n_cars,
+                    const double* d_poles4, int32_t n_poles, const double* d_crowns4, int32_t n_crowns,
+                    double* d_x, double* d_y, double* d_z, uint8_t* d_kind, void* stream);
+
 /* ------------------------------------------------ primitives (exposed) ---- */
 /* LSD radix sort of (key, value) pairs, the "Morton/voxel-key radix sort" of the
  * hot path; exposed for tests and benchmarks.  Sorts bits [0, end_bit).

@@ -683,7 +683,7 @@ def test_knn_normals_cov_match_oracle(cell):
     assert bad.sum() == 0, f'{bad.sum()} normals differ by more than 1e-9'
     print(f'normals bit-identical: {np.mean((got_n == want_n).all(axis=1)):.4f}')
     report_tie_exposure(coords)
-    check_normals_independently(coords, got_n, 0.2, 30)
+    check_normals_independently(t, d_sel, m, bbox_sel, coords, got_n, 0.2, 30, cell)
 
 
 def report_tie_exposure(coords, k_row=15, k_nn=30):
@@ -700,35 +700,42 @@ def report_tie_exposure(coords, k_row=15, k_nn=30):
     return cut_row, cut_nn, in_row, in_nn
 
 
-def check_normals_independently(coords, normals, radius, max_nn, sample=60000, seed=5):
-    """The device normals against a formulation that shares NOTHING with upcp_math.cuh / upcp_oracle.c (both
-    transcribe Open3D's FastEigen3x3): scipy cKDTree neighbourhoods, two-pass (centred) covariance, LAPACK
-    eigh.  The eigenvector of the smallest eigenvalue is defined up to sign and as well as the eigenvalue gap
-    allows; the single-pass covariance of Open3D loses ~ |x|^2 eps of absolute accuracy (coordinates ~ 5e5)."""
-    from scipy.spatial import cKDTree
-    rng = np.random.default_rng(seed)
-    ids = rng.choice(len(coords), size=min(sample, len(coords)), replace=False)
-    tree = cKDTree(coords)
-    dist, nb = tree.query(coords[ids], k=max_nn, distance_upper_bound=np.nextafter(radius, 0.0))
-    checked = worst = 0
-    for row, (d, j) in enumerate(zip(dist, nb)):
-        j = j[np.isfinite(d)]
-        if len(j) < 3:
-            assert np.array_equal(normals[ids[row]], [0.0, 0.0, 1.0])
-            continue
-        q = coords[j] - coords[j].mean(axis=0)
-        w, v = np.linalg.eigh(q.T @ q / len(j))
-        gap = w[1] - w[0]
-        noise = 64 * np.finfo(float).eps * float((coords[j] ** 2).sum(axis=1).max())      # cancellation of E[xx] - E[x]E[x]
-        if gap < 1e4 * noise:
-            continue                                      # the direction is not determined to 1e-4 by the data
-        c = abs(float(v[:, 0] @ normals[ids[row]]))
-        worst = max(worst, 1.0 - c)
-        checked += 1
-        assert c > 1.0 - 1e-6, (row, c, gap, noise)
-    print(f'normals vs cKDTree + two-pass covariance + eigh: {checked} of {len(ids)} sampled points checked, '
-          f'worst 1 - |cos| = {worst:.2e}')
-    assert checked > 0.5 * len(ids)
+def check_normals_independently(t, d_sel, m, bbox_sel, coords, normals, radius, max_nn, cell=None):
+    """The device normals against an eigen-solver that shares NOTHING with upcp_math.cuh / upcp_oracle.c (both
+    transcribe Open3D's analytic FastEigen3x3): LAPACK eigh on the SAME covariance.  The covariance is Open3D's
+    single-pass cumulant form over the hybrid-search neighbours in ascending order -- re-derived here with
+    numpy (cumsum adds sequentially, in neighbour order) from the device's own 30-neighbour rows, so the rows,
+    the hybrid cut and the summation are checked on the way.  (A two-pass covariance is NOT comparable: with
+    coordinates ~ 5e5 the single-pass form carries ~ eps |x|^2 ~ 5e-5 m^2 of rounding noise, part of what
+    the reference computes.)  The smallest eigenvector is defined up to sign and as well as the gap allows."""
+    d_knn, d_d2, d_nrm, _, _ = rgmod.knn_normals_device(t, d_sel, m, bbox_sel, max_nn, max_nn, radius, cell_size=cell,
+                                                       want_d2=True, want_cov=False, want_curv=False)
+    assert np.array_equal(d_nrm.cpu().numpy(), normals)                       # normals do not depend on knn
+    idx, d2 = d_knn.cpu().numpy().astype(np.int64), d_d2.cpu().numpy()
+    inside = (d2 < radius * radius) & (idx >= 0)
+    assert (np.diff(inside.astype(np.int8), axis=1) <= 0).all()               # ascending: the cut is a prefix
+    n = inside.sum(axis=1)
+    P = np.where(inside[:, :, None], coords[np.maximum(idx, 0)], 0.0)         # (m, max_nn, 3); zeros add nothing
+    s1 = np.cumsum(P, axis=1)[:, -1, :]
+    prod = np.stack([P[:, :, 0] * P[:, :, 0], P[:, :, 0] * P[:, :, 1], P[:, :, 0] * P[:, :, 2],
+                     P[:, :, 1] * P[:, :, 1], P[:, :, 1] * P[:, :, 2], P[:, :, 2] * P[:, :, 2]], axis=2)
+    s2 = np.cumsum(prod, axis=1)[:, -1, :]
+    ok = n >= 3
+    assert np.array_equal(normals[~ok], np.tile([0.0, 0.0, 1.0], ((~ok).sum(), 1)))
+    nn = n[ok].astype(np.float64)[:, None]
+    mean, sq = s1[ok] / nn, s2[ok] / nn
+    C = np.empty((ok.sum(), 3, 3))
+    C[:, 0, 0] = sq[:, 0] - mean[:, 0] * mean[:, 0]; C[:, 0, 1] = C[:, 1, 0] = sq[:, 1] - mean[:, 0] * mean[:, 1]
+    C[:, 0, 2] = C[:, 2, 0] = sq[:, 2] - mean[:, 0] * mean[:, 2]; C[:, 1, 1] = sq[:, 3] - mean[:, 1] * mean[:, 1]
+    C[:, 1, 2] = C[:, 2, 1] = sq[:, 4] - mean[:, 1] * mean[:, 2]; C[:, 2, 2] = sq[:, 5] - mean[:, 2] * mean[:, 2]
+    w, v = np.linalg.eigh(C)
+    scale = np.abs(w).max(axis=1)
+    well = (w[:, 1] - w[:, 0]) > 1e-6 * scale                                # direction determined to ~ 1e-9
+    cosv = np.abs(np.einsum('ij,ij->i', v[:, :, 0], normals[ok]))
+    worst = float((1.0 - cosv[well]).max())
+    print(f'normals vs LAPACK eigh on the re-derived single-pass covariance: {well.sum()} of {ok.sum()} points with a '
+          f'separated smallest eigenvalue, worst 1 - |cos| = {worst:.2e}; {(~well).sum()} near-degenerate skipped')
+    assert well.sum() > 0.9 * ok.sum() and worst < 1e-9
 
 
 def test_knn_sorted_space_equals_compact_space():
