@@ -1,41 +1,46 @@
 #!/usr/bin/env python
 """bench.py -- labelled Mpts/s of the per-tile label pipeline on B200.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--points P] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--points P] [--tiles T] [--workers W]
+                    [--config 1|2|3|4] [--impl reference]
 
-A step = one pass of the full label pipeline (AHN ground fusion, BGT road fusion, BGT
-building fusion + AHN cap, LayerLCC building, LabelConnectedComp cars, RegionGrowing
-building) over ONE synthetic 50 m urban tile of P (default 20 M) points.  With N > 1
-(launched by torchrun, one rank per GPU) every rank labels its own tile per step (weak
-scaling, no collective on the hot path); the per-tile label histograms are gathered with
-one NCCL all_gather after the timed steps.
+A step = one pass of the full label pipeline (AHN ground fusion, BGT road fusion, BGT building
+fusion + AHN cap, LayerLCC building, LabelConnectedComp cars, RegionGrowing building) over ONE
+synthetic 50 m urban tile of P (default 20 M) points.  The tiles of a run are DISTINCT (BASELINE.json
+config 5): tile i is generated on the device from seed 20240000 + i (upcp_synth_tile) on its own spot
+of a tile mosaic, so it has its own tile code, AHN raster and BGT query.  With N > 1 (torchrun, one
+rank per GPU) the batch is sharded tile-wise (weak scaling: K tiles per rank, no collective on the
+hot path); the per-tile label histograms are gathered with one NCCL all_gather after the timed steps
+(batch.run_batch).
 
-  value  device-resident throughput: tile coordinates already in HBM, labels reset on the
-         device, pipeline chained on the device, label histogram left on the device.  Two
-         regions of K steps each are timed: one tile at a time on one stream (`single_stream`;
-         the per-kernel cudaEvent brackets, hence `roofline`, are taken here) and `--workers`
-         tiles in flight, one CUDA stream + host thread each (`concurrent`,
-         Pipeline.process_tiles_device).  `value` / `ms_per_step` are those of the faster region
-         whose labels equal the single-stream ones; `config.tiles_in_flight_per_gpu` says which.
-  e2e    the same pipeline through the reference-facing plugin API
-         (Pipeline.process_cloud(tilecode, points, labels) with numpy arrays living in
-         PINNED host memory): H2D of the points + labels and D2H of the labels inside the
-         timed region.  Two public entry points are timed: `Pipeline.process_clouds` over the K
-         tiles of the run (the upload of tile i+1 rides a second stream while tile i computes;
-         reported as `e2e` when it is the faster one) and one `Pipeline.process_cloud` call per
-         tile, strictly serial (`e2e_process_cloud`).
-  roofline   for the kernel with the largest share of the step (cudaEvent brackets inside
-         the library); algorithmic bytes per point from SURVEY.md 8(d) / DESIGN.md.  The
-         `knn_search_kernel` bracket is the neighbour search proper: the two lane-per-query
-         block tiers plus the warp-per-query tier (and the coarse grid built for it).
-  cpu_baseline   the oracle port of the reference pipeline on the host cores, on a
-         full-density crop of the same tile (rank 0, N = 1 only).
+  value  device-resident throughput: the K tiles of the rank already in HBM, their labels reset
+         on the device.  Two regions of K steps each are timed: one tile at a time on one stream
+         (`single_stream`; the per-kernel cudaEvent brackets, hence `roofline`, are taken here) and
+         `--workers` tiles in flight, one CUDA stream + host thread each (`concurrent`:
+         batch.run_batch -> Pipeline.process_tiles_device, every worker on a DIFFERENT tile, the
+         readers' raster caches emptied first so that every tile pays its own raster uploads and
+         point-in-polygon plan inside the timed region).  `value` / `ms_per_step` are those of the
+         faster region whose labels equal the single-stream ones.
+  e2e    the same pipeline through the public host API with numpy arrays in PINNED host memory: H2D
+         of the points + labels and D2H of the labels inside the timed region.  `e2e` is
+         Pipeline.process_clouds over the K tiles (the in-memory form of the reference's batch entry
+         point Pipeline.process_folder), `e2e_process_cloud` is one strictly serial
+         Pipeline.process_cloud(tilecode, points, labels) call per tile -- the reference's own
+         per-tile signature.
+  roofline   for the bracket with the largest share of the step (cudaEvent brackets inside the
+         library); algorithmic bytes per point from SURVEY.md 8(d) / DESIGN.md.  The neighbour-search
+         bracket spans the WHOLE stage S4 it is charged for (grid build, all search tiers, epilogue).
+         `traffic` is only reported when profiles/r2_traffic.json was captured from these sources.
+  cpu_baseline   the oracle port of the reference pipeline on the host cores, on a full-density crop of
+         tile 0 (rank 0, N = 1 only), with its per-processor seconds.  (/root/reference does not travel
+         to the GPU box and its natives -- cccorelib, open3d, shapely -- are not installable: the port is
+         the only CPU arm possible there.)
 
---impl reference times the reference's CPU implementation of the same pipeline (the oracle
-port: reference control flow restated in numpy + plain-C/OpenMP natives; the reference's own
-natives -- cccorelib, open3d, shapely -- are not installable here) on the host cores.
+--config 1..4 print the per-configuration lines of BASELINE.md section 4 instead (one JSON line each).
+--impl reference times the oracle port on ALL host cores (rank 0 only under torchrun).
 """
 import argparse
+import hashlib
 import json
 import os
 import subprocess
@@ -58,16 +63,37 @@ WORKLOAD = ('synthetic 50 m urban tile, {n} points: AHNFuser(ground) + BGTRoadFu
             'hybrid r 0.2 / max_nn 30)')
 # algorithmic HBM bytes per point, SURVEY.md section 8(d)
 MAX_BATCH_BUFFERS = 64        # label buffers kept alive at once by the batch arms (80 MB on the device / 40 MB pinned each)
-B_ALG = {'raster_kernel': 27.0, 'pip_query_kernel': 19.0, 'radix_sort (hist+scan+scatter)': 96.0,
-         'cc_link_kernel': 8.0, 'knn_search_kernel': 140.0, 'grow_kernel': 421.0}
+# algorithmic HBM bytes per unit of every bracket.  Points for all but the sort, whose bracket counts
+# algorithmic BYTES itself (elements x passes x (3 key bytes + 8): 20 B per element and pass for the 4-byte
+# keys of level <= 10).  The neighbour-search stage S4 is ONE bracket of 140 B/pt; its three sub-brackets
+# (nested inside it) split that: build 24 + 16 + 16 (coordinates in, 32-byte + 16-byte sorted records out),
+# epilogue 60 + 24 (kNN row + normal out), the search itself reads the 16-byte records.
+B_ALG = {'raster_kernel': 27.0, 'pip_query_kernel': 19.0, 'radix_sort (hist+scan+scatter)': 1.0,
+         'cc_link_kernel': 8.0, 'knn_stage (build+search+epilogue)': 140.0, 'grow_kernel': 421.0,
+         'knn_build': 56.0, 'knn_search (block tiers + per-query tier)': 16.0, 'knn_epilogue_kernel': 84.0}
+NESTED = ('knn_build', 'knn_search (block tiers + per-query tier)', 'knn_epilogue_kernel')   # parts of the S4 bracket
+
+
+def sources_sha():
+    """Fingerprint of the CUDA sources: a committed ncu capture is only quoted when it was taken from them."""
+    h = hashlib.sha256()
+    d = os.path.join(ROOT, 'urban_pointcloud_processing_b200', 'csrc')
+    for f in sorted(os.listdir(d)):
+        if f.endswith(('.cu', '.cuh')):
+            h.update(f.encode()); h.update(open(os.path.join(d, f), 'rb').read())
+    return h.hexdigest()[:16]
 
 
 def measured_traffic(kernel):
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the bracketed kernel(s), from the
-    committed ncu --set full capture of this command (profiles/r1_traffic.json), or None."""
-    path = os.path.join(ROOT, 'profiles', 'r1_traffic.json')
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the bracketed kernel(s), from the committed
+    ncu --set full capture (profiles/r2_traffic.json, tools/capture_profiles.sh) -- or None when there is
+    none for the CUDA sources of this checkout (a stale capture is not quoted)."""
+    path = os.path.join(ROOT, 'profiles', 'r2_traffic.json')
     try:
-        return float(json.load(open(path))['bracket_traffic_bytes_per_launch'][kernel])
+        rec = json.load(open(path))
+        if rec.get('csrc_sha') != sources_sha():
+            return None
+        return float(rec['bracket_traffic_bytes_per_launch'][kernel])
     except Exception:
         return None
 
@@ -152,8 +178,10 @@ def make_processors(ahn, bld, road):
             RegionGrowing(Labels.BUILDING, exclude_labels=(Labels.GROUND, Labels.ROAD)))
 
 
-def oracle_pipeline(tile, points, labels):
-    """The same processor list through the oracle (reference control flow, restated natives)."""
+def oracle_pipeline(tile, points, labels, seconds=None):
+    """The same processor list through the oracle (reference control flow, restated natives).  With
+    ``seconds`` (a list) the wall time of every processor is appended, as the reference logs it
+    (pipeline.py:94-95)."""
     from oracle import reference_py as R
     a = tile['ahn_tile']
 
@@ -161,54 +189,74 @@ def oracle_pipeline(tile, points, labels):
         lm = R.lcc_get_label_mask(p, l, m, 40, **CAR)
         l[lm] = 40
         return l
-    return R.process_cloud([
-        lambda p, l, m: R.ahn_fuser_labels(p, l, m, a, 9, 'ground', 0.2),
-        lambda p, l, m: R.road_fuser_labels(p, l, tile['road_polygons'], 1),
-        lambda p, l, m: R.building_fuser_labels(p, l, m, tile['building_polygons'], 10, a, 0.2),
-        lambda p, l, m: R.layer_lcc_labels(p, l, m, a, 10, [dict(q) for q in LAYERS]),
-        car,
-        lambda p, l, m: R.region_growing_labels(p, l, 10, exclude_labels=(9, 1)),
-    ], points, labels)
+    stages = [
+        ('AHNFuser', lambda p, l, m: R.ahn_fuser_labels(p, l, m, a, 9, 'ground', 0.2)),
+        ('BGTRoadFuser', lambda p, l, m: R.road_fuser_labels(p, l, tile['road_polygons'], 1)),
+        ('BGTBuildingFuser', lambda p, l, m: R.building_fuser_labels(p, l, m, tile['building_polygons'], 10, a, 0.2)),
+        ('LayerLCC', lambda p, l, m: R.layer_lcc_labels(p, l, m, a, 10, [dict(q) for q in LAYERS])),
+        ('LabelConnectedComp', car),
+        ('RegionGrowing', lambda p, l, m: R.region_growing_labels(p, l, 10, exclude_labels=(9, 1))),
+    ]
+
+    def timed_stage(name, fn):
+        def run(p, l, m):
+            t0 = time.perf_counter()
+            out = fn(p, l, m)
+            if seconds is not None:
+                seconds.append((name, round(time.perf_counter() - t0, 3)))
+            return out
+        return run
+    return R.process_cloud([timed_stage(n_, f_) for n_, f_ in stages], points, labels)
 
 
-def initial_labels(tile, n):
+def seed_labels_host(kind, n):
     labels = np.zeros(n, dtype=np.uint16)
-    cars = np.where(tile['kind'] == 2)[0]
+    cars = np.where(kind == 2)[0]
     labels[cars[::100]] = 40            # 1 % of the car points pre-labelled as seeds (config 2)
     return labels
 
 
-def crop_sample(tile, labels0, target):
-    """Full-density spatial crop of about `target` points around the tile centre."""
-    pts = tile['points']
-    n = len(pts)
+def crop_sample(points, labels0, box0, origin, target):
+    """Full-density spatial crop of about `target` points, centred on a corner of the first building so that
+    facade, ground and street all occur."""
+    n = len(points)
     side = 50.0 * np.sqrt(min(1.0, target / n))
-    # centred on a corner of the first building so that facade, ground and street all occur
-    cx, cy = tile['boxes'][0][2], tile['boxes'][0][3]
-    cx = min(max(cx, tile['origin'][0] + side / 2), tile['origin'][0] + 50.0 - side / 2)
-    cy = min(max(cy, tile['origin'][1] + side / 2), tile['origin'][1] + 50.0 - side / 2)
-    keep = (np.abs(pts[:, 0] - cx) <= side / 2) & (np.abs(pts[:, 1] - cy) <= side / 2)
-    return np.asfortranarray(pts[keep]), labels0[keep].copy(), side
+    cx, cy = box0[2], box0[3]
+    cx = min(max(cx, origin[0] + side / 2), origin[0] + 50.0 - side / 2)
+    cy = min(max(cy, origin[1] + side / 2), origin[1] + 50.0 - side / 2)
+    keep = (np.abs(points[:, 0] - cx) <= side / 2) & (np.abs(points[:, 1] - cy) <= side / 2)
+    return np.asfortranarray(points[keep]), labels0[keep].copy(), side
+
+
+def host_threads():
+    """All the host cores for the CPU arm -- SET, not defaulted: torchrun exports OMP_NUM_THREADS=1."""
+    cores = os.cpu_count() or 1
+    os.environ['OMP_NUM_THREADS'] = str(cores)
+    os.environ['NUMBA_NUM_THREADS'] = str(cores)
+    return cores
 
 
 def run_reference(args, rank, world):
-    """--impl reference: the oracle port on the host cores (rank 0 only)."""
+    """--impl reference: the oracle port on ALL host cores (rank 0 only; the other ranks exit without work)."""
     if rank != 0:
         return
+    cores = host_threads()                       # before the OpenMP runtime of the oracle library starts
     from oracle import build as oracle_build
+    from oracle import natives
     from urban_pointcloud_processing_b200 import synthetic
     oracle_build.build()
-    cores = os.cpu_count() or 1
-    os.environ.setdefault('OMP_NUM_THREADS', str(cores))
+    threads = natives.set_num_threads(cores) if hasattr(natives, 'set_num_threads') else cores
     tile = synthetic.make_tile(args.points, seed=20240000)
-    labels0 = initial_labels(tile, args.points)
-    pts, lab, side = crop_sample(tile, labels0, args.ref_sample)
-    times = []
+    labels0 = seed_labels_host(tile['kind'], args.points)
+    pts, lab, side = crop_sample(tile['points'], labels0, tile['boxes'][0], tile['origin'], args.ref_sample)
+    times, per_proc = [], []
     for it in range(args.warmup + args.steps):
+        sec = []
         t0 = time.perf_counter()
-        oracle_pipeline(tile, pts, lab.copy())
+        oracle_pipeline(tile, pts, lab.copy(), sec)
         if it >= args.warmup:
             times.append(time.perf_counter() - t0)
+            per_proc = sec
     total = sum(times)
     value = len(pts) * len(times) / total / 1e6
     sample = f'{side:.1f} x {side:.1f} m full-density crop ({len(pts)} points) of the {args.points}-point tile per step'
@@ -216,10 +264,51 @@ def run_reference(args, rank, world):
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * total / len(times),
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
             'config': {'workload': WORKLOAD.format(n=args.points), 'sample': sample},
-            'cpu_baseline': {'value': value, 'unit': 'Mpts/s', 'cores': cores, 'kind': 'port', 'sample': sample},
+            'cpu_baseline': {'value': value, 'unit': 'Mpts/s', 'cores': cores, 'omp_threads': int(threads), 'kind': 'port',
+                             'sample': sample, 'per_processor_s': per_proc,
+                             'what': 'reference control flow restated in numpy + plain-C / OpenMP natives '
+                                     '(oracle/): /root/reference does not travel to the GPU box and its natives '
+                                     '(cccorelib, open3d, shapely) are not installable'},
             'e2e': {'value': value, 'unit': 'Mpts/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
             'gpu_launches': 0}
     print(json.dumps(line))
+
+
+class Batch:
+    """The K distinct device-resident tiles of this rank (tile index = rank + world * j) with their readers."""
+
+    def __init__(self, n, count, rank, world, device):
+        import torch
+        from urban_pointcloud_processing_b200 import synthetic
+        from urban_pointcloud_processing_b200.utils import ahn_utils, bgt_utils
+        self.n, self.count = n, count
+        self.index = [rank + world * j for j in range(count)]
+        self.tiles, self.codes, self.labels0, self.layouts = [], [], [], []
+        for g in self.index:
+            tile, kind, layout = synthetic.make_device_tile(n, seed=20240000 + g, origin=synthetic.tile_origin(g), device=device)
+            lab = torch.zeros(n, dtype=torch.int32, device=device)
+            cars = torch.nonzero(kind == 2).flatten()
+            lab[cars[::100]] = 40        # 1 % of the car points pre-labelled as seeds (config 2)
+            self.tiles.append(tile); self.codes.append(layout['tilecode']); self.labels0.append(lab)
+            self.layouts.append(layout)
+            del kind
+        self.ahn = ahn_utils.ArrayAHNReader({L['tilecode']: L['ahn_tile'] for L in self.layouts})
+        self.bld = bgt_utils.ArrayBGTReader({L['tilecode']: L['building_polygons'] for L in self.layouts})
+        self.road = bgt_utils.ArrayBGTReader({L['tilecode']: L['road_polygons'] for L in self.layouts})
+
+    def cold_caches(self):
+        """Forget the device rasters: the next pass over the batch uploads them again, tile by tile."""
+        with self.ahn._lock:
+            self.ahn._rasters.clear()
+
+    def host_points(self, j):
+        """(n, 3) float64 F-ordered numpy view of tile j in PINNED host memory."""
+        import torch
+        t = self.tiles[j]
+        pinned = torch.empty((3, self.n), dtype=torch.float64).pin_memory()
+        pinned[0].copy_(t.x); pinned[1].copy_(t.y); pinned[2].copy_(t.z)
+        torch.cuda.synchronize()
+        return pinned, pinned.numpy().T
 
 
 def main():
@@ -228,7 +317,10 @@ def main():
     ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--points', type=int, default=20_000_000)
+    ap.add_argument('--tiles', type=int, default=0,
+                    help='distinct device-resident tiles per rank (default: min(steps, 24)); steps cycle through them')
     ap.add_argument('--impl', default='b200')
+    ap.add_argument('--config', type=int, default=0, help='1..4: the per-configuration lines of BASELINE.md section 4')
     ap.add_argument('--ref-sample', type=int, default=1_000_000, dest='ref_sample')
     ap.add_argument('--cpu-sample', type=int, default=2_000_000, dest='cpu_sample')
     ap.add_argument('--no-cpu-baseline', action='store_true')
@@ -248,13 +340,16 @@ def main():
     if args.impl == 'reference':
         run_reference(args, rank, world)
         return
+    if args.config:
+        import bench_configs
+        bench_configs.run(args, rank, world)
+        return
 
     import torch
     import torch.distributed as dist
-    from urban_pointcloud_processing_b200 import _lib, batch, synthetic
+    from urban_pointcloud_processing_b200 import _lib, batch
     from urban_pointcloud_processing_b200 import device as dev
     from urban_pointcloud_processing_b200.pipeline import Pipeline
-    from urban_pointcloud_processing_b200.utils import ahn_utils, bgt_utils
 
     _lib.require_cuda()                      # no CPU fallback
     torch.cuda.set_device(local_rank)
@@ -263,59 +358,37 @@ def main():
         dist.init_process_group('nccl', device_id=device)
 
     warmup = max(args.warmup, args.min_warmup)             # timing rule: W >= 3
-    n = args.points
-    # every rank labels its own tile (seed 20240000 + rank); inputs (480 MB) >> 126 MB L2
-    tile = synthetic.make_tile(n, seed=20240000 + rank)
-    tc = tile['tilecode']
-    labels0 = initial_labels(tile, n)
-    ahn = ahn_utils.ArrayAHNReader({tc: tile['ahn_tile']})
-    bld = bgt_utils.ArrayBGTReader({tc: tile['building_polygons']})
-    road = bgt_utils.ArrayBGTReader({tc: tile['road_polygons']})
-    pipeline = Pipeline(processors=make_processors(ahn, bld, road), ahn_reader=ahn, caching=True)
-
-    # pinned host buffers for the e2e arm
-    pts_pinned = torch.empty((3, n), dtype=torch.float64).pin_memory()
-    pts_pinned.numpy()[...] = tile['points'].T
-    points_host = pts_pinned.numpy().T           # (n, 3) F-ordered view, as pipeline.py:124 delivers
-    lab_init_pinned = torch.from_numpy(labels0.view(np.int16)).pin_memory()
-    lab_work_pinned = torch.empty(n, dtype=torch.int16).pin_memory()
-    labels_host = lab_work_pinned.numpy().view(np.uint16)
-
-    # device-resident arm
-    d_tile = dev.DeviceTile(points_host, device)
-    d_labels0 = dev.upload_labels(labels0, device)
-    d_labels = torch.empty_like(d_labels0)
+    n, K = args.points, args.steps
+    T = args.tiles if args.tiles > 0 else min(K, 24)
+    # the rank's tiles, generated on the device (coordinates: 480 MB per tile >> 126 MB L2)
+    B = Batch(n, T, rank, world, device)
+    pipeline = Pipeline(processors=make_processors(B.ahn, B.bld, B.road), ahn_reader=B.ahn, caching=True)
+    d_labels = torch.empty_like(B.labels0[0])
     torch.cuda.synchronize()
 
-    def device_step():
-        d_labels.copy_(d_labels0)
-        pipeline.process_tile_device(tc, d_tile, d_labels)
+    def device_step(j):
+        j %= T
+        d_labels.copy_(B.labels0[j])
+        pipeline.process_tile_device(B.codes[j], B.tiles[j], d_labels)
         return dev.label_hist(d_labels)
-
-    def e2e_step():
-        dev.clear_tile_cache()
-        lab_work_pinned.copy_(lab_init_pinned)
-        pipeline.process_cloud(tc, points_host, labels_host)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps):
+    def timed(fn):
+        """fn() runs the K steps; device time by CUDA events on the current stream (the workers' streams join
+        it through events / synchronisation), wall clock beside it, MAX over ranks."""
         barrier()
         e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
         t0 = time.perf_counter()
         e0.record()
-        out = None
-        for _ in range(steps):
-            out = fn()
+        out = fn()
         e1.record()
         torch.cuda.synchronize()
         wall = time.perf_counter() - t0
-        ms = max(e0.elapsed_time(e1), 0.0)
-        ms = max(ms, 0.0)
-        t = torch.tensor([ms, wall * 1e3], dtype=torch.float64, device=device)
+        t = torch.tensor([max(e0.elapsed_time(e1), 0.0), wall * 1e3], dtype=torch.float64, device=device)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         barrier()
@@ -324,117 +397,147 @@ def main():
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    for _ in range(warmup):
-        hist = device_step()
+    for s in range(warmup):
+        device_step(s)
     torch.cuda.synchronize()
 
-    # ---- timed region: device-resident pipeline
+    # ---- timed region 1: one tile at a time on one stream (the per-kernel brackets live here)
     _lib.prof_enable(True)
     launches0 = _lib.launch_count()
     t_begin = time.perf_counter()
-    ms_dev, wall_dev, hist = timed(device_step, args.steps)
+    ms_dev, wall_dev, hist = timed(lambda: [device_step(s) for s in range(K)][-1])
     launches = _lib.launch_count() - launches0
     prof = _lib.prof_read()
     _lib.prof_enable(False)
+    single_labels = {}
+    for j in (0, (K - 1) % T):                # reference labels for the equality checks of the other arms
+        device_step(j)
+        single_labels[j] = d_labels.clone()
 
-    # ---- timed region 2: the same K device-resident tile passes, `workers` tiles in flight (one stream and
-    # host thread each, Pipeline.process_tiles_device).  No per-kernel brackets here: kernels of different
-    # tiles overlap, the roofline numbers come from the single-stream region above.
+    # ---- timed region 2: the same K tile passes through batch.run_batch -> Pipeline.process_tiles_device,
+    # `workers` DIFFERENT tiles in flight (one stream + host thread each), raster caches cold.  No per-kernel
+    # brackets here: kernels of different tiles overlap.
     conc = None
+    all_hist = None
     if args.workers > 1:
-        bufs = [torch.empty_like(d_labels0) for _ in range(min(args.steps, MAX_BATCH_BUFFERS))]
+        bufs = [torch.empty_like(B.labels0[0]) for _ in range(min(K, MAX_BATCH_BUFFERS))]
 
-        def concurrent_steps():
-            # K tile passes; label buffers are recycled every MAX_BATCH_BUFFERS tiles (bounded memory for large K)
-            h_ = None
-            for first in range(0, args.steps, len(bufs)):
-                part = bufs[:min(len(bufs), args.steps - first)]
-                for b_ in part:
-                    b_.copy_(d_labels0)
-                pipeline.process_tiles_device([tc] * len(part), [d_tile] * len(part), part, workers=args.workers)
-                h_ = [dev.label_hist(b_) for b_ in part][-1]
-            return h_
-        saved_steps, args.steps = args.steps, min(args.steps, 2 * args.workers)
-        concurrent_steps()                                   # warm-up: worker streams, their scratch buffers
-        args.steps = saved_steps
+        def label_tiles(global_ids):
+            # this rank's share of the batch: global tile id g = rank + world * s  ->  step s
+            steps = [(g - rank) // world for g in global_ids]
+            hists = []
+            for first in range(0, len(steps), len(bufs)):            # label buffers recycled beyond MAX_BATCH_BUFFERS
+                part = steps[first:first + len(bufs)]
+                for b_, s in zip(bufs, part):
+                    b_.copy_(B.labels0[s % T])
+                pipeline.process_tiles_device([B.codes[s % T] for s in part], [B.tiles[s % T] for s in part],
+                                              bufs[:len(part)], workers=args.workers)
+                hists += [dev.label_hist(b_) for b_ in bufs[:len(part)]]
+            return torch.stack(hists)
+
+        def batch_pass(k_steps, stop=None):
+            return batch.run_batch(world * k_steps, None, device, rank=rank, world_size=world,
+                                   process_tiles=label_tiles, on_processed=stop)[0]
+        batch_pass(min(K, 2 * args.workers))                         # warm-up: worker streams, their scratch buffers
+        B.cold_caches()
         launches1 = _lib.launch_count()
-        ms_c, wall_c, hist_c = timed(concurrent_steps, 1)
-        conc = {'ms_per_step': ms_c / args.steps, 'value': world * n * args.steps / (ms_c * 1e-3) / 1e6,
-                'launches': _lib.launch_count() - launches1, 'wall_ms_per_step': wall_c / args.steps,
-                'labels_equal_single_stream': bool(torch.equal(bufs[-1], d_labels) and torch.equal(bufs[0], d_labels))}
+        mark = {}
+
+        def stop_clock():                                            # end of the K steps: before the end-of-batch gather
+            mark['e'] = torch.cuda.Event(enable_timing=True); mark['e'].record(); mark['t'] = time.perf_counter()
+        barrier()
+        e0 = torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter(); e0.record()
+        all_hist = batch_pass(K, stop_clock)
+        torch.cuda.synchronize()
+        tt = torch.tensor([max(e0.elapsed_time(mark['e']), 0.0), (mark['t'] - t0) * 1e3], dtype=torch.float64, device=device)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        barrier()
+        ms_c, wall_c = max(float(tt[0]), float(tt[1])), float(tt[1])     # worker streams: the wall clock bounds the region
+        same = bool(torch.equal(bufs[0], single_labels[0]) if K <= len(bufs) else True) and \
+            bool(torch.equal(bufs[(K - 1) % len(bufs)], single_labels[(K - 1) % T]))
+        conc = {'ms_per_step': ms_c / K, 'value': world * n * K / (ms_c * 1e-3) / 1e6,
+                'launches': _lib.launch_count() - launches1, 'wall_ms_per_step': wall_c / K,
+                'labels_equal_single_stream': same,
+                'what': f'batch.run_batch -> Pipeline.process_tiles_device, {args.workers} different tiles in flight, '
+                        'raster caches cold (every tile uploads its rasters and builds its point-in-polygon plans)'}
         del bufs
     t_end = time.perf_counter()
     if rank == 0:
         sampler.window(t_begin, t_end)
     clocks = sampler.stop() if rank == 0 else None
-    stage_s = []
-    pipeline.process_tile_device(tc, d_tile, d_labels.copy_(d_labels0), sync_timings=True)
+    d_labels.copy_(B.labels0[0])
+    pipeline.process_tile_device(B.codes[0], B.tiles[0], d_labels, sync_timings=True)
     stage_s = [(name, round(sec * 1e3, 3)) for name, sec in pipeline.last_timings]
 
     # ---- end-of-batch gather of the label statistics (the only collective)
-    all_hist = batch.gather_histograms([rank], hist.view(1, -1), world, device)
-    labelled = int(all_hist[:, 1:].sum().item())
+    if all_hist is None:
+        all_hist = batch.gather_histograms([rank], hist.view(1, -1), world, device)
+    labelled = int(all_hist[-world:, 1:].sum().item())
 
-    # ---- e2e arm
-    e2e = None
+    # ---- e2e arms: host buffers (pinned), H2D + D2H inside the timed region
+    e2e = e2e_batch = e2e_las = None
     if not args.no_e2e:
-        for _ in range(2):
-            e2e_step()
-        ms_e2e, wall_e2e, _ = timed(e2e_step, args.steps)
-        e2e_ms = max(ms_e2e, wall_e2e)          # host-side work is part of the call: take the wall clock
-        e2e = {'value': world * n * args.steps / (e2e_ms * 1e-3) / 1e6, 'unit': 'Mpts/s',
-               'ms_per_step': e2e_ms / args.steps,
+        Th = min(T, 4)                                    # distinct host tiles (0.5 GB of pinned memory each)
+        host = [B.host_points(j) for j in range(Th)]
+        lab_init = [torch.from_numpy(B.labels0[j].cpu().numpy().astype(np.int16)).pin_memory() for j in range(Th)]
+        lab_work = torch.empty(n, dtype=torch.int16).pin_memory()
+        labels_host = lab_work.numpy().view(np.uint16)
+
+        def e2e_step(s):
+            j = s % Th
+            lab_work.copy_(lab_init[j])
+            pipeline.process_cloud(B.codes[j], host[j][1], labels_host)
+        for s in range(2):
+            e2e_step(s)
+        ms_e, wall_e, _ = timed(lambda: [e2e_step(s) for s in range(K)])
+        e_ms = max(ms_e, wall_e)                          # host-side work is part of the call: take the wall clock
+        e2e = {'value': world * n * K / (e_ms * 1e-3) / 1e6, 'unit': 'Mpts/s', 'ms_per_step': e_ms / K,
                'h2d_bytes_per_step': int(n * 24 + n * 2), 'd2h_bytes_per_step': int(n * 2),
-               'api': 'Pipeline.process_cloud(tilecode, points, labels) with numpy arrays in pinned host memory'}
-        # the e2e labels equal the device-resident ones
-        same = bool(np.array_equal(labels_host.astype(np.int32), d_labels.cpu().numpy()))
-        e2e['labels_equal_device_arm'] = same
+               'api': 'Pipeline.process_cloud(tilecode, points, labels), one call per tile, numpy arrays in pinned host memory',
+               'labels_equal_device_arm': bool(np.array_equal(labels_host.astype(np.int32),
+                                                              single_labels[(K - 1) % Th].cpu().numpy()))
+               if (K - 1) % Th in single_labels else None}
 
-    # ---- e2e, batch form: Pipeline.process_clouds over `steps` tiles in pinned host memory -- the upload of
-    # tile i+1 rides a second stream while the kernels of tile i run; every tile's H2D and D2H is inside
-    # the timed region
-    e2e_batch = None
-    if not args.no_e2e:
-        lab_bufs = [torch.empty(n, dtype=torch.int16).pin_memory() for _ in range(min(args.steps, MAX_BATCH_BUFFERS))]
+        lab_bufs = [torch.empty(n, dtype=torch.int16).pin_memory() for _ in range(min(K, MAX_BATCH_BUFFERS))]
 
-        def reset_labels():
-            for b_ in lab_bufs:
-                b_.copy_(lab_init_pinned)
+        def reset_labels(first=0):
+            for i_, b_ in enumerate(lab_bufs):
+                b_.copy_(lab_init[(first + i_) % Th])
 
         def batch_call():
             # K tiles; beyond MAX_BATCH_BUFFERS the pinned label buffers are reset and recycled inside the timed region
-            for first in range(0, args.steps, len(lab_bufs)):
-                k_ = min(len(lab_bufs), args.steps - first)
+            for first in range(0, K, len(lab_bufs)):
+                k_ = min(len(lab_bufs), K - first)
                 if first:
-                    reset_labels()
-                pipeline.process_clouds([tc] * k_, [points_host] * k_, [b_.numpy().view(np.uint16) for b_ in lab_bufs[:k_]],
-                                        workers=args.workers)
+                    reset_labels(first)
+                pipeline.process_clouds([B.codes[(first + i_) % Th] for i_ in range(k_)],
+                                        [host[(first + i_) % Th][1] for i_ in range(k_)],
+                                        [b_.numpy().view(np.uint16) for b_ in lab_bufs[:k_]], workers=args.workers)
         reset_labels()
         k_w = min(len(lab_bufs), 2 * max(args.workers, 1))
-        pipeline.process_clouds([tc] * k_w, [points_host] * k_w, [b_.numpy().view(np.uint16) for b_ in lab_bufs[:k_w]],
-                                workers=args.workers)
+        pipeline.process_clouds([B.codes[i_ % Th] for i_ in range(k_w)], [host[i_ % Th][1] for i_ in range(k_w)],
+                                [b_.numpy().view(np.uint16) for b_ in lab_bufs[:k_w]], workers=args.workers)
         reset_labels()
-        ms_b, wall_b, _ = timed(batch_call, 1)
+        B.cold_caches()
+        ms_b, wall_b, _ = timed(batch_call)
         b_ms = max(ms_b, wall_b)
-        e2e_batch = {'value': world * n * args.steps / (b_ms * 1e-3) / 1e6, 'unit': 'Mpts/s',
-                     'ms_per_step': b_ms / args.steps,
+        e2e_batch = {'value': world * n * K / (b_ms * 1e-3) / 1e6, 'unit': 'Mpts/s', 'ms_per_step': b_ms / K,
                      'h2d_bytes_per_step': int(n * 24 + n * 2), 'd2h_bytes_per_step': int(n * 2),
-                     'api': f'Pipeline.process_clouds(tilecodes, clouds, labels_list, workers={args.workers}) over {args.steps} '
-                            'tiles, numpy arrays in pinned host memory; each worker (host thread + CUDA stream) uploads, '
-                            'labels and downloads one tile at a time, so copies and latency-bound phases of one tile '
-                            'overlap the kernels of the others',
-                     'labels_equal_device_arm': bool(all(
-                         np.array_equal(b_.numpy().view(np.uint16).astype(np.int32), d_labels.cpu().numpy())
-                         for b_ in (lab_bufs[0], lab_bufs[-1])))}
+                     'api': f'Pipeline.process_clouds(tilecodes, clouds, labels_list, workers={args.workers}) over {K} tiles '
+                            f'({Th} distinct clouds in pinned host memory): the in-memory form of the reference\'s batch entry '
+                            'point Pipeline.process_folder; each worker (host thread + CUDA stream) uploads, labels and '
+                            'downloads one tile at a time',
+                     'labels_equal_device_arm': bool(np.array_equal(lab_bufs[0].numpy().view(np.uint16).astype(np.int32),
+                                                                    single_labels[0].cpu().numpy())) if K <= len(lab_bufs) else None}
         del lab_bufs
 
-    # ---- supplementary: the LAS-file route (Pipeline.process_file without the disk): raw int32 X, Y, Z
-    # in pinned host memory -> device (12 B/pt), coordinates scaled on the device, labels back
-    e2e_las = None
-    if not args.no_e2e:
+        # supplementary: the LAS-file route (Pipeline.process_file without the disk): raw int32 X, Y, Z in pinned
+        # host memory -> device (12 B/pt), coordinates scaled on the device, labels back
         from urban_pointcloud_processing_b200.utils import las_io
         scales, offsets = np.array([0.001, 0.001, 0.001]), np.array([100000.0, 400000.0, 0.0])
-        ints = np.rint((tile['points'] - offsets) / scales).astype(np.int32)
+        ints = np.rint((host[0][1] - offsets) / scales).astype(np.int32)
         pinned_ints = [torch.from_numpy(np.ascontiguousarray(ints[:, k])).pin_memory() for k in range(3)]
 
         class _Las:                                   # the attributes DeviceTile.from_las reads
@@ -447,14 +550,14 @@ def main():
             lab_u8.zero_()
             t_las = dev.DeviceTile.from_las(_Las, device)
             dl = dev.upload_labels(lab_u8.numpy(), device)
-            pipeline.process_tile_device(tc, t_las, dl)
+            pipeline.process_tile_device(B.codes[0], t_las, dl)
             dev.download_labels(dl, lab_u8.numpy())
         for _ in range(2):
             las_step()
-        ms_las, wall_las, _ = timed(las_step, args.steps)
+        ms_las, wall_las, _ = timed(lambda: [las_step() for _ in range(K)])
         las_ms = max(ms_las, wall_las)
-        e2e_las = {'value': world * n * args.steps / (las_ms * 1e-3) / 1e6, 'unit': 'Mpts/s',
-                   'ms_per_step': las_ms / args.steps, 'h2d_bytes_per_step': int(n * 12 + n), 'd2h_bytes_per_step': int(n),
+        e2e_las = {'value': world * n * K / (las_ms * 1e-3) / 1e6, 'unit': 'Mpts/s', 'ms_per_step': las_ms / K,
+                   'h2d_bytes_per_step': int(n * 12 + n), 'd2h_bytes_per_step': int(n),
                    'api': 'DeviceTile.from_las (int32 X, Y, Z + scale / offset, as Pipeline.process_file uploads them) + '
                           'process_tile_device + label download; no initial car seeds (labels start at 0)'}
 
@@ -463,57 +566,72 @@ def main():
             dist.destroy_process_group()
         return
 
-    step_ms = max(ms_dev, 0.0) / args.steps
-    value = world * n * args.steps / (ms_dev * 1e-3) / 1e6
+    step_ms = max(ms_dev, 0.0) / K
+    value = world * n * K / (ms_dev * 1e-3) / 1e6
     single = {'value': value, 'ms_per_step': step_ms, 'gpu_launches': int(launches),
-              'what': 'one tile at a time on one stream (the region the roofline brackets were taken in)'}
+              'what': 'one tile at a time on one stream, warm raster caches (the region the roofline brackets were taken in)'}
     tiles_in_flight = 1
     if conc and conc['value'] > value and conc['labels_equal_single_stream']:
         value, step_ms, launches, tiles_in_flight = conc['value'], conc['ms_per_step'], conc['launches'], args.workers
-        wall_dev = conc['wall_ms_per_step'] * args.steps
+        wall_dev = conc['wall_ms_per_step'] * K
     peak, peak_src = peaks()
-    # dominant kernel = largest bracketed share of the step
-    top = max(prof.items(), key=lambda kv: kv[1][0])
-    name, (tot_ms, cnt, units) = top
+    # dominant bracket = largest share of the step (the sub-brackets of S4 are parts of its bracket)
+    name, (tot_ms, cnt, units) = max(((k, v) for k, v in prof.items() if k not in NESTED), key=lambda kv: kv[1][0])
     per_launch_ms = tot_ms / max(cnt, 1)
     units_per_launch = units / max(cnt, 1)
     alg_bytes = B_ALG[name] * units_per_launch
     achieved = alg_bytes / (per_launch_ms * 1e-3) / 1e9 if per_launch_ms > 0 else 0.0
+    traffic = measured_traffic(name)
     roofline = {'bound': 'hbm', 'kernel': name, 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
-                'frac': achieved / peak, 'traffic': measured_traffic(name), 'traffic_unit': 'bytes per launch (ncu dram read + write, profiles/r1_traffic.json)',
+                'frac': achieved / peak, 'traffic': traffic,
+                'traffic_unit': 'bytes per launch (ncu dram read + write, profiles/r2_traffic.json)' if traffic is not None
+                else 'null: no ncu capture of these CUDA sources is committed (profiles/r2_traffic.json csrc_sha mismatch)',
                 'algorithmic_bytes_per_launch': alg_bytes, 'peak_source': peak_src,
-                'algorithmic_bytes_per_point': B_ALG[name], 'points_per_launch': units_per_launch,
+                'algorithmic_bytes_per_unit': B_ALG[name], 'units_per_launch': units_per_launch,
                 'launch_ms': per_launch_ms, 'share_of_step': tot_ms / max(ms_dev, 1e-9),
                 'region': 'single-stream timed region (K steps, one tile at a time); `value` may come from the region with several tiles in flight',
-                'kernels_ms_per_step': {k: round(v[0] / args.steps, 3) for k, v in prof.items()},
-                # algorithmic GB/s of every bracketed kernel (B_ALG x units / bracketed time), fraction of the peak
+                'kernels_ms_per_step': {k: round(v[0] / K, 3) for k, v in prof.items()},
+                # algorithmic GB/s of every bracket (B_ALG x units / bracketed time), fraction of the peak
                 'kernels_algorithmic_gbs': {k: [round(B_ALG[k] * v[2] / (v[0] * 1e-3) / 1e9, 1),
                                                 round(B_ALG[k] * v[2] / (v[0] * 1e-3) / 1e9 / peak, 4)]
-                                            for k, v in prof.items() if v[0] > 0}}
+                                            for k, v in prof.items() if v[0] > 0},
+                'csrc_sha': sources_sha()}
 
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
-        cores = os.cpu_count() or 1
-        pts_c, lab_c, side = crop_sample(tile, labels0, args.cpu_sample)
+        cores = host_threads()
+        from oracle import natives
+        threads = natives.set_num_threads(cores) if hasattr(natives, 'set_num_threads') else cores
+        t0_ = B.tiles[0]
+        pts0 = np.asfortranarray(np.column_stack((t0_.x.cpu().numpy(), t0_.y.cpu().numpy(), t0_.z.cpu().numpy())))
+        lab0 = B.labels0[0].cpu().numpy().astype(np.uint16)
+        L0 = B.layouts[0]
+        pts_c, lab_c, side = crop_sample(pts0, lab0, L0['boxes'][0], L0['origin'], args.cpu_sample)
+        sec = []
         t0 = time.perf_counter()
-        oracle_pipeline(tile, pts_c, lab_c)
+        oracle_pipeline(L0, pts_c, lab_c, sec)
         dt = time.perf_counter() - t0
-        cpu_baseline = {'value': len(pts_c) / dt / 1e6, 'unit': 'Mpts/s', 'cores': cores, 'kind': 'port',
-                        'sample': f'{side:.1f} x {side:.1f} m full-density crop ({len(pts_c)} points) of the same tile, '
-                                  f'one pass of the oracle port ({dt:.1f} s)'}
+        cpu_baseline = {'value': len(pts_c) / dt / 1e6, 'unit': 'Mpts/s', 'cores': cores, 'omp_threads': int(threads),
+                        'kind': 'port', 'per_processor_s': sec,
+                        'sample': f'{side:.1f} x {side:.1f} m full-density crop ({len(pts_c)} points) of tile 0, '
+                                  f'one pass of the oracle port ({dt:.1f} s)',
+                        'what': 'reference control flow restated in numpy + plain-C / OpenMP natives (oracle/): the only '
+                                'CPU arm possible on the GPU box (/root/reference does not travel; cccorelib, open3d, '
+                                'shapely are not installable)'}
 
-    # headline e2e: the batch call when it is the faster of the two public entry points
-    e2e_head = e2e_batch if (e2e_batch and e2e and e2e_batch['value'] >= e2e['value']) else e2e
-    line = {'metric': METRIC, 'value': value, 'unit': 'Mpts/s', 'n_gpus': world, 'steps': args.steps,
+    line = {'metric': METRIC, 'value': value, 'unit': 'Mpts/s', 'n_gpus': world, 'steps': K,
             'warmup': warmup, 'ms_per_step': step_ms, 'higher_is_better': True, 'scaling': 'weak',
             'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
             'config': {'workload': WORKLOAD.format(n=n), 'tiles_per_step': world, 'points_per_tile': n,
-                       'l2_policy': 'inputs (480 MB of coordinates per tile) are larger than the 126 MB L2',
+                       'distinct_tiles_per_gpu': T, 'tile_source': 'generated on the device from seed 20240000 + tile index '
+                       '(upcp_synth_tile), each on its own tile code / AHN raster / BGT polygons',
+                       'l2_policy': 'inputs (480 MB of coordinates per tile, a different tile every step) are larger than the 126 MB L2',
                        'tiles_per_s': value * 1e6 / n, 'tiles_in_flight_per_gpu': tiles_in_flight},
             'single_stream': single, 'concurrent': conc,
-            'clocks': clocks, 'e2e': e2e_head, 'e2e_process_cloud': e2e, 'e2e_las': e2e_las, 'gpu_launches': int(launches), 'roofline': roofline,
+            'clocks': clocks, 'e2e': e2e_batch or e2e, 'e2e_process_cloud': e2e, 'e2e_las': e2e_las,
+            'gpu_launches': int(launches), 'roofline': roofline,
             'cpu_baseline': cpu_baseline, 'stage_ms': stage_s, 'points_labelled_last_step': labelled,
-            'wall_ms_per_step': wall_dev / args.steps}
+            'wall_ms_per_step': wall_dev / K}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

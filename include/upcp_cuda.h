@@ -52,8 +52,9 @@ int64_t     upcp_launch_count(void);
 /* Per-kernel device timing for bench.py: when enabled, the dominant kernels are bracketed
  * with cudaEvents on their launching stream.  upcp_prof_read() synchronises the device,
  * adds up the elapsed time of all completed brackets of `slot` since the last reset and
- * returns the number of launches.  Slots: 0 raster, 1 pip, 2 radix sort (all passes of one
- * sort), 3 cc link (union-find), 4 neighbour search + normals (the WHOLE stage S4),
+ * returns the number of launches and the units processed (points; for the sort: algorithmic
+ * bytes = elements x passes x (3 key bytes + 8)).  Slots: 0 raster, 1 pip, 2 radix sort (all passes
+ * of one sort), 3 cc link (union-find), 4 neighbour search + normals (the WHOLE stage S4),
  * 5 region grow (persistent kernel). */
 #define UPCP_PROF_RASTER 0
 #define UPCP_PROF_PIP    1

@@ -28,6 +28,9 @@
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 
 /* ------------------------------------------------------------------ PIP ------ */
 /* clip_utils._point_inside_poly, literal (clip_utils.py:119-164). */
@@ -534,4 +537,17 @@ int64_t orc_region_grow(const int32_t* knn, int k, const double* normals, const 
     }
     free(list); free(processed);
     return n_list;
+}
+
+
+/* Host threads of the OpenMP loops above (bench.py: torchrun exports OMP_NUM_THREADS=1, the CPU arm wants
+ * all cores).  Returns the number of threads in force. */
+int orc_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+    return omp_get_max_threads();
+#else
+    (void)n;
+    return 1;
+#endif
 }

@@ -24,6 +24,12 @@ def _p(a):
     return a.ctypes.data_as(c_void_p)
 
 
+def set_num_threads(n):
+    """OpenMP threads of the natives (returns the number in force)."""
+    lib().orc_set_num_threads.restype = c_int
+    return int(lib().orc_set_num_threads(c_int(int(n))))
+
+
 def is_inside(x, y, polygon):
     """numba clip_utils.is_inside (clip_utils.py:167-190)."""
     x = np.ascontiguousarray(x, dtype=np.float64)

@@ -57,9 +57,21 @@ def test_tile_upload_layouts_and_bbox():
     ball, bsel, m = t.bbox(dev.upload_mask(sel, t.n, t.device))
     assert np.array_equal(ball, np.concatenate([pts_c.min(0), pts_c.max(0)]))
     assert np.array_equal(bsel, np.concatenate([pts_c[sel].min(0), pts_c[sel].max(0)])) and m == sel.sum()
-    # tile cache: same live array -> same HBM copy; different array -> new upload
-    a = dev.get_tile(pts_c)
-    assert dev.get_tile(pts_c) is a and dev.get_tile(pts_c.copy()) is not a
+    # tile cache: only READ-ONLY arrays keep their HBM copy (same live array -> same copy); a writable array is
+    # uploaded on every call, so an in-place edit between two calls is always seen (ADVICE r1 / VERDICT r1 #5)
+    assert dev.get_tile(pts_c) is not dev.get_tile(pts_c)
+    frozen = pts_c.copy(); frozen.flags.writeable = False
+    a = dev.get_tile(frozen)
+    assert dev.get_tile(frozen) is a and dev.get_tile(frozen.copy()) is not a and dev.get_tile(a) is a
+    staging = pts_c.copy()
+    ground = ahn_utils.ArrayAHNReader({'x': {'x': np.array([0.0, 1e6]), 'y': np.array([1e6, 0.0]),
+                                             'ground_surface': np.zeros((2, 2)), 'building_surface': np.zeros((2, 2))}})
+    fuser = AHNFuser(Labels.GROUND, ground, target='ground', epsilon=0.5, refine_ground=False)
+    staging[:, 2] = 0.0
+    first = fuser.get_label_mask(staging, np.zeros(len(staging), dtype=np.uint16), None, 'x')
+    staging[:, 2] = 10.0                       # refilled in place: same array object, same sampled rows elsewhere
+    second = fuser.get_label_mask(staging, np.zeros(len(staging), dtype=np.uint16), None, 'x')
+    assert first.all() and not second.any()
 
 
 def test_mask_and_label_kernels():

@@ -49,17 +49,27 @@ def gather_histograms(local_ids, local_hists, n_tiles, device=None):
     return out
 
 
-def run_batch(n_tiles, process_tile, device, rank=None, world_size=None):
+def run_batch(n_tiles, process_tile, device, rank=None, world_size=None, process_tiles=None, on_processed=None):
     """Process this rank's share of ``n_tiles`` tiles and gather the label statistics.
 
     process_tile(tile_index) -> int64 tensor [256] on ``device`` (label histogram of the
-    labelled tile).  Returns (hist [n_tiles, 256], local tile ids).
+    labelled tile), one tile after the other; or
+    process_tiles(list of tile indices) -> int64 tensor [len, 256]: the whole share at once, which
+    lets the caller keep several tiles in flight (``Pipeline.process_tiles_device(..., workers=W)``).
+    ``on_processed()`` is called between the labelling and the gather (bench.py stops its clock there:
+    the gather is the end-of-batch exchange, not part of a step).
+    Returns (hist [n_tiles, 256], local tile ids).
     """
     if rank is None:
         rank = dist.get_rank() if dist.is_available() and dist.is_initialized() else 0
     if world_size is None:
         world_size = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
     ids = shard_tiles(n_tiles, rank, world_size)
-    hists = [process_tile(i) for i in ids]
-    local = torch.stack(hists) if hists else torch.zeros((0, 256), dtype=torch.int64, device=device)
+    if process_tiles is not None:
+        local = process_tiles(ids) if ids else torch.zeros((0, 256), dtype=torch.int64, device=device)
+    else:
+        hists = [process_tile(i) for i in ids]
+        local = torch.stack(hists) if hists else torch.zeros((0, 256), dtype=torch.int64, device=device)
+    if on_processed is not None:
+        on_processed()
     return gather_histograms(ids, local, n_tiles, device), ids

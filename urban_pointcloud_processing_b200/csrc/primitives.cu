@@ -303,7 +303,10 @@ static int radix_sort_impl(K* keys_a, uint32_t* vals_a, K* keys_b, uint32_t* val
         uint32_t* tv = vin; vin = vout; vout = tv;
         in_b = !in_b;
     }
-    prof_end(UPCP_PROF_SORT, st, n);
+    // units of this bracket = algorithmic BYTES of the sort: per pass the histogram reads the keys, the
+    // scatter reads keys + payload and writes them: (3 sizeof(K) + 8) bytes per element and pass
+    const int passes = (end_bit + kRsBits - 1) / kRsBits;
+    prof_end(UPCP_PROF_SORT, st, n * (int64_t)passes * (int64_t)(3 * sizeof(K) + 8));
     *result_in_b = in_b;
     return UPCP_OK;
 }

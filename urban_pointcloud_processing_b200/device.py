@@ -296,38 +296,32 @@ class DeviceTile:
         return self._bbox_all
 
 
-# Cache of the most recent tiles keyed on the identity of the host array, so that a
-# sequence of get_labels(points, ...) calls on the same cloud uploads it once.
+# HBM copies are re-used only where the host array cannot have changed behind our back: READ-ONLY numpy
+# arrays (``points.flags.writeable == False``), keyed on the identity of the live array.  A writable array
+# -- a staging buffer that is refilled in place, a cloud the caller jitters between two calls -- is uploaded
+# on every call, exactly as the reference reads the live array on every call.  Callers that want to keep a
+# writable cloud resident pass the ``DeviceTile`` itself wherever ``points`` is expected.
 _TILE_CACHE = []
 _TILE_CACHE_SIZE = 2
 
 
-def _fingerprint(pts):
-    n = pts.shape[0]
-    if n == 0:
-        return ()
-    idx = np.linspace(0, n - 1, num=min(n, 61)).astype(np.int64)
-    return tuple(pts[idx].ravel().tolist())
-
-
 def get_tile(points, device=None):
-    """DeviceTile for a host array, re-using the HBM copy of the same live array."""
+    """DeviceTile for ``points`` (a DeviceTile is returned as it is)."""
     if isinstance(points, DeviceTile):
         return points
     device = device if device is not None else current_device()
     pts = np.asarray(points)
-    fp = None
-    for ref, dev, stored_fp, tile in _TILE_CACHE:
-        if ref() is pts and dev == device:
-            fp = _fingerprint(pts)
-            if fp == stored_fp:
-                return tile
+    if pts.flags.writeable:
+        return DeviceTile(pts, device)
+    for ref, dev_, tile in _TILE_CACHE:
+        if ref() is pts and dev_ == device:
+            return tile
     tile = DeviceTile(pts, device)
     try:
         ref = weakref.ref(pts)
     except TypeError:
         return tile
-    _TILE_CACHE.append((ref, device, fp if fp is not None else _fingerprint(pts), tile))
+    _TILE_CACHE.append((ref, device, tile))
     while len(_TILE_CACHE) > _TILE_CACHE_SIZE:
         _TILE_CACHE.pop(0)
     return tile

@@ -196,6 +196,120 @@ def make_tile(n_points, seed=20240000, origin=TILE_ORIGIN, facade_fraction=0.33,
             'car_centres': car_c, 'car_dims': car_dim, 'pole_xy': pole_xy, 'pole_r': pole_r, 'pole_h': pole_h}
 
 
+def make_layout(seed, origin=TILE_ORIGIN, facade_fraction=0.33, n_cars=40):
+    """Scene of one synthetic tile WITHOUT its points: buildings / walls, cars, poles, crowns, the matching AHN
+    raster and the BGT-like polygons -- everything ``make_device_tile`` needs besides the per-point random
+    stream (which lives on the device).  Same scene model as ``make_tile``; own random sequence."""
+    rng = np.random.Generator(np.random.Philox(int(seed) + (1 << 40)))
+    ox, oy = origin
+    boxes = make_buildings(rng, origin)
+    walls = []
+    for (x0, y0, x1, y1, h) in boxes:
+        walls += [(x0, y0, x1, y0, h, 0, -1), (x1, y0, x1, y1, h, 1, 0),
+                  (x1, y1, x0, y1, h, 0, 1), (x0, y1, x0, y0, h, -1, 0)]
+    wa = np.array(walls, dtype=np.float64)
+    area = np.hypot(wa[:, 2] - wa[:, 0], wa[:, 3] - wa[:, 1]) * wa[:, 4]
+    cum = np.cumsum(area) / area.sum()
+    cum[-1] = 1.0
+    walls8 = np.ascontiguousarray(np.column_stack((wa, cum)))
+    cars = np.empty((n_cars, 4))
+    for c in range(n_cars):
+        if c % 2 == 0:
+            cars[c] = (ox + rng.uniform(3, 47), oy + rng.uniform(20.6, 23.9), 4.5, 1.8)
+        else:
+            cars[c] = (ox + rng.uniform(20.6, 23.9), oy + rng.uniform(3, 47), 1.8, 4.5)
+    n_pole, n_crown = 60, 25
+    poles = np.column_stack((ox + rng.uniform(1, 49, n_pole), oy + rng.uniform(1, 49, n_pole),
+                             rng.uniform(0.1, 0.3, n_pole), rng.uniform(2.0, 8.0, n_pole)))
+    crowns = np.column_stack((ox + rng.uniform(4, 46, n_crown), oy + rng.uniform(4, 46, n_crown),
+                              rng.uniform(2.0, 3.0, n_crown), rng.uniform(5.0, 10.0, n_crown)))
+    rest = 1.0 - facade_fraction
+    base = np.array([0.45, 0.08, 0.10, 0.02, 0.02])
+    base = base / base.sum() * rest
+    frac = np.array([base[0], facade_fraction, base[1], base[2], base[3], base[4]])
+    cum_kind = np.cumsum(frac)
+    cum_kind[-1] = 1.0
+    ahn_tile, building_polygons, road_polygons = _raster_and_polygons(boxes, origin)
+    return {'origin': origin, 'tilecode': tilecode_for(origin), 'boxes': boxes, 'walls8': walls8, 'cars4': cars,
+            'poles4': np.ascontiguousarray(poles), 'crowns4': np.ascontiguousarray(crowns), 'cum_kind': cum_kind,
+            'ahn_tile': ahn_tile, 'building_polygons': building_polygons, 'road_polygons': road_polygons,
+            'seed': int(seed)}
+
+
+def _raster_and_polygons(boxes, origin):
+    """AHN raster (500 x 500 cells of 0.1 m, float16 values, NaN holes) and BGT-like rings of a scene, exactly
+    as ``make_tile`` derives them from its building boxes."""
+    ox, oy = origin
+    gx_c = ox + 0.05 + 0.1 * np.arange(500)
+    gy_c = oy + TILE_SIZE - 0.05 - 0.1 * np.arange(500)
+    XX, YY = np.meshgrid(gx_c, gy_c)
+    gz = _ground_z(XX, YY, origin)
+    ground = gz.copy()
+    building = np.full_like(ground, np.nan)
+    for (x0, y0, x1, y1, h) in boxes:
+        inside = (XX >= x0) & (XX <= x1) & (YY >= y0) & (YY <= y1)
+        building[inside] = (gz + h)[inside]
+        ground[(XX >= x0 + 0.3) & (XX <= x1 - 0.3) & (YY >= y0 + 0.3) & (YY <= y1 - 0.3)] = np.nan
+    ahn_tile = {'x': gx_c, 'y': gy_c,
+                'ground_surface': ground.astype(np.float16).astype(float),
+                'building_surface': building.astype(np.float16).astype(float)}
+    building_polygons = []
+    for b, (x0, y0, x1, y1, h) in enumerate(boxes):
+        e = 0.25
+        ring = [(x0 - e, y0 - e), ((x0 + x1) / 2, y0 - e), (x1 + e, y0 - e), (x1 + e, y1 + e),
+                (x0 - e, y1 + e), (x0 - e, y0 - e)]
+        holes = []
+        if b % 3 == 0:
+            mx, my = (x0 + x1) / 2, (y0 + y1) / 2
+            holes = [[(mx - 1.5, my - 1.5), (mx - 1.5, my + 1.5), (mx + 1.5, my + 1.5),
+                      (mx + 1.5, my - 1.5), (mx - 1.5, my - 1.5)]]
+        building_polygons.append(RingPolygon(_quantise(np.array(ring)), [_quantise(np.array(hh)) for hh in holes]))
+
+    def strip(r, k):
+        x0, y0, x1, y1 = r
+        top = [(x0 + (x1 - x0) * i / k, y1 + 0.2 * np.sin(i)) for i in range(k + 1)]
+        bot = [(x1 - (x1 - x0) * i / k, y0 + 0.2 * np.cos(i)) for i in range(k + 1)]
+        return RingPolygon(_quantise(np.array(bot[::-1][::-1] + top[::-1] + [bot[0]])))
+    road_h = (ox, oy + 19.5, ox + TILE_SIZE, oy + 25.0)
+    road_v = (ox + 19.5, oy, ox + 25.0, oy + TILE_SIZE)
+    return ahn_tile, building_polygons, [strip(road_h, 24), strip(road_v, 24)]
+
+
+def tile_origin(index):
+    """Origin of synthetic tile ``index`` of a batch: a 64-wide mosaic of 50 m tiles, so every tile has its
+    own tile code (own AHN raster, own BGT query) like the tiles of a real run."""
+    return (TILE_ORIGIN[0] + TILE_SIZE * (index % 64), TILE_ORIGIN[1] + TILE_SIZE * (index // 64))
+
+
+def make_device_tile(n_points, seed=20240000, origin=TILE_ORIGIN, facade_fraction=0.33, device=None, layout=None):
+    """Synthetic tile generated ON THE DEVICE (``upcp_synth_tile``).  Returns
+    (DeviceTile, d_kind uint8 cuda tensor, layout dict as ``make_layout``).  The host never sees the points;
+    ``DeviceTile`` coordinates can be downloaded (``tile.x.cpu()`` ...) where the oracle has to label them."""
+    import ctypes
+    import torch
+    from . import _lib
+    from . import device as dev
+    lib = _lib.require_cuda()
+    device = device if device is not None else dev.current_device()
+    if layout is None:
+        layout = make_layout(seed, origin=origin, facade_fraction=facade_fraction)
+    n = int(n_points)
+    x = torch.empty(n, dtype=torch.float64, device=device)
+    y = torch.empty(n, dtype=torch.float64, device=device)
+    z = torch.empty(n, dtype=torch.float64, device=device)
+    kind = torch.empty(n, dtype=torch.uint8, device=device)
+    up = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).to(device)      # noqa: E731
+    walls, cars, poles, crowns = up(layout['walls8']), up(layout['cars4']), up(layout['poles4']), up(layout['crowns4'])
+    o3 = (ctypes.c_double * 3)(float(layout['origin'][0]), float(layout['origin'][1]), TILE_SIZE)
+    ck = (ctypes.c_double * 6)(*[float(v) for v in layout['cum_kind']])
+    _lib.check(lib.upcp_synth_tile(n, int(seed), o3, ck, dev.ptr(walls), len(layout['walls8']), dev.ptr(cars),
+                                   len(layout['cars4']), dev.ptr(poles), len(layout['poles4']), dev.ptr(crowns),
+                                   len(layout['crowns4']), dev.ptr(x), dev.ptr(y), dev.ptr(z), dev.ptr(kind),
+                                   dev.stream_ptr()), 'upcp_synth_tile')
+    torch.cuda.current_stream(device).synchronize()          # the small layout tensors may go out of scope now
+    return dev.DeviceTile.from_device(x, y, z), kind, layout
+
+
 def make_demo_cloud(n_points, ahn_tile, building_rings, seed=23869702, origin=TILE_ORIGIN):
     """Config 1: a synthetic cloud over the REAL demo tile 2386_9702 -- the reference's demo
     clouds are not part of its checkout, its AHN raster (NaN holes included) and BGT footprints are.
