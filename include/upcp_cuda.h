@@ -195,7 +195,9 @@ int upcp_raster_classify(const double* d_x, const double* d_y, const double* d_z
  * h_ring_xy is (total_vertices, 2) fp64 C-ordered, ring r uses vertices
  * h_ring_off[r] .. h_ring_off[r+1]-1.  h_ring_poly[r] is the polygon id
  * (non-decreasing), h_ring_hole[r] is 0 for the exterior ring (which must come
- * first within its polygon) and 1 for an interior ring.
+ * first within its polygon), 1 for an interior ring, 2 for a loop of an EVEN-ODD
+ * polygon (the polygon is the XOR of its loops: the outer edges of an alpha complex,
+ * alpha_shape_utils.py:40-92, stitched in any order).
  * Semantics per polygon: bbox-inclusive prefilter (clip_utils.py:22-40,219-236),
  * crossing number with boundary == inside; interiors clear what the exterior set.
  * The plan bins ring bounding boxes per uniform grid cell and ring edges per
@@ -205,6 +207,16 @@ int    upcp_pip_plan_create(const double* h_ring_xy, const int64_t* h_ring_off,
                             const int32_t* h_ring_poly, const uint8_t* h_ring_hole,
                             int32_t n_rings, int32_t grid_dim /* 0 = auto */,
                             upcp_pip_plan** out);
+/* The same for BUFFERED polygons: every polygon of the plan is taken as polygon.buffer(offset)
+ * (BGTPolyReader.filter_tile(offset=...), bgt_utils.py:154-163; poly.buffer(0.05) in
+ * AHNFuser._refine_layer, ahn_fuser.py:104-107).  The buffer is evaluated as a distance -- inside the
+ * polygon or within `offset` of its boundary (offset > 0); inside and farther than |offset| from it
+ * (offset < 0) -- i.e. the exact Minkowski sum where GEOS cuts the round joins into 8 segments per
+ * quarter circle [ext, unverified: parity unpinned against GEOS].  Query such a plan with
+ * upcp_pip_query_buffered. */
+int    upcp_pip_plan_create_buffered(const double* h_ring_xy, const int64_t* h_ring_off,
+                                     const int32_t* h_ring_poly, const uint8_t* h_ring_hole,
+                                     int32_t n_rings, int32_t grid_dim, double offset, upcp_pip_plan** out);
 size_t upcp_pip_plan_bytes(const upcp_pip_plan* plan);
 /* Copies the plan blob into d_plan (cudaMemcpyAsync from the plan's host blob). */
 int    upcp_pip_plan_upload(const upcp_pip_plan* plan, void* d_plan, size_t bytes,
@@ -213,6 +225,8 @@ void   upcp_pip_plan_destroy(upcp_pip_plan* plan);
 /* d_out[i] = (d_sel ? d_sel[i] != 0 : 1) && point i inside the polygon set. */
 int    upcp_pip_query(const void* d_plan, const double* d_x, const double* d_y,
                       int64_t n, const uint8_t* d_sel, uint8_t* d_out, void* stream);
+int    upcp_pip_query_buffered(const void* d_plan, const double* d_x, const double* d_y,
+                               int64_t n, const uint8_t* d_sel, uint8_t* d_out, void* stream);
 
 /* ------------------------------------ connected components (S3) ----------- */
 /* Octree parameters exactly as CCCoreLib derives them (float32 arithmetic):

@@ -518,13 +518,38 @@ def golden_config1(upcp):
                         checksum_points=np.array(int(mm(points).astype(np.int64).sum())))
 
 
+def golden_alpha(upcp):
+    """Outer edges of the alpha complex from the REAL get_alpha_shape_edges (scipy only) on seeded clusters --
+    pins utils/alpha_shape_utils.alpha_shape_edges and the oracle's literal loop."""
+    from upcp.utils import alpha_shape_utils as RA
+    rng = np.random.default_rng(20240099)
+    out = {}
+    for k in range(8):
+        n = int(rng.integers(50, 2500))
+        pts = np.column_stack((rng.normal(0, 0.6 + 0.5 * k, n), rng.normal(0, 0.3 + 0.15 * k, n)))
+        if k % 3 == 1:                                     # an L-shaped, hollow cluster
+            pts = pts[(np.abs(pts[:, 0]) > 0.4) | (pts[:, 1] > 0.0)]
+        if k == 7:
+            pts = np.vstack([pts, pts[:40]])                 # duplicate xy (points above each other)
+        pts = from_mm(mm(pts + np.array([119320.0, 485120.0])))
+        for alpha in (2.0, 0.7):
+            edges = RA.get_alpha_shape_edges(pts, alpha, only_outer=True)          # REAL reference
+            assert edges == R.alpha_shape_outer_edges(pts, alpha), 'oracle alpha-shape mismatch'
+            und = np.array(sorted(tuple(sorted(e)) for e in edges), dtype=np.int32).reshape(-1, 2)
+            out[f'edges_{k}_{alpha}'] = und
+        out[f'points_mm_{k}'] = mm(pts).astype(np.int64)
+    out['n_cases'] = np.array(8)
+    np.savez_compressed(os.path.join(GOLDEN, 'alpha_golden.npz'), **out)
+    print(f"  alpha: {sum(len(v) for k_, v in out.items() if k_.startswith('edges'))} outer edges over 16 cases")
+
+
 def main():
     os.makedirs(GOLDEN, exist_ok=True)
     upcp = ref_harness.load_reference()
     print('reference loaded from', upcp.__file__)
     steps = {'demo_data': lambda u: copy_demo_data(), 'pip': golden_pip, 'raster': golden_raster,
              'scalars': golden_scalars, 'demo': golden_demo, 'pipeline': golden_pipeline, 'objects': golden_objects,
-             'variants': golden_variants, 'config1': golden_config1}
+             'variants': golden_variants, 'config1': golden_config1, 'alpha': golden_alpha}
     wanted = sys.argv[1:] or list(steps)
     for name in wanted:
         print(name)

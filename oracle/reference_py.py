@@ -42,8 +42,51 @@ def rectangle_clip(points, rect):
             & (points[:, 1] >= rect[1]) & (points[:, 1] <= rect[3]))
 
 
+def seg_dist2(ax, ay, bx, by, px, py):
+    """Squared distance from the points (px, py) to the segment a-b; the expressions of the device code."""
+    ex, ey = bx - ax, by - ay
+    wx, wy = px - ax, py - ay
+    len2 = ex * ex + ey * ey
+    t = (wx * ex + wy * ey) / len2 if len2 > 0.0 else np.zeros_like(px)
+    t = np.minimum(np.maximum(t, 0.0), 1.0)
+    dx, dy = wx - t * ex, wy - t * ey
+    return dx * dx + dy * dy
+
+
+def poly_clip_buffered(points, poly, d, return_exposure=False):
+    """poly_clip(points, poly.buffer(d)) with the buffer taken as a DISTANCE (what the device evaluates where
+    the reference calls GEOS: bgt_utils.py:154-163, ahn_fuser.py:104-107): inside the polygon or within d of
+    its boundary (d > 0); inside and farther than |d| from it (d < 0).  GEOS cuts the round joins at convex
+    corners into 8 segments per quarter circle, i.e. its buffer is smaller by up to d (1 - cos(pi/32)) there:
+    ``return_exposure`` also returns the number of points that lie in that sliver of a vertex' arc."""
+    exterior = np.array(poly.exterior.coords)
+    interiors = [np.array(interior.coords) for interior in poly.interiors if len(interior.coords) >= 3]
+    n = len(points)
+    if len(exterior) < 3:
+        return (np.zeros(n, dtype=bool), 0) if return_exposure else np.zeros(n, dtype=bool)
+    px, py = np.ascontiguousarray(points[:, 0]), np.ascontiguousarray(points[:, 1])
+    inside = natives.is_inside(px, py, exterior)
+    for interior in interiors:
+        inside &= ~natives.is_inside(px, py, interior)
+    dmin2 = np.full(n, np.inf)
+    vmin2 = np.full(n, np.inf)                   # distance to the nearest VERTEX (round joins)
+    for ring in [exterior] + interiors:
+        for k in range(len(ring) - 1):
+            dmin2 = np.minimum(dmin2, seg_dist2(ring[k, 0], ring[k, 1], ring[k + 1, 0], ring[k + 1, 1], px, py))
+            vmin2 = np.minimum(vmin2, (px - ring[k, 0]) ** 2 + (py - ring[k, 1]) ** 2)
+    out = (inside | (dmin2 <= d * d)) if d > 0 else (inside & (dmin2 > d * d))
+    if return_exposure:
+        lo = abs(d) * np.cos(np.pi / 32.0)
+        sliver = (dmin2 == vmin2) & (dmin2 <= d * d) & (dmin2 > lo * lo) & ~inside
+        return out, int(sliver.sum())
+    return out
+
+
 def poly_clip(points, poly):
-    """clip_utils.poly_clip (utils/clip_utils.py:193-238); poly has .exterior.coords/.interiors."""
+    """clip_utils.poly_clip (utils/clip_utils.py:193-238); poly has .exterior.coords/.interiors.  A polygon
+    carrying a pending buffer (``offset`` attribute, no shapely) goes through ``poly_clip_buffered``."""
+    if getattr(poly, 'offset', 0.0):
+        return poly_clip_buffered(points, poly, float(poly.offset))
     clip_mask = np.zeros((len(points),), dtype=bool)
     exterior = np.array(poly.exterior.coords)
     interiors = [np.array(interior.coords) for interior in poly.interiors]
@@ -64,14 +107,117 @@ def poly_clip(points, poly):
 
 
 # ------------------------------------------------------------------ fusers --------
-def ahn_fuser_labels(points, labels, mask, ahn_tile, label, target='ground', epsilon=0.2):
-    """AHNFuser.get_labels with refine_ground=False (fusion/ahn_fuser.py:128-173)."""
+REFINE_DEFAULTS = {'bottom': 0.02, 'top': 0.5, 'grid_size': 0.4, 'min_comp_size': 50, 'buffer': 0.05,
+                   'use_concave': True, 'concave_alpha': 2.0}
+
+
+def alpha_shape_outer_edges(points, alpha):
+    """alpha_shape_utils.get_alpha_shape_edges(points, alpha, only_outer=True) (alpha_shape_utils.py:40-92),
+    the literal loop; returns a set of directed (i, j) pairs."""
+    from scipy.spatial import Delaunay
+    assert points.shape[0] > 3, 'Need at least four points'
+    edges = set()
+
+    def add_edge(i, j):
+        if (i, j) in edges or (j, i) in edges:
+            assert (j, i) in edges, "Can't go twice over same directed edge right?"
+            edges.remove((j, i))
+            return
+        edges.add((i, j))
+    for ia, ib, ic in Delaunay(points).simplices:
+        pa, pb, pc = points[ia], points[ib], points[ic]
+        a = np.sqrt((pa[0] - pb[0]) ** 2 + (pa[1] - pb[1]) ** 2)
+        b = np.sqrt((pb[0] - pc[0]) ** 2 + (pb[1] - pc[1]) ** 2)
+        c = np.sqrt((pc[0] - pa[0]) ** 2 + (pc[1] - pa[1]) ** 2)
+        s = (a + b + c) / 2.0
+        int_var = s * (s - a) * (s - b) * (s - c)
+        if int_var <= 0:
+            continue
+        circum_r = a * b * c / (4.0 * np.sqrt(int_var))
+        if circum_r < (1 / alpha):
+            add_edge(int(ia), int(ib)); add_edge(int(ib), int(ic)); add_edge(int(ic), int(ia))
+    return edges
+
+
+def edges_clip_buffered(points, verts, edges, d):
+    """Points inside the region bounded by ``edges`` (pairs into ``verts``; even-odd rule: for the outer edges
+    of a triangle complex that is the union of the triangles, i.e. the polygons generate_poly_from_edges
+    builds, alpha_shape_utils.py:177-203) or within d of them -- ``poly_clip(points, poly.buffer(d))`` with
+    the buffer as a distance.  The crossing rule per edge is clip_utils._point_inside_poly's."""
+    px, py = np.ascontiguousarray(points[:, 0]), np.ascontiguousarray(points[:, 1])
+    parity = np.zeros(len(px), dtype=bool)
+    boundary = np.zeros(len(px), dtype=bool)
+    dmin2 = np.full(len(px), np.inf)
+    for i, j in edges:
+        seg = np.array([verts[i], verts[j], verts[i]])              # a closed two-edge ring crosses twice: use one edge
+        xi, yi, xj, yj = verts[i][0], verts[i][1], verts[j][0], verts[j][1]
+        dy, dy2 = py - yi, py - yj
+        cand = (dy * dy2 <= 0.0) & ((px >= xi) | (px >= xj))
+        nonh = cand & ((dy < 0) | (dy2 < 0))
+        with np.errstate(invalid='ignore', divide='ignore'):
+            F = dy * (xj - xi) / (dy - dy2) + xi
+        parity ^= nonh & (px > F)
+        boundary |= nonh & (px == F)
+        hor = cand & ~nonh & (dy2 == 0) & ((px == xj) | ((dy == 0) & ((px - xi) * (px - xj) <= 0)))
+        boundary |= hor
+        dmin2 = np.minimum(dmin2, seg_dist2(xi, yi, xj, yj, px, py))
+        del seg
+    inside = parity | boundary
+    return (inside | (dmin2 <= d * d)) if d > 0 else (inside & (dmin2 > d * d)) if d < 0 else inside
+
+
+def refine_ground_mask(points, points_z, ground_mask, labels, target_label, params):
+    """AHNFuser._refine_ground + _refine_layer (fusion/ahn_fuser.py:76-126) on the masked points; the hull
+    polygons as regions (outer edges of the alpha complex / convex hull ring), buffer as a distance."""
+    from scipy.spatial import ConvexHull
+    with np.errstate(invalid='ignore'):
+        mask = ((points[:, 2] <= points_z + params['top']) & (points[:, 2] >= points_z - params['bottom']))
+    ref_mask = np.zeros((len(points),), dtype=bool)
+    if np.count_nonzero(labels[mask] == target_label) == 0:
+        return ref_mask
+    pts, lab, gmask = points[mask, :], labels[mask], ground_mask[mask]
+    add = np.zeros((len(pts),), dtype=bool)
+    label_ids = np.where(lab == target_label)[0]
+    ground_ids = np.where(gmask)[0]
+    point_components = lcc_get_components(pts[label_ids], params['grid_size'], params['min_comp_size'])
+    for cc in sorted(set(np.unique(point_components)).difference((-1,))):
+        cc_mask = (point_components == cc)
+        xy = np.ascontiguousarray(pts[label_ids[cc_mask], 0:2])
+        if params['use_concave']:
+            edges = alpha_shape_outer_edges(xy, params['concave_alpha'])
+        else:
+            hull = ConvexHull(xy, qhull_options='QJ').vertices
+            edges = {(int(hull[k]), int(hull[(k + 1) % len(hull)])) for k in range(len(hull))}
+        if len(edges) < 3:
+            continue
+        # bounding-box prefilter (only an optimisation here)
+        used = np.array(sorted({i for e in edges for i in e}))
+        lo, hi = xy[used].min(0) - abs(params['buffer']), xy[used].max(0) + abs(params['buffer'])
+        gp = pts[ground_ids]
+        near = np.where((gp[:, 0] >= lo[0]) & (gp[:, 0] <= hi[0]) & (gp[:, 1] >= lo[1]) & (gp[:, 1] <= hi[1]))[0]
+        if len(near):
+            hit = edges_clip_buffered(gp[near], xy, edges, params['buffer'])
+            add[ground_ids[near[hit]]] = True
+    ref_mask[mask] = add
+    return ref_mask
+
+
+def ahn_fuser_labels(points, labels, mask, ahn_tile, label, target='ground', epsilon=0.2, refine_ground=False,
+                     params=None):
+    """AHNFuser.get_labels (fusion/ahn_fuser.py:128-173)."""
     surface = 'ground_surface' if target == 'ground' else 'building_surface'
     target_z = interpolate(ahn_tile, points[mask, :], surface)
     label_mask = np.zeros((len(points),), dtype=bool)
     with np.errstate(invalid='ignore'):
         if target == 'ground':
-            label_mask[mask] = (np.abs(points[mask, 2] - target_z) < epsilon)
+            ground_mask = (np.abs(points[mask, 2] - target_z) < epsilon)
+            if refine_ground and np.count_nonzero(ground_mask) > 0:
+                p = dict(REFINE_DEFAULTS, **(params or {}))
+                tmp_labels = labels[mask].copy()
+                tmp_labels[ground_mask] = label
+                ref_mask = refine_ground_mask(points[mask], target_z, ground_mask, tmp_labels, UNKNOWN, p)
+                ground_mask = ground_mask & ~ref_mask
+            label_mask[mask] = ground_mask
         else:
             label_mask[mask] = points[mask, 2] < target_z + epsilon
     labels[label_mask] = label

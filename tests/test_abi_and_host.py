@@ -207,8 +207,11 @@ def test_readers_on_demo_data():
     assert len(road.filter_tile('2386_9702', bgt_types=['rijbaan_lokale_weg', 'parkeervlak', 'fietspad'])) == 15
     assert len(road.filter_tile('2386_9702', bgt_types=['fietspad'])) < 15
     if not bgt_utils.HAVE_SHAPELY:
-        with pytest.raises(NotImplementedError):
-            bld.filter_tile('2386_9702', offset=0.25)
+        # no GEOS: the buffer is carried as a pending offset and evaluated by the point-in-polygon kernel
+        buffered = bld.filter_tile('2386_9702', bgt_types=['pand'], offset=0.25, merge=True)
+        assert len(buffered) == 7 and all(p.offset == 0.25 for p in buffered)
+        assert [p.exterior.coords for p in buffered] == [p.exterior.coords for p in polys]
+        assert buffered[0].buffer(-0.25).offset == 0.0 and polys[0].buffer(0) is polys[0]
     assert las_utils.get_bbox_from_tile_code('2386_9702') == ((119300, 485150), (119350, 485100))
     assert las_utils.get_tilecode_from_filename('filtered_2386_9702.laz') == '2386_9702'
     assert math_utils.get_octree_level(np.array([[0, 0, 0], [50., 20, 3]]), 0.05) == 10

@@ -228,6 +228,78 @@ def test_pip_matches_reference_golden(golden, name):
     assert np.array_equal(one, ref)
 
 
+def test_buffered_polygons_match_distance_oracle():
+    """polygon.buffer(offset) evaluated as a distance (upcp_pip_plan_create_buffered): star-shaped rings with
+    holes, positive and negative offsets, probes on and around the offset curve -- bit for bit the numpy
+    restatement of the same expressions.  (GEOS itself is in neither container: unpinned, exposure counted.)"""
+    rng = np.random.default_rng(77)
+    polys = synthetic.make_polygon_lattice(n_side=6, seed=3)
+    demo = os.path.join(GOLDEN, 'demo')
+    real = bgt_utils.BGTPolyReader(bgt_file=os.path.join(demo, 'bgt_buildings_demo.csv'))
+    for offset in (0.25, 0.05, -0.03):
+        for name, plist in (('lattice', [p.buffer(offset) for p in polys]),
+                            ('bgt', real.filter_tile('2386_9702', bgt_types=['pand'], offset=offset, merge=True))):
+            assert all(abs(p.offset - offset) < 1e-15 for p in plist)
+            rings = [np.array(p.exterior.coords) for p in plist]
+            allv = np.vstack(rings)
+            lo, hi = allv.min(0) - 1.0, allv.max(0) + 1.0
+            pts = lo + rng.random((400_000, 2)) * (hi - lo)
+            # probes hugging the offset curve: ring points pushed out / in by about |offset|
+            k = rng.integers(0, len(allv), 100_000)
+            ang = rng.uniform(0, 2 * np.pi, len(k))
+            rad = abs(offset) * (1.0 + rng.normal(0, 0.02, len(k)))
+            pts = np.vstack([pts, allv[k] + np.column_stack((rad * np.cos(ang), rad * np.sin(ang)))])
+            pts = np.ascontiguousarray(np.round(pts, 3))
+            want = np.zeros(len(pts), dtype=bool)
+            exposed = 0
+            for p in plist:
+                m, e = R.poly_clip_buffered(pts, p, offset, return_exposure=True)
+                want |= m
+                exposed += e
+            t = dev.DeviceTile(pts)
+            got = dev.download_mask(dev.PipPlan(plist).query(t))
+            assert np.array_equal(got, want), (name, offset, int((got != want).sum()))
+            plain = dev.download_mask(dev.PipPlan([RingPolygon(np.array(p.exterior.coords),
+                                                               [np.array(i.coords) for i in p.interiors]) for p in plist]).query(t))
+            assert (got | plain).sum() == (got.sum() if offset > 0 else plain.sum())       # buffer grows / shrinks the set
+            print(f'{name}, offset {offset}: {got.sum()} inside (unbuffered {plain.sum()}), {exposed} probes in the '
+                  f'round-join sliver where GEOS (quad_segs 8) would differ')
+    # the fusers accept the offset (notebook 0: BGTBuildingFuser(offset=0.25)) and agree with the oracle
+    tile = synthetic.make_tile(200_000, seed=91)
+    ahn, bld, road = readers_for(tile)
+    labels = np.zeros(len(tile['points']), dtype=np.uint16)
+    got = BGTBuildingFuser(Labels.BUILDING, bgt_reader=bld, offset=0.25, ahn_reader=ahn).get_labels(
+        tile['points'], labels.copy(), labels == 0, tile['tilecode'])
+    want = R.building_fuser_labels(tile['points'], labels.copy(), labels == 0,
+                                   [p.buffer(0.25) for p in tile['building_polygons']], Labels.BUILDING, tile['ahn_tile'], 0.2)
+    plain = R.building_fuser_labels(tile['points'], labels.copy(), labels == 0, tile['building_polygons'], Labels.BUILDING,
+                                    tile['ahn_tile'], 0.2)
+    assert np.array_equal(got, want) and (got == Labels.BUILDING).sum() > (plain == Labels.BUILDING).sum()
+
+
+def test_ahn_fuser_refine_ground_matches_oracle():
+    """AHNFuser(refine_ground=True) -- the reference's default (ahn_fuser.py:40-41,76-126): tentative ground under
+    unlabelled clusters is removed again.  Device band test + clustering + clipping against all cluster hulls,
+    host Delaunay per cluster; against the oracle's restatement of the same control flow (hull = outer edges
+    of the alpha complex, pinned by alpha_golden.npz; buffer as a distance, unpinned against GEOS)."""
+    tile = synthetic.make_tile(400_000, seed=63, facade_fraction=0.25)
+    pts, tc = tile['points'], tile['tilecode']
+    ahn, _, _ = readers_for(tile)
+    for params in ({}, {'use_concave': False}, {'concave_alpha': 0.7, 'buffer': 0.2, 'min_comp_size': 20}):
+        labels = np.zeros(len(pts), dtype=np.uint16)
+        labels[::17] = 3                                       # some points arrive labelled (not UNKNOWN)
+        mask = labels == 0
+        want = R.ahn_fuser_labels(pts, labels.copy(), mask, tile['ahn_tile'], Labels.GROUND, 'ground', 0.2,
+                                  refine_ground=True, params=dict(params))
+        plain = R.ahn_fuser_labels(pts, labels.copy(), mask, tile['ahn_tile'], Labels.GROUND, 'ground', 0.2)
+        got = AHNFuser(Labels.GROUND, ahn, target='ground', epsilon=0.2, refine_ground=True,
+                       params=dict(params)).get_labels(pts, labels.copy(), mask, tc)
+        removed = int(((plain == Labels.GROUND) & (want != Labels.GROUND)).sum())
+        print(f'refine_ground {params}: {removed} of {(plain == Labels.GROUND).sum()} tentative ground points removed, '
+              f'{int((got != want).sum())} labels differ from the oracle')
+        assert np.array_equal(got, want) and removed > 100
+
+
 def test_pip_lattice_5000_polygons_matches_oracle():
     polys = synthetic.make_polygon_lattice()
     tile = synthetic.make_tile(400000, seed=9)

@@ -352,3 +352,29 @@ def test_config1_oracle_matches_reference_golden(golden):
     grown = R.region_growing_labels(points, o.copy(), 10, exclude_labels=(9,))
     assert np.array_equal(grown, g['labels_region_growing'])
     assert np.count_nonzero(grown == 10) > np.count_nonzero(o == 10) + 100_000
+
+
+def test_alpha_shape_edges_match_reference_golden(golden):
+    """Outer edges of the alpha complex: the product's vectorised alpha_shape_edges and the oracle's literal loop
+    against the REAL get_alpha_shape_edges (alpha_golden.npz); the edges stitch into closed trails."""
+    from urban_pointcloud_processing_b200.utils import alpha_shape_utils as A
+    g = golden('alpha_golden.npz')
+    for k in range(int(g['n_cases'])):
+        pts = from_mm(g[f'points_mm_{k}'])
+        for alpha in (2.0, 0.7):
+            want = g[f'edges_{k}_{alpha}']
+            got = A.alpha_shape_edges(pts, alpha)
+            assert np.array_equal(got, want.astype(np.int64)), (k, alpha)
+            ora = R.alpha_shape_outer_edges(pts, alpha)
+            assert sorted(tuple(sorted(e)) for e in ora) == [tuple(e) for e in want.tolist()]
+            trails = A.closed_trails(got)
+            assert sum(len(t) - 1 for t in trails) == len(got) and all(t[0] == t[-1] for t in trails)
+            # even-odd over the trails == union of the kept triangles: probe with the oracle's edge-soup test
+            if len(got):
+                rng = np.random.default_rng(k)
+                probes = pts[rng.integers(0, len(pts), 300)] + rng.normal(0, 0.05, (300, 2))
+                soup = R.edges_clip_buffered(probes, pts, [tuple(e) for e in got.tolist()], 0.0)
+                loops = np.zeros(len(probes), dtype=bool)
+                for t in trails:
+                    loops ^= natives.is_inside(probes[:, 0], probes[:, 1], pts[t])
+                assert np.array_equal(soup, loops)

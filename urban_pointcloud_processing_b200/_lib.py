@@ -69,10 +69,13 @@ _PROTOTYPES = {
                                      c_void_p, c_int32, c_void_p]),
     'upcp_pip_plan_create': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32,
                                      POINTER(c_void_p)]),
+    'upcp_pip_plan_create_buffered': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_double,
+                                              POINTER(c_void_p)]),
     'upcp_pip_plan_bytes': (c_size_t, [c_void_p]),
     'upcp_pip_plan_upload': (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
     'upcp_pip_plan_destroy': (None, [c_void_p]),
     'upcp_pip_query': (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
+    'upcp_pip_query_buffered': (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
     'upcp_octree_params': (c_int, [POINTER(c_double), c_int, POINTER(c_float)]),
     'upcp_octree_level': (c_int, [POINTER(c_double), c_int, c_double]),
     'upcp_lcc_ws_bytes': (c_size_t, [c_int64, c_int64, c_int]),

@@ -19,6 +19,16 @@
 //     arithmetic); every listed edge goes through the exact reference test in fp64.
 // The plan is a few MB at most and stays L2-resident; the point stream is read
 // once, coalesced (16 B/pt in, 1 B/pt out).
+//
+// Buffered polygons (`offset` != 0: BGTPolyReader.filter_tile(offset=...), bgt_utils.py:154-163;
+// `poly.buffer(0.05)` in AHNFuser._refine_layer, ahn_fuser.py:104-107).  The reference hands the
+// polygon to GEOS, which is in neither container; the plan carries the offset instead and the
+// query evaluates the buffer as what it is, a distance: a point is in buffer(P, d > 0) iff it is in
+// P or within d of its boundary; in buffer(P, d < 0) iff it is in P and farther than |d| from the
+// boundary.  That is the exact Minkowski sum where GEOS approximates the round joins at convex
+// corners by 8 segments per quarter circle (quad_segs = 8: the arcs are cut by up to
+// d (1 - cos(pi / 32)) = 0.0048 d, 1.2 mm for the notebook's d = 0.25 m); along straight edges
+// the two agree to rounding.  [ext, unverified -- parity unpinned against GEOS, see DESIGN.md]
 #include <math.h>
 #include <string.h>
 #include <vector>
@@ -28,6 +38,7 @@
 struct PipHeader {
     int32_t magic, n_rings, gx, gy;
     double x0, y0, inv_cw, inv_ch;
+    double offset;           // buffer distance of every polygon of the plan (0 = the reference's exact test)
     int64_t off_ring_bbox;   // double[R][4]  xmin ymin xmax ymax
     int64_t off_ring_meta;   // int32 [R][4]  poly, is_hole, slab_base, n_slabs
     int64_t off_ring_slab;   // double[R][2]  slab y0, inv_h
@@ -62,6 +73,89 @@ __device__ __forceinline__ int dev_cell(double v, double origin, double inv, int
     if (!(t > 0.0)) return 0;
     if (t >= (double)n) return n - 1;
     return (int)floor(t);
+}
+
+// squared distance from p to the segment a-b (fp64, no FMA: the oracle evaluates the same expressions)
+__device__ __forceinline__ double seg_dist2(double ax, double ay, double bx, double by, double px, double py) {
+    const double ex = bx - ax, ey = by - ay;
+    const double wx = px - ax, wy = py - ay;
+    const double len2 = ex * ex + ey * ey;
+    double t = len2 > 0.0 ? (wx * ex + wy * ey) / len2 : 0.0;
+    t = fmin(fmax(t, 0.0), 1.0);
+    const double dx = wx - t * ex, dy = wy - t * ey;
+    return dx * dx + dy * dy;
+}
+
+// Buffered polygons: see the header comment.  Same plan layout; ring bounding boxes, cell lists and
+// slabs were built with the buffer distance added, so one slab holds every edge that the crossing test
+// or the distance test of a point may need.
+__global__ void __launch_bounds__(kBlock)
+pip_query_offset_kernel(const char* __restrict__ plan, const double* __restrict__ x,
+                        const double* __restrict__ y, int64_t n, const uint8_t* __restrict__ sel,
+                        uint8_t* __restrict__ out) {
+    const PipHeader* h = (const PipHeader*)plan;
+    const double2* ring_bbox = (const double2*)(plan + h->off_ring_bbox);
+    const int4* ring_meta = (const int4*)(plan + h->off_ring_meta);
+    const double2* ring_slab = (const double2*)(plan + h->off_ring_slab);
+    const int32_t* slab_start = (const int32_t*)(plan + h->off_slab_start);
+    const int32_t* slab_edges = (const int32_t*)(plan + h->off_slab_edges);
+    const double2* verts = (const double2*)(plan + h->off_verts);
+    const int32_t* cell_start = (const int32_t*)(plan + h->off_cell_start);
+    const int32_t* cell_rings = (const int32_t*)(plan + h->off_cell_rings);
+    const int gx = h->gx, gy = h->gy;
+    const double x0 = h->x0, y0 = h->y0, inv_cw = h->inv_cw, inv_ch = h->inv_ch;
+    const double d = h->offset, D = fabs(d), D2 = d * d;
+    const double inf = __longlong_as_double(0x7ff0000000000000LL);
+
+    int64_t stride = (int64_t)gridDim.x * kBlock;
+    for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < n; i += stride) {
+        bool s = sel ? (sel[i] != 0) : true;
+        bool inside_any = false;
+        if (s) {
+            double px = x[i], py = y[i];
+            int cx = dev_cell(px, x0, inv_cw, gx);
+            int cy = dev_cell(py, y0, inv_ch, gy);
+            int c = cy * gx + cx;
+            int k0 = __ldg(cell_start + c), k1 = __ldg(cell_start + c + 1);
+            int cur_poly = -1;
+            bool in_ext = false, in_hole = false;
+            double dmin2 = inf;
+            auto close_polygon = [&]() {
+                const bool in = in_ext && !in_hole;
+                return d > 0.0 ? (in || dmin2 <= D2) : (in && dmin2 > D2);
+            };
+            for (int k = k0; k < k1; ++k) {
+                int r = __ldg(cell_rings + k);
+                int4 meta = __ldg(ring_meta + r);
+                if (meta.x != cur_poly) {
+                    if (cur_poly >= 0) inside_any = inside_any || close_polygon();
+                    if (inside_any) break;
+                    in_ext = false; in_hole = false; dmin2 = inf;
+                    cur_poly = meta.x;
+                }
+                double2 bmin = __ldg(ring_bbox + 2 * r), bmax = __ldg(ring_bbox + 2 * r + 1);
+                if (!(px >= bmin.x - D && px <= bmax.x + D && py >= bmin.y - D && py <= bmax.y + D)) continue;
+                double2 sl = __ldg(ring_slab + r);
+                int si = dev_cell(py, sl.x, sl.y, meta.w);
+                int e0 = __ldg(slab_start + meta.z + si), e1 = __ldg(slab_start + meta.z + si + 1);
+                int parity = 0;
+                bool boundary = false;
+                for (int e = e0; e < e1; ++e) {
+                    int vi = __ldg(slab_edges + e);
+                    double2 a = __ldg(verts + vi), b = __ldg(verts + vi + 1);
+                    int res = pip_edge(a.x, a.y, b.x, b.y, px, py);
+                    if (res == 2) boundary = true; else parity ^= res;
+                    dmin2 = fmin(dmin2, seg_dist2(a.x, a.y, b.x, b.y, px, py));
+                }
+                const bool in = boundary || (parity != 0);
+                if (meta.y == 0) in_ext = in;
+                else if (meta.y == 1) { if (in) in_hole = true; }
+                else in_ext = in_ext != in;                    // even-odd loop: the polygon is the XOR of its loops
+            }
+            if (cur_poly >= 0 && !inside_any) inside_any = close_polygon();
+        }
+        out[i] = inside_any ? 1 : 0;
+    }
 }
 
 __global__ void __launch_bounds__(kBlock)
@@ -101,7 +195,7 @@ pip_query_kernel(const char* __restrict__ plan, const double* __restrict__ x,
                     cur_in = false;
                     cur_poly = meta.x;
                 }
-                bool is_hole = meta.y != 0;
+                bool is_hole = meta.y == 1;
                 if (is_hole && !cur_in) continue;
                 double2 bmin = __ldg(ring_bbox + 2 * r), bmax = __ldg(ring_bbox + 2 * r + 1);
                 // rectangle_clip (clip_utils.py:38-39): inclusive on all four sides
@@ -119,8 +213,9 @@ pip_query_kernel(const char* __restrict__ plan, const double* __restrict__ x,
                     parity ^= res;
                 }
                 bool in = boundary || (parity != 0);
-                if (!is_hole) cur_in = in;
-                else if (in) cur_in = false;
+                if (meta.y == 0) cur_in = in;
+                else if (is_hole) { if (in) cur_in = false; }
+                else cur_in = cur_in != in;                    // even-odd loop
             }
             inside_any = inside_any || cur_in;
         }
@@ -137,8 +232,16 @@ extern "C" {
 int upcp_pip_plan_create(const double* h_ring_xy, const int64_t* h_ring_off,
                          const int32_t* h_ring_poly, const uint8_t* h_ring_hole,
                          int32_t n_rings, int32_t grid_dim, upcp_pip_plan** out) {
+    return upcp_pip_plan_create_buffered(h_ring_xy, h_ring_off, h_ring_poly, h_ring_hole, n_rings, grid_dim, 0.0, out);
+}
+
+int upcp_pip_plan_create_buffered(const double* h_ring_xy, const int64_t* h_ring_off,
+                                  const int32_t* h_ring_poly, const uint8_t* h_ring_hole,
+                                  int32_t n_rings, int32_t grid_dim, double offset, upcp_pip_plan** out) {
     if (!out) UPCP_FAIL(UPCP_E_INVALID, "pip_plan_create: out is NULL");
     *out = nullptr;
+    if (!(offset == offset) || fabs(offset) > 1e12) UPCP_FAIL(UPCP_E_INVALID, "pip_plan_create: bad offset");
+    const double D = fabs(offset);
     if (n_rings < 0 || (n_rings > 0 && (!h_ring_xy || !h_ring_off || !h_ring_poly || !h_ring_hole)))
         UPCP_FAIL(UPCP_E_INVALID, "pip_plan_create: NULL input");
     const int R = n_rings;
@@ -159,13 +262,15 @@ int upcp_pip_plan_create(const double* h_ring_xy, const int64_t* h_ring_off,
         for (int r = 0; r < R; ++r) {
             int64_t a = h_ring_off[r], b = h_ring_off[r + 1];
             int nv = (int)(b - a);
-            bool hole = h_ring_hole[r] != 0;
+            const int kind = h_ring_hole[r];                  // 0 exterior, 1 interior, 2 loop of an even-odd polygon
+            if (kind > 2) UPCP_FAIL(UPCP_E_INVALID, "pip_plan_create: ring kind must be 0, 1 or 2");
+            bool hole = kind == 1;
             if (h_ring_poly[r] != prev_poly) {
                 prev_poly = h_ring_poly[r];
                 // clip_utils.py:214-216: exterior with < 3 coords => polygon clips nothing
-                poly_alive = !hole && nv >= 3;
+                poly_alive = kind == 2 || (!hole && nv >= 3);
                 if (hole) UPCP_FAIL(UPCP_E_INVALID, "pip_plan_create: first ring of a polygon must be its exterior");
-            } else if (!hole) {
+            } else if (kind == 0) {
                 UPCP_FAIL(UPCP_E_INVALID, "pip_plan_create: a polygon has one exterior ring");
             }
             double xmin = INFINITY, ymin = INFINITY, xmax = -INFINITY, ymax = -INFINITY;
@@ -178,7 +283,7 @@ int upcp_pip_plan_create(const double* h_ring_xy, const int64_t* h_ring_off,
             // clip_utils.py:229-231: interiors with < 3 coords are skipped
             active[r] = poly_alive && nv >= 3 && isfinite(xmin) && isfinite(ymin) && isfinite(xmax) && isfinite(ymax);
             if (active[r]) {
-                ux0 = fmin(ux0, xmin); uy0 = fmin(uy0, ymin); ux1 = fmax(ux1, xmax); uy1 = fmax(uy1, ymax);
+                ux0 = fmin(ux0, xmin - D); uy0 = fmin(uy0, ymin - D); ux1 = fmax(ux1, xmax + D); uy1 = fmax(uy1, ymax + D);
             }
         }
     }
@@ -199,10 +304,10 @@ int upcp_pip_plan_create(const double* h_ring_xy, const int64_t* h_ring_off,
 
     std::vector<int32_t> cell_start((size_t)gx * gy + 1, 0);
     auto ring_cells = [&](int r, int& cx0, int& cx1, int& cy0, int& cy1) {
-        cx0 = clampi((long long)host_cell(bbox[4 * r + 0], ux0, inv_cw, gx) - 1, 0, gx - 1);
-        cx1 = clampi((long long)host_cell(bbox[4 * r + 2], ux0, inv_cw, gx) + 1, 0, gx - 1);
-        cy0 = clampi((long long)host_cell(bbox[4 * r + 1], uy0, inv_ch, gy) - 1, 0, gy - 1);
-        cy1 = clampi((long long)host_cell(bbox[4 * r + 3], uy0, inv_ch, gy) + 1, 0, gy - 1);
+        cx0 = clampi((long long)host_cell(bbox[4 * r + 0] - D, ux0, inv_cw, gx) - 1, 0, gx - 1);
+        cx1 = clampi((long long)host_cell(bbox[4 * r + 2] + D, ux0, inv_cw, gx) + 1, 0, gx - 1);
+        cy0 = clampi((long long)host_cell(bbox[4 * r + 1] - D, uy0, inv_ch, gy) - 1, 0, gy - 1);
+        cy1 = clampi((long long)host_cell(bbox[4 * r + 3] + D, uy0, inv_ch, gy) + 1, 0, gy - 1);
     };
     for (int r = 0; r < R; ++r) {
         if (!active[r]) continue;
@@ -235,10 +340,10 @@ int upcp_pip_plan_create(const double* h_ring_xy, const int64_t* h_ring_off,
     for (int r = 0; r < R; ++r) {
         int nv = (int)(h_ring_off[r + 1] - h_ring_off[r]);
         int ns = active[r] ? (nv < 1 ? 1 : (nv > 4096 ? 4096 : nv)) : 1;
-        double ymin = bbox[4 * r + 1], ymax = bbox[4 * r + 3];
+        double ymin = bbox[4 * r + 1] - D, ymax = bbox[4 * r + 3] + D;      // slabs cover the buffered extent
         double hh = active[r] ? (ymax - ymin) : 0.0;
         meta[4 * r + 0] = h_ring_poly[r];
-        meta[4 * r + 1] = h_ring_hole[r] ? 1 : 0;
+        meta[4 * r + 1] = h_ring_hole[r];
         meta[4 * r + 2] = (int32_t)total_slabs;
         meta[4 * r + 3] = ns;
         slab_geo[2 * r + 0] = active[r] ? ymin : 0.0;
@@ -249,7 +354,7 @@ int upcp_pip_plan_create(const double* h_ring_xy, const int64_t* h_ring_off,
     std::vector<int32_t> slab_start((size_t)total_slabs + 1, 0);
     auto edge_slabs = [&](int r, int64_t v, int& s0, int& s1) {
         double ya = h_ring_xy[2 * v + 1], yb = h_ring_xy[2 * (v + 1) + 1];
-        double lo = fmin(ya, yb), hi = fmax(ya, yb);
+        double lo = fmin(ya, yb) - D, hi = fmax(ya, yb) + D;               // every slab a point within D of the edge can lie in
         int ns = meta[4 * r + 3];
         s0 = clampi((long long)host_cell(lo, slab_geo[2 * r], slab_geo[2 * r + 1], ns) - 1, 0, ns - 1);
         s1 = clampi((long long)host_cell(hi, slab_geo[2 * r], slab_geo[2 * r + 1], ns) + 1, 0, ns - 1);
@@ -287,7 +392,7 @@ int upcp_pip_plan_create(const double* h_ring_xy, const int64_t* h_ring_off,
     PipHeader hd;
     memset(&hd, 0, sizeof(hd));
     hd.magic = kPipMagic; hd.n_rings = R; hd.gx = gx; hd.gy = gy;
-    hd.x0 = ux0; hd.y0 = uy0; hd.inv_cw = inv_cw; hd.inv_ch = inv_ch;
+    hd.x0 = ux0; hd.y0 = uy0; hd.inv_cw = inv_cw; hd.inv_ch = inv_ch; hd.offset = offset;
     size_t off = align_up(sizeof(PipHeader), 256);
     auto place = [&](size_t bytes) { size_t o = off; off = align_up(off + (bytes ? bytes : 1), 256); return (int64_t)o; };
     hd.off_ring_bbox = place((size_t)R * 4 * sizeof(double));
@@ -342,6 +447,16 @@ int upcp_pip_query(const void* d_plan, const double* d_x, const double* d_y, int
     pip_query_kernel<<<grid_for(n, kBlock), kBlock, 0, (cudaStream_t)stream>>>(
         (const char*)d_plan, d_x, d_y, n, d_sel, d_out);
     prof_end(UPCP_PROF_PIP, (cudaStream_t)stream, n);
+    UPCP_LAUNCH_OK();
+    return UPCP_OK;
+}
+
+int upcp_pip_query_buffered(const void* d_plan, const double* d_x, const double* d_y, int64_t n,
+                            const uint8_t* d_sel, uint8_t* d_out, void* stream) {
+    if (n < 0 || !d_plan) UPCP_FAIL(UPCP_E_INVALID, "pip_query_buffered: bad argument");
+    if (n == 0) return UPCP_OK;
+    pip_query_offset_kernel<<<grid_for(n, kBlock), kBlock, 0, (cudaStream_t)stream>>>(
+        (const char*)d_plan, d_x, d_y, n, d_sel, d_out);
     UPCP_LAUNCH_OK();
     return UPCP_OK;
 }

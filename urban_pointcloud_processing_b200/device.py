@@ -383,6 +383,14 @@ def rings_from_polygons(polygons):
     (clip_utils.py:211-212)."""
     xy, off, poly_id, hole = [], [0], [], []
     for p, poly in enumerate(polygons):
+        if hasattr(poly, 'loops'):                     # even-odd region (alpha_shape_utils.LoopPolygon): ring kind 2
+            for loop in poly.loops:
+                ring = np.asarray(loop.coords, dtype=np.float64).reshape(-1, 2)
+                xy.append(ring)
+                off.append(off[-1] + ring.shape[0])
+                poly_id.append(p)
+                hole.append(2)
+            continue
         if hasattr(poly, 'exterior'):
             ext = np.asarray(poly.exterior.coords, dtype=np.float64)
             ints = [np.asarray(i.coords, dtype=np.float64) for i in poly.interiors]
@@ -402,32 +410,48 @@ def rings_from_polygons(polygons):
 
 
 class PipPlan:
-    """Device-resident point-in-polygon plan for a set of polygons."""
+    """Device-resident point-in-polygon plan for a set of polygons.  Polygons that carry a pending buffer
+    (``RingPolygon.offset``, i.e. ``filter_tile(offset=...)`` / ``poly.buffer(d)`` without shapely) are
+    grouped by offset into buffered sub-plans; the query ORs the groups."""
 
     def __init__(self, polygons, device=None, grid_dim=0):
-        lib = _lib.require_cuda()
+        _lib.require_cuda()
         self.device = device if device is not None else current_device()
+        groups = {}
+        for poly in polygons:
+            groups.setdefault(float(getattr(poly, 'offset', 0.0) or 0.0), []).append(poly)
+        self.parts = [self._build(polys, off, grid_dim) for off, polys in sorted(groups.items())]
+        self.n_rings = sum(p[2] for p in self.parts)
+        self.n_vertices = sum(p[3] for p in self.parts)
+        self.nbytes = sum(int(p[0].numel()) for p in self.parts)
+        self.blob = self.parts[0][0] if len(self.parts) == 1 else None
+
+    def _build(self, polygons, offset, grid_dim):
+        lib = _lib.load()
         ring_xy, off, poly_id, hole = rings_from_polygons(polygons)
-        self.n_rings = int(poly_id.shape[0])
-        self.n_vertices = int(ring_xy.shape[0])
         handle = ctypes.c_void_p()
-        _lib.check(lib.upcp_pip_plan_create(
+        _lib.check(lib.upcp_pip_plan_create_buffered(
             ring_xy.ctypes.data_as(ctypes.c_void_p), off.ctypes.data_as(ctypes.c_void_p),
             poly_id.ctypes.data_as(ctypes.c_void_p), hole.ctypes.data_as(ctypes.c_void_p),
-            self.n_rings, int(grid_dim), ctypes.byref(handle)), 'upcp_pip_plan_create')
+            int(poly_id.shape[0]), int(grid_dim), float(offset), ctypes.byref(handle)), 'upcp_pip_plan_create_buffered')
         try:
             nbytes = lib.upcp_pip_plan_bytes(handle)
-            self.blob = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
-            _lib.check(lib.upcp_pip_plan_upload(handle, ptr(self.blob), nbytes, stream_ptr()),
-                       'upcp_pip_plan_upload')
+            blob = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+            _lib.check(lib.upcp_pip_plan_upload(handle, ptr(blob), nbytes, stream_ptr()), 'upcp_pip_plan_upload')
         finally:
             lib.upcp_pip_plan_destroy(handle)
-        self.nbytes = int(nbytes)
+        return blob, float(offset), int(poly_id.shape[0]), int(ring_xy.shape[0])
 
     def query(self, tile, d_sel=None):
         """uint8 mask [N]: point inside the polygon set (restricted to d_sel)."""
         lib = _lib.load()
-        out = torch.empty(tile.n, dtype=torch.uint8, device=self.device)
-        _lib.check(lib.upcp_pip_query(ptr(self.blob), ptr(tile.x), ptr(tile.y), tile.n, ptr(d_sel), ptr(out),
-                                      stream_ptr()), 'upcp_pip_query')
+        out = None
+        for blob, offset, _, _ in self.parts:
+            part = torch.empty(tile.n, dtype=torch.uint8, device=self.device)
+            fn, name = (lib.upcp_pip_query, 'upcp_pip_query') if offset == 0.0 else \
+                (lib.upcp_pip_query_buffered, 'upcp_pip_query_buffered')
+            _lib.check(fn(ptr(blob), ptr(tile.x), ptr(tile.y), tile.n, ptr(d_sel), ptr(part), stream_ptr()), name)
+            out = part if out is None else mask_combine(out, part, 'or', out=out)
+        if out is None:
+            out = torch.zeros(tile.n, dtype=torch.uint8, device=self.device)
         return out

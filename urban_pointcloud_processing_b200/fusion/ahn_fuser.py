@@ -69,10 +69,8 @@ class AHNFuser(AbstractProcessor):
 
     def _refine_ground_device(self, tile, d_labels, d_mask, d_ground, raster, tilecode):
         """ahn_fuser.py:111-126 / :76-109 with the clustering and the clipping on the GPU."""
-        from ..region_growing.label_connected_comp import LabelConnectedComp
         from ..utils import refine_utils
-        return refine_utils.refine_ground(self, LabelConnectedComp, tile, d_labels, d_mask,
-                                          d_ground, raster, tilecode)
+        return refine_utils.refine_ground(self, tile, d_labels, d_mask, d_ground, raster, tilecode)
 
     def _label_mask_device(self, tile, d_labels, d_mask, tilecode):
         logger.info(f'AHN [{self.method}/{self.target}] fuser ' +

@@ -4,11 +4,13 @@
 
 The reference builds shapely polygons (``Polygon(poly).buffer(offset)``, optional
 ``unary_union``, bgt_utils.py:154-163).  shapely/GEOS is an optional dependency here:
-when importable it is used exactly as the reference does; otherwise only ``offset == 0``
-is supported and polygons are returned as ``RingPolygon`` objects exposing the same
-``.exterior.coords`` / ``.interiors`` protocol that ``poly_clip`` reads
-(clip_utils.py:211-212).  For ``offset == 0`` the OR of per-polygon masks equals the mask
-of the union up to measure-zero boundary sets."""
+when importable it is used exactly as the reference does; otherwise polygons are returned as
+``RingPolygon`` objects exposing the same ``.exterior.coords`` / ``.interiors`` protocol that
+``poly_clip`` reads (clip_utils.py:211-212), and a buffer is carried as the polygon's ``offset``
+attribute: the point-in-polygon kernel evaluates it as a distance (``upcp_pip_plan_create_buffered``:
+the exact Minkowski sum where GEOS cuts round joins into 8 segments per quarter circle; unpinned
+against GEOS).  The OR of per-polygon masks equals the mask of the union up to
+measure-zero boundary sets, so ``merge=True`` needs no polygon union."""
 import ast
 import logging
 import os
@@ -38,7 +40,8 @@ class _Ring:
 class RingPolygon:
     """Minimal polygon: closed exterior ring + optional interior rings."""
 
-    def __init__(self, shell, holes=()):
+    def __init__(self, shell, holes=(), offset=0.0):
+        self.offset = float(offset)                    # pending buffer distance (evaluated on the device)
         shell = np.asarray(shell, dtype=np.float64).reshape(-1, 2)
         if len(shell) >= 1 and not np.array_equal(shell[0], shell[-1]):
             shell = np.vstack([shell, shell[:1]])      # shapely closes rings implicitly
@@ -51,9 +54,13 @@ class RingPolygon:
             self.interiors.append(_Ring(h))
 
     def buffer(self, offset):
-        if offset != 0:
-            raise NotImplementedError('polygon offsetting needs shapely (not installed)')
-        return self
+        """``shapely.Polygon.buffer``: the same rings with the distance added to the pending offset (the
+        point-in-polygon kernel evaluates it; nothing is re-vertexed on the host)."""
+        if offset == 0:
+            return self
+        out = RingPolygon.__new__(RingPolygon)
+        out.exterior, out.interiors, out.offset = self.exterior, self.interiors, self.offset + float(offset)
+        return out
 
 
 class BGTReader(ABC):
@@ -114,10 +121,7 @@ class BGTPolyReader(BGTReader):
             else:
                 poly_offset = [_ShapelyPolygon(poly).buffer(offset) for poly in polygons]
         else:
-            if offset != 0:
-                raise NotImplementedError(
-                    'BGTPolyReader.filter_tile(offset != 0) needs shapely/GEOS, which is not installed')
-            poly_offset = [RingPolygon(poly) for poly in polygons]
+            poly_offset = [RingPolygon(poly).buffer(offset) for poly in polygons]
         return [poly for poly in poly_offset if len(poly.exterior.coords) > 1]
 
 
