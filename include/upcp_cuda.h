@@ -409,6 +409,21 @@ int upcp_prism_clip(const double* d_x, const double* d_y, const double* d_z, int
                     const uint8_t* d_sel, const double* d_ring_xy, const int32_t* d_ring_off,
                     const double* d_zrange, int32_t n_prisms, uint8_t* d_out, void* stream);
 
+/* ------------------------------------ AHN preprocessing ("next" row 4) ---- */
+/* SpatialInterpolator.__call__ (reference utils/interpolation.py:156-308) for 2-D data, as
+ * preprocessing/ahn_preprocessing.py:129-236 uses it to rasterise an AHN cloud: for every position the
+ * n_neighbors (<= 32) nearest data points with distance < max_dist (scipy cKDTree.query semantics),
+ *   method 0 `idw`: value of the nearest point if it lies within conf_dist, else
+ *                   sum(w v) / sum(w), w = 1 / (d ** power + reg), in ascending (distance, index) order;
+ *   method 1 `max`: maximum of their values;
+ * fill_value where no point lies within max_dist.  h_bbox4 = x_min, y_min, x_max, y_max of the data points.
+ * Replaces: scipy cKDTree + the per-position Python loop of interpolation.py:276-303. */
+size_t upcp_interpolate_ws_bytes(int64_t n);
+int upcp_interpolate(const double* d_px, const double* d_py, const double* d_pv, int64_t n, const double* h_bbox4,
+                     const double* d_qx, const double* d_qy, int64_t nq, int method, int n_neighbors,
+                     double max_dist, double power, double reg, double conf_dist, double fill_value,
+                     double* d_out, void* d_ws, size_t ws_bytes, void* stream);
+
 /* ------------------------------------------ synthetic tiles (measurement) ---- */
 /* synthetic urban tile i generated ON THE DEVICE from seed 20240000 + i (the
  * reference ships no clouds and 512 x 20 M points cannot be fed from the host).  Scene model and value

@@ -543,13 +543,61 @@ def golden_alpha(upcp):
     print(f"  alpha: {sum(len(v) for k_, v in out.items() if k_.startswith('edges'))} outer edges over 16 cases")
 
 
+def ahn_cloud(seed=424242, n=60000):
+    """A synthetic AHN-like aerial cloud over tile 2386_9702 (+ 1 m buffer): ~ 20 points / m2, classes ground (2),
+    building (6), other (1), water (9), with gaps (no ground under buildings, an empty strip)."""
+    rng = np.random.default_rng(seed)
+    x = 119299.0 + rng.random(n) * 52.0
+    y = 485099.0 + rng.random(n) * 52.0
+    cls = np.full(n, 2, dtype=np.uint8)
+    z = 0.4 + 0.3 * np.sin((x - 119300) / 7.0) * np.cos((y - 485100) / 9.0) + rng.normal(0, 0.03, n)
+    for (x0, y0, x1, y1, h) in ((119305, 485104, 119318, 485117, 9.0), (119327, 485125, 119341, 485139, 14.5)):
+        inside = (x > x0) & (x < x1) & (y > y0) & (y < y1)
+        cls[inside] = 6
+        z[inside] = h + 0.02 * (x[inside] - x0) + rng.normal(0, 0.05, inside.sum())
+    other = rng.random(n) < 0.08
+    cls[other & (cls == 2)] = 1
+    z[other & (cls == 1)] += rng.random((other & (cls == 1)).sum()) * 6.0
+    strip = (y > 485142) & (y < 485144.5)
+    keep = ~strip
+    cls[(x > 119344) & (cls == 2)] = 9
+    # a few grid-exact points: positions that coincide with a raster cell centre (confusion distance)
+    x[:50] = 119300.05 + 0.1 * rng.integers(0, 500, 50); y[:50] = 485149.95 - 0.1 * rng.integers(0, 500, 50)
+    X = mm(x[keep]); Y = mm(y[keep]); Z = mm(z[keep])
+    return X.astype(np.int32), Y.astype(np.int32), Z.astype(np.int32), cls[keep]
+
+
+def golden_ahn_preprocessing(upcp):
+    """The REAL SpatialInterpolator (scipy cKDTree + the reference's loop) through the reference's
+    _get_ahn_surface arithmetic on a synthetic AHN cloud: ground (idw, 8 nearest within 1 m, power 2) and
+    building (max within 0.5 m) rasters, rounded to 2 decimals / float16 as process_ahn_las_tile stores them."""
+    from upcp.utils.interpolation import SpatialInterpolator
+    X, Y, Z, cls = ahn_cloud()
+    x, y, z = from_mm(X), from_mm(Y), from_mm(Z)
+    (x_min, y_max), (x_max, y_min) = (119300, 485150), (119350, 485100)
+    res = 0.1
+    grid_y, grid_x = np.mgrid[y_max - res / 2:y_min:-res, x_min + res / 2:x_max:res]
+    positions = np.vstack((grid_x.reshape(-1), grid_y.reshape(-1))).T
+    out = {'X': X, 'Y': Y, 'Z': Z, 'classification': cls}
+    for name, label, method, max_dist in (('ground', 2, 'idw', 1), ('building', 6, 'max', 0.5)):
+        m = cls == label
+        pts = np.vstack((x, y, z)).T[m]
+        idw = SpatialInterpolator(pts[:, 0:2], pts[:, 2], method=method)                 # REAL reference class
+        grid = idw(positions, n_neighbors=8, max_dist=max_dist, power=2., fill_value=np.nan)
+        out[name + '_f64'] = grid.reshape(grid_x.shape)
+        out[name] = np.around(grid.reshape(grid_x.shape), decimals=2).astype('float16')
+    np.savez_compressed(os.path.join(GOLDEN, 'ahn_preprocessing_golden.npz'), **out)
+    print(f"  ahn preprocessing: ground NaN {np.isnan(out['ground']).mean():.3f}, building NaN {np.isnan(out['building']).mean():.3f}")
+
+
 def main():
     os.makedirs(GOLDEN, exist_ok=True)
     upcp = ref_harness.load_reference()
     print('reference loaded from', upcp.__file__)
     steps = {'demo_data': lambda u: copy_demo_data(), 'pip': golden_pip, 'raster': golden_raster,
              'scalars': golden_scalars, 'demo': golden_demo, 'pipeline': golden_pipeline, 'objects': golden_objects,
-             'variants': golden_variants, 'config1': golden_config1, 'alpha': golden_alpha}
+             'variants': golden_variants, 'config1': golden_config1, 'alpha': golden_alpha,
+             'ahn_preprocessing': golden_ahn_preprocessing}
     wanted = sys.argv[1:] or list(steps)
     for name in wanted:
         print(name)

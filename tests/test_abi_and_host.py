@@ -260,6 +260,54 @@ def test_native_las_io_round_trip(tmp_path):
             las_utils.read_las(str(tmp_path / 'x_2386_9702.laz'))
 
 
+def _las14_bytes(fmt, n, evlr_payloads, rng):
+    """A minimal LAS 1.4 file of point format 6-8 built by hand (375-byte header, no VLRs, optional EVLRs)."""
+    import struct
+    size = {6: 30, 7: 36, 8: 38}[fmt]
+    raw = bytearray(375)
+    raw[0:4] = b'LASF'; raw[24], raw[25] = 1, 4
+    struct.pack_into('<H', raw, 94, 375); struct.pack_into('<I', raw, 96, 375); struct.pack_into('<I', raw, 100, 0)
+    raw[104] = fmt; struct.pack_into('<H', raw, 105, size); struct.pack_into('<I', raw, 107, 0)
+    struct.pack_into('<3d', raw, 131, 0.001, 0.001, 0.001); struct.pack_into('<3d', raw, 155, 0.0, 0.0, 0.0)
+    struct.pack_into('<Q', raw, 247, n)
+    rec = rng.integers(0, 255, (n, size), dtype=np.uint8)
+    body = rec.tobytes()
+    evlr = b''
+    for k, payload in enumerate(evlr_payloads):
+        evlr += struct.pack('<H16sHQ32s', 0, b'upcp_test', 100 + k, len(payload), b'an extended vlr') + payload
+    struct.pack_into('<Q', raw, 235, 375 + len(body) if evlr_payloads else 0)
+    struct.pack_into('<I', raw, 243, len(evlr_payloads))
+    return bytes(raw) + body + evlr, rec, evlr
+
+
+@pytest.mark.parametrize('fmt', [6, 7, 8])
+@pytest.mark.parametrize('n_evlr', [0, 2])
+def test_native_las14_round_trip_keeps_evlrs(tmp_path, fmt, n_evlr):
+    """LAS 1.4, point formats 6-8: adding the `label` byte moves everything behind the point records; the extended
+    VLRs are carried through and the header points at their new place."""
+    import struct
+    from urban_pointcloud_processing_b200.utils import las_io, las_utils
+    rng = np.random.default_rng(fmt * 10 + n_evlr)
+    blob, rec, evlr = _las14_bytes(fmt, 777, [bytes(rng.integers(0, 255, 300 + 50 * k, dtype=np.uint8)) for k in range(n_evlr)], rng)
+    f1 = tmp_path / 'filtered_2386_9702.las'
+    f1.write_bytes(blob)
+    las = las_io.read(str(f1))
+    assert las.header.point_count == 777 and las.n_evlrs == n_evlr and las.evlrs == evlr
+    assert np.array_equal(las.classification, rec[:, 16])
+    labels = rng.integers(0, 99, 777).astype(np.uint16)
+    f2 = str(tmp_path / 'labelled_2386_9702.las')
+    las_utils.label_and_save_las(las, labels, f2)
+    out = open(f2, 'rb').read()
+    back = las_io.read(f2)
+    assert np.array_equal(back.label, labels.astype(np.uint8)) and np.array_equal(back.records[:, :rec.shape[1]], rec)
+    start, count = struct.unpack_from('<Q', out, 235)[0], struct.unpack_from('<I', out, 243)[0]
+    assert count == n_evlr and back.n_evlrs == n_evlr and back.evlrs == evlr
+    if n_evlr:
+        assert start == back.header.offset_to_points + 777 * back.header.point_size and out[start:] == evlr
+    else:
+        assert start == 0 and len(out) == back.header.offset_to_points + 777 * back.header.point_size
+
+
 def test_bgt_point_reader_matches_reference_semantics(tmp_path):
     """utils.bgt_utils.BGTPointReader (bgt_utils.py:97-126): inclusive tile bbox with padding, type include /
     exclude lists, tuples with or without the type; and, where /root/reference is present, the reference's own

@@ -43,8 +43,10 @@ class LasData:
     """The subset of ``laspy.LasData`` the pipeline uses: ``x y z`` (scaled fp64), ``X Y Z`` (raw
     int32), ``header``, ``point_format.extra_dimension_names``, ``label``, ``write``."""
 
-    def __init__(self, header, vlrs, records, extra_dims):
+    def __init__(self, header, vlrs, records, extra_dims, evlrs=b'', n_evlrs=0):
         self.header = header
+        self.evlrs = evlrs                    # LAS 1.4 extended VLRs, kept verbatim (they follow the point records)
+        self.n_evlrs = n_evlrs
         self.vlrs = vlrs                      # list of (user_id, record_id, description, payload)
         self.records = records                # uint8 [n, point_size]
         self._extra = extra_dims              # list of (name, numpy dtype, byte offset in record)
@@ -60,6 +62,13 @@ class LasData:
     x = property(lambda self: self.X * self.header.scales[0] + self.header.offsets[0])
     y = property(lambda self: self.Y * self.header.scales[1] + self.header.offsets[1])
     z = property(lambda self: self.Z * self.header.scales[2] + self.header.offsets[2])
+
+    @property
+    def classification(self):
+        """ASPRS class of every point: 5 bits of byte 15 (formats 0-5), byte 16 (formats 6-10)."""
+        if self.header.point_format_id >= 6:
+            return self.records[:, 16].copy()
+        return self.records[:, 15] & 0x1f
 
     def _extra_view(self, name):
         for nm, dt, off in self._extra:
@@ -112,10 +121,18 @@ class LasData:
         struct.pack_into('<I', raw, 96, offset_to_points)
         struct.pack_into('<I', raw, 100, len(self.vlrs))
         struct.pack_into('<H', raw, 105, self.records.shape[1])
+        body = np.ascontiguousarray(self.records).tobytes()
+        if h.version >= (1, 4) and h.header_size >= 375:
+            # LAS 1.4: the extended VLRs follow the point records, whose size changes with the `label` byte --
+            # carry them through and point the header at where they now start
+            struct.pack_into('<Q', raw, 235, offset_to_points + len(body) if self.n_evlrs else 0)
+            struct.pack_into('<I', raw, 243, self.n_evlrs)
         with open(path, 'wb') as f:
             f.write(bytes(raw))
             f.write(vlr_blob)
-            f.write(np.ascontiguousarray(self.records).tobytes())
+            f.write(body)
+            if self.n_evlrs:
+                f.write(self.evlrs)
 
 
 def read(path):
@@ -176,7 +193,15 @@ def read(path):
     body = np.frombuffer(data, dtype=np.uint8, count=n * h.point_size, offset=h.offset_to_points)
     records = body.reshape(n, h.point_size).copy()
     extra = [e for e in extra if e[2] + e[1].itemsize <= h.point_size and e[1].kind != 'V']
-    return LasData(h, vlrs, records, extra)
+    evlrs, n_evlrs = b'', 0
+    if h.version >= (1, 4) and h.header_size >= 375:
+        start = struct.unpack_from('<Q', data, 235)[0]
+        n_evlrs = struct.unpack_from('<I', data, 243)[0]
+        if n_evlrs and h.offset_to_points + n * h.point_size <= start <= len(data):
+            evlrs = data[start:]
+        else:
+            n_evlrs = 0
+    return LasData(h, vlrs, records, extra, evlrs, n_evlrs)
 
 
 def create(points_int, scales, offsets, point_format_id=1):
