@@ -355,6 +355,34 @@ int upcp_region_grow_resume(const int32_t* d_knn, int knn, const double* d_norma
 int upcp_region_grow_end(int64_t m, uint8_t* d_region, int64_t* d_info, void* d_ws, size_t ws_bytes,
                          void* stream);
 
+/* Region growing over FIXED-RADIUS neighbourhoods: RegionGrowing._region_growing(method='radius')
+ * (region_growing.py:59-73,104-109; KDTreeFlann.search_radius_vector_3d: squared distance < radius^2,
+ * ascending, first returned index dropped).  Neighbourhoods are walked on a uniform grid, never stored.
+ * All per-point arrays are in COMPACT-id space (position within np.where(sel)[0]); the four calls share one
+ * workspace and must be given the same n, m, bounding box and radius.
+ *   prepare     builds the grid; d_flag[m] receives the curvature seed flag of every point (1 seed, 0 not,
+ *               2 undecided: the reference's unshifted single-pass covariance could fall on either side --
+ *               resolve from upcp_radius_neighbours with LAPACK); d_nb_count[m] (optional) the neighbourhood
+ *               sizes; the initial seeds (d_seed) are queued;
+ *   grow        d_extra == NULL: grows from the queued initial seeds with d_can_seed (2 = not a seed);
+ *               d_extra != NULL: resumes from those of the n_extra listed points that are in the region and
+ *               are seeds now (growth is monotone: same least fixpoint);
+ *   region      d_region[m] = 1 for the grown region, d_info[2] = region size, seeds expanded; synchronises;
+ *   neighbours  for nq query points the neighbours within radius as (x, y, z, compact id) quadruples:
+ *               query i owns d_out4[4 * d_offsets2[2i] ...] with d_offsets2[2i + 1] entries (unordered;
+ *               *d_total > cap means the buffer was too small: call again with a larger one). */
+size_t upcp_radius_ws_bytes(int64_t n, int64_t m);
+int upcp_radius_prepare(const double* d_x, const double* d_y, const double* d_z, int64_t n, const uint8_t* d_sel, int64_t m,
+                        const double* h_bbox_sel6, double radius, const double* d_normals, const uint8_t* d_seed,
+                        double threshold_curve, uint8_t* d_flag, uint32_t* d_nb_count, void* d_ws, size_t ws_bytes, void* stream);
+int upcp_radius_grow(int64_t n, int64_t m, const double* h_bbox_sel6, double radius, const uint8_t* d_can_seed,
+                     double threshold_angle_deg, const int64_t* d_extra, int64_t n_extra,
+                     void* d_ws, size_t ws_bytes, void* stream);
+int upcp_radius_region(int64_t n, int64_t m, uint8_t* d_region, int64_t* d_info, void* d_ws, size_t ws_bytes, void* stream);
+int upcp_radius_neighbours(int64_t n, int64_t m, const double* h_bbox_sel6, double radius, const int64_t* d_queries, int64_t nq,
+                           int64_t* d_offsets2, double* d_out4, int64_t cap, int64_t* d_total, void* d_ws, size_t ws_bytes,
+                           void* stream);
+
 /* Scatter a compact per-selected-point mask back to the full tile:
  * d_out[i] = d_compact[rank(i)] for selected i, 0 otherwise
  * (region_growing.py:139, `label_mask[mask_indices[region]] = True`). */

@@ -188,7 +188,20 @@ class _KDTreeFlann:
         return n, list(row[:n]), list(d2[idx][:n])
 
     def search_radius_vector_3d(self, query, radius):
-        raise NotImplementedError('open3d stand-in: radius search is not on the get_labels path')
+        """KDTreeFlann.search_radius_vector_3d: every point with squared distance < radius^2 (nanoflann
+        RadiusResultSet), ascending; ties by index.  Candidates from a scipy cKDTree ball query with a little
+        slack, the decision and the order from the exact squared distance ((dx*dx + dy*dy) + dz*dz)."""
+        from scipy.spatial import cKDTree
+        if not hasattr(self, '_tree'):
+            self._tree = cKDTree(self.pts)
+        q = np.asarray(query, dtype=np.float64).reshape(3)
+        cand = np.asarray(self._tree.query_ball_point(q, radius * (1.0 + 1e-9) + 1e-12), dtype=np.int64)
+        d = self.pts[cand] - q
+        d2 = (d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1]) + d[:, 2] * d[:, 2]
+        keep = d2 < radius * radius
+        cand, d2 = cand[keep], d2[keep]
+        order = np.lexsort((cand, d2))
+        return len(order), list(cand[order]), list(d2[order])
 
 
 def _make_modules():

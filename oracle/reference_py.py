@@ -550,6 +550,66 @@ def rg_setup(coords, max_nn=30, grow_region_knn=15, grow_region_radius=0.2, thre
     return knn, normals, can_seed
 
 
+def radius_rows(coords, radius):
+    """search_radius_vector_3d of every point (region_growing.py:104-106): lists of indices with squared
+    distance < radius^2 in ascending (squared distance, index) order."""
+    from scipy.spatial import cKDTree
+    tree = cKDTree(coords)
+    rows = []
+    for i, cand in enumerate(tree.query_ball_point(coords, radius * (1.0 + 1e-9) + 1e-12)):
+        cand = np.asarray(cand, dtype=np.int64)
+        d = coords[cand] - coords[i]
+        d2 = (d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1]) + d[:, 2] * d[:, 2]
+        keep = d2 < radius * radius
+        cand, d2 = cand[keep], d2[keep]
+        rows.append(cand[np.lexsort((cand, d2))])
+    return rows
+
+
+def curvature_of_rows(coords, rows, threshold_curve):
+    """_compute_point_curvature per point (region_growing.py:59-73): Open3D's single-pass cumulant covariance of
+    the neighbours IN THEIR ORDER, LAPACK eig (unsorted), eig_val[0] / sum < threshold."""
+    out = np.zeros(len(rows), dtype=bool)
+    with np.errstate(all='ignore'):
+        for i, row in enumerate(rows):
+            p = coords[row]
+            n = float(len(row))
+            s1 = np.cumsum(p, axis=0)[-1] / n
+            prod = np.stack([p[:, 0] * p[:, 0], p[:, 0] * p[:, 1], p[:, 0] * p[:, 2], p[:, 1] * p[:, 1], p[:, 1] * p[:, 2],
+                             p[:, 2] * p[:, 2]], axis=1)
+            s2 = np.cumsum(prod, axis=0)[-1] / n
+            cov = np.array([[s2[0] - s1[0] * s1[0], s2[1] - s1[0] * s1[1], s2[2] - s1[0] * s1[2]],
+                            [s2[1] - s1[0] * s1[1], s2[3] - s1[1] * s1[1], s2[4] - s1[1] * s1[2]],
+                            [s2[2] - s1[0] * s1[2], s2[4] - s1[1] * s1[2], s2[5] - s1[2] * s1[2]]])
+            eig_val = np.linalg.eig(cov)[0]
+            out[i] = (eig_val[0] / eig_val.sum()) < threshold_curve
+    return out
+
+
+def rg_literal_loop_rows(rows, normals, seed_ids, can_seed, threshold_angle):
+    """The `while` loop of _region_growing with variable-length neighbour lists (method='radius')."""
+    list_of_seed_ids = list(seed_ids)
+    region = list(seed_ids)
+    processed = np.full(len(rows), False)
+    processed[list_of_seed_ids] = True
+    idx = 0
+    while idx < len(list_of_seed_ids):
+        seed = list_of_seed_ids[idx]
+        seed_normal = normals[seed]
+        for neighbor_id in rows[seed][1:]:
+            if processed[neighbor_id]:
+                continue
+            if vector_angle(seed_normal, normals[neighbor_id]) < threshold_angle:
+                region.append(neighbor_id)
+                processed[neighbor_id] = True
+                if can_seed[neighbor_id]:
+                    list_of_seed_ids.append(neighbor_id)
+        idx = idx + 1
+    out = np.zeros(len(rows), dtype=bool)
+    out[region] = True
+    return out
+
+
 def rg_literal_loop(knn, normals, seed_ids, can_seed, threshold_angle):
     """The Python `while` loop of _region_growing, literally (region_growing.py:94-139)."""
     list_of_seed_ids = list(seed_ids)
@@ -580,8 +640,9 @@ def rg_literal_loop(knn, normals, seed_ids, can_seed, threshold_angle):
 
 def region_growing_labels(points, labels, label, exclude_labels=(), threshold_angle=20,
                           threshold_curve=1.0, max_nn=30, grow_region_knn=15, grow_region_radius=0.2,
-                          literal=False, angle_tol=0.0, return_near=False):
-    """RegionGrowing.get_labels (region_growing/region_growing.py:143-170)."""
+                          literal=False, angle_tol=0.0, return_near=False, method='knn'):
+    """RegionGrowing.get_labels (region_growing/region_growing.py:143-170); method='radius' is what
+    _region_growing('radius') computes (:104-106, only reachable by calling it directly)."""
     mask = np.ones((len(labels),), dtype=bool)
     for exclude_label in exclude_labels:
         mask = mask & (labels != exclude_label)
@@ -591,6 +652,14 @@ def region_growing_labels(points, labels, label, exclude_labels=(), threshold_an
     near_full = np.zeros(len(mask), dtype=bool)
     if len(mask_indices) > 0 and len(seed_ids) > 0:
         coords = np.ascontiguousarray(points[mask, :3])
+        if method == 'radius':
+            rows = radius_rows(coords, grow_region_radius)
+            normals = natives.normals_hybrid(coords, grow_region_radius, max_nn)
+            can_seed = curvature_of_rows(coords, rows, threshold_curve)
+            region = rg_literal_loop_rows(rows, normals, seed_ids.tolist(), can_seed, threshold_angle)
+            label_mask[mask_indices[region]] = True
+            labels[label_mask] = label
+            return (labels, near_full) if return_near else labels
         knn, normals, can_seed = rg_setup(coords, max_nn, grow_region_knn, grow_region_radius,
                                           threshold_curve)
         if literal:

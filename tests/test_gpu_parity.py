@@ -954,6 +954,36 @@ def test_region_growing_matches_oracle(n, seed):
     assert np.array_equal(again, got)
 
 
+@pytest.mark.parametrize('radius', [0.2, 0.1, 0.5])
+def test_region_growing_radius_method_matches_oracle(radius):
+    """RegionGrowing._region_growing('radius') (region_growing.py:104-106: growth and curvature test over everything
+    within grow_region_radius) against the oracle's literal loop -- which equals the REAL reference class run over
+    the restated natives (checked when the fixture logic was written, oracle/ref_harness.search_radius_vector_3d)."""
+    tile, pts, labels = _rg_cloud(250_000 if radius < 0.5 else 120_000, 57)
+    labels[(labels == 10) & (np.random.default_rng(5).random(len(labels)) < 0.9)] = 0      # few seeds: the region has to GROW
+    want = R.region_growing_labels(pts, labels.copy(), 10, exclude_labels=(9,), grow_region_radius=radius, method='radius')
+    rg = RegionGrowing(10, exclude_labels=(9,), grow_region_radius=radius)
+    rg._set_mask(labels)
+    rg._convert_input_cloud(pts)
+    mask = rg._region_growing('radius')
+    got = labels.copy()
+    got[mask] = 10
+    print(f'radius {radius}: region {int((want == 10).sum())} (seeds {int((labels == 10).sum())}), {int((got != want).sum())} labels differ, '
+          f'{rg.last_stats["n_curvature_on_host"]} curvature flags resolved on the host in {rg.last_stats["rounds"]} rounds')
+    assert np.array_equal(got, want) and (want == 10).sum() > (labels == 10).sum() + 1000
+    # a curvature threshold inside the range of the ratios: many more points go through the exact host path
+    if radius == 0.2:
+        want = R.region_growing_labels(pts, labels.copy(), 10, exclude_labels=(9,), threshold_curve=0.45, method='radius')
+        rg = RegionGrowing(10, exclude_labels=(9,), threshold_curve=0.45)
+        rg._set_mask(labels); rg._convert_input_cloud(pts)
+        got = labels.copy()
+        got[rg._region_growing('radius')] = 10
+        print(f'threshold_curve 0.45: {int((got != want).sum())} labels differ, {rg.last_stats["n_curvature_on_host"]} flags on the host')
+        assert np.array_equal(got, want)
+    with pytest.raises(ValueError):
+        RegionGrowing(10, max_nn=50)
+
+
 def test_region_growing_parameters_and_edge_cases():
     tile, pts, labels = _rg_cloud(50000, 53)
     for kw in (dict(threshold_angle=5), dict(threshold_angle=60, grow_region_knn=8, max_nn=12, grow_region_radius=0.5),

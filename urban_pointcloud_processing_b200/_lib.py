@@ -101,6 +101,14 @@ _PROTOTYPES = {
     'upcp_region_grow_resume': (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int64, c_void_p,
                                         c_int64, c_double, c_void_p, c_size_t, c_void_p]),
     'upcp_region_grow_end': (c_int, [c_int64, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    'upcp_radius_ws_bytes': (c_size_t, [c_int64, c_int64]),
+    'upcp_radius_prepare': (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int64, POINTER(c_double), c_double,
+                                    c_void_p, c_void_p, c_double, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    'upcp_radius_grow': (c_int, [c_int64, c_int64, POINTER(c_double), c_double, c_void_p, c_double, c_void_p, c_int64,
+                                 c_void_p, c_size_t, c_void_p]),
+    'upcp_radius_region': (c_int, [c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    'upcp_radius_neighbours': (c_int, [c_int64, c_int64, POINTER(c_double), c_double, c_void_p, c_int64, c_void_p, c_void_p,
+                                       c_int64, c_void_p, c_void_p, c_size_t, c_void_p]),
     'upcp_compact_ws_bytes': (c_size_t, [c_int64]),
     'upcp_mask_scatter': (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     'upcp_mask_gather': (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,

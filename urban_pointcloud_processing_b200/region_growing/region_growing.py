@@ -243,6 +243,80 @@ def region_grow_overlapped(d_knn, d_normals, d_seed, d_flag, d_cov, threshold_cu
     return d_region, d_info, n_host
 
 
+def _exact_radius_curvature(q, nb, threshold_curve):
+    """The reference's curvature test for ONE point from its radius neighbourhood (region_growing.py:59-73):
+    neighbours in ascending (squared distance, compact id) order, Open3D's single-pass cumulant covariance of
+    their raw coordinates in that order, LAPACK eig (unsorted), eig_val[0] / sum < threshold."""
+    d = nb[:, :3] - q
+    d2 = (d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1]) + d[:, 2] * d[:, 2]
+    p = nb[np.lexsort((nb[:, 3], d2)), :3]
+    n = float(len(p))
+    s1 = np.cumsum(p, axis=0)[-1] / n
+    prod = np.stack([p[:, 0] * p[:, 0], p[:, 0] * p[:, 1], p[:, 0] * p[:, 2], p[:, 1] * p[:, 1], p[:, 1] * p[:, 2],
+                     p[:, 2] * p[:, 2]], axis=1)
+    s2 = np.cumsum(prod, axis=0)[-1] / n
+    cov = np.array([[s2[0] - s1[0] * s1[0], s2[1] - s1[0] * s1[1], s2[2] - s1[0] * s1[2]],
+                    [s2[1] - s1[0] * s1[1], s2[3] - s1[1] * s1[1], s2[4] - s1[1] * s1[2]],
+                    [s2[2] - s1[0] * s1[2], s2[4] - s1[1] * s1[2], s2[5] - s1[2] * s1[2]]])
+    with np.errstate(all='ignore'):
+        eig_val = np.linalg.eig(cov)[0]
+        return bool((eig_val[0] / eig_val.sum()) < threshold_curve)
+
+
+def region_grow_radius_device(tile, d_sel, m, bbox_sel, d_normals, d_seed, radius, threshold_angle, threshold_curve):
+    """Least fixpoint of the growth over fixed-radius neighbourhoods (``_region_growing('radius')``,
+    region_growing.py:104-106) on the device; all arrays in compact-id space.  Curvature flags the device
+    cannot decide (see csrc/radius.cu) are resolved on the host from the exact ordered neighbour lists -- only
+    for points the growth actually reaches -- and the growth resumed until nothing is left undecided.
+    Returns (d_region uint8 [m], stats dict)."""
+    lib = _lib.load()
+    device = tile.device
+    bbox_arr = (ctypes.c_double * 6)(*[float(v) for v in bbox_sel])
+    ws = dev.workspace(device, slot=3).get(lib.upcp_radius_ws_bytes(tile.n, m))
+    d_flag = torch.empty(m, dtype=torch.uint8, device=device)
+    _lib.check(lib.upcp_radius_prepare(dev.ptr(tile.x), dev.ptr(tile.y), dev.ptr(tile.z), tile.n, dev.ptr(d_sel), m, bbox_arr,
+                                       float(radius), dev.ptr(d_normals), dev.ptr(d_seed), float(threshold_curve),
+                                       dev.ptr(d_flag), None, dev.ptr(ws), ws.numel(), dev.stream_ptr()), 'upcp_radius_prepare')
+    d_region = torch.empty(m, dtype=torch.uint8, device=device)
+    d_info = torch.zeros(2, dtype=torch.int64, device=device)
+    d_extra, n_host, rounds = None, 0, 0
+    # compact id -> coordinates of the few undecided points (queries of the host resolution)
+    d_ids = torch.nonzero(d_sel).flatten() if d_sel is not None else None
+    while True:
+        rounds += 1
+        _lib.check(lib.upcp_radius_grow(tile.n, m, bbox_arr, float(radius), dev.ptr(d_flag), float(threshold_angle),
+                                        dev.ptr(d_extra), 0 if d_extra is None else int(d_extra.numel()),
+                                        dev.ptr(ws), ws.numel(), dev.stream_ptr()), 'upcp_radius_grow')
+        _lib.check(lib.upcp_radius_region(tile.n, m, dev.ptr(d_region), dev.ptr(d_info), dev.ptr(ws), ws.numel(),
+                                          dev.stream_ptr()), 'upcp_radius_region')
+        d_und = torch.nonzero((d_flag == 2) & (d_region != 0)).flatten()
+        nq = int(d_und.numel())
+        if nq == 0:
+            break
+        n_host += nq
+        d_off = torch.empty((nq, 2), dtype=torch.int64, device=device)
+        d_tot = torch.zeros(1, dtype=torch.int64, device=device)
+        cap = max(4096, 512 * nq)
+        while True:
+            d_nb = torch.empty((cap, 4), dtype=torch.float64, device=device)
+            _lib.check(lib.upcp_radius_neighbours(tile.n, m, bbox_arr, float(radius), dev.ptr(d_und), nq, dev.ptr(d_off),
+                                                  dev.ptr(d_nb), cap, dev.ptr(d_tot), dev.ptr(ws), ws.numel(),
+                                                  dev.stream_ptr()), 'upcp_radius_neighbours')
+            total = int(d_tot.item())
+            if total <= cap:
+                break
+            cap = total
+        off, nb = d_off.cpu().numpy(), d_nb[:total].cpu().numpy()
+        orig = d_ids[d_und] if d_ids is not None else d_und
+        q = torch.stack((tile.x[orig], tile.y[orig], tile.z[orig]), dim=1).cpu().numpy()
+        res = np.array([_exact_radius_curvature(q[i], nb[off[i, 0]:off[i, 0] + off[i, 1]], threshold_curve) for i in range(nq)])
+        d_flag[d_und] = torch.from_numpy(res.astype(np.uint8)).to(device)
+        d_extra = d_und
+        if not res.any():
+            break
+    return d_region, {'n_curvature_on_host': n_host, 'rounds': rounds, '_d_info': d_info}
+
+
 def mask_gather(d_sel, d_full, m):
     lib = _lib.load()
     n = d_sel.numel()
@@ -286,7 +360,39 @@ class RegionGrowing(AbstractProcessor):
         self.grow_region_radius = grow_region_radius
         self.exclude_labels = exclude_labels
         self.cell_size = None           # search-grid cell size; None = radius / 2
+        self.method = 'knn'             # 'radius': what the reference computes through _region_growing('radius')
         self.last_stats = {}
+        if max(int(grow_region_knn), int(max_nn)) > 32:
+            # (the reference accepts any value; the per-query tier of the search keeps one neighbour per lane)
+            raise ValueError('RegionGrowing on the B200 extension supports grow_region_knn and max_nn up to 32 '
+                             f'(got grow_region_knn={grow_region_knn}, max_nn={max_nn})')
+
+    # -- the reference's internal protocol (get_labels = _set_mask + _convert_input_cloud + _region_growing,
+    # region_growing.py:164-168), kept because method='radius' is only reachable through it
+    def _set_mask(self, las_labels):
+        self._las_labels = np.asarray(las_labels)
+        mask = np.ones((len(self._las_labels),), dtype=bool)
+        for exclude_label in self.exclude_labels:
+            mask = mask & (self._las_labels != exclude_label)
+        self.list_of_seed_ids = np.where(self._las_labels[mask] == self.label)[0].tolist()
+        self.mask_indices = np.where(mask)[0]
+        self.label_mask = np.zeros(len(mask), dtype=bool)
+        self.mask = mask
+
+    def _convert_input_cloud(self, las):
+        self._points = las
+
+    def _region_growing(self, method='knn'):
+        """Label mask (numpy bool[N]) of the grown region, for the cloud / labels handed to
+        ``_convert_input_cloud`` / ``_set_mask``."""
+        saved, self.method = self.method, method
+        try:
+            tile = dev.get_tile(self._points)
+            d_labels = dev.upload_labels(self._las_labels, tile.device)
+            self.label_mask = dev.download_mask(self._label_mask_device(tile, d_labels, None))
+        finally:
+            self.method = saved
+        return self.label_mask
 
     def _label_mask_device(self, tile, d_labels, d_mask, tilecode=None):
         logger.info('KDTree based Region Growing ' + f'(label={self.label}, {Labels.get_str(self.label)}).')
@@ -304,6 +410,18 @@ class RegionGrowing(AbstractProcessor):
         if n_seeds == 0:
             logger.debug('Input point cloud does not contain any seed points.')
             return d_label_mask
+        if self.method == 'radius':
+            # normals from the hybrid search as always (region_growing.py:89-92); neighbourhoods of the growth and of
+            # the curvature test = everything within grow_region_radius (:61-63,104-106)
+            _, _, d_normals, _, _ = knn_normals_device(tile, d_sel, m, bbox_sel, 1, self.max_nn, self.grow_region_radius,
+                                                       cell_size=self.cell_size, want_cov=False, want_curv=False)
+            d_seed = mask_gather(d_sel, d_seed_full, m)
+            d_region, stats = region_grow_radius_device(tile, d_sel, m, bbox_sel, d_normals, d_seed, self.grow_region_radius,
+                                                        self.threshold_angle, self.threshold_curve)
+            self.last_stats = dict(stats, n_selected=m, n_seeds=n_seeds)
+            return mask_scatter(d_sel, d_region)
+        if self.method != 'knn':
+            raise ValueError(f"method must be 'knn' or 'radius' (got {self.method!r})")
         # everything below lives in the search grid's spatial order (close points, close rows)
         d_knn, d_normals, d_cov, d_flag, d_order = knn_normals_sorted_device(
             tile, d_sel, m, bbox_sel, self.grow_region_knn, self.max_nn, self.grow_region_radius,
