@@ -437,6 +437,18 @@ int upcp_prism_clip(const double* d_x, const double* d_y, const double* d_z, int
                     const uint8_t* d_sel, const double* d_ring_xy, const int32_t* d_ring_off,
                     const double* d_zrange, int32_t n_prisms, uint8_t* d_out, void* stream);
 
+/* ---------------------------------------- LAZ ingest ("next" row 1), host ---- */
+/* Decode LASzip-compressed point records (what laspy[lazrs] does for las_utils.read_las,
+ * las_utils.py:118-120).  Host code, no device work.  Covers the "pointwise chunked" compressor with the
+ * version-2 item codecs of point formats 0-3 (POINT10, GPSTIME11, RGB12, extra BYTEs); LAS 1.4 layered
+ * items return UPCP_E_CAPACITY.
+ *   h_vlr / vlr_bytes : payload of the "laszip encoded" VLR (record id 22204);
+ *   h_data            : the file from offset-to-point-data to its end (data_bytes), which sits at
+ *                       data_file_offset in the file (the chunk table is addressed by file position);
+ *   h_out             : n_points * point_size bytes, the records as an uncompressed .las holds them. */
+int upcp_laz_decode(const uint8_t* h_vlr, int32_t vlr_bytes, const uint8_t* h_data, int64_t data_bytes,
+                    int64_t data_file_offset, int64_t n_points, int32_t point_size, uint8_t* h_out);
+
 /* ------------------------------------ AHN preprocessing ("next" row 4) ---- */
 /* SpatialInterpolator.__call__ (reference utils/interpolation.py:156-308) for 2-D data, as
  * preprocessing/ahn_preprocessing.py:129-236 uses it to rasterise an AHN cloud: for every position the

@@ -46,11 +46,11 @@ def pack(mask):
 def copy_demo_data():
     dst = os.path.join(GOLDEN, 'demo')
     os.makedirs(dst, exist_ok=True)
-    for rel in ('ahn/ahn_2386_9702.npz', 'bgt/bgt_buildings_demo.csv', 'bgt/bgt_roads_demo.csv'):
+    for rel in ('ahn/ahn_2386_9702.npz', 'ahn/ahn_2386_9702.laz', 'bgt/bgt_buildings_demo.csv', 'bgt/bgt_roads_demo.csv'):
         shutil.copyfile(os.path.join(REF_DATA, rel), os.path.join(dst, os.path.basename(rel)))
     with open(os.path.join(dst, 'README.md'), 'w') as f:
         f.write('Demo DATA fixtures copied verbatim from the reference checkout '
-                '(`datasets/ahn/ahn_2386_9702.npz`, `datasets/bgt/bgt_buildings_demo.csv`, '
+                '(`datasets/ahn/ahn_2386_9702.npz`, `datasets/ahn/ahn_2386_9702.laz`, `datasets/bgt/bgt_buildings_demo.csv`, '
                 '`datasets/bgt/bgt_roads_demo.csv`; Amsterdam-AI-Team/Urban_PointCloud_Processing, '
                 'GPL-3.0; sources: AHN / BGT open data).  Data only, no source code.\n')
 

@@ -766,6 +766,22 @@ def test_ahn_preprocessing_matches_reference_golden(golden, tmp_path):
         assert np.array_equal(np.isfinite(got), ok) and np.abs(got[ok] - want[ok]).max() < 1e-11
 
 
+def test_ahn_preprocessing_of_the_demo_laz_equals_the_shipped_npz(tmp_path):
+    """The reference ships datasets/ahn/ahn_2386_9702.laz AND the ahn_2386_9702.npz it made from it
+    (notebooks/1.AHN_preprocessing).  Native LAZ decode (csrc/laz.cu) + process_ahn_las_tile on the GPU must
+    reproduce that file: x, y, ground, building, all 250 000 float16 cells of both surfaces."""
+    from urban_pointcloud_processing_b200.preprocessing import ahn_preprocessing as AP
+    demo = os.path.join(GOLDEN, 'demo')
+    out = np.load(AP.process_ahn_las_tile(os.path.join(demo, 'ahn_2386_9702.laz'), out_folder=str(tmp_path)))
+    ref = np.load(os.path.join(demo, 'ahn_2386_9702.npz'))
+    assert np.array_equal(out['x'], ref['x']) and np.array_equal(out['y'], ref['y'])
+    for name in ('ground', 'building'):
+        assert out[name].dtype == ref[name].dtype == np.float16
+        same = (out[name] == ref[name]) | (np.isnan(out[name]) & np.isnan(ref[name]))
+        print(f'{name}: {int((~same).sum())} of {same.size} cells differ from the raster the reference shipped')
+        assert same.all()
+
+
 def test_layer_lcc_dense_matches_oracle():
     """A cloud dense enough for the layers to actually grow (the 60 k golden tile is sparse)."""
     tile = synthetic.make_tile(1500000, seed=31, facade_fraction=0.6)

@@ -4,6 +4,7 @@
 #include <vector>
 #include <cstdio>
 #include <cstring>
+#include <nvtx3/nvToolsExt.h>          // header-only NVTX v3: ranges cost nothing unless a tool is attached
 #include "common.cuh"
 
 namespace upcp {
@@ -61,7 +62,13 @@ static std::atomic<int> g_prof_on{0};
 static std::vector<ProfBracket> g_prof[UPCP_PROF_SLOTS];
 static thread_local cudaEvent_t g_prof_open[UPCP_PROF_SLOTS];   // per host thread: begin / end pair up on the thread's own stream
 
+static const char* const kSlotNames[UPCP_PROF_SLOTS] = {
+    "raster_kernel", "pip_query_kernel", "radix_sort (hist+scan+scatter)", "cc_link_kernel",
+    "knn_stage (build+search+epilogue)", "grow_kernel", "knn_build", "knn_search (block tiers + per-query tier)",
+    "knn_epilogue_kernel"};
+
 void prof_begin(int slot, cudaStream_t st) {
+    nvtxRangePushA(kSlotNames[slot]);          // NVTX range named like the bracket (nsys / ncu --nvtx)
     if (!g_prof_on.load(std::memory_order_relaxed)) return;
     std::lock_guard<std::mutex> lk(g_prof_mu);
     cudaEvent_t e;
@@ -71,6 +78,7 @@ void prof_begin(int slot, cudaStream_t st) {
 }
 
 void prof_end(int slot, cudaStream_t st, int64_t units) {
+    nvtxRangePop();
     if (!g_prof_on.load(std::memory_order_relaxed)) return;
     std::lock_guard<std::mutex> lk(g_prof_mu);
     if (!g_prof_open[slot]) return;
@@ -113,10 +121,7 @@ int upcp_prof_read(int slot, double* total_ms, int64_t* launches, int64_t* units
 }
 
 const char* upcp_prof_slot_name(int slot) {
-    static const char* names[UPCP_PROF_SLOTS] = {"raster_kernel", "pip_query_kernel", "radix_sort (hist+scan+scatter)",
-                                                 "cc_link_kernel", "knn_stage (build+search+epilogue)", "grow_kernel",
-                                                 "knn_build", "knn_search (block tiers + per-query tier)",
-                                                 "knn_epilogue_kernel"};
+    const char* const* names = upcp::kSlotNames;
     return (slot >= 0 && slot < UPCP_PROF_SLOTS) ? names[slot] : "";
 }
 

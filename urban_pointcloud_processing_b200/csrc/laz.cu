@@ -1,0 +1,562 @@
+// "Next" row 1 -- LAZ ingest: decoder for LASzip-compressed point data, host code.
+//
+// The reference reads its tiles with laspy[lazrs] (las_utils.read_las, reference utils/las_utils.py:118-120;
+// every CycloMedia tile and the demo AHN clouds are .laz).  Neither laspy nor a LASzip library is in this
+// image, and the format is a published one (M. Isenburg, "LASzip: lossless compression of LiDAR data", PE&RS
+// 2013; LASzip 2.x / 3.x open-source reference implementation): an adaptive arithmetic coder (A. Said's FastAC)
+// driven by per-field context models.  This file restates the DECODER for the "pointwise chunked" compressor
+// (type 2) with the version-2 item codecs of point formats 0-3: POINT10 (20 bytes), GPSTIME11, RGB12 and BYTE
+// (extra bytes).  Output = the uncompressed point records, byte for byte what an uncompressed .las holds.
+// LAS 1.4 "layered" items (formats 6-10, compressor 3) are not covered.
+//
+// Conformance is pinned on the two demo clouds of the reference (datasets/ahn/ahn_*.laz, format 1, 43 536 and
+// 45 345 points): decoded coordinate ranges equal the header's min / max exactly, the returns histogram equals
+// the header's, and the rasters computed from the decoded points equal the ahn_*.npz files the reference
+// shipped beside them (tests/test_abi_and_host.py, tests/test_gpu_parity.py).
+#include <stdint.h>
+#include <string.h>
+#include <new>
+#include <vector>
+#include "common.cuh"
+
+namespace upcp {
+namespace laz {
+
+typedef uint8_t U8; typedef uint16_t U16; typedef uint32_t U32; typedef int32_t I32; typedef int64_t I64; typedef uint64_t U64;
+
+constexpr U32 AC_MinLength = 0x01000000u, AC_MaxLength = 0xFFFFFFFFu;
+constexpr U32 BM_LengthShift = 13, BM_MaxCount = 1u << BM_LengthShift;
+constexpr U32 DM_LengthShift = 15, DM_MaxCount = 1u << DM_LengthShift;
+
+struct ByteStream {
+    const U8* p; const U8* end; bool overrun;
+    U8 get() { if (p < end) return *p++; overrun = true; return 0; }
+};
+
+struct BitModel {
+    U32 update_cycle, bits_until_update, bit_0_prob, bit_0_count, bit_count;
+    void init() { bit_0_count = 1; bit_count = 2; bit_0_prob = 1u << (BM_LengthShift - 1); update_cycle = bits_until_update = 4; }
+    void update() {
+        if ((bit_count += update_cycle) > BM_MaxCount) {
+            bit_count = (bit_count + 1) >> 1;
+            bit_0_count = (bit_0_count + 1) >> 1;
+            if (bit_0_count == bit_count) ++bit_count;
+        }
+        const U32 scale = 0x80000000u / bit_count;
+        bit_0_prob = (bit_0_count * scale) >> (31 - BM_LengthShift);
+        update_cycle = (5 * update_cycle) >> 2;
+        if (update_cycle > 64) update_cycle = 64;
+        bits_until_update = update_cycle;
+    }
+};
+
+struct SymbolModel {
+    U32 symbols = 0, last_symbol = 0, table_size = 0, table_shift = 0, total_count = 0, update_cycle = 0, symbols_until_update = 0;
+    std::vector<U32> distribution, symbol_count, decoder_table;
+    void create(U32 n) { symbols = n; }
+    void init() {
+        if (distribution.empty()) {
+            last_symbol = symbols - 1;
+            if (symbols > 16) {
+                U32 table_bits = 3;
+                while (symbols > (1u << (table_bits + 2))) ++table_bits;
+                table_size = 1u << table_bits;
+                table_shift = DM_LengthShift - table_bits;
+                decoder_table.assign(table_size + 2, 0);
+            } else { table_size = table_shift = 0; }
+            distribution.assign(symbols, 0);
+            symbol_count.assign(symbols, 0);
+        }
+        total_count = 0;
+        update_cycle = symbols;
+        for (U32 k = 0; k < symbols; ++k) symbol_count[k] = 1;
+        update();
+        symbols_until_update = update_cycle = (symbols + 6) >> 1;
+    }
+    void update() {
+        if ((total_count += update_cycle) > DM_MaxCount) {
+            total_count = 0;
+            for (U32 n = 0; n < symbols; ++n) total_count += (symbol_count[n] = (symbol_count[n] + 1) >> 1);
+        }
+        U32 sum = 0, s = 0;
+        const U32 scale = 0x80000000u / total_count;
+        if (table_size == 0) {
+            for (U32 k = 0; k < symbols; ++k) { distribution[k] = (scale * sum) >> (31 - DM_LengthShift); sum += symbol_count[k]; }
+        } else {
+            for (U32 k = 0; k < symbols; ++k) {
+                distribution[k] = (scale * sum) >> (31 - DM_LengthShift);
+                sum += symbol_count[k];
+                const U32 w = distribution[k] >> table_shift;
+                while (s < w) decoder_table[++s] = k - 1;
+            }
+            decoder_table[0] = 0;
+            while (s <= table_size) decoder_table[++s] = symbols - 1;
+        }
+        update_cycle = (5 * update_cycle) >> 2;
+        const U32 max_cycle = (symbols + 6) << 3;
+        if (update_cycle > max_cycle) update_cycle = max_cycle;
+        symbols_until_update = update_cycle;
+    }
+};
+
+struct Decoder {
+    ByteStream* in = nullptr;
+    U32 value = 0, length = 0;
+    void init(ByteStream* s) {
+        in = s;
+        length = AC_MaxLength;
+        value = ((U32)in->get() << 24); value |= ((U32)in->get() << 16); value |= ((U32)in->get() << 8); value |= (U32)in->get();
+    }
+    void renorm() { do { value = (value << 8) | in->get(); } while ((length <<= 8) < AC_MinLength); }
+    U32 decodeBit(BitModel* m) {
+        const U32 x = m->bit_0_prob * (length >> BM_LengthShift);
+        const U32 sym = (value >= x);
+        if (sym == 0) { length = x; ++m->bit_0_count; } else { value -= x; length -= x; }
+        if (length < AC_MinLength) renorm();
+        if (--m->bits_until_update == 0) m->update();
+        return sym;
+    }
+    U32 decodeSymbol(SymbolModel* m) {
+        U32 n, sym, x, y = length;
+        if (m->table_size) {
+            const U32 dv = value / (length >>= DM_LengthShift);
+            const U32 t = dv >> m->table_shift;
+            sym = m->decoder_table[t];
+            n = m->decoder_table[t + 1] + 1;
+            while (n > sym + 1) {
+                const U32 k = (sym + n) >> 1;
+                if (m->distribution[k] > dv) n = k; else sym = k;
+            }
+            x = m->distribution[sym] * length;
+            if (sym != m->last_symbol) y = m->distribution[sym + 1] * length;
+        } else {
+            x = sym = 0;
+            length >>= DM_LengthShift;
+            U32 k = (n = m->symbols) >> 1;
+            do {
+                const U32 z = length * m->distribution[k];
+                if (z > value) { n = k; y = z; } else { sym = k; x = z; }
+            } while ((k = (sym + n) >> 1) != sym);
+        }
+        value -= x;
+        length = y - x;
+        if (length < AC_MinLength) renorm();
+        ++m->symbol_count[sym];
+        if (--m->symbols_until_update == 0) m->update();
+        return sym;
+    }
+    U32 readBits(U32 bits) {
+        if (bits > 19) {
+            const U32 lo = readShort();
+            bits -= 16;
+            const U32 hi = readBits(bits) << 16;
+            return hi | lo;
+        }
+        const U32 sym = value / (length >>= bits);
+        value -= length * sym;
+        if (length < AC_MinLength) renorm();
+        return sym;
+    }
+    U32 readShort() {
+        const U32 sym = value / (length >>= 16);
+        value -= length * sym;
+        if (length < AC_MinLength) renorm();
+        return sym & 0xffffu;
+    }
+    U32 readInt() { const U32 lo = readShort(); const U32 hi = readShort(); return (hi << 16) | lo; }
+};
+
+struct IntegerCompressor {
+    Decoder* dec = nullptr;
+    U32 k = 0, contexts = 1, bits_high = 8, bits = 16, corr_bits = 0, corr_range = 0;
+    I32 corr_min = 0, corr_max = 0;
+    std::vector<SymbolModel> mBits, mCorrector;      // mCorrector[0] is unused (bit model below)
+    BitModel mCorrector0;
+    void create(Decoder* d, U32 bits_, U32 contexts_ = 1, U32 bits_high_ = 8) {
+        dec = d; bits = bits_; contexts = contexts_; bits_high = bits_high_;
+        if (bits && bits < 32) {
+            corr_bits = bits; corr_range = 1u << bits;
+            corr_min = -((I32)(corr_range / 2)); corr_max = corr_min + (I32)corr_range - 1;
+        } else { corr_bits = 32; corr_range = 0; corr_min = INT32_MIN; corr_max = INT32_MAX; }
+        mBits.assign(contexts, SymbolModel());
+        for (auto& m : mBits) m.create(corr_bits + 1);
+        mCorrector.assign(corr_bits + 1, SymbolModel());
+        for (U32 i = 1; i <= corr_bits; ++i) mCorrector[i].create(i <= bits_high ? (1u << i) : (1u << bits_high));
+    }
+    void init() {
+        for (auto& m : mBits) m.init();
+        mCorrector0.init();
+        for (U32 i = 1; i <= corr_bits; ++i) mCorrector[i].init();
+    }
+    I32 readCorrector(SymbolModel* mb) {
+        I32 c;
+        k = dec->decodeSymbol(mb);
+        if (k) {
+            if (k < 32) {
+                if (k <= bits_high) c = (I32)dec->decodeSymbol(&mCorrector[k]);
+                else {
+                    const U32 k1 = k - bits_high;
+                    c = (I32)dec->decodeSymbol(&mCorrector[k]);
+                    const I32 c1 = (I32)dec->readBits(k1);
+                    c = (I32)(((U32)c << k1) | (U32)c1);
+                }
+                if (c >= (I32)(1u << (k - 1))) c += 1; else c -= (I32)((1u << k) - 1);
+            } else c = corr_min;
+        } else c = (I32)dec->decodeBit(&mCorrector0);
+        return c;
+    }
+    I32 decompress(I32 pred, U32 context = 0) {
+        I32 real = (I32)((U32)pred + (U32)readCorrector(&mBits[context]));
+        if (real < 0) real = (I32)((U32)real + corr_range);
+        else if ((U32)real >= corr_range) real = (I32)((U32)real - corr_range);
+        return real;
+    }
+    U32 getK() const { return k; }
+};
+
+struct StreamingMedian5 {
+    I32 values[5]; bool high;
+    void init() { values[0] = values[1] = values[2] = values[3] = values[4] = 0; high = true; }
+    void add(I32 v) {
+        if (high) {
+            if (v < values[2]) {
+                values[4] = values[3]; values[3] = values[2];
+                if (v < values[0]) { values[2] = values[1]; values[1] = values[0]; values[0] = v; }
+                else if (v < values[1]) { values[2] = values[1]; values[1] = v; }
+                else values[2] = v;
+            } else {
+                if (v < values[3]) { values[4] = values[3]; values[3] = v; } else values[4] = v;
+                high = false;
+            }
+        } else {
+            if (values[2] < v) {
+                values[0] = values[1]; values[1] = values[2];
+                if (values[4] < v) { values[2] = values[3]; values[3] = values[4]; values[4] = v; }
+                else if (values[3] < v) { values[2] = values[3]; values[3] = v; }
+                else values[2] = v;
+            } else {
+                if (values[1] < v) { values[0] = values[1]; values[1] = v; } else values[0] = v;
+                high = true;
+            }
+        }
+    }
+    I32 get() const { return values[2]; }
+};
+
+static const U8 number_return_map[8][8] = {
+    {15, 14, 13, 12, 11, 10, 9, 8}, {14, 0, 1, 3, 6, 10, 10, 9}, {13, 1, 2, 4, 7, 11, 11, 10}, {12, 3, 4, 5, 8, 12, 12, 11},
+    {11, 6, 7, 8, 9, 13, 13, 12}, {10, 10, 11, 12, 13, 14, 14, 13}, {9, 10, 11, 12, 13, 14, 15, 14}, {8, 9, 10, 11, 12, 13, 14, 15}};
+static const U8 number_return_level[8][8] = {
+    {0, 1, 2, 3, 4, 5, 6, 7}, {1, 0, 1, 2, 3, 4, 5, 6}, {2, 1, 0, 1, 2, 3, 4, 5}, {3, 2, 1, 0, 1, 2, 3, 4},
+    {4, 3, 2, 1, 0, 1, 2, 3}, {5, 4, 3, 2, 1, 0, 1, 2}, {6, 5, 4, 3, 2, 1, 0, 1}, {7, 6, 5, 4, 3, 2, 1, 0}};
+
+static inline U8 u8_fold(I32 n) { return (U8)(n & 0xff); }
+static inline U8 u8_clamp(I32 n) { return n <= 0 ? 0 : (n >= 255 ? 255 : (U8)n); }
+
+struct ItemReader {
+    virtual ~ItemReader() {}
+    virtual void init(const U8* item) = 0;
+    virtual void read(U8* item) = 0;
+};
+
+struct Point10Reader : ItemReader {
+    Decoder* dec;
+    U8 last_item[20];
+    U16 last_intensity[16];
+    StreamingMedian5 last_x_diff_median5[16], last_y_diff_median5[16];
+    I32 last_height[8];
+    SymbolModel m_changed_values, m_scan_angle_rank[2];
+    std::vector<SymbolModel> m_bit_byte, m_classification, m_user_data;
+    std::vector<char> has_bit_byte, has_classification, has_user_data;
+    IntegerCompressor ic_intensity, ic_point_source_ID, ic_dx, ic_dy, ic_z;
+    explicit Point10Reader(Decoder* d) : dec(d) {
+        m_changed_values.create(64);
+        m_scan_angle_rank[0].create(256); m_scan_angle_rank[1].create(256);
+        m_bit_byte.assign(256, SymbolModel()); m_classification.assign(256, SymbolModel()); m_user_data.assign(256, SymbolModel());
+        ic_intensity.create(d, 16, 4); ic_point_source_ID.create(d, 16); ic_dx.create(d, 32, 2); ic_dy.create(d, 32, 22);
+        ic_z.create(d, 32, 20);
+    }
+    void init(const U8* item) override {
+        for (int i = 0; i < 16; ++i) {
+            last_x_diff_median5[i].init(); last_y_diff_median5[i].init();
+            last_intensity[i] = 0; last_height[i / 2] = 0;
+        }
+        m_changed_values.init(); m_scan_angle_rank[0].init(); m_scan_angle_rank[1].init();
+        has_bit_byte.assign(256, 0); has_classification.assign(256, 0); has_user_data.assign(256, 0);
+        ic_intensity.init(); ic_point_source_ID.init(); ic_dx.init(); ic_dy.init(); ic_z.init();
+        memcpy(last_item, item, 20);
+        last_item[12] = 0; last_item[13] = 0;         // the intensity of the first point is not a prediction base
+    }
+    static SymbolModel* lazy(std::vector<SymbolModel>& v, std::vector<char>& has, U32 i) {
+        if (!has[i]) { v[i] = SymbolModel(); v[i].create(256); v[i].init(); has[i] = 1; }
+        return &v[i];
+    }
+    void read(U8* item) override {
+        U32 r, n, m, l;
+        I32 x, y, z;
+        U16 intensity, psid;
+        memcpy(&x, last_item, 4); memcpy(&y, last_item + 4, 4); memcpy(&z, last_item + 8, 4);
+        memcpy(&intensity, last_item + 12, 2); memcpy(&psid, last_item + 18, 2);
+        const U32 changed = dec->decodeSymbol(&m_changed_values);
+        if (changed) {
+            if (changed & 32) last_item[14] = (U8)dec->decodeSymbol(lazy(m_bit_byte, has_bit_byte, last_item[14]));
+            r = last_item[14] & 7; n = (last_item[14] >> 3) & 7;
+            m = number_return_map[n][r]; l = number_return_level[n][r];
+            if (changed & 16) {
+                intensity = (U16)ic_intensity.decompress(last_intensity[m], (m < 3 ? m : 3));
+                last_intensity[m] = intensity;
+            } else intensity = last_intensity[m];
+            if (changed & 8) last_item[15] = (U8)dec->decodeSymbol(lazy(m_classification, has_classification, last_item[15]));
+            if (changed & 4) {
+                const I32 val = (I32)dec->decodeSymbol(&m_scan_angle_rank[(last_item[14] >> 6) & 1]);
+                last_item[16] = u8_fold(val + last_item[16]);
+            }
+            if (changed & 2) last_item[17] = (U8)dec->decodeSymbol(lazy(m_user_data, has_user_data, last_item[17]));
+            if (changed & 1) psid = (U16)ic_point_source_ID.decompress(psid);
+        } else {
+            r = last_item[14] & 7; n = (last_item[14] >> 3) & 7;
+            m = number_return_map[n][r]; l = number_return_level[n][r];
+        }
+        I32 median = last_x_diff_median5[m].get();
+        I32 diff = ic_dx.decompress(median, n == 1);
+        x = (I32)((U32)x + (U32)diff);
+        last_x_diff_median5[m].add(diff);
+        median = last_y_diff_median5[m].get();
+        U32 k_bits = ic_dx.getK();
+        diff = ic_dy.decompress(median, (n == 1) + (k_bits < 20 ? (k_bits & ~1u) : 20));
+        y = (I32)((U32)y + (U32)diff);
+        last_y_diff_median5[m].add(diff);
+        k_bits = (ic_dx.getK() + ic_dy.getK()) / 2;
+        z = ic_z.decompress(last_height[l], (n == 1) + (k_bits < 18 ? (k_bits & ~1u) : 18));
+        last_height[l] = z;
+        memcpy(last_item, &x, 4); memcpy(last_item + 4, &y, 4); memcpy(last_item + 8, &z, 4);
+        memcpy(last_item + 12, &intensity, 2); memcpy(last_item + 18, &psid, 2);
+        memcpy(item, last_item, 20);
+    }
+};
+
+struct GpsTime11Reader : ItemReader {
+    static constexpr I32 MULTI = 500, MULTI_MINUS = -10, MULTI_UNCHANGED = MULTI - MULTI_MINUS + 1,
+                         MULTI_CODE_FULL = MULTI - MULTI_MINUS + 2, MULTI_TOTAL = MULTI - MULTI_MINUS + 6;
+    Decoder* dec;
+    U32 last = 0, next = 0;
+    U64 last_gpstime[4];
+    I32 last_gpstime_diff[4], multi_extreme_counter[4];
+    SymbolModel m_multi, m_0diff;
+    IntegerCompressor ic;
+    explicit GpsTime11Reader(Decoder* d) : dec(d) { m_multi.create(MULTI_TOTAL); m_0diff.create(6); ic.create(d, 32, 9); }
+    void init(const U8* item) override {
+        last = next = 0;
+        for (int i = 0; i < 4; ++i) { last_gpstime_diff[i] = 0; multi_extreme_counter[i] = 0; last_gpstime[i] = 0; }
+        m_multi.init(); m_0diff.init(); ic.init();
+        memcpy(&last_gpstime[0], item, 8);
+    }
+    void full() {
+        next = (next + 1) & 3;
+        last_gpstime[next] = (U64)(U32)ic.decompress((I32)(last_gpstime[last] >> 32), 8);
+        last_gpstime[next] = last_gpstime[next] << 32;
+        last_gpstime[next] |= (U64)dec->readInt();
+        last = next;
+        last_gpstime_diff[last] = 0;
+        multi_extreme_counter[last] = 0;
+    }
+    void read(U8* item) override {
+        I32 multi;
+        if (last_gpstime_diff[last] == 0) {
+            multi = (I32)dec->decodeSymbol(&m_0diff);
+            if (multi == 1) {
+                last_gpstime_diff[last] = ic.decompress(0, 0);
+                last_gpstime[last] = (U64)((I64)last_gpstime[last] + last_gpstime_diff[last]);
+                multi_extreme_counter[last] = 0;
+            } else if (multi == 2) {
+                full();
+            } else if (multi > 2) {
+                last = (last + (U32)multi - 2) & 3;
+                read(item);
+                return;
+            }
+        } else {
+            multi = (I32)dec->decodeSymbol(&m_multi);
+            if (multi == 1) {
+                last_gpstime[last] = (U64)((I64)last_gpstime[last] + ic.decompress(last_gpstime_diff[last], 1));
+                multi_extreme_counter[last] = 0;
+            } else if (multi < MULTI_UNCHANGED) {
+                I32 gpstime_diff;
+                if (multi == 0) {
+                    gpstime_diff = ic.decompress(0, 7);
+                    if (++multi_extreme_counter[last] > 3) { last_gpstime_diff[last] = gpstime_diff; multi_extreme_counter[last] = 0; }
+                } else if (multi < MULTI) {
+                    gpstime_diff = ic.decompress((I32)((U32)multi * (U32)last_gpstime_diff[last]), multi < 10 ? 2 : 3);
+                } else if (multi == MULTI) {
+                    gpstime_diff = ic.decompress((I32)((U32)MULTI * (U32)last_gpstime_diff[last]), 4);
+                    if (++multi_extreme_counter[last] > 3) { last_gpstime_diff[last] = gpstime_diff; multi_extreme_counter[last] = 0; }
+                } else {
+                    multi = MULTI - multi;
+                    if (multi > MULTI_MINUS) {
+                        gpstime_diff = ic.decompress((I32)((U32)multi * (U32)last_gpstime_diff[last]), 5);
+                    } else {
+                        gpstime_diff = ic.decompress((I32)((U32)MULTI_MINUS * (U32)last_gpstime_diff[last]), 6);
+                        if (++multi_extreme_counter[last] > 3) { last_gpstime_diff[last] = gpstime_diff; multi_extreme_counter[last] = 0; }
+                    }
+                }
+                last_gpstime[last] = (U64)((I64)last_gpstime[last] + gpstime_diff);
+            } else if (multi == MULTI_CODE_FULL) {
+                full();
+            } else if (multi >= MULTI_CODE_FULL) {
+                last = (last + (U32)multi - (U32)MULTI_CODE_FULL) & 3;
+                read(item);
+                return;
+            }
+        }
+        memcpy(item, &last_gpstime[last], 8);
+    }
+};
+
+struct Rgb12Reader : ItemReader {
+    Decoder* dec;
+    U16 last_item[3];
+    SymbolModel m_byte_used, m_diff[6];
+    explicit Rgb12Reader(Decoder* d) : dec(d) { m_byte_used.create(128); for (auto& m : m_diff) m.create(256); }
+    void init(const U8* item) override { m_byte_used.init(); for (auto& m : m_diff) m.init(); memcpy(last_item, item, 6); }
+    void read(U8* out) override {
+        U16 item[3];
+        U8 corr;
+        I32 diff = 0;
+        const U32 sym = dec->decodeSymbol(&m_byte_used);
+        if (sym & 1) { corr = (U8)dec->decodeSymbol(&m_diff[0]); item[0] = (U16)u8_fold(corr + (last_item[0] & 255)); }
+        else item[0] = last_item[0] & 0xFF;
+        if (sym & 2) { corr = (U8)dec->decodeSymbol(&m_diff[1]); item[0] |= ((U16)u8_fold(corr + (last_item[0] >> 8))) << 8; }
+        else item[0] |= (last_item[0] & 0xFF00);
+        if (sym & 64) {
+            diff = (item[0] & 0x00FF) - (last_item[0] & 0x00FF);
+            if (sym & 4) { corr = (U8)dec->decodeSymbol(&m_diff[2]); item[1] = (U16)u8_fold(corr + u8_clamp(diff + (last_item[1] & 255))); }
+            else item[1] = last_item[1] & 0xFF;
+            if (sym & 16) {
+                corr = (U8)dec->decodeSymbol(&m_diff[4]);
+                diff = (diff + ((item[1] & 0x00FF) - (last_item[1] & 0x00FF))) / 2;
+                item[2] = (U16)u8_fold(corr + u8_clamp(diff + (last_item[2] & 255)));
+            } else item[2] = last_item[2] & 0xFF;
+            diff = (item[0] >> 8) - (last_item[0] >> 8);
+            if (sym & 8) { corr = (U8)dec->decodeSymbol(&m_diff[3]); item[1] |= ((U16)u8_fold(corr + u8_clamp(diff + (last_item[1] >> 8)))) << 8; }
+            else item[1] |= (last_item[1] & 0xFF00);
+            if (sym & 32) {
+                corr = (U8)dec->decodeSymbol(&m_diff[5]);
+                diff = (diff + ((item[1] >> 8) - (last_item[1] >> 8))) / 2;
+                item[2] |= ((U16)u8_fold(corr + u8_clamp(diff + (last_item[2] >> 8)))) << 8;
+            } else item[2] |= (last_item[2] & 0xFF00);
+        } else { item[1] = item[0]; item[2] = item[0]; }
+        memcpy(last_item, item, 6);
+        memcpy(out, item, 6);
+    }
+};
+
+struct ByteReader : ItemReader {
+    Decoder* dec;
+    U32 number;
+    std::vector<U8> last_item;
+    std::vector<SymbolModel> m_byte;
+    ByteReader(Decoder* d, U32 n) : dec(d), number(n), last_item(n), m_byte(n) { for (auto& m : m_byte) m.create(256); }
+    void init(const U8* item) override { for (auto& m : m_byte) m.init(); memcpy(last_item.data(), item, number); }
+    void read(U8* item) override {
+        for (U32 i = 0; i < number; ++i) { item[i] = u8_fold(last_item[i] + (I32)dec->decodeSymbol(&m_byte[i])); }
+        memcpy(last_item.data(), item, number);
+    }
+};
+
+}  // namespace laz
+}  // namespace upcp
+
+using namespace upcp;
+
+extern "C" {
+
+/* see include/upcp_cuda.h */
+int upcp_laz_decode(const uint8_t* h_vlr, int32_t vlr_bytes, const uint8_t* h_data, int64_t data_bytes, int64_t data_file_offset,
+                    int64_t n_points, int32_t point_size, uint8_t* h_out) {
+    using namespace upcp::laz;
+    if (!h_vlr || !h_data || !h_out || vlr_bytes < 34 || n_points < 0 || point_size < 20 || data_bytes < 8)
+        UPCP_FAIL(UPCP_E_INVALID, "laz_decode: bad argument");
+    U16 compressor, coder, num_items;
+    I32 chunk_size;
+    memcpy(&compressor, h_vlr, 2); memcpy(&coder, h_vlr + 2, 2); memcpy(&chunk_size, h_vlr + 12, 4); memcpy(&num_items, h_vlr + 32, 2);
+    if (coder != 0) UPCP_FAIL(UPCP_E_CAPACITY, "laz_decode: unknown entropy coder");
+    if (compressor != 2) UPCP_FAIL(UPCP_E_CAPACITY, "laz_decode: only the pointwise chunked compressor (LAS 1.0 - 1.3 point formats 0 - 3) is supported");
+    if (vlr_bytes < 34 + 6 * (int)num_items) UPCP_FAIL(UPCP_E_INVALID, "laz_decode: truncated laszip VLR");
+    if (n_points == 0) return UPCP_OK;
+    try {
+        Decoder dec;
+        std::vector<ItemReader*> readers;
+        std::vector<U32> sizes;
+        struct Cleanup { std::vector<ItemReader*>& r; ~Cleanup() { for (auto p : r) delete p; } } cleanup{readers};
+        U32 total = 0;
+        for (int i = 0; i < (int)num_items; ++i) {
+            U16 type, size, version;
+            memcpy(&type, h_vlr + 34 + 6 * i, 2); memcpy(&size, h_vlr + 36 + 6 * i, 2); memcpy(&version, h_vlr + 38 + 6 * i, 2);
+            if (version != 2) UPCP_FAIL(UPCP_E_CAPACITY, "laz_decode: only version-2 item codecs are supported");
+            if (type == 6 && size == 20) readers.push_back(new Point10Reader(&dec));
+            else if (type == 7 && size == 8) readers.push_back(new GpsTime11Reader(&dec));
+            else if (type == 8 && size == 6) readers.push_back(new Rgb12Reader(&dec));
+            else if (type == 0 && size >= 1) readers.push_back(new ByteReader(&dec, size));
+            else UPCP_FAIL(UPCP_E_CAPACITY, "laz_decode: unsupported item type (wave packets / LAS 1.4 layered items)");
+            sizes.push_back(size);
+            total += size;
+        }
+        if ((I32)total != point_size) UPCP_FAIL(UPCP_E_INVALID, "laz_decode: item sizes do not add up to the point size");
+        // The point data starts with the file position of the chunk table (the byte size of every chunk,
+        // itself arithmetic-coded).  A sequential read does not need it -- every chunk ends where the decoder
+        // stopped reading, LASzip relies on the same property -- but when it is there the chunk starts are
+        // taken from it, as LASzip's integrity check does.
+        const I64 per_chunk = chunk_size > 0 ? (I64)chunk_size : n_points;
+        std::vector<I64> chunk_start;                                  // offsets into h_data, empty = sequential
+        {
+            I64 table_pos;
+            memcpy(&table_pos, h_data, 8);
+            if (table_pos == -1 && data_bytes >= 16) memcpy(&table_pos, h_data + data_bytes - 8, 8);
+            const I64 rel = table_pos - data_file_offset;
+            if (table_pos > 0 && rel >= 8 && rel + 8 <= data_bytes) {
+                U32 version, number_chunks;
+                memcpy(&version, h_data + rel, 4); memcpy(&number_chunks, h_data + rel + 4, 4);
+                const I64 expect = (n_points + per_chunk - 1) / per_chunk;
+                if (version == 0 && (I64)number_chunks == expect) {
+                    ByteStream ts{h_data + rel + 8, h_data + data_bytes, false};
+                    Decoder td;
+                    td.init(&ts);
+                    IntegerCompressor ic;
+                    ic.create(&td, 32, 2);
+                    ic.init();
+                    I64 pos = 8;
+                    I32 prev = 0;
+                    for (U32 c = 0; c < number_chunks; ++c) {
+                        chunk_start.push_back(pos);
+                        prev = ic.decompress(c ? prev : 0, 1);
+                        pos += (I64)(U32)prev;
+                    }
+                    if (ts.overrun || pos != rel) chunk_start.clear();       // inconsistent table: read sequentially
+                }
+            }
+        }
+        ByteStream in{h_data + 8, h_data + data_bytes, false};
+        for (I64 i = 0; i < n_points; ++i) {
+            U8* out = h_out + i * point_size;
+            if (i % per_chunk == 0) {
+                if (!chunk_start.empty()) in.p = h_data + chunk_start[(size_t)(i / per_chunk)];
+                // first point of a chunk: stored raw; then the coder starts afresh
+                if (in.end - in.p < point_size) UPCP_FAIL(UPCP_E_INVALID, "laz_decode: truncated chunk");
+                memcpy(out, in.p, point_size);
+                in.p += point_size;
+                U32 off = 0;
+                for (size_t r = 0; r < readers.size(); ++r) { readers[r]->init(out + off); off += sizes[r]; }
+                if (i + 1 < n_points && (i + 1) % per_chunk != 0) dec.init(&in);
+            } else {
+                U32 off = 0;
+                for (size_t r = 0; r < readers.size(); ++r) { readers[r]->read(out + off); off += sizes[r]; }
+            }
+            if (in.overrun) UPCP_FAIL(UPCP_E_INVALID, "laz_decode: compressed stream ended early");
+        }
+    } catch (const std::bad_alloc&) {
+        UPCP_FAIL(UPCP_E_INTERNAL, "laz_decode: out of host memory");
+    }
+    return UPCP_OK;
+}
+
+}  // extern "C"

@@ -147,8 +147,7 @@ def read(path):
     h.offset_to_points = struct.unpack_from('<I', data, 96)[0]
     n_vlrs = struct.unpack_from('<I', data, 100)[0]
     fmt = data[104]
-    if fmt & 0x80 or fmt & 0x40:
-        raise ValueError(f'{path}: compressed (LAZ) point data needs laspy[lazrs]')
+    compressed = bool(fmt & 0x80) or bool(fmt & 0x40)
     h.point_format_id = fmt & 0x3f
     h.point_size = struct.unpack_from('<H', data, 105)[0]
     legacy_count = struct.unpack_from('<I', data, 107)[0]
@@ -190,8 +189,11 @@ def read(path):
                 extra.append((name, dt, off))
                 off += dt.itemsize
     n = int(h.point_count)
-    body = np.frombuffer(data, dtype=np.uint8, count=n * h.point_size, offset=h.offset_to_points)
-    records = body.reshape(n, h.point_size).copy()
+    if compressed:
+        records, vlrs = _decode_laz(path, data, h, vlrs, n)
+    else:
+        body = np.frombuffer(data, dtype=np.uint8, count=n * h.point_size, offset=h.offset_to_points)
+        records = body.reshape(n, h.point_size).copy()
     extra = [e for e in extra if e[2] + e[1].itemsize <= h.point_size and e[1].kind != 'V']
     evlrs, n_evlrs = b'', 0
     if h.version >= (1, 4) and h.header_size >= 375:
@@ -202,6 +204,32 @@ def read(path):
         else:
             n_evlrs = 0
     return LasData(h, vlrs, records, extra, evlrs, n_evlrs)
+
+
+_LASZIP_USER, _LASZIP_RECORD = b'laszip encoded', 22204
+
+
+def _decode_laz(path, data, h, vlrs, n):
+    """LASzip-compressed point data -> uncompressed records through the native decoder (``upcp_laz_decode``,
+    csrc/laz.cu).  The result is an ordinary in-memory LAS: the laszip VLR is dropped and the compression bits
+    of the header's point format byte are cleared, so ``write`` produces a plain .las."""
+    import ctypes
+
+    from .. import _lib
+    lib = _lib.load()
+    payload = next((v[3] for v in vlrs if v[0] == _LASZIP_USER and v[1] == _LASZIP_RECORD), None)
+    if payload is None:
+        raise ValueError(f'{path}: compressed point data without a laszip VLR')
+    records = np.empty((n, h.point_size), dtype=np.uint8)
+    body = np.frombuffer(data, dtype=np.uint8, offset=h.offset_to_points)
+    vlr = np.frombuffer(payload, dtype=np.uint8)
+    _lib.check(lib.upcp_laz_decode(vlr.ctypes.data_as(ctypes.c_void_p), len(payload), body.ctypes.data_as(ctypes.c_void_p),
+                                   len(body), int(h.offset_to_points), n, int(h.point_size),
+                                   records.ctypes.data_as(ctypes.c_void_p)), f'upcp_laz_decode({path})')
+    raw = bytearray(h.raw)
+    raw[104] = h.point_format_id
+    h.raw = bytes(raw)
+    return records, [v for v in vlrs if not (v[0] == _LASZIP_USER and v[1] == _LASZIP_RECORD)]
 
 
 def create(points_int, scales, offsets, point_format_id=1):

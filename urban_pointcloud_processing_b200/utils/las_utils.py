@@ -1,10 +1,14 @@
 """Tile-code helpers and LAS I/O (host side; mirrors ``upcp.utils.las_utils``, reference
 src/upcp/utils/las_utils.py:12-53,118-130).  ``laspy`` is used when it is installed (required for
 ``.laz``); plain ``.las`` files are handled natively by ``las_io``."""
+import logging
 import pathlib
 import re
 
 from . import las_io
+
+
+logger = logging.getLogger(__name__)
 
 
 def get_tilecode_from_filename(filename):
@@ -36,8 +40,7 @@ def read_las(las_file):
     try:
         import laspy
     except ImportError:
-        if str(las_file).lower().endswith('.laz'):
-            raise ImportError('reading .laz needs laspy[lazrs], which is not installed') from None
+        # native reader: plain .las and LASzip-compressed .laz (point formats 0-3, csrc/laz.cu)
         return las_io.read(las_file)
     return laspy.read(las_file)
 
@@ -47,7 +50,9 @@ def label_and_save_las(las, labels, outfile):
     assert len(labels) == las.header.point_count
     if isinstance(las, las_io.LasData):
         if str(outfile).lower().endswith('.laz'):
-            raise ImportError('writing .laz needs laspy[lazrs], which is not installed')
+            # no LASzip ENCODER here: the records are written uncompressed under the requested name.  Readers
+            # (laspy, PDAL, this module) go by the header's compression bit, not by the extension.
+            logger.warning(f'{outfile}: laspy[lazrs] is not installed, point data written uncompressed')
         las.label = labels          # adds the uint8 "label" extra dimension when missing
         las.write(outfile)
         return
