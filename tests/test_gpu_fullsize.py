@@ -250,6 +250,68 @@ def test_config3_region_growing_50m_fixpoint():
           f'added by a second pass = {n_regrown}, angle tests within 1e-6 deg of the threshold: {n_near}')
 
 
+def test_config3_knn_rows_and_normals_50m_match_oracle_on_a_crop():
+    """Config 3 at full size, checked against the ORACLE rather than against the device's own graph: the kNN rows,
+    squared distances and hybrid normals the device computed for the 50 M-point tile (facade-heavy, generated on
+    the device) are compared with natives.knn / natives.normals_hybrid on a ~2.5 M-point spatial crop, for the
+    interior points of the crop (whose neighbourhoods lie inside it), for grow_region_radius 0.1 / 0.2 / 0.5; then
+    RegionGrowing runs for the two other radii of the configuration.  The exposure to the one ambiguity of
+    the restated neighbour order -- exact distance ties -- is counted on the same crop."""
+    from oracle import natives
+    from test_gpu_parity import report_tie_exposure
+    tile, kind, layout = synthetic.make_device_tile(N50, seed=20240003, origin=synthetic.tile_origin(3), facade_fraction=0.7)
+    del kind
+    tc = layout['tilecode']
+    ahn = __import__('urban_pointcloud_processing_b200.utils.ahn_utils', fromlist=['x']).ArrayAHNReader({tc: layout['ahn_tile']})
+    bld = __import__('urban_pointcloud_processing_b200.utils.bgt_utils', fromlist=['x']).ArrayBGTReader({tc: layout['building_polygons']})
+    d_labels = torch.zeros(N50, dtype=torch.int32, device=tile.device)
+    Pipeline(processors=(AHNFuser(Labels.GROUND, ahn, target='ground', epsilon=0.2, refine_ground=False),
+                         BGTBuildingFuser(Labels.BUILDING, bgt_reader=bld, offset=0, ahn_reader=ahn)),
+             ahn_reader=ahn, caching=True).process_tile_device(tc, tile, d_labels)
+    d_sel = (d_labels != Labels.GROUND).to(torch.uint8)
+    _, bbox_sel, m = tile.bbox(d_sel)
+    # crop: 11 m square around a building corner (facade, balcony clutter and street level all occur)
+    cx, cy = layout['boxes'][0][2], layout['boxes'][0][3]
+    side, margin = 11.0, 0.75
+    ox, oy = layout['origin']
+    cx = min(max(cx, ox + side / 2), ox + 50.0 - side / 2); cy = min(max(cy, oy + side / 2), oy + 50.0 - side / 2)
+    d_in = (d_sel != 0) & ((tile.x - cx).abs() <= side / 2) & ((tile.y - cy).abs() <= side / 2)
+    d_ids = torch.nonzero(d_in).flatten()
+    compact = torch.cumsum(d_sel.to(torch.int32), 0, dtype=torch.int32) - 1           # compact id of every selected point
+    d_cid = compact[d_ids].long()
+    crop_of_compact = torch.full((m,), -1, dtype=torch.int32, device=tile.device)
+    crop_of_compact[d_cid] = torch.arange(len(d_cid), dtype=torch.int32, device=tile.device)
+    coords = torch.stack((tile.x[d_ids], tile.y[d_ids], tile.z[d_ids]), dim=1).cpu().numpy()
+    assert len(coords) > 1_500_000
+    want_idx, want_d2 = natives.knn(coords, 15, want_d2=True)
+    interior = (np.abs(coords[:, 0] - cx) <= side / 2 - margin) & (np.abs(coords[:, 1] - cy) <= side / 2 - margin) & \
+        (want_d2[:, 14] < 0.7 ** 2)
+    d_int = torch.from_numpy(np.where(interior)[0]).to(tile.device)
+    report_tie_exposure(coords)
+    for radius in (0.2, 0.1, 0.5):
+        d_knn, d_d2, d_nrm, _, _ = rgmod.knn_normals_device(tile, d_sel, m, bbox_sel, 15, 30, radius, want_d2=True,
+                                                          want_cov=False, want_curv=False)
+        rows = crop_of_compact[d_knn[d_cid[d_int]].long()].cpu().numpy()                  # neighbours as crop indices
+        assert np.array_equal(rows, want_idx[interior]), radius
+        assert np.array_equal(d_d2[d_cid[d_int]].cpu().numpy(), want_d2[interior]), radius
+        want_n = natives.normals_hybrid(coords, radius, 30)[interior]
+        got_n = d_nrm[d_cid[d_int]].cpu().numpy()
+        bad = np.abs(got_n - want_n).max(axis=1) > 1e-9
+        print(f'config 3, radius {radius}: {int(interior.sum())} interior points of a {len(coords)}-point crop of the {m} selected: '
+              f'kNN rows / d2 identical, normals bit-identical {np.mean((got_n == want_n).all(axis=1)):.4f}, beyond 1e-9: {int(bad.sum())}')
+        assert bad.sum() == 0
+        del d_knn, d_d2, d_nrm
+    for radius in (0.1, 0.5):
+        d_out = d_labels.clone()
+        rg = RegionGrowing(Labels.BUILDING, exclude_labels=(Labels.GROUND,), grow_region_radius=radius)
+        rg._apply_device(tile, d_out, None, tc)
+        grown, seeds0 = d_out == Labels.BUILDING, d_labels == Labels.BUILDING
+        assert bool((grown | ~seeds0).all()) and bool(torch.equal(d_out == Labels.GROUND, d_labels == Labels.GROUND))
+        assert int(grown.sum()) > int(seeds0.sum()) + 50_000 and bool(torch.equal(d_out[~grown], d_labels[~grown]))
+        print(f'config 3, radius {radius}: region {int(grown.sum())} from {int(seeds0.sum())} seeds, '
+              f'{rg.last_stats["n_curvature_on_host"]} curvature flags on the host')
+
+
 # --------------------------------------------------- config 5: full pipeline, one tile ---
 def test_config5_pipeline_20m_host_api_equals_device_arm(tile20):
     pts = np.asfortranarray(tile20['points'])
