@@ -17,6 +17,14 @@
 //     crossing parity and the boundary test unchanged.  Lists are supersets (one
 //     extra slab / cell on each side absorbs host/device rounding of the index
 //     arithmetic); every listed edge goes through the exact reference test in fp64.
+//   * a fine TAG grid (<= 512 x 512 one-byte cells over the same bbox): 0 = no point of the cell is inside
+//     the set, 1 = every point is, 2 = an edge passes through or next to the cell.  The crossing rule of
+//     the reference is the consistent half-open one (an edge is counted iff its other end lies strictly
+//     above the ray, clip_utils.py:139-160), so the result is constant over any cell no edge comes near;
+//     such a cell is classified ONCE on the host with the exact test (one evaluation per connected group
+//     of cells) and its points need one byte lookup instead of the ring / slab / edge walk.  Only the
+//     thin band of cells along the edges (inflated by a cell: rounding of the index arithmetic, points
+//     within rounding of an edge) runs the exact test.
 // The plan is a few MB at most and stays L2-resident; the point stream is read
 // once, coalesced (16 B/pt in, 1 B/pt out).
 //
@@ -39,6 +47,10 @@ struct PipHeader {
     int32_t magic, n_rings, gx, gy;
     double x0, y0, inv_cw, inv_ch;
     double offset;           // buffer distance of every polygon of the plan (0 = the reference's exact test)
+    int32_t gt, n_verts;     // tag grid size (gt x gt over the same bbox), 0 = none; number of vertices
+    double inv_tw, inv_th;
+    int64_t off_tags;        // uint8 [gt*gt]: 0 outside, 1 inside, 2 mixed (filled on the device after the upload)
+    int64_t off_edge_ok;     // uint8 [n_verts]: vertex v -> v + 1 is an edge of an active ring
     int64_t off_ring_bbox;   // double[R][4]  xmin ymin xmax ymax
     int64_t off_ring_meta;   // int32 [R][4]  poly, is_hole, slab_base, n_slabs
     int64_t off_ring_slab;   // double[R][2]  slab y0, inv_h
@@ -158,10 +170,23 @@ pip_query_offset_kernel(const char* __restrict__ plan, const double* __restrict_
     }
 }
 
-__global__ void __launch_bounds__(kBlock)
-pip_query_kernel(const char* __restrict__ plan, const double* __restrict__ x,
-                 const double* __restrict__ y, int64_t n, const uint8_t* __restrict__ sel,
-                 uint8_t* __restrict__ out) {
+#if defined(__CUDA_ARCH__)
+#define PIP_LD(p) __ldg(p)
+#else
+#define PIP_LD(p) (*(p))
+#endif
+
+__host__ __device__ __forceinline__ int pip_cell(double v, double origin, double inv, int n) {
+    double t = (v - origin) * inv;
+    if (!(t > 0.0)) return 0;
+    if (t >= (double)n) return n - 1;
+    return (int)floor(t);
+}
+
+// The exact test of one point against the polygon set of a plan (reference semantics: inclusive bounding-box
+// prefilter, crossing number with boundary == inside, interiors clear what the exterior set, OR over
+// polygons).  Device: the query kernel; host: classification of the uniform cells of the tag grid.
+__host__ __device__ __forceinline__ bool pip_exact(const char* __restrict__ plan, double px, double py) {
     const PipHeader* h = (const PipHeader*)plan;
     const double2* ring_bbox = (const double2*)(plan + h->off_ring_bbox);
     const int4* ring_meta = (const int4*)(plan + h->off_ring_meta);
@@ -171,55 +196,167 @@ pip_query_kernel(const char* __restrict__ plan, const double* __restrict__ x,
     const double2* verts = (const double2*)(plan + h->off_verts);
     const int32_t* cell_start = (const int32_t*)(plan + h->off_cell_start);
     const int32_t* cell_rings = (const int32_t*)(plan + h->off_cell_rings);
-    const int gx = h->gx, gy = h->gy;
-    const double x0 = h->x0, y0 = h->y0, inv_cw = h->inv_cw, inv_ch = h->inv_ch;
-
-    int64_t stride = (int64_t)gridDim.x * kBlock;
-    for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < n; i += stride) {
-        bool s = sel ? (sel[i] != 0) : true;
-        bool inside_any = false;
-        if (s) {
-            double px = x[i], py = y[i];
-            int cx = dev_cell(px, x0, inv_cw, gx);
-            int cy = dev_cell(py, y0, inv_ch, gy);
-            int c = cy * gx + cx;
-            int k0 = __ldg(cell_start + c), k1 = __ldg(cell_start + c + 1);
-            int cur_poly = -1;
-            bool cur_in = false;
-            for (int k = k0; k < k1; ++k) {
-                int r = __ldg(cell_rings + k);
-                int4 meta = __ldg(ring_meta + r);
-                if (meta.x != cur_poly) {
-                    inside_any = inside_any || cur_in;
-                    if (inside_any) break;      // OR over polygons: nothing can undo it
-                    cur_in = false;
-                    cur_poly = meta.x;
-                }
-                bool is_hole = meta.y == 1;
-                if (is_hole && !cur_in) continue;
-                double2 bmin = __ldg(ring_bbox + 2 * r), bmax = __ldg(ring_bbox + 2 * r + 1);
-                // rectangle_clip (clip_utils.py:38-39): inclusive on all four sides
-                if (!(px >= bmin.x && px <= bmax.x && py >= bmin.y && py <= bmax.y)) continue;
-                double2 sl = __ldg(ring_slab + r);
-                int si = dev_cell(py, sl.x, sl.y, meta.w);
-                int e0 = __ldg(slab_start + meta.z + si), e1 = __ldg(slab_start + meta.z + si + 1);
-                int parity = 0;
-                bool boundary = false;
-                for (int e = e0; e < e1; ++e) {
-                    int vi = __ldg(slab_edges + e);
-                    double2 a = __ldg(verts + vi), b = __ldg(verts + vi + 1);
-                    int res = pip_edge(a.x, a.y, b.x, b.y, px, py);
-                    if (res == 2) { boundary = true; break; }
-                    parity ^= res;
-                }
-                bool in = boundary || (parity != 0);
-                if (meta.y == 0) cur_in = in;
-                else if (is_hole) { if (in) cur_in = false; }
-                else cur_in = cur_in != in;                    // even-odd loop
-            }
+    const int cx = pip_cell(px, h->x0, h->inv_cw, h->gx);
+    const int cy = pip_cell(py, h->y0, h->inv_ch, h->gy);
+    const int c = cy * h->gx + cx;
+    const int k0 = PIP_LD(cell_start + c), k1 = PIP_LD(cell_start + c + 1);
+    bool inside_any = false;
+    int cur_poly = -1;
+    bool cur_in = false;
+    for (int k = k0; k < k1; ++k) {
+        const int r = PIP_LD(cell_rings + k);
+        const int4 meta = PIP_LD(ring_meta + r);
+        if (meta.x != cur_poly) {
             inside_any = inside_any || cur_in;
+            if (inside_any) break;      // OR over polygons: nothing can undo it
+            cur_in = false;
+            cur_poly = meta.x;
         }
-        out[i] = inside_any ? 1 : 0;
+        const bool is_hole = meta.y == 1;
+        if (is_hole && !cur_in) continue;
+        const double2 bmin = PIP_LD(ring_bbox + 2 * r), bmax = PIP_LD(ring_bbox + 2 * r + 1);
+        // rectangle_clip (clip_utils.py:38-39): inclusive on all four sides
+        if (!(px >= bmin.x && px <= bmax.x && py >= bmin.y && py <= bmax.y)) continue;
+        const double2 sl = PIP_LD(ring_slab + r);
+        const int si = pip_cell(py, sl.x, sl.y, meta.w);
+        const int e0 = PIP_LD(slab_start + meta.z + si), e1 = PIP_LD(slab_start + meta.z + si + 1);
+        int parity = 0;
+        bool boundary = false;
+        for (int e = e0; e < e1; ++e) {
+            const int vi = PIP_LD(slab_edges + e);
+            const double2 a = PIP_LD(verts + vi), b = PIP_LD(verts + vi + 1);
+            const int res = pip_edge(a.x, a.y, b.x, b.y, px, py);
+            if (res == 2) { boundary = true; break; }
+            parity ^= res;
+        }
+        const bool in = boundary || (parity != 0);
+        if (meta.y == 0) cur_in = in;
+        else if (is_hole) { if (in) cur_in = false; }
+        else cur_in = cur_in != in;                    // even-odd loop
+    }
+    return inside_any || cur_in;
+}
+
+// ---- tag grid, built on the device from the uploaded plan (three tiny launches) ----
+__global__ void __launch_bounds__(kBlock)
+pip_tag_init_kernel(char* __restrict__ plan) {
+    const PipHeader* h = (const PipHeader*)plan;
+    const int gt = h->gt;
+    uint8_t* tags = (uint8_t*)(plan + h->off_tags);
+    for (int c = blockIdx.x * kBlock + threadIdx.x; c < gt * gt; c += gridDim.x * kBlock) {
+        const int cx = c % gt, cy = c / gt;
+        // the border cells also receive the points outside the grid (clamped index): always exact
+        tags[c] = (cx == 0 || cy == 0 || cx == gt - 1 || cy == gt - 1) ? 2 : 0;
+    }
+}
+// every edge marks the cells it passes through or next to: pieces of at most ~2 cells, the cells of every
+// piece's bounding box plus one more cell on every side
+__global__ void __launch_bounds__(kBlock)
+pip_tag_edges_kernel(char* __restrict__ plan) {
+    const PipHeader* h = (const PipHeader*)plan;
+    const int gt = h->gt;
+    uint8_t* tags = (uint8_t*)(plan + h->off_tags);
+    const uint8_t* edge_ok = (const uint8_t*)(plan + h->off_edge_ok);
+    const double2* verts = (const double2*)(plan + h->off_verts);
+    for (int v = blockIdx.x * kBlock + threadIdx.x; v + 1 < h->n_verts; v += gridDim.x * kBlock) {
+        if (!edge_ok[v]) continue;
+        const double2 a = verts[v], b = verts[v + 1];
+        const double len_cells = fmax(fabs(b.x - a.x) * h->inv_tw, fabs(b.y - a.y) * h->inv_th);
+        const int pieces = len_cells > 2.0 ? (int)fmin(ceil(len_cells / 2.0), 1e6) : 1;
+        for (int k = 0; k < pieces; ++k) {
+            const double t0 = (double)k / pieces, t1 = (double)(k + 1) / pieces;
+            const double x_0 = a.x + t0 * (b.x - a.x), x_1 = a.x + t1 * (b.x - a.x);
+            const double y_0 = a.y + t0 * (b.y - a.y), y_1 = a.y + t1 * (b.y - a.y);
+            const int cx0 = max(pip_cell(fmin(x_0, x_1), h->x0, h->inv_tw, gt) - 1, 0), cx1 = min(pip_cell(fmax(x_0, x_1), h->x0, h->inv_tw, gt) + 1, gt - 1);
+            const int cy0 = max(pip_cell(fmin(y_0, y_1), h->y0, h->inv_th, gt) - 1, 0), cy1 = min(pip_cell(fmax(y_0, y_1), h->y0, h->inv_th, gt) + 1, gt - 1);
+            for (int cy = cy0; cy <= cy1; ++cy)
+                for (int cx = cx0; cx <= cx1; ++cx) tags[cy * gt + cx] = 2;
+        }
+    }
+}
+// every cell no edge comes near: ONE exact evaluation at its centre decides all its points
+__global__ void __launch_bounds__(kBlock)
+pip_tag_classify_kernel(char* __restrict__ plan) {
+    const PipHeader* h = (const PipHeader*)plan;
+    const int gt = h->gt;
+    uint8_t* tags = (uint8_t*)(plan + h->off_tags);
+    for (int c = blockIdx.x * kBlock + threadIdx.x; c < gt * gt; c += gridDim.x * kBlock) {
+        if (tags[c] == 2) continue;
+        const double px = h->x0 + ((double)(c % gt) + 0.5) / h->inv_tw, py = h->y0 + ((double)(c / gt) + 0.5) / h->inv_th;
+        tags[c] = pip_exact(plan, px, py) ? 1 : 0;
+    }
+}
+
+// Query kernel.  The points of a tile arrive in no spatial order, so nearly every warp holds SOME point of
+// the thin band of mixed cells; a per-point "tag, else exact" would make every warp walk the exact path
+// (a chain of ~8 dependent loads) with one or two lanes.  A CTA therefore takes 4 x kBlock consecutive
+// points per round: every thread loads four points with all loads independent (selection byte and
+// coordinates together, then the four tag bytes), writes the result of the decided ones and appends the
+// undecided ones -- coordinates and index -- to a CTA-local list in shared memory.  The list is walked by
+// the exact test only when it holds at least kPipFlush points (and once at the end), so that every lane of
+// every warp of the CTA has a point while the other CTAs of the SM keep streaming.
+constexpr int kPipPerThread = 4;
+constexpr int kPipTile = kPipPerThread * kBlock;
+constexpr int kPipFlush = 512;
+constexpr int kPipCap = kPipFlush + kPipTile;
+
+__global__ void __launch_bounds__(kBlock, 4)
+pip_query_kernel(const char* __restrict__ plan, const double* __restrict__ x,
+                 const double* __restrict__ y, int64_t n, const uint8_t* __restrict__ sel,
+                 uint8_t* __restrict__ out) {
+    __shared__ double s_x[kPipCap], s_y[kPipCap];
+    __shared__ uint32_t s_i[kPipCap];
+    __shared__ int s_cnt;
+    const PipHeader* h = (const PipHeader*)plan;
+    const int gt = h->gt;
+    const uint8_t* tags = (const uint8_t*)(plan + h->off_tags);
+    const double x0 = h->x0, y0 = h->y0, inv_tw = h->inv_tw, inv_th = h->inv_th;
+    const int lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) s_cnt = 0;
+    __syncthreads();
+    for (int64_t base = (int64_t)blockIdx.x * kPipTile; ; base += (int64_t)gridDim.x * kPipTile) {
+        const bool last = base >= n;        // uniform over the CTA: one more pass to drain the list
+        if (!last) {
+            double px[kPipPerThread], py[kPipPerThread];
+            bool s[kPipPerThread];
+            int tag[kPipPerThread];
+#pragma unroll
+            for (int u = 0; u < kPipPerThread; ++u) {
+                const int64_t i = base + u * kBlock + threadIdx.x;
+                const bool in = i < n;
+                s[u] = in && (sel ? (sel[i] != 0) : true);
+                px[u] = in ? x[i] : 0.0;
+                py[u] = in ? y[i] : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < kPipPerThread; ++u) {
+                tag[u] = 0;
+                if (s[u]) tag[u] = gt > 0 ? (int)__ldg(tags + pip_cell(py[u], y0, inv_th, gt) * gt + pip_cell(px[u], x0, inv_tw, gt)) : 2;
+            }
+#pragma unroll
+            for (int u = 0; u < kPipPerThread; ++u) {
+                const int64_t i = base + u * kBlock + threadIdx.x;
+                if (i < n) out[i] = tag[u] == 1 ? 1 : 0;
+                const uint32_t bal = __ballot_sync(0xffffffffu, tag[u] == 2);
+                if (bal) {
+                    int at = 0;
+                    const int leader = __ffs(bal) - 1;
+                    if (lane == leader) at = atomicAdd(&s_cnt, __popc(bal));
+                    at = __shfl_sync(0xffffffffu, at, leader) + __popc(bal & ((1u << lane) - 1u));
+                    if (tag[u] == 2) { s_x[at] = px[u]; s_y[at] = py[u]; s_i[at] = (uint32_t)i; }
+                }
+            }
+        }
+        __syncthreads();
+        const int m = s_cnt;
+        __syncthreads();                    // nobody appends for the next round before everyone has read the count
+        if (m >= kPipFlush || (last && m > 0)) {
+            for (int k = threadIdx.x; k < m; k += kBlock) out[s_i[k]] = pip_exact(plan, s_x[k], s_y[k]) ? 1 : 0;
+            __syncthreads();
+            if (threadIdx.x == 0) s_cnt = 0;
+            __syncthreads();
+        }
+        if (last) break;
     }
 }
 
@@ -420,6 +557,30 @@ int upcp_pip_plan_create_buffered(const double* h_ring_xy, const int64_t* h_ring
     if (V) memcpy(p + hd.off_verts, h_ring_xy, (size_t)V * 2 * sizeof(double));
     memcpy(p + hd.off_cell_start, cell_start.data(), cell_start.size() * sizeof(int32_t));
     if (!cell_rings.empty()) memcpy(p + hd.off_cell_rings, cell_rings.data(), cell_rings.size() * sizeof(int32_t));
+    // --- tag grid (see the header comment): space and geometry here, the classification itself runs on the
+    // device right after the upload (upcp_pip_plan_upload).  Not for buffered plans or NaN vertices.
+    if (offset == 0.0 && any_active) {
+        bool finite = true;
+        std::vector<uint8_t> edge_ok((size_t)(V > 0 ? V : 1), 0);          // 1: vertex v and v + 1 form an edge of an active ring
+        for (int r = 0; r < R && finite; ++r) {
+            if (!active[r]) continue;
+            for (int64_t v = h_ring_off[r]; v < h_ring_off[r + 1]; ++v) {
+                finite = finite && isfinite(h_ring_xy[2 * v]) && isfinite(h_ring_xy[2 * v + 1]);
+                if (v + 1 < h_ring_off[r + 1]) edge_ok[(size_t)v] = 1;
+            }
+        }
+        if (finite) {
+            const int gt = 512;
+            const size_t at_tags = align_up(plan->blob.size(), 256);
+            const size_t at_ok = align_up(at_tags + (size_t)gt * gt, 256);
+            plan->blob.resize(align_up(at_ok + edge_ok.size(), 256), 0);
+            memcpy(plan->blob.data() + at_ok, edge_ok.data(), edge_ok.size());
+            PipHeader* hp = (PipHeader*)plan->blob.data();
+            hp->gt = gt; hp->n_verts = (int32_t)V;
+            hp->inv_tw = w > 0 ? (double)gt / w : 0.0; hp->inv_th = hgt > 0 ? (double)gt / hgt : 0.0;
+            hp->off_tags = (int64_t)at_tags; hp->off_edge_ok = (int64_t)at_ok; hp->total_bytes = (int64_t)plan->blob.size();
+        }
+    }
     *out = plan;
     return UPCP_OK;
 }
@@ -431,6 +592,18 @@ int upcp_pip_plan_upload(const upcp_pip_plan* plan, void* d_plan, size_t bytes, 
     if (bytes < plan->blob.size()) UPCP_FAIL(UPCP_E_WORKSPACE, "pip_plan_upload: device buffer too small");
     cudaStream_t st = (cudaStream_t)stream;
     UPCP_CUDA_OK(cudaMemcpyAsync(d_plan, plan->blob.data(), plan->blob.size(), cudaMemcpyHostToDevice, st));
+    const PipHeader* hp = (const PipHeader*)plan->blob.data();
+    if (hp->gt > 0) {
+        const int cells = hp->gt * hp->gt;
+        pip_tag_init_kernel<<<grid_for(cells, kBlock), kBlock, 0, st>>>((char*)d_plan);
+        UPCP_LAUNCH_OK();
+        if (hp->n_verts > 1) {
+            pip_tag_edges_kernel<<<grid_for(hp->n_verts, kBlock), kBlock, 0, st>>>((char*)d_plan);
+            UPCP_LAUNCH_OK();
+        }
+        pip_tag_classify_kernel<<<grid_for(cells, kBlock), kBlock, 0, st>>>((char*)d_plan);
+        UPCP_LAUNCH_OK();
+    }
     // the blob is pageable host memory owned by the plan: make the copy complete
     // before the caller may destroy the plan
     UPCP_CUDA_OK(cudaStreamSynchronize(st));
@@ -443,8 +616,11 @@ int upcp_pip_query(const void* d_plan, const double* d_x, const double* d_y, int
                    const uint8_t* d_sel, uint8_t* d_out, void* stream) {
     if (n < 0 || !d_plan) UPCP_FAIL(UPCP_E_INVALID, "pip_query: bad argument");
     if (n == 0) return UPCP_OK;
+    if (n >= ((int64_t)1 << 32)) UPCP_FAIL(UPCP_E_CAPACITY, "pip_query: n must be < 2^32");
     prof_begin(UPCP_PROF_PIP, (cudaStream_t)stream);
-    pip_query_kernel<<<grid_for(n, kBlock), kBlock, 0, (cudaStream_t)stream>>>(
+    const int64_t tiles = (n + kPipTile - 1) / kPipTile;
+    const int64_t resident = (int64_t)num_sms() * 4;
+    pip_query_kernel<<<(unsigned)(tiles < resident ? tiles : resident), kBlock, 0, (cudaStream_t)stream>>>(
         (const char*)d_plan, d_x, d_y, n, d_sel, d_out);
     prof_end(UPCP_PROF_PIP, (cudaStream_t)stream, n);
     UPCP_LAUNCH_OK();

@@ -20,20 +20,26 @@ struct RasterParams {
     const double* values;
 };
 
-template <bool SMEM_BINS>
-__device__ __forceinline__ double raster_value(const RasterParams& r, const double* sbx,
-                                               const double* sby, double inv_step_x, double inv_step_y,
-                                               double px, double py) {
-    const double* bx = SMEM_BINS ? sbx : r.bin_x;
-    const double* by = SMEM_BINS ? sby : r.bin_y;
-    // arithmetic guess (uniform-step estimate, steps inverted once per thread), then exact fix-up
-    // against the same fp64 bin edges numpy compares with
-    int gx = guess_index(px, bx[0], inv_step_x, r.nx);
-    int gy = (py == py) ? guess_index(-py, -by[0], inv_step_y, r.ny) : -1;
-    int ix = digitize_asc_wrap(bx, r.nx, px, gx);
-    int iy = digitize_desc_wrap(by, r.ny, py, gy);
-    return __ldg(r.values + (size_t)iy * r.nx + ix);
+// One axis of the cell index.  `t` = (coordinate - first edge) / step in the direction the edges run.
+// When the edges of the axis were verified (once per CTA, while they are staged) to lie within 1e-7 of a
+// step of first + i x step, a coordinate whose `t` is farther than 1e-6 from an integer is on the same
+// side of every edge as its arithmetic position says -- the rounding of `t` is twelve orders smaller --
+// and the index is floor(t) without reading an edge.  The others (4 in a million, NaN, non-uniform edges)
+// take the exact search against the edges numpy compares with.
+template <bool ASC>
+__device__ __forceinline__ int raster_axis(const double* bins, int n, bool uniform, double t, double v) {
+    const double f = floor(t);
+    if (uniform && t - f >= 1e-6 && t - f <= 1.0 - 1e-6)
+        return (t < 0.0 || t >= (double)n) ? n - 1 : (int)f;       // "-1" wraps to the last cell like the numpy index
+    const int g = (t == t) ? (!(t > -1.0) ? -1 : (t >= (double)n ? n - 1 : (int)f)) : -1;
+    return ASC ? digitize_asc_wrap(bins, n, v, g) : digitize_desc_wrap(bins, n, v, g);
 }
+
+// kPerThread points per thread and round, every load of a round independent of the others of its kind:
+// the selection bytes, then the coordinates of the selected points, then the raster values -- three
+// round trips per FOUR points instead of per point (the kernel was latency- not bandwidth-limited with
+// one point in flight per thread: ncu r2, issue slots 56-62 % busy at 3.3 TB/s).
+constexpr int kPerThread = 4;
 
 template <bool SMEM_BINS, bool CLASSIFY>
 __global__ void __launch_bounds__(kBlock)
@@ -45,28 +51,66 @@ raster_kernel(const double* __restrict__ x, const double* __restrict__ y,
     extern __shared__ double s_bins[];
     double* sbx = s_bins;
     double* sby = s_bins + (SMEM_BINS ? r.nx : 0);
+    const double b0x = r.bin_x[0], b0y = r.bin_y[0];
+    const double step_x = r.nx >= 2 ? r.bin_x[1] - b0x : 0.0;
+    const double step_y = r.ny >= 2 ? b0y - r.bin_y[1] : 0.0;
+    bool uni_x = false, uni_y = false;
     if (SMEM_BINS) {
-        for (int i = threadIdx.x; i < r.nx; i += kBlock) sbx[i] = r.bin_x[i];
-        for (int i = threadIdx.x; i < r.ny; i += kBlock) sby[i] = r.bin_y[i];
-        __syncthreads();
+        bool okx = step_x > 0.0, oky = step_y > 0.0;
+        for (int i = threadIdx.x; i < r.nx; i += kBlock) {
+            const double e = r.bin_x[i];
+            sbx[i] = e;
+            okx = okx && fabs(e - (b0x + (double)i * step_x)) <= 1e-7 * step_x;
+        }
+        for (int i = threadIdx.x; i < r.ny; i += kBlock) {
+            const double e = r.bin_y[i];
+            sby[i] = e;
+            oky = oky && fabs(e - (b0y - (double)i * step_y)) <= 1e-7 * step_y;
+        }
+        uni_x = __syncthreads_and(okx) != 0;
+        uni_y = __syncthreads_and(oky) != 0;
     }
     const double* bx = SMEM_BINS ? sbx : r.bin_x;
     const double* by = SMEM_BINS ? sby : r.bin_y;
-    const double inv_step_x = r.nx >= 2 ? 1.0 / (bx[1] - bx[0]) : 0.0;
-    const double inv_step_y = r.ny >= 2 ? 1.0 / (by[0] - by[1]) : 0.0;
-    int64_t stride = (int64_t)gridDim.x * kBlock;
-    for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < n; i += stride) {
-        bool s = sel ? (sel[i] != 0) : true;
-        if (CLASSIFY) {
-            bool res = false;
-            if (s) {
-                double v = raster_value<SMEM_BINS>(r, sbx, sby, inv_step_x, inv_step_y, x[i], y[i]);
-                res = classify_height(mode, z[i], v, a, b);
+    const double inv_step_x = step_x != 0.0 ? 1.0 / step_x : 0.0;
+    const double inv_step_y = step_y != 0.0 ? 1.0 / step_y : 0.0;
+    constexpr int kTile = kPerThread * kBlock;
+    for (int64_t base = (int64_t)blockIdx.x * kTile; base < n; base += (int64_t)gridDim.x * kTile) {
+        bool s[kPerThread];
+        double px[kPerThread], py[kPerThread], pz[kPerThread], v[kPerThread];
+#pragma unroll
+        for (int u = 0; u < kPerThread; ++u) {
+            const int64_t i = base + u * kBlock + threadIdx.x;
+            s[u] = i < n && (sel ? (sel[i] != 0) : true);
+        }
+#pragma unroll
+        for (int u = 0; u < kPerThread; ++u) {
+            const int64_t i = base + u * kBlock + threadIdx.x;
+            px[u] = py[u] = pz[u] = 0.0;
+            if (s[u]) {
+                px[u] = x[i]; py[u] = y[i];
+                if (CLASSIFY) pz[u] = z[i];
             }
-            if (out_mask) out_mask[i] = res ? 1 : 0;
-            if (labels && res) labels[i] = assign;
-        } else {
-            if (s) out_val[i] = raster_value<SMEM_BINS>(r, sbx, sby, inv_step_x, inv_step_y, x[i], y[i]);
+        }
+#pragma unroll
+        for (int u = 0; u < kPerThread; ++u) {
+            v[u] = 0.0;
+            if (s[u]) {
+                const int ix = raster_axis<true>(bx, r.nx, uni_x, (px[u] - b0x) * inv_step_x, px[u]);
+                const int iy = raster_axis<false>(by, r.ny, uni_y, (b0y - py[u]) * inv_step_y, py[u]);
+                v[u] = __ldg(r.values + (size_t)iy * r.nx + ix);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < kPerThread; ++u) {
+            const int64_t i = base + u * kBlock + threadIdx.x;
+            if (CLASSIFY) {
+                const bool res = s[u] && classify_height(mode, pz[u], v[u], a, b);
+                if (i < n && out_mask) out_mask[i] = res ? 1 : 0;
+                if (labels && res) labels[i] = assign;
+            } else {
+                if (s[u]) out_val[i] = v[u];
+            }
         }
     }
 }
@@ -79,13 +123,19 @@ static int launch_raster(bool classify, const double* d_x, const double* d_y, co
                          int32_t assign, cudaStream_t st) {
     RasterParams r;
     r.bin_x = d_bin_x; r.nx = nx; r.bin_y = d_bin_y; r.ny = ny; r.values = d_values;
-    int grid = grid_for(n, kBlock);
     bool smem_bins = nx <= kMaxBinsSmem && ny <= kMaxBinsSmem;
     size_t smem = smem_bins ? (size_t)(nx + ny) * sizeof(double) : 0;
     prof_begin(UPCP_PROF_RASTER, st);
-#define UPCP_RASTER_LAUNCH(SB, CL)                                                   \
-    raster_kernel<SB, CL><<<grid, kBlock, smem, st>>>(d_x, d_y, d_z, n, d_sel, r, mode, a, b, \
-                                                     d_out_val, d_out_mask, d_labels, assign)
+    // one wave of resident CTAs (the kernel strides over tiles of kPerThread x kBlock points): a grid
+    // larger than what is resident would run its tail at partial occupancy
+#define UPCP_RASTER_LAUNCH(SB, CL)                                                                       \
+    do {                                                                                                 \
+        int per_sm = 0;                                                                                  \
+        UPCP_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, raster_kernel<SB, CL>, kBlock, smem)); \
+        int grid = grid_for((n + kPerThread - 1) / kPerThread, kBlock, per_sm < 1 ? 1 : per_sm);         \
+        raster_kernel<SB, CL><<<grid, kBlock, smem, st>>>(d_x, d_y, d_z, n, d_sel, r, mode, a, b,        \
+                                                         d_out_val, d_out_mask, d_labels, assign);       \
+    } while (0)
     if (smem_bins) { if (classify) UPCP_RASTER_LAUNCH(true, true); else UPCP_RASTER_LAUNCH(true, false); }
     else           { if (classify) UPCP_RASTER_LAUNCH(false, true); else UPCP_RASTER_LAUNCH(false, false); }
 #undef UPCP_RASTER_LAUNCH
