@@ -52,8 +52,9 @@ raster_kernel(const double* __restrict__ x, const double* __restrict__ y,
     double* sbx = s_bins;
     double* sby = s_bins + (SMEM_BINS ? r.nx : 0);
     const double b0x = r.bin_x[0], b0y = r.bin_y[0];
-    const double step_x = r.nx >= 2 ? r.bin_x[1] - b0x : 0.0;
-    const double step_y = r.ny >= 2 ? b0y - r.bin_y[1] : 0.0;
+    // the mean step over the whole axis: the difference of two neighbouring edges carries their rounding
+    const double step_x = r.nx >= 2 ? (r.bin_x[r.nx - 1] - b0x) / (double)(r.nx - 1) : 0.0;
+    const double step_y = r.ny >= 2 ? (b0y - r.bin_y[r.ny - 1]) / (double)(r.ny - 1) : 0.0;
     bool uni_x = false, uni_y = false;
     if (SMEM_BINS) {
         bool okx = step_x > 0.0, oky = step_y > 0.0;
