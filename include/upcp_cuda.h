@@ -84,7 +84,10 @@ typedef struct upcp_tuning {
     int32_t knn_coarse;           /* cell factor of the per-query tier's second grid (1 = none)          */
     int32_t grow_local_chain;     /* region growth: warp-local continuation cap (0..32)                  */
     int32_t grow_ctas_per_sm;     /* region growth: resident CTAs per SM of the persistent kernel (>= 1) */
-    int32_t reserved[10];
+    int32_t knn_guess_tenths;     /* block tiers: first histogram range = this / 10 x the k-th squared distance a
+                                     planar cloud of the block's point count would have (30 = 3.0)       */
+    int32_t knn_guess_max_pct;    /* ... tried only when below this percentage of the certifiable range  */
+    int32_t reserved[8];
 } upcp_tuning;
 void upcp_tuning_default(upcp_tuning* out);
 int  upcp_tuning_get(upcp_tuning* out);

@@ -1,17 +1,29 @@
-"""Per-kernel DRAM traffic / time / instruction counts from `ncu -i rep --page raw --csv`, in the format of
-profiles/r*_traffic.json (what bench.py reports as roofline.traffic).
-    python tools/traffic_from_raw.py raw.csv "<source description>" > profiles/rN_traffic.json"""
+"""Per-bracket DRAM traffic / time / instruction counts from `ncu --nvtx ... --page raw --csv`, in the format of
+profiles/r2_traffic.json (what bench.py reports as roofline.traffic).  A kernel belongs to every bracket whose NVTX
+range (api.cu pushes one per cudaEvent bracket, named like the bracket) is on its range stack; only the FIRST pipeline
+pass of the capture is counted (one launch of the S4 bracket).
+    python tools/traffic_from_raw.py raw.csv "<source description>" > profiles/r2_traffic.json"""
 import collections
 import csv
+import hashlib
 import json
+import os
 import sys
 
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 UNIT = {'byte': 1.0, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9, 'Tbyte': 1e12,
         'ns': 1e-6, 'us': 1e-3, 'ms': 1.0, 's': 1e3, 'inst': 1.0}
-# cudaEvent brackets of bench.py -> the kernels inside them
-BRACKETS = {'knn_search_kernel': ('knn_block_kernel', 'knn_select_kernel'),
-            'cc_link_kernel': ('cc_link_kernel',), 'raster_kernel': ('raster_kernel',),
-            'pip_query_kernel': ('pip_query_kernel',), 'grow_kernel': ('grow_kernel', 'grow_seed_pass_kernel')}
+BRACKETS = ['raster_kernel', 'pip_query_kernel', 'radix_sort (hist+scan+scatter)', 'cc_link_kernel',
+            'knn_stage (build+search+epilogue)', 'grow_kernel', 'knn_build', 'knn_search (block tiers + per-query tier)',
+            'knn_epilogue_kernel']
+
+def sources_sha():
+    h = hashlib.sha256()
+    d = os.path.join(ROOT, 'urban_pointcloud_processing_b200', 'csrc')
+    for f in sorted(os.listdir(d)):
+        if f.endswith(('.cu', '.cuh')):
+            h.update(f.encode()); h.update(open(os.path.join(d, f), 'rb').read())
+    return h.hexdigest()[:16]
 
 
 def short(name):
@@ -32,30 +44,43 @@ def main(path, source):
     rows = list(csv.reader(open(path, errors='replace')))
     hdr, units = rows[0], rows[1]
     col = {h: i for i, h in enumerate(hdr)}
+    nvtx_cols = [i for i, h in enumerate(hdr) if 'Push/Pop' in h]
 
     def val(r, name):
         return float(r[col[name]].replace(',', '')) * UNIT.get(units[col[name]], 1.0)
     per = collections.OrderedDict()
+    br = {b: {'kernels': 0, 'dram_bytes': 0.0, 'time_ms': 0.0, 'calls': 0} for b in BRACKETS}
+    prev_inside = set()
+    grown = False
     for r in rows[2:]:
         if len(r) != len(hdr):
             continue
-        k = per.setdefault(short(r[col['Kernel Name']]), {'launches': 0, 'dram_read_bytes': 0.0, 'dram_write_bytes': 0.0,
-                                                            'time_ms': 0.0, 'warp_inst': 0.0})
+        stack = ' '.join(r[i] for i in nvtx_cols)
+        name = short(r[col['Kernel Name']])
+        inside = set(b for b in BRACKETS if b in stack)
+        grown = grown or 'grow_kernel' in inside
+        if grown and 'raster_kernel' in inside:
+            break                          # the second pipeline pass begins (AHNFuser's raster launch)
+        traffic = val(r, 'dram__bytes_read.sum') + val(r, 'dram__bytes_write.sum')
+        t = val(r, 'gpu__time_duration.sum')
+        k = per.setdefault(name, {'launches': 0, 'dram_read_bytes': 0.0, 'dram_write_bytes': 0.0, 'time_ms': 0.0,
+                                  'warp_inst': 0.0})
         k['launches'] += 1
         k['dram_read_bytes'] += val(r, 'dram__bytes_read.sum')
         k['dram_write_bytes'] += val(r, 'dram__bytes_write.sum')
-        k['time_ms'] += val(r, 'gpu__time_duration.sum')
+        k['time_ms'] += t
         k['warp_inst'] += val(r, 'smsp__inst_executed.sum')
-    brackets = {}
-    for name, parts in BRACKETS.items():
-        ks = [v for k, v in per.items() if any(k.startswith(p) for p in parts)]
-        if not ks:
-            continue
-        total = sum(v['dram_read_bytes'] + v['dram_write_bytes'] for v in ks)
-        # one bracket per pipeline pass for the search / growth, one per launch otherwise
-        launches = max(v['launches'] for v in ks) if len(parts) == 1 else min(v['launches'] for v in ks)
-        brackets[name] = total / max(launches, 1)
-    json.dump({'source': source, 'per_kernel': per, 'bracket_traffic_bytes_per_launch': brackets}, sys.stdout, indent=1)
+        for b in inside:
+            br[b]['kernels'] += 1; br[b]['dram_bytes'] += traffic; br[b]['time_ms'] += t
+            if b not in prev_inside:       # a bracket = one contiguous group of launches carrying its range
+                br[b]['calls'] += 1
+        prev_inside = inside
+    out = {b: {'calls': v['calls'], 'kernels': v['kernels'], 'bytes': v['dram_bytes'], 'time_ms': v['time_ms']}
+           for b, v in br.items() if v['kernels']}
+    json.dump({'source': source, 'csrc_sha': sources_sha(), 'per_kernel': per, 'brackets_first_pass': out,
+               'bracket_traffic_bytes_per_launch': {b: v['bytes'] / max(v['calls'], 1) for b, v in out.items()},
+               'note': 'cudaMemsetAsync of the 4 B x G cell table (~270 MB per S4 launch) is not a kernel and is not in these sums'},
+              sys.stdout, indent=1)
     print()
 
 

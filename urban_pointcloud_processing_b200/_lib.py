@@ -31,7 +31,7 @@ class Tuning(Structure):
     """``upcp_tuning`` of include/upcp_cuda.h (explicit, process-wide kernel tuning knobs)."""
     _fields_ = [('knn_tiers', c_int32), ('knn_tier1_max_block', c_int32), ('knn_tier2_max_block', c_int32),
                 ('knn_coarse', c_int32), ('grow_local_chain', c_int32), ('grow_ctas_per_sm', c_int32),
-                ('reserved', c_int32 * 10)]
+                ('knn_guess_tenths', c_int32), ('knn_guess_max_pct', c_int32), ('reserved', c_int32 * 8)]
 
 
 _PROTOTYPES = {

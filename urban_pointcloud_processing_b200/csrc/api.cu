@@ -47,6 +47,8 @@ static void tuning_defaults(upcp_tuning* t) {
     t->knn_coarse = 2;
     t->grow_local_chain = 2;
     t->grow_ctas_per_sm = 1;
+    t->knn_guess_tenths = 30;
+    t->knn_guess_max_pct = 25;
 }
 
 upcp_tuning tuning() {
@@ -138,7 +140,8 @@ int upcp_tuning_set(const upcp_tuning* in) {
     if (!in) UPCP_FAIL(UPCP_E_INVALID, "tuning_set: NULL");
     if (in->knn_tiers < 1 || in->knn_tiers > 2 || in->knn_tier1_max_block < 1 || in->knn_tier1_max_block > 60000 ||
         in->knn_tier2_max_block < 1 || in->knn_tier2_max_block > 60000 || in->knn_coarse < 1 || in->knn_coarse > 16 ||
-        in->grow_local_chain < 0 || in->grow_local_chain > 32 || in->grow_ctas_per_sm < 1 || in->grow_ctas_per_sm > 8)
+        in->grow_local_chain < 0 || in->grow_local_chain > 32 || in->grow_ctas_per_sm < 1 || in->grow_ctas_per_sm > 8 ||
+        in->knn_guess_tenths < 5 || in->knn_guess_tenths > 1000 || in->knn_guess_max_pct < 0 || in->knn_guess_max_pct > 100)
         UPCP_FAIL(UPCP_E_INVALID, "tuning_set: value out of range");
     std::lock_guard<std::mutex> lk(upcp::g_tune_mu);
     upcp::g_tune = *in;

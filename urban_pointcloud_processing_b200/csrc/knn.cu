@@ -197,6 +197,7 @@ struct BlockArgs {
     uint8_t* todo;                                     // [m] 1 = not served by this tier
     int k_row; double radius2;                         // kNN row length, squared normal-estimation radius
     uint32_t max_total;                                // blocks with more candidates go to the next tier (<= 60000: u16 counters)
+    double guess_factor, guess_max_share;              // first histogram range (upcp_tuning.knn_guess_*)
 };
 
 // One lane per query; see the header comment.  The per-lane histogram is kBuckets counters in
@@ -249,6 +250,38 @@ knn_block_kernel(BlockArgs a) {
         const double tau_full = reach * reach * (1.0 - 1e-9);
         const int x0 = max(cx - R, 0), x1 = min(cx + R, g.nx - 1);
         bool active = valid && reach > 0.0;
+        // Pruning inside the block.  Both passes only look at candidates below a squared distance (the
+        // histogram range, then the keep limit) that in dense surroundings is far smaller than a cell: a
+        // grid row -- or the outer cells of its x range -- whose nearest face lies beyond that distance
+        // cannot hold such a candidate and is not walked.  near(d, f): lower bound of the coordinate
+        // difference to any point of the d-th cell from the query's own, f = the query's offset inside its
+        // cell; fp32 with the grid's assignment slack and a 2^-6 margin on the limit (the fp32 distance
+        // error is below 2^-8 of the range, see above), so the pruned set is exactly what the unpruned
+        // passes would have counted / kept.
+        const float cellf = (float)g.cell, slackf = (float)(g.slack + g.cell * 1e-6);
+        const float fxq = (float)(qp.x - (g.ox + (double)cx * g.cell));
+        const float fyq = (float)(qp.y - (g.oy + (double)cy * g.cell));
+        const float fzq = (float)(qp.z - (g.oz + (double)cz * g.cell));
+        auto near = [&](int d, float f) -> float {
+            if (d == 0) return 0.0f;
+            const float v = (d < 0 ? f + (float)(-d - 1) * cellf : (cellf - f) + (float)(d - 1) * cellf) - slackf;
+            return v > 0.0f ? v : 0.0f;
+        };
+        // x range of row (dy, dz) that can hold a candidate within sqrt(lim2): false = none
+        auto row_range = [&](int dy, int dz, float lim2, int& xa, int& xb) -> bool {
+            const float ay = near(dy, fyq), az = near(dz, fzq);
+            const float yz2 = ay * ay + az * az;
+            if (yz2 > lim2) return false;
+            int ea = 0, eb = 0;
+#pragma unroll
+            for (int d = 1; d <= R; ++d) {
+                const float a = near(-d, fxq), b = near(d, fxq);
+                if (a * a + yz2 <= lim2) ea = d;
+                if (b * b + yz2 <= lim2) eb = d;
+            }
+            xa = max(cx - ea, x0); xb = min(cx + eb, x1);
+            return true;
+        };
 
         // cheap certificate first: a block with fewer than k_row points cannot serve the query
         // (2 prefix lookups per row instead of a wasted counting pass)
@@ -274,8 +307,8 @@ knn_block_kernel(BlockArgs a) {
         double tau = tau_full;
         {
             const double side = (double)(2 * R + 1) * g.cell;
-            const double guess = 3.0 * (double)K * side * side / (3.141592653589793 * (double)(total > 0 ? total : 1));
-            if (guess < 0.25 * tau) tau = guess;        // only where the full range would be too coarse
+            const double guess = a.guess_factor * (double)K * side * side / (3.141592653589793 * (double)(total > 0 ? total : 1));
+            if (guess < a.guess_max_share * tau) tau = guess;        // only where the full range would be too coarse
         }
         auto fp32_ok = [&](double t) {
             const double err = 3.47 * sqrt(t) * delta + 3.0 * delta * delta + t * (1.0 / 4194304.0);
@@ -294,16 +327,18 @@ knn_block_kernel(BlockArgs a) {
                 for (int b = 0; b < kBuckets; ++b) HIST(b) = 0;
             }
             // ---- pass A: radial histogram of the block's candidates
+            const float lim_a = (float)(tau * (1.0 + 1.0 / 64.0));
 #pragma unroll 1
             for (int dz = -R; dz <= R; ++dz) {
 #pragma unroll 1
                 for (int dy = -R; dy <= R; ++dy) {
                     const int yy = cy + dy, zz = cz + dz;
                     uint32_t p = 0, pb = 0;
-                    if (counting && yy >= 0 && yy < g.ny && zz >= 0 && zz < g.nz) {
+                    int xa = x0, xb = x1;
+                    if (counting && yy >= 0 && yy < g.ny && zz >= 0 && zz < g.nz && row_range(dy, dz, lim_a, xa, xb)) {
                         const uint32_t row = ((uint32_t)zz * (uint32_t)g.ny + (uint32_t)yy) * (uint32_t)g.nx;
-                        p = __ldg(a.cell_first + row + x0);
-                        pb = __ldg(a.cell_first + row + x1 + 1);
+                        p = __ldg(a.cell_first + row + xa);
+                        pb = __ldg(a.cell_first + row + xb + 1);
                     }
                     for (; p + 1 < pb; p += 2) {
                         const float4 c0 = __ldg(a.spf + p), c1 = __ldg(a.spf + p + 1);
@@ -359,16 +394,18 @@ knn_block_kernel(BlockArgs a) {
         bool overflow = false;
         uint32_t kept = 0;
         if (__any_sync(kFull, active)) {
+            const float lim_b = (float)(((double)tkeep / (double)kBuckets + 1.0 / 64.0) * tau);
 #pragma unroll 1
             for (int dz = -R; dz <= R; ++dz) {
 #pragma unroll 1
                 for (int dy = -R; dy <= R; ++dy) {
                     const int yy = cy + dy, zz = cz + dz;
                     uint32_t p = 0, pb = 0;
-                    if (active && yy >= 0 && yy < g.ny && zz >= 0 && zz < g.nz) {
+                    int xa = x0, xb = x1;
+                    if (active && yy >= 0 && yy < g.ny && zz >= 0 && zz < g.nz && row_range(dy, dz, lim_b, xa, xb)) {
                         const uint32_t row = ((uint32_t)zz * (uint32_t)g.ny + (uint32_t)yy) * (uint32_t)g.nx;
-                        p = __ldg(a.cell_first + row + x0);
-                        pb = __ldg(a.cell_first + row + x1 + 1);
+                        p = __ldg(a.cell_first + row + xa);
+                        pb = __ldg(a.cell_first + row + xb + 1);
                     }
                     for (; p < pb; ++p) {
                         const float4 c0 = __ldg(a.spf + p);
@@ -909,6 +946,7 @@ static int knn_impl(const double* d_x, const double* d_y, const double* d_z, int
     // served by the warp-per-query tier, which prunes (swept on the bench tile: 60000 / 4000 / 1500 / 600 /
     // 300 candidates -> 17.6 / 17.4 / 17.2 / 16.5 / 17.0 ms for the search): upcp_tuning.knn_tier2_max_block.
     ba.max_total = (uint32_t)tune.knn_tier1_max_block;
+    ba.guess_factor = 0.1 * (double)tune.knn_guess_tenths; ba.guess_max_share = 0.01 * (double)tune.knn_guess_max_pct;
     // the filter passes live on L1 hits (each candidate is read by ~150 queries, twice): keep the
     // shared-memory carve-out at what the resident CTAs need, the rest of the 256 KB stays L1
     UPCP_CUDA_OK(cudaFuncSetAttribute(knn_block_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, 40));
