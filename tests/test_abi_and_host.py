@@ -461,3 +461,32 @@ def test_ahn_reader_cache_is_safe_under_concurrent_tiles(tmp_path, monkeypatch):
     # caching off: still the right tile, nothing kept
     reader.set_caching(False)
     assert reader.filter_tile(codes[1])['ground_surface'][0, 0] == 1.0 and len(reader._tiles) == 0
+
+
+def test_per_thread_diagnostics():
+    """one processor object is driven by several worker threads; what a call leaves behind for
+    inspection belongs to the calling thread (abstract_processor.PerThread)."""
+    import threading
+    from urban_pointcloud_processing_b200.abstract_processor import PerThread
+
+    class P:
+        last = PerThread(list)
+        level = PerThread(lambda: None)
+
+    p, q = P(), P()
+    p.last = ['main']
+    seen = {}
+
+    def work(k):
+        assert p.last == [] and p.level is None            # a fresh thread reads the default, not main's value
+        p.last = [k]
+        p.level = k
+        barrier.wait()
+        seen[k] = (list(p.last), p.level)
+
+    barrier = threading.Barrier(2)
+    ts = [threading.Thread(target=work, args=(k,)) for k in (1, 2)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    assert seen == {1: ([1], 1), 2: ([2], 2)}
+    assert p.last == ['main'] and q.last == [] and p.level is None

@@ -11,11 +11,44 @@ Every processor exposes
   * ``_label_mask_device(tile, d_labels, d_mask, tilecode) -> uint8 cuda tensor`` --
     the device-resident form the Pipeline chains without leaving HBM.
 """
+import threading
 from abc import ABC, abstractmethod
 
 import numpy as np
 
 from . import device as dev
+
+
+class PerThread:
+    """Diagnostic attribute with one value per host thread.
+
+    ``Pipeline.process_clouds`` / ``process_folder(workers=W)`` drive ONE processor object from W threads, each on
+    its own tile; what a call leaves behind for inspection (``last_timings``, ``last_stats``, ``last_objects``,
+    ``octree_level``) belongs to the thread that made the call, so that a worker never reads -- or, in
+    ``CarFuser``, clips with -- another tile's value.  A thread that has not set the attribute reads the default."""
+
+    def __init__(self, factory):
+        self.factory = factory
+
+    def __set_name__(self, owner, name):
+        self.name = name
+
+    def _store(self, obj):
+        store = obj.__dict__.get('_per_thread')
+        if store is None:
+            store = obj.__dict__.setdefault('_per_thread', threading.local())
+        return store
+
+    def __get__(self, obj, owner=None):
+        if obj is None:
+            return self
+        store = self._store(obj)
+        if not hasattr(store, self.name):
+            setattr(store, self.name, self.factory())
+        return getattr(store, self.name)
+
+    def __set__(self, obj, value):
+        setattr(self._store(obj), self.name, value)
 
 
 class AbstractProcessor(ABC):

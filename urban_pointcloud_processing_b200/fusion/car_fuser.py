@@ -10,7 +10,7 @@ import logging
 
 import numpy as np
 
-from ..abstract_processor import AbstractProcessor
+from ..abstract_processor import AbstractProcessor, PerThread
 from ..labels import Labels
 from ..region_growing.label_connected_comp import lcc_device
 from ..utils import object_utils
@@ -31,6 +31,8 @@ class CarFuser(AbstractProcessor):
     bgt_reader : BGTPolyReader object
         Used to load road part polygons.
     """
+
+    last_objects = PerThread(list)      # accepted (ring, bottom, top) boxes of the calling thread's last tile
 
     def __init__(self, label, ahn_reader, bgt_reader, grid_size=0.05, min_component_size=5000,
                  overlap_perc=20, params={}, exclude_types=["fietspad", "voetpad"]):
@@ -76,7 +78,7 @@ class CarFuser(AbstractProcessor):
         d_comp, _, _ = lcc_device(tile, d_mask, self.grid_size, self.min_component_size, level_from='sel',
                                   want_comp=True, want_fill=False)
         stats = object_utils.ComponentStats(tile, d_comp, d_gz)
-        self.last_objects = self._car_like_objects(stats, road_polygons, **self.params)
-        logger.debug(f'{len(self.last_objects)} cars labelled.')
-        return object_utils.prism_clip_device(tile, d_mask, [o[0] for o in self.last_objects],
-                                              [(o[1], o[2]) for o in self.last_objects])
+        objects = self._car_like_objects(stats, road_polygons, **self.params)
+        self.last_objects = objects
+        logger.debug(f'{len(objects)} cars labelled.')
+        return object_utils.prism_clip_device(tile, d_mask, [o[0] for o in objects], [(o[1], o[2]) for o in objects])

@@ -18,6 +18,7 @@ import time
 import numpy as np
 
 from . import device as dev
+from .abstract_processor import PerThread
 from .analysis import analysis_tools
 from .utils import las_utils
 
@@ -40,6 +41,8 @@ class Pipeline:
     """
 
     FILE_TYPES = ('.LAS', '.las', '.LAZ', '.laz')
+
+    last_timings = PerThread(list)      # (processor, seconds) of the calling thread's last tile
 
     def __init__(self, processors=[], exclude_labels=[], ahn_reader=None, caching=True):
         if ahn_reader is None and caching:

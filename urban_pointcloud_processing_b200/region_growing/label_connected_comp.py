@@ -16,7 +16,7 @@ import torch
 
 from .. import _lib
 from .. import device as dev
-from ..abstract_processor import AbstractProcessor
+from ..abstract_processor import AbstractProcessor, PerThread
 from ..labels import Labels
 
 logger = logging.getLogger(__name__)
@@ -79,6 +79,8 @@ class LabelConnectedComp(AbstractProcessor):
         When labelling a cluster, at least this proportion of points should already be
         labelled.
     """
+
+    octree_level = PerThread(lambda: None)      # level of the calling thread's last call
 
     def __init__(self, label=-1, exclude_labels=[], set_debug=False, grid_size=0.1,
                  min_component_size=100, threshold=0.1):

@@ -17,7 +17,7 @@ import torch
 
 from .. import _lib
 from .. import device as dev
-from ..abstract_processor import AbstractProcessor
+from ..abstract_processor import AbstractProcessor, PerThread
 from ..labels import Labels
 
 logger = logging.getLogger(__name__)
@@ -349,6 +349,8 @@ class RegionGrowing(AbstractProcessor):
     """
 
     ignores_mask = True        # _set_mask (region_growing.py:34-49) replaces the incoming mask
+
+    last_stats = PerThread(dict)        # counters of the calling thread's last call
 
     def __init__(self, label, exclude_labels=[], threshold_angle=20, threshold_curve=1.0, max_nn=30,
                  grow_region_knn=15, grow_region_radius=0.2):
