@@ -100,6 +100,24 @@ def test_mask_and_label_kernels():
         host = labels.copy()
         assert dev.download_labels(d_labels, host) is host and np.array_equal(host, want)
         assert np.array_equal(dev.label_hist(d_labels).cpu().numpy(), R.label_histogram(want))
+    # the stream kernels take 4 / 16 elements per thread when the buffers are aligned: ragged sizes and views that
+    # start at an odd element (unaligned pointers) must take the element-wise path to the same result
+    import torch
+    for n in (0, 1, 3, 17, 4099):
+        for off in (0, 1, 3):
+            labels = rng.choice(np.array([0, 1, 9, 10]), size=n + off).astype(np.int32)
+            mask = rng.random(n + off) < 0.5
+            other = rng.random(n + off) < 0.5
+            d_l = torch.from_numpy(labels).to(device)[off:]
+            d_m = dev.upload_mask(mask, n + off, device)[off:]
+            d_o = dev.upload_mask(other, n + off, device)[off:]
+            l, m, o = labels[off:], mask[off:], other[off:]
+            assert np.array_equal(dev.download_mask(dev.mask_build(d_l, d_m, eq=(10,), ne=(9,))), (m | (l == 10)) & (l != 9))
+            assert np.array_equal(dev.download_mask(dev.mask_combine(d_m, d_o, 'andnot')), m & ~o)
+            assert dev.mask_count(d_m) == m.sum()
+            dev.labels_assign(d_l, d_m, 7)
+            want = l.copy(); want[m] = 7
+            assert np.array_equal(d_l.cpu().numpy(), want)
 
 
 def test_las_ingest_scaled_on_device_and_process_file(tmp_path):

@@ -17,6 +17,9 @@ BRACKETS = ['raster_kernel', 'pip_query_kernel', 'radix_sort (hist+scan+scatter)
             'knn_stage (build+search+epilogue)', 'grow_kernel', 'knn_build', 'knn_search (block tiers + per-query tier)',
             'knn_epilogue_kernel']
 
+SINGLE = ('raster_kernel', 'pip_query_kernel', 'knn_epilogue_kernel')     # one kernel launch per bracket
+
+
 def sources_sha():
     h = hashlib.sha256()
     d = os.path.join(ROOT, 'urban_pointcloud_processing_b200', 'csrc')
@@ -72,7 +75,9 @@ def main(path, source):
         k['warp_inst'] += val(r, 'smsp__inst_executed.sum')
         for b in inside:
             br[b]['kernels'] += 1; br[b]['dram_bytes'] += traffic; br[b]['time_ms'] += t
-            if b not in prev_inside:       # a bracket = one contiguous group of launches carrying its range
+            # a bracket = one launch of the kernel it is named after, else one contiguous group of launches
+            # carrying its range
+            if name.split('<')[0] == b or (b not in SINGLE and b not in prev_inside):
                 br[b]['calls'] += 1
         prev_inside = inside
     out = {b: {'calls': v['calls'], 'kernels': v['kernels'], 'bytes': v['dram_bytes'], 'time_ms': v['time_ms']}

@@ -21,8 +21,8 @@
 //     the set, 1 = every point is, 2 = an edge passes through or next to the cell.  The crossing rule of
 //     the reference is the consistent half-open one (an edge is counted iff its other end lies strictly
 //     above the ray, clip_utils.py:139-160), so the result is constant over any cell no edge comes near;
-//     such a cell is classified ONCE on the host with the exact test (one evaluation per connected group
-//     of cells) and its points need one byte lookup instead of the ring / slab / edge walk.  Only the
+//     such a cell is classified ONCE with the exact test at its centre (three small kernels right after
+//     the upload) and its points need one byte lookup instead of the ring / slab / edge walk.  Only the
 //     thin band of cells along the edges (inflated by a cell: rounding of the index arithmetic, points
 //     within rounding of an edge) runs the exact test.
 // The plan is a few MB at most and stays L2-resident; the point stream is read

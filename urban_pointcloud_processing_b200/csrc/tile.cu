@@ -162,46 +162,83 @@ struct LabelSets {
     int n_eq, n_ne;
 };
 
+__device__ __forceinline__ bool mask_rule(int32_t l, bool m, const LabelSets& sets) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) if (k < sets.n_eq) m = m || (l == sets.eq[k]);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) if (k < sets.n_ne) m = m && (l != sets.ne[k]);
+    return m;
+}
+
+// The glue kernels are pure streams: four elements per thread through 16-byte label and 4-byte mask accesses
+// (the entry points check the alignment; the tail is finished element-wise by the same kernel).
 __global__ void __launch_bounds__(kBlock)
 mask_build_kernel(const int32_t* __restrict__ labels, int64_t n,
                   const uint8_t* __restrict__ mask_in, int base, LabelSets sets,
-                  uint8_t* __restrict__ out) {
-    int64_t stride = (int64_t)gridDim.x * kBlock;
-    for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < n; i += stride) {
-        int32_t l = labels[i];
-        bool m = mask_in ? (mask_in[i] != 0) : (base != 0);
-#pragma unroll
-        for (int k = 0; k < 8; ++k) if (k < sets.n_eq) m = m || (l == sets.eq[k]);
-#pragma unroll
-        for (int k = 0; k < 8; ++k) if (k < sets.n_ne) m = m && (l != sets.ne[k]);
-        out[i] = m ? 1 : 0;
+                  uint8_t* __restrict__ out, int vec) {
+    const int64_t stride = (int64_t)gridDim.x * kBlock;
+    const int64_t tid = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+    const int64_t n4 = vec ? n >> 2 : 0;
+    for (int64_t i = tid; i < n4; i += stride) {
+        const int4 l = reinterpret_cast<const int4*>(labels)[i];
+        uchar4 mi = make_uchar4(base != 0, base != 0, base != 0, base != 0);
+        if (mask_in) mi = reinterpret_cast<const uchar4*>(mask_in)[i];
+        uchar4 o;
+        o.x = mask_rule(l.x, mi.x != 0, sets); o.y = mask_rule(l.y, mi.y != 0, sets);
+        o.z = mask_rule(l.z, mi.z != 0, sets); o.w = mask_rule(l.w, mi.w != 0, sets);
+        reinterpret_cast<uchar4*>(out)[i] = o;
     }
+    for (int64_t i = (n4 << 2) + tid; i < n; i += stride)
+        out[i] = mask_rule(labels[i], mask_in ? (mask_in[i] != 0) : (base != 0), sets) ? 1 : 0;
 }
 
 __global__ void __launch_bounds__(kBlock)
 mask_combine_kernel(const uint8_t* __restrict__ a, const uint8_t* __restrict__ b,
-                    int64_t n, int op, uint8_t* __restrict__ out) {
-    int64_t stride = (int64_t)gridDim.x * kBlock;
-    for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < n; i += stride) {
-        bool va = a[i] != 0, vb = b[i] != 0;
-        bool r = (op == 0) ? (va && vb) : (op == 1) ? (va || vb) : (va && !vb);
-        out[i] = r ? 1 : 0;
+                    int64_t n, int op, uint8_t* __restrict__ out, int vec) {
+    const int64_t stride = (int64_t)gridDim.x * kBlock;
+    const int64_t tid = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+    auto rule = [op](uint8_t x, uint8_t y) -> uint8_t {
+        const bool va = x != 0, vb = y != 0;
+        return ((op == 0) ? (va && vb) : (op == 1) ? (va || vb) : (va && !vb)) ? 1 : 0;
+    };
+    const int64_t n4 = vec ? n >> 2 : 0;
+    for (int64_t i = tid; i < n4; i += stride) {
+        const uchar4 x = reinterpret_cast<const uchar4*>(a)[i], y = reinterpret_cast<const uchar4*>(b)[i];
+        reinterpret_cast<uchar4*>(out)[i] = make_uchar4(rule(x.x, y.x), rule(x.y, y.y), rule(x.z, y.z), rule(x.w, y.w));
     }
+    for (int64_t i = (n4 << 2) + tid; i < n; i += stride) out[i] = rule(a[i], b[i]);
 }
 
 __global__ void __launch_bounds__(kBlock)
 labels_assign_kernel(int32_t* __restrict__ labels, int64_t n,
-                     const uint8_t* __restrict__ mask, int32_t value) {
-    int64_t stride = (int64_t)gridDim.x * kBlock;
-    for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < n; i += stride)
+                     const uint8_t* __restrict__ mask, int32_t value, int vec) {
+    const int64_t stride = (int64_t)gridDim.x * kBlock;
+    const int64_t tid = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+    const int64_t n4 = vec ? n >> 2 : 0;
+    for (int64_t i = tid; i < n4; i += stride) {
+        const uchar4 m = reinterpret_cast<const uchar4*>(mask)[i];
+        int32_t* l = labels + (i << 2);
+        if (m.x) l[0] = value;
+        if (m.y) l[1] = value;
+        if (m.z) l[2] = value;
+        if (m.w) l[3] = value;
+    }
+    for (int64_t i = (n4 << 2) + tid; i < n; i += stride)
         if (mask[i]) labels[i] = value;
 }
 
 __global__ void __launch_bounds__(kBlock)
-mask_count_kernel(const uint8_t* __restrict__ mask, int64_t n, unsigned long long* __restrict__ out) {
+mask_count_kernel(const uint8_t* __restrict__ mask, int64_t n, unsigned long long* __restrict__ out, int vec) {
     unsigned long long c = 0;
-    int64_t stride = (int64_t)gridDim.x * kBlock;
-    for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < n; i += stride)
+    const int64_t stride = (int64_t)gridDim.x * kBlock;
+    const int64_t tid = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+    const int64_t n16 = vec ? n >> 4 : 0;
+    for (int64_t i = tid; i < n16; i += stride) {
+        const uint4 w = reinterpret_cast<const uint4*>(mask)[i];
+        // (0xff in every non-zero byte) -> 8 bits per counted element
+        c += (__popc(__vcmpne4(w.x, 0u)) + __popc(__vcmpne4(w.y, 0u)) + __popc(__vcmpne4(w.z, 0u)) + __popc(__vcmpne4(w.w, 0u))) >> 3;
+    }
+    for (int64_t i = (n16 << 4) + tid; i < n; i += stride)
         c += mask[i] != 0;
     c = warp_sum(c);
     __shared__ unsigned long long s[kBlock / 32];
@@ -233,6 +270,8 @@ label_hist_kernel(const int32_t* __restrict__ labels, int64_t n, unsigned long l
 }  // namespace upcp
 
 using namespace upcp;
+
+static inline int aligned_to(const void* p, size_t a) { return ((uintptr_t)p % a) == 0; }   // NULL counts as aligned
 
 namespace upcp {
 // x = X * scale + offset in fp64, two roundings (this translation unit is compiled without FMA
@@ -317,7 +356,8 @@ int upcp_mask_build(const int32_t* d_labels, int64_t n, const uint8_t* d_mask_in
     LabelSets sets;
     sets.n_eq = n_eq; sets.n_ne = n_ne;
     for (int k = 0; k < 8; ++k) { sets.eq[k] = k < n_eq ? h_eq[k] : 0; sets.ne[k] = k < n_ne ? h_ne[k] : 0; }
-    mask_build_kernel<<<grid_for(n, kBlock), kBlock, 0, (cudaStream_t)stream>>>(d_labels, n, d_mask_in, base, sets, d_out);
+    mask_build_kernel<<<grid_for((n + 3) / 4, kBlock), kBlock, 0, (cudaStream_t)stream>>>(d_labels, n, d_mask_in, base, sets, d_out,
+        aligned_to(d_labels, 16) && aligned_to(d_mask_in, 4) && aligned_to(d_out, 4));
     UPCP_LAUNCH_OK();
     return UPCP_OK;
 }
@@ -326,7 +366,8 @@ int upcp_mask_combine(const uint8_t* d_a, const uint8_t* d_b, int64_t n, int op,
                       uint8_t* d_out, void* stream) {
     if (n < 0 || op < 0 || op > 2) UPCP_FAIL(UPCP_E_INVALID, "mask_combine: bad op");
     if (n == 0) return UPCP_OK;
-    mask_combine_kernel<<<grid_for(n, kBlock), kBlock, 0, (cudaStream_t)stream>>>(d_a, d_b, n, op, d_out);
+    mask_combine_kernel<<<grid_for((n + 3) / 4, kBlock), kBlock, 0, (cudaStream_t)stream>>>(d_a, d_b, n, op, d_out,
+        aligned_to(d_a, 4) && aligned_to(d_b, 4) && aligned_to(d_out, 4));
     UPCP_LAUNCH_OK();
     return UPCP_OK;
 }
@@ -334,7 +375,8 @@ int upcp_mask_combine(const uint8_t* d_a, const uint8_t* d_b, int64_t n, int op,
 int upcp_labels_assign(int32_t* d_labels, int64_t n, const uint8_t* d_mask, int32_t value, void* stream) {
     if (n < 0) UPCP_FAIL(UPCP_E_INVALID, "labels_assign: n < 0");
     if (n == 0) return UPCP_OK;
-    labels_assign_kernel<<<grid_for(n, kBlock), kBlock, 0, (cudaStream_t)stream>>>(d_labels, n, d_mask, value);
+    labels_assign_kernel<<<grid_for((n + 3) / 4, kBlock), kBlock, 0, (cudaStream_t)stream>>>(d_labels, n, d_mask, value,
+        aligned_to(d_labels, 16) && aligned_to(d_mask, 4));
     UPCP_LAUNCH_OK();
     return UPCP_OK;
 }
@@ -344,7 +386,7 @@ int upcp_mask_count(const uint8_t* d_mask, int64_t n, int64_t* d_count, void* st
     cudaStream_t st = (cudaStream_t)stream;
     UPCP_CUDA_OK(cudaMemsetAsync(d_count, 0, sizeof(int64_t), st));
     if (n == 0) return UPCP_OK;
-    mask_count_kernel<<<grid_for(n, kBlock, 4), kBlock, 0, st>>>(d_mask, n, (unsigned long long*)d_count);
+    mask_count_kernel<<<grid_for((n + 15) / 16, kBlock, 4), kBlock, 0, st>>>(d_mask, n, (unsigned long long*)d_count, aligned_to(d_mask, 16));
     UPCP_LAUNCH_OK();
     return UPCP_OK;
 }
