@@ -17,7 +17,10 @@ import bench as B
 GOLDEN_DEMO = os.path.join(B.ROOT, 'tests', 'golden', 'demo')
 
 
-def _timed(torch, fn, reps, warm=1):
+_SAMPLER = None          # nvidia-smi clocks / throttle reasons; the window is the first (device-resident) timed region
+
+
+def _timed(torch, fn, reps, warm=3):
     for _ in range(warm):
         fn()
     torch.cuda.synchronize()
@@ -29,7 +32,10 @@ def _timed(torch, fn, reps, warm=1):
         out = fn()
     e1.record()
     torch.cuda.synchronize()
-    wall = (time.perf_counter() - t0) * 1e3
+    t1 = time.perf_counter()
+    wall = (t1 - t0) * 1e3
+    if _SAMPLER is not None and getattr(_SAMPLER, 't0', None) is None:
+        _SAMPLER.window(t0, t1)
     return max(e0.elapsed_time(e1), 0.0) / reps, wall / reps, out
 
 
@@ -45,10 +51,10 @@ def _line(args, metric, workload, value, ms, extra, roofline, cpu, e2e, launches
     if roofline is not None:
         roofline = dict(roofline, bound='hbm', peak=peak, unit='GB/s', frac=roofline['achieved'] / peak, peak_source=peak_src,
                         traffic=None, csrc_sha=B.sources_sha())
-    line = {'metric': metric, 'value': value, 'unit': 'Mpts/s', 'n_gpus': 1, 'steps': args.steps, 'warmup': max(args.warmup, 1),
+    line = {'metric': metric, 'value': value, 'unit': 'Mpts/s', 'n_gpus': 1, 'steps': args.steps, 'warmup': max(args.warmup, 3),
             'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
             'data': 'synthetic', 'config': dict({'workload': workload}, **extra), 'e2e': e2e, 'gpu_launches': int(launches),
-            'roofline': roofline, 'cpu_baseline': cpu}
+            'roofline': roofline, 'cpu_baseline': cpu, 'clocks': _SAMPLER.stop() if _SAMPLER is not None else None}
     print(json.dumps(line))
 
 
@@ -95,7 +101,7 @@ def config1(args, torch, dev, _lib):
         pipe.process_tile_device('2386_9702', tile, d_lab)
         rg._apply_device(tile, d_lab, None, '2386_9702')
     l0 = _lib.launch_count()
-    ms, wall, _ = _timed(torch, device_step, args.steps, warm=max(args.warmup, 1))
+    ms, wall, _ = _timed(torch, device_step, args.steps, warm=max(args.warmup, 3))
     launches = (_lib.launch_count() - l0) // (args.steps + max(args.warmup, 1))
     lab_pinned = torch.zeros(n, dtype=torch.int16).pin_memory()
     labels_host = lab_pinned.numpy().view(np.uint16)
@@ -290,7 +296,7 @@ def config4(args, torch, dev, _lib):
         pipe.process_tile_device(tc, tile, d_lab)
     _lib.prof_enable(True)
     l0 = _lib.launch_count()
-    ms, wall, _ = _timed(torch, step, args.steps, warm=max(args.warmup, 1))
+    ms, wall, _ = _timed(torch, step, args.steps, warm=max(args.warmup, 3))
     launches = (_lib.launch_count() - l0) // (args.steps + max(args.warmup, 1))
     prof = _lib.prof_read(); _lib.prof_enable(False)
     calls = args.steps + max(args.warmup, 1)
@@ -339,4 +345,7 @@ def run(args, rank, world):
     from urban_pointcloud_processing_b200 import device as dev
     _lib.require_cuda()
     torch.cuda.set_device(int(os.environ.get('LOCAL_RANK', '0')))
+    global _SAMPLER
+    _SAMPLER = B.ClockSampler(int(os.environ.get('LOCAL_RANK', '0')))
+    _SAMPLER.start()
     {1: config1, 2: config2, 3: config3, 4: config4}[args.config](args, torch, dev, _lib)
