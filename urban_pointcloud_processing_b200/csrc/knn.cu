@@ -618,42 +618,52 @@ knn_select_kernel(SelectArgs a) {
         int Rdone = -1, Rn = 1;
         const int Rmax = max(g.nx, max(g.ny, g.nz));
         while (true) {
-            // (only rows that exist: the grid may be much shorter than the radius along y or z)
-            const int ylo = max(cy - Rn, 0), yhi = min(cy + Rn, g.ny - 1);
-            const int zlo = max(cz - Rn, 0), zhi = min(cz + Rn, g.nz - 1);
-            const int wy = yhi - ylo + 1;
-            const int total = wy * (zhi - zlo + 1);
-            for (int t0 = 0; t0 < total; t0 += 32) {
-                const int t = t0 + lane;
-                uint32_t f1 = 0, n1 = 0, f2 = 0, n2 = 0;
-                if (t < total) {
-                    const int yy = ylo + t % wy, zz = zlo + t / wy;
-                    const int dy = yy - cy, dz = zz - cz;
-                    {
+            // Rows are taken ring by ring around the query's own row, nearest first: what the inner rings find
+            // tightens need_d before the outer rings are set up, and most of those are dropped before any load
+            // (an isolated point next to a dense surface meets the surface in a few rows, not in all of them).
+            for (int r = 0; r <= Rn; ++r) {
+                // the four edges of ring r: dy = -r, dy = +r, dz = -r, dz = +r
+                if (cy - r < 0 && cy + r >= g.ny && cz - r < 0 && cz + r >= g.nz) break;      // beyond the grid
+                if (need_d < inf) {
+                    const double gmin = fmax(0.0, (double)(r - 1) * g.cell - g.slack);          // (y, z) gap of every row of the ring
+                    if (gmin * gmin * (1.0 - 1e-9) > need_d) break;
+                }
+                const int ring_n = r == 0 ? 1 : 8 * r;
+                for (int j0 = 0; j0 < ring_n; j0 += 32) {
+                    const int j = j0 + lane;
+                    uint32_t f1 = 0, n1 = 0, f2 = 0, n2 = 0;
+                    int dy = 0, dz = 0;
+                    if (r > 0 && j < ring_n) {
+                        const int side = j / (2 * r), o = j - side * 2 * r;
+                        dy = side == 0 ? o - r : side == 1 ? r : side == 2 ? r - o : -r;
+                        dz = side == 0 ? -r : side == 1 ? o - r : side == 2 ? r : r - o;
+                    }
+                    const int yy = cy + dy, zz = cz + dz;
+                    if (j < ring_n && yy >= 0 && yy < g.ny && zz >= 0 && zz < g.nz) {
                         const double gy = axis_gap(qy, g.oy, yy, cy), gz = axis_gap(qz, g.oz, zz, cz);
                         const double lb_yz = (gy * gy + gz * gz) * (1.0 - 1e-9);
                         if (!(lb_yz > need_d)) {
                             const uint32_t row = ((uint32_t)zz * (uint32_t)g.ny + (uint32_t)yy) * (uint32_t)g.nx;
-                            // cells farther than this along x cannot matter any more
-                            int hw = Rn;
+                            // along x only the cells that overlap [qx - s, qx + s] can hold anything still needed,
+                            // s^2 = what the row's (y, z) gap leaves of need_d (plus the assignment slack)
+                            int xa = max(cx - Rn, 0), xb = min(cx + Rn, g.nx - 1);
                             if (need_d < inf) {
-                                const double h = (sqrt(need_d - lb_yz) + g.slack) * g.inv_cell + 2.0;
-                                if (h < (double)hw) hw = (int)h;
+                                const double sx = sqrt(need_d - lb_yz) * (1.0 + 1e-9) + 2.0 * g.slack;
+                                xa = max(xa, cell_coord(qx - sx, g.ox, g.inv_cell, g.nx));
+                                xb = min(xb, cell_coord(qx + sx, g.ox, g.inv_cell, g.nx));
                             }
-                            const int xa = max(cx - hw, 0), xb = min(cx + hw, g.nx - 1);
-                            const bool inner = dy >= -Rdone && dy <= Rdone && dz >= -Rdone && dz <= Rdone;
-                            if (!inner) {
+                            if (r > Rdone) {
                                 range(row + xa, row + xb, f1, n1);
-                            } else {
+                            } else {                                   // inside the finished block: the two end pieces
                                 const int xl = cx - Rdone - 1, xr = cx + Rdone + 1;
                                 if (xa <= xl) range(row + xa, row + xl, f1, n1);
                                 if (xr <= xb) range(row + xr, row + xb, f2, n2);
                             }
                         }
                     }
+                    if (__any_sync(kFull, n1 != 0)) process_ranges(f1, n1);
+                    if (__any_sync(kFull, n2 != 0)) process_ranges(f2, n2);
                 }
-                if (__any_sync(kFull, n1 != 0)) process_ranges(f1, n1);
-                if (__any_sync(kFull, n2 != 0)) process_ranges(f2, n2);
             }
             Rdone = Rn;
             // ---- termination: distance from the query to the unexplored region (warp-uniform)
