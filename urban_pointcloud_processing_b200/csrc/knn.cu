@@ -393,6 +393,10 @@ knn_block_kernel(BlockArgs a) {
         // ---- pass B: append the candidates of buckets <= b* (+ a quarter bucket) to the row
         bool overflow = false;
         uint32_t kept = 0;
+        // row slot s of query q lives at out_pos[s * m + q]: one 32 x 32 -> 64-bit multiply-add per store
+        // (m < 2^30 is checked at entry)
+        char* const out_q = reinterpret_cast<char*>(a.out_pos + q);
+        const uint32_t row_stride = (uint32_t)a.m * 4u;
         if (__any_sync(kFull, active)) {
             const float lim_b = (float)(((double)tkeep / (double)kBuckets + 1.0 / 64.0) * tau);
 #pragma unroll 1
@@ -416,7 +420,7 @@ knn_block_kernel(BlockArgs a) {
                             const uint32_t slot = HIST(b0);
                             HIST(b0) = (uint16_t)(slot + 1);
                             ++kept;
-                            if (slot < (uint32_t)kRow) a.out_pos[(size_t)slot * a.m + q] = p;
+                            if (slot < (uint32_t)kRow) *reinterpret_cast<uint32_t*>(out_q + (uint64_t)slot * row_stride) = p;
                             else overflow = true;
                         }
                     }
@@ -918,6 +922,7 @@ static int knn_impl(const double* d_x, const double* d_y, const double* d_z, int
     uint8_t* todo[2] = {ws.take<uint8_t>((size_t)m), ws.take<uint8_t>((size_t)m)};
     uint32_t* todo_idx[2] = {ws.take<uint32_t>((size_t)m), ws.take<uint32_t>((size_t)m)};
     if (!ws.ok) UPCP_FAIL(UPCP_E_WORKSPACE, "knn: workspace too small");
+    if (m >= ((int64_t)1 << 30)) UPCP_FAIL(UPCP_E_CAPACITY, "knn: at most 2^30 - 1 selected points");
     if (G > grid_cell_cap(m)) UPCP_FAIL(UPCP_E_INTERNAL, "knn: grid larger than its cap");
 
     const upcp_tuning tune = tuning();
