@@ -47,7 +47,13 @@ def minimum_bounding_rectangle(points):
     The candidate orientations are the hull edge directions folded into [0, pi/2); as in the
     reference the hull is walked as an OPEN chain (the edge closing the qhull vertex cycle is not
     a candidate), and every product goes through the same numpy calls on the same operands so
-    that the corners come out bit for bit."""
+    that the corners come out bit for bit.
+
+    Said plainly: this is the reference's function restated, not a redesign.  It is host code
+    for a handful of clusters per tile; the corners feed a point-in-prism test whose membership must be
+    bit-exact, and they only are when cos / arctan2 / dot are numpy's (glibc, BLAS) on the same operands -- a
+    device hull + rotating calipers would differ in the last ulp of a corner.  The device side of these
+    fusers is objects.cu (cluster statistics, gathers, prism clip)."""
     from scipy.spatial import ConvexHull
     points = np.asarray(points)
     quarter = np.pi / 2.
