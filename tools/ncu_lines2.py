@@ -6,7 +6,7 @@ import sys
 rep, rx = sys.argv[1], sys.argv[2]
 share = float(sys.argv[3]) if len(sys.argv) > 3 else 0.01
 out = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv', '--print-source', 'cuda,sass', '--kernel-name',
-                      rx, '--launch-count', '1'], capture_output=True, text=True).stdout
+                      rx, '--launch-count', '1', '--launch-skip', sys.argv[4] if len(sys.argv) > 4 else '0'], capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
 def I(x):
     try:

@@ -154,37 +154,64 @@ cc_link_kernel(const K* __restrict__ ucell, const uint32_t* __restrict__ n_cells
     const uint32_t c_total = *n_cells;
     const int dim = 1 << level;
     const K axis_mask = ((K)1 << level) - 1;
-    uint32_t stride = gridDim.x * kBlock;
-    for (uint32_t c = blockIdx.x * kBlock + threadIdx.x; c < c_total; c += stride) {
-        const K key = ucell[c];
+    const uint32_t stride = gridDim.x * kBlock;
+    const uint32_t lane = threadIdx.x & 31;
+    // The loop runs warp-uniform (every lane the same number of rounds) and the lanes are brought back together
+    // with __syncwarp() after every union: a lane that loses a compare-and-swap race or walks a long parent
+    // chain would otherwise run ahead of / behind the others for the REST of the body (independent thread
+    // scheduling does not reconverge on its own here: ncu showed 1.6 of 32 lanes per issued instruction).
+    for (uint32_t cw = blockIdx.x * kBlock + threadIdx.x - lane; cw < c_total; cw += stride) {
+        const uint32_t c = cw + lane;
+        const bool valid = c < c_total;
+        const K key = valid ? ucell[c] : (K)0;
         const int cx = (int)(key & axis_mask);
         const int cy = (int)((key >> level) & axis_mask);
         const int cz = (int)((key >> (2 * level)) & axis_mask);
         // (dz, dy, dx) = (0, 0, +1): next entry of the sorted unique-key array
-        if (cx + 1 < dim && c + 1 < c_total && ucell[c + 1] == key + 1) uf_union(parent, c, c + 1);
+        if (valid && cx + 1 < dim && c + 1 < c_total && ucell[c + 1] == key + 1) uf_union(parent, c, c + 1);
+        __syncwarp();
+        // is the cell left of this one occupied (this cell continues an x-run of its row)?
+        const bool own_left = valid && cx > 0 && c > 0 && ucell[c - 1] == key - 1;
         // rows (dz, dy) in {(0,+1), (+1,-1), (+1,0), (+1,+1)}: x in [cx-1, cx+1]
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
             const int dz = r == 0 ? 0 : 1;
             const int dy = r == 0 ? 1 : r - 2;
             const int ny = cy + dy, nz = cz + dz;
-            if (ny < 0 || ny >= dim || nz >= dim) continue;
-            const int x0 = cx > 0 ? cx - 1 : 0;
-            const int x1 = cx + 1 < dim ? cx + 1 : dim - 1;
-            const K k0 = pack_key<K>(x0, ny, nz, level);
-            const K k1 = pack_key<K>(x1, ny, nz, level);
-            // the cells of grid row (ny, nz) are one contiguous run of the sorted list: with the row
-            // table (levels <= 12) the search is confined to that run, else to everything after c
-            uint32_t lo = c + 1, hi = c_total;
-            if (row_first) {
-                const uint32_t rowid = (uint32_t)nz * (uint32_t)dim + (uint32_t)ny;
-                lo = __ldg(row_first + rowid); hi = __ldg(row_first + rowid + 1);
+            // which of the row's cells at x - 1 (L), x (M), x + 1 (R) are occupied, and where
+            bool pl = false, pm = false, pr = false;
+            uint32_t il = 0, im = 0, ir = 0;
+            if (valid && !(ny < 0 || ny >= dim || nz >= dim)) {
+                const int x0 = cx > 0 ? cx - 1 : 0;
+                const int x1 = cx + 1 < dim ? cx + 1 : dim - 1;
+                const K k0 = pack_key<K>(x0, ny, nz, level);
+                const K k1 = pack_key<K>(x1, ny, nz, level);
+                const K km = pack_key<K>(cx, ny, nz, level);
+                // the cells of grid row (ny, nz) are one contiguous run of the sorted list: with the row
+                // table (levels <= 12) the search is confined to that run, else to everything after c
+                uint32_t lo = c + 1, hi = c_total;
+                if (row_first) {
+                    const uint32_t rowid = (uint32_t)nz * (uint32_t)dim + (uint32_t)ny;
+                    lo = __ldg(row_first + rowid); hi = __ldg(row_first + rowid + 1);
+                }
+                uint32_t idx = lower_bound_key<K>(ucell, lo, hi, k0);
+                for (int t = 0; t < 3 && idx < hi; ++t, ++idx) {
+                    const K v = ucell[idx];
+                    if (v > k1) break;
+                    if (v < km) { pl = true; il = idx; }
+                    else if (v == km) { pm = true; im = idx; }
+                    else { pr = true; ir = idx; }
+                }
             }
-            uint32_t idx = lower_bound_key<K>(ucell, lo, hi, k0);
-            for (int t = 0; t < 3 && idx < hi; ++t, ++idx) {
-                if (ucell[idx] > k1) break;
-                uf_union(parent, c, idx);
-            }
+            __syncwarp();
+            // Every pair of occupied cells with |dx| <= 1 is an edge of the cell graph, but x-neighbours of one
+            // row are already joined (the union above), so ONE union per pair of adjacent x-runs gives the same
+            // components: the first cell of this run joins the run(s) it touches, a later cell only a run that
+            // STARTS at x + 1 (R occupied, M empty) -- any run through L or M already touches the cell at x - 1.
+            if (!own_left && pl) uf_union(parent, c, il);
+            if (!own_left && pm && !pl) uf_union(parent, c, im);
+            if (pr && !pm) uf_union(parent, c, ir);
+            __syncwarp();
         }
     }
 }
