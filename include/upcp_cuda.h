@@ -220,8 +220,10 @@ int    upcp_pip_plan_create(const double* h_ring_xy, const int64_t* h_ring_off,
 int    upcp_pip_plan_create_buffered(const double* h_ring_xy, const int64_t* h_ring_off,
                                      const int32_t* h_ring_poly, const uint8_t* h_ring_hole,
                                      int32_t n_rings, int32_t grid_dim, double offset, upcp_pip_plan** out);
+/* Size of the DEVICE buffer the plan needs (the host blob plus the tag grid the device fills in). */
 size_t upcp_pip_plan_bytes(const upcp_pip_plan* plan);
-/* Copies the plan blob into d_plan (cudaMemcpyAsync from the plan's host blob). */
+/* Copies the plan blob into d_plan (cudaMemcpyAsync from the plan's host blob) and classifies the cells of
+ * its tag grid (three small kernels on `stream`). */
 int    upcp_pip_plan_upload(const upcp_pip_plan* plan, void* d_plan, size_t bytes,
                             void* stream);
 void   upcp_pip_plan_destroy(upcp_pip_plan* plan);

@@ -63,7 +63,8 @@ struct PipHeader {
 };
 
 struct upcp_pip_plan {
-    std::vector<char> blob;
+    std::vector<char> blob;        // header + lists + edge flags (host side, uploaded)
+    size_t device_bytes = 0;       // blob + the tag grid the device fills in after the upload
 };
 
 namespace upcp {
@@ -540,11 +541,40 @@ int upcp_pip_plan_create_buffered(const double* h_ring_xy, const int64_t* h_ring
     hd.off_verts = place((size_t)V * 2 * sizeof(double));
     hd.off_cell_start = place(cell_start.size() * sizeof(int32_t));
     hd.off_cell_rings = place(cell_rings.size() * sizeof(int32_t));
+    // tag grid (see the header comment): space and geometry here, the classification itself runs on the
+    // device right after the upload (upcp_pip_plan_upload).  Not for buffered plans or NaN / infinite vertices.
+    bool want_tags = offset == 0.0 && any_active;
+    for (int r = 0; r < R && want_tags; ++r) {
+        if (!active[r]) continue;
+        for (int64_t v = h_ring_off[r]; v < h_ring_off[r + 1]; ++v)
+            want_tags = want_tags && isfinite(h_ring_xy[2 * v]) && isfinite(h_ring_xy[2 * v + 1]);
+    }
+    size_t host_bytes = off;                 // what the host blob holds and the upload copies
+    if (want_tags) {
+        // resolution: the band of cells along the edges (about four cells wide) should stay a small part of the
+        // area -- 512 x 512 for an ordinary BGT tile, finer where thousands of footprints leave no cell far
+        // from an edge (the table stays L2-resident at up to 4 MB)
+        double edge_len = 0.0;
+        for (int r = 0; r < R; ++r) {
+            if (!active[r]) continue;
+            for (int64_t v = h_ring_off[r]; v + 1 < h_ring_off[r + 1]; ++v)
+                edge_len += hypot(h_ring_xy[2 * (v + 1)] - h_ring_xy[2 * v], h_ring_xy[2 * (v + 1) + 1] - h_ring_xy[2 * v + 1]);
+        }
+        int gt = 512;
+        const double area = w * hgt, side = fmax(w, hgt);
+        while (gt < 2048 && area > 0.0 && edge_len * (4.0 * side / gt) > 0.25 * area) gt *= 2;
+        hd.gt = gt; hd.n_verts = (int32_t)V;
+        hd.inv_tw = w > 0 ? (double)gt / w : 0.0; hd.inv_th = hgt > 0 ? (double)gt / hgt : 0.0;
+        hd.off_edge_ok = place((size_t)(V > 0 ? V : 1));
+        host_bytes = off;
+        hd.off_tags = place((size_t)gt * gt);             // device only: filled by the tag kernels after the upload
+    }
     hd.total_bytes = (int64_t)off;
 
     upcp_pip_plan* plan = new (std::nothrow) upcp_pip_plan();
     if (!plan) UPCP_FAIL(UPCP_E_INTERNAL, "pip_plan_create: out of host memory");
-    plan->blob.assign(off, 0);
+    plan->blob.assign(host_bytes, 0);
+    plan->device_bytes = off;
     char* p = plan->blob.data();
     memcpy(p, &hd, sizeof(hd));
     if (R) {
@@ -557,39 +587,22 @@ int upcp_pip_plan_create_buffered(const double* h_ring_xy, const int64_t* h_ring
     if (V) memcpy(p + hd.off_verts, h_ring_xy, (size_t)V * 2 * sizeof(double));
     memcpy(p + hd.off_cell_start, cell_start.data(), cell_start.size() * sizeof(int32_t));
     if (!cell_rings.empty()) memcpy(p + hd.off_cell_rings, cell_rings.data(), cell_rings.size() * sizeof(int32_t));
-    // --- tag grid (see the header comment): space and geometry here, the classification itself runs on the
-    // device right after the upload (upcp_pip_plan_upload).  Not for buffered plans or NaN vertices.
-    if (offset == 0.0 && any_active) {
-        bool finite = true;
-        std::vector<uint8_t> edge_ok((size_t)(V > 0 ? V : 1), 0);          // 1: vertex v and v + 1 form an edge of an active ring
-        for (int r = 0; r < R && finite; ++r) {
+    if (want_tags) {
+        uint8_t* edge_ok = (uint8_t*)(p + hd.off_edge_ok);               // 1: vertex v and v + 1 form an edge of an active ring
+        for (int r = 0; r < R; ++r) {
             if (!active[r]) continue;
-            for (int64_t v = h_ring_off[r]; v < h_ring_off[r + 1]; ++v) {
-                finite = finite && isfinite(h_ring_xy[2 * v]) && isfinite(h_ring_xy[2 * v + 1]);
-                if (v + 1 < h_ring_off[r + 1]) edge_ok[(size_t)v] = 1;
-            }
-        }
-        if (finite) {
-            const int gt = 512;
-            const size_t at_tags = align_up(plan->blob.size(), 256);
-            const size_t at_ok = align_up(at_tags + (size_t)gt * gt, 256);
-            plan->blob.resize(align_up(at_ok + edge_ok.size(), 256), 0);
-            memcpy(plan->blob.data() + at_ok, edge_ok.data(), edge_ok.size());
-            PipHeader* hp = (PipHeader*)plan->blob.data();
-            hp->gt = gt; hp->n_verts = (int32_t)V;
-            hp->inv_tw = w > 0 ? (double)gt / w : 0.0; hp->inv_th = hgt > 0 ? (double)gt / hgt : 0.0;
-            hp->off_tags = (int64_t)at_tags; hp->off_edge_ok = (int64_t)at_ok; hp->total_bytes = (int64_t)plan->blob.size();
+            for (int64_t v = h_ring_off[r]; v + 1 < h_ring_off[r + 1]; ++v) edge_ok[(size_t)v] = 1;
         }
     }
     *out = plan;
     return UPCP_OK;
 }
 
-size_t upcp_pip_plan_bytes(const upcp_pip_plan* plan) { return plan ? plan->blob.size() : 0; }
+size_t upcp_pip_plan_bytes(const upcp_pip_plan* plan) { return plan ? plan->device_bytes : 0; }
 
 int upcp_pip_plan_upload(const upcp_pip_plan* plan, void* d_plan, size_t bytes, void* stream) {
     if (!plan || !d_plan) UPCP_FAIL(UPCP_E_INVALID, "pip_plan_upload: NULL argument");
-    if (bytes < plan->blob.size()) UPCP_FAIL(UPCP_E_WORKSPACE, "pip_plan_upload: device buffer too small");
+    if (bytes < plan->device_bytes) UPCP_FAIL(UPCP_E_WORKSPACE, "pip_plan_upload: device buffer too small");
     cudaStream_t st = (cudaStream_t)stream;
     UPCP_CUDA_OK(cudaMemcpyAsync(d_plan, plan->blob.data(), plan->blob.size(), cudaMemcpyHostToDevice, st));
     const PipHeader* hp = (const PipHeader*)plan->blob.data();

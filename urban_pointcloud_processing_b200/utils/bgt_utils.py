@@ -34,7 +34,8 @@ except Exception:  # pragma: no cover - shapely absent in this image
 
 class _Ring:
     def __init__(self, coords):
-        self.coords = [tuple(c) for c in np.asarray(coords, dtype=np.float64).reshape(-1, 2)]
+        self.xy = np.ascontiguousarray(np.asarray(coords, dtype=np.float64).reshape(-1, 2))   # what the device plan reads
+        self.coords = [tuple(c) for c in self.xy]                                             # shapely's view of the ring
 
 
 class RingPolygon:
