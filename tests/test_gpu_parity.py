@@ -1028,3 +1028,64 @@ def test_region_growing_parameters_and_edge_cases():
     # no seeds -> unchanged; antiparallel normals are NOT merged (vector_angle has no abs)
     l0 = np.where(labels == 10, 0, labels)
     assert np.array_equal(RegionGrowing(10, exclude_labels=(9,)).get_labels(pts, l0.copy(), None, ''), l0)
+
+
+@pytest.mark.gpu
+def test_device_generated_tiles_config5():
+    """the bench tiles are generated ON THE DEVICE (upcp_synth_tile) from seed 20240000 + i.
+    The generator is deterministic, tiles differ, the points lie on the LAS millimetre grid inside their tile --
+    and for sampled tiles the labels of the device pipeline equal the oracle's on the downloaded copy."""
+    import torch
+    from urban_pointcloud_processing_b200.fusion import AHNFuser, BGTBuildingFuser, BGTRoadFuser
+    from urban_pointcloud_processing_b200.labels import Labels
+    from urban_pointcloud_processing_b200.pipeline import Pipeline
+    from urban_pointcloud_processing_b200.region_growing import LabelConnectedComp, LayerLCC
+    from urban_pointcloud_processing_b200.region_growing.region_growing import RegionGrowing
+    from urban_pointcloud_processing_b200.utils import ahn_utils, bgt_utils
+    n = 150000
+    layers = [{'bottom': 12., 'grid_size': 0.1, 'threshold': 0.5}, {'bottom': 0., 'top': 12., 'grid_size': 0.05, 'threshold': 0.5}]
+    seen = []
+    for i in (0, 1, 7):
+        seed, origin = 20240000 + i, synthetic.tile_origin(i)
+        tile, d_kind, layout = synthetic.make_device_tile(n, seed=seed, origin=origin)
+        again, d_kind2, _ = synthetic.make_device_tile(n, seed=seed, origin=origin)
+        pts = torch.stack((tile.x, tile.y, tile.z), dim=1).cpu().numpy()
+        assert np.array_equal(pts, torch.stack((again.x, again.y, again.z), dim=1).cpu().numpy())
+        assert torch.equal(d_kind, d_kind2)
+        assert all(not np.array_equal(pts, p) for p in seen)
+        seen.append(pts)
+        kind = d_kind.cpu().numpy()
+        frac = np.bincount(kind, minlength=6) / n
+        cum = np.asarray(layout['cum_kind'], dtype=float)
+        assert np.allclose(frac, np.diff(np.concatenate(([0.0], cum))), atol=0.01)
+        assert np.all(pts[:, 0] >= origin[0] - 1e-9) and np.all(pts[:, 0] <= origin[0] + synthetic.TILE_SIZE + 1e-9)
+        assert np.all(pts[:, 1] >= origin[1] - 1e-9) and np.all(pts[:, 1] <= origin[1] + synthetic.TILE_SIZE + 1e-9)
+        assert np.allclose(pts * 1000.0, np.round(pts * 1000.0), atol=1e-4)          # millimetre grid
+        # the device pipeline on the device-resident tile against the oracle on the downloaded copy
+        tc, a = layout['tilecode'], layout['ahn_tile']
+        ahn = ahn_utils.ArrayAHNReader({tc: a})
+        bld = bgt_utils.ArrayBGTReader({tc: layout['building_polygons']})
+        road = bgt_utils.ArrayBGTReader({tc: layout['road_polygons']})
+        procs = (AHNFuser(Labels.GROUND, ahn, target='ground', epsilon=0.2, refine_ground=False),
+                 BGTRoadFuser(Labels.ROAD, bgt_reader=road),
+                 BGTBuildingFuser(Labels.BUILDING, bgt_reader=bld, offset=0, ahn_reader=ahn),
+                 LayerLCC(Labels.BUILDING, ahn, params=[dict(p) for p in layers]),
+                 LabelConnectedComp(Labels.CAR, grid_size=0.1, min_component_size=30, threshold=0.02),
+                 RegionGrowing(Labels.BUILDING, exclude_labels=(Labels.GROUND, Labels.ROAD)))
+        labels0 = np.zeros(n, dtype=np.uint16)
+        labels0[np.where(kind == 2)[0][::40]] = Labels.CAR
+        d_labels = dev.upload_labels(labels0, tile.device)
+        Pipeline(processors=procs, ahn_reader=ahn, caching=True).process_tile_device(tc, tile, d_labels)
+        got = d_labels.cpu().numpy()
+        want = R.process_cloud([
+            lambda p, l, m: R.ahn_fuser_labels(p, l, m, a, Labels.GROUND, 'ground', 0.2),
+            lambda p, l, m: R.road_fuser_labels(p, l, layout['road_polygons'], Labels.ROAD),
+            lambda p, l, m: R.building_fuser_labels(p, l, m, layout['building_polygons'], Labels.BUILDING, a, 0.2),
+            lambda p, l, m: R.layer_lcc_labels(p, l, m, a, Labels.BUILDING, [dict(q) for q in layers]),
+            lambda p, l, m: (l.__setitem__(R.lcc_get_label_mask(p, l, m, Labels.CAR, grid_size=0.1,
+                                                                min_component_size=30, threshold=0.02), Labels.CAR), l)[1],
+            lambda p, l, m: R.region_growing_labels(p, l, Labels.BUILDING, exclude_labels=(Labels.GROUND, Labels.ROAD)),
+        ], np.asfortranarray(pts), labels0.copy())
+        n_diff = int(np.count_nonzero(got != want.astype(np.int32)))
+        print(f'device tile {i}: {n} points, kinds {np.round(frac, 3).tolist()}, {n_diff} labels differ from the oracle')
+        assert n_diff == 0
