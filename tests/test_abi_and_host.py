@@ -490,3 +490,22 @@ def test_per_thread_diagnostics():
     [t.join() for t in ts]
     assert seen == {1: ([1], 1), 2: ([2], 2)}
     assert p.last == ['main'] and q.last == [] and p.level is None
+
+
+def test_rings_fast_path_equals_generic_path():
+    """device.rings_from_polygons flattens the readers' own RingPolygon objects without per-ring conversion; the
+    ring arrays must be exactly those of the generic (shapely-like .exterior.coords / .interiors) path."""
+    from urban_pointcloud_processing_b200 import device as dev
+    polys = synthetic.make_polygon_lattice(n_side=9, seed=11)
+    assert any(len(p.interiors) for p in polys)
+
+    class Generic:                      # hides the type: forces the generic path
+        def __init__(self, p):
+            self.exterior, self.interiors = p.exterior, p.interiors
+    fast = dev.rings_from_polygons(polys)
+    slow = dev.rings_from_polygons([Generic(p) for p in polys])
+    for a, b in zip(fast, slow):
+        assert a.dtype == b.dtype and np.array_equal(a, b)
+    assert fast[1][0] == 0 and fast[1][-1] == fast[0].shape[0] and len(fast[1]) == len(fast[2]) + 1
+    empty = dev.rings_from_polygons([])
+    assert empty[0].shape == (0, 2) and list(empty[1]) == [0]
