@@ -454,6 +454,18 @@ int upcp_prism_clip(const double* d_x, const double* d_y, const double* d_z, int
 int upcp_laz_decode(const uint8_t* h_vlr, int32_t vlr_bytes, const uint8_t* h_data, int64_t data_bytes,
                     int64_t data_file_offset, int64_t n_points, int32_t point_size, uint8_t* h_out);
 
+/* The inverse: LASzip-compress point records for las_utils.label_and_save_las_as_laz (las_utils.py:133-164;
+ * laspy writes `.laz` through lazrs).  Host code.  Point formats 0-3 (+ extra bytes), "pointwise chunked"
+ * compressor, version-2 item codecs -- what upcp_laz_decode reads.
+ *   h_points        : n_points * point_size bytes, uncompressed records;
+ *   data_file_offset: where the returned bytes will sit in the file (= offset to point data of the header);
+ *   h_vlr58         : receives the payload of the "laszip encoded" VLR (record id 22204), *vlr_bytes of it;
+ *   h_out / out_cap : receives the point data section (chunk-table position, chunks, chunk table);
+ *                     *out_bytes is always set, UPCP_E_WORKSPACE means "call again with at least that much". */
+int upcp_laz_encode(const uint8_t* h_points, int64_t n_points, int32_t point_size, int32_t point_format, int32_t chunk_size,
+                    int64_t data_file_offset, uint8_t* h_vlr58, int32_t* vlr_bytes, uint8_t* h_out, int64_t out_cap,
+                    int64_t* out_bytes);
+
 /* ------------------------------------ AHN preprocessing ("next" row 4) ---- */
 /* SpatialInterpolator.__call__ (reference utils/interpolation.py:156-308) for 2-D data, as
  * preprocessing/ahn_preprocessing.py:129-236 uses it to rasterise an AHN cloud: for every position the

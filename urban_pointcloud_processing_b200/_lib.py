@@ -122,6 +122,8 @@ _PROTOTYPES = {
     'upcp_prism_clip': (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p,
                                 c_int32, c_void_p, c_void_p]),
     'upcp_laz_decode': (c_int, [c_void_p, c_int32, c_void_p, c_int64, c_int64, c_int64, c_int32, c_void_p]),
+    'upcp_laz_encode': (c_int, [c_void_p, c_int64, c_int32, c_int32, c_int32, c_int64, c_void_p, POINTER(c_int32), c_void_p, c_int64,
+                              POINTER(c_int64)]),
     'upcp_interpolate_ws_bytes': (c_size_t, [c_int64]),
     'upcp_interpolate': (c_int, [c_void_p, c_void_p, c_void_p, c_int64, POINTER(c_double), c_void_p, c_void_p, c_int64,
                                  c_int, c_int, c_double, c_double, c_double, c_double, c_double, c_void_p, c_void_p,

@@ -1,4 +1,5 @@
-// "Next" row 1 -- LAZ ingest: decoder for LASzip-compressed point data, host code.
+// "Next" row 1 -- LAZ ingest and write-back: decoder AND encoder for LASzip-compressed point data,
+// host code (the encoder is the second half of this file).
 //
 // The reference reads its tiles with laspy[lazrs] (las_utils.read_las, reference utils/las_utils.py:118-120;
 // every CycloMedia tile and the demo AHN clouds are .laz).  Neither laspy nor a LASzip library is in this
@@ -463,6 +464,317 @@ struct ByteReader : ItemReader {
     }
 };
 
+
+// ------------------------------------------------------------------------------------------------ encoder ----
+// The inverse of everything above, for las_utils.label_and_save_las_as_laz (reference utils/las_utils.py:133-164:
+// laspy writes `.laz` through lazrs).  Same models, same contexts, same state updates as the readers -- the
+// arithmetic ENCODER of FastAC (base / length interval, carry propagation into the bytes already written,
+// byte-wise renormalisation, and a final flush that leaves the stream exactly as long as the decoder reads).
+// Pinned on the reference's own data: re-encoding the decoded demo clouds reproduces their compressed point
+// data byte for byte (tests/test_abi_and_host.py).
+struct Encoder {
+    std::vector<U8>* out = nullptr;
+    U32 base = 0, length = 0;
+    void init(std::vector<U8>* o) { out = o; base = 0; length = AC_MaxLength; }
+    void propagate_carry() {
+        size_t i = out->size();
+        while (i > 0 && (*out)[i - 1] == 0xFFu) { (*out)[i - 1] = 0; --i; }
+        if (i > 0) ++(*out)[i - 1];
+    }
+    void renorm() { do { out->push_back((U8)(base >> 24)); base <<= 8; } while ((length <<= 8) < AC_MinLength); }
+    void encodeBit(BitModel* m, U32 sym) {
+        const U32 x = m->bit_0_prob * (length >> BM_LengthShift);
+        if (sym == 0) { length = x; ++m->bit_0_count; }
+        else { const U32 init_base = base; base += x; length -= x; if (init_base > base) propagate_carry(); }
+        if (length < AC_MinLength) renorm();
+        if (--m->bits_until_update == 0) m->update();
+    }
+    void encodeSymbol(SymbolModel* m, U32 sym) {
+        U32 x;
+        const U32 init_base = base;
+        if (sym == m->last_symbol) {
+            x = m->distribution[sym] * (length >> DM_LengthShift);
+            base += x; length -= x;
+        } else {
+            x = m->distribution[sym] * (length >>= DM_LengthShift);
+            base += x; length = m->distribution[sym + 1] * length - x;
+        }
+        if (init_base > base) propagate_carry();
+        if (length < AC_MinLength) renorm();
+        ++m->symbol_count[sym];
+        if (--m->symbols_until_update == 0) m->update();
+    }
+    void writeShort(U32 sym) {
+        const U32 init_base = base;
+        base += (sym & 0xffffu) * (length >>= 16);
+        if (init_base > base) propagate_carry();
+        if (length < AC_MinLength) renorm();
+    }
+    void writeBits(U32 bits, U32 sym) {
+        if (bits > 19) { writeShort(sym & 0xffffu); sym >>= 16; bits -= 16; }
+        const U32 init_base = base;
+        base += sym * (length >>= bits);
+        if (init_base > base) propagate_carry();
+        if (length < AC_MinLength) renorm();
+    }
+    void writeInt(U32 sym) { writeShort(sym & 0xffffu); writeShort(sym >> 16); }
+    void done() {
+        const U32 init_base = base;
+        bool another_byte = true;
+        if (length > 2 * AC_MinLength) { base += AC_MinLength; length = AC_MinLength >> 1; }
+        else { base += AC_MinLength >> 1; length = AC_MinLength >> 9; another_byte = false; }
+        if (init_base > base) propagate_carry();
+        renorm();
+        // the decoder reads four bytes ahead: pad so that it ends exactly where the stream does
+        out->push_back(0); out->push_back(0);
+        if (another_byte) out->push_back(0);
+    }
+};
+
+// IntegerCompressor::compress (shares the models of the struct above through a decoder-less instance)
+struct IntegerEncoder {
+    Encoder* enc = nullptr;
+    IntegerCompressor m;             // models, ranges and the last k
+    void create(Encoder* e, U32 bits, U32 contexts = 1, U32 bits_high = 8) { enc = e; m.create(nullptr, bits, contexts, bits_high); }
+    void init() { m.init(); }
+    U32 getK() const { return m.k; }
+    void compress(I32 pred, I32 real, U32 context = 0) {
+        I32 corr = (I32)((U32)real - (U32)pred);
+        if (m.corr_range) {
+            if (corr < m.corr_min) corr = (I32)((U32)corr + m.corr_range);
+            else if (corr > m.corr_max) corr = (I32)((U32)corr - m.corr_range);
+        }
+        SymbolModel* mb = &m.mBits[context];
+        // the tightest interval [-(2^k - 1), 2^k] that holds the corrector
+        U32 c1 = corr <= 0 ? (U32)0 - (U32)corr : (U32)corr - 1u;
+        U32 k = 0;
+        while (c1) { c1 >>= 1; ++k; }
+        m.k = k;
+        enc->encodeSymbol(mb, k);
+        if (k) {
+            if (k < 32) {
+                U32 c = corr < 0 ? (U32)corr + ((1u << k) - 1u) : (U32)corr - 1u;      // into [0, 2^k - 1]
+                if (k <= m.bits_high) enc->encodeSymbol(&m.mCorrector[k], c);
+                else {
+                    const U32 k1 = k - m.bits_high;
+                    const U32 lo = c & ((1u << k1) - 1u);
+                    c >>= k1;
+                    enc->encodeSymbol(&m.mCorrector[k], c);
+                    enc->writeBits(k1, lo);
+                }
+            }
+        } else enc->encodeBit(&m.mCorrector0, (U32)corr);
+    }
+};
+
+struct ItemWriter {
+    virtual ~ItemWriter() {}
+    virtual void init(const U8* item) = 0;
+    virtual void write(const U8* item) = 0;
+};
+
+struct Point10Writer : ItemWriter {
+    Encoder* enc;
+    U8 last_item[20];
+    U16 last_intensity[16];
+    StreamingMedian5 last_x_diff_median5[16], last_y_diff_median5[16];
+    I32 last_height[8];
+    SymbolModel m_changed_values, m_scan_angle_rank[2];
+    std::vector<SymbolModel> m_bit_byte, m_classification, m_user_data;
+    std::vector<char> has_bit_byte, has_classification, has_user_data;
+    IntegerEncoder ic_intensity, ic_point_source_ID, ic_dx, ic_dy, ic_z;
+    explicit Point10Writer(Encoder* e) : enc(e) {
+        m_changed_values.create(64);
+        m_scan_angle_rank[0].create(256); m_scan_angle_rank[1].create(256);
+        m_bit_byte.assign(256, SymbolModel()); m_classification.assign(256, SymbolModel()); m_user_data.assign(256, SymbolModel());
+        ic_intensity.create(e, 16, 4); ic_point_source_ID.create(e, 16); ic_dx.create(e, 32, 2); ic_dy.create(e, 32, 22);
+        ic_z.create(e, 32, 20);
+    }
+    void init(const U8* item) override {
+        for (int i = 0; i < 16; ++i) {
+            last_x_diff_median5[i].init(); last_y_diff_median5[i].init();
+            last_intensity[i] = 0; last_height[i / 2] = 0;
+        }
+        m_changed_values.init(); m_scan_angle_rank[0].init(); m_scan_angle_rank[1].init();
+        has_bit_byte.assign(256, 0); has_classification.assign(256, 0); has_user_data.assign(256, 0);
+        ic_intensity.init(); ic_point_source_ID.init(); ic_dx.init(); ic_dy.init(); ic_z.init();
+        memcpy(last_item, item, 20);
+        last_item[12] = 0; last_item[13] = 0;
+    }
+    void write(const U8* item) override {
+        I32 x, y, z, lx, ly;
+        U16 intensity, psid, lpsid;
+        memcpy(&x, item, 4); memcpy(&y, item + 4, 4); memcpy(&z, item + 8, 4);
+        memcpy(&intensity, item + 12, 2); memcpy(&psid, item + 18, 2);
+        memcpy(&lx, last_item, 4); memcpy(&ly, last_item + 4, 4); memcpy(&lpsid, last_item + 18, 2);
+        const U32 r = item[14] & 7, n = (item[14] >> 3) & 7;
+        const U32 m = number_return_map[n][r], l = number_return_level[n][r];
+        const U32 changed = ((U32)(last_item[14] != item[14]) << 5) | ((U32)(last_intensity[m] != intensity) << 4) |
+                            ((U32)(last_item[15] != item[15]) << 3) | ((U32)(last_item[16] != item[16]) << 2) |
+                            ((U32)(last_item[17] != item[17]) << 1) | (U32)(lpsid != psid);
+        enc->encodeSymbol(&m_changed_values, changed);
+        if (changed & 32) enc->encodeSymbol(Point10Reader::lazy(m_bit_byte, has_bit_byte, last_item[14]), item[14]);
+        if (changed & 16) { ic_intensity.compress(last_intensity[m], intensity, (m < 3 ? m : 3)); last_intensity[m] = intensity; }
+        if (changed & 8) enc->encodeSymbol(Point10Reader::lazy(m_classification, has_classification, last_item[15]), item[15]);
+        if (changed & 4) enc->encodeSymbol(&m_scan_angle_rank[(item[14] >> 6) & 1], u8_fold((I32)item[16] - (I32)last_item[16]));
+        if (changed & 2) enc->encodeSymbol(Point10Reader::lazy(m_user_data, has_user_data, last_item[17]), item[17]);
+        if (changed & 1) ic_point_source_ID.compress(lpsid, psid);
+        I32 median = last_x_diff_median5[m].get();
+        I32 diff = (I32)((U32)x - (U32)lx);
+        ic_dx.compress(median, diff, n == 1);
+        last_x_diff_median5[m].add(diff);
+        U32 k_bits = ic_dx.getK();
+        median = last_y_diff_median5[m].get();
+        diff = (I32)((U32)y - (U32)ly);
+        ic_dy.compress(median, diff, (n == 1) + (k_bits < 20 ? (k_bits & ~1u) : 20));
+        last_y_diff_median5[m].add(diff);
+        k_bits = (ic_dx.getK() + ic_dy.getK()) / 2;
+        ic_z.compress(last_height[l], z, (n == 1) + (k_bits < 18 ? (k_bits & ~1u) : 18));
+        last_height[l] = z;
+        memcpy(last_item, item, 20);
+    }
+};
+
+struct GpsTime11Writer : ItemWriter {
+    typedef GpsTime11Reader G;
+    Encoder* enc;
+    U32 last = 0, next = 0;
+    U64 last_gpstime[4];
+    I32 last_gpstime_diff[4], multi_extreme_counter[4];
+    SymbolModel m_multi, m_0diff;
+    IntegerEncoder ic;
+    explicit GpsTime11Writer(Encoder* e) : enc(e) { m_multi.create(G::MULTI_TOTAL); m_0diff.create(6); ic.create(e, 32, 9); }
+    void init(const U8* item) override {
+        last = next = 0;
+        for (int i = 0; i < 4; ++i) { last_gpstime_diff[i] = 0; multi_extreme_counter[i] = 0; last_gpstime[i] = 0; }
+        m_multi.init(); m_0diff.init(); ic.init();
+        memcpy(&last_gpstime[0], item, 8);
+    }
+    static bool fits32(I64 d) { return d == (I64)(I32)d; }
+    void bump(I32 diff) { if (++multi_extreme_counter[last] > 3) { last_gpstime_diff[last] = diff; multi_extreme_counter[last] = 0; } }
+    // the value belongs to another of the four running sequences, or starts a new one
+    void far_away(U64 t, SymbolModel* model, U32 code_full) {
+        for (U32 i = 1; i < 4; ++i) {
+            if (fits32((I64)(t - last_gpstime[(last + i) & 3]))) {
+                enc->encodeSymbol(model, code_full + i);
+                last = (last + i) & 3;
+                write_time(t);
+                return;
+            }
+        }
+        enc->encodeSymbol(model, code_full);
+        ic.compress((I32)(last_gpstime[last] >> 32), (I32)(t >> 32), 8);
+        enc->writeInt((U32)t);
+        next = (next + 1) & 3;
+        last = next;
+        last_gpstime_diff[last] = 0;
+        multi_extreme_counter[last] = 0;
+        last_gpstime[last] = t;
+    }
+    void write_time(U64 t) {
+        if (last_gpstime_diff[last] == 0) {
+            if (t == last_gpstime[last]) { enc->encodeSymbol(&m_0diff, 0); return; }
+            const I64 d64 = (I64)(t - last_gpstime[last]);
+            if (fits32(d64)) {
+                enc->encodeSymbol(&m_0diff, 1);
+                ic.compress(0, (I32)d64, 0);
+                last_gpstime_diff[last] = (I32)d64;
+                multi_extreme_counter[last] = 0;
+                last_gpstime[last] = t;
+            } else far_away(t, &m_0diff, 2);
+        } else {
+            if (t == last_gpstime[last]) { enc->encodeSymbol(&m_multi, (U32)G::MULTI_UNCHANGED); return; }
+            const I64 d64 = (I64)(t - last_gpstime[last]);
+            if (fits32(d64)) {
+                const I32 d = (I32)d64, ld = last_gpstime_diff[last];
+                const float mf = (float)d / (float)ld;
+                const I32 multi = mf >= 0.0f ? (I32)(mf + 0.5f) : (I32)(mf - 0.5f);
+                if (multi == 1) {
+                    enc->encodeSymbol(&m_multi, 1);
+                    ic.compress(ld, d, 1);
+                    multi_extreme_counter[last] = 0;
+                } else if (multi > 0) {
+                    if (multi < G::MULTI) {
+                        enc->encodeSymbol(&m_multi, (U32)multi);
+                        ic.compress((I32)((U32)multi * (U32)ld), d, multi < 10 ? 2 : 3);
+                    } else {
+                        enc->encodeSymbol(&m_multi, (U32)G::MULTI);
+                        ic.compress((I32)((U32)G::MULTI * (U32)ld), d, 4);
+                        bump(d);
+                    }
+                } else if (multi < 0) {
+                    if (multi > G::MULTI_MINUS) {
+                        enc->encodeSymbol(&m_multi, (U32)(G::MULTI - multi));
+                        ic.compress((I32)((U32)multi * (U32)ld), d, 5);
+                    } else {
+                        enc->encodeSymbol(&m_multi, (U32)(G::MULTI - G::MULTI_MINUS));
+                        ic.compress((I32)((U32)G::MULTI_MINUS * (U32)ld), d, 6);
+                        bump(d);
+                    }
+                } else {
+                    enc->encodeSymbol(&m_multi, 0);
+                    ic.compress(0, d, 7);
+                    bump(d);
+                }
+                last_gpstime[last] = t;
+            } else far_away(t, &m_multi, (U32)G::MULTI_CODE_FULL);
+        }
+    }
+    void write(const U8* item) override { U64 t; memcpy(&t, item, 8); write_time(t); }
+};
+
+struct Rgb12Writer : ItemWriter {
+    Encoder* enc;
+    U16 last_item[3];
+    SymbolModel m_byte_used, m_diff[6];
+    explicit Rgb12Writer(Encoder* e) : enc(e) { m_byte_used.create(128); for (auto& m : m_diff) m.create(256); }
+    void init(const U8* item) override { m_byte_used.init(); for (auto& m : m_diff) m.init(); memcpy(last_item, item, 6); }
+    void write(const U8* in) override {
+        U16 item[3];
+        memcpy(item, in, 6);
+        I32 diff_l = 0, diff_h = 0, corr;
+        U32 sym = (U32)((last_item[0] & 0x00FF) != (item[0] & 0x00FF)) << 0;
+        sym |= (U32)((last_item[0] & 0xFF00) != (item[0] & 0xFF00)) << 1;
+        sym |= (U32)((last_item[1] & 0x00FF) != (item[1] & 0x00FF)) << 2;
+        sym |= (U32)((last_item[1] & 0xFF00) != (item[1] & 0xFF00)) << 3;
+        sym |= (U32)((last_item[2] & 0x00FF) != (item[2] & 0x00FF)) << 4;
+        sym |= (U32)((last_item[2] & 0xFF00) != (item[2] & 0xFF00)) << 5;
+        sym |= (U32)(((item[0] & 0x00FF) != (item[1] & 0x00FF)) || ((item[0] & 0x00FF) != (item[2] & 0x00FF)) ||
+                     ((item[0] & 0xFF00) != (item[1] & 0xFF00)) || ((item[0] & 0xFF00) != (item[2] & 0xFF00))) << 6;
+        enc->encodeSymbol(&m_byte_used, sym);
+        if (sym & 1) { diff_l = (I32)(item[0] & 255) - (I32)(last_item[0] & 255); enc->encodeSymbol(&m_diff[0], u8_fold(diff_l)); }
+        if (sym & 2) { diff_h = (I32)(item[0] >> 8) - (I32)(last_item[0] >> 8); enc->encodeSymbol(&m_diff[1], u8_fold(diff_h)); }
+        if (sym & 64) {
+            if (sym & 4) { corr = (I32)(item[1] & 255) - (I32)u8_clamp(diff_l + (last_item[1] & 255)); enc->encodeSymbol(&m_diff[2], u8_fold(corr)); }
+            if (sym & 16) {
+                diff_l = (diff_l + (I32)(item[1] & 255) - (I32)(last_item[1] & 255)) / 2;
+                corr = (I32)(item[2] & 255) - (I32)u8_clamp(diff_l + (last_item[2] & 255));
+                enc->encodeSymbol(&m_diff[4], u8_fold(corr));
+            }
+            if (sym & 8) { corr = (I32)(item[1] >> 8) - (I32)u8_clamp(diff_h + (last_item[1] >> 8)); enc->encodeSymbol(&m_diff[3], u8_fold(corr)); }
+            if (sym & 32) {
+                diff_h = (diff_h + (I32)(item[1] >> 8) - (I32)(last_item[1] >> 8)) / 2;
+                corr = (I32)(item[2] >> 8) - (I32)u8_clamp(diff_h + (last_item[2] >> 8));
+                enc->encodeSymbol(&m_diff[5], u8_fold(corr));
+            }
+        }
+        memcpy(last_item, item, 6);
+    }
+};
+
+struct ByteWriter : ItemWriter {
+    Encoder* enc;
+    U32 number;
+    std::vector<U8> last_item;
+    std::vector<SymbolModel> m_byte;
+    ByteWriter(Encoder* e, U32 n) : enc(e), number(n), last_item(n), m_byte(n) { for (auto& m : m_byte) m.create(256); }
+    void init(const U8* item) override { for (auto& m : m_byte) m.init(); memcpy(last_item.data(), item, number); }
+    void write(const U8* item) override {
+        for (U32 i = 0; i < number; ++i) enc->encodeSymbol(&m_byte[i], u8_fold((I32)item[i] - (I32)last_item[i]));
+        memcpy(last_item.data(), item, number);
+    }
+};
+
 }  // namespace laz
 }  // namespace upcp
 
@@ -555,6 +867,94 @@ int upcp_laz_decode(const uint8_t* h_vlr, int32_t vlr_bytes, const uint8_t* h_da
         }
     } catch (const std::bad_alloc&) {
         UPCP_FAIL(UPCP_E_INTERNAL, "laz_decode: out of host memory");
+    }
+    return UPCP_OK;
+}
+
+
+/* see include/upcp_cuda.h */
+int upcp_laz_encode(const uint8_t* h_points, int64_t n_points, int32_t point_size, int32_t point_format, int32_t chunk_size,
+                    int64_t data_file_offset, uint8_t* h_vlr58, int32_t* vlr_bytes, uint8_t* h_out, int64_t out_cap,
+                    int64_t* out_bytes) {
+    using namespace upcp::laz;
+    if (!h_vlr58 || !vlr_bytes || !out_bytes || n_points < 0 || (n_points > 0 && !h_points) || chunk_size < 1 || data_file_offset < 0)
+        UPCP_FAIL(UPCP_E_INVALID, "laz_encode: bad argument");
+    *out_bytes = 0;
+    static const int kBase[4] = {20, 28, 26, 34};
+    if (point_format < 0 || point_format > 3) UPCP_FAIL(UPCP_E_CAPACITY, "laz_encode: point formats 0 - 3 only (LAS 1.4 formats need the layered codecs)");
+    const int extra = point_size - kBase[point_format];
+    if (extra < 0 || extra > 65535) UPCP_FAIL(UPCP_E_INVALID, "laz_encode: point size smaller than the point format's record");
+    try {
+        // items of the record: POINT10 [GPSTIME11] [RGB12] [BYTE x extra], all version 2
+        struct Item { U16 type, size, version; };
+        std::vector<Item> items;
+        items.push_back({6, 20, 2});
+        if (point_format == 1 || point_format == 3) items.push_back({7, 8, 2});
+        if (point_format == 2 || point_format == 3) items.push_back({8, 6, 2});
+        if (extra > 0) items.push_back({0, (U16)extra, 2});
+        // the "laszip encoded" VLR payload (record id 22204)
+        U8* v = h_vlr58;
+        memset(v, 0, 58);
+        const U16 compressor = 2, coder = 0, revision = 0, num_items = (U16)items.size();
+        const U32 options = 0;
+        const I64 minus1 = -1;
+        memcpy(v, &compressor, 2); memcpy(v + 2, &coder, 2);
+        v[4] = 2; v[5] = 2;                                   // the format version of LASzip 2.2: chunked, version-2 items
+        memcpy(v + 6, &revision, 2); memcpy(v + 8, &options, 4); memcpy(v + 12, &chunk_size, 4);
+        memcpy(v + 16, &minus1, 8); memcpy(v + 24, &minus1, 8); memcpy(v + 32, &num_items, 2);
+        for (size_t i = 0; i < items.size(); ++i) {
+            memcpy(v + 34 + 6 * i, &items[i].type, 2); memcpy(v + 36 + 6 * i, &items[i].size, 2); memcpy(v + 38 + 6 * i, &items[i].version, 2);
+        }
+        *vlr_bytes = 34 + 6 * (int)items.size();
+
+        std::vector<U8> out(8, 0);                            // file position of the chunk table, patched below
+        Encoder enc;
+        std::vector<ItemWriter*> writers;
+        struct Cleanup { std::vector<ItemWriter*>& w; ~Cleanup() { for (auto p : w) delete p; } } cleanup{writers};
+        for (const Item& it : items) {
+            if (it.type == 6) writers.push_back(new Point10Writer(&enc));
+            else if (it.type == 7) writers.push_back(new GpsTime11Writer(&enc));
+            else if (it.type == 8) writers.push_back(new Rgb12Writer(&enc));
+            else writers.push_back(new ByteWriter(&enc, it.size));
+        }
+        std::vector<U32> chunk_bytes;
+        size_t chunk_begin = out.size();
+        bool open = false;
+        for (I64 i = 0; i < n_points; ++i) {
+            const U8* pt = h_points + i * point_size;
+            if (i % chunk_size == 0) {
+                if (open) { enc.done(); chunk_bytes.push_back((U32)(out.size() - chunk_begin)); chunk_begin = out.size(); }
+                out.insert(out.end(), pt, pt + point_size);            // first point of a chunk: raw
+                U32 off = 0;
+                for (size_t w = 0; w < writers.size(); ++w) { writers[w]->init(pt + off); off += items[w].size; }
+                enc.init(&out);
+                open = true;
+            } else {
+                U32 off = 0;
+                for (size_t w = 0; w < writers.size(); ++w) { writers[w]->write(pt + off); off += items[w].size; }
+            }
+        }
+        if (open) { enc.done(); chunk_bytes.push_back((U32)(out.size() - chunk_begin)); }
+        // chunk table: version, count, then the chunk sizes through the integer compressor (context 1)
+        const I64 table_pos = data_file_offset + (I64)out.size();
+        memcpy(out.data(), &table_pos, 8);
+        const U32 version = 0, number_chunks = (U32)chunk_bytes.size();
+        U8 head[8];
+        memcpy(head, &version, 4); memcpy(head + 4, &number_chunks, 4);
+        out.insert(out.end(), head, head + 8);
+        if (number_chunks) {
+            enc.init(&out);
+            IntegerEncoder ic;
+            ic.create(&enc, 32, 2);
+            ic.init();
+            for (U32 c = 0; c < number_chunks; ++c) ic.compress(c ? (I32)chunk_bytes[c - 1] : 0, (I32)chunk_bytes[c], 1);
+            enc.done();
+        }
+        *out_bytes = (int64_t)out.size();
+        if (!h_out || out_cap < (int64_t)out.size()) UPCP_FAIL(UPCP_E_WORKSPACE, "laz_encode: output buffer too small (out_bytes holds the size)");
+        memcpy(h_out, out.data(), out.size());
+    } catch (const std::bad_alloc&) {
+        UPCP_FAIL(UPCP_E_INTERNAL, "laz_encode: out of host memory");
     }
     return UPCP_OK;
 }

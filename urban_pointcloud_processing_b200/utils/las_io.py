@@ -16,6 +16,7 @@ import struct
 import numpy as np
 
 _STD_SIZE = {0: 20, 1: 28, 2: 26, 3: 34, 4: 57, 5: 63, 6: 30, 7: 36, 8: 38, 9: 59, 10: 67}
+_LASZIP_USER, _LASZIP_RECORD = b'laszip encoded', 22204
 _EXTRA_BYTES_USER = b'LASF_Spec'
 _EXTRA_BYTES_RECORD = 4
 _EB_SIZES = {1: 1, 2: 1, 3: 2, 4: 2, 5: 4, 6: 4, 7: 8, 8: 8, 9: 4, 10: 8}
@@ -111,17 +112,40 @@ class LasData:
                 return
         self.vlrs.append((_EXTRA_BYTES_USER, _EXTRA_BYTES_RECORD, b'Extra bytes', bytes(desc)))
 
-    def write(self, path):
+    def write(self, path, compress=None):
+        """Write the cloud; ``compress`` (default: by the ``.laz`` extension, as laspy does) LASzip-compresses the
+        point records through the native encoder (``upcp_laz_encode``: point formats 0-3; other formats are
+        written uncompressed)."""
         h = self.header
+        if compress is None:
+            compress = str(path).lower().endswith('.laz')
+        compress = bool(compress) and h.point_format_id <= 3
         raw = bytearray(h.raw[:h.header_size])
-        vlr_blob = b''
-        for user, rec, desc, payload in self.vlrs:
-            vlr_blob += struct.pack('<H16sHH32s', 0, user.ljust(16, b'\0'), rec, len(payload), desc.ljust(32, b'\0')) + payload
+        vlrs = [v for v in self.vlrs if not (v[0] == _LASZIP_USER and v[1] == _LASZIP_RECORD)]
+        if compress:
+            vlrs = vlrs + [(_LASZIP_USER, _LASZIP_RECORD, b'upcp-b200 laszip', bytes(34 + 6 * 4))]       # sized below
+        def blob(vs):
+            out = b''
+            for user, rec, desc, payload in vs:
+                out += struct.pack('<H16sHH32s', 0, user.ljust(16, b'\0'), rec, len(payload), desc.ljust(32, b'\0')) + payload
+            return out
+        if compress:
+            # the VLR's length depends on the number of items only: size it, then encode against the final offset
+            n_items = 1 + (h.point_format_id in (1, 3)) + (h.point_format_id in (2, 3)) + \
+                (self.records.shape[1] > _STD_SIZE[h.point_format_id])
+            vlrs[-1] = vlrs[-1][:3] + (bytes(34 + 6 * n_items),)
+            offset_to_points = h.header_size + len(blob(vlrs))
+            payload, body = _encode_laz(self.records, h.point_format_id, offset_to_points)
+            assert len(payload) == 34 + 6 * n_items
+            vlrs[-1] = vlrs[-1][:3] + (payload,)
+        vlr_blob = blob(vlrs)
         offset_to_points = h.header_size + len(vlr_blob)
         struct.pack_into('<I', raw, 96, offset_to_points)
-        struct.pack_into('<I', raw, 100, len(self.vlrs))
+        struct.pack_into('<I', raw, 100, len(vlrs))
+        raw[104] = (h.point_format_id & 0x3f) | (0x80 if compress else 0)
         struct.pack_into('<H', raw, 105, self.records.shape[1])
-        body = np.ascontiguousarray(self.records).tobytes()
+        if not compress:
+            body = np.ascontiguousarray(self.records).tobytes()
         if h.version >= (1, 4) and h.header_size >= 375:
             # LAS 1.4: the extended VLRs follow the point records, whose size changes with the `label` byte --
             # carry them through and point the header at where they now start
@@ -206,7 +230,30 @@ def read(path):
     return LasData(h, vlrs, records, extra, evlrs, n_evlrs)
 
 
-_LASZIP_USER, _LASZIP_RECORD = b'laszip encoded', 22204
+
+def _encode_laz(records, point_format_id, offset_to_points, chunk_size=50000):
+    """Uncompressed records -> (payload of the laszip VLR, point data section) through ``upcp_laz_encode``."""
+    import ctypes
+
+    from .. import _lib
+    lib = _lib.load()
+    rec = np.ascontiguousarray(records, dtype=np.uint8)
+    n, size = rec.shape
+    vlr = np.zeros(58, dtype=np.uint8)
+    vlr_bytes = ctypes.c_int32(0)
+    out_bytes = ctypes.c_int64(0)
+    cap = int(n * size * 0.6) + 4096
+    for _ in range(2):
+        out = np.empty(cap, dtype=np.uint8)
+        rc = lib.upcp_laz_encode(rec.ctypes.data_as(ctypes.c_void_p), n, size, int(point_format_id), int(chunk_size),
+                                 int(offset_to_points), vlr.ctypes.data_as(ctypes.c_void_p), ctypes.byref(vlr_bytes),
+                                 out.ctypes.data_as(ctypes.c_void_p), cap, ctypes.byref(out_bytes))
+        if rc == -3 and out_bytes.value > cap:          # UPCP_E_WORKSPACE: the size needed is in out_bytes
+            cap = int(out_bytes.value)
+            continue
+        _lib.check(rc, 'upcp_laz_encode')
+        return vlr[:vlr_bytes.value].tobytes(), out[:out_bytes.value].tobytes()
+    raise RuntimeError('upcp_laz_encode: output size changed between two calls')
 
 
 def _decode_laz(path, data, h, vlrs, n):

@@ -39,22 +39,23 @@ def read_las(las_file):
     """Read a las file and return the las object (las_utils.py:118-120)."""
     try:
         import laspy
-    except ImportError:
+        laspy_read = laspy.read                 # (a stand-in module without the reader counts as "not installed")
+    except (ImportError, AttributeError):
         # native reader: plain .las and LASzip-compressed .laz (point formats 0-3, csrc/laz.cu)
         return las_io.read(las_file)
-    return laspy.read(las_file)
+    return laspy_read(las_file)
 
 
 def label_and_save_las(las, labels, outfile):
     """Label a las file using the provided class labels and save to outfile (las_utils.py:123-130)."""
     assert len(labels) == las.header.point_count
     if isinstance(las, las_io.LasData):
-        if str(outfile).lower().endswith('.laz'):
-            # no LASzip ENCODER here: the records are written uncompressed under the requested name.  Readers
-            # (laspy, PDAL, this module) go by the header's compression bit, not by the extension.
-            logger.warning(f'{outfile}: laspy[lazrs] is not installed, point data written uncompressed')
         las.label = labels          # adds the uint8 "label" extra dimension when missing
-        las.write(outfile)
+        if str(outfile).lower().endswith('.laz') and las.header.point_format_id > 3:
+            # the native LASzip encoder covers point formats 0-3; LAS 1.4 formats are written uncompressed under
+            # the requested name (readers go by the header's compression bit, not by the extension)
+            logger.warning(f'{outfile}: point format {las.header.point_format_id} is written uncompressed')
+        las.write(outfile)          # `.laz`: LASzip-compressed through csrc/laz.cu, as laspy[lazrs] would
         return
     import laspy
     if 'label' not in las.point_format.extra_dimension_names:
