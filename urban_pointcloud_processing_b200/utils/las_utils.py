@@ -1,6 +1,6 @@
 """Tile-code helpers and LAS I/O (host side; mirrors ``upcp.utils.las_utils``, reference
-src/upcp/utils/las_utils.py:12-53,118-130).  ``laspy`` is used when it is installed (required for
-``.laz``); plain ``.las`` files are handled natively by ``las_io``."""
+src/upcp/utils/las_utils.py:12-53,118-130).  ``laspy`` is used when it is installed; without it ``las_io`` reads
+and writes ``.las`` and -- through the native LASzip decoder / encoder of csrc/laz.cu -- ``.laz`` (point formats 0-3)."""
 import logging
 import pathlib
 import re
