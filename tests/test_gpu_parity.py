@@ -186,6 +186,17 @@ def test_process_folder_pipelined_equals_per_file(tmp_path):
         c, b = las_utils.read_las(str(out_c / f'labelled_{tc}.las')), las_utils.read_las(str(out_b / f'labelled_{tc}.las'))
         assert np.array_equal(c.label, b.label) and np.array_equal(c.X, b.X)
     assert pipe.process_folder(str(tmp_path / 'missing')) is None
+    # the reference's own file type: `.laz` in, `.laz` out (native LASzip decoder / encoder, csrc/laz.cu)
+    laz_in, laz_out = tmp_path / 'laz_in', tmp_path / 'laz_out'
+    laz_in.mkdir()
+    for tc in tcs:
+        las_utils.read_las(str(in_dir / f'filtered_{tc}.las')).write(str(laz_in / f'filtered_{tc}.laz'))
+        assert open(laz_in / f'filtered_{tc}.laz', 'rb').read()[104] & 0x80
+    pipe.process_folder(str(laz_in), str(laz_out), in_prefix='filtered_', out_prefix='labelled_')
+    for tc in tcs:
+        z, b = las_utils.read_las(str(laz_out / f'labelled_{tc}.laz')), las_utils.read_las(str(out_b / f'labelled_{tc}.las'))
+        assert open(laz_out / f'labelled_{tc}.laz', 'rb').read()[104] & 0x80            # written compressed
+        assert np.array_equal(z.label, b.label) and np.array_equal(z.records, b.records)
 
 
 # ------------------------------------------------------------------------ raster ---

@@ -8,7 +8,7 @@ the labels once at the end.  Processors that are not drop-ins (no
 ``_label_mask_device``) are still accepted: the labels are synchronised to the host
 around them and their own ``get_labels`` is called, exactly as the reference does.
 LAS file I/O (``process_file`` / ``process_folder``): ``laspy`` when installed, the native
-``utils.las_io`` for plain ``.las`` otherwise; with drop-in processors only the raw integer
+``utils.las_io`` (``.las`` and, through csrc/laz.cu, ``.laz``) otherwise; with drop-in processors only the raw integer
 coordinates are uploaded and scaled on the device."""
 import logging
 import os
@@ -281,7 +281,8 @@ class Pipeline:
         logger.info(f'File processed in {duration:.2f}s, ' + f'output written to {out_file}.\n' + '=' * 20)
 
     def process_file(self, in_file, out_file=None, mask=None):
-        """Process a single LAS file and save the result (pipeline.py:99-137); ``.laz`` needs laspy."""
+        """Process a single LAS / LAZ file and save the result (pipeline.py:99-137); ``.laz`` goes through laspy when it is
+        installed, else through the native LASzip decoder / encoder (point formats 0-3)."""
         logger.info(f'Processing file {in_file}.')
         start = time.time()
         if not os.path.isfile(in_file):
