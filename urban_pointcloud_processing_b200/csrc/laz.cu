@@ -16,7 +16,10 @@
 // shipped beside them (tests/test_abi_and_host.py, tests/test_gpu_parity.py).
 #include <stdint.h>
 #include <string.h>
+#include <algorithm>
+#include <atomic>
 #include <new>
+#include <thread>
 #include <vector>
 #include "common.cuh"
 
@@ -796,29 +799,39 @@ int upcp_laz_decode(const uint8_t* h_vlr, int32_t vlr_bytes, const uint8_t* h_da
     if (vlr_bytes < 34 + 6 * (int)num_items) UPCP_FAIL(UPCP_E_INVALID, "laz_decode: truncated laszip VLR");
     if (n_points == 0) return UPCP_OK;
     try {
-        Decoder dec;
-        std::vector<ItemReader*> readers;
-        std::vector<U32> sizes;
-        struct Cleanup { std::vector<ItemReader*>& r; ~Cleanup() { for (auto p : r) delete p; } } cleanup{readers};
+        struct Spec { U16 type, size; };
+        std::vector<Spec> specs;
         U32 total = 0;
         for (int i = 0; i < (int)num_items; ++i) {
             U16 type, size, version;
             memcpy(&type, h_vlr + 34 + 6 * i, 2); memcpy(&size, h_vlr + 36 + 6 * i, 2); memcpy(&version, h_vlr + 38 + 6 * i, 2);
             if (version != 2) UPCP_FAIL(UPCP_E_CAPACITY, "laz_decode: only version-2 item codecs are supported");
-            if (type == 6 && size == 20) readers.push_back(new Point10Reader(&dec));
-            else if (type == 7 && size == 8) readers.push_back(new GpsTime11Reader(&dec));
-            else if (type == 8 && size == 6) readers.push_back(new Rgb12Reader(&dec));
-            else if (type == 0 && size >= 1) readers.push_back(new ByteReader(&dec, size));
-            else UPCP_FAIL(UPCP_E_CAPACITY, "laz_decode: unsupported item type (wave packets / LAS 1.4 layered items)");
-            sizes.push_back(size);
+            if (!((type == 6 && size == 20) || (type == 7 && size == 8) || (type == 8 && size == 6) || (type == 0 && size >= 1)))
+                UPCP_FAIL(UPCP_E_CAPACITY, "laz_decode: unsupported item type (wave packets / LAS 1.4 layered items)");
+            specs.push_back({type, size});
             total += size;
         }
         if ((I32)total != point_size) UPCP_FAIL(UPCP_E_INVALID, "laz_decode: item sizes do not add up to the point size");
+        // one decoder + item readers per worker (a chunk is an independent stream)
+        struct Worker {
+            Decoder dec;
+            std::vector<ItemReader*> readers;
+            explicit Worker(const std::vector<Spec>& sp) {
+                for (const Spec& it : sp) {
+                    if (it.type == 6) readers.push_back(new Point10Reader(&dec));
+                    else if (it.type == 7) readers.push_back(new GpsTime11Reader(&dec));
+                    else if (it.type == 8) readers.push_back(new Rgb12Reader(&dec));
+                    else readers.push_back(new ByteReader(&dec, it.size));
+                }
+            }
+            ~Worker() { for (auto p : readers) delete p; }
+        };
         // The point data starts with the file position of the chunk table (the byte size of every chunk,
         // itself arithmetic-coded).  A sequential read does not need it -- every chunk ends where the decoder
         // stopped reading, LASzip relies on the same property -- but when it is there the chunk starts are
-        // taken from it, as LASzip's integrity check does.
+        // taken from it, as LASzip's integrity check does, and the chunks are decoded in parallel.
         const I64 per_chunk = chunk_size > 0 ? (I64)chunk_size : n_points;
+        const I64 n_chunks = (n_points + per_chunk - 1) / per_chunk;
         std::vector<I64> chunk_start;                                  // offsets into h_data, empty = sequential
         {
             I64 table_pos;
@@ -828,8 +841,7 @@ int upcp_laz_decode(const uint8_t* h_vlr, int32_t vlr_bytes, const uint8_t* h_da
             if (table_pos > 0 && rel >= 8 && rel + 8 <= data_bytes) {
                 U32 version, number_chunks;
                 memcpy(&version, h_data + rel, 4); memcpy(&number_chunks, h_data + rel + 4, 4);
-                const I64 expect = (n_points + per_chunk - 1) / per_chunk;
-                if (version == 0 && (I64)number_chunks == expect) {
+                if (version == 0 && (I64)number_chunks == n_chunks) {
                     ByteStream ts{h_data + rel + 8, h_data + data_bytes, false};
                     Decoder td;
                     td.init(&ts);
@@ -844,33 +856,62 @@ int upcp_laz_decode(const uint8_t* h_vlr, int32_t vlr_bytes, const uint8_t* h_da
                         pos += (I64)(U32)prev;
                     }
                     if (ts.overrun || pos != rel) chunk_start.clear();       // inconsistent table: read sequentially
+                    else chunk_start.push_back(rel);                         // (end of the last chunk)
                 }
             }
         }
-        ByteStream in{h_data + 8, h_data + data_bytes, false};
-        for (I64 i = 0; i < n_points; ++i) {
-            U8* out = h_out + i * point_size;
-            if (i % per_chunk == 0) {
-                if (!chunk_start.empty()) in.p = h_data + chunk_start[(size_t)(i / per_chunk)];
-                // first point of a chunk: stored raw; then the coder starts afresh
-                if (in.end - in.p < point_size) UPCP_FAIL(UPCP_E_INVALID, "laz_decode: truncated chunk");
-                memcpy(out, in.p, point_size);
-                in.p += point_size;
+        // points [c * per_chunk, ...) of chunk c from `in`; false = truncated / overrun
+        auto decode_chunk = [&](Worker& w, ByteStream& in, I64 c) -> bool {
+            const I64 i0 = c * per_chunk, i1 = (i0 + per_chunk < n_points) ? i0 + per_chunk : n_points;
+            for (I64 i = i0; i < i1; ++i) {
+                U8* out = h_out + i * point_size;
                 U32 off = 0;
-                for (size_t r = 0; r < readers.size(); ++r) { readers[r]->init(out + off); off += sizes[r]; }
-                if (i + 1 < n_points && (i + 1) % per_chunk != 0) dec.init(&in);
-            } else {
-                U32 off = 0;
-                for (size_t r = 0; r < readers.size(); ++r) { readers[r]->read(out + off); off += sizes[r]; }
+                if (i == i0) {
+                    // first point of a chunk: stored raw; then the coder starts afresh
+                    if (in.end - in.p < point_size) return false;
+                    memcpy(out, in.p, point_size);
+                    in.p += point_size;
+                    for (size_t r = 0; r < w.readers.size(); ++r) { w.readers[r]->init(out + off); off += specs[r].size; }
+                    if (i + 1 < i1) w.dec.init(&in);
+                } else {
+                    for (size_t r = 0; r < w.readers.size(); ++r) { w.readers[r]->read(out + off); off += specs[r].size; }
+                }
+                if (in.overrun) return false;
             }
-            if (in.overrun) UPCP_FAIL(UPCP_E_INVALID, "laz_decode: compressed stream ended early");
+            return true;
+        };
+        bool ok = true;
+        if (chunk_start.empty()) {
+            Worker w(specs);
+            ByteStream in{h_data + 8, h_data + data_bytes, false};
+            for (I64 c = 0; c < n_chunks && ok; ++c) ok = decode_chunk(w, in, c);
+        } else {
+            unsigned hw = std::thread::hardware_concurrency();
+            const I64 n_threads = std::max<I64>(1, std::min<I64>(std::min<I64>(hw ? hw : 1, 32), n_chunks));
+            std::atomic<I64> next{0};
+            std::atomic<int> failed{0}, oom{0};
+            auto body = [&]() {
+                try {
+                    Worker w(specs);
+                    for (I64 c = next.fetch_add(1); c < n_chunks && !failed.load(); c = next.fetch_add(1)) {
+                        ByteStream in{h_data + chunk_start[(size_t)c], h_data + data_bytes, false};
+                        if (!decode_chunk(w, in, c)) failed.store(1);
+                    }
+                } catch (const std::bad_alloc&) { oom.store(1); failed.store(1); }
+            };
+            std::vector<std::thread> pool;
+            for (I64 t = 1; t < n_threads; ++t) pool.emplace_back(body);
+            body();
+            for (auto& t : pool) t.join();
+            if (oom.load()) UPCP_FAIL(UPCP_E_INTERNAL, "laz_decode: out of host memory");
+            ok = !failed.load();
         }
+        if (!ok) UPCP_FAIL(UPCP_E_INVALID, "laz_decode: compressed stream ended early");
     } catch (const std::bad_alloc&) {
         UPCP_FAIL(UPCP_E_INTERNAL, "laz_decode: out of host memory");
     }
     return UPCP_OK;
 }
-
 
 /* see include/upcp_cuda.h */
 int upcp_laz_encode(const uint8_t* h_points, int64_t n_points, int32_t point_size, int32_t point_format, int32_t chunk_size,
@@ -907,34 +948,63 @@ int upcp_laz_encode(const uint8_t* h_points, int64_t n_points, int32_t point_siz
         }
         *vlr_bytes = 34 + 6 * (int)items.size();
 
-        std::vector<U8> out(8, 0);                            // file position of the chunk table, patched below
-        Encoder enc;
-        std::vector<ItemWriter*> writers;
-        struct Cleanup { std::vector<ItemWriter*>& w; ~Cleanup() { for (auto p : w) delete p; } } cleanup{writers};
-        for (const Item& it : items) {
-            if (it.type == 6) writers.push_back(new Point10Writer(&enc));
-            else if (it.type == 7) writers.push_back(new GpsTime11Writer(&enc));
-            else if (it.type == 8) writers.push_back(new Rgb12Writer(&enc));
-            else writers.push_back(new ByteWriter(&enc, it.size));
-        }
-        std::vector<U32> chunk_bytes;
-        size_t chunk_begin = out.size();
-        bool open = false;
-        for (I64 i = 0; i < n_points; ++i) {
-            const U8* pt = h_points + i * point_size;
-            if (i % chunk_size == 0) {
-                if (open) { enc.done(); chunk_bytes.push_back((U32)(out.size() - chunk_begin)); chunk_begin = out.size(); }
-                out.insert(out.end(), pt, pt + point_size);            // first point of a chunk: raw
-                U32 off = 0;
-                for (size_t w = 0; w < writers.size(); ++w) { writers[w]->init(pt + off); off += items[w].size; }
-                enc.init(&out);
-                open = true;
-            } else {
-                U32 off = 0;
-                for (size_t w = 0; w < writers.size(); ++w) { writers[w]->write(pt + off); off += items[w].size; }
+        struct Worker {
+            Encoder enc;
+            std::vector<ItemWriter*> writers;
+            explicit Worker(const std::vector<Item>& its) {
+                for (const Item& it : its) {
+                    if (it.type == 6) writers.push_back(new Point10Writer(&enc));
+                    else if (it.type == 7) writers.push_back(new GpsTime11Writer(&enc));
+                    else if (it.type == 8) writers.push_back(new Rgb12Writer(&enc));
+                    else writers.push_back(new ByteWriter(&enc, it.size));
+                }
             }
+            ~Worker() { for (auto p : writers) delete p; }
+        };
+        // every chunk is an independent stream: first point raw, the rest through a freshly initialised coder;
+        // the chunks are encoded in parallel and laid out in order
+        const I64 n_chunks = (n_points + chunk_size - 1) / chunk_size;
+        std::vector<std::vector<U8>> parts((size_t)n_chunks);
+        auto encode_chunk = [&](Worker& w, I64 c) {
+            std::vector<U8> o;                       // (local: neighbouring entries of `parts` share cache lines)
+            const I64 i0 = c * (I64)chunk_size, i1 = (i0 + chunk_size < n_points) ? i0 + chunk_size : n_points;
+            o.reserve((size_t)((i1 - i0) * point_size / 3 + point_size + 16));
+            for (I64 i = i0; i < i1; ++i) {
+                const U8* pt = h_points + i * point_size;
+                U32 off = 0;
+                if (i == i0) {
+                    o.insert(o.end(), pt, pt + point_size);
+                    for (size_t k = 0; k < w.writers.size(); ++k) { w.writers[k]->init(pt + off); off += items[k].size; }
+                    w.enc.init(&o);
+                } else {
+                    for (size_t k = 0; k < w.writers.size(); ++k) { w.writers[k]->write(pt + off); off += items[k].size; }
+                }
+            }
+            w.enc.done();
+            parts[(size_t)c] = std::move(o);
+        };
+        {
+            unsigned hw = std::thread::hardware_concurrency();
+            const I64 n_threads = std::max<I64>(1, std::min<I64>(std::min<I64>(hw ? hw : 1, 32), n_chunks));
+            std::atomic<I64> next{0};
+            std::atomic<int> oom{0};
+            auto body = [&]() {
+                try {
+                    Worker w(items);
+                    for (I64 c = next.fetch_add(1); c < n_chunks && !oom.load(); c = next.fetch_add(1)) encode_chunk(w, c);
+                } catch (const std::bad_alloc&) { oom.store(1); }
+            };
+            std::vector<std::thread> pool;
+            for (I64 t = 1; t < n_threads; ++t) pool.emplace_back(body);
+            if (n_chunks > 0) body();
+            for (auto& t : pool) t.join();
+            if (oom.load()) UPCP_FAIL(UPCP_E_INTERNAL, "laz_encode: out of host memory");
         }
-        if (open) { enc.done(); chunk_bytes.push_back((U32)(out.size() - chunk_begin)); }
+        std::vector<U8> out(8, 0);                            // file position of the chunk table, patched below
+        std::vector<U32> chunk_bytes;
+        for (const auto& part : parts) { out.insert(out.end(), part.begin(), part.end()); chunk_bytes.push_back((U32)part.size()); }
+        parts.clear();
+        Encoder enc;
         // chunk table: version, count, then the chunk sizes through the integer compressor (context 1)
         const I64 table_pos = data_file_offset + (I64)out.size();
         memcpy(out.data(), &table_pos, 8);
