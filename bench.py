@@ -477,7 +477,7 @@ def main():
     labelled = int(all_hist[-world:, 1:].sum().item())
 
     # ---- e2e arms: host buffers (pinned), H2D + D2H inside the timed region
-    e2e = e2e_batch = e2e_las = None
+    e2e = e2e_batch = e2e_las = e2e_laz = None
     if not args.no_e2e:
         Th = min(T, 4)                                    # distinct host tiles (0.5 GB of pinned memory each)
         host = [B.host_points(j) for j in range(Th)]
@@ -561,6 +561,33 @@ def main():
                    'api': 'DeviceTile.from_las (int32 X, Y, Z + scale / offset, as Pipeline.process_file uploads them) + '
                           'process_tile_device + label download; no initial car seeds (labels start at 0)'}
 
+        # supplementary: the reference's own file route, Pipeline.process_file from a `.laz` on disk to a labelled
+        # `.laz` on disk (native LASzip decoder / encoder on the host threads; rank 0 only, two files)
+        e2e_laz = None
+        if rank == 0:
+            import shutil
+            import tempfile
+            td = tempfile.mkdtemp(prefix='upcp_bench_')
+            try:
+                src = os.path.join(td, f'filtered_{B.codes[0]}.laz')
+                las0 = las_io.create(ints, scales, offsets, point_format_id=1)
+                las0.write(src)
+                del las0
+                t0_ = time.perf_counter()
+                reps_ = 2
+                for r_ in range(reps_):
+                    pipeline.process_file(src, os.path.join(td, f'labelled_{r_}_{B.codes[0]}.laz'))
+                torch.cuda.synchronize()
+                laz_s = (time.perf_counter() - t0_) / reps_
+                e2e_laz = {'value': n / laz_s / 1e6, 'unit': 'Mpts/s', 'ms_per_step': laz_s * 1e3, 'files': reps_,
+                           'laz_bytes_in': os.path.getsize(src),
+                           'laz_bytes_out': os.path.getsize(os.path.join(td, f'labelled_0_{B.codes[0]}.laz')),
+                           'api': 'Pipeline.process_file(in.laz, out.laz): LASzip decode (host threads) -> int32 upload -> '
+                                  'label pipeline -> label download -> LASzip encode; one file after the other '
+                                  '(process_folder overlaps the codec of neighbouring files with the labelling)'}
+            finally:
+                shutil.rmtree(td, ignore_errors=True)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -628,7 +655,7 @@ def main():
                        'l2_policy': 'inputs (480 MB of coordinates per tile, a different tile every step) are larger than the 126 MB L2',
                        'tiles_per_s': value * 1e6 / n, 'tiles_in_flight_per_gpu': tiles_in_flight},
             'single_stream': single, 'concurrent': conc,
-            'clocks': clocks, 'e2e': e2e_batch or e2e, 'e2e_process_cloud': e2e, 'e2e_las': e2e_las,
+            'clocks': clocks, 'e2e': e2e_batch or e2e, 'e2e_process_cloud': e2e, 'e2e_las': e2e_las, 'e2e_laz_file': e2e_laz,
             'gpu_launches': int(launches), 'roofline': roofline,
             'cpu_baseline': cpu_baseline, 'stage_ms': stage_s, 'points_labelled_last_step': labelled,
             'wall_ms_per_step': wall_dev / K}
