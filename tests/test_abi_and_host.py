@@ -325,6 +325,17 @@ def test_native_laz_decoder_on_the_reference_demo_cloud(tmp_path):
     bad.write_bytes(raw[:len(raw) // 2])
     with pytest.raises(_lib.UpcpCudaError):
         las_io.read(str(bad))
+    # variable-size chunks (chunk size 0xFFFFFFFF in the laszip VLR) are refused, not mis-read as one chunk
+    var = bytearray(raw)
+    pos = struct.unpack_from('<H', raw, 94)[0]
+    for _ in range(struct.unpack_from('<I', raw, 100)[0]):
+        _, _, rec, length, _ = struct.unpack_from('<H16sHH32s', raw, pos)
+        if rec == 22204:
+            struct.pack_into('<i', var, pos + 54 + 12, -1)
+        pos += 54 + length
+    (tmp_path / 'var_2386_9702.laz').write_bytes(bytes(var))
+    with pytest.raises(_lib.UpcpCudaError, match='variable-size'):
+        las_io.read(str(tmp_path / 'var_2386_9702.laz'))
     # written back as a plain .las (laszip VLR dropped, compression bit cleared) and read again
     out = str(tmp_path / 'plain_2386_9702.las')
     las.write(out)

@@ -797,6 +797,7 @@ int upcp_laz_decode(const uint8_t* h_vlr, int32_t vlr_bytes, const uint8_t* h_da
     if (coder != 0) UPCP_FAIL(UPCP_E_CAPACITY, "laz_decode: unknown entropy coder");
     if (compressor != 2) UPCP_FAIL(UPCP_E_CAPACITY, "laz_decode: only the pointwise chunked compressor (LAS 1.0 - 1.3 point formats 0 - 3) is supported");
     if (vlr_bytes < 34 + 6 * (int)num_items) UPCP_FAIL(UPCP_E_INVALID, "laz_decode: truncated laszip VLR");
+    if (chunk_size < 0) UPCP_FAIL(UPCP_E_CAPACITY, "laz_decode: variable-size chunks (chunk size 0xFFFFFFFF) are not supported");
     if (n_points == 0) return UPCP_OK;
     try {
         struct Spec { U16 type, size; };
