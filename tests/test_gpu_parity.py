@@ -1100,3 +1100,40 @@ def test_device_generated_tiles_config5():
         n_diff = int(np.count_nonzero(got != want.astype(np.int32)))
         print(f'device tile {i}: {n} points, kinds {np.round(frac, 3).tolist()}, {n_diff} labels differ from the oracle')
         assert n_diff == 0
+
+
+@pytest.mark.gpu
+def test_notebook0_processor_sequence_with_its_defaults():
+    """The in-scope part of the reference's "0. Complete solution" notebook, composed as there and with its arguments:
+    AHNFuser(refine_ground=True) -> BGTRoadFuser -> NoiseFilter -> BGTBuildingFuser(offset=0.25) -> CarFuser ->
+    LayerLCC(building top / bottom) through Pipeline.process_cloud, against the oracle's composition of the same steps
+    (buffers as distances; the cluster size limits are scaled to the test cloud's density)."""
+    from urban_pointcloud_processing_b200.fusion import CarFuser, NoiseFilter
+    tile = synthetic.make_tile(500_000, seed=2024, n_cars=12)
+    pts, tc, a = tile['points'], tile['tilecode'], tile['ahn_tile']
+    ahn, bld, road = readers_for(tile)
+    car_params = {'min_height': 1.2, 'max_height': 2.4, 'min_width': 1.4, 'max_width': 2.4, 'min_length': 3.0, 'max_length': 6.0}
+    layers = [{'bottom': 12., 'grid_size': 0.1, 'threshold': 0.5}, {'bottom': 0., 'top': 12., 'grid_size': 0.05, 'threshold': 0.5}]
+    procs = (AHNFuser(Labels.GROUND, ahn, target='ground', epsilon=0.2, refine_ground=True),
+             BGTRoadFuser(Labels.ROAD, bgt_reader=road),
+             NoiseFilter(Labels.NOISE, ahn_reader=ahn, epsilon=0.2, min_component_size=20),
+             BGTBuildingFuser(Labels.BUILDING, bgt_reader=bld, offset=0.25, ahn_reader=ahn),
+             CarFuser(Labels.CAR, ahn, bgt_reader=road, exclude_types=['fietspad'], grid_size=0.05, min_component_size=150,
+                      params=car_params),
+             LayerLCC(Labels.BUILDING, ahn, params=[dict(p) for p in layers]))
+    labels = np.zeros(len(pts), dtype=np.uint16)
+    got = Pipeline(processors=procs, ahn_reader=ahn, caching=True).process_cloud(tc, pts, labels.copy())
+    roads = road.filter_tile(tc, exclude_types=['fietspad'], merge=False)
+    want = R.process_cloud([
+        lambda p, l, m: R.ahn_fuser_labels(p, l, m, a, Labels.GROUND, 'ground', 0.2, refine_ground=True, params={}),
+        lambda p, l, m: R.road_fuser_labels(p, l, tile['road_polygons'], Labels.ROAD),
+        lambda p, l, m: R.noise_filter_labels(p, l, m, a, Labels.NOISE, epsilon=0.2, grid_size=0.1, min_component_size=20),
+        lambda p, l, m: R.building_fuser_labels(p, l, m, [q.buffer(0.25) for q in tile['building_polygons']], Labels.BUILDING, a, 0.2),
+        lambda p, l, m: R.car_fuser_labels(p, l, m, a, roads, Labels.CAR, grid_size=0.05, min_component_size=150,
+                                           overlap_perc=20, params=car_params),
+        lambda p, l, m: R.layer_lcc_labels(p, l, m, a, Labels.BUILDING, [dict(q) for q in layers]),
+    ], pts, labels.copy())
+    hist = dict(zip(*[v.tolist() for v in np.unique(got, return_counts=True)]))
+    print(f'notebook-0 sequence: {len(pts)} points, labels {hist}, {int((got != want).sum())} differ from the oracle')
+    assert np.array_equal(got, want)
+    assert all(hist.get(int(k), 0) > 0 for k in (Labels.GROUND, Labels.ROAD, Labels.BUILDING, Labels.NOISE))
