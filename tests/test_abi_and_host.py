@@ -501,6 +501,19 @@ def test_per_thread_diagnostics():
     [t.join() for t in ts]
     assert seen == {1: ([1], 1), 2: ([2], 2)}
     assert p.last == ['main'] and q.last == [] and p.level is None
+    # objects that carry such diagnostics still pickle / deep-copy (the per-thread store is dropped)
+    import copy
+    import pickle
+    from urban_pointcloud_processing_b200.fusion import CarFuser
+    from urban_pointcloud_processing_b200.pipeline import Pipeline
+    car = CarFuser(40, ahn_reader=None, bgt_reader=None, params={'min_height': 1.0})
+    car.last_objects = [('ring', 0.0, 1.0)]
+    pipe = Pipeline(processors=(car,), caching=False)
+    pipe.last_timings = [('CarFuser', 0.1)]
+    for clone in (pickle.loads(pickle.dumps(pipe)), copy.deepcopy(pipe)):
+        assert clone.last_timings == [] and clone.processors[0].last_objects == []
+        assert clone.processors[0].params == {'min_height': 1.0} and clone.processors[0].label == 40
+    assert pipe.last_timings == [('CarFuser', 0.1)] and car.last_objects == [('ring', 0.0, 1.0)]
 
 
 def test_rings_fast_path_equals_generic_path():

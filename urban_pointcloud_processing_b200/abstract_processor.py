@@ -51,6 +51,14 @@ class PerThread:
         setattr(self._store(obj), self.name, value)
 
 
+def drop_per_thread_state(obj):
+    """``__getstate__`` helper: the per-thread store is a ``threading.local`` and does not pickle; a copy of the
+    object (``copy.deepcopy``, ``pickle`` for a process pool) starts with empty diagnostics."""
+    state = obj.__dict__.copy()
+    state.pop('_per_thread', None)
+    return state
+
+
 class AbstractProcessor(ABC):
     """Abstract base class for automatic labelling of point clouds.
 
@@ -63,6 +71,9 @@ class AbstractProcessor(ABC):
     def __init__(self, label):
         self.label = label
         super().__init__()
+
+    def __getstate__(self):
+        return drop_per_thread_state(self)
 
     # ---- device-resident core, implemented by every drop-in -----------------
     @abstractmethod

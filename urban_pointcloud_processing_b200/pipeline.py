@@ -18,7 +18,7 @@ import time
 import numpy as np
 
 from . import device as dev
-from .abstract_processor import PerThread
+from .abstract_processor import PerThread, drop_per_thread_state
 from .analysis import analysis_tools
 from .utils import las_utils
 
@@ -55,6 +55,9 @@ class Pipeline:
         if self.caching:
             self.ahn_reader.set_caching(self.caching)
         self.last_timings = []
+
+    def __getstate__(self):
+        return drop_per_thread_state(self)
 
     def _create_mask(self, mask, labels):
         """Create mask based on `exclude_labels` (dead in the reference too: the mask is
